@@ -1,0 +1,144 @@
+/*
+ * dmc_b200.h -- C ABI of the B200-native DMC P-frame / DMCI forward engine.
+ *
+ * This is the drop-in boundary for the one hot path this repository owns: the
+ * `forward()` of the reference's codec modules.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference root):
+ *
+ *   dmc_forward   <-> DMC.forward(x, qp, dpb, after_i)
+ *                       old          src/models/video_model.py:338-388
+ *                       performance  src/refactor/seg_video_model.py:301-365
+ *                       fast         src/refactor/seg_video_model_fast.py:328-411
+ *                       mask_prop    src/refactor/mask_prop_seg_video_model.py:331-417
+ *   dmci_forward  <-> DMCI.forward(x, qp)           src/models/image_model.py:205-261
+ *   dmc_set_weight / dmc_finalize_weights
+ *                 <-> nn.Module.load_state_dict() of those classes; keys and
+ *                     shapes are exactly the reference state_dict layout
+ *                     (trainer_seg_video_model.py:744-846 loads them)
+ *   dmc_frame_stats
+ *                 <-> caller-side metrics: rate_distortion_loss / _roi_mse /
+ *                     _psnr_from_mse   trainer_seg_video_model.py:598-601,655-660,904-934
+ *
+ * Conventions
+ *   - plain C, no exceptions: every int-returning function returns 0 on success
+ *     or a negative DMC_E_* code; dmc_last_error() gives the message.
+ *   - every tensor pointer is a DEVICE pointer to contiguous fp32 in the
+ *     reference's own layout (NCHW); the caller (torch) owns all of them.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Work is enqueued asynchronously; nothing here synchronises the host.
+ *   - one engine handle per (variant, batch, height, width); a handle is
+ *     thread-compatible (use it from one thread / one stream at a time).
+ *   - height and width must be multiples of 64 (the reference's `performance`
+ *     variant never pads: seg_video_model.py:331).
+ */
+#ifndef DMC_B200_H_
+#define DMC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct dmc_engine dmc_engine;
+
+/* trainer_seg_video_model.py:478-495 (`dmc_variant`) + the intra model */
+enum {
+  DMC_VARIANT_OLD = 0,
+  DMC_VARIANT_PERFORMANCE = 1,
+  DMC_VARIANT_FAST = 2,
+  DMC_VARIANT_MASK_PROP = 3,
+  DMC_VARIANT_INTRA = 4
+};
+
+enum {
+  DMC_OK = 0,
+  DMC_E_INVALID = -1,   /* bad argument / unknown key / shape mismatch      */
+  DMC_E_CUDA = -2,      /* a CUDA runtime or driver call failed             */
+  DMC_E_STATE = -3,     /* weights missing or not finalised                 */
+  DMC_E_UNSUPPORTED = -4
+};
+
+/* dmc_create flags */
+enum {
+  DMC_FLAG_SIMT_GEMM = 1,   /* run every contraction on the fp32 CUDA-core kernel
+                               (validation backend) instead of tcgen05          */
+  DMC_FLAG_KEEP_TAPS = 2,   /* keep intermediate tensors readable via dmc_get_tap */
+  DMC_FLAG_RECON_BF16X1 = 4 /* recon_generation_net contractions with 1 bf16 term */
+};
+
+int dmc_create(int variant, int batch, int height, int width, int flags, dmc_engine** out);
+void dmc_destroy(dmc_engine* e);
+/* message of the last failure on this handle (or of the last failed dmc_create if e==NULL) */
+const char* dmc_last_error(const dmc_engine* e);
+
+/* The state_dict keys this engine consumes (a subset of the reference's: unused
+ * tensors such as hyper_in_adapter.* are not listed). */
+int dmc_num_weights(const dmc_engine* e);
+const char* dmc_weight_key(const dmc_engine* e, int index);
+/* shape4 receives up to 4 dims; returns ndim or a negative error */
+int dmc_weight_shape(const dmc_engine* e, int index, int64_t* shape4);
+
+/* Hand one state_dict tensor (fp32, device, contiguous) to the engine.  Unknown keys
+ * return DMC_E_INVALID; the data is repacked on `stream` into the engine's own
+ * split-bf16 tiles, the caller's buffer is not retained. */
+int dmc_set_weight(dmc_engine* e, const char* key, const float* dev_ptr,
+                   const int64_t* shape, int ndim, void* stream);
+int dmc_finalize_weights(dmc_engine* e, void* stream);
+
+/* One P-frame.  x: (B,3,H,W).  mask: (B,1,H,W) or NULL (3-channel call).
+ * dpb_frame: (B,3,H,W), read iff after_i != 0.  dpb_feature: (B,256,H/8,W/8), read iff
+ * after_i == 0.  Outputs: x_hat (B,3,H,W) in [0,1]; feature (B,256,H/8,W/8);
+ * bpp3 = B x {bpp, bpp_y, bpp_z}; mask_pred (B,1,H,W) or NULL -- written only by
+ * mask_prop with after_i == 0 (the predictor's logits); finite_flag (int32, device)
+ * or NULL: set to 1 if any latent/feature was non-finite (the reference's
+ * _finite_check, seg_video_model_fast.py:152-156, without its host syncs). */
+int dmc_forward(dmc_engine* e, const float* x, const float* mask, const float* dpb_frame,
+                const float* dpb_feature, int qp, int after_i, float* x_hat, float* feature,
+                float* bpp3, float* mask_pred, int32_t* finite_flag, void* stream);
+
+/* One I-frame through DMCI (engine created with DMC_VARIANT_INTRA). */
+int dmci_forward(dmc_engine* e, const float* x, int qp, float* x_hat, float* bpp3, void* stream);
+
+/* Intermediate tensors of the last forward, converted to NCHW fp32 (needs
+ * DMC_FLAG_KEEP_TAPS).  shape4 receives (B,C,H,W); dst may be NULL to query the shape. */
+int dmc_get_tap(dmc_engine* e, const char* name, float* dst, int64_t capacity_elems,
+                int64_t* shape4, void* stream);
+
+/* Fused caller-side statistics.  Adds to stats7 (7 doubles, device):
+ *   [0] sum bits_y  [1] sum bits_z  [2] sum (x_hat-x)^2  [3] sum m*(x_hat-x)^2
+ *   [4] sum m (x3 channels)  [5] number of elements B*3*H*W  [6] number of frames (B)
+ * m = (mask > 0).  mask may be NULL (ROI terms untouched). bpp3 as produced by dmc_forward. */
+int dmc_frame_stats(double* stats7, const float* x_hat, const float* x, const float* mask,
+                    const float* bpp3, int batch, int height, int width, void* stream);
+
+/* ---- single-operator entry points (the same kernels the engine launches), used by the
+ * per-layer parity tests.  All tensors NCHW fp32 on the device. ---- */
+
+/* act: 0 none, 1 WSiLU (layers.py:8-10), 2 ReLU.  backend: 0 tcgen05 split-bf16, 1 SIMT fp32.
+ * nsplit: 3 (fp32-grade, 6 MMA terms) or 1 (plain bf16).  groups must be 1 or cin (depthwise 3x3). */
+int dmc_op_conv2d(const float* x, const float* weight, const float* bias, float* out, int batch,
+                  int cin, int height, int width, int cout, int ksize, int stride, int padding,
+                  int groups, int act, int nsplit, int backend, void* stream);
+/* DepthConvBlock (layers.py:43-79); weights in the order adaptor(w,b or NULL,NULL), dc.0, dc.2,
+ * dc.3, ffn.0, ffn.2; quant_step: (cout) or NULL. */
+int dmc_op_depth_conv_block(const float* x, const float* const* weights12, const float* quant_step,
+                            float* out, int batch, int cin, int cout, int height, int width,
+                            int shortcut, int nsplit, int backend, void* stream);
+/* formula 0: models/common_model.py:36-42, 1: refactor/common_model.py:37-68 */
+int dmc_op_gaussian_bits(const float* sym, const float* sigma, float* bits, int64_t n, int formula,
+                         void* stream);
+
+int dmc_num_sms(void);
+const char* dmc_version(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMC_B200_H_ */

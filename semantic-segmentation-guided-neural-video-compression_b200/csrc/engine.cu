@@ -1,0 +1,1124 @@
+// Host side of the DMC engine: builds, per (variant, B, H, W), the static launch program of one
+// frame -- buffers, packed weights, TMA descriptors and the ordered list of kernel launches --
+// and exposes it through the C ABI of include/dmc_b200.h.
+//
+// The program follows the reference dataflow:
+//   old          src/models/video_model.py:338-388
+//   performance  src/refactor/seg_video_model.py:301-365
+//   fast         src/refactor/seg_video_model_fast.py:328-411
+//   mask_prop    src/refactor/mask_prop_seg_video_model.py:331-417
+//   intra        src/models/image_model.py:205-261
+// Channel concatenations never exist as copies: producers write straight into column slices
+// of a wider S3 buffer (a View), which the consumer reads as one operand.
+#include <cuda.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dmc_b200.h"
+#include "kernels.h"
+
+using namespace dmc;
+
+namespace {
+
+std::string g_create_error;
+
+[[noreturn]] void fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw std::runtime_error(buf);
+}
+#define CUDA_OK(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t err__ = (call);                                                             \
+    if (err__ != cudaSuccess) fail("%s failed: %s", #call, cudaGetErrorString(err__));      \
+  } while (0)
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct Act {          // an S3 tensor with its geometry (rows = B*H*W)
+  View v{nullptr, 0, 0, 0};
+  int B = 0, H = 0, W = 0;
+  long long M() const { return (long long)B * H * W; }
+};
+
+struct Conv {         // dense convolution lowered to a contraction
+  GemmW g;
+  int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
+  CUtensorMap tmap;
+};
+struct DW {
+  float* w9c = nullptr;
+  float* bias = nullptr;
+  int C = 0;
+};
+struct DCB {          // layers.py:43-79
+  Conv* adaptor = nullptr;
+  Conv *dc0 = nullptr, *dc3 = nullptr, *ffn0 = nullptr, *ffn2 = nullptr;
+  DW* dw = nullptr;
+  int cin = 0, cout = 0;
+};
+
+struct WSlot {
+  std::string key;
+  std::vector<int64_t> shape;
+  std::function<void(const float*, cudaStream_t)> load;
+  bool set = false;
+};
+
+struct EpiSpec {
+  int act = ACT_NONE;
+  const Act* res1 = nullptr;
+  const Act* res2 = nullptr;
+  const float* scale_table = nullptr;   // (72, C) table, row chosen by qp at launch
+  int scale_C = 0;
+  float* out_f32 = nullptr;
+  int ld_f32 = 0;
+  bool clamp01 = false;
+  int nsplit = 3;
+};
+
+}  // namespace
+
+struct dmc_engine {
+  int variant = 0, B = 0, H = 0, W = 0, flags = 0;
+  std::string error;
+  bool finalized = false;
+
+  // per-call state read by the launch closures
+  struct Cur {
+    const float *x = nullptr, *mask = nullptr, *dpb_frame = nullptr, *dpb_feature = nullptr;
+    float *x_hat = nullptr, *feature = nullptr, *bpp3 = nullptr, *mask_pred = nullptr;
+    int32_t* finite = nullptr;
+    int qp = 0;
+  } cur;
+  bool cur_after_i = true;
+
+  std::vector<void*> allocs;
+  std::vector<std::unique_ptr<Conv>> convs;
+  std::vector<std::unique_ptr<DW>> dws;
+  std::vector<std::unique_ptr<DCB>> dcbs;
+  std::vector<std::unique_ptr<Act>> acts;
+  std::vector<std::unique_ptr<CUtensorMap>> tmaps;
+  std::vector<WSlot> slots;
+  std::map<std::string, int> slot_index;
+  std::map<std::string, Act> scratch;
+  std::map<std::string, Act> taps;               // S3 taps
+  struct F32Tap { const float* p; int B, C, H, W; };
+  std::map<std::string, F32Tap> ftaps;           // fp32 row-major [M, C] taps
+
+  typedef std::function<void(cudaStream_t)> Op;
+  std::vector<Op> prog_head_i, prog_head_p, prog_common;
+  std::vector<Op>* prog = nullptr;               // where the builder appends
+
+  double* bits_y = nullptr;
+  double* bits_z = nullptr;
+  float* bpp_scratch = nullptr;
+
+  ~dmc_engine() {
+    for (void* p : allocs) cudaFree(p);
+  }
+
+  bool simt() const { return flags & DMC_FLAG_SIMT_GEMM; }
+  bool keep_taps() const { return flags & DMC_FLAG_KEEP_TAPS; }
+
+  // ------------------------------------------------------------ memory
+  void* dalloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    CUDA_OK(cudaMalloc(&p, bytes));
+    allocs.push_back(p);
+    return p;
+  }
+  Act new_act(int b, int h, int w, int C) {
+    Act a;
+    a.B = b; a.H = h; a.W = w;
+    long long M = a.M();
+    int ld = round_up(C, 8);
+    long long ps = (M * ld + 7) / 8 * 8;
+    a.v.p = (bf16*)dalloc((size_t)ps * 3 * sizeof(bf16));
+    a.v.ps = ps; a.v.ld = ld; a.v.C = C;
+    if (ld != C) CUDA_OK(cudaMemset(a.v.p, 0, (size_t)ps * 3 * sizeof(bf16)));
+    return a;
+  }
+  // scratch buffers are shared by every block of the same geometry (one stream, in-order)
+  Act get_scratch(const std::string& tag, int b, int h, int w, int C) {
+    char key[160];
+    snprintf(key, sizeof key, "%s:%d:%d:%d:%d", tag.c_str(), b, h, w, C);
+    auto it = scratch.find(key);
+    if (it != scratch.end()) return it->second;
+    Act a = new_act(b, h, w, C);
+    scratch[key] = a;
+    return a;
+  }
+  static Act slice(const Act& a, int c0, int C) {
+    Act s = a;
+    s.v.p = a.v.p + c0;
+    s.v.C = C;
+    return s;
+  }
+  float* new_f32(size_t n) { return (float*)dalloc(n * sizeof(float)); }
+
+  // ------------------------------------------------------------ weights
+  void add_slot(const std::string& key, std::vector<int64_t> shape,
+                std::function<void(const float*, cudaStream_t)> load) {
+    slot_index[key] = (int)slots.size();
+    slots.push_back(WSlot{key, std::move(shape), std::move(load), false});
+  }
+  // raw fp32 copy of a tensor (per-QP tables, tiny convs)
+  float* add_table(const std::string& key, std::vector<int64_t> shape) {
+    size_t n = 1;
+    for (auto s : shape) n *= (size_t)s;
+    float* d = new_f32(n);
+    add_slot(key, shape, [d, n](const float* src, cudaStream_t st) {
+      CUDA_OK(cudaMemcpyAsync(d, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    });
+    return d;
+  }
+  Conv* add_conv(const std::string& key, int cin, int cout, int k, int stride, int pad,
+                 int pack = PACK_PLAIN) {
+    convs.emplace_back(new Conv());
+    Conv* c = convs.back().get();
+    c->cin = cin; c->cout = cout; c->k = k; c->stride = stride; c->pad = pad;
+    GemmW& g = c->g;
+    g.N = cout; g.K = cin * k * k; g.pack = pack;
+    if (pack == PACK_PAIR) {
+      int c2 = cout / 2;
+      g.ncols = (c2 + 31) / 32 * 64;
+      g.BN = (g.ncols % 128 == 0) ? 128 : 64;
+    } else if (pack == PACK_SHUF2) {
+      g.Cg = cout / 4;
+      g.Cg_pad = round_up(g.Cg, 32);
+      g.ncols = 4 * g.Cg_pad;
+      g.BN = (g.ncols % 128 == 0) ? 128 : ((g.ncols % 96 == 0) ? 96 : 64);
+    } else {
+      g.ncols = cout;
+      if (cout % 128 == 0) g.BN = 128;
+      else if (cout % 160 == 0) g.BN = 160;
+      else if (cout % 96 == 0) g.BN = 96;
+      else if (cout % 64 == 0) g.BN = 64;
+      else g.BN = (cout > 96) ? 128 : (cout > 64 ? 96 : 64);
+    }
+    g.Npad = round_up(round_up(g.ncols, g.BN), 64);
+    g.Kld = round_up(g.K, 64);
+    g.w = (bf16*)dalloc((size_t)3 * g.Npad * g.Kld * sizeof(bf16));
+    g.bias = new_f32(g.Npad);
+    g.tmap = &c->tmap;
+    if (!simt()) {
+      if (make_tmap_weight(&c->tmap, g) != 0) fail("%s: %s", key.c_str(), umma_last_error());
+    }
+    add_slot(key + ".weight", {cout, cin, k, k}, [c](const float* src, cudaStream_t st) {
+      pack_gemm_weight(src, c->cout, c->cin, c->k, c->k, c->g, st);
+    });
+    add_slot(key + ".bias", {cout}, [c](const float* src, cudaStream_t st) {
+      pack_gemm_bias(src, c->cout, c->g, st);
+    });
+    return c;
+  }
+  DW* add_dw(const std::string& key, int C) {
+    dws.emplace_back(new DW());
+    DW* d = dws.back().get();
+    d->C = C;
+    d->w9c = new_f32((size_t)9 * C);
+    d->bias = new_f32(C);
+    add_slot(key + ".weight", {C, 1, 3, 3},
+             [d](const float* src, cudaStream_t st) { pack_dw_weight(src, d->w9c, d->C, st); });
+    add_slot(key + ".bias", {C}, [d](const float* src, cudaStream_t st) {
+      CUDA_OK(cudaMemcpyAsync(d->bias, src, d->C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    });
+    return d;
+  }
+  DCB* add_dcb(const std::string& key, int cin, int cout, bool force_adaptor = false) {
+    dcbs.emplace_back(new DCB());
+    DCB* b = dcbs.back().get();
+    b->cin = cin; b->cout = cout;
+    if (cin != cout || force_adaptor) b->adaptor = add_conv(key + ".adaptor", cin, cout, 1, 1, 0);
+    b->dc0 = add_conv(key + ".dc.0", cout, cout, 1, 1, 0);
+    b->dw = add_dw(key + ".dc.2", cout);
+    b->dc3 = add_conv(key + ".dc.3", cout, cout, 1, 1, 0);
+    b->ffn0 = add_conv(key + ".ffn.0", cout, cout * 4, 1, 1, 0, PACK_PAIR);
+    b->ffn2 = add_conv(key + ".ffn.2", cout * 2, cout, 1, 1, 0);
+    return b;
+  }
+
+  // ------------------------------------------------------------ op builders
+  void op(Op f) { prog->push_back(std::move(f)); }
+
+  void tap(const std::string& name, const Act& a) {
+    if (!keep_taps()) return;
+    Act copy = new_act(a.B, a.H, a.W, a.v.C);
+    Act src = a;
+    long long M = a.M();
+    op([src, copy, M](cudaStream_t st) { copy_view(src.v, copy.v, M, st); });
+    taps[name] = copy;
+  }
+
+  // contraction of `in` (rows x K) with conv weight `c` into `out` (S3) or spec.out_f32
+  void gemm(const Act& in, Conv* c, const Act* out, EpiSpec spec, int shuf_H = 0, int shuf_W = 0) {
+    const GemmW* g = &c->g;
+    if (in.v.C != g->K) fail("gemm: operand has %d columns, weight expects K=%d", in.v.C, g->K);
+    Epi e;
+    memset(&e, 0, sizeof e);
+    e.bias = g->bias;
+    e.act = spec.act;
+    e.pack = g->pack;
+    if (spec.res1) e.res1 = spec.res1->v;
+    if (spec.res2) e.res2 = spec.res2->v;
+    if (out) e.out = out->v;
+    e.out_f32 = spec.out_f32;
+    e.ld_f32 = spec.ld_f32;
+    e.n_out = (g->pack == PACK_PAIR) ? g->N / 2 : (g->pack == PACK_SHUF2 ? g->Cg : g->N);
+    e.H = shuf_H; e.W = shuf_W; e.Cg = g->Cg; e.Cg_pad = g->Cg_pad;
+    if (spec.clamp01) { e.do_clamp = 1; e.clamp_lo = 0.f; e.clamp_hi = 1.f; }
+    if (out && out->v.C < e.n_out) fail("gemm: destination has %d columns, need %d", out->v.C, e.n_out);
+    long long M = in.M();
+    View a = in.v;
+    bool aligned = ((uintptr_t)a.p % 16 == 0) && (a.ld % 8 == 0) && (a.ps % 8 == 0);
+    bool out_ok = !out || (((uintptr_t)out->v.p % 16 == 0) && (out->v.ld % 8 == 0));
+    bool use_umma = !simt() && aligned && out_ok && (g->K % 8 == 0) && (e.n_out % 8 == 0) &&
+                    (!spec.out_f32 || (spec.ld_f32 % 4 == 0));
+    const float* table = spec.scale_table;
+    int sc = spec.scale_C;
+    int nsplit = spec.nsplit;
+    dmc_engine* self = this;
+    if (use_umma) {
+      tmaps.emplace_back(new CUtensorMap());
+      CUtensorMap* tm = tmaps.back().get();
+      if (make_tmap_act(tm, a, M) != 0) fail("gemm A map: %s", umma_last_error());
+      int K = g->K;
+      op([self, tm, g, e, M, K, nsplit, table, sc](cudaStream_t st) {
+        Epi ee = e;
+        if (table) ee.scale = table + (size_t)self->cur.qp * sc;
+        if (gemm_umma(tm, *g, ee, M, K, nsplit, st) != 0) fail("gemm_umma: %s", umma_last_error());
+      });
+    } else {
+      op([self, a, g, e, M, table, sc](cudaStream_t st) {
+        Epi ee = e;
+        if (table) ee.scale = table + (size_t)self->cur.qp * sc;
+        gemm_simt(a, *g, ee, M, st);
+      });
+    }
+  }
+
+  // k x k convolution with stride/pad: im2col into a scratch S3 matrix, then the contraction
+  void conv_kxk(const Act& in, Conv* c, const Act* out, EpiSpec spec, bool shuf2 = false) {
+    int Ho = (in.H + 2 * c->pad - c->k) / c->stride + 1;
+    int Wo = (in.W + 2 * c->pad - c->k) / c->stride + 1;
+    Act col = get_scratch("im2col", in.B, Ho, Wo, c->k * c->k * c->cin);
+    Act src = in;
+    int k = c->k, s = c->stride, p = c->pad, cin = c->cin;
+    op([src, col, k, s, p, Ho, Wo, cin](cudaStream_t st) {
+      im2col(src.v, col.v, src.B, src.H, src.W, k, s, p, Ho, Wo, cin, 0, st);
+    });
+    gemm(col, c, out, spec, shuf2 ? Ho : 0, shuf2 ? Wo : 0);
+  }
+
+  // DepthConvBlock; `out` may alias `x` (every element is read before it is written by the same thread)
+  void dcb(DCB* w, const Act& x, const Act& out, bool shortcut, const float* scale_table, int nsplit,
+           float* out_f32 = nullptr, int ld_f32 = 0) {
+    int C = w->cout;
+    Act xin = x;
+    EpiSpec s0;
+    s0.nsplit = nsplit;
+    if (w->adaptor) {
+      xin = get_scratch("dcb_x", x.B, x.H, x.W, C);
+      gemm(x, w->adaptor, &xin, s0);
+    }
+    Act t = get_scratch("dcb_t", x.B, x.H, x.W, C);
+    Act t2 = get_scratch("dcb_t2", x.B, x.H, x.W, C);
+    Act o1 = get_scratch("dcb_o1", x.B, x.H, x.W, C);
+    Act u = get_scratch("dcb_u", x.B, x.H, x.W, 2 * C);
+    EpiSpec s1 = s0;
+    s1.act = ACT_WSILU;
+    gemm(xin, w->dc0, &t, s1);
+    DW* dw = w->dw;
+    op([t, t2, dw](cudaStream_t st) { dwconv3x3(t.v, dw->w9c, dw->bias, t2.v, t.B, t.H, t.W, st); });
+    EpiSpec s2 = s0;
+    s2.res1 = &xin;
+    gemm(t2, w->dc3, &o1, s2);
+    gemm(o1, w->ffn0, &u, s1);
+    EpiSpec s3 = s0;
+    s3.res1 = &o1;
+    if (shortcut) s3.res2 = &xin;
+    s3.scale_table = scale_table;
+    s3.scale_C = C;
+    s3.out_f32 = out_f32;
+    s3.ld_f32 = ld_f32;
+    gemm(u, w->ffn2, out_f32 ? nullptr : &out, s3);
+  }
+
+  void build_p();
+  void build_intra();
+  void finalize(cudaStream_t st);
+  void run(std::vector<Op>& p, cudaStream_t st) {
+    for (auto& f : p) f(st);
+  }
+};
+
+// ====================================================================== P-frame program
+void dmc_engine::build_p() {
+  const bool refactor = variant != DMC_VARIANT_OLD;
+  const int H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16, H32 = H / 32, W32 = W / 32,
+            H64 = H / 64, W64 = W / 64;
+  const int CD = 256, CY = 128, CZ = 128, CR = 320, QP = 72;
+  const int ns = 3;
+  const int ns_recon = (flags & DMC_FLAG_RECON_BF16X1) ? 1 : 3;
+  dmc_engine* self = this;
+
+  // ---- weights, in the reference's registration order (documentation only; lookup is by key)
+  float* q_encoder = add_table("q_encoder", {QP, CD, 1, 1});
+  float* q_decoder = add_table("q_decoder", {QP, CD, 1, 1});
+  float* q_feature = add_table("q_feature", {QP, CD, 1, 1});
+  float* q_recon = add_table("q_recon", {QP, CR, 1, 1});
+  float* q_sft = (variant == DMC_VARIANT_PERFORMANCE) ? add_table("q_sft", {QP, CD, 1, 1}) : nullptr;
+  float* bitparm[11];
+  {
+    const char* names[11] = {"f1.h", "f1.b", "f1.a", "f2.h", "f2.b", "f2.a",
+                             "f3.h", "f3.b", "f3.a", "f4.h", "f4.b"};
+    for (int i = 0; i < 11; ++i)
+      bitparm[i] = add_table(std::string("bit_estimator_z.") + names[i], {QP, CZ, 1, 1});
+  }
+  DCB* fa_i = add_dcb("feature_adaptor_i", 192, CD);
+  Conv* fa_p = add_conv("feature_adaptor_p", CD, CD, 1, 1, 0);
+  DCB* fe1[2];
+  DCB* fe2[4];
+  for (int i = 0; i < 2; ++i) fe1[i] = add_dcb("feature_extractor.conv1." + std::to_string(i), CD, CD);
+  for (int i = 0; i < 4; ++i) fe2[i] = add_dcb("feature_extractor.conv2." + std::to_string(i), CD, CD);
+  Conv* enc_conv1 = add_conv("encoder.conv1", 192, CD, 1, 1, 0);
+  DCB* enc_b[3];
+  enc_b[0] = add_dcb("encoder.conv2.0", 2 * CD, CD);
+  enc_b[1] = add_dcb("encoder.conv2.1", CD, CD);
+  enc_b[2] = add_dcb(refactor ? "encoder.conv2.2" : "encoder.conv3", CD, CD);
+  Conv* enc_down = add_conv("encoder.down", CD, CY, 3, 2, 1);
+  DCB* he0 = add_dcb("hyper_encoder.conv.0", CY, CZ);
+  Conv* he1d = add_conv("hyper_encoder.conv.1.down", CZ, CZ, 2, 2, 0);
+  DCB* he1 = add_dcb("hyper_encoder.conv.1.conv", CZ, CZ);
+  Conv* he2d = add_conv("hyper_encoder.conv.2.down", CZ, CZ, 2, 2, 0);
+  DCB* he2 = add_dcb("hyper_encoder.conv.2.conv", CZ, CZ);
+  Conv* hd0u = add_conv("hyper_decoder.conv.0.up.conv.0", CZ, CZ * 4, 1, 1, 0, PACK_SHUF2);
+  DCB* hd0 = add_dcb("hyper_decoder.conv.0.conv", CZ, CZ);
+  Conv* hd1u = add_conv("hyper_decoder.conv.1.up.conv.0", CZ, CZ * 4, 1, 1, 0, PACK_SHUF2);
+  DCB* hd1 = add_dcb("hyper_decoder.conv.1.conv", CZ, CZ);
+  DCB* hd2 = add_dcb("hyper_decoder.conv.2", CZ, CY);
+  Conv* tpd = add_conv("temporal_prior_encoder.down", CD, 2 * CY, 2, 2, 0);
+  DCB* tpc = add_dcb("temporal_prior_encoder.conv", 2 * CY, 2 * CY);
+  DCB* pf[3];
+  for (int i = 0; i < 3; ++i) pf[i] = add_dcb("y_prior_fusion.conv." + std::to_string(i), 3 * CY, 3 * CY);
+  Conv* pf3 = add_conv("y_prior_fusion.conv.3", 3 * CY, 3 * CY, 1, 1, 0);
+  DCB* sp0 = add_dcb("y_spatial_prior.conv.0", 4 * CY, 3 * CY);
+  DCB* sp1 = add_dcb("y_spatial_prior.conv.1", 3 * CY, 3 * CY);
+  Conv* sp2 = add_conv("y_spatial_prior.conv.2", 3 * CY, 2 * CY, 1, 1, 0);
+  Conv* dec_up = add_conv("decoder.up.conv.0", CY, CD * 4, 3, 1, 1, PACK_SHUF2);
+  DCB* dec_b[3];
+  const std::string dpre = refactor ? "decoder.conv." : "decoder.conv1.";
+  dec_b[0] = add_dcb(dpre + "0", 2 * CD, CD);
+  dec_b[1] = add_dcb(dpre + "1", CD, CD);
+  dec_b[2] = add_dcb(dpre + "2", CD, CD);
+  Conv* dec_proj = add_conv(refactor ? "decoder.proj" : "decoder.conv2", CD, CD, 1, 1, 0);
+  DCB* rec[4];
+  rec[0] = add_dcb("recon_generation_net.conv.0", CD, CR);
+  for (int i = 1; i < 4; ++i) rec[i] = add_dcb("recon_generation_net.conv." + std::to_string(i), CR, CR);
+  Conv* rec_head = add_conv("recon_generation_net.head", CR, 192, 1, 1, 0);
+
+  Conv* sft_conv1 = nullptr; DCB* sft_b[3] = {nullptr, nullptr, nullptr}; Conv* sft_down = nullptr;
+  float *mf_w0 = nullptr, *mf_b0 = nullptr, *mf_w2 = nullptr, *mf_b2 = nullptr;
+  float *me_w = nullptr, *me_b = nullptr, *mp4_w = nullptr, *mp4_b = nullptr;
+  Conv *mp0 = nullptr, *mp2 = nullptr;
+  if (variant == DMC_VARIANT_PERFORMANCE) {
+    sft_conv1 = add_conv("mask_sft.conv1", 64, CD, 1, 1, 0);
+    for (int i = 0; i < 3; ++i) sft_b[i] = add_dcb("mask_sft.conv2." + std::to_string(i), CD, CD);
+    sft_down = add_conv("mask_sft.down", CD, 2 * CY, 3, 2, 1);
+  }
+  if (variant == DMC_VARIANT_FAST || variant == DMC_VARIANT_MASK_PROP) {
+    mf_w0 = add_table("mask_film.net.0.weight", {16, 1, 3, 3});
+    mf_b0 = add_table("mask_film.net.0.bias", {16});
+    mf_w2 = add_table("mask_film.net.2.weight", {2 * CY, 16, 1, 1});
+    mf_b2 = add_table("mask_film.net.2.bias", {2 * CY});
+  }
+  if (variant == DMC_VARIANT_MASK_PROP) {
+    me_w = add_table("mask_predictor.mask_embed.weight", {CD, 1, 3, 3});
+    me_b = add_table("mask_predictor.mask_embed.bias", {CD});
+    mp0 = add_conv("mask_predictor.net.0", 3 * CD, CD / 4, 3, 1, 1);
+    mp2 = add_conv("mask_predictor.net.2", CD / 4, CD / 4, 3, 1, 1);
+    mp4_w = add_table("mask_predictor.net.4.weight", {1, CD / 4, 1, 1});
+    mp4_b = add_table("mask_predictor.net.4.bias", {1});
+  }
+
+  // ---- persistent buffers
+  bits_y = (double*)dalloc(sizeof(double) * B);
+  bits_z = (double*)dalloc(sizeof(double) * B);
+  bpp_scratch = new_f32(3 * B);
+  Act X8 = new_act(B, H8, W8, 192);            // pixel_unshuffle(x, 8)
+  Act F8 = new_act(B, H8, W8, 192);            // pixel_unshuffle(dpb.frame, 8)
+  Act FP = new_act(B, H8, W8, CD);             // dpb.feature
+  Act FEAT0 = new_act(B, H8, W8, CD);          // temporal feature
+  Act PA = new_act(B, H8, W8, CD), PB = new_act(B, H8, W8, CD);   // ping-pong
+  Act X1 = new_act(B, H8, W8, CD);
+  Act CTXT = new_act(B, H8, W8, CD);
+  Act XC = new_act(B, H8, W8, 2 * CD);         // [encoder.conv1 out / decoder.up out | ctx]
+  Act XC_lo = slice(XC, 0, CD), CTX = slice(XC, CD, CD);
+  Act Y = new_act(B, H16, W16, CY);
+  Act YF = new_act(B, H16, W16, CY);           // FiLM'd y (performance) / hyper input (fast)
+  Act HA = new_act(B, H16, W16, CZ);
+  Act D32 = new_act(B, H32, W32, CZ), H32a = new_act(B, H32, W32, CZ);
+  Act D64 = new_act(B, H64, W64, CZ), Z = new_act(B, H64, W64, CZ), ZH = new_act(B, H64, W64, CZ);
+  Act U32 = new_act(B, H32, W32, CZ), G32 = new_act(B, H32, W32, CZ);
+  Act U16 = new_act(B, H16, W16, CZ), G16 = new_act(B, H16, W16, CZ);
+  Act HT = new_act(B, H16, W16, 3 * CY);       // [hier | temporal]
+  Act HIER = slice(HT, 0, CY), TEMP = slice(HT, CY, 2 * CY);
+  Act TD = new_act(B, H16, W16, 2 * CY);
+  Act P0 = new_act(B, H16, W16, 3 * CY), P1 = new_act(B, H16, W16, 3 * CY);
+  Act PC = new_act(B, H16, W16, 4 * CY);       // [y_hat (running) | q_dec | sigma0 | mu0]
+  Act YH0 = slice(PC, 0, CY), PARAMS = slice(PC, CY, 3 * CY);
+  Act S0 = new_act(B, H16, W16, 3 * CY), S1 = new_act(B, H16, W16, 3 * CY);
+  Act SP = new_act(B, H16, W16, 2 * CY);
+  Act YHAT = new_act(B, H16, W16, CY);
+  Act FEAT = new_act(B, H8, W8, CD);
+  Act R0 = new_act(B, H8, W8, CR), R1 = new_act(B, H8, W8, CR);
+  const long long M8 = (long long)B * H8 * W8, M16 = (long long)B * H16 * W16;
+  float* sym = new_f32((size_t)M16 * CY);
+  float* sig = new_f32((size_t)M16 * CY);
+  float* RF = new_f32((size_t)M8 * 192);
+
+  // ---- head: temporal feature (video_model.py:348-351)
+  prog = &prog_head_i;
+  op([self, F8](cudaStream_t st) { unshuffle8_in(self->cur.dpb_frame, F8.v, self->B, 3, self->H, self->W, st); });
+  dcb(fa_i, F8, FEAT0, false, nullptr, ns);
+  prog = &prog_head_p;
+  op([self, FP](cudaStream_t st) { nchw_to_s3(self->cur.dpb_feature, FP.v, FP.B, 256, FP.H, FP.W, st); });
+  {
+    EpiSpec s; s.nsplit = ns;
+    gemm(FP, fa_p, &FEAT0, s);
+  }
+
+  prog = &prog_common;
+  double* by = bits_y; double* bz = bits_z; int nb = B;
+  op([by, bz, nb](cudaStream_t st) {
+    CUDA_OK(cudaMemsetAsync(by, 0, sizeof(double) * nb, st));
+    CUDA_OK(cudaMemsetAsync(bz, 0, sizeof(double) * nb, st));
+  });
+  tap("feature_in", FEAT0);
+  // ---- feature extractor (video_model.py:23-49)
+  dcb(fe1[0], FEAT0, PA, false, nullptr, ns);
+  dcb(fe1[1], PA, X1, false, nullptr, ns);
+  op([self, X1, CTXT, q_feature, M8](cudaStream_t st) {
+    scale_cols(X1.v, q_feature + (size_t)self->cur.qp * 256, CTXT.v, M8, st);
+  });
+  dcb(fe2[0], X1, PA, false, nullptr, ns);
+  dcb(fe2[1], PA, PB, false, nullptr, ns);
+  dcb(fe2[2], PB, PA, false, nullptr, ns);
+  dcb(fe2[3], PA, CTX, false, nullptr, ns);
+  tap("ctx", CTX);
+  tap("ctx_t", CTXT);
+  // ---- encoder (video_model.py:52-75 / seg_video_model.py:41-59)
+  op([self, X8](cudaStream_t st) { unshuffle8_in(self->cur.x, X8.v, self->B, 3, self->H, self->W, st); });
+  {
+    EpiSpec s; s.nsplit = ns;
+    gemm(X8, enc_conv1, &XC_lo, s);
+  }
+  dcb(enc_b[0], XC, PA, false, nullptr, ns);
+  dcb(enc_b[1], PA, PB, false, nullptr, ns);
+  dcb(enc_b[2], PB, PA, false, q_encoder, ns);
+  {
+    EpiSpec s; s.nsplit = ns;
+    conv_kxk(PA, enc_down, &Y, s);
+  }
+  tap("y_enc", Y);
+
+  // ---- mask conditioning
+  Act YQ = Y;          // the y that is quantised
+  Act HIN = Y;         // the hyper-encoder input
+  if (variant == DMC_VARIANT_PERFORMANCE) {
+    // SFT (seg_video_model.py:159-196) and FiLM on y itself (:327-328)
+    Act MK = new_act(B, H8, W8, 64);
+    Act GB = new_act(B, H16, W16, 2 * CY);
+    op([self, MK](cudaStream_t st) {
+      if (self->cur.mask) unshuffle8_in(self->cur.mask, MK.v, self->B, 1, self->H, self->W, st);
+      else CUDA_OK(cudaMemsetAsync(MK.v.p, 0, (size_t)MK.v.ps * 3 * sizeof(bf16), st));
+    });
+    EpiSpec s; s.nsplit = ns;
+    gemm(MK, sft_conv1, &PB, s);
+    dcb(sft_b[0], PB, PA, false, nullptr, ns);
+    dcb(sft_b[1], PA, PB, false, nullptr, ns);
+    dcb(sft_b[2], PB, PA, false, q_sft, ns);
+    conv_kxk(PA, sft_down, &GB, s);
+    op([Y, GB, YF, M16](cudaStream_t st) { film(Y.v, GB.v, YF.v, M16, 128, st); });
+    tap("gamma_beta", GB);
+    YQ = YF;
+    HIN = YF;
+  } else if (variant == DMC_VARIANT_FAST || variant == DMC_VARIANT_MASK_PROP) {
+    float* mpool = new_f32((size_t)M16);
+    float* logits_full = nullptr;
+    if (variant == DMC_VARIANT_MASK_PROP) {
+      // MaskPredictor (mask_predictor.py:27-46), only when after_i == 0 and a mask was given
+      float* mdown = new_f32((size_t)M8);
+      float* logit8 = new_f32((size_t)M8);
+      logits_full = new_f32((size_t)B * H * W);
+      Act ME = new_act(B, H8, W8, CD);
+      Act COL = get_scratch("im2col", B, H8, W8, 9 * 3 * CD);
+      Act PM1 = new_act(B, H8, W8, CD / 4), PM2 = new_act(B, H8, W8, CD / 4);
+      std::vector<Op> pred;
+      std::vector<Op>* saved = prog;
+      prog = &pred;
+      op([self, mdown](cudaStream_t st) { bilinear_down8(self->cur.mask, mdown, self->B, self->H, self->W, st); });
+      op([mdown, me_w, me_b, ME](cudaStream_t st) { conv3x3_c1(mdown, me_w, me_b, ME.v, ME.B, ME.H, ME.W, 256, st); });
+      Act srcs[3] = {ME, CTX, CTXT};
+      for (int i = 0; i < 3; ++i) {
+        Act s = srcs[i];
+        int off = i * CD;
+        op([s, COL, off](cudaStream_t st) {
+          im2col(s.v, COL.v, s.B, s.H, s.W, 3, 1, 1, s.H, s.W, 3 * 256, off, st);
+        });
+      }
+      EpiSpec sa; sa.nsplit = ns; sa.act = ACT_WSILU;
+      gemm(COL, mp0, &PM1, sa);
+      conv_kxk(PM1, mp2, &PM2, sa);
+      op([PM2, mp4_w, mp4_b, logit8, M8](cudaStream_t st) { conv1x1_to1(PM2.v, mp4_w, mp4_b, logit8, M8, 64, st); });
+      op([self, logit8, logits_full, H8, W8](cudaStream_t st) {
+        float* dst = self->cur.mask_pred ? self->cur.mask_pred : logits_full;
+        bilinear_up8(logit8, dst, self->B, H8, W8, st);
+      });
+      prog = saved;
+      auto pred_ops = std::make_shared<std::vector<Op>>(std::move(pred));
+      // guarded: the predictor runs only on non-first P frames with a mask
+      // (mask_prop_seg_video_model.py:365-368)
+      struct Guard { dmc_engine* e; std::shared_ptr<std::vector<Op>> ops; };
+      Guard gd{self, pred_ops};
+      op([gd](cudaStream_t st) {
+        if (gd.e->cur_after_i || !gd.e->cur.mask) return;
+        for (auto& f : *gd.ops) f(st);
+      });
+      ftaps["mask_logits8"] = F32Tap{logit8, B, 1, H8, W8};
+    }
+    op([self, mpool, logits_full, Y, YF, mf_w0, mf_b0, mf_w2, mf_b2, H16, W16](cudaStream_t st) {
+      const float* m = self->cur.mask;
+      if (self->variant == DMC_VARIANT_MASK_PROP && !self->cur_after_i && m)
+        m = self->cur.mask_pred ? self->cur.mask_pred : logits_full;
+      if (m) avgpool16_clamp(m, mpool, self->B, self->H, self->W, st);
+      maskfilm_apply(m ? mpool : nullptr, Y.v, YF.v, mf_w0, mf_b0, mf_w2, mf_b2, self->B, H16, W16, 128, st);
+    });
+    HIN = YF;
+  }
+  tap("y", YQ);
+  tap("hyper_in", HIN);
+
+  // ---- hyper encoder (video_model.py:123-133)
+  dcb(he0, HIN, HA, false, nullptr, ns);
+  {
+    EpiSpec s; s.nsplit = ns;
+    conv_kxk(HA, he1d, &D32, s);
+    dcb(he1, D32, H32a, true, nullptr, ns);
+    conv_kxk(H32a, he2d, &D64, s);
+    dcb(he2, D64, Z, true, nullptr, ns);
+  }
+  tap("z", Z);
+  {
+    int HW64 = H64 * W64;
+    op([self, Z, ZH, HW64, bitparm, bz](cudaStream_t st) {
+      BitparmRow t;
+      for (int i = 0; i < 11; ++i) t.p[i] = bitparm[i] + (size_t)self->cur.qp * 128;
+      round_z_bits(Z.v, ZH.v, self->B, HW64, 128, t, bz, st);
+    });
+  }
+  tap("z_hat", ZH);
+  // ---- hyper decoder (video_model.py:136-146) + temporal prior + fusion (:236-243,149-160)
+  {
+    EpiSpec s; s.nsplit = ns;
+    gemm(ZH, hd0u, &U32, s, H64, W64);
+    dcb(hd0, U32, G32, true, nullptr, ns);
+    gemm(G32, hd1u, &U16, s, H32, W32);
+    dcb(hd1, U16, G16, true, nullptr, ns);
+    dcb(hd2, G16, HIER, false, nullptr, ns);
+    conv_kxk(CTXT, tpd, &TD, s);
+    dcb(tpc, TD, TEMP, true, nullptr, ns);
+    tap("hier", HIER);
+    tap("temporal", TEMP);
+    dcb(pf[0], HT, P0, false, nullptr, ns);
+    dcb(pf[1], P0, P1, false, nullptr, ns);
+    dcb(pf[2], P1, P0, false, nullptr, ns);
+    gemm(P0, pf3, &PARAMS, s);
+  }
+  tap("params", PARAMS);
+  // ---- two-step checkerboard quantisation (models/common_model.py:121-149)
+  PriorArgs pa;
+  memset(&pa, 0, sizeof pa);
+  pa.scheme = 2; pa.B = B; pa.H = H16; pa.W = W16; pa.C = CY;
+  pa.y = YQ.v; pa.params = PARAMS.v; pa.sp = SP.v; pa.yh = YH0.v; pa.sym = sym; pa.sig = sig;
+  {
+    PriorArgs a0 = pa; a0.step = 0;
+    op([a0](cudaStream_t st) { prior_step(a0, st); });
+    tap("y_hat_0", YH0);
+    dcb(sp0, PC, S0, false, nullptr, ns);
+    dcb(sp1, S0, S1, false, nullptr, ns);
+    EpiSpec s; s.nsplit = ns;
+    gemm(S1, sp2, &SP, s);
+    tap("spatial_prior", SP);
+    PriorArgs a1 = pa; a1.step = 1;
+    op([a1](cudaStream_t st) { prior_step(a1, st); });
+    int formula = refactor ? 1 : 0;
+    op([a1, YHAT, formula, by](cudaStream_t st) { prior_finish(a1, YHAT.v, formula, by, st); });
+  }
+  tap("y_hat", YHAT);
+  ftaps["y_q"] = F32Tap{sym, B, CY, H16, W16};
+  ftaps["scales_hat"] = F32Tap{sig, B, CY, H16, W16};
+  // ---- decoder (video_model.py:78-97 / seg_video_model.py:62-77)
+  {
+    EpiSpec s; s.nsplit = ns;
+    if (refactor) { s.scale_table = q_decoder; s.scale_C = CD; }
+    conv_kxk(YHAT, dec_up, &XC_lo, s, true);
+    dcb(dec_b[0], XC, PA, false, nullptr, ns);
+    dcb(dec_b[1], PA, PB, false, nullptr, ns);
+    dcb(dec_b[2], PB, PA, false, nullptr, ns);
+    EpiSpec s2; s2.nsplit = ns;
+    if (!refactor) { s2.scale_table = q_decoder; s2.scale_C = CD; }
+    gemm(PA, dec_proj, &FEAT, s2);
+  }
+  op([self, FEAT](cudaStream_t st) { s3_to_nchw(FEAT.v, self->cur.feature, FEAT.B, 256, FEAT.H, FEAT.W, st); });
+  // ---- reconstruction (video_model.py:100-120)
+  dcb(rec[0], FEAT, R0, false, nullptr, ns_recon);
+  dcb(rec[1], R0, R1, false, nullptr, ns_recon);
+  dcb(rec[2], R1, R0, false, nullptr, ns_recon);
+  dcb(rec[3], R0, R1, false, q_recon, ns_recon);
+  {
+    EpiSpec s; s.nsplit = ns_recon; s.out_f32 = RF; s.ld_f32 = 192;
+    gemm(R1, rec_head, nullptr, s);
+  }
+  op([self, RF](cudaStream_t st) { shuffle8_out(RF, 192, self->cur.x_hat, self->B, 3, self->H, self->W, st); });
+  // ---- rate (video_model.py:373-378)
+  int pixels = H * W;
+  op([self, by, bz, pixels](cudaStream_t st) { finalize_bpp(by, bz, self->cur.bpp3, self->B, pixels, st); });
+  if (true) {
+    op([self, YQ, FEAT, M16, M8](cudaStream_t st) {
+      if (!self->cur.finite) return;
+      CUDA_OK(cudaMemsetAsync(self->cur.finite, 0, sizeof(int32_t), st));
+      finite_check(YQ.v, M16, self->cur.finite, st);
+      finite_check(FEAT.v, M8, self->cur.finite, st);
+    });
+  }
+}
+
+// ====================================================================== I-frame program
+void dmc_engine::build_intra() {
+  const int H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16, H32 = H / 32, W32 = W / 32,
+            H64 = H / 64, W64 = W / 64;
+  const int CE = 368, N = 256, CZ = 128, QP = 64;
+  const int ns = 3;
+  dmc_engine* self = this;
+
+  float* q_enc = add_table("q_scale_enc", {QP, CE, 1, 1});
+  float* q_dec = add_table("q_scale_dec", {QP, CE, 1, 1});
+  float* bitparm[11];
+  {
+    const char* names[11] = {"f1.h", "f1.b", "f1.a", "f2.h", "f2.b", "f2.a",
+                             "f3.h", "f3.b", "f3.a", "f4.h", "f4.b"};
+    for (int i = 0; i < 11; ++i)
+      bitparm[i] = add_table(std::string("bit_estimator_z.") + names[i], {QP, CZ, 1, 1});
+  }
+  DCB* enc1 = add_dcb("enc.enc_1", 192, CE);
+  DCB* enc2[6];
+  for (int i = 0; i < 6; ++i) enc2[i] = add_dcb("enc.enc_2." + std::to_string(i), CE, CE);
+  Conv* enc_down = add_conv("enc.enc_2.6", CE, N, 3, 2, 1);
+  DCB* he0 = add_dcb("hyper_enc.0", N, CZ);
+  Conv* he1d = add_conv("hyper_enc.1.down", CZ, CZ, 2, 2, 0);
+  DCB* he1 = add_dcb("hyper_enc.1.conv", CZ, CZ);
+  Conv* he2d = add_conv("hyper_enc.2.down", CZ, CZ, 2, 2, 0);
+  DCB* he2 = add_dcb("hyper_enc.2.conv", CZ, CZ);
+  Conv* hd0u = add_conv("hyper_dec.0.up.conv.0", CZ, CZ * 4, 1, 1, 0, PACK_SHUF2);
+  DCB* hd0 = add_dcb("hyper_dec.0.conv", CZ, CZ);
+  Conv* hd1u = add_conv("hyper_dec.1.up.conv.0", CZ, CZ * 4, 1, 1, 0, PACK_SHUF2);
+  DCB* hd1 = add_dcb("hyper_dec.1.conv", CZ, CZ);
+  DCB* hd2 = add_dcb("hyper_dec.2", CZ, N);
+  DCB* pf0 = add_dcb("y_prior_fusion.0", N, 2 * N);
+  DCB* pf1 = add_dcb("y_prior_fusion.1", 2 * N, 2 * N);
+  DCB* pf2 = add_dcb("y_prior_fusion.2", 2 * N, 2 * N);
+  Conv* pf3 = add_conv("y_prior_fusion.3", 2 * N, 2 * N + 2, 1, 1, 0);
+  Conv* red = add_conv("y_spatial_prior_reduction", 2 * N + 2, N, 1, 1, 0);
+  DCB* ad[3];
+  for (int i = 0; i < 3; ++i)
+    ad[i] = add_dcb("y_spatial_prior_adaptor_" + std::to_string(i + 1), 2 * N, 2 * N, true);
+  DCB* spb[3];
+  for (int i = 0; i < 3; ++i) spb[i] = add_dcb("y_spatial_prior." + std::to_string(i), 2 * N, 2 * N);
+  Conv* sp3 = add_conv("y_spatial_prior.3", 2 * N, 2 * N, 1, 1, 0);
+  Conv* dec_up = add_conv("dec.dec_1.0.up.conv.0", N, CE * 4, 1, 1, 0, PACK_SHUF2);
+  DCB* dec0 = add_dcb("dec.dec_1.0.conv", CE, CE);
+  DCB* dec1[12];
+  for (int i = 0; i < 12; ++i) dec1[i] = add_dcb("dec.dec_1." + std::to_string(i + 1), CE, CE);
+  DCB* dec2 = add_dcb("dec.dec_2", CE, 192);
+
+  bits_y = (double*)dalloc(sizeof(double) * B);
+  bits_z = (double*)dalloc(sizeof(double) * B);
+  Act X8 = new_act(B, H8, W8, 192);
+  Act EA = new_act(B, H8, W8, CE), EB = new_act(B, H8, W8, CE);
+  Act Y = new_act(B, H16, W16, N);
+  Act HA = new_act(B, H16, W16, CZ);
+  Act D32 = new_act(B, H32, W32, CZ), H32a = new_act(B, H32, W32, CZ);
+  Act D64 = new_act(B, H64, W64, CZ), Z = new_act(B, H64, W64, CZ), ZH = new_act(B, H64, W64, CZ);
+  Act U32 = new_act(B, H32, W32, CZ), G32 = new_act(B, H32, W32, CZ);
+  Act U16 = new_act(B, H16, W16, CZ), G16 = new_act(B, H16, W16, CZ);
+  Act HP = new_act(B, H16, W16, N);
+  Act FA = new_act(B, H16, W16, 2 * N), FB = new_act(B, H16, W16, 2 * N);
+  Act PARAMS = new_act(B, H16, W16, 2 * N + 2);
+  Act Q = new_act(B, H16, W16, 2 * N);          // [y_hat so far | reduced common params]
+  Act YHS = slice(Q, 0, N), COMMON = slice(Q, N, N);
+  Act SP = new_act(B, H16, W16, 2 * N);
+  Act YHAT = new_act(B, H16, W16, N);
+  const long long M8 = (long long)B * H8 * W8, M16 = (long long)B * H16 * W16;
+  float* sym = new_f32((size_t)M16 * N);
+  float* sig = new_f32((size_t)M16 * N);
+  float* RF = new_f32((size_t)M8 * 192);
+
+  prog = &prog_common;
+  double* by = bits_y; double* bz = bits_z; int nb = B;
+  op([by, bz, nb](cudaStream_t st) {
+    CUDA_OK(cudaMemsetAsync(by, 0, sizeof(double) * nb, st));
+    CUDA_OK(cudaMemsetAsync(bz, 0, sizeof(double) * nb, st));
+  });
+  // encoder (image_model.py:16-43)
+  op([self, X8](cudaStream_t st) { unshuffle8_in(self->cur.x, X8.v, self->B, 3, self->H, self->W, st); });
+  dcb(enc1, X8, EA, false, q_enc, ns);
+  {
+    Act a = EA, b = EB;
+    for (int i = 0; i < 6; ++i) { dcb(enc2[i], a, b, false, nullptr, ns); std::swap(a, b); }
+    EpiSpec s; s.nsplit = ns;
+    conv_kxk(a, enc_down, &Y, s);
+  }
+  tap("y", Y);
+  // hyper path (image_model.py:216-226)
+  {
+    EpiSpec s; s.nsplit = ns;
+    dcb(he0, Y, HA, false, nullptr, ns);
+    conv_kxk(HA, he1d, &D32, s);
+    dcb(he1, D32, H32a, true, nullptr, ns);
+    conv_kxk(H32a, he2d, &D64, s);
+    dcb(he2, D64, Z, true, nullptr, ns);
+    tap("z", Z);
+    int HW64 = H64 * W64;
+    op([self, Z, ZH, HW64, bitparm, bz](cudaStream_t st) {
+      BitparmRow t;
+      for (int i = 0; i < 11; ++i) t.p[i] = bitparm[i] + (size_t)self->cur.qp * 128;
+      round_z_bits(Z.v, ZH.v, self->B, HW64, 128, t, bz, st);
+    });
+    tap("z_hat", ZH);
+    gemm(ZH, hd0u, &U32, s, H64, W64);
+    dcb(hd0, U32, G32, true, nullptr, ns);
+    gemm(G32, hd1u, &U16, s, H32, W32);
+    dcb(hd1, U16, G16, true, nullptr, ns);
+    dcb(hd2, G16, HP, false, nullptr, ns);
+    dcb(pf0, HP, FA, false, nullptr, ns);
+    dcb(pf1, FA, FB, false, nullptr, ns);
+    dcb(pf2, FB, FA, false, nullptr, ns);
+    gemm(FA, pf3, &PARAMS, s);
+    tap("params", PARAMS);
+    gemm(PARAMS, red, &COMMON, s);
+  }
+  // four-step prior (models/common_model.py:188-248)
+  PriorArgs pa;
+  memset(&pa, 0, sizeof pa);
+  pa.scheme = 4; pa.B = B; pa.H = H16; pa.W = W16; pa.C = N;
+  pa.y = Y.v; pa.params = PARAMS.v; pa.sp = SP.v; pa.yh = YHS.v; pa.sym = sym; pa.sig = sig;
+  for (int step = 0; step < 4; ++step) {
+    if (step > 0) {
+      dcb(ad[step - 1], Q, FA, false, nullptr, ns);
+      dcb(spb[0], FA, FB, false, nullptr, ns);
+      dcb(spb[1], FB, FA, false, nullptr, ns);
+      dcb(spb[2], FA, FB, false, nullptr, ns);
+      EpiSpec s; s.nsplit = ns;
+      gemm(FB, sp3, &SP, s);
+    }
+    PriorArgs a = pa; a.step = step;
+    op([a](cudaStream_t st) { prior_step(a, st); });
+  }
+  {
+    PriorArgs a = pa; a.step = 3;
+    op([a, YHAT, by](cudaStream_t st) { prior_finish(a, YHAT.v, 0, by, st); });
+  }
+  tap("y_hat", YHAT);
+  ftaps["y_q"] = F32Tap{sym, B, N, H16, W16};
+  ftaps["scales_hat"] = F32Tap{sig, B, N, H16, W16};
+  // decoder (image_model.py:46-93)
+  {
+    EpiSpec s; s.nsplit = ns;
+    gemm(YHAT, dec_up, &EA, s, H16, W16);
+    dcb(dec0, EA, EB, true, nullptr, ns);
+    Act a = EB, b = EA;
+    for (int i = 0; i < 12; ++i) {
+      dcb(dec1[i], a, b, false, i == 11 ? q_dec : nullptr, ns);
+      std::swap(a, b);
+    }
+    dcb(dec2, a, a, false, nullptr, ns, RF, 192);
+  }
+  op([self, RF](cudaStream_t st) { shuffle8_out(RF, 192, self->cur.x_hat, self->B, 3, self->H, self->W, st); });
+  int pixels = H * W;
+  op([self, by, bz, pixels](cudaStream_t st) { finalize_bpp(by, bz, self->cur.bpp3, self->B, pixels, st); });
+}
+
+void dmc_engine::finalize(cudaStream_t st) {
+  for (auto& s : slots)
+    if (!s.set) fail("weight '%s' was never set", s.key.c_str());
+  (void)st;
+  finalized = true;
+}
+
+// ====================================================================== C ABI
+namespace {
+template <class F>
+int guarded(dmc_engine* e, F f) {
+  try {
+    f();
+    return DMC_OK;
+  } catch (const std::exception& ex) {
+    if (e) e->error = ex.what();
+    else g_create_error = ex.what();
+    const char* w = ex.what();
+    if (strstr(w, "cuda") || strstr(w, "CUDA")) return DMC_E_CUDA;
+    return DMC_E_INVALID;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int dmc_create(int variant, int batch, int height, int width, int flags, dmc_engine** out) {
+  if (!out) return DMC_E_INVALID;
+  *out = nullptr;
+  dmc_engine* e = nullptr;
+  int rc = guarded(nullptr, [&] {
+    if (variant < DMC_VARIANT_OLD || variant > DMC_VARIANT_INTRA) fail("unknown variant %d", variant);
+    if (batch < 1 || height < 64 || width < 64 || height % 64 || width % 64)
+      fail("batch must be >= 1 and height/width multiples of 64 (got %d, %d, %d)", batch, height, width);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      fail("CUDA device required: this engine has no CPU path");
+    e = new dmc_engine();
+    e->variant = variant; e->B = batch; e->H = height; e->W = width; e->flags = flags;
+    try {
+      if (variant == DMC_VARIANT_INTRA) e->build_intra();
+      else e->build_p();
+    } catch (...) {
+      delete e;
+      e = nullptr;
+      throw;
+    }
+  });
+  if (rc == DMC_OK) *out = e;
+  return rc;
+}
+
+void dmc_destroy(dmc_engine* e) { delete e; }
+
+const char* dmc_last_error(const dmc_engine* e) { return e ? e->error.c_str() : g_create_error.c_str(); }
+
+int dmc_num_weights(const dmc_engine* e) { return e ? (int)e->slots.size() : DMC_E_INVALID; }
+const char* dmc_weight_key(const dmc_engine* e, int i) {
+  if (!e || i < 0 || i >= (int)e->slots.size()) return nullptr;
+  return e->slots[i].key.c_str();
+}
+int dmc_weight_shape(const dmc_engine* e, int i, int64_t* shape4) {
+  if (!e || i < 0 || i >= (int)e->slots.size() || !shape4) return DMC_E_INVALID;
+  const auto& s = e->slots[i].shape;
+  for (size_t k = 0; k < s.size() && k < 4; ++k) shape4[k] = s[k];
+  return (int)s.size();
+}
+
+int dmc_set_weight(dmc_engine* e, const char* key, const float* dev_ptr, const int64_t* shape, int ndim,
+                   void* stream) {
+  if (!e || !key || !dev_ptr) return DMC_E_INVALID;
+  return guarded(e, [&] {
+    auto it = e->slot_index.find(key);
+    if (it == e->slot_index.end()) fail("unknown state_dict key '%s'", key);
+    WSlot& s = e->slots[it->second];
+    if ((int)s.shape.size() != ndim) fail("%s: expected %d dims, got %d", key, (int)s.shape.size(), ndim);
+    for (int i = 0; i < ndim; ++i)
+      if (s.shape[i] != shape[i])
+        fail("%s: dim %d is %lld, expected %lld", key, i, (long long)shape[i], (long long)s.shape[i]);
+    s.load(dev_ptr, (cudaStream_t)stream);
+    CUDA_OK(cudaGetLastError());
+    s.set = true;
+  });
+}
+
+int dmc_finalize_weights(dmc_engine* e, void* stream) {
+  if (!e) return DMC_E_INVALID;
+  int rc = guarded(e, [&] { e->finalize((cudaStream_t)stream); });
+  return rc == DMC_E_INVALID ? DMC_E_STATE : rc;
+}
+
+int dmc_forward(dmc_engine* e, const float* x, const float* mask, const float* dpb_frame,
+                const float* dpb_feature, int qp, int after_i, float* x_hat, float* feature,
+                float* bpp3, float* mask_pred, int32_t* finite_flag, void* stream) {
+  if (!e) return DMC_E_INVALID;
+  if (e->variant == DMC_VARIANT_INTRA) { e->error = "dmc_forward on an intra engine"; return DMC_E_INVALID; }
+  if (!e->finalized) { e->error = "weights not finalised"; return DMC_E_STATE; }
+  if (!x || !x_hat || !feature || !bpp3 || (after_i ? !dpb_frame : !dpb_feature) || qp < 0 || qp >= 72) {
+    e->error = "dmc_forward: null tensor or qp outside [0,72)";
+    return DMC_E_INVALID;
+  }
+  return guarded(e, [&] {
+    auto& c = e->cur;
+    c.x = x; c.mask = (e->variant == DMC_VARIANT_OLD) ? nullptr : mask;
+    c.dpb_frame = dpb_frame; c.dpb_feature = dpb_feature; c.qp = qp;
+    c.x_hat = x_hat; c.feature = feature; c.bpp3 = bpp3; c.mask_pred = mask_pred; c.finite = finite_flag;
+    e->cur_after_i = after_i != 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    e->run(after_i ? e->prog_head_i : e->prog_head_p, st);
+    e->run(e->prog_common, st);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int dmci_forward(dmc_engine* e, const float* x, int qp, float* x_hat, float* bpp3, void* stream) {
+  if (!e) return DMC_E_INVALID;
+  if (e->variant != DMC_VARIANT_INTRA) { e->error = "dmci_forward on a P-frame engine"; return DMC_E_INVALID; }
+  if (!e->finalized) { e->error = "weights not finalised"; return DMC_E_STATE; }
+  if (!x || !x_hat || !bpp3 || qp < 0 || qp >= 64) {
+    e->error = "dmci_forward: null tensor or qp outside [0,64)";
+    return DMC_E_INVALID;
+  }
+  return guarded(e, [&] {
+    auto& c = e->cur;
+    c = dmc_engine::Cur();
+    c.x = x; c.qp = qp; c.x_hat = x_hat; c.bpp3 = bpp3;
+    e->run(e->prog_common, (cudaStream_t)stream);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int dmc_get_tap(dmc_engine* e, const char* name, float* dst, int64_t capacity, int64_t* shape4,
+                void* stream) {
+  if (!e || !name) return DMC_E_INVALID;
+  return guarded(e, [&] {
+    cudaStream_t st = (cudaStream_t)stream;
+    auto it = e->taps.find(name);
+    if (it != e->taps.end()) {
+      const Act& a = it->second;
+      if (shape4) { shape4[0] = a.B; shape4[1] = a.v.C; shape4[2] = a.H; shape4[3] = a.W; }
+      if (!dst) return;
+      if (capacity < a.M() * a.v.C) fail("tap '%s' needs %lld elements", name, a.M() * a.v.C);
+      if (a.v.C % 8 == 0 && (uintptr_t)a.v.p % 16 == 0) s3_to_nchw(a.v, dst, a.B, a.v.C, a.H, a.W, st);
+      else fail("tap '%s' has an unaligned layout", name);
+      return;
+    }
+    auto jt = e->ftaps.find(name);
+    if (jt == e->ftaps.end()) fail("no tap named '%s' (create with DMC_FLAG_KEEP_TAPS)", name);
+    const auto& f = jt->second;
+    if (shape4) { shape4[0] = f.B; shape4[1] = f.C; shape4[2] = f.H; shape4[3] = f.W; }
+    if (!dst) return;
+    if (capacity < (int64_t)f.B * f.C * f.H * f.W) fail("tap '%s' too small a buffer", name);
+    f32rows_to_nchw(f.p, f.C, dst, f.B, f.C, f.H, f.W, st);
+  });
+}
+
+int dmc_frame_stats(double* stats7, const float* x_hat, const float* x, const float* mask,
+                    const float* bpp3, int batch, int height, int width, void* stream) {
+  if (!stats7 || !x_hat || !x) return DMC_E_INVALID;
+  frame_stats(stats7, x_hat, x, mask, bpp3, batch, height, width, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
+}
+
+int dmc_num_sms(void) { return num_sms(); }
+const char* dmc_version(void) { return "dmc_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- single-operator entry points
+namespace {
+void set_slot(dmc_engine& e, const std::string& key, const float* p, cudaStream_t st) {
+  auto it = e.slot_index.find(key);
+  if (it == e.slot_index.end()) fail("internal: no slot %s", key.c_str());
+  e.slots[it->second].load(p, st);
+  e.slots[it->second].set = true;
+}
+}  // namespace
+
+extern "C" int dmc_op_conv2d(const float* x, const float* weight, const float* bias, float* out, int batch,
+                             int cin, int height, int width, int cout, int ksize, int stride, int padding,
+                             int groups, int act, int nsplit, int backend, void* stream) {
+  return guarded(nullptr, [&] {
+    if (!x || !weight || !out) fail("dmc_op_conv2d: null tensor");
+    cudaStream_t st = (cudaStream_t)stream;
+    dmc_engine e;
+    e.variant = -1; e.B = batch; e.H = height; e.W = width;
+    e.flags = backend == 1 ? DMC_FLAG_SIMT_GEMM : 0;
+    e.prog = &e.prog_common;
+    Act in = e.new_act(batch, height, width, cin);
+    int Ho = (height + 2 * padding - ksize) / stride + 1, Wo = (width + 2 * padding - ksize) / stride + 1;
+    Act o = e.new_act(batch, Ho, Wo, cout);
+    nchw_to_s3(x, in.v, batch, cin, height, width, st);
+    if (groups == cin && groups > 1) {
+      if (ksize != 3 || stride != 1 || padding != 1 || cin != cout) fail("depthwise: only 3x3 s1 p1");
+      DW* d = e.add_dw("w", cin);
+      set_slot(e, "w.weight", weight, st);
+      if (bias) set_slot(e, "w.bias", bias, st);
+      else CUDA_OK(cudaMemsetAsync(d->bias, 0, sizeof(float) * cin, st));
+      dwconv3x3(in.v, d->w9c, d->bias, o.v, batch, height, width, st);
+    } else if (groups == 1) {
+      Conv* c = e.add_conv("w", cin, cout, ksize, stride, padding);
+      set_slot(e, "w.weight", weight, st);
+      if (bias) set_slot(e, "w.bias", bias, st);
+      else pack_gemm_bias(nullptr, cout, c->g, st);
+      EpiSpec s; s.act = act; s.nsplit = nsplit;
+      if (ksize == 1 && stride == 1 && padding == 0) e.gemm(in, c, &o, s);
+      else e.conv_kxk(in, c, &o, s);
+      e.run(e.prog_common, st);
+    } else {
+      fail("groups must be 1 or cin");
+    }
+    s3_to_nchw(o.v, out, batch, cout, Ho, Wo, st);
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+extern "C" int dmc_op_depth_conv_block(const float* x, const float* const* w12, const float* quant_step,
+                                       float* out, int batch, int cin, int cout, int height, int width,
+                                       int shortcut, int nsplit, int backend, void* stream) {
+  return guarded(nullptr, [&] {
+    if (!x || !w12 || !out) fail("dmc_op_depth_conv_block: null tensor");
+    cudaStream_t st = (cudaStream_t)stream;
+    dmc_engine e;
+    e.variant = -1; e.B = batch; e.H = height; e.W = width;
+    e.flags = backend == 1 ? DMC_FLAG_SIMT_GEMM : 0;
+    e.prog = &e.prog_common;
+    DCB* b = e.add_dcb("b", cin, cout, w12[0] != nullptr);
+    if ((cin != cout) && !w12[0]) fail("adaptor weights required when cin != cout");
+    const char* names[6] = {"b.adaptor", "b.dc.0", "b.dc.2", "b.dc.3", "b.ffn.0", "b.ffn.2"};
+    for (int i = 0; i < 6; ++i) {
+      if (i == 0 && !b->adaptor) continue;
+      if (!w12[2 * i] || !w12[2 * i + 1]) fail("missing weight %s", names[i]);
+      set_slot(e, std::string(names[i]) + ".weight", w12[2 * i], st);
+      set_slot(e, std::string(names[i]) + ".bias", w12[2 * i + 1], st);
+    }
+    float* table = nullptr;
+    if (quant_step) {
+      table = e.new_f32(cout);
+      CUDA_OK(cudaMemcpyAsync(table, quant_step, sizeof(float) * cout, cudaMemcpyDeviceToDevice, st));
+    }
+    Act in = e.new_act(batch, height, width, cin);
+    Act o = e.new_act(batch, height, width, cout);
+    nchw_to_s3(x, in.v, batch, cin, height, width, st);
+    e.cur.qp = 0;
+    e.dcb(b, in, o, shortcut != 0, table, nsplit);
+    e.run(e.prog_common, st);
+    s3_to_nchw(o.v, out, batch, cout, height, width, st);
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+extern "C" int dmc_op_gaussian_bits(const float* sym, const float* sigma, float* bits, int64_t n, int formula,
+                                    void* stream) {
+  if (!sym || !sigma || !bits || n < 0) return DMC_E_INVALID;
+  gaussian_bits(sym, sigma, bits, n, formula, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
+}

@@ -1,0 +1,750 @@
+// Element-wise / stencil / entropy-model kernels of the DMC engine (sm_100a).
+// All of them are HBM-bound: one thread owns 8 consecutive channels (16 B per S3 plane) so
+// every global access is a 128-bit transaction, rows are contiguous in the channel dimension
+// and consecutive threads touch consecutive 16 B chunks.
+#include "kernels.h"
+
+#include <math.h>
+
+namespace dmc {
+
+static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------ weights
+__global__ void k_pack_gemm_weight(const float* __restrict__ w, bf16* __restrict__ out, int cout,
+                                   int cin, int kh, int kw, int Npad, int Kld, int K, int pack,
+                                   int Cg, int Cg_pad) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Npad * Kld) return;
+  int r = (int)(idx / Kld), kk = (int)(idx % Kld);
+  int n = -1;
+  if (pack == PACK_PAIR) {
+    int c2 = cout / 2;
+    int ch = (r >> 6) * 32 + (r & 31);
+    if (ch < c2) n = ((r & 63) < 32) ? ch : c2 + ch;
+  } else if (pack == PACK_SHUF2) {
+    int g = r / Cg_pad, c = r % Cg_pad;
+    if (c < Cg && g < 4) n = c * 4 + g;
+  } else if (r < cout) {
+    n = r;
+  }
+  float v = 0.0f;
+  if (n >= 0 && kk < K) {
+    int ci = kk % cin, tap = kk / cin;
+    int y = tap / kw, x = tap % kw;
+    v = w[(((long long)n * cin + ci) * kh + y) * kw + x];
+  }
+  bf16 h, m, l;
+  split3(v, h, m, l);
+  long long ps = (long long)Npad * Kld;
+  out[idx] = h;
+  out[ps + idx] = m;
+  out[2 * ps + idx] = l;
+}
+
+__global__ void k_pack_bias(const float* __restrict__ b, float* __restrict__ out, int cout, int Npad,
+                            int pack, int Cg, int Cg_pad) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Npad) return;
+  int n = -1;
+  if (pack == PACK_PAIR) {
+    int c2 = cout / 2;
+    int ch = (r >> 6) * 32 + (r & 31);
+    if (ch < c2) n = ((r & 63) < 32) ? ch : c2 + ch;
+  } else if (pack == PACK_SHUF2) {
+    int g = r / Cg_pad, c = r % Cg_pad;
+    if (c < Cg && g < 4) n = c * 4 + g;
+  } else if (r < cout) {
+    n = r;
+  }
+  out[r] = (n >= 0 && b) ? b[n] : 0.0f;
+}
+
+void pack_gemm_weight(const float* w, int cout, int cin, int kh, int kw, const GemmW& g,
+                      cudaStream_t st) {
+  long long n = (long long)g.Npad * g.Kld;
+  k_pack_gemm_weight<<<cdiv(n, 256), 256, 0, st>>>(w, g.w, cout, cin, kh, kw, g.Npad, g.Kld, g.K,
+                                                   g.pack, g.Cg, g.Cg_pad);
+}
+void pack_gemm_bias(const float* bias, int cout, const GemmW& g, cudaStream_t st) {
+  k_pack_bias<<<cdiv(g.Npad, 256), 256, 0, st>>>(bias, g.bias, cout, g.Npad, g.pack, g.Cg, g.Cg_pad);
+}
+
+__global__ void k_pack_dw(const float* __restrict__ w, float* __restrict__ out, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * C) return;
+  int tap = i / C, c = i % C;
+  out[i] = w[c * 9 + tap];
+}
+void pack_dw_weight(const float* w, float* out9c, int C, cudaStream_t st) {
+  k_pack_dw<<<cdiv(9 * C, 256), 256, 0, st>>>(w, out9c, C);
+}
+
+// ------------------------------------------------------------------ layout conversion
+__global__ void k_unshuffle8_in(const float* __restrict__ x, View out, int B, int Cimg, int H, int W) {
+  int W8 = W / 8, H8 = H / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H8 * Cimg * 8 * W8;
+  if (idx >= total) return;
+  int w8 = (int)(idx % W8);
+  long long t = idx / W8;
+  int dy = (int)(t % 8); t /= 8;
+  int c = (int)(t % Cimg); t /= Cimg;
+  int h8 = (int)(t % H8);
+  int b = (int)(t / H8);
+  const float* src = x + (((long long)b * Cimg + c) * H + (h8 * 8 + dy)) * W + w8 * 8;
+  float4 a = *reinterpret_cast<const float4*>(src);
+  float4 d = *reinterpret_cast<const float4*>(src + 4);
+  float v[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+  long long m = ((long long)b * H8 + h8) * W8 + w8;
+  st3x8(out, m, c * 64 + dy * 8, v);
+}
+void unshuffle8_in(const float* x, View out, int B, int Cimg, int H, int W, cudaStream_t st) {
+  long long total = (long long)B * (H / 8) * Cimg * 8 * (W / 8);
+  k_unshuffle8_in<<<cdiv(total, 256), 256, 0, st>>>(x, out, B, Cimg, H, W);
+}
+
+__global__ void k_shuffle8_out(const float* __restrict__ in, int ld, float* __restrict__ x, int B,
+                               int Cimg, int H, int W) {
+  int W8 = W / 8, H8 = H / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * Cimg * H * W8;
+  if (idx >= total) return;
+  int w8 = (int)(idx % W8);
+  long long t = idx / W8;
+  int h = (int)(t % H); t /= H;
+  int c = (int)(t % Cimg);
+  int b = (int)(t / Cimg);
+  int h8 = h / 8, dy = h % 8;
+  long long m = ((long long)b * H8 + h8) * W8 + w8;
+  const float* src = in + m * ld + c * 64 + dy * 8;
+  float4 a = *reinterpret_cast<const float4*>(src);
+  float4 d = *reinterpret_cast<const float4*>(src + 4);
+  a.x = fminf(fmaxf(a.x, 0.f), 1.f); a.y = fminf(fmaxf(a.y, 0.f), 1.f);
+  a.z = fminf(fmaxf(a.z, 0.f), 1.f); a.w = fminf(fmaxf(a.w, 0.f), 1.f);
+  d.x = fminf(fmaxf(d.x, 0.f), 1.f); d.y = fminf(fmaxf(d.y, 0.f), 1.f);
+  d.z = fminf(fmaxf(d.z, 0.f), 1.f); d.w = fminf(fmaxf(d.w, 0.f), 1.f);
+  float* dst = x + (((long long)b * Cimg + c) * H + h) * W + w8 * 8;
+  *reinterpret_cast<float4*>(dst) = a;
+  *reinterpret_cast<float4*>(dst + 4) = d;
+}
+void shuffle8_out(const float* in, int ld, float* x, int B, int Cimg, int H, int W, cudaStream_t st) {
+  long long total = (long long)B * Cimg * H * (W / 8);
+  k_shuffle8_out<<<cdiv(total, 256), 256, 0, st>>>(in, ld, x, B, Cimg, H, W);
+}
+
+// NCHW fp32 <-> S3 rows.  Thread = (pixel, 8 channels), pixel fastest so the NCHW side is coalesced.
+__global__ void k_nchw_to_s3(const float* __restrict__ x, View out, int C, long long HW) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  int c8 = blockIdx.y, b = blockIdx.z;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = c8 * 8 + i;
+    v[i] = (c < C) ? x[((long long)b * C + c) * HW + p] : 0.0f;
+  }
+  st3x8(out, (long long)b * HW + p, c8 * 8, v);
+}
+void nchw_to_s3(const float* x, View out, int B, int C, int H, int W, cudaStream_t st) {
+  long long HW = (long long)H * W;
+  dim3 grid(cdiv(HW, 256), (C + 7) / 8, B);
+  k_nchw_to_s3<<<grid, 256, 0, st>>>(x, out, C, HW);
+}
+__global__ void k_s3_to_nchw(View in, float* __restrict__ x, int C, long long HW) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  int c8 = blockIdx.y, b = blockIdx.z;
+  float v[8];
+  ld3x8(in, (long long)b * HW + p, c8 * 8, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = c8 * 8 + i;
+    if (c < C) x[((long long)b * C + c) * HW + p] = v[i];
+  }
+}
+void s3_to_nchw(View in, float* x, int B, int C, int H, int W, cudaStream_t st) {
+  long long HW = (long long)H * W;
+  dim3 grid(cdiv(HW, 256), (C + 7) / 8, B);
+  k_s3_to_nchw<<<grid, 256, 0, st>>>(in, x, C, HW);
+}
+__global__ void k_f32rows_to_nchw(const float* __restrict__ in, int ld, float* __restrict__ x, int C,
+                                  long long HW) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  int c = blockIdx.y, b = blockIdx.z;
+  x[((long long)b * C + c) * HW + p] = in[((long long)b * HW + p) * ld + c];
+}
+void f32rows_to_nchw(const float* in, int ld, float* x, int B, int C, int H, int W, cudaStream_t st) {
+  long long HW = (long long)H * W;
+  dim3 grid(cdiv(HW, 256), C, B);
+  k_f32rows_to_nchw<<<grid, 256, 0, st>>>(in, ld, x, C, HW);
+}
+
+__global__ void k_scale_cols(View in, const float* __restrict__ scale, View out, long long M, int C8) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * C8) return;
+  long long m = idx / C8;
+  int c = (int)(idx % C8) * 8;
+  float v[8];
+  ld3x8(in, m, c, v);
+  if (scale) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = mul_rn(v[i], scale[c + i]);
+  }
+  st3x8(out, m, c, v);
+}
+void scale_cols(View in, const float* scale, View out, long long M, cudaStream_t st) {
+  int C8 = in.C / 8;
+  k_scale_cols<<<cdiv(M * C8, 256), 256, 0, st>>>(in, scale, out, M, C8);
+}
+void copy_view(View in, View out, long long M, cudaStream_t st) { scale_cols(in, nullptr, out, M, st); }
+
+__global__ void k_finite_check(View v, long long M, int C8, int* flag) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * C8) return;
+  long long m = idx / C8;
+  int c = (int)(idx % C8) * 8;
+  uint4 a = *reinterpret_cast<const uint4*>(v.p + m * v.ld + c);
+  const uint32_t* u = &a.x;
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bad |= ((u[i] & 0x7f80u) == 0x7f80u) | ((u[i] & 0x7f800000u) == 0x7f800000u);
+  }
+  if (bad) atomicOr(flag, 1);
+}
+void finite_check(View v, long long M, int* flag, cudaStream_t st) {
+  int C8 = v.C / 8;
+  k_finite_check<<<cdiv(M * C8, 256), 256, 0, st>>>(v, M, C8, flag);
+}
+
+// ------------------------------------------------------------------ depthwise 3x3 (layers.py:56)
+__global__ void k_dwconv3x3(View in, const float* __restrict__ w9c, const float* __restrict__ bias,
+                            View out, int B, int H, int W, int C8) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = (long long)B * H * W;
+  if (idx >= M * C8) return;
+  long long m = idx / C8;
+  int c = (int)(idx % C8) * 8;
+  int C = in.C;
+  int w = (int)(m % W);
+  int h = (int)((m / W) % H);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    if ((unsigned)(h + dy) >= (unsigned)H) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      if ((unsigned)(w + dx) >= (unsigned)W) continue;
+      float v[8];
+      ld3x8(in, m + (long long)dy * W + dx, c, v);
+      const float* wt = w9c + ((dy + 1) * 3 + (dx + 1)) * C + c;
+      float4 w0 = *reinterpret_cast<const float4*>(wt);
+      float4 w1 = *reinterpret_cast<const float4*>(wt + 4);
+      acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+      acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+      acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+      acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = add_rn(acc[i], bias[c + i]);
+  st3x8(out, m, c, acc);
+}
+void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, int H, int W,
+               cudaStream_t st) {
+  int C8 = in.C / 8;
+  long long n = (long long)B * H * W * C8;
+  k_dwconv3x3<<<cdiv(n, 256), 256, 0, st>>>(in, w9c, bias, out, B, H, W, C8);
+}
+
+// ------------------------------------------------------------------ im2col (k x k, stride, pad)
+__global__ void k_im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, int Ho,
+                         int Wo, int tap_stride, int col_off, int C8) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long Mo = (long long)B * Ho * Wo;
+  int taps = k * k;
+  if (idx >= Mo * taps * C8) return;
+  int c = (int)(idx % C8) * 8;
+  long long t = idx / C8;
+  int tap = (int)(t % taps);
+  long long mo = t / taps;
+  int wo = (int)(mo % Wo);
+  int ho = (int)((mo / Wo) % Ho);
+  int b = (int)(mo / ((long long)Wo * Ho));
+  int hi = ho * stride - pad + tap / k, wi = wo * stride - pad + tap % k;
+  uint4 z = make_uint4(0, 0, 0, 0), a = z, bb = z, cc = z;
+  if ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W) {
+    const bf16* q = in.p + (((long long)b * H + hi) * W + wi) * in.ld + c;
+    a = *reinterpret_cast<const uint4*>(q);
+    bb = *reinterpret_cast<const uint4*>(q + in.ps);
+    cc = *reinterpret_cast<const uint4*>(q + 2 * in.ps);
+  }
+  bf16* d = out.p + mo * out.ld + tap * tap_stride + col_off + c;
+  *reinterpret_cast<uint4*>(d) = a;
+  *reinterpret_cast<uint4*>(d + out.ps) = bb;
+  *reinterpret_cast<uint4*>(d + 2 * out.ps) = cc;
+}
+void im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, int Ho, int Wo,
+            int tap_stride, int col_off, cudaStream_t st) {
+  int C8 = in.C / 8;
+  long long n = (long long)B * Ho * Wo * k * k * C8;
+  k_im2col<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, H, W, k, stride, pad, Ho, Wo, tap_stride,
+                                         col_off, C8);
+}
+
+// ------------------------------------------------------------------ fp32 CUDA-core GEMM
+// out[m][n] = sum_k A[m][k] * W[n][k]; 64x64 tile, 256 threads, 4x4 outputs per thread with
+// columns tx, tx+16, tx+32, tx+48 so that in PACK_PAIR mode (tile = one 64-column group) a
+// thread holds both members of every chunk-add pair.  Validation backend + odd shapes.
+__global__ void __launch_bounds__(256) k_gemm_simt(View a, const bf16* __restrict__ wp, long long wps,
+                                                   int Kld, int K, long long M, Epi e) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  long long m0 = (long long)blockIdx.x * 64;
+  int n0 = blockIdx.y * 64;
+  int lr = tid >> 2, lk = (tid & 3) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    long long ar = m0 + lr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int k = k0 + lk + i;
+      As[lk + i][lr] = (ar < M && k < K) ? ld3(a, ar, k) : 0.0f;
+      const bf16* q = wp + (long long)(n0 + lr) * Kld + k;
+      Bs[lk + i][lr] = (k < Kld) ? join3(q[0], q[wps], q[2 * wps]) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float partner = (e.pack == PACK_PAIR && j < 2) ? acc[i][j + 2] : 0.0f;
+      epi_store(e, m, n0 + tx + 16 * j, acc[i][j], partner);
+    }
+  }
+}
+void gemm_simt(View a, const GemmW& w, const Epi& e, long long M, cudaStream_t st) {
+  dim3 grid(cdiv(M, 64), w.Npad / 64);
+  k_gemm_simt<<<grid, 256, 0, st>>>(a, w.w, (long long)w.Npad * w.Kld, w.Kld, w.K, M, e);
+}
+
+// ------------------------------------------------------------------ block reduction helper
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (wid == 0)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;  // valid in thread 0
+}
+
+// ------------------------------------------------------------------ likelihoods
+__device__ __forceinline__ float bits_old(float s, float sigma) {
+  // models/common_model.py:30-42: Normal(0, clamp(sigma)).cdf difference, log(p + 1e-5)
+  float sg = fminf(fmaxf(sigma, 1e-5f), 1e10f);
+  float inv = 1.0f / sg;
+  const float r2 = 1.41421356237309504880f;
+  float hi = mul_rn(0.5f, add_rn(1.0f, erff(mul_rn(add_rn(s, 0.5f), inv) / r2)));
+  float lo = mul_rn(0.5f, add_rn(1.0f, erff(mul_rn(sub_rn(s, 0.5f), inv) / r2)));
+  float p = sub_rn(hi, lo);
+  float b = mul_rn(logf(add_rn(p, 1e-5f)), -1.4426950408889634f);
+  return fmaxf(b, 0.0f);
+}
+__device__ __forceinline__ float nan_to_num(float v, float nanv, float pinf, float ninf) {
+  if (isnan(v)) return nanv;
+  if (isinf(v)) return v > 0 ? pinf : ninf;
+  return v;
+}
+__device__ __forceinline__ float bits_refactor(float s, float sigma) {
+  // refactor/common_model.py:37-68; the +-6 clamp is seg_video_model.py:347
+  s = fminf(fmaxf(s, -6.0f), 6.0f);
+  s = nan_to_num(s, 0.0f, 1e4f, -1e4f);
+  float sg = nan_to_num(sigma, 1e-5f, 1e10f, 1e-5f);
+  sg = fminf(fmaxf(sg, 1e-5f), 1e10f);
+  float inv = 1.0f / sg;
+  float zh = fminf(fmaxf(mul_rn(add_rn(s, 0.5f), inv), -12.0f), 12.0f);
+  float zl = fminf(fmaxf(mul_rn(sub_rn(s, 0.5f), inv), -12.0f), 12.0f);
+  const float r2 = 1.41421356237309504880f;
+  float p = mul_rn(0.5f, sub_rn(erff(zh / r2), erff(zl / r2)));
+  p = nan_to_num(p, 0.0f, 0.0f, 0.0f);
+  p = fmaxf(p, 1e-9f);
+  return -log2f(p);
+}
+
+__global__ void k_gaussian_bits(const float* __restrict__ sym, const float* __restrict__ sigma,
+                                float* __restrict__ bits, long long n, int formula) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bits[i] = formula ? bits_refactor(sym[i], sigma[i]) : bits_old(sym[i], sigma[i]);
+}
+void gaussian_bits(const float* sym, const float* sigma, float* bits, long long n, int formula,
+                   cudaStream_t st) {
+  k_gaussian_bits<<<cdiv(n, 256), 256, 0, st>>>(sym, sigma, bits, n, formula);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// checkerboard owner step of element (h, w, c)   (models/common_model.py:101-114,152-169)
+__device__ __forceinline__ int prior_owner(int scheme, int h, int w, int c, int C) {
+  if (scheme == 2) return (h + w + (c >= C / 2 ? 1 : 0)) & 1;
+  const int own[4][4] = {{0, 3, 2, 1}, {3, 0, 1, 2}, {2, 1, 0, 3}, {1, 2, 3, 0}};  // [quarter][pos]
+  int pos = (h & 1) * 2 + (w & 1);
+  return own[c / (C / 4)][pos];
+}
+
+// One checkerboard step of compress_prior_2x / _4x (models/common_model.py:81-90,121-149,188-248)
+__global__ void k_prior_step(PriorArgs a) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = (long long)a.B * a.H * a.W;
+  if (idx >= M * a.C) return;
+  long long m = idx / a.C;
+  int c = (int)(idx % a.C);
+  int w = (int)(m % a.W), h = (int)((m / a.W) % a.H);
+  int owner = prior_owner(a.scheme, h, w, c, a.C);
+  if (owner != a.step) {
+    if (a.step == 0) st3(a.yh, m, c, 0.0f);
+    return;
+  }
+  float y = ld3(a.y, m, c);
+  float ys, sg, mu;
+  if (a.scheme == 2) {
+    float q = fmaxf(ld3(a.params, m, c), 0.5f);          // inference.py:29-33
+    ys = mul_rn(y, 1.0f / q);
+    if (a.step == 0) { sg = ld3(a.params, m, a.C + c); mu = ld3(a.params, m, 2 * a.C + c); }
+  } else {
+    float qe = add_rn(mul_rn(sigmoidf_(ld3(a.params, m, 0)), 1.5f), 0.5f);   // common_model.py:178-180
+    ys = mul_rn(y, qe);
+    if (a.step == 0) { sg = ld3(a.params, m, 2 + c); mu = ld3(a.params, m, 2 + a.C + c); }
+  }
+  if (a.step > 0) { sg = ld3(a.sp, m, c); mu = ld3(a.sp, m, a.C + c); }
+  float s = rintf(sub_rn(ys, mu));                        // torch.round = half-to-even
+  st3(a.yh, m, c, add_rn(s, mu));
+  a.sym[idx] = s;
+  a.sig[idx] = sg;
+}
+void prior_step(const PriorArgs& a, cudaStream_t st) {
+  long long n = (long long)a.B * a.H * a.W * a.C;
+  k_prior_step<<<cdiv(n, 256), 256, 0, st>>>(a);
+}
+
+__global__ void k_prior_finish(PriorArgs a, View y_hat, int formula, double* bits_acc) {
+  long long per = (long long)a.H * a.W * a.C;
+  int b = blockIdx.y;
+  double local = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long idx = (long long)b * per + i;
+    long long m = idx / a.C;
+    int c = (int)(idx % a.C);
+    float q;
+    if (a.scheme == 2) q = fmaxf(ld3(a.params, m, c), 0.5f);
+    else q = add_rn(mul_rn(sigmoidf_(ld3(a.params, m, 1)), 1.5f), 0.5f);
+    st3(y_hat, m, c, mul_rn(ld3(a.yh, m, c), q));         // inference.py:35-38
+    float s = a.sym[idx], sg = a.sig[idx];
+    local += (double)(formula ? bits_refactor(s, sg) : bits_old(s, sg));
+  }
+  double tot = block_sum(local);
+  if (threadIdx.x == 0) atomicAdd(&bits_acc[b], tot);
+}
+void prior_finish(const PriorArgs& a, View y_hat, int formula, double* bits_acc, cudaStream_t st) {
+  long long per = (long long)a.H * a.W * a.C;
+  unsigned gx = cdiv(per, 256 * 4);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, a.B);
+  k_prior_finish<<<grid, 256, 0, st>>>(a, y_hat, formula, bits_acc);
+}
+
+// Bitparm chain (entropy_models.py:84-106) -> sigmoid (:139-150)
+__device__ __forceinline__ float bitparm_cdf(float v, const BitparmRow& t, int c) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float h = t.p[3 * k][c], b = t.p[3 * k + 1][c];
+    float sp = (h > 20.0f) ? h : log1pf(expf(h));          // F.softplus
+    v = add_rn(mul_rn(v, sp), b);
+    if (k < 3) v = add_rn(v, mul_rn(tanhf(v), tanhf(t.p[3 * k + 2][c])));
+  }
+  return sigmoidf_(v);
+}
+__global__ void k_round_z_bits(View z, View z_hat, long long per, int C, BitparmRow t,
+                               double* bits_acc) {
+  int b = blockIdx.y;
+  double local = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long idx = (long long)b * per + i;
+    long long m = idx / C;
+    int c = (int)(idx % C);
+    float zr = rintf(ld3(z, m, c));
+    st3(z_hat, m, c, zr);
+    float p = sub_rn(bitparm_cdf(add_rn(zr, 0.5f), t, c), bitparm_cdf(sub_rn(zr, 0.5f), t, c));
+    float bits = fmaxf(mul_rn(logf(add_rn(p, 1e-5f)), -1.4426950408889634f), 0.0f);
+    local += (double)bits;
+  }
+  double tot = block_sum(local);
+  if (threadIdx.x == 0) atomicAdd(&bits_acc[b], tot);
+}
+void round_z_bits(View z, View z_hat, int B, int HW, int C, BitparmRow t, double* bits_acc,
+                  cudaStream_t st) {
+  long long per = (long long)HW * C;
+  unsigned gx = cdiv(per, 256 * 4);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, B);
+  k_round_z_bits<<<grid, 256, 0, st>>>(z, z_hat, per, C, t, bits_acc);
+}
+
+__global__ void k_finalize_bpp(const double* by, const double* bz, float* bpp3, int B, float pixels) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float y = (float)by[b] / pixels, z = (float)bz[b] / pixels;
+  bpp3[3 * b] = add_rn(y, z);
+  bpp3[3 * b + 1] = y;
+  bpp3[3 * b + 2] = z;
+}
+void finalize_bpp(const double* by, const double* bz, float* bpp3, int B, int pixels, cudaStream_t st) {
+  k_finalize_bpp<<<cdiv(B, 64), 64, 0, st>>>(by, bz, bpp3, B, (float)pixels);
+}
+
+// ------------------------------------------------------------------ mask conditioning
+__global__ void k_film(View y, View gb, View out, long long M, int C) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int C8 = C / 8;
+  if (idx >= M * C8) return;
+  long long m = idx / C8;
+  int c = (int)(idx % C8) * 8;
+  float v[8], g[8], b[8];
+  ld3x8(y, m, c, v);
+  ld3x8(gb, m, c, g);
+  ld3x8(gb, m, C + c, b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = add_rn(mul_rn(v[i], add_rn(1.0f, g[i])), b[i]);  // seg_video_model.py:327-328
+  st3x8(out, m, c, v);
+}
+void film(View y, View gb, View out, long long M, int C, cudaStream_t st) {
+  k_film<<<cdiv(M * (C / 8), 256), 256, 0, st>>>(y, gb, out, M, C);
+}
+
+// F.adaptive_avg_pool2d to (H/16, W/16) + clamp(0,1)  (seg_video_model_fast.py:306-307)
+__global__ void k_avgpool16_clamp(const float* __restrict__ mask, float* __restrict__ out, int B,
+                                  int H, int W) {
+  int Wo = W / 16, Ho = H / 16;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * Ho * Wo) return;
+  int wo = (int)(idx % Wo), ho = (int)((idx / Wo) % Ho), b = (int)(idx / ((long long)Wo * Ho));
+  const float* src = mask + ((long long)b * H + ho * 16) * W + wo * 16;
+  float s = 0.0f;
+  for (int y = 0; y < 16; ++y) {
+    const float4* r = reinterpret_cast<const float4*>(src + (long long)y * W);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      float4 v = r[x];
+      s = add_rn(s, v.x); s = add_rn(s, v.y); s = add_rn(s, v.z); s = add_rn(s, v.w);
+    }
+  }
+  s = s / 256.0f;
+  out[idx] = fminf(fmaxf(s, 0.0f), 1.0f);
+}
+void avgpool16_clamp(const float* mask, float* out, int B, int H, int W, cudaStream_t st) {
+  long long n = (long long)B * (H / 16) * (W / 16);
+  k_avgpool16_clamp<<<cdiv(n, 128), 128, 0, st>>>(mask, out, B, H, W);
+}
+
+// MaskFiLM: 3x3 (1->16) + ReLU + 1x1 (16->2C), then hyper_in = y*(1+gamma)+beta
+// (seg_video_model_fast.py:159-180,312-314).  One block per pixel, one thread per channel.
+__global__ void k_maskfilm_apply(const float* __restrict__ m, View y, View out,
+                                 const float* __restrict__ w0, const float* __restrict__ b0,
+                                 const float* __restrict__ w2, const float* __restrict__ b2, int H,
+                                 int W, int C) {
+  __shared__ float hid[16];
+  long long pix = blockIdx.x;
+  int w = (int)(pix % W), h = (int)((pix / W) % H);
+  if (threadIdx.x < 16) {
+    float acc = 0.0f;
+    if (m) {
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          if ((unsigned)(h + dy) >= (unsigned)H || (unsigned)(w + dx) >= (unsigned)W) continue;
+          acc = fmaf(m[pix + dy * W + dx], w0[threadIdx.x * 9 + (dy + 1) * 3 + dx + 1], acc);
+        }
+    }
+    hid[threadIdx.x] = fmaxf(add_rn(acc, b0[threadIdx.x]), 0.0f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float g = 0.0f, b = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      g = fmaf(hid[k], w2[c * 16 + k], g);
+      b = fmaf(hid[k], w2[(C + c) * 16 + k], b);
+    }
+    g = add_rn(g, b2[c]);
+    b = add_rn(b, b2[C + c]);
+    float v = ld3(y, pix, c);
+    st3(out, pix, c, add_rn(mul_rn(v, add_rn(1.0f, g)), b));
+  }
+}
+void maskfilm_apply(const float* m, View y, View out, const float* w0, const float* b0,
+                    const float* w2, const float* b2, int B, int H, int W, int C, cudaStream_t st) {
+  k_maskfilm_apply<<<(unsigned)((long long)B * H * W), 128, 0, st>>>(m, y, out, w0, b0, w2, b2, H, W, C);
+}
+
+// F.interpolate(bilinear, align_corners=False) by exactly 1/8 and 8 (mask_predictor.py:35,44)
+__global__ void k_bilinear_down8(const float* __restrict__ in, float* __restrict__ out, int B, int H,
+                                 int W) {
+  int Ho = H / 8, Wo = W / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * Ho * Wo) return;
+  int wo = (int)(idx % Wo), ho = (int)((idx / Wo) % Ho), b = (int)(idx / ((long long)Wo * Ho));
+  const float* p = in + ((long long)b * H + ho * 8 + 3) * W + wo * 8 + 3;
+  float top = add_rn(mul_rn(0.5f, p[0]), mul_rn(0.5f, p[1]));
+  float bot = add_rn(mul_rn(0.5f, p[W]), mul_rn(0.5f, p[W + 1]));
+  out[idx] = add_rn(mul_rn(0.5f, top), mul_rn(0.5f, bot));
+}
+void bilinear_down8(const float* in, float* out, int B, int H, int W, cudaStream_t st) {
+  long long n = (long long)B * (H / 8) * (W / 8);
+  k_bilinear_down8<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, H, W);
+}
+__global__ void k_bilinear_up8(const float* __restrict__ in, float* __restrict__ out, int B, int h,
+                               int w) {
+  int Ho = h * 8, Wo = w * 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * Ho * Wo) return;
+  int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho), b = (int)(idx / ((long long)Wo * Ho));
+  float sy = fmaxf(sub_rn(mul_rn(0.125f, add_rn((float)oy, 0.5f)), 0.5f), 0.0f);
+  float sx = fmaxf(sub_rn(mul_rn(0.125f, add_rn((float)ox, 0.5f)), 0.5f), 0.0f);
+  int y0 = (int)sy, x0 = (int)sx;
+  int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  float ly1 = sub_rn(sy, (float)y0), lx1 = sub_rn(sx, (float)x0);
+  float ly0 = sub_rn(1.0f, ly1), lx0 = sub_rn(1.0f, lx1);
+  const float* p = in + (long long)b * h * w;
+  float top = add_rn(mul_rn(lx0, p[y0 * w + x0]), mul_rn(lx1, p[y0 * w + x1]));
+  float bot = add_rn(mul_rn(lx0, p[y1 * w + x0]), mul_rn(lx1, p[y1 * w + x1]));
+  out[idx] = add_rn(mul_rn(ly0, top), mul_rn(ly1, bot));
+}
+void bilinear_up8(const float* in, float* out, int B, int h, int w, cudaStream_t st) {
+  long long n = (long long)B * h * 8 * w * 8;
+  k_bilinear_up8<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, h, w);
+}
+
+__global__ void k_conv3x3_c1(const float* __restrict__ in, const float* __restrict__ wt,
+                             const float* __restrict__ bias, View out, int B, int H, int W, int C) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = (long long)B * H * W;
+  if (idx >= M * C) return;
+  long long m = idx / C;
+  int c = (int)(idx % C);
+  int w = (int)(m % W), h = (int)((m / W) % H);
+  float acc = 0.0f;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      if ((unsigned)(h + dy) >= (unsigned)H || (unsigned)(w + dx) >= (unsigned)W) continue;
+      acc = fmaf(in[m + dy * W + dx], wt[c * 9 + (dy + 1) * 3 + dx + 1], acc);
+    }
+  st3(out, m, c, add_rn(acc, bias[c]));
+}
+void conv3x3_c1(const float* in, const float* w, const float* b, View out, int B, int h, int w_,
+                int C, cudaStream_t st) {
+  long long n = (long long)B * h * w_ * C;
+  k_conv3x3_c1<<<cdiv(n, 256), 256, 0, st>>>(in, w, b, out, B, h, w_, C);
+}
+
+__global__ void k_conv1x1_to1(View in, const float* __restrict__ wt, const float* __restrict__ bias,
+                              float* __restrict__ out, long long M, int K) {
+  long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float acc = 0.0f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(ld3(in, m, k), wt[k], acc);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[m] = add_rn(acc, bias[0]);
+}
+void conv1x1_to1(View in, const float* w, const float* b, float* out, long long M, int K,
+                 cudaStream_t st) {
+  k_conv1x1_to1<<<cdiv(M * 32, 256), 256, 0, st>>>(in, w, b, out, M, K);
+}
+
+// ------------------------------------------------------------------ caller-side statistics
+// trainer_seg_video_model.py:655-660 (_roi_mse), :904-934 (mse), bits from bpp.
+__global__ void k_frame_stats(double* stats, const float* __restrict__ xh, const float* __restrict__ x,
+                              const float* __restrict__ mask, long long HW, long long n) {
+  double se = 0.0, rse = 0.0, rn = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float d = sub_rn(xh[i], x[i]);
+    float d2 = mul_rn(d, d);
+    se += (double)d2;
+    if (mask) {
+      long long b = i / (3 * HW);
+      if (mask[b * HW + (i % HW)] > 0.0f) { rse += (double)d2; rn += 1.0; }
+    }
+  }
+  se = block_sum(se);
+  rse = block_sum(rse);
+  rn = block_sum(rn);
+  if (threadIdx.x == 0) {
+    atomicAdd(&stats[2], se);
+    if (mask) { atomicAdd(&stats[3], rse); atomicAdd(&stats[4], rn); }
+  }
+}
+__global__ void k_frame_stats_bits(double* stats, const float* bpp3, int B, double pixels, double n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (bpp3) {
+      double by = 0, bz = 0;
+      for (int b = 0; b < B; ++b) { by += (double)bpp3[3 * b + 1] * pixels; bz += (double)bpp3[3 * b + 2] * pixels; }
+      stats[0] += by; stats[1] += bz;
+    }
+    stats[5] += n;
+    stats[6] += (double)B;
+  }
+}
+void frame_stats(double* stats7, const float* x_hat, const float* x, const float* mask,
+                 const float* bpp3, int B, int H, int W, cudaStream_t st) {
+  long long HW = (long long)H * W, n = (long long)B * 3 * HW;
+  unsigned grid = (unsigned)min((long long)num_sms() * 8, (long long)cdiv(n, 256));
+  k_frame_stats<<<grid, 256, 0, st>>>(stats7, x_hat, x, mask, HW, n);
+  k_frame_stats_bits<<<1, 32, 0, st>>>(stats7, bpp3, B, (double)HW, (double)n);
+}
+
+}  // namespace dmc

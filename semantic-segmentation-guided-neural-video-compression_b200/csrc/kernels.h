@@ -1,0 +1,100 @@
+// Host-side launchers of every kernel of the engine.  All launch asynchronously on `st`.
+#pragma once
+#include "common.cuh"
+
+namespace dmc {
+
+int num_sms();
+
+// ---------------- weights ----------------
+// Packed contraction weight: S3 [3][Npad][Kld] bf16, K index = (kh*KW + kw)*Cin + ci.
+struct GemmW {
+  bf16* w = nullptr;
+  float* bias = nullptr;   // [Npad], packed order, zero on padding
+  int N = 0, K = 0;        // logical (N = cout, K = cin*kh*kw)
+  int ncols = 0;           // packed columns before tile padding (pair / shuffle layouts included)
+  int Npad = 0, Kld = 0;   // allocated rows (multiple of 64 and of BN) / row pitch (multiple of 64)
+  int pack = PACK_PLAIN;
+  int BN = 128;            // tcgen05 N tile this weight was padded for
+  int Cg = 0, Cg_pad = 0;  // PACK_SHUF2
+  void* tmap = nullptr;    // host copy of the CUtensorMap (128 B) for the tcgen05 path
+};
+void pack_gemm_weight(const float* w_oihw, int cout, int cin, int kh, int kw, const GemmW& g,
+                      cudaStream_t st);
+void pack_gemm_bias(const float* bias, int cout, const GemmW& g, cudaStream_t st);   // nullptr -> zeros
+// depthwise 3x3: (C,1,3,3) -> [9][C] fp32
+void pack_dw_weight(const float* w, float* out9c, int C, cudaStream_t st);
+
+// ---------------- layout conversion ----------------
+// (B,Cimg,H,W) fp32 NCHW -> S3 [B*H/8*W/8, Cimg*64], channel = c*64 + dy*8 + dx (F.pixel_unshuffle)
+void unshuffle8_in(const float* x, View out, int B, int Cimg, int H, int W, cudaStream_t st);
+// fp32 row-major [M, Cimg*64] (ld) -> (B,Cimg,H,W) NCHW, clamped to [0,1] (F.pixel_shuffle + clamp)
+void shuffle8_out(const float* in, int ld, float* x, int B, int Cimg, int H, int W, cudaStream_t st);
+void nchw_to_s3(const float* x, View out, int B, int C, int H, int W, cudaStream_t st);
+void s3_to_nchw(View in, float* x, int B, int C, int H, int W, cudaStream_t st);
+void f32rows_to_nchw(const float* in, int ld, float* x, int B, int C, int H, int W, cudaStream_t st);
+void scale_cols(View in, const float* scale, View out, long long M, cudaStream_t st);
+void copy_view(View in, View out, long long M, cudaStream_t st);
+void finite_check(View v, long long M, int* flag, cudaStream_t st);
+
+// ---------------- convolution pieces ----------------
+void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, int H, int W,
+               cudaStream_t st);
+// dst columns: tap * tap_stride + col_off + c
+void im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, int Ho, int Wo,
+            int tap_stride, int col_off, cudaStream_t st);
+void gemm_simt(View a, const GemmW& w, const Epi& e, long long M, cudaStream_t st);
+
+// tcgen05 path (gemm_umma.cu).  `tmapA` is a host CUtensorMap built by make_tmap_act.
+int make_tmap_act(void* tmap_out, View a, long long M);                    // box 64 x 128
+int make_tmap_weight(void* tmap_out, const GemmW& w);                      // box 64 x BN
+int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int K, int nsplit,
+              cudaStream_t st);
+const char* umma_last_error();
+
+// ---------------- entropy model ----------------
+struct PriorArgs {
+  int scheme;          // 2 or 4 (checkerboard steps)
+  int step;
+  int B, H, W, C;
+  View y;              // latent y (after FiLM for `performance`)
+  View params;         // scheme 2: [q_dec | sigma0 | mu0] (3C); scheme 4: [qe, qd | sigma0 | mu0] (2+2C)
+  View sp;             // steps >= 1: spatial prior output [sigma | mu] (2C)
+  View yh;             // running y_hat (pre q_dec), C columns, written for owned elements
+  float* sym;          // [M, C] fp32
+  float* sig;          // [M, C] fp32
+};
+void prior_step(const PriorArgs& a, cudaStream_t st);
+// y_hat = yh * q_dec -> out; bits(sym, sig) summed per sample into bits_acc[b] (double)
+void prior_finish(const PriorArgs& a, View y_hat, int formula, double* bits_acc, cudaStream_t st);
+// z -> round -> z_hat (S3) + factorized bits; tables: 11 pointers to rows (C floats) for this qp:
+// f1.h f1.b f1.a f2.h f2.b f2.a f3.h f3.b f3.a f4.h f4.b
+struct BitparmRow { const float* p[11]; };
+void round_z_bits(View z, View z_hat, int B, int HW, int C, BitparmRow t, double* bits_acc,
+                  cudaStream_t st);
+void finalize_bpp(const double* bits_y, const double* bits_z, float* bpp3, int B, int pixels,
+                  cudaStream_t st);
+void gaussian_bits(const float* sym, const float* sigma, float* bits, long long n, int formula,
+                   cudaStream_t st);
+
+// ---------------- mask conditioning ----------------
+void film(View y, View gb, View out, long long M, int C, cudaStream_t st);   // y*(1+g)+b, gb=[g|b]
+// 16x16 block mean of an fp32 (B,1,H,W) map, clamped to [0,1] -> (B,H/16,W/16) fp32
+void avgpool16_clamp(const float* mask, float* out, int B, int H, int W, cudaStream_t st);
+// MaskFiLM (3x3 1->16, ReLU, 1x1 16->2C) + FiLM on y;  m == nullptr means an all-zero mask
+void maskfilm_apply(const float* m, View y, View out, const float* w0, const float* b0,
+                    const float* w2, const float* b2, int B, int H, int W, int C, cudaStream_t st);
+void bilinear_down8(const float* in, float* out, int B, int H, int W, cudaStream_t st);  // -> H/8
+void bilinear_up8(const float* in, float* out, int B, int h, int w, cudaStream_t st);    // -> 8h
+// 3x3 conv with a single input channel (mask_embed): fp32 map (B,h,w) -> S3 [M, C]
+void conv3x3_c1(const float* in, const float* w, const float* b, View out, int B, int h, int w_,
+                int C, cudaStream_t st);
+// 1x1 conv to a single channel: S3 [M,K] -> fp32 [M]
+void conv1x1_to1(View in, const float* w, const float* b, float* out, long long M, int K,
+                 cudaStream_t st);
+
+// ---------------- caller-side statistics ----------------
+void frame_stats(double* stats7, const float* x_hat, const float* x, const float* mask,
+                 const float* bpp3, int B, int H, int W, cudaStream_t st);
+
+}  // namespace dmc
