@@ -132,6 +132,17 @@ int dmc_op_depth_conv_block(const float* x, const float* const* weights12, const
 int dmc_op_gaussian_bits(const float* sym, const float* sigma, float* bits, int64_t n, int formula,
                          void* stream);
 
+/* ---- measurement support (bench.py) ---- */
+/* number of kernels this library has launched in this process so far */
+int64_t dmc_kernel_launches(void);
+/* While enabled, every contraction launch of this engine is bracketed by CUDA events on its
+ * stream.  dmc_profile_read synchronises, then returns the summed device time of those launches
+ * (ms), their count, and their algorithmic FLOPs (2*M*N*K with the convolution's logical sizes),
+ * and clears the record. */
+int dmc_profile_enable(dmc_engine* e, int on);
+int dmc_profile_read(dmc_engine* e, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops,
+                     double* issued_flops);
+
 int dmc_num_sms(void);
 const char* dmc_version(void);
 

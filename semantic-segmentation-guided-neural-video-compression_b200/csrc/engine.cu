@@ -126,6 +126,21 @@ struct dmc_engine {
   double* bits_z = nullptr;
   float* bpp_scratch = nullptr;
 
+  // measurement (dmc_profile_*): events around every contraction launch
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  double prof_flops = 0, prof_issued = 0;
+  void prof_begin(cudaStream_t st, double flops, double issued) {
+    cudaEvent_t a, b;
+    CUDA_OK(cudaEventCreate(&a));
+    CUDA_OK(cudaEventCreate(&b));
+    CUDA_OK(cudaEventRecord(a, st));
+    prof_events.emplace_back(a, b);
+    prof_flops += flops;
+    prof_issued += issued;
+  }
+  void prof_end(cudaStream_t st) { CUDA_OK(cudaEventRecord(prof_events.back().second, st)); }
+
   ~dmc_engine() {
     for (void* p : allocs) cudaFree(p);
   }
@@ -204,11 +219,11 @@ struct dmc_engine {
       g.BN = (g.ncols % 128 == 0) ? 128 : ((g.ncols % 96 == 0) ? 96 : 64);
     } else {
       g.ncols = cout;
+      // N tile <= 128: two fp32 accumulators per tile, double buffered, fill the 512 TMEM columns
       if (cout % 128 == 0) g.BN = 128;
-      else if (cout % 160 == 0) g.BN = 160;
       else if (cout % 96 == 0) g.BN = 96;
-      else if (cout % 64 == 0) g.BN = 64;
-      else g.BN = (cout > 96) ? 128 : (cout > 64 ? 96 : 64);
+      else if (cout <= 64) g.BN = 64;
+      else g.BN = (cout > 96) ? 128 : 96;
     }
     g.Npad = round_up(round_up(g.ncols, g.BN), 64);
     g.Kld = round_up(g.K, 64);
@@ -300,13 +315,19 @@ struct dmc_engine {
       op([self, tm, g, e, M, K, nsplit, table, sc](cudaStream_t st) {
         Epi ee = e;
         if (table) ee.scale = table + (size_t)self->cur.qp * sc;
+        double fl = 2.0 * (double)M * g->N * g->K;
+        if (self->profile) self->prof_begin(st, fl, fl * (nsplit == 3 ? 6 : 1));
         if (gemm_umma(tm, *g, ee, M, K, nsplit, st) != 0) fail("gemm_umma: %s", umma_last_error());
+        if (self->profile) self->prof_end(st);
       });
     } else {
       op([self, a, g, e, M, table, sc](cudaStream_t st) {
         Epi ee = e;
         if (table) ee.scale = table + (size_t)self->cur.qp * sc;
+        double fl = 2.0 * (double)M * g->N * g->K;
+        if (self->profile) self->prof_begin(st, fl, fl);
         gemm_simt(a, *g, ee, M, st);
+        if (self->profile) self->prof_end(st);
       });
     }
   }
@@ -1005,7 +1026,7 @@ int dmc_get_tap(dmc_engine* e, const char* name, float* dst, int64_t capacity, i
       if (shape4) { shape4[0] = a.B; shape4[1] = a.v.C; shape4[2] = a.H; shape4[3] = a.W; }
       if (!dst) return;
       if (capacity < a.M() * a.v.C) fail("tap '%s' needs %lld elements", name, a.M() * a.v.C);
-      if (a.v.C % 8 == 0 && (uintptr_t)a.v.p % 16 == 0) s3_to_nchw(a.v, dst, a.B, a.v.C, a.H, a.W, st);
+      if (a.v.ld % 8 == 0 && (uintptr_t)a.v.p % 16 == 0) s3_to_nchw(a.v, dst, a.B, a.v.C, a.H, a.W, st);
       else fail("tap '%s' has an unaligned layout", name);
       return;
     }
@@ -1026,6 +1047,33 @@ int dmc_frame_stats(double* stats7, const float* x_hat, const float* x, const fl
   return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
 }
 
+int64_t dmc_kernel_launches(void) { return (int64_t)launch_count(); }
+int dmc_profile_enable(dmc_engine* e, int on) {
+  if (!e) return DMC_E_INVALID;
+  e->profile = on != 0;
+  return DMC_OK;
+}
+int dmc_profile_read(dmc_engine* e, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops,
+                     double* issued_flops) {
+  if (!e) return DMC_E_INVALID;
+  return guarded(e, [&] {
+    CUDA_OK(cudaDeviceSynchronize());
+    double ms = 0;
+    for (auto& pr : e->prof_events) {
+      float t = 0;
+      CUDA_OK(cudaEventElapsedTime(&t, pr.first, pr.second));
+      ms += t;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_launches) *gemm_launches = (int64_t)e->prof_events.size();
+    if (gemm_flops) *gemm_flops = e->prof_flops;
+    if (issued_flops) *issued_flops = e->prof_issued;
+    e->prof_events.clear();
+    e->prof_flops = e->prof_issued = 0;
+  });
+}
 int dmc_num_sms(void) { return num_sms(); }
 const char* dmc_version(void) { return "dmc_b200 0.1 (sm_100a)"; }
 

@@ -7,9 +7,15 @@
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 ->
 //               fp32 in TMEM).  nsplit == 3 issues the 6 cross terms hh,hm,mh,hl,lh,mm per
 //               16-wide k step (fp32-grade product), nsplit == 1 issues hh only.
+//               The tensor core adds into its fp32 accumulator with truncation, a bias that grows
+//               with the number of adds (measured: ~0.2 ulp per MMA).  The dominant hh term
+//               therefore has its own accumulator and the five small terms (<= 2^-8 of it) share
+//               a second one; the epilogue adds the two in round-to-nearest fp32.  That cuts the
+//               truncating adds into the large accumulator 6x.
 //   warps 2..5  epilogue: tcgen05.ld the accumulator (lane == output row), bias / WSiLU /
 //               chunk-add pairing / residuals / per-channel scale, split back into S3 planes
-//               and store 16 B vectors.  TMEM is double buffered (columns 0 and 256) so the
+//               and store 16 B vectors.  TMEM is double buffered (column bases 0 and 256, each
+//               holding the main accumulator at +0 and the small-terms one at +128) so the
 //               epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -325,8 +331,9 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       const int nterms = (p.nsplit == 3) ? 6 : 1;
-      const int ta[6] = {0, 0, 1, 0, 2, 1};
-      const int tw[6] = {0, 1, 0, 2, 0, 1};
+      // term 0 = hi*hi -> main accumulator; terms 1..5 (smallest first) -> second accumulator
+      const int ta[6] = {0, 0, 2, 1, 0, 1};
+      const int tw[6] = {0, 2, 0, 1, 1, 0};
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const int buf = tcount & 1;
@@ -346,7 +353,8 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int t = 0; t < nterms; ++t) {
               const uint64_t ad = make_desc(sa + ta[t] * kATileBytes + ks * 32);
               const uint64_t bd = make_desc(sw + tw[t] * wTileBytes + ks * 32);
-              tc_mma(d_tmem, ad, bd, idesc, (kb | ks | t) ? 1u : 0u);
+              if (t == 0) tc_mma(d_tmem, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+              else tc_mma(d_tmem + 128u, ad, bd, idesc, (kb | ks | (t - 1)) ? 1u : 0u);
             }
           }
           tc_commit(bar_empty(s));
@@ -366,19 +374,31 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(bar_tfull(buf), tph, p.err, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 256u;
+      const bool two_acc = p.nsplit == 3;
+      auto load_chunk = [&](int c, uint32_t* r) {     // accumulator columns [c, c+32) of this row
+        tc_ld32(taddr + c, r);
+        if (two_acc) {
+          uint32_t s2[32];
+          tc_ld32(taddr + 128u + c, s2);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            r[i] = __float_as_uint(add_rn(__uint_as_float(r[i]), __uint_as_float(s2[i])));
+        } else {
+          tc_wait_ld();
+        }
+      };
       if (e.pack == PACK_PAIR) {
         for (int c0 = 0; c0 < p.BN; c0 += 64) {
           uint32_t r0[32], r1[32];
-          tc_ld32(taddr + c0, r0);
-          tc_ld32(taddr + c0 + 32, r1);
-          tc_wait_ld();
+          load_chunk(c0, r0);
+          load_chunk(c0 + 32, r1);
           epilogue_chunk(e, m, row_ok, n_idx + c0, r0, r1);
         }
       } else {
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
           uint32_t r0[32];
-          tc_ld32(taddr + c0, r0);
-          tc_wait_ld();
+          load_chunk(c0, r0);
           epilogue_chunk(e, m, row_ok, n_idx + c0, r0, r0);
         }
       }
@@ -414,7 +434,7 @@ int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int 
     cudaMalloc(&d_err, sizeof(int));
     cudaMemset(d_err, 0, sizeof(int));
   }
-  if (!w.tmap || (w.BN % 32) || w.BN > 256 || (e.pack == PACK_PAIR && (w.BN % 64))) {
+  if (!w.tmap || (w.BN % 32) || w.BN > (nsplit == 3 ? 128 : 256) || (e.pack == PACK_PAIR && (w.BN % 64))) {
     snprintf(g_umma_err, sizeof g_umma_err, "gemm_umma: unsupported weight tiling BN=%d", w.BN);
     return -1;
   }
@@ -440,7 +460,7 @@ int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int 
   CUtensorMap ta, tw;
   memcpy(&ta, tmapA, sizeof ta);
   memcpy(&tw, w.tmap, sizeof tw);
-  k_gemm_umma<<<grid, kThreads, smem, st>>>(ta, tw, e, p);
+  (note_launch(), k_gemm_umma)<<<grid, kThreads, smem, st>>>(ta, tw, e, p);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     snprintf(g_umma_err, sizeof g_umma_err, "k_gemm_umma launch: %s", cudaGetErrorString(err));

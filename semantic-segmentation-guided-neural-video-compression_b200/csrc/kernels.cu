@@ -10,6 +10,10 @@ namespace dmc {
 
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
+static long long g_launches = 0;
+void note_launch() { ++g_launches; }
+long long launch_count() { return g_launches; }
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -74,11 +78,11 @@ __global__ void k_pack_bias(const float* __restrict__ b, float* __restrict__ out
 void pack_gemm_weight(const float* w, int cout, int cin, int kh, int kw, const GemmW& g,
                       cudaStream_t st) {
   long long n = (long long)g.Npad * g.Kld;
-  k_pack_gemm_weight<<<cdiv(n, 256), 256, 0, st>>>(w, g.w, cout, cin, kh, kw, g.Npad, g.Kld, g.K,
+  (note_launch(), k_pack_gemm_weight)<<<cdiv(n, 256), 256, 0, st>>>(w, g.w, cout, cin, kh, kw, g.Npad, g.Kld, g.K,
                                                    g.pack, g.Cg, g.Cg_pad);
 }
 void pack_gemm_bias(const float* bias, int cout, const GemmW& g, cudaStream_t st) {
-  k_pack_bias<<<cdiv(g.Npad, 256), 256, 0, st>>>(bias, g.bias, cout, g.Npad, g.pack, g.Cg, g.Cg_pad);
+  (note_launch(), k_pack_bias)<<<cdiv(g.Npad, 256), 256, 0, st>>>(bias, g.bias, cout, g.Npad, g.pack, g.Cg, g.Cg_pad);
 }
 
 __global__ void k_pack_dw(const float* __restrict__ w, float* __restrict__ out, int C) {
@@ -88,7 +92,7 @@ __global__ void k_pack_dw(const float* __restrict__ w, float* __restrict__ out, 
   out[i] = w[c * 9 + tap];
 }
 void pack_dw_weight(const float* w, float* out9c, int C, cudaStream_t st) {
-  k_pack_dw<<<cdiv(9 * C, 256), 256, 0, st>>>(w, out9c, C);
+  (note_launch(), k_pack_dw)<<<cdiv(9 * C, 256), 256, 0, st>>>(w, out9c, C);
 }
 
 // ------------------------------------------------------------------ layout conversion
@@ -112,7 +116,7 @@ __global__ void k_unshuffle8_in(const float* __restrict__ x, View out, int B, in
 }
 void unshuffle8_in(const float* x, View out, int B, int Cimg, int H, int W, cudaStream_t st) {
   long long total = (long long)B * (H / 8) * Cimg * 8 * (W / 8);
-  k_unshuffle8_in<<<cdiv(total, 256), 256, 0, st>>>(x, out, B, Cimg, H, W);
+  (note_launch(), k_unshuffle8_in)<<<cdiv(total, 256), 256, 0, st>>>(x, out, B, Cimg, H, W);
 }
 
 __global__ void k_shuffle8_out(const float* __restrict__ in, int ld, float* __restrict__ x, int B,
@@ -141,7 +145,7 @@ __global__ void k_shuffle8_out(const float* __restrict__ in, int ld, float* __re
 }
 void shuffle8_out(const float* in, int ld, float* x, int B, int Cimg, int H, int W, cudaStream_t st) {
   long long total = (long long)B * Cimg * H * (W / 8);
-  k_shuffle8_out<<<cdiv(total, 256), 256, 0, st>>>(in, ld, x, B, Cimg, H, W);
+  (note_launch(), k_shuffle8_out)<<<cdiv(total, 256), 256, 0, st>>>(in, ld, x, B, Cimg, H, W);
 }
 
 // NCHW fp32 <-> S3 rows.  Thread = (pixel, 8 channels), pixel fastest so the NCHW side is coalesced.
@@ -160,7 +164,7 @@ __global__ void k_nchw_to_s3(const float* __restrict__ x, View out, int C, long 
 void nchw_to_s3(const float* x, View out, int B, int C, int H, int W, cudaStream_t st) {
   long long HW = (long long)H * W;
   dim3 grid(cdiv(HW, 256), (C + 7) / 8, B);
-  k_nchw_to_s3<<<grid, 256, 0, st>>>(x, out, C, HW);
+  (note_launch(), k_nchw_to_s3)<<<grid, 256, 0, st>>>(x, out, C, HW);
 }
 __global__ void k_s3_to_nchw(View in, float* __restrict__ x, int C, long long HW) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,7 +181,7 @@ __global__ void k_s3_to_nchw(View in, float* __restrict__ x, int C, long long HW
 void s3_to_nchw(View in, float* x, int B, int C, int H, int W, cudaStream_t st) {
   long long HW = (long long)H * W;
   dim3 grid(cdiv(HW, 256), (C + 7) / 8, B);
-  k_s3_to_nchw<<<grid, 256, 0, st>>>(in, x, C, HW);
+  (note_launch(), k_s3_to_nchw)<<<grid, 256, 0, st>>>(in, x, C, HW);
 }
 __global__ void k_f32rows_to_nchw(const float* __restrict__ in, int ld, float* __restrict__ x, int C,
                                   long long HW) {
@@ -189,7 +193,7 @@ __global__ void k_f32rows_to_nchw(const float* __restrict__ in, int ld, float* _
 void f32rows_to_nchw(const float* in, int ld, float* x, int B, int C, int H, int W, cudaStream_t st) {
   long long HW = (long long)H * W;
   dim3 grid(cdiv(HW, 256), C, B);
-  k_f32rows_to_nchw<<<grid, 256, 0, st>>>(in, ld, x, C, HW);
+  (note_launch(), k_f32rows_to_nchw)<<<grid, 256, 0, st>>>(in, ld, x, C, HW);
 }
 
 __global__ void k_scale_cols(View in, const float* __restrict__ scale, View out, long long M, int C8) {
@@ -206,8 +210,8 @@ __global__ void k_scale_cols(View in, const float* __restrict__ scale, View out,
   st3x8(out, m, c, v);
 }
 void scale_cols(View in, const float* scale, View out, long long M, cudaStream_t st) {
-  int C8 = in.C / 8;
-  k_scale_cols<<<cdiv(M * C8, 256), 256, 0, st>>>(in, scale, out, M, C8);
+  int C8 = (in.C + 7) / 8;   // a ragged tail stays inside the row pitch (ld is a multiple of 8)
+  (note_launch(), k_scale_cols)<<<cdiv(M * C8, 256), 256, 0, st>>>(in, scale, out, M, C8);
 }
 void copy_view(View in, View out, long long M, cudaStream_t st) { scale_cols(in, nullptr, out, M, st); }
 
@@ -227,7 +231,7 @@ __global__ void k_finite_check(View v, long long M, int C8, int* flag) {
 }
 void finite_check(View v, long long M, int* flag, cudaStream_t st) {
   int C8 = v.C / 8;
-  k_finite_check<<<cdiv(M * C8, 256), 256, 0, st>>>(v, M, C8, flag);
+  (note_launch(), k_finite_check)<<<cdiv(M * C8, 256), 256, 0, st>>>(v, M, C8, flag);
 }
 
 // ------------------------------------------------------------------ depthwise 3x3 (layers.py:56)
@@ -269,7 +273,7 @@ void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, in
                cudaStream_t st) {
   int C8 = in.C / 8;
   long long n = (long long)B * H * W * C8;
-  k_dwconv3x3<<<cdiv(n, 256), 256, 0, st>>>(in, w9c, bias, out, B, H, W, C8);
+  (note_launch(), k_dwconv3x3)<<<cdiv(n, 256), 256, 0, st>>>(in, w9c, bias, out, B, H, W, C8);
 }
 
 // ------------------------------------------------------------------ im2col (k x k, stride, pad)
@@ -303,7 +307,7 @@ void im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, 
             int tap_stride, int col_off, cudaStream_t st) {
   int C8 = in.C / 8;
   long long n = (long long)B * Ho * Wo * k * k * C8;
-  k_im2col<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, H, W, k, stride, pad, Ho, Wo, tap_stride,
+  (note_launch(), k_im2col)<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, H, W, k, stride, pad, Ho, Wo, tap_stride,
                                          col_off, C8);
 }
 
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(View a, const bf16* __restric
 }
 void gemm_simt(View a, const GemmW& w, const Epi& e, long long M, cudaStream_t st) {
   dim3 grid(cdiv(M, 64), w.Npad / 64);
-  k_gemm_simt<<<grid, 256, 0, st>>>(a, w.w, (long long)w.Npad * w.Kld, w.Kld, w.K, M, e);
+  (note_launch(), k_gemm_simt)<<<grid, 256, 0, st>>>(a, w.w, (long long)w.Npad * w.Kld, w.Kld, w.K, M, e);
 }
 
 // ------------------------------------------------------------------ block reduction helper
@@ -380,13 +384,18 @@ __device__ __forceinline__ double block_sum(double v) {
 }
 
 // ------------------------------------------------------------------ likelihoods
+// erf rounded from double: correctly rounded fp32, which is what the CPU reference's 1-ulp
+// vectorised erf returns almost everywhere; CUDA's 2-ulp erff flips the last bit often enough to
+// move p by whole quanta where p sits at the fp32 cancellation floor (p ~ 1e-7).
+__device__ __forceinline__ float erf_cr(float x) { return (float)erf((double)x); }
+
 __device__ __forceinline__ float bits_old(float s, float sigma) {
   // models/common_model.py:30-42: Normal(0, clamp(sigma)).cdf difference, log(p + 1e-5)
   float sg = fminf(fmaxf(sigma, 1e-5f), 1e10f);
   float inv = 1.0f / sg;
   const float r2 = 1.41421356237309504880f;
-  float hi = mul_rn(0.5f, add_rn(1.0f, erff(mul_rn(add_rn(s, 0.5f), inv) / r2)));
-  float lo = mul_rn(0.5f, add_rn(1.0f, erff(mul_rn(sub_rn(s, 0.5f), inv) / r2)));
+  float hi = mul_rn(0.5f, add_rn(1.0f, erf_cr(mul_rn(add_rn(s, 0.5f), inv) / r2)));
+  float lo = mul_rn(0.5f, add_rn(1.0f, erf_cr(mul_rn(sub_rn(s, 0.5f), inv) / r2)));
   float p = sub_rn(hi, lo);
   float b = mul_rn(logf(add_rn(p, 1e-5f)), -1.4426950408889634f);
   return fmaxf(b, 0.0f);
@@ -406,7 +415,7 @@ __device__ __forceinline__ float bits_refactor(float s, float sigma) {
   float zh = fminf(fmaxf(mul_rn(add_rn(s, 0.5f), inv), -12.0f), 12.0f);
   float zl = fminf(fmaxf(mul_rn(sub_rn(s, 0.5f), inv), -12.0f), 12.0f);
   const float r2 = 1.41421356237309504880f;
-  float p = mul_rn(0.5f, sub_rn(erff(zh / r2), erff(zl / r2)));
+  float p = mul_rn(0.5f, sub_rn(erf_cr(zh / r2), erf_cr(zl / r2)));
   p = nan_to_num(p, 0.0f, 0.0f, 0.0f);
   p = fmaxf(p, 1e-9f);
   return -log2f(p);
@@ -420,7 +429,7 @@ __global__ void k_gaussian_bits(const float* __restrict__ sym, const float* __re
 }
 void gaussian_bits(const float* sym, const float* sigma, float* bits, long long n, int formula,
                    cudaStream_t st) {
-  k_gaussian_bits<<<cdiv(n, 256), 256, 0, st>>>(sym, sigma, bits, n, formula);
+  (note_launch(), k_gaussian_bits)<<<cdiv(n, 256), 256, 0, st>>>(sym, sigma, bits, n, formula);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -465,7 +474,7 @@ __global__ void k_prior_step(PriorArgs a) {
 }
 void prior_step(const PriorArgs& a, cudaStream_t st) {
   long long n = (long long)a.B * a.H * a.W * a.C;
-  k_prior_step<<<cdiv(n, 256), 256, 0, st>>>(a);
+  (note_launch(), k_prior_step)<<<cdiv(n, 256), 256, 0, st>>>(a);
 }
 
 __global__ void k_prior_finish(PriorArgs a, View y_hat, int formula, double* bits_acc) {
@@ -492,7 +501,7 @@ void prior_finish(const PriorArgs& a, View y_hat, int formula, double* bits_acc,
   unsigned gx = cdiv(per, 256 * 4);
   if (gx < 1) gx = 1;
   dim3 grid(gx, a.B);
-  k_prior_finish<<<grid, 256, 0, st>>>(a, y_hat, formula, bits_acc);
+  (note_launch(), k_prior_finish)<<<grid, 256, 0, st>>>(a, y_hat, formula, bits_acc);
 }
 
 // Bitparm chain (entropy_models.py:84-106) -> sigmoid (:139-150)
@@ -530,7 +539,7 @@ void round_z_bits(View z, View z_hat, int B, int HW, int C, BitparmRow t, double
   unsigned gx = cdiv(per, 256 * 4);
   if (gx < 1) gx = 1;
   dim3 grid(gx, B);
-  k_round_z_bits<<<grid, 256, 0, st>>>(z, z_hat, per, C, t, bits_acc);
+  (note_launch(), k_round_z_bits)<<<grid, 256, 0, st>>>(z, z_hat, per, C, t, bits_acc);
 }
 
 __global__ void k_finalize_bpp(const double* by, const double* bz, float* bpp3, int B, float pixels) {
@@ -542,7 +551,7 @@ __global__ void k_finalize_bpp(const double* by, const double* bz, float* bpp3, 
   bpp3[3 * b + 2] = z;
 }
 void finalize_bpp(const double* by, const double* bz, float* bpp3, int B, int pixels, cudaStream_t st) {
-  k_finalize_bpp<<<cdiv(B, 64), 64, 0, st>>>(by, bz, bpp3, B, (float)pixels);
+  (note_launch(), k_finalize_bpp)<<<cdiv(B, 64), 64, 0, st>>>(by, bz, bpp3, B, (float)pixels);
 }
 
 // ------------------------------------------------------------------ mask conditioning
@@ -561,7 +570,7 @@ __global__ void k_film(View y, View gb, View out, long long M, int C) {
   st3x8(out, m, c, v);
 }
 void film(View y, View gb, View out, long long M, int C, cudaStream_t st) {
-  k_film<<<cdiv(M * (C / 8), 256), 256, 0, st>>>(y, gb, out, M, C);
+  (note_launch(), k_film)<<<cdiv(M * (C / 8), 256), 256, 0, st>>>(y, gb, out, M, C);
 }
 
 // F.adaptive_avg_pool2d to (H/16, W/16) + clamp(0,1)  (seg_video_model_fast.py:306-307)
@@ -586,7 +595,7 @@ __global__ void k_avgpool16_clamp(const float* __restrict__ mask, float* __restr
 }
 void avgpool16_clamp(const float* mask, float* out, int B, int H, int W, cudaStream_t st) {
   long long n = (long long)B * (H / 16) * (W / 16);
-  k_avgpool16_clamp<<<cdiv(n, 128), 128, 0, st>>>(mask, out, B, H, W);
+  (note_launch(), k_avgpool16_clamp)<<<cdiv(n, 128), 128, 0, st>>>(mask, out, B, H, W);
 }
 
 // MaskFiLM: 3x3 (1->16) + ReLU + 1x1 (16->2C), then hyper_in = y*(1+gamma)+beta
@@ -625,7 +634,7 @@ __global__ void k_maskfilm_apply(const float* __restrict__ m, View y, View out,
 }
 void maskfilm_apply(const float* m, View y, View out, const float* w0, const float* b0,
                     const float* w2, const float* b2, int B, int H, int W, int C, cudaStream_t st) {
-  k_maskfilm_apply<<<(unsigned)((long long)B * H * W), 128, 0, st>>>(m, y, out, w0, b0, w2, b2, H, W, C);
+  (note_launch(), k_maskfilm_apply)<<<(unsigned)((long long)B * H * W), 128, 0, st>>>(m, y, out, w0, b0, w2, b2, H, W, C);
 }
 
 // F.interpolate(bilinear, align_corners=False) by exactly 1/8 and 8 (mask_predictor.py:35,44)
@@ -642,7 +651,7 @@ __global__ void k_bilinear_down8(const float* __restrict__ in, float* __restrict
 }
 void bilinear_down8(const float* in, float* out, int B, int H, int W, cudaStream_t st) {
   long long n = (long long)B * (H / 8) * (W / 8);
-  k_bilinear_down8<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, H, W);
+  (note_launch(), k_bilinear_down8)<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, H, W);
 }
 __global__ void k_bilinear_up8(const float* __restrict__ in, float* __restrict__ out, int B, int h,
                                int w) {
@@ -663,7 +672,7 @@ __global__ void k_bilinear_up8(const float* __restrict__ in, float* __restrict__
 }
 void bilinear_up8(const float* in, float* out, int B, int h, int w, cudaStream_t st) {
   long long n = (long long)B * h * 8 * w * 8;
-  k_bilinear_up8<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, h, w);
+  (note_launch(), k_bilinear_up8)<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, h, w);
 }
 
 __global__ void k_conv3x3_c1(const float* __restrict__ in, const float* __restrict__ wt,
@@ -687,7 +696,7 @@ __global__ void k_conv3x3_c1(const float* __restrict__ in, const float* __restri
 void conv3x3_c1(const float* in, const float* w, const float* b, View out, int B, int h, int w_,
                 int C, cudaStream_t st) {
   long long n = (long long)B * h * w_ * C;
-  k_conv3x3_c1<<<cdiv(n, 256), 256, 0, st>>>(in, w, b, out, B, h, w_, C);
+  (note_launch(), k_conv3x3_c1)<<<cdiv(n, 256), 256, 0, st>>>(in, w, b, out, B, h, w_, C);
 }
 
 __global__ void k_conv1x1_to1(View in, const float* __restrict__ wt, const float* __restrict__ bias,
@@ -702,7 +711,7 @@ __global__ void k_conv1x1_to1(View in, const float* __restrict__ wt, const float
 }
 void conv1x1_to1(View in, const float* w, const float* b, float* out, long long M, int K,
                  cudaStream_t st) {
-  k_conv1x1_to1<<<cdiv(M * 32, 256), 256, 0, st>>>(in, w, b, out, M, K);
+  (note_launch(), k_conv1x1_to1)<<<cdiv(M * 32, 256), 256, 0, st>>>(in, w, b, out, M, K);
 }
 
 // ------------------------------------------------------------------ caller-side statistics
@@ -743,8 +752,8 @@ void frame_stats(double* stats7, const float* x_hat, const float* x, const float
                  const float* bpp3, int B, int H, int W, cudaStream_t st) {
   long long HW = (long long)H * W, n = (long long)B * 3 * HW;
   unsigned grid = (unsigned)min((long long)num_sms() * 8, (long long)cdiv(n, 256));
-  k_frame_stats<<<grid, 256, 0, st>>>(stats7, x_hat, x, mask, HW, n);
-  k_frame_stats_bits<<<1, 32, 0, st>>>(stats7, bpp3, B, (double)HW, (double)n);
+  (note_launch(), k_frame_stats)<<<grid, 256, 0, st>>>(stats7, x_hat, x, mask, HW, n);
+  (note_launch(), k_frame_stats_bits)<<<1, 32, 0, st>>>(stats7, bpp3, B, (double)HW, (double)n);
 }
 
 }  // namespace dmc

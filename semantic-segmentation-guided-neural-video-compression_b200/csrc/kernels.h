@@ -5,6 +5,8 @@
 namespace dmc {
 
 int num_sms();
+void note_launch();            // every kernel launch of the library is counted
+long long launch_count();
 
 // ---------------- weights ----------------
 // Packed contraction weight: S3 [3][Npad][Kld] bf16, K index = (kh*KW + kw)*Cin + ci.
