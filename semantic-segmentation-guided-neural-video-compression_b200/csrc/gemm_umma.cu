@@ -12,9 +12,10 @@
 //               therefore has its own accumulator and the five small terms (<= 2^-8 of it) share
 //               a second one; the epilogue adds the two in round-to-nearest fp32.  That cuts the
 //               truncating adds into the large accumulator 6x.
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (lane == output row), bias / WSiLU /
-//               chunk-add pairing / residuals / per-channel scale, split back into S3 planes
-//               and store 16 B vectors.  TMEM is double buffered (column bases 0 and 256, each
+//   warps 2..9  epilogue (two warps per TMEM lane quadrant, alternating 32-column chunks):
+//               tcgen05.ld the accumulator (lane == output row), bias / WSiLU / chunk-add pairing /
+//               residuals / per-channel scale, split back into S3 planes; residual loads and
+//               output stores are staged through shared memory so they are coalesced.  TMEM is double buffered (column bases 0 and 256, each
 //               holding the main accumulator at +0 and the small-terms one at +128) so the
 //               epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
@@ -177,10 +178,60 @@ struct UmmaParams {
 };
 
 constexpr int kATileBytes = 128 * 64 * 2;   // one plane of a 128 x 64 bf16 tile
-constexpr int kThreads = 192;
+constexpr int kThreads = 64 + 32 * 8;   // TMA warp, MMA warp, 8 epilogue warps
+
+// ---- epilogue of one 32-column chunk, executed by a whole warp (lane == accumulator row) ----
+// Global traffic is staged through a per-warp shared-memory tile (32 rows x 64 B payload, rows
+// padded to 80 B so both the row-wise and the 8-rows-x-4-slots access patterns are conflict-free or
+// 2-way): a warp-level access then covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 B,
+// which cuts the L1 wavefronts per tile 4x (the first version of this kernel was LSU-bound there).
+constexpr int kStageRowBytes = 80;
+constexpr int kStageBytes = 32 * kStageRowBytes;
+constexpr int kEpiWarps = 8;
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)
+               : "memory");
+  return v;
+}
+
+// t[i] (+)= plane values of the 32 columns [dcol, dcol+32) of this lane's row, loaded coalesced.
+__device__ __forceinline__ void staged_load_plane(const View& src, int plane, long long drow, bool row_ok,
+                                                  int dcol, int ncols, uint32_t stage, int lane, float* t,
+                                                  bool first) {
+  const int slot = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    const long long rr = __shfl_sync(0xffffffffu, drow, r);
+    const bool ok = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, r) && (slot * 8 < ncols);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (ok) val = *reinterpret_cast<const uint4*>(src.p + plane * src.ps + rr * src.ld + dcol + slot * 8);
+    st_shared_v4(stage + r * kStageRowBytes + slot * 16, val);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 q = ld_shared_v4(stage + lane * kStageRowBytes + j * 16);
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float lo = bf16lo(u[k]), hi = bf16hi(u[k]);
+      t[8 * j + 2 * k] = first ? lo : add_rn(t[8 * j + 2 * k], lo);
+      t[8 * j + 2 * k + 1] = first ? hi : add_rn(t[8 * j + 2 * k + 1], hi);
+    }
+  }
+  __syncwarp();
+}
 
 __device__ __forceinline__ void epilogue_chunk(const Epi& e, long long m, bool row_ok, int n0,
-                                               const uint32_t* r0, const uint32_t* r1) {
+                                               const uint32_t* r0, const uint32_t* r1, uint32_t stage,
+                                               int lane) {
   // destination of packed columns [n0, n0+32) (PACK_PAIR: [n0, n0+32) + partners [n0+32, n0+64))
   long long drow = m;
   int dcol = n0, limit = e.n_out;
@@ -196,7 +247,8 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, long long m, bool r
     long long b = t / e.H;
     drow = (b * (2 * e.H) + (2 * h + (g >> 1))) * (2LL * e.W) + (2 * w + (g & 1));
   }
-  if (!row_ok || dcol >= limit) return;
+  if (dcol >= limit) return;                       // warp-uniform
+  const int ncols = min(32, limit - dcol);         // multiple of 8, warp-uniform
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]);
@@ -223,40 +275,72 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, long long m, bool r
       v[i + 3] = add_rn(v[i + 3], apply_act(add_rn(__uint_as_float(r1[i + 3]), b.w), e.act));
     }
   }
+  // residuals: x = (lo + mid) + hi exactly as join3, then v += x
+  if (e.res1.p) {
+    float t[32];
+    staged_load_plane(e.res1, 2, drow, row_ok, dcol, ncols, stage, lane, t, true);
+    staged_load_plane(e.res1, 1, drow, row_ok, dcol, ncols, stage, lane, t, false);
+    staged_load_plane(e.res1, 0, drow, row_ok, dcol, ncols, stage, lane, t, false);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int c = dcol + 8 * j;
-    if (c + 8 > limit) break;
-    float* x = v + 8 * j;
-    if (e.res1.p) {
-      float t[8];
-      ld3x8(e.res1, drow, c, t);
+    for (int i = 0; i < 32; ++i) v[i] = add_rn(v[i], t[i]);
+  }
+  if (e.res2.p) {
+    float t[32];
+    staged_load_plane(e.res2, 2, drow, row_ok, dcol, ncols, stage, lane, t, true);
+    staged_load_plane(e.res2, 1, drow, row_ok, dcol, ncols, stage, lane, t, false);
+    staged_load_plane(e.res2, 0, drow, row_ok, dcol, ncols, stage, lane, t, false);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = add_rn(x[i], t[i]);
-    }
-    if (e.res2.p) {
-      float t[8];
-      ld3x8(e.res2, drow, c, t);
+    for (int i = 0; i < 32; ++i) v[i] = add_rn(v[i], t[i]);
+  }
+  if (e.scale) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = add_rn(x[i], t[i]);
+    for (int i = 0; i < 32; i += 4) {
+      if (i < ncols) {
+        float4 s4 = *reinterpret_cast<const float4*>(e.scale + dcol + i);
+        v[i] = mul_rn(v[i], s4.x); v[i + 1] = mul_rn(v[i + 1], s4.y);
+        v[i + 2] = mul_rn(v[i + 2], s4.z); v[i + 3] = mul_rn(v[i + 3], s4.w);
+      }
     }
-    if (e.scale) {
-      float4 s0 = *reinterpret_cast<const float4*>(e.scale + c);
-      float4 s1 = *reinterpret_cast<const float4*>(e.scale + c + 4);
-      x[0] = mul_rn(x[0], s0.x); x[1] = mul_rn(x[1], s0.y); x[2] = mul_rn(x[2], s0.z);
-      x[3] = mul_rn(x[3], s0.w); x[4] = mul_rn(x[4], s1.x); x[5] = mul_rn(x[5], s1.y);
-      x[6] = mul_rn(x[6], s1.z); x[7] = mul_rn(x[7], s1.w);
-    }
-    if (e.do_clamp) {
+  }
+  if (e.do_clamp) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = fminf(fmaxf(x[i], e.clamp_lo), e.clamp_hi);
+    for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], e.clamp_lo), e.clamp_hi);
+  }
+  if (e.out_f32 && row_ok) {                       // fp32 rows (2 launches per frame): direct stores
+    float* d = e.out_f32 + drow * e.ld_f32 + dcol;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)
+      if (i < ncols) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+  if (e.out.p) {
+    uint32_t ph[16], pm[16], pl[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      bf16 h0, m0, l0, h1, m1, l1;
+      split3(v[2 * i], h0, m0, l0);
+      split3(v[2 * i + 1], h1, m1, l1);
+      ph[i] = pack_bf16(h0, h1);
+      pm[i] = pack_bf16(m0, m1);
+      pl[i] = pack_bf16(l0, l1);
     }
-    if (e.out_f32) {
-      float* d = e.out_f32 + drow * e.ld_f32 + c;
-      *reinterpret_cast<float4*>(d) = make_float4(x[0], x[1], x[2], x[3]);
-      *reinterpret_cast<float4*>(d + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    const int slot = lane & 3;
+#pragma unroll
+    for (int plane = 0; plane < 3; ++plane) {
+      const uint32_t* q = plane == 0 ? ph : (plane == 1 ? pm : pl);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st_shared_v4(stage + lane * kStageRowBytes + j * 16, make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2);
+        const long long rr = __shfl_sync(0xffffffffu, drow, r);
+        const bool ok = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, r) && (slot * 8 < ncols);
+        const uint4 val = ld_shared_v4(stage + r * kStageRowBytes + slot * 16);
+        if (ok) *reinterpret_cast<uint4*>(e.out.p + plane * e.out.ps + rr * e.out.ld + dcol + slot * 8) = val;
+      }
+      __syncwarp();
     }
-    if (e.out.p) st3x8(e.out, drow, c, x);
   }
 }
 
@@ -276,6 +360,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   auto bar_tfull = [&](int b) { return barBase + 128u + 8u * b; };
   auto bar_tempty = [&](int b) { return barBase + 144u + 8u * b; };
   const uint32_t tmemSlot = barBase + 160u;
+  const uint32_t stageBase = barBase + 256u;          // kEpiWarps x kStageBytes of epilogue staging
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -286,7 +371,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull(b), 1);
-      mbar_init(bar_tempty(b), 4);
+      mbar_init(bar_tempty(b), kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -363,7 +448,9 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;           // two warps per quadrant split the column chunks
+    const uint32_t stage = stageBase + (uint32_t)(warp - 2) * kStageBytes;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int buf = tcount & 1;
@@ -389,17 +476,17 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       };
       if (e.pack == PACK_PAIR) {
-        for (int c0 = 0; c0 < p.BN; c0 += 64) {
+        for (int c0 = half * 64; c0 < p.BN; c0 += 128) {
           uint32_t r0[32], r1[32];
           load_chunk(c0, r0);
           load_chunk(c0 + 32, r1);
-          epilogue_chunk(e, m, row_ok, n_idx + c0, r0, r1);
+          epilogue_chunk(e, m, row_ok, n_idx + c0, r0, r1, stage, lane);
         }
       } else {
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
           uint32_t r0[32];
           load_chunk(c0, r0);
-          epilogue_chunk(e, m, row_ok, n_idx + c0, r0, r0);
+          epilogue_chunk(e, m, row_ok, n_idx + c0, r0, r0, stage, lane);
         }
       }
       tc_fence_before();
@@ -446,7 +533,8 @@ int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int 
   p.BN = w.BN;
   p.nsplit = nsplit;
   const int stage_bytes = nsplit * (kATileBytes + w.BN * 128);
-  int stages = (smem_max - 2048) / stage_bytes;
+  const int fixed = 1024 + 256 + kEpiWarps * kStageBytes;   // alignment slack + barriers + epilogue staging
+  int stages = (smem_max - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 1) {
     snprintf(g_umma_err, sizeof g_umma_err, "gemm_umma: stage of %d bytes does not fit", stage_bytes);
@@ -454,7 +542,7 @@ int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int 
   }
   p.stages = stages;
   p.err = d_err;
-  const int smem = stages * stage_bytes + 2048;
+  const int smem = stages * stage_bytes + fixed;
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
   CUtensorMap ta, tw;
