@@ -42,6 +42,7 @@ SIGNATURES = {
     "dmc_profile_enable": (c_int, [c_void_p, c_int]),
     "dmc_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), POINTER(c_double),
                                  POINTER(c_double)]),
+    "dmc_bench_gemm": (c_int, [c_int] * 8 + [POINTER(c_float)]),
     "dmc_num_sms": (c_int, []),
     "dmc_version": (c_char_p, []),
 }

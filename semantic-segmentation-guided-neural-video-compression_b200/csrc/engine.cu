@@ -56,7 +56,7 @@ struct Act {          // an S3 tensor with its geometry (rows = B*H*W)
 struct Conv {         // dense convolution lowered to a contraction
   GemmW g;
   int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap_half;
 };
 struct DW {
   float* w9c = nullptr;
@@ -230,8 +230,10 @@ struct dmc_engine {
     g.w = (bf16*)dalloc((size_t)3 * g.Npad * g.Kld * sizeof(bf16));
     g.bias = new_f32(g.Npad);
     g.tmap = &c->tmap;
+    g.tmap_half = &c->tmap_half;
     if (!simt()) {
-      if (make_tmap_weight(&c->tmap, g) != 0) fail("%s: %s", key.c_str(), umma_last_error());
+      if (make_tmap_weight(&c->tmap, g, g.BN) != 0) fail("%s: %s", key.c_str(), umma_last_error());
+      if (make_tmap_weight(&c->tmap_half, g, g.BN / 2) != 0) fail("%s: %s", key.c_str(), umma_last_error());
     }
     add_slot(key + ".weight", {cout, cin, k, k}, [c](const float* src, cudaStream_t st) {
       pack_gemm_weight(src, c->cout, c->cin, c->k, c->k, c->g, st);
@@ -1169,4 +1171,45 @@ extern "C" int dmc_op_gaussian_bits(const float* sym, const float* sigma, float*
   if (!sym || !sigma || !bits || n < 0) return DMC_E_INVALID;
   gaussian_bits(sym, sigma, bits, n, formula, (cudaStream_t)stream);
   return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
+}
+
+extern "C" int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int pair, int iters, int probe,
+                              float* ms_per_launch) {
+  return guarded(nullptr, [&] {
+    if (rows < 1 || k < 8 || n < 8 || iters < 1 || !ms_per_launch) fail("dmc_bench_gemm: bad arguments");
+    dmc_engine e;
+    e.variant = -1; e.B = 1; e.H = 1; e.W = rows;
+    e.prog = &e.prog_common;
+    Conv* c = e.add_conv("w", k, n, 1, 1, 0, mode == 3 ? PACK_PAIR : PACK_PLAIN);
+    CUDA_OK(cudaMemset(c->g.w, 0, (size_t)3 * c->g.Npad * c->g.Kld * sizeof(bf16)));
+    CUDA_OK(cudaMemset(c->g.bias, 0, sizeof(float) * c->g.Npad));
+    Act in = e.new_act(1, 1, rows, k);
+    Act out = e.new_act(1, 1, rows, mode == 3 ? n / 2 : n);
+    Act res = e.new_act(1, 1, rows, n);
+    CUDA_OK(cudaMemset(in.v.p, 0, (size_t)in.v.ps * 3 * sizeof(bf16)));
+    CUDA_OK(cudaMemset(res.v.p, 0, (size_t)res.v.ps * 3 * sizeof(bf16)));
+    EpiSpec s;
+    s.nsplit = nsplit;
+    if (mode == 1 || mode == 3) s.act = ACT_WSILU;
+    if (mode == 2) s.res1 = &res;
+    e.gemm(in, c, &out, s);
+    umma_set_pair(pair != 0);
+    umma_set_debug(probe);
+    cudaEvent_t a, b;
+    CUDA_OK(cudaEventCreate(&a));
+    CUDA_OK(cudaEventCreate(&b));
+    for (int i = 0; i < 3; ++i) e.run(e.prog_common, 0);
+    CUDA_OK(cudaEventRecord(a, 0));
+    for (int i = 0; i < iters; ++i) e.run(e.prog_common, 0);
+    CUDA_OK(cudaEventRecord(b, 0));
+    cudaError_t err = cudaEventSynchronize(b);
+    umma_set_debug(0);
+    umma_set_pair(true);
+    CUDA_OK(err);
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, a, b));
+    *ms_per_launch = ms / iters;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  });
 }

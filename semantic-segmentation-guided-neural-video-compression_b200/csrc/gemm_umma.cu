@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.h"
@@ -72,9 +73,9 @@ static int encode3d(void* out, const void* base, uint64_t d0, uint64_t d1, uint6
 int make_tmap_act(void* tmap_out, View a, long long M) {
   return encode3d(tmap_out, a.p, (uint64_t)a.C, (uint64_t)M, (uint64_t)a.ld * 2, (uint64_t)a.ps * 2, 128);
 }
-int make_tmap_weight(void* tmap_out, const GemmW& w) {
+int make_tmap_weight(void* tmap_out, const GemmW& w, int box_rows) {
   return encode3d(tmap_out, w.w, (uint64_t)w.Kld, (uint64_t)w.Npad, (uint64_t)w.Kld * 2,
-                  (uint64_t)w.Npad * w.Kld * 2, (uint32_t)w.BN);
+                  (uint64_t)w.Npad * w.Kld * 2, (uint32_t)box_rows);
 }
 
 // ------------------------------------------------------------------ device helpers (PTX)
@@ -174,6 +175,7 @@ struct UmmaParams {
   long long M;
   int m_tiles, n_tiles, k_blocks;
   int BN, nsplit, stages;
+  int dbg;     // probe switches: 1 = no TMA loads, 2 = no MMA issue, 4 = no epilogue global traffic
   int* err;
 };
 
@@ -181,12 +183,14 @@ constexpr int kATileBytes = 128 * 64 * 2;   // one plane of a 128 x 64 bf16 tile
 constexpr int kThreads = 64 + 32 * 8;   // TMA warp, MMA warp, 8 epilogue warps
 
 // ---- epilogue of one 32-column chunk, executed by a whole warp (lane == accumulator row) ----
-// Global traffic is staged through a per-warp shared-memory tile (32 rows x 64 B payload, rows
-// padded to 80 B so both the row-wise and the 8-rows-x-4-slots access patterns are conflict-free or
-// 2-way): a warp-level access then covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 B,
-// which cuts the L1 wavefronts per tile 4x (the first version of this kernel was LSU-bound there).
+// The epilogue is issue-bound (the first versions spent 30-60 warp instructions per output element,
+// more SM issue slots per tile than the 6144-cycle main loop), so everything here is written for
+// instruction count: packed bf16x2 conversions, a reciprocal-based WSiLU, row addresses computed once
+// per tile, no shuffles.  Global traffic is staged through a per-warp shared-memory tile (16 rows x
+// 64 B payload, rows padded to 80 B): a warp-level access covers 8 rows x 64 contiguous bytes
+// instead of 32 rows x 16 B, which cuts the L1 wavefronts per tile 4x.
 constexpr int kStageRowBytes = 80;
-constexpr int kStageBytes = 32 * kStageRowBytes;
+constexpr int kStageBytes = 16 * kStageRowBytes;   // rows pass through 16 at a time
 constexpr int kEpiWarps = 8;
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
@@ -199,53 +203,96 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
                : "memory");
   return v;
 }
-
-// t[i] (+)= plane values of the 32 columns [dcol, dcol+32) of this lane's row, loaded coalesced.
-__device__ __forceinline__ void staged_load_plane(const View& src, int plane, long long drow, bool row_ok,
-                                                  int dcol, int ncols, uint32_t stage, int lane, float* t,
-                                                  bool first) {
-  const int slot = lane & 3;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = i * 8 + (lane >> 2);
-    const long long rr = __shfl_sync(0xffffffffu, drow, r);
-    const bool ok = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, r) && (slot * 8 < ncols);
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (ok) val = *reinterpret_cast<const uint4*>(src.p + plane * src.ps + rr * src.ld + dcol + slot * 8);
-    st_shared_v4(stage + r * kStageRowBytes + slot * 16, val);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 q = ld_shared_v4(stage + lane * kStageRowBytes + j * 16);
-    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float lo = bf16lo(u[k]), hi = bf16hi(u[k]);
-      t[8 * j + 2 * k] = first ? lo : add_rn(t[8 * j + 2 * k], lo);
-      t[8 * j + 2 * k + 1] = first ? hi : add_rn(t[8 * j + 2 * k + 1], hi);
-    }
-  }
-  __syncwarp();
+// two floats -> packed bf16x2 (lo half = a), round to nearest even: one F2FP instruction
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// layers.py:8-10 silu(4x)/4 == x / (1 + exp(-4x)); the reciprocal is MUFU.RCP (<= 1 ulp) instead of
+// an IEEE division: <= 2 ulp from the reference's result, 10 instructions instead of ~30.
+__device__ __forceinline__ float wsilu_fast(float x) {
+  const float e = expf(mul_rn(-4.0f, x));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(add_rn(1.0f, e)));
+  return mul_rn(x, r);
+}
+__device__ __forceinline__ float act_fast(float v, int act) {
+  if (act == ACT_WSILU) return wsilu_fast(v);
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  return v;
 }
 
-__device__ __forceinline__ void epilogue_chunk(const Epi& e, long long m, bool row_ok, int n0,
-                                               const uint32_t* r0, const uint32_t* r1, uint32_t stage,
+// Rows of the staging passes this lane touches: row group i covers tile rows i*8 + lane/4.
+struct RowMap {
+  long long base[4];   // destination row (before the pixel-shuffle group offset)
+  bool ok[4];
+};
+
+// one S3 plane of 32 rows x 32 columns through the staging tile: t = g (first) or t += g
+template <bool kFirst>
+__device__ __forceinline__ void stage_plane_in(const uint4 (&g)[4], uint32_t wr, uint32_t rd, int lane, float* t) {
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    st_shared_v4(wr, g[2 * pass]);
+    st_shared_v4(wr + 8 * kStageRowBytes, g[2 * pass + 1]);
+    __syncwarp();
+    if ((lane >> 4) == pass) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 q = ld_shared_v4(rd + j * 16);
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float lo = bf16lo(u[k]), hi = bf16hi(u[k]);
+          t[8 * j + 2 * k] = kFirst ? lo : add_rn(t[8 * j + 2 * k], lo);
+          t[8 * j + 2 * k + 1] = kFirst ? hi : add_rn(t[8 * j + 2 * k + 1], hi);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// t[32] = hi+mid+lo of the 32 columns [dcol, dcol+32) of this lane's row of `src` ((lo+mid)+hi, exactly
+// join3).  All 12 global loads (3 planes x 4 row groups) are issued before the first use, so a
+// residual costs one memory round trip; the rows then pass through the staging tile 16 at a time.
+__device__ __forceinline__ void staged_load_s3(const View& src, const RowMap& rm, long long goff, int dcol,
+                                               int ncols, uint32_t stage, int lane, float* t) {
+  const int slot = lane & 3;
+  const bool col_ok = slot * 8 < ncols;
+  uint4 gh[4], gm[4], gl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bf16* q = src.p + (rm.base[i] + goff) * src.ld + dcol + slot * 8;
+    gh[i] = gm[i] = gl[i] = make_uint4(0, 0, 0, 0);
+    if (rm.ok[i] && col_ok) {
+      gh[i] = *reinterpret_cast<const uint4*>(q);
+      gm[i] = *reinterpret_cast<const uint4*>(q + src.ps);
+      gl[i] = *reinterpret_cast<const uint4*>(q + 2 * src.ps);
+    }
+  }
+  const uint32_t wr = stage + (lane >> 2) * kStageRowBytes + slot * 16;
+  const uint32_t rd = stage + (lane & 15) * kStageRowBytes;
+  stage_plane_in<true>(gl, wr, rd, lane, t);
+  stage_plane_in<false>(gm, wr, rd, lane, t);
+  stage_plane_in<false>(gh, wr, rd, lane, t);
+}
+
+// v: accumulator (+ partner for PACK_PAIR in r1) of columns [n0, n0+32) of this lane's row.
+__device__ __forceinline__ void epilogue_chunk(const Epi& e, const RowMap& rm, long long m_own, bool own_ok,
+                                               int n0, uint32_t* r0, const uint32_t* r1, uint32_t stage,
                                                int lane) {
   // destination of packed columns [n0, n0+32) (PACK_PAIR: [n0, n0+32) + partners [n0+32, n0+64))
-  long long drow = m;
   int dcol = n0, limit = e.n_out;
+  long long goff = 0;                              // pixel-shuffle group offset of the destination row
   if (e.pack == PACK_PAIR) {
     dcol = (n0 >> 6) * 32;
   } else if (e.pack == PACK_SHUF2) {
-    int g = n0 / e.Cg_pad;
+    const int g = n0 / e.Cg_pad;
     dcol = n0 - g * e.Cg_pad;
     limit = e.Cg;
-    int w = (int)(m % e.W);
-    long long t = m / e.W;
-    int h = (int)(t % e.H);
-    long long b = t / e.H;
-    drow = (b * (2 * e.H) + (2 * h + (g >> 1))) * (2LL * e.W) + (2 * w + (g & 1));
+    goff = (long long)(g >> 1) * (2LL * e.W) + (g & 1);
   }
   if (dcol >= limit) return;                       // warp-uniform
   const int ncols = min(32, limit - dcol);         // multiple of 8, warp-uniform
@@ -255,40 +302,35 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, long long m, bool r
   if (e.bias) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      float4 b = *reinterpret_cast<const float4*>(e.bias + n0 + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + i));
       v[i] = add_rn(v[i], b.x); v[i + 1] = add_rn(v[i + 1], b.y);
       v[i + 2] = add_rn(v[i + 2], b.z); v[i + 3] = add_rn(v[i + 3], b.w);
     }
   }
   if (e.act != ACT_NONE) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], e.act);
+    for (int i = 0; i < 32; ++i) v[i] = act_fast(v[i], e.act);
   }
   if (e.pack == PACK_PAIR) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e.bias) b = *reinterpret_cast<const float4*>(e.bias + n0 + 32 + i);
-      v[i] = add_rn(v[i], apply_act(add_rn(__uint_as_float(r1[i]), b.x), e.act));
-      v[i + 1] = add_rn(v[i + 1], apply_act(add_rn(__uint_as_float(r1[i + 1]), b.y), e.act));
-      v[i + 2] = add_rn(v[i + 2], apply_act(add_rn(__uint_as_float(r1[i + 2]), b.z), e.act));
-      v[i + 3] = add_rn(v[i + 3], apply_act(add_rn(__uint_as_float(r1[i + 3]), b.w), e.act));
+      if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + 32 + i));
+      v[i] = add_rn(v[i], act_fast(add_rn(__uint_as_float(r1[i]), b.x), e.act));
+      v[i + 1] = add_rn(v[i + 1], act_fast(add_rn(__uint_as_float(r1[i + 1]), b.y), e.act));
+      v[i + 2] = add_rn(v[i + 2], act_fast(add_rn(__uint_as_float(r1[i + 2]), b.z), e.act));
+      v[i + 3] = add_rn(v[i + 3], act_fast(add_rn(__uint_as_float(r1[i + 3]), b.w), e.act));
     }
   }
-  // residuals: x = (lo + mid) + hi exactly as join3, then v += x
   if (e.res1.p) {
     float t[32];
-    staged_load_plane(e.res1, 2, drow, row_ok, dcol, ncols, stage, lane, t, true);
-    staged_load_plane(e.res1, 1, drow, row_ok, dcol, ncols, stage, lane, t, false);
-    staged_load_plane(e.res1, 0, drow, row_ok, dcol, ncols, stage, lane, t, false);
+    staged_load_s3(e.res1, rm, goff, dcol, ncols, stage, lane, t);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = add_rn(v[i], t[i]);
   }
   if (e.res2.p) {
     float t[32];
-    staged_load_plane(e.res2, 2, drow, row_ok, dcol, ncols, stage, lane, t, true);
-    staged_load_plane(e.res2, 1, drow, row_ok, dcol, ncols, stage, lane, t, false);
-    staged_load_plane(e.res2, 0, drow, row_ok, dcol, ncols, stage, lane, t, false);
+    staged_load_s3(e.res2, rm, goff, dcol, ncols, stage, lane, t);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = add_rn(v[i], t[i]);
   }
@@ -296,7 +338,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, long long m, bool r
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       if (i < ncols) {
-        float4 s4 = *reinterpret_cast<const float4*>(e.scale + dcol + i);
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(e.scale + dcol + i));
         v[i] = mul_rn(v[i], s4.x); v[i + 1] = mul_rn(v[i + 1], s4.y);
         v[i + 2] = mul_rn(v[i + 2], s4.z); v[i + 3] = mul_rn(v[i + 3], s4.w);
       }
@@ -306,52 +348,122 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, long long m, bool r
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], e.clamp_lo), e.clamp_hi);
   }
-  if (e.out_f32 && row_ok) {                       // fp32 rows (2 launches per frame): direct stores
+  if (e.out_f32 && own_ok) {                       // fp32 rows (2 launches per frame): direct stores
+    long long drow = m_own;
+    if (e.pack == PACK_SHUF2) {
+      const int w = (int)(m_own % e.W);
+      const long long tt = m_own / e.W;
+      drow = ((tt / e.H) * (2 * e.H) + 2 * (int)(tt % e.H)) * (2LL * e.W) + 2 * w + goff;
+    }
     float* d = e.out_f32 + drow * e.ld_f32 + dcol;
 #pragma unroll
     for (int i = 0; i < 32; i += 4)
       if (i < ncols) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
   if (e.out.p) {
-    uint32_t ph[16], pm[16], pl[16];
+    // exact 3-way split, two elements per conversion: hi = bf16x2(v), mid = bf16x2(v - hi), lo = bf16x2(rest)
+    uint32_t* ph = r0;                              // the accumulator registers are dead by now
+    uint32_t pm[16], pl[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      bf16 h0, m0, l0, h1, m1, l1;
-      split3(v[2 * i], h0, m0, l0);
-      split3(v[2 * i + 1], h1, m1, l1);
-      ph[i] = pack_bf16(h0, h1);
-      pm[i] = pack_bf16(m0, m1);
-      pl[i] = pack_bf16(l0, l1);
+      const float a = v[2 * i], b = v[2 * i + 1];
+      const uint32_t h = cvt_bf16x2(a, b);
+      const float ra = sub_rn(a, bf16lo(h)), rb = sub_rn(b, bf16hi(h));
+      const uint32_t mm = cvt_bf16x2(ra, rb);
+      ph[i] = h;
+      pm[i] = mm;
+      pl[i] = cvt_bf16x2(sub_rn(ra, bf16lo(mm)), sub_rn(rb, bf16hi(mm)));
     }
     const int slot = lane & 3;
+    const bool col_ok = slot * 8 < ncols;
+    const uint32_t wr = stage + (lane & 15) * kStageRowBytes;
+    const uint32_t rd = stage + (lane >> 2) * kStageRowBytes + slot * 16;
+    bf16* dst[4];
 #pragma unroll
-    for (int plane = 0; plane < 3; ++plane) {
-      const uint32_t* q = plane == 0 ? ph : (plane == 1 ? pm : pl);
+    for (int i = 0; i < 4; ++i) dst[i] = e.out.p + (rm.base[i] + goff) * e.out.ld + dcol + slot * 8;
+    auto store_plane = [&](const uint32_t* q, long long poff) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        st_shared_v4(stage + lane * kStageRowBytes + j * 16, make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]));
-      __syncwarp();
+      for (int pass = 0; pass < 2; ++pass) {
+        if ((lane >> 4) == pass) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = i * 8 + (lane >> 2);
-        const long long rr = __shfl_sync(0xffffffffu, drow, r);
-        const bool ok = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, r) && (slot * 8 < ncols);
-        const uint4 val = ld_shared_v4(stage + r * kStageRowBytes + slot * 16);
-        if (ok) *reinterpret_cast<uint4*>(e.out.p + plane * e.out.ps + rr * e.out.ld + dcol + slot * 8) = val;
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(wr + j * 16, make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint4 val = ld_shared_v4(rd + i * 8 * kStageRowBytes);
+          if (rm.ok[2 * pass + i] && col_ok) *reinterpret_cast<uint4*>(dst[2 * pass + i] + poff) = val;
+        }
+        __syncwarp();
       }
-      __syncwarp();
-    }
+    };
+    store_plane(ph, 0);
+    store_plane(pm, e.out.ps);
+    store_plane(pl, 2 * e.out.ps);
   }
 }
 
+// ---- cluster / pair (cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {   // same offset in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                 uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// kPair == false: one CTA per 128 x BN tile (cta_group::1).
+// kPair == true : a cluster of two CTAs owns a 256 x BN tile (cta_group::2).  Each CTA loads its own
+//                 128 rows of A and HALF of the W tile (BN/2 rows); the leader CTA issues one
+//                 M=256 MMA that reads W from both CTAs' shared memory and writes each CTA's 128
+//                 accumulator rows into that CTA's TMEM.  L2->SM operand traffic per MMA drops to
+//                 3/4 and a stage shrinks from 96 KB to 72 KB, so the ring holds 3 stages.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
             const Epi e, const UmmaParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t wTileBytes = (uint32_t)p.BN * 128u;
+  const uint32_t base = smem_u32(smem_raw);
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const uint32_t wRows = kPair ? (uint32_t)p.BN / 2u : (uint32_t)p.BN;
+  const uint32_t wTileBytes = wRows * 128u;
   const uint32_t stageBytes = (uint32_t)p.nsplit * (kATileBytes + wTileBytes);
   const uint32_t barBase = base + (uint32_t)p.stages * stageBytes;
   // barriers: full[8] | empty[8] | tfull[2] | tempty[2] | tmem ptr
@@ -363,6 +475,10 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t stageBase = barBase + 256u;          // kEpiWarps x kStageBytes of epilogue staging
 
   if (warp == 0 && lane == 0) {
+    if (base & 1023u) {                               // SWIZZLE_128B tiles need 1024-byte alignment
+      if (p.err) atomicExch(p.err, 9);
+      __trap();
+    }
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     for (int s = 0; s < p.stages; ++s) {
@@ -371,56 +487,79 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull(b), 1);
-      mbar_init(bar_tempty(b), kEpiWarps);
+      mbar_init(bar_tempty(b), kEpiWarps * (kPair ? 2 : 1));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     const uint32_t ncols = 512;
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmemSlot),
-                 "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmemSlot), "r"(ncols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmemSlot), "r"(ncols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();                      // peer barriers are initialised before any remote use
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmemSlot) : "memory");
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // tile walk: (cluster of) CTA(s) `unit` takes tiles unit, unit + units, ...
+  const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int rowsPerTile = kPair ? 256 : 128;
+  const int total_tiles = p.m_tiles * p.n_tiles;      // m_tiles counts 256-row tiles when kPair
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_idx = (tile / p.n_tiles) * 128, n_idx = (tile % p.n_tiles) * p.BN;
+      for (int tile = unit; tile < total_tiles; tile += units) {
+        const int m_idx = (tile / p.n_tiles) * rowsPerTile + (int)rank * 128;
+        const int n_idx = (tile % p.n_tiles) * p.BN + (int)rank * (int)(kPair ? wRows : 0u);
         for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(bar_empty(s), ph ^ 1, p.err, 1);
-          mbar_expect_tx(bar_full(s), stageBytes);
           const uint32_t sa = base + s * stageBytes;
           const uint32_t sw = sa + p.nsplit * kATileBytes;
-          for (int pl = 0; pl < p.nsplit; ++pl) {
-            tma_load_3d(sa + pl * kATileBytes, &tmA, kb * 64, m_idx, pl, bar_full(s));
-            tma_load_3d(sw + pl * wTileBytes, &tmW, kb * 64, n_idx, pl, bar_full(s));
+          if (p.dbg & 1) {
+            if (leader) mbar_arrive(bar_full(s));
+          } else if (kPair) {
+            // both CTAs' bytes complete on the LEADER's barrier, which the leader arms for 2 stages' worth
+            if (leader) mbar_expect_tx(bar_full(s), 2u * stageBytes);
+            const uint32_t lbar = mapa(bar_full(s), 0);
+            for (int pl = 0; pl < p.nsplit; ++pl) {
+              tma_load_3d_pair(sa + pl * kATileBytes, &tmA, kb * 64, m_idx, pl, lbar);
+              tma_load_3d_pair(sw + pl * wTileBytes, &tmW, kb * 64, n_idx, pl, lbar);
+            }
+          } else {
+            mbar_expect_tx(bar_full(s), stageBytes);
+            for (int pl = 0; pl < p.nsplit; ++pl) {
+              tma_load_3d(sa + pl * kATileBytes, &tmA, kb * 64, m_idx, pl, bar_full(s));
+              tma_load_3d(sw + pl * wTileBytes, &tmW, kb * 64, n_idx, pl, bar_full(s));
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
-      // N>>3 at [17,23), M>>4 at [24,29)
+      // N>>3 at [17,23), M>>4 at [24,29)  (M = 256 for the pair)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
+                             ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
       const int nterms = (p.nsplit == 3) ? 6 : 1;
       // term 0 = hi*hi -> main accumulator; terms 1..5 (smallest first) -> second accumulator
       const int ta[6] = {0, 0, 2, 1, 0, 1};
       const int tw[6] = {0, 2, 0, 1, 1, 0};
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      for (int tile = unit; tile < total_tiles; tile += units, ++tcount) {
         const int buf = tcount & 1;
         const uint32_t tph = (tcount >> 1) & 1;
         mbar_wait(bar_tempty(buf), tph ^ 1, p.err, 2);
@@ -435,16 +574,21 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t sw = sa + p.nsplit * kATileBytes;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
+            if (p.dbg & 2) break;
             for (int t = 0; t < nterms; ++t) {
               const uint64_t ad = make_desc(sa + ta[t] * kATileBytes + ks * 32);
               const uint64_t bd = make_desc(sw + tw[t] * wTileBytes + ks * 32);
-              if (t == 0) tc_mma(d_tmem, ad, bd, idesc, (kb | ks) ? 1u : 0u);
-              else tc_mma(d_tmem + 128u, ad, bd, idesc, (kb | ks | (t - 1)) ? 1u : 0u);
+              const uint32_t d = t == 0 ? d_tmem : d_tmem + 128u;
+              const uint32_t acc = t == 0 ? ((kb | ks) ? 1u : 0u) : ((kb | ks | (t - 1)) ? 1u : 0u);
+              if (kPair) tc_mma_pair(d, ad, bd, idesc, acc);
+              else tc_mma(d, ad, bd, idesc, acc);
             }
           }
-          tc_commit(bar_empty(s));
+          if (kPair) tc_commit_pair(bar_empty(s));
+          else tc_commit(bar_empty(s));
         }
-        tc_commit(bar_tfull(buf));
+        if (kPair) tc_commit_pair(bar_tfull(buf));
+        else tc_commit(bar_tfull(buf));
       }
     }
   } else {
@@ -452,12 +596,25 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = (warp - 2) >> 2;           // two warps per quadrant split the column chunks
     const uint32_t stage = stageBase + (uint32_t)(warp - 2) * kStageBytes;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = unit; tile < total_tiles; tile += units, ++tcount) {
       const int buf = tcount & 1;
       const uint32_t tph = (tcount >> 1) & 1;
-      const long long m = (long long)(tile / p.n_tiles) * 128 + quad * 32 + lane;
+      const long long m_warp0 = (long long)(tile / p.n_tiles) * rowsPerTile + (long long)rank * 128 + quad * 32;
+      const long long m = m_warp0 + lane;
       const int n_idx = (tile % p.n_tiles) * p.BN;
-      const bool row_ok = m < p.M;
+      const bool row_ok = (m < p.M) && !(p.dbg & 4);
+      RowMap rm;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long mr = m_warp0 + i * 8 + (lane >> 2);
+        rm.ok[i] = (mr < p.M) && !(p.dbg & 4);
+        rm.base[i] = mr;
+        if (e.pack == PACK_SHUF2) {                  // nn.PixelShuffle(2): (b, h, w) -> (b, 2h, 2w) + group offset
+          const int w = (int)(mr % e.W);
+          const long long tt = mr / e.W;
+          rm.base[i] = ((tt / e.H) * (2 * e.H) + 2 * (int)(tt % e.H)) * (2LL * e.W) + 2 * w;
+        }
+      }
       mbar_wait(bar_tfull(buf), tph, p.err, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 256u;
@@ -480,40 +637,59 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t r0[32], r1[32];
           load_chunk(c0, r0);
           load_chunk(c0 + 32, r1);
-          epilogue_chunk(e, m, row_ok, n_idx + c0, r0, r1, stage, lane);
+          epilogue_chunk(e, rm, m, row_ok, n_idx + c0, r0, r1, stage, lane);
         }
       } else {
         for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
           uint32_t r0[32];
           load_chunk(c0, r0);
-          epilogue_chunk(e, m, row_ok, n_idx + c0, r0, r0, stage, lane);
+          epilogue_chunk(e, rm, m, row_ok, n_idx + c0, r0, r0, stage, lane);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty(buf));
+      if (lane == 0) {
+        if (!kPair || leader) mbar_arrive(bar_tempty(buf));
+        else mbar_arrive_cluster(mapa(bar_tempty(buf), 0));   // the leader's MMA thread waits for both CTAs
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();                      // nobody leaves while the peer can still touch its smem
   if (warp == 1) {
     const uint32_t ncols = 512;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols)
-                 : "memory");
+    if (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
+}
+
+static int g_umma_dbg = 0;
+void umma_set_debug(int mask) { g_umma_dbg = mask; }
+static bool g_pair_enabled = true;
+void umma_set_pair(bool on) { g_pair_enabled = on; }
+static void read_env_once() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* v = getenv("DMC_UMMA_PAIR");     // DMC_UMMA_PAIR=0 forces the one-CTA kernel (A/B runs)
+  if (v && v[0] == '0') g_pair_enabled = false;
 }
 
 int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int K, int nsplit,
               cudaStream_t st) {
   static int smem_max = 0;
   static int* d_err = nullptr;
+  read_env_once();
   if (!smem_max) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (cudaFuncSetAttribute(k_gemm_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) !=
-        cudaSuccess) {
+    if (cudaFuncSetAttribute(k_gemm_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gemm_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) {
       snprintf(g_umma_err, sizeof g_umma_err, "cudaFuncSetAttribute(max dynamic smem=%d) failed", smem_max);
       smem_max = 0;
       return -1;
@@ -525,15 +701,17 @@ int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int 
     snprintf(g_umma_err, sizeof g_umma_err, "gemm_umma: unsupported weight tiling BN=%d", w.BN);
     return -1;
   }
+  // the pair kernel needs BN/2 rows of W per CTA to be a whole number of 8-row swizzle groups
+  const bool pair = g_pair_enabled && w.tmap_half && (w.BN % 32 == 0) && M > 128;
   UmmaParams p;
   p.M = M;
-  p.m_tiles = (int)((M + 127) / 128);
+  p.m_tiles = pair ? (int)((M + 255) / 256) : (int)((M + 127) / 128);
   p.n_tiles = (w.ncols + w.BN - 1) / w.BN;
   p.k_blocks = (K + 63) / 64;
   p.BN = w.BN;
   p.nsplit = nsplit;
-  const int stage_bytes = nsplit * (kATileBytes + w.BN * 128);
-  const int fixed = 1024 + 256 + kEpiWarps * kStageBytes;   // alignment slack + barriers + epilogue staging
+  const int stage_bytes = nsplit * (kATileBytes + (pair ? w.BN / 2 : w.BN) * 128);
+  const int fixed = 256 + kEpiWarps * kStageBytes;   // barriers + epilogue staging (base is 1024-aligned)
   int stages = (smem_max - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 1) {
@@ -541,15 +719,38 @@ int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int 
     return -1;
   }
   p.stages = stages;
+  p.dbg = g_umma_dbg;
   p.err = d_err;
   const int smem = stages * stage_bytes + fixed;
-  int grid = p.m_tiles * p.n_tiles;
-  if (grid > num_sms()) grid = num_sms();
   CUtensorMap ta, tw;
   memcpy(&ta, tmapA, sizeof ta);
-  memcpy(&tw, w.tmap, sizeof tw);
-  (note_launch(), k_gemm_umma)<<<grid, kThreads, smem, st>>>(ta, tw, e, p);
-  cudaError_t err = cudaGetLastError();
+  memcpy(&tw, pair ? w.tmap_half : w.tmap, sizeof tw);
+  cudaError_t err;
+  note_launch();
+  if (pair) {
+    int grid = 2 * p.m_tiles * p.n_tiles;
+    const int cap = num_sms() & ~1;
+    if (grid > cap) grid = cap;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, k_gemm_umma<true>, ta, tw, e, p);
+  } else {
+    int grid = p.m_tiles * p.n_tiles;
+    if (grid > num_sms()) grid = num_sms();
+    k_gemm_umma<false><<<grid, kThreads, smem, st>>>(ta, tw, e, p);
+    err = cudaGetLastError();
+  }
   if (err != cudaSuccess) {
     snprintf(g_umma_err, sizeof g_umma_err, "k_gemm_umma launch: %s", cudaGetErrorString(err));
     return -1;

@@ -19,7 +19,8 @@ struct GemmW {
   int pack = PACK_PLAIN;
   int BN = 128;            // tcgen05 N tile this weight was padded for
   int Cg = 0, Cg_pad = 0;  // PACK_SHUF2
-  void* tmap = nullptr;    // host copy of the CUtensorMap (128 B) for the tcgen05 path
+  void* tmap = nullptr;    // host CUtensorMap (128 B), box = 64 k x BN rows (one-CTA kernel)
+  void* tmap_half = nullptr;  // box = 64 k x BN/2 rows (CTA-pair kernel: each CTA loads half of W)
 };
 void pack_gemm_weight(const float* w_oihw, int cout, int cin, int kh, int kw, const GemmW& g,
                       cudaStream_t st);
@@ -49,7 +50,9 @@ void gemm_simt(View a, const GemmW& w, const Epi& e, long long M, cudaStream_t s
 
 // tcgen05 path (gemm_umma.cu).  `tmapA` is a host CUtensorMap built by make_tmap_act.
 int make_tmap_act(void* tmap_out, View a, long long M);                    // box 64 x 128
-int make_tmap_weight(void* tmap_out, const GemmW& w);                      // box 64 x BN
+int make_tmap_weight(void* tmap_out, const GemmW& w, int box_rows);        // box 64 x box_rows
+void umma_set_debug(int mask);  // probe switches of k_gemm_umma (bench tool only)
+void umma_set_pair(bool on);   // use the cta_group::2 kernel where possible (default on)
 int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int K, int nsplit,
               cudaStream_t st);
 const char* umma_last_error();

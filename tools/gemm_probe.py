@@ -1,0 +1,30 @@
+"""Times single contraction launches in isolation and with parts of the kernel switched off
+(no TMA / no MMA / no epilogue traffic) to see which of the three pipelines bounds it."""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402,F401
+import dmc_b200 as D  # noqa: E402
+
+lib = D._capi.load()
+torch.zeros(1, device="cuda")
+M = 38400
+SHAPES = [("dc0 256->256 plain", 256, 256, 0), ("dc0 256->256 wsilu", 256, 256, 1), ("dc3 256->256 +res", 256, 256, 2),
+          ("ffn0 256->1024 pair", 256, 1024, 3), ("ffn2 512->256 +res", 512, 256, 2), ("head 320->192", 320, 192, 0)]
+PROBES = [(0, "full"), (4, "no-epi-mem"), (2, "no-mma"), (1, "no-tma"), (3, "no-tma,no-mma"), (6, "no-mma,no-epi"),
+          (5, "no-tma,no-epi")]
+for name, k, n, mode in SHAPES:
+    flops = 2.0 * M * k * n * 6
+    for pair in (0, 1):
+        row = []
+        for probe, pname in PROBES:
+            ms = ctypes.c_float()
+            rc = lib.dmc_bench_gemm(M, k, n, mode, 3, pair, 20, probe, ctypes.byref(ms))
+            if rc != 0:
+                row.append(f"{pname}=ERR({lib.dmc_last_error(None).decode()[:60]})")
+                break
+            row.append(f"{pname}={ms.value * 1e3:7.1f}us")
+        print(f"{name:22s} pair={pair} issued={flops / 1e9:6.1f}GF  " + "  ".join(row), flush=True)
