@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -56,7 +57,7 @@ struct Act {          // an S3 tensor with its geometry (rows = B*H*W)
 struct Conv {         // dense convolution lowered to a contraction
   GemmW g;
   int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
-  CUtensorMap tmap, tmap_half;
+  CUtensorMap tmap, tmap_half, tmap_s3;
 };
 struct DW {
   float* w9c = nullptr;
@@ -146,6 +147,11 @@ struct dmc_engine {
   }
 
   bool simt() const { return flags & DMC_FLAG_SIMT_GEMM; }
+  bool use_s3 = s3_default();    // route qualifying contractions to the specialised CTA-pair kernel
+  static bool s3_default() {
+    const char* v = getenv("DMC_GEMM_S3");          // DMC_GEMM_S3=0 keeps every launch on the general kernel (A/B runs)
+    return !(v && v[0] == '0');
+  }
   bool keep_taps() const { return flags & DMC_FLAG_KEEP_TAPS; }
 
   // ------------------------------------------------------------ memory
@@ -211,7 +217,7 @@ struct dmc_engine {
     if (pack == PACK_PAIR) {
       int c2 = cout / 2;
       g.ncols = (c2 + 31) / 32 * 64;
-      g.BN = (g.ncols % 128 == 0) ? 128 : 64;
+      g.BN = (g.ncols > 64) ? 128 : 64;      // an odd number of 64-column groups leaves half a tile of zero rows
     } else if (pack == PACK_SHUF2) {
       g.Cg = cout / 4;
       g.Cg_pad = round_up(g.Cg, 32);
@@ -231,7 +237,9 @@ struct dmc_engine {
     g.bias = new_f32(g.Npad);
     g.tmap = &c->tmap;
     g.tmap_half = &c->tmap_half;
+    g.tmap_s3 = &c->tmap_s3;
     if (!simt()) {
+      if (make_tmap_s3_weight(&c->tmap_s3, g) != 0) fail("%s: %s", key.c_str(), gemm_s3_last_error());
       if (make_tmap_weight(&c->tmap, g, g.BN) != 0) fail("%s: %s", key.c_str(), umma_last_error());
       if (make_tmap_weight(&c->tmap_half, g, g.BN / 2) != 0) fail("%s: %s", key.c_str(), umma_last_error());
     }
@@ -309,7 +317,31 @@ struct dmc_engine {
     int sc = spec.scale_C;
     int nsplit = spec.nsplit;
     dmc_engine* self = this;
-    if (use_umma) {
+    auto tma_ok = [](const View& v) { return (uintptr_t)v.p % 16 == 0 && v.ld % 8 == 0 && v.ps % 8 == 0; };
+    if (use_umma && use_s3 && gemm_s3_supports(*g, e, nsplit) && tma_ok(out->v) &&
+        (!spec.res1 || tma_ok(spec.res1->v))) {
+      CUtensorMap* tm3[3];
+      for (auto& t : tm3) {
+        tmaps.emplace_back(new CUtensorMap());
+        t = tmaps.back().get();
+      }
+      if (make_tmap_s3_act(tm3[0], a, M) != 0) fail("gemm A map: %s", gemm_s3_last_error());
+      if (make_tmap_s3_rows(tm3[1], out->v, e.n_out, M) != 0) fail("gemm out map: %s", gemm_s3_last_error());
+      if (spec.res1 && make_tmap_s3_rows(tm3[2], spec.res1->v, e.n_out, M) != 0)
+        fail("gemm residual map: %s", gemm_s3_last_error());
+      CUtensorMap* ta = tm3[0];
+      CUtensorMap* to = tm3[1];
+      CUtensorMap* tr = spec.res1 ? tm3[2] : nullptr;
+      int K = g->K;
+      op([self, ta, to, tr, g, e, M, K, table, sc](cudaStream_t st) {
+        Epi ee = e;
+        if (table) ee.scale = table + (size_t)self->cur.qp * sc;
+        double fl = 2.0 * (double)M * g->N * g->K;
+        if (self->profile) self->prof_begin(st, fl, fl * 6);
+        if (gemm_s3(ta, *g, ee, to, tr, M, K, st) != 0) fail("gemm_s3: %s", gemm_s3_last_error());
+        if (self->profile) self->prof_end(st);
+      });
+    } else if (use_umma) {
       tmaps.emplace_back(new CUtensorMap());
       CUtensorMap* tm = tmaps.back().get();
       if (make_tmap_act(tm, a, M) != 0) fail("gemm A map: %s", umma_last_error());
@@ -1180,6 +1212,7 @@ extern "C" int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int 
     dmc_engine e;
     e.variant = -1; e.B = 1; e.H = 1; e.W = rows;
     e.prog = &e.prog_common;
+    e.use_s3 = pair == 2;
     Conv* c = e.add_conv("w", k, n, 1, 1, 0, mode == 3 ? PACK_PAIR : PACK_PLAIN);
     CUDA_OK(cudaMemset(c->g.w, 0, (size_t)3 * c->g.Npad * c->g.Kld * sizeof(bf16)));
     CUDA_OK(cudaMemset(c->g.bias, 0, sizeof(float) * c->g.Npad));
@@ -1195,6 +1228,7 @@ extern "C" int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int 
     e.gemm(in, c, &out, s);
     umma_set_pair(pair != 0);
     umma_set_debug(probe);
+    gemm_s3_set_debug(probe);
     cudaEvent_t a, b;
     CUDA_OK(cudaEventCreate(&a));
     CUDA_OK(cudaEventCreate(&b));
@@ -1204,6 +1238,7 @@ extern "C" int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int 
     CUDA_OK(cudaEventRecord(b, 0));
     cudaError_t err = cudaEventSynchronize(b);
     umma_set_debug(0);
+    gemm_s3_set_debug(0);
     umma_set_pair(true);
     CUDA_OK(err);
     float ms = 0;

@@ -21,6 +21,7 @@ struct GemmW {
   int Cg = 0, Cg_pad = 0;  // PACK_SHUF2
   void* tmap = nullptr;    // host CUtensorMap (128 B), box = 64 k x BN rows (one-CTA kernel)
   void* tmap_half = nullptr;  // box = 64 k x BN/2 rows (CTA-pair kernel: each CTA loads half of W)
+  void* tmap_s3 = nullptr;    // box = 32 k x BN/2 rows x 3 planes, SWIZZLE_64B (gemm_s3.cu)
 };
 void pack_gemm_weight(const float* w_oihw, int cout, int cin, int kh, int kw, const GemmW& g,
                       cudaStream_t st);
@@ -56,6 +57,17 @@ void umma_set_pair(bool on);   // use the cta_group::2 kernel where possible (de
 int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int K, int nsplit,
               cudaStream_t st);
 const char* umma_last_error();
+
+// Specialised CTA-pair kernel with a TMA epilogue (gemm_s3.cu): S3 out, plain / chunk-add-pair column
+// layouts, <= 1 residual, 6-term product.  gemm_s3_supports() says whether a launch qualifies.
+int make_tmap_s3_act(void* tmap_out, View a, long long M);                 // box 32 x 128 x 3
+int make_tmap_s3_weight(void* tmap_out, const GemmW& w);                   // box 32 x BN/2 x 3
+int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M);      // box 16 x 32 x 3
+bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit);
+void gemm_s3_set_debug(int mask);
+int gemm_s3(const void* tmapA, const GemmW& w, const Epi& e, const void* tmapOut, const void* tmapRes,
+            long long M, int K, cudaStream_t st);
+const char* gemm_s3_last_error();
 
 // ---------------- entropy model ----------------
 struct PriorArgs {

@@ -14,11 +14,12 @@ torch.zeros(1, device="cuda")
 M = 38400
 SHAPES = [("dc0 256->256 plain", 256, 256, 0), ("dc0 256->256 wsilu", 256, 256, 1), ("dc3 256->256 +res", 256, 256, 2),
           ("ffn0 256->1024 pair", 256, 1024, 3), ("ffn2 512->256 +res", 512, 256, 2), ("head 320->192", 320, 192, 0)]
-PROBES = [(0, "full"), (4, "no-epi-mem"), (2, "no-mma"), (1, "no-tma"), (3, "no-tma,no-mma"), (6, "no-mma,no-epi"),
-          (5, "no-tma,no-epi")]
+PROBES = [(0, "full"), (4, "no-epi-mem"), (12, "no-epi"), (2, "no-mma"), (3, "no-tma,no-mma"), (13, "mma-only"),
+          (14, "tma-only")]
+KERNELS = [int(a) for a in sys.argv[1:]] or [0, 2]          # 0 one-CTA general kernel, 1 its CTA-pair variant, 2 gemm_s3
 for name, k, n, mode in SHAPES:
     flops = 2.0 * M * k * n * 6
-    for pair in (0, 1):
+    for pair in KERNELS:
         row = []
         for probe, pname in PROBES:
             ms = ctypes.c_float()
@@ -27,4 +28,4 @@ for name, k, n, mode in SHAPES:
                 row.append(f"{pname}=ERR({lib.dmc_last_error(None).decode()[:60]})")
                 break
             row.append(f"{pname}={ms.value * 1e3:7.1f}us")
-        print(f"{name:22s} pair={pair} issued={flops / 1e9:6.1f}GF  " + "  ".join(row), flush=True)
+        print(f"{name:22s} kernel={pair} issued={flops / 1e9:6.1f}GF  " + "  ".join(row), flush=True)
