@@ -145,10 +145,15 @@ int dmc_profile_read(dmc_engine* e, double* gemm_ms, int64_t* gemm_launches, dou
 
 /* Times one contraction launch in isolation (bench / profiling tool): rows x k -> n on zero-filled
  * S3 buffers, `iters` launches between two CUDA events.  mode: 0 plain, 1 +WSiLU, 2 +residual,
- * 3 chunk-add pair layout (n = 4C, writes n/2 columns).  pair: 1 = cta_group::2 kernel, 0 = one CTA.
- * probe: 0 normal; bit0 no TMA loads, bit1 no MMA issue, bit2 no epilogue global traffic. */
+ * 3 chunk-add pair layout (n = 4C, writes n/2 columns).  pair: 0 = general kernel on one CTA, 1 = its
+ * cta_group::2 variant, 2 = the specialised CTA-pair kernel of gemm_s3.cu.
+ * probe: 0 normal; bit0 no TMA loads, bit1 no MMA issue, bit2 no epilogue global traffic, bit3 no
+ * epilogue at all (gemm_s3 only). */
 int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int pair, int iters, int probe,
                    float* ms_per_launch);
+
+/* Times the depthwise 3x3 kernel alone on zero-filled S3 buffers (bench / profiling tool). */
+int dmc_bench_dwconv(int batch, int height, int width, int channels, int iters, float* ms_per_launch);
 
 int dmc_num_sms(void);
 const char* dmc_version(void);

@@ -1248,3 +1248,31 @@ extern "C" int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int 
     cudaEventDestroy(b);
   });
 }
+
+extern "C" int dmc_bench_dwconv(int batch, int height, int width, int channels, int iters, float* ms_per_launch) {
+  return guarded(nullptr, [&] {
+    if (batch < 1 || height < 1 || width < 1 || channels % 8 || iters < 1 || !ms_per_launch)
+      fail("dmc_bench_dwconv: bad arguments");
+    dmc_engine e;
+    e.variant = -1; e.B = batch; e.H = height; e.W = width;
+    Act in = e.new_act(batch, height, width, channels), out = e.new_act(batch, height, width, channels);
+    CUDA_OK(cudaMemset(in.v.p, 0, (size_t)in.v.ps * 3 * sizeof(bf16)));
+    float* w = e.new_f32((size_t)9 * channels);
+    float* b = e.new_f32(channels);
+    CUDA_OK(cudaMemset(w, 0, sizeof(float) * 9 * channels));
+    CUDA_OK(cudaMemset(b, 0, sizeof(float) * channels));
+    cudaEvent_t t0, t1;
+    CUDA_OK(cudaEventCreate(&t0));
+    CUDA_OK(cudaEventCreate(&t1));
+    for (int i = 0; i < 3; ++i) dwconv3x3(in.v, w, b, out.v, batch, height, width, 0);
+    CUDA_OK(cudaEventRecord(t0, 0));
+    for (int i = 0; i < iters; ++i) dwconv3x3(in.v, w, b, out.v, batch, height, width, 0);
+    CUDA_OK(cudaEventRecord(t1, 0));
+    CUDA_OK(cudaEventSynchronize(t1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, t0, t1));
+    *ms_per_launch = ms / iters;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+  });
+}

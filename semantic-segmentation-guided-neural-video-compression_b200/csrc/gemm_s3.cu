@@ -96,7 +96,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default .release.cta semantics (what CUTLASS' ClusterBarrier::arrive uses): ordering of the TMEM reads is
+  // carried by tcgen05.fence::before_thread_sync, a cluster-scope release would add a full MEMBAR per tile
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -160,8 +162,8 @@ __device__ __forceinline__ void tma_store(const CUtensorMap* map, uint32_t src, 
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+__device__ __forceinline__ void tma_store_wait_read1() {   // at most one store still reading shared memory
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -189,6 +191,36 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uin
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// Issued from warp-uniform code by the lane whose `sel` is non-zero: no divergent branch around the
+// instruction, so the (uniform) descriptors can stay in uniform registers.
+__device__ __forceinline__ void tc_mma_pair_sel(uint32_t sel, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sel)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair_sel(uint32_t sel, uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(mask), "r"(sel)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
@@ -244,7 +276,8 @@ constexpr int kS3APlane = 128 * kS3BK * 2;        // one plane of a 128 x 32 bf1
 constexpr int kS3EpiWarps = 8;
 constexpr int kS3Threads = 64 + 32 * kS3EpiWarps; // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kS3ChunkBytes = 3 * 32 * 32;        // [3 planes][32 rows][16 bf16]
-constexpr int kS3WarpSmem = 3 * kS3ChunkBytes;    // one store tile + two residual tiles per epilogue warp
+constexpr int kS3Ring = 3;                        // staging tiles per epilogue warp (residual in -> result out)
+constexpr int kS3WarpSmem = kS3Ring * kS3ChunkBytes;
 constexpr int kS3BarBytes = 512;
 
 // Shared-memory descriptor of a K-major SWIZZLE_64B operand tile (cute::UMMA::SmemDescriptor):
@@ -265,20 +298,20 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = smem_u32(smem_raw);
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = blockIdx.x & 1u;             // cluster = (2,1,1): rank in the pair, provably warp-uniform
   const bool leader = rank == 0;
   const uint32_t wRows = (uint32_t)p.BN >> 1;
   const uint32_t wPlane = wRows * (kS3BK * 2);
   const uint32_t stageBytes = 3u * (kS3APlane + wPlane);
   const uint32_t epiBase = base + (uint32_t)p.stages * stageBytes;
   const uint32_t barBase = epiBase + kS3EpiWarps * kS3WarpSmem;
-  // barriers: full[8] | empty[8] | tfull[2] | tempty[2] | res[8 warps][2] | tmem slot
+  // barriers: full[8] | empty[8] | tfull[2] | tempty[2] | res[8 warps][3 (+1 pad)] | tmem slot
   auto bar_full = [&](int s) { return barBase + 8u * s; };
   auto bar_empty = [&](int s) { return barBase + 64u + 8u * s; };
   auto bar_tfull = [&](int b) { return barBase + 128u + 8u * b; };
   auto bar_tempty = [&](int b) { return barBase + 144u + 8u * b; };
-  auto bar_res = [&](int w, int b) { return barBase + 160u + 16u * w + 8u * b; };
-  const uint32_t tmemSlot = barBase + 288u;
+  auto bar_res = [&](int w, int b) { return barBase + 160u + 32u * w + 8u * b; };
+  const uint32_t tmemSlot = barBase + 416u;
 
   if (warp == 0 && lane == 0) {
     if (base & 1023u) {
@@ -298,8 +331,7 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_init(bar_tempty(b), kS3EpiWarps * 2);
     }
     for (int w = 0; w < kS3EpiWarps; ++w) {
-      mbar_init(bar_res(w, 0), 1);
-      mbar_init(bar_res(w, 1), 1);
+      for (int b = 0; b < kS3Ring; ++b) mbar_init(bar_res(w, b), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -313,8 +345,7 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   cluster_sync_all();                      // peer barriers are initialised before any remote use
   tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmemSlot) : "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmemSlot - base));
 
   const int unit = (int)(blockIdx.x >> 1);
   const int units = (int)(gridDim.x >> 1);
@@ -322,17 +353,18 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   if (warp == 0) {
     // ------------------------------------------------------------ operand producer (both CTAs)
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = unit; tile < total_tiles; tile += units) {
-        const int mt = tile / p.n_tiles;
-        const int m_idx = mt * 256 + (int)rank * 128;
-        const int n_idx = (tile - mt * p.n_tiles) * p.BN + (int)(rank * wRows);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(bar_empty(s), ph ^ 1, p.err, 1);
-          const uint32_t sa = base + s * stageBytes;
-          const uint32_t sw = sa + 3 * kS3APlane;
+    // (whole warp walks the loop, one elected lane issues: addresses stay in uniform registers)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = unit; tile < total_tiles; tile += units) {
+      const int mt = tile / p.n_tiles;
+      const int m_idx = mt * 256 + (int)rank * 128;
+      const int n_idx = (tile - mt * p.n_tiles) * p.BN + (int)(rank * wRows);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(bar_empty(s), ph ^ 1, p.err, 1);
+        const uint32_t sa = base + s * stageBytes;
+        const uint32_t sw = sa + 3 * kS3APlane;
+        if (elect_one()) {
           if (p.dbg & 1) {
             if (leader) mbar_arrive(bar_full(s));
           } else {
@@ -342,13 +374,16 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tma_load_pair(sa, &tmA, kb * kS3BK, m_idx, lbar);
             tma_load_pair(sw, &tmW, kb * kS3BK, n_idx, lbar);
           }
-          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
-    if (lane == 0 && leader) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    // The whole warp walks the loop so that every address below is warp-uniform (uniform registers,
+    // no per-MMA register -> uniform-register shuffling); one elected lane issues.
+    if (leader) {
       // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
       // N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | (16u << 24);
@@ -364,29 +399,32 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(bar_full(s), ph, p.err, 3);
           tc_fence_after();
-          if (!(p.dbg & 2)) {
-            const uint32_t sa = base + s * stageBytes;
-            const uint64_t da = s3_desc(sa);
-            const uint64_t dw = s3_desc(sa + 3 * kS3APlane);
-            const uint32_t first = kb == 0 ? 0u : 1u;
+          const uint32_t sa = base + s * stageBytes;
+          const uint64_t da = s3_desc(sa);
+          const uint64_t dw = s3_desc(sa + 3 * kS3APlane);
+          const uint32_t first = kb == 0 ? 0u : 1u;
+          if (elect_one()) {
+            if (!(p.dbg & 2)) {
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              // term 0 = hi*hi -> main accumulator; the five small terms (smallest first) -> second one
-              // (plane index: 0 hi, 1 mid, 2 lo):  hl, lh, mm, hm, mh
-              const uint64_t a0 = da + 2 * ks, a1 = a0 + aStep, a2 = a0 + 2 * aStep;
-              const uint64_t w0 = dw + 2 * ks, w1 = w0 + wStep, w2 = w0 + 2 * wStep;
-              tc_mma_pair(d_main, a0, w0, idesc, ks == 0 ? first : 1u);
-              tc_mma_pair(d_small, a0, w2, idesc, ks == 0 ? first : 1u);
-              tc_mma_pair(d_small, a2, w0, idesc, 1u);
-              tc_mma_pair(d_small, a1, w1, idesc, 1u);
-              tc_mma_pair(d_small, a0, w1, idesc, 1u);
-              tc_mma_pair(d_small, a1, w0, idesc, 1u);
+              for (int ks = 0; ks < 2; ++ks) {
+                // term 0 = hi*hi -> main accumulator; the five small terms (smallest first) -> second one
+                // (plane index: 0 hi, 1 mid, 2 lo):  hl, lh, mm, hm, mh
+                const uint64_t a0 = da + 2 * ks, a1 = a0 + aStep, a2 = a0 + 2 * aStep;
+                const uint64_t w0 = dw + 2 * ks, w1 = w0 + wStep, w2 = w0 + 2 * wStep;
+                tc_mma_pair(d_main, a0, w0, idesc, ks == 0 ? first : 1u);
+                tc_mma_pair(d_small, a0, w2, idesc, ks == 0 ? first : 1u);
+                tc_mma_pair(d_small, a2, w0, idesc, 1u);
+                tc_mma_pair(d_small, a1, w1, idesc, 1u);
+                tc_mma_pair(d_small, a0, w1, idesc, 1u);
+                tc_mma_pair(d_small, a1, w0, idesc, 1u);
+              }
             }
+            tc_commit_pair(bar_empty(s));
+            if (kb == p.k_blocks - 1) tc_commit_pair(bar_tfull(buf));
           }
-          tc_commit_pair(bar_empty(s));
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        tc_commit_pair(bar_tfull(buf));
       }
     }
   } else {
@@ -403,8 +441,9 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       nchunk = p.BN >> 5;
       acc0 = half * (p.BN >> 1);
     }
-    const uint32_t outBuf = epiBase + (uint32_t)ew * kS3WarpSmem;
-    const uint32_t resBuf = outBuf + kS3ChunkBytes;
+    // ring of staging tiles: chunk k of this warp lives in tile k % kS3Ring -- first as the residual
+    // (TMA load, issued one chunk ahead), then overwritten in place by the result (TMA store)
+    const uint32_t ringBuf = epiBase + (uint32_t)ew * kS3WarpSmem;
     const uint32_t swz = (uint32_t)((lane >> 2) & 1) << 4;        // SWIZZLE_32B: 16-byte unit ^= row bit 2
     const uint32_t rowOff = (uint32_t)lane * 32u;
     const bool epi_mem = !(p.dbg & 12);
@@ -417,18 +456,18 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     };
     auto dest_row = [&](int tile) { return (tile / p.n_tiles) * 256 + (int)rank * 128 + quad * 32; };
 
-    uint32_t res_issued = 0, res_waited = 0;
-    auto issue_res = [&](int tile, int c) {     // lane 0 only
+    uint32_t ld_slot = 0, ld_par = 0;           // ring position / barrier parity of the next residual load
+    uint32_t slot = 0, par = 0;                 // ... of the chunk being processed
+    auto issue_res = [&](int tile, int c) {     // whole warp; lane 0 issues
       const int dcol = dest_col(tile, c);
       if (dcol >= p.n_out) return;
-      const uint32_t b = res_issued & 1;
-      mbar_expect_tx(bar_res(ew, b), kS3ChunkBytes);
-      tma_load_local(resBuf + b * kS3ChunkBytes, &tmRes, dcol, dest_row(tile), bar_res(ew, b));
+      if (lane == 0) {
+        mbar_expect_tx(bar_res(ew, ld_slot), kS3ChunkBytes);
+        tma_load_local(ringBuf + ld_slot * kS3ChunkBytes, &tmRes, dcol, dest_row(tile), bar_res(ew, ld_slot));
+      }
+      if (++ld_slot == kS3Ring) { ld_slot = 0; ld_par ^= 1; }
     };
-    if (kRes && epi_mem && nchunk > 0 && unit < total_tiles) {
-      if (lane == 0) issue_res(unit, 0);
-      if (dest_col(unit, 0) < p.n_out) ++res_issued;
-    }
+    if (kRes && epi_mem && nchunk > 0 && unit < total_tiles) issue_res(unit, 0);
 
     uint32_t tcount = 0;
     for (int tile = unit; tile < total_tiles; tile += units, ++tcount) {
@@ -451,14 +490,14 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int acol = acc0 + 16 * c;                     // accumulator column of this chunk
         const int dcol = dest_col(tile, c);
         const bool valid = dcol < p.n_out;                  // warp-uniform
-        // prefetch the residual tile of the next chunk
-        if (kRes && epi_mem) {
+        // The staging tile two chunks back must have been read by its TMA store before it is reused
+        // (by the residual load issued next, or by this chunk's own result when there is no residual).
+        if (lane == 0) tma_store_wait_read1();
+        __syncwarp();
+        if (kRes && epi_mem) {                  // prefetch the residual tile of the next chunk
           int nt = tile, nc = c + 1;
           if (nc == nchunk) { nc = 0; nt += units; }
-          if (nt < total_tiles) {
-            if (lane == 0) issue_res(nt, nc);
-            if (dest_col(nt, nc) < p.n_out) ++res_issued;
-          }
+          if (nt < total_tiles) issue_res(nt, nc);
         }
         float v[16];
         if (valid) {
@@ -506,10 +545,8 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         if (!valid) continue;
         if (kRes && epi_mem) {
-          const uint32_t rb = res_waited & 1;
-          mbar_wait(bar_res(ew, rb), (res_waited >> 1) & 1, p.err, 5);
-          ++res_waited;
-          const uint32_t src = resBuf + rb * kS3ChunkBytes + rowOff;
+          mbar_wait(bar_res(ew, slot), par, p.err, 5);
+          const uint32_t src = ringBuf + slot * kS3ChunkBytes + rowOff;
           float t[16];
 #pragma unroll
           for (int pl = 2; pl >= 0; --pl) {    // (lo + mid) + hi, exactly join3
@@ -551,10 +588,7 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           pm_[i] = m;
           pl_[i] = cvt_bf16x2(sub_rn(r0, bf16lo(m)), sub_rn(r1, bf16hi(m)));
         }
-        // the previous store of this warp must have finished reading the staging tile
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-        const uint32_t dst = outBuf + rowOff;
+        const uint32_t dst = ringBuf + slot * kS3ChunkBytes + rowOff;
         st_shared_v4(dst + swz, ph_[0], ph_[1], ph_[2], ph_[3]);
         st_shared_v4(dst + (16u ^ swz), ph_[4], ph_[5], ph_[6], ph_[7]);
         st_shared_v4(dst + 1024 + swz, pm_[0], pm_[1], pm_[2], pm_[3]);
@@ -563,7 +597,8 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         st_shared_v4(dst + 2048 + (16u ^ swz), pl_[4], pl_[5], pl_[6], pl_[7]);
         fence_async_smem();
         __syncwarp();
-        if (lane == 0 && epi_mem) tma_store(&tmOut, outBuf, dcol, row0);
+        if (lane == 0 && epi_mem) tma_store(&tmOut, ringBuf + slot * kS3ChunkBytes, dcol, row0);
+        if (++slot == kS3Ring) { slot = 0; par ^= 1; }
       }
     }
     if (lane == 0) tma_store_wait_all();

@@ -29,3 +29,11 @@ for name, k, n, mode in SHAPES:
                 break
             row.append(f"{pname}={ms.value * 1e3:7.1f}us")
         print(f"{name:22s} kernel={pair} issued={flops / 1e9:6.1f}GF  " + "  ".join(row), flush=True)
+
+for C in (256, 320, 128):
+    ms = ctypes.c_float()
+    hh, ww = (160, 240) if C != 128 else (80, 120)
+    rc = lib.dmc_bench_dwconv(1, hh, ww, C, 20, ctypes.byref(ms))
+    gb = hh * ww * C * 12 / 1e9
+    print(f"dwconv3x3 {hh}x{ww}x{C}: {ms.value * 1e3:7.1f}us  {gb / ms.value * 1e3:7.0f} GB/s (read+write S3)" if rc == 0
+          else f"dwconv ERR {lib.dmc_last_error(None).decode()}", flush=True)
