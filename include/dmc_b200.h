@@ -152,8 +152,10 @@ int dmc_profile_read(dmc_engine* e, double* gemm_ms, int64_t* gemm_launches, dou
 int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int pair, int iters, int probe,
                    float* ms_per_launch);
 
-/* Times the depthwise 3x3 kernel alone on zero-filled S3 buffers (bench / profiling tool). */
-int dmc_bench_dwconv(int batch, int height, int width, int channels, int iters, float* ms_per_launch);
+/* Times the depthwise 3x3 kernel alone on zero-filled buffers (bench / profiling tool); f32_in selects the
+ * variant that reads fp32 rows (the one DepthConvBlock uses) instead of S3 planes. */
+int dmc_bench_dwconv(int batch, int height, int width, int channels, int f32_in, int iters,
+                     float* ms_per_launch);
 
 int dmc_num_sms(void);
 const char* dmc_version(void);

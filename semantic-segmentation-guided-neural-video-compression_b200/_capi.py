@@ -43,7 +43,7 @@ SIGNATURES = {
     "dmc_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), POINTER(c_double),
                                  POINTER(c_double)]),
     "dmc_bench_gemm": (c_int, [c_int] * 8 + [POINTER(c_float)]),
-    "dmc_bench_dwconv": (c_int, [c_int] * 5 + [POINTER(c_float)]),
+    "dmc_bench_dwconv": (c_int, [c_int] * 6 + [POINTER(c_float)]),
     "dmc_num_sms": (c_int, []),
     "dmc_version": (c_char_p, []),
 }

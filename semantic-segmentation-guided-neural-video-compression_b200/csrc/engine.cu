@@ -183,6 +183,16 @@ struct dmc_engine {
     scratch[key] = a;
     return a;
   }
+  std::map<std::string, float*> scratch_f32;
+  float* get_scratch_f32(const std::string& tag, size_t n) {
+    char key[160];
+    snprintf(key, sizeof key, "%s:%zu", tag.c_str(), n);
+    auto it = scratch_f32.find(key);
+    if (it != scratch_f32.end()) return it->second;
+    float* p = new_f32(n);
+    scratch_f32[key] = p;
+    return p;
+  }
   static Act slice(const Act& a, int c0, int C) {
     Act s = a;
     s.v.p = a.v.p + c0;
@@ -318,7 +328,7 @@ struct dmc_engine {
     int nsplit = spec.nsplit;
     dmc_engine* self = this;
     auto tma_ok = [](const View& v) { return (uintptr_t)v.p % 16 == 0 && v.ld % 8 == 0 && v.ps % 8 == 0; };
-    if (use_umma && use_s3 && gemm_s3_supports(*g, e, nsplit) && tma_ok(out->v) &&
+    if (use_umma && use_s3 && gemm_s3_supports(*g, e, nsplit) && (!out || tma_ok(out->v)) &&
         (!spec.res1 || tma_ok(spec.res1->v))) {
       CUtensorMap* tm3[3];
       for (auto& t : tm3) {
@@ -326,7 +336,12 @@ struct dmc_engine {
         t = tmaps.back().get();
       }
       if (make_tmap_s3_act(tm3[0], a, M) != 0) fail("gemm A map: %s", gemm_s3_last_error());
-      if (make_tmap_s3_rows(tm3[1], out->v, e.n_out, M) != 0) fail("gemm out map: %s", gemm_s3_last_error());
+      if (spec.out_f32) {
+        if (make_tmap_f32_rows(tm3[1], spec.out_f32, e.n_out, spec.ld_f32, M) != 0)
+          fail("gemm fp32 out map: %s", gemm_s3_last_error());
+      } else if (make_tmap_s3_rows(tm3[1], out->v, e.n_out, M) != 0) {
+        fail("gemm out map: %s", gemm_s3_last_error());
+      }
       if (spec.res1 && make_tmap_s3_rows(tm3[2], spec.res1->v, e.n_out, M) != 0)
         fail("gemm residual map: %s", gemm_s3_last_error());
       CUtensorMap* ta = tm3[0];
@@ -390,15 +405,21 @@ struct dmc_engine {
       xin = get_scratch("dcb_x", x.B, x.H, x.W, C);
       gemm(x, w->adaptor, &xin, s0);
     }
-    Act t = get_scratch("dcb_t", x.B, x.H, x.W, C);
+    // dc.0's output only feeds the depthwise conv: it stays fp32 rows (4 B/element, no S3 join in the consumer)
+    float* t32 = get_scratch_f32("dcb_t32", (size_t)x.M() * C);
     Act t2 = get_scratch("dcb_t2", x.B, x.H, x.W, C);
     Act o1 = get_scratch("dcb_o1", x.B, x.H, x.W, C);
     Act u = get_scratch("dcb_u", x.B, x.H, x.W, 2 * C);
     EpiSpec s1 = s0;
     s1.act = ACT_WSILU;
-    gemm(xin, w->dc0, &t, s1);
+    {
+      EpiSpec sd = s1;
+      sd.out_f32 = t32;
+      sd.ld_f32 = C;
+      gemm(xin, w->dc0, nullptr, sd);
+    }
     DW* dw = w->dw;
-    op([t, t2, dw](cudaStream_t st) { dwconv3x3(t.v, dw->w9c, dw->bias, t2.v, t.B, t.H, t.W, st); });
+    op([t32, C, t2, dw](cudaStream_t st) { dwconv3x3_f32(t32, C, dw->w9c, dw->bias, t2.v, t2.B, t2.H, t2.W, st); });
     EpiSpec s2 = s0;
     s2.res1 = &xin;
     gemm(t2, w->dc3, &o1, s2);
@@ -1249,7 +1270,8 @@ extern "C" int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int 
   });
 }
 
-extern "C" int dmc_bench_dwconv(int batch, int height, int width, int channels, int iters, float* ms_per_launch) {
+extern "C" int dmc_bench_dwconv(int batch, int height, int width, int channels, int f32_in, int iters,
+                                float* ms_per_launch) {
   return guarded(nullptr, [&] {
     if (batch < 1 || height < 1 || width < 1 || channels % 8 || iters < 1 || !ms_per_launch)
       fail("dmc_bench_dwconv: bad arguments");
@@ -1264,9 +1286,15 @@ extern "C" int dmc_bench_dwconv(int batch, int height, int width, int channels, 
     cudaEvent_t t0, t1;
     CUDA_OK(cudaEventCreate(&t0));
     CUDA_OK(cudaEventCreate(&t1));
-    for (int i = 0; i < 3; ++i) dwconv3x3(in.v, w, b, out.v, batch, height, width, 0);
+    float* in32 = e.new_f32((size_t)in.M() * channels);
+    CUDA_OK(cudaMemset(in32, 0, sizeof(float) * in.M() * channels));
+    auto run = [&] {
+      if (f32_in) dwconv3x3_f32(in32, channels, w, b, out.v, batch, height, width, 0);
+      else dwconv3x3(in.v, w, b, out.v, batch, height, width, 0);
+    };
+    for (int i = 0; i < 3; ++i) run();
     CUDA_OK(cudaEventRecord(t0, 0));
-    for (int i = 0; i < iters; ++i) dwconv3x3(in.v, w, b, out.v, batch, height, width, 0);
+    for (int i = 0; i < iters; ++i) run();
     CUDA_OK(cudaEventRecord(t1, 0));
     CUDA_OK(cudaEventSynchronize(t1));
     float ms = 0;

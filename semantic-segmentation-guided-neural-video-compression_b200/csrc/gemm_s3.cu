@@ -82,6 +82,28 @@ int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M) {
                    CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+// fp32 result rows [M, ld]: 2-D map, box = 16 columns x 32 rows, SWIZZLE_64B
+int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M) {
+  auto fn = s3_get_encode();
+  if (!fn) {
+    snprintf(g_s3_err, sizeof g_s3_err, "cuTensorMapEncodeTiled entry point unavailable");
+    return -1;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn((CUtensorMap*)tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_s3_err, sizeof g_s3_err, "cuTensorMapEncodeTiled (fp32 rows) failed (%d): base=%p cols=%d ld=%d", (int)r,
+             (void*)base, cols, ld);
+    return -1;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ device helpers (PTX)
 namespace s3 {
 
@@ -159,6 +181,12 @@ __device__ __forceinline__ void tma_load_local(uint32_t dst, const CUtensorMap* 
 __device__ __forceinline__ void tma_store(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(0)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -289,7 +317,10 @@ __device__ __forceinline__ uint64_t s3_desc(uint32_t saddr) {
   return ((uint64_t)hi << 32) | lo;
 }
 
-template <int kAct, int kPack, int kRes>
+// kF32: the result leaves as fp32 rows [M, ld] (one 2-D TMA store of 16 columns x 32 rows per chunk,
+// SWIZZLE_64B staging) instead of S3 planes -- used where the consumer is not a contraction
+// (the depthwise 3x3 after dc.0, the pixel-shuffle tail after the reconstruction head).
+template <int kAct, int kPack, int kRes, int kF32>
 __global__ void __launch_bounds__(kS3Threads, 1)
 k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -576,6 +607,20 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             v[4 * i + 2] = mul_rn(v[4 * i + 2], q.z); v[4 * i + 3] = mul_rn(v[4 * i + 3], q.w);
           }
         }
+        if (kF32) {
+          // fp32 rows: 64 B per lane, 16-byte unit u of row r sits at u ^ ((r >> 1) & 3)  (SWIZZLE_64B)
+          const uint32_t dst = ringBuf + slot * kS3ChunkBytes + (uint32_t)lane * 64u;
+          const uint32_t sw64 = (uint32_t)((lane >> 1) & 3) << 4;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            st_shared_v4(dst + (((uint32_t)u << 4) ^ sw64), __float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
+                         __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && epi_mem) tma_store_2d(&tmOut, ringBuf + slot * kS3ChunkBytes, dcol, row0);
+          if (++slot == kS3Ring) { slot = 0; par ^= 1; }
+          continue;
+        }
         // exact 3-way split, two elements per conversion
         uint32_t ph_[8], pm_[8], pl_[8];
 #pragma unroll
@@ -618,8 +663,13 @@ static int g_s3_dbg = 0;
 void gemm_s3_set_debug(int mask) { g_s3_dbg = mask; }
 
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit) {
-  if (nsplit != 3 || !w.tmap_s3 || !e.out.p || e.out_f32 || e.do_clamp || e.res2.p) return false;
+  if (nsplit != 3 || !w.tmap_s3 || e.do_clamp || e.res2.p) return false;
   if (w.BN % 32 || w.BN > 128) return false;
+  if (e.out_f32) {                       // fp32 rows: plain layout, no residual, and not both outputs at once
+    return !e.out.p && e.pack == PACK_PLAIN && !e.res1.p && (e.act == ACT_NONE || e.act == ACT_WSILU) &&
+           e.ld_f32 % 4 == 0 && (uintptr_t)e.out_f32 % 16 == 0;
+  }
+  if (!e.out.p) return false;
   if (e.pack == PACK_PLAIN) {
     if (e.act == ACT_NONE) return true;
     return e.act == ACT_WSILU && !e.res1.p;
@@ -628,7 +678,7 @@ bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit) {
   return false;
 }
 
-template <int kAct, int kPack, int kRes>
+template <int kAct, int kPack, int kRes, int kF32>
 static cudaError_t launch_s3(int grid, int smem, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw,
                              const CUtensorMap& to, const CUtensorMap& tr, const S3Params& p) {
   static bool attr_set = false;
@@ -636,7 +686,7 @@ static cudaError_t launch_s3(int grid, int smem, cudaStream_t st, const CUtensor
     int dev = 0, smem_max = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_s3<kAct, kPack, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_s3<kAct, kPack, kRes, kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_max);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -654,7 +704,7 @@ static cudaError_t launch_s3(int grid, int smem, cudaStream_t st, const CUtensor
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_gemm_s3<kAct, kPack, kRes>, ta, tw, to, tr, p);
+  return cudaLaunchKernelEx(&cfg, k_gemm_s3<kAct, kPack, kRes, kF32>, ta, tw, to, tr, p);
 }
 
 int gemm_s3(const void* tmapA, const GemmW& w, const Epi& e, const void* tmapOut, const void* tmapRes,
@@ -704,10 +754,12 @@ int gemm_s3(const void* tmapA, const GemmW& w, const Epi& e, const void* tmapOut
   memcpy(&tr, tmapRes ? tmapRes : tmapOut, sizeof tr);
   note_launch();
   cudaError_t err;
-  if (e.pack == PACK_PAIR) err = launch_s3<ACT_WSILU, PACK_PAIR, 0>(grid, smem, st, ta, tw, to, tr, p);
-  else if (e.act == ACT_WSILU) err = launch_s3<ACT_WSILU, PACK_PLAIN, 0>(grid, smem, st, ta, tw, to, tr, p);
-  else if (e.res1.p) err = launch_s3<ACT_NONE, PACK_PLAIN, 1>(grid, smem, st, ta, tw, to, tr, p);
-  else err = launch_s3<ACT_NONE, PACK_PLAIN, 0>(grid, smem, st, ta, tw, to, tr, p);
+  if (e.out_f32 && e.act == ACT_WSILU) err = launch_s3<ACT_WSILU, PACK_PLAIN, 0, 1>(grid, smem, st, ta, tw, to, tr, p);
+  else if (e.out_f32) err = launch_s3<ACT_NONE, PACK_PLAIN, 0, 1>(grid, smem, st, ta, tw, to, tr, p);
+  else if (e.pack == PACK_PAIR) err = launch_s3<ACT_WSILU, PACK_PAIR, 0, 0>(grid, smem, st, ta, tw, to, tr, p);
+  else if (e.act == ACT_WSILU) err = launch_s3<ACT_WSILU, PACK_PLAIN, 0, 0>(grid, smem, st, ta, tw, to, tr, p);
+  else if (e.res1.p) err = launch_s3<ACT_NONE, PACK_PLAIN, 1, 0>(grid, smem, st, ta, tw, to, tr, p);
+  else err = launch_s3<ACT_NONE, PACK_PLAIN, 0, 0>(grid, smem, st, ta, tw, to, tr, p);
   if (err != cudaSuccess) {
     snprintf(g_s3_err, sizeof g_s3_err, "k_gemm_s3 launch: %s", cudaGetErrorString(err));
     return -1;

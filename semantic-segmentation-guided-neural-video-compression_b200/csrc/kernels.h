@@ -44,6 +44,9 @@ void finite_check(View v, long long M, int* flag, cudaStream_t st);
 // ---------------- convolution pieces ----------------
 void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, int H, int W,
                cudaStream_t st);
+// same with the input as fp32 rows [M, ld] (what the contraction in front of it writes)
+void dwconv3x3_f32(const float* in, int ld, const float* w9c, const float* bias, View out, int B, int H, int W,
+                   cudaStream_t st);
 // dst columns: tap * tap_stride + col_off + c
 void im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, int Ho, int Wo,
             int tap_stride, int col_off, cudaStream_t st);
@@ -63,6 +66,7 @@ const char* umma_last_error();
 int make_tmap_s3_act(void* tmap_out, View a, long long M);                 // box 32 x 128 x 3
 int make_tmap_s3_weight(void* tmap_out, const GemmW& w);                   // box 32 x BN/2 x 3
 int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M);      // box 16 x 32 x 3
+int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M);   // fp32 rows, box 16 x 32
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit);
 void gemm_s3_set_debug(int mask);
 int gemm_s3(const void* tmapA, const GemmW& w, const Epi& e, const void* tmapOut, const void* tmapRes,

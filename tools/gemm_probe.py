@@ -16,7 +16,8 @@ SHAPES = [("dc0 256->256 plain", 256, 256, 0), ("dc0 256->256 wsilu", 256, 256, 
           ("ffn0 256->1024 pair", 256, 1024, 3), ("ffn2 512->256 +res", 512, 256, 2), ("head 320->192", 320, 192, 0)]
 PROBES = [(0, "full"), (4, "no-epi-mem"), (12, "no-epi"), (2, "no-mma"), (3, "no-tma,no-mma"), (13, "mma-only"),
           (14, "tma-only")]
-KERNELS = [int(a) for a in sys.argv[1:]] or [0, 2]          # 0 one-CTA general kernel, 1 its CTA-pair variant, 2 gemm_s3
+ARGS = sys.argv[1:]
+KERNELS = [int(a) for a in ARGS if a.isdigit()] or ([] if "dw" in ARGS else [0, 2])   # 0 general one-CTA, 1 its pair variant, 2 gemm_s3
 for name, k, n, mode in SHAPES:
     flops = 2.0 * M * k * n * 6
     for pair in KERNELS:
@@ -31,9 +32,10 @@ for name, k, n, mode in SHAPES:
         print(f"{name:22s} kernel={pair} issued={flops / 1e9:6.1f}GF  " + "  ".join(row), flush=True)
 
 for C in (256, 320, 128):
-    ms = ctypes.c_float()
-    hh, ww = (160, 240) if C != 128 else (80, 120)
-    rc = lib.dmc_bench_dwconv(1, hh, ww, C, 20, ctypes.byref(ms))
-    gb = hh * ww * C * 12 / 1e9
-    print(f"dwconv3x3 {hh}x{ww}x{C}: {ms.value * 1e3:7.1f}us  {gb / ms.value * 1e3:7.0f} GB/s (read+write S3)" if rc == 0
-          else f"dwconv ERR {lib.dmc_last_error(None).decode()}", flush=True)
+    for f32 in (0, 1):
+        ms = ctypes.c_float()
+        hh, ww = (160, 240) if C != 128 else (80, 120)
+        rc = lib.dmc_bench_dwconv(1, hh, ww, C, f32, 20, ctypes.byref(ms))
+        gb = hh * ww * C * (10 if f32 else 12) / 1e9
+        print(f"dwconv3x3 {hh}x{ww}x{C} f32_in={f32}: {ms.value * 1e3:7.1f}us  {gb / ms.value * 1e3:7.0f} GB/s (read+write)" if rc == 0
+              else f"dwconv ERR {lib.dmc_last_error(None).decode()}", flush=True)
