@@ -157,6 +157,11 @@ int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int pair, int i
 int dmc_bench_dwconv(int batch, int height, int width, int channels, int f32_in, int iters,
                      float* ms_per_launch);
 
+/* Times a stack of `blocks` DepthConvBlocks (zero weights and inputs) the way a frame runs them: chained
+ * contraction launches + depthwise kernels.  Reports milliseconds per block (bench / profiling tool). */
+int dmc_bench_dcb(int batch, int height, int width, int cin, int cout, int blocks, int iters,
+                  float* ms_per_block);
+
 int dmc_num_sms(void);
 const char* dmc_version(void);
 

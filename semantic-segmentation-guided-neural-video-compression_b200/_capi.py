@@ -44,6 +44,7 @@ SIGNATURES = {
                                  POINTER(c_double)]),
     "dmc_bench_gemm": (c_int, [c_int] * 8 + [POINTER(c_float)]),
     "dmc_bench_dwconv": (c_int, [c_int] * 6 + [POINTER(c_float)]),
+    "dmc_bench_dcb": (c_int, [c_int] * 7 + [POINTER(c_float)]),
     "dmc_num_sms": (c_int, []),
     "dmc_version": (c_char_p, []),
 }

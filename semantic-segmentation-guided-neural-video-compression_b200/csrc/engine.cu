@@ -43,7 +43,9 @@ std::string g_create_error;
 #define CUDA_OK(call)                                                                       \
   do {                                                                                      \
     cudaError_t err__ = (call);                                                             \
-    if (err__ != cudaSuccess) fail("%s failed: %s", #call, cudaGetErrorString(err__));      \
+    if (err__ != cudaSuccess)                                                               \
+      fail("%s failed: %s (chain kernel wait code %d)", #call, cudaGetErrorString(err__),   \
+           gemm_s3_trap_code());                                                            \
   } while (0)
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -143,6 +145,7 @@ struct dmc_engine {
   void prof_end(cudaStream_t st) { CUDA_OK(cudaEventRecord(prof_events.back().second, st)); }
 
   ~dmc_engine() {
+    for (S3Chain* c : chains) s3_chain_destroy(c);
     for (void* p : allocs) cudaFree(p);
   }
 
@@ -288,7 +291,40 @@ struct dmc_engine {
   }
 
   // ------------------------------------------------------------ op builders
-  void op(Op f) { prog->push_back(std::move(f)); }
+  void op(Op f) {
+    flush_chain();
+    prog->push_back(std::move(f));
+  }
+  void set_prog(std::vector<Op>* p) {
+    flush_chain();
+    prog = p;
+  }
+
+  // ---- chain staging (gemm_s3.cu): stages collected by gemm(), turned into one launch by flush_chain()
+  std::vector<S3StageDesc> pend;
+  long long pend_M = 0;
+  double pend_flops = 0, pend_issued = 0;
+  std::vector<S3Chain*> chains;
+  bool chain_layers = chain_default();
+  static bool chain_default() {
+    const char* v = getenv("DMC_GEMM_CHAIN");       // DMC_GEMM_CHAIN=0: one launch per layer (A/B runs)
+    return !(v && v[0] == '0');
+  }
+  void flush_chain() {
+    if (pend.empty()) return;
+    S3Chain* c = s3_chain_create(pend.data(), (int)pend.size(), pend_M);
+    if (!c) fail("s3_chain_create: %s", gemm_s3_last_error());
+    chains.push_back(c);
+    dmc_engine* self = this;
+    const double fl = pend_flops, issued = pend_issued;
+    prog->push_back([self, c, fl, issued](cudaStream_t st) {
+      if (self->profile) self->prof_begin(st, fl, issued);
+      if (s3_chain_launch(c, self->cur.qp, st) != 0) fail("s3_chain_launch: %s", gemm_s3_last_error());
+      if (self->profile) self->prof_end(st);
+    });
+    pend.clear();
+    pend_flops = pend_issued = 0;
+  }
 
   void tap(const std::string& name, const Act& a) {
     if (!keep_taps()) return;
@@ -344,18 +380,22 @@ struct dmc_engine {
       }
       if (spec.res1 && make_tmap_s3_rows(tm3[2], spec.res1->v, e.n_out, M) != 0)
         fail("gemm residual map: %s", gemm_s3_last_error());
-      CUtensorMap* ta = tm3[0];
-      CUtensorMap* to = tm3[1];
-      CUtensorMap* tr = spec.res1 ? tm3[2] : nullptr;
-      int K = g->K;
-      op([self, ta, to, tr, g, e, M, K, table, sc](cudaStream_t st) {
-        Epi ee = e;
-        if (table) ee.scale = table + (size_t)self->cur.qp * sc;
-        double fl = 2.0 * (double)M * g->N * g->K;
-        if (self->profile) self->prof_begin(st, fl, fl * 6);
-        if (gemm_s3(ta, *g, ee, to, tr, M, K, st) != 0) fail("gemm_s3: %s", gemm_s3_last_error());
-        if (self->profile) self->prof_end(st);
-      });
+      // consecutive qualifying contractions over the same rows become stages of one chain launch
+      if (!pend.empty() && (pend_M != M || (int)pend.size() >= s3_chain_max_stages() || !chain_layers)) flush_chain();
+      S3StageDesc d;
+      d.tmA = tm3[0];
+      d.w = g;
+      d.e = e;
+      d.tmOut = tm3[1];
+      d.tmRes = spec.res1 ? tm3[2] : nullptr;
+      d.K = g->K;
+      d.nsplit = nsplit;
+      d.scale_table = table;
+      d.scale_C = sc;
+      pend.push_back(d);
+      pend_M = M;
+      pend_flops += 2.0 * (double)M * g->N * g->K;
+      pend_issued += 2.0 * (double)M * g->N * g->K * (nsplit == 3 ? 6 : 1);
     } else if (use_umma) {
       tmaps.emplace_back(new CUtensorMap());
       CUtensorMap* tm = tmaps.back().get();
@@ -568,17 +608,17 @@ void dmc_engine::build_p() {
   float* RF = new_f32((size_t)M8 * 192);
 
   // ---- head: temporal feature (video_model.py:348-351)
-  prog = &prog_head_i;
+  set_prog(&prog_head_i);
   op([self, F8](cudaStream_t st) { unshuffle8_in(self->cur.dpb_frame, F8.v, self->B, 3, self->H, self->W, st); });
   dcb(fa_i, F8, FEAT0, false, nullptr, ns);
-  prog = &prog_head_p;
+  set_prog(&prog_head_p);
   op([self, FP](cudaStream_t st) { nchw_to_s3(self->cur.dpb_feature, FP.v, FP.B, 256, FP.H, FP.W, st); });
   {
     EpiSpec s; s.nsplit = ns;
     gemm(FP, fa_p, &FEAT0, s);
   }
 
-  prog = &prog_common;
+  set_prog(&prog_common);
   double* by = bits_y; double* bz = bits_z; int nb = B;
   op([by, bz, nb](cudaStream_t st) {
     CUDA_OK(cudaMemsetAsync(by, 0, sizeof(double) * nb, st));
@@ -646,7 +686,7 @@ void dmc_engine::build_p() {
       Act PM1 = new_act(B, H8, W8, CD / 4), PM2 = new_act(B, H8, W8, CD / 4);
       std::vector<Op> pred;
       std::vector<Op>* saved = prog;
-      prog = &pred;
+      set_prog(&pred);
       op([self, mdown](cudaStream_t st) { bilinear_down8(self->cur.mask, mdown, self->B, self->H, self->W, st); });
       op([mdown, me_w, me_b, ME](cudaStream_t st) { conv3x3_c1(mdown, me_w, me_b, ME.v, ME.B, ME.H, ME.W, 256, st); });
       Act srcs[3] = {ME, CTX, CTXT};
@@ -665,7 +705,7 @@ void dmc_engine::build_p() {
         float* dst = self->cur.mask_pred ? self->cur.mask_pred : logits_full;
         bilinear_up8(logit8, dst, self->B, H8, W8, st);
       });
-      prog = saved;
+      set_prog(saved);
       auto pred_ops = std::make_shared<std::vector<Op>>(std::move(pred));
       // guarded: the predictor runs only on non-first P frames with a mask
       // (mask_prop_seg_video_model.py:365-368)
@@ -782,6 +822,7 @@ void dmc_engine::build_p() {
       finite_check(FEAT.v, M8, self->cur.finite, st);
     });
   }
+  flush_chain();
 }
 
 // ====================================================================== I-frame program
@@ -854,7 +895,7 @@ void dmc_engine::build_intra() {
   float* sig = new_f32((size_t)M16 * N);
   float* RF = new_f32((size_t)M8 * 192);
 
-  prog = &prog_common;
+  set_prog(&prog_common);
   double* by = bits_y; double* bz = bits_z; int nb = B;
   op([by, bz, nb](cudaStream_t st) {
     CUDA_OK(cudaMemsetAsync(by, 0, sizeof(double) * nb, st));
@@ -937,6 +978,7 @@ void dmc_engine::build_intra() {
   op([self, RF](cudaStream_t st) { shuffle8_out(RF, 192, self->cur.x_hat, self->B, 3, self->H, self->W, st); });
   int pixels = H * W;
   op([self, by, bz, pixels](cudaStream_t st) { finalize_bpp(by, bz, self->cur.bpp3, self->B, pixels, st); });
+  flush_chain();
 }
 
 void dmc_engine::finalize(cudaStream_t st) {
@@ -1173,6 +1215,7 @@ extern "C" int dmc_op_conv2d(const float* x, const float* weight, const float* b
       EpiSpec s; s.act = act; s.nsplit = nsplit;
       if (ksize == 1 && stride == 1 && padding == 0) e.gemm(in, c, &o, s);
       else e.conv_kxk(in, c, &o, s);
+      e.flush_chain();
       e.run(e.prog_common, st);
     } else {
       fail("groups must be 1 or cin");
@@ -1212,6 +1255,7 @@ extern "C" int dmc_op_depth_conv_block(const float* x, const float* const* w12, 
     nchw_to_s3(x, in.v, batch, cin, height, width, st);
     e.cur.qp = 0;
     e.dcb(b, in, o, shortcut != 0, table, nsplit);
+    e.flush_chain();
     e.run(e.prog_common, st);
     s3_to_nchw(o.v, out, batch, cout, height, width, st);
     CUDA_OK(cudaStreamSynchronize(st));
@@ -1247,6 +1291,7 @@ extern "C" int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int 
     if (mode == 1 || mode == 3) s.act = ACT_WSILU;
     if (mode == 2) s.res1 = &res;
     e.gemm(in, c, &out, s);
+    e.flush_chain();
     umma_set_pair(pair != 0);
     umma_set_debug(probe);
     gemm_s3_set_debug(probe);
@@ -1300,6 +1345,46 @@ extern "C" int dmc_bench_dwconv(int batch, int height, int width, int channels, 
     float ms = 0;
     CUDA_OK(cudaEventElapsedTime(&ms, t0, t1));
     *ms_per_launch = ms / iters;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+  });
+}
+
+extern "C" int dmc_bench_dcb(int batch, int height, int width, int cin, int cout, int blocks, int iters,
+                             float* ms_per_block) {
+  return guarded(nullptr, [&] {
+    if (batch < 1 || height < 1 || width < 1 || cin % 8 || cout % 8 || blocks < 1 || iters < 1 || !ms_per_block)
+      fail("dmc_bench_dcb: bad arguments");
+    dmc_engine e;
+    e.variant = -1; e.B = batch; e.H = height; e.W = width;
+    e.prog = &e.prog_common;
+    Act a = e.new_act(batch, height, width, cin), b = e.new_act(batch, height, width, cout),
+        c = e.new_act(batch, height, width, cout);
+    CUDA_OK(cudaMemset(a.v.p, 0, (size_t)a.v.ps * 3 * sizeof(bf16)));
+    for (int i = 0; i < blocks; ++i) {
+      DCB* w = e.add_dcb("b" + std::to_string(i), i == 0 ? cin : cout, cout);
+      e.dcb(w, i == 0 ? a : (i % 2 ? b : c), i % 2 ? c : b, false, nullptr, 3);
+    }
+    e.flush_chain();
+    for (auto& cv : e.convs) {
+      CUDA_OK(cudaMemset(cv->g.w, 0, (size_t)3 * cv->g.Npad * cv->g.Kld * sizeof(bf16)));
+      CUDA_OK(cudaMemset(cv->g.bias, 0, sizeof(float) * cv->g.Npad));
+    }
+    for (auto& d : e.dws) {
+      CUDA_OK(cudaMemset(d->w9c, 0, sizeof(float) * 9 * d->C));
+      CUDA_OK(cudaMemset(d->bias, 0, sizeof(float) * d->C));
+    }
+    cudaEvent_t t0, t1;
+    CUDA_OK(cudaEventCreate(&t0));
+    CUDA_OK(cudaEventCreate(&t1));
+    for (int i = 0; i < 2; ++i) e.run(e.prog_common, 0);
+    CUDA_OK(cudaEventRecord(t0, 0));
+    for (int i = 0; i < iters; ++i) e.run(e.prog_common, 0);
+    CUDA_OK(cudaEventRecord(t1, 0));
+    CUDA_OK(cudaEventSynchronize(t1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, t0, t1));
+    *ms_per_block = ms / iters / blocks;
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);
   });

@@ -1,23 +1,34 @@
-// Specialised tcgen05 contraction for the layers that carry the frame: S3 in, S3 out,
-//   out = epilogue(A[M,K] . W[N,K]^T)   with the fp32-grade 6-term split product.
+// Persistent tcgen05 "chain" kernel for the layers that carry the frame: S3 in, S3 (or fp32 rows) out,
+//   out_l = epilogue_l(A_l[M,K_l] . W_l[N_l,K_l]^T),  l = 0 .. L-1,
+// where every layer is a 1x1 convolution over the same M rows and A_l is normally the output of
+// layer l-1 (a DepthConvBlock is dc.3 -> ffn.0 -> ffn.2 -> the next block's dc.0).  ONE launch walks a
+// host-built table of (layer, 256-row tile, N tile) entries; a tile of layer l starts as soon as all
+// N tiles of layer l-1 for the SAME rows are stored (a global counter per (layer, row tile), release /
+// acquire at gpu scope), so
+//   * 148 SMs share  sum_l tiles_l  work items instead of rounding every layer up to whole waves
+//     (M = 38400 gives 4.05 waves of 256 x 128 tiles per 256-channel layer: 19 % idle when launched alone),
+//   * there are no launch gaps / pipeline refills / drained tails between the layers of a chain,
+//   * the intermediate activations are consumed a few tiles after they are written: they come from L2.
+// The table is layer-major, every dependency points backwards in it and all clusters are resident
+// (grid <= #SM), so waits cannot deadlock; they are bounded anyway and trap instead of hanging.
 //
-// What differs from the general kernel in gemm_umma.cu (which stays as the path for pixel-shuffle
-// stores, fp32 outputs, two residuals and single-term products):
-//   * always a cluster of two CTAs working on one 256 x BN tile with cta_group::2 MMAs: each CTA
-//     loads its own 128 rows of A and HALF of the W tile, so the L2 -> SM operand traffic per MMA
-//     cycle drops from 64 to 48 B/clk (the chip sustains ~42 B/clk/SM);
-//   * K is staged in blocks of 32 (SWIZZLE_64B): a stage is 36 KB instead of 96 KB, four of them are
-//     in flight, and TMA latency is covered with half the shared memory;
-//   * the epilogue is compile-time specialised (activation / chunk-add pairing / residual) and moves
-//     no global memory itself: residual tiles arrive by TMA (one 3-plane box per warp and 16-column
-//     chunk, prefetched one chunk ahead) and results leave by TMA store from a swizzled staging
-//     tile.  The epilogue of the general kernel was instruction-fetch bound (10 k SASS lines, local
-//     memory spills); this one is ~1.5 k instructions per instantiation with no spills.
+// Inside a tile (what differs from the general kernel in gemm_umma.cu, which stays as the path for
+// pixel-shuffle stores, two residuals and odd shapes):
+//   * a cluster of two CTAs works on one 256 x BN tile with cta_group::2 MMAs: each CTA loads its own
+//     128 rows of A and HALF of the W tile (L2 -> SM operand traffic per MMA cycle 64 -> 48 B/clk);
+//   * K is staged in blocks of 32 (SWIZZLE_64B): a stage is 36 KB, four of them are in flight;
+//   * MMA / TMA issue runs in warp-uniform code with one elected lane, so descriptors live in uniform
+//     registers (the per-thread version spent ~12 instructions and a branch per MMA);
+//   * the epilogue is specialised per layer kind and moves no global memory itself: residual tiles
+//     arrive by TMA (one 3-plane box per warp and 16-column chunk, prefetched one chunk ahead) and
+//     results leave by TMA store from a swizzled staging tile (ring of three per warp).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "kernels.h"
 
@@ -25,6 +36,10 @@ namespace dmc {
 
 static char g_s3_err[512] = "";
 const char* gemm_s3_last_error() { return g_s3_err; }
+// 0, or which bounded wait of the chain kernel timed out before it trapped: 1 operand ring slot, 2 TMEM buffer,
+// 3 operand bytes, 4 accumulator, 5 residual tile, 6 previous layer's row tile (global counter), 9 smem alignment
+static volatile int* g_s3_trap = nullptr;
+int gemm_s3_trap_code() { return g_s3_trap ? *g_s3_trap : 0; }
 
 // ------------------------------------------------------------------ tensor maps (host)
 static PFN_cuTensorMapEncodeTiled_v12000 s3_get_encode() {
@@ -135,7 +150,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a broken pipeline traps (launch error) instead of hanging the GPU.
 __device__ __noinline__ void mbar_timeout(int* err, int code) {
-  if (err) atomicExch(err, code);
+  if (err) *reinterpret_cast<volatile int*>(err) = code;
   __threadfence_system();
   __trap();
 }
@@ -192,6 +207,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void tma_store_wait_read1() {   // at most one store still reading shared memory
   asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_1() {       // all but the newest bulk store are complete
+  asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -288,21 +306,39 @@ __device__ __forceinline__ float wsilu_fast(float x) {
 
 }  // namespace s3
 
-struct S3Params {
-  long long M;
-  int m_tiles;     // 256-row tiles
-  int n_tiles, k_blocks, BN, stages;
-  int n_out;       // destination columns
-  int dbg;         // probe switches: 1 no operand loads, 2 no MMA issue, 4 no epilogue TMA traffic, 8 no epilogue math
+
+enum { S3_PLAIN = 0, S3_WSILU = 1, S3_RES = 2, S3_PAIR = 3, S3_F32 = 4, S3_F32_WSILU = 5 };
+constexpr int kS3MaxStages = 5;
+
+struct alignas(64) S3StageDev {
+  CUtensorMap tmA, tmW, tmOut, tmRes;
   const float* bias;
   const float* scale;
+  int k_blocks, BN, n_tiles, n_out;
+  int kind;          // S3_*
+  int nterms;        // 6: fp32-grade split product (two accumulators), 1: hi*hi only
+  uint32_t need;     // increments of done[l-1][row tile] per launch that complete layer l-1 for a row tile
+  int publish;       // a later layer of the chain waits for this one: completed tiles are counted in done[l]
+};
+struct S3ChainParams {
+  S3StageDev st[kS3MaxStages];
+  const uint32_t* table;   // entries: layer << 28 | n tile << 20 | row tile
+  uint32_t* done;          // [layers][row tiles], monotonic across launches
+  int n_entries, MT;
+  uint32_t epoch;          // launch number (1-based): layer l-1 is complete at done == epoch * need
+  uint32_t stageBytes;     // operand ring stage (sized for the widest W tile of the chain)
+  int stages;
+  int dbg;                 // probe switches: 1 no operand loads, 2 no MMA issue, 4 no epilogue TMA traffic, 8 no epilogue math
   int* err;
 };
 
 constexpr int kS3BK = 32;
 constexpr int kS3APlane = 128 * kS3BK * 2;        // one plane of a 128 x 32 bf16 tile
 constexpr int kS3EpiWarps = 8;
-constexpr int kS3Threads = 64 + 32 * kS3EpiWarps; // TMA warp, MMA warp, 8 epilogue warps
+// warp group 0: TMA producer, MMA issuer, two spare warps (56 registers); warp groups 1-2: eight epilogue
+// warps (224 registers, setmaxnreg) -- the six inlined epilogue variants do not fit the 168 registers a
+// 384-thread CTA gets by default
+constexpr int kS3Threads = 128 + 32 * kS3EpiWarps;
 constexpr int kS3ChunkBytes = 3 * 32 * 32;        // [3 planes][32 rows][16 bf16]
 constexpr int kS3Ring = 3;                        // staging tiles per epilogue warp (residual in -> result out)
 constexpr int kS3WarpSmem = kS3Ring * kS3ChunkBytes;
@@ -317,53 +353,242 @@ __device__ __forceinline__ uint64_t s3_desc(uint32_t saddr) {
   return ((uint64_t)hi << 32) | lo;
 }
 
-// kF32: the result leaves as fp32 rows [M, ld] (one 2-D TMA store of 16 columns x 32 rows per chunk,
-// SWIZZLE_64B staging) instead of S3 planes -- used where the consumer is not a contraction
-// (the depthwise 3x3 after dc.0, the pixel-shuffle tail after the reconstruction head).
-template <int kAct, int kPack, int kRes, int kF32>
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// orders this thread's generic-proxy global accesses (the flag acquire / release) with its async-proxy
+// ones (TMA loads / stores of the tensors the flag guards)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// Per-warp epilogue state that lives across tiles and layers.
+struct EpiCtx {
+  uint32_t ringBuf;          // this warp's staging ring
+  uint32_t barRes;           // its kS3Ring residual barriers (8 B apart)
+  uint32_t slot;             // ring position of the chunk being processed (advances with every stored chunk)
+  uint32_t res_phase;        // bit s: parity the next residual wait on ring barrier s has to see
+  int lane, quad, half;
+  uint32_t rank;
+  bool epi_mem;
+};
+
+__device__ __forceinline__ int s3_nchunk(int kind, int BN, int half) {
+  if (kind == S3_PAIR) return (half * 64 < BN) ? 2 : 0;   // one 64-column group (32 values + 32 partners) per warp
+  return BN >> 5;
+}
+// destination column of chunk c of N tile nt for this warp
+__device__ __forceinline__ int s3_dest_col(int kind, int BN, int half, int nt, int c) {
+  const int n_idx = nt * BN;
+  if (kind == S3_PAIR) return ((n_idx >> 6) + half) * 32 + 16 * c;
+  return n_idx + half * (BN >> 1) + 16 * c;
+}
+
+// One tile of one layer, one epilogue warp.  `next_res(c)` is called once per chunk (after the staging
+// ring slot two chunks back is known to be free) so the caller can prefetch the residual of the item
+// that follows chunk c.
+// The fields of a layer the epilogue needs, read ONCE per tile into registers (the layer record sits in the
+// kernel parameters under a run-time index: every access is an indexed constant load).
+struct StageRegs {
+  const float* bias;
+  const float* scale;
+  const CUtensorMap* tmOut;
+  const CUtensorMap* tmRes;
+  int BN, n_out, kind;
+  uint32_t need;
+  bool two_acc;
+};
+__device__ __forceinline__ StageRegs s3_load_stage(const S3StageDev& S) {
+  StageRegs r;
+  r.bias = S.bias; r.scale = S.scale; r.tmOut = &S.tmOut; r.tmRes = &S.tmRes;
+  r.BN = S.BN; r.n_out = S.n_out; r.kind = S.kind; r.need = S.need; r.two_acc = S.nterms != 1;
+  return r;
+}
+
+template <int kAct, int kPack, int kRes, int kF32, class NextRes, class Release>
+__device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, int mt, int nt, uint32_t taddr,
+                                                 int* err, NextRes next_res, Release release_tmem) {
+  using namespace s3;
+  const int lane = x.lane;
+  const int nchunk = s3_nchunk(kPack == PACK_PAIR ? S3_PAIR : S3_PLAIN, S.BN, x.half);
+  const int acc0 = (kPack == PACK_PAIR) ? x.half * 64 : x.half * (S.BN >> 1);
+  const int n_idx = nt * S.BN;
+  const int row0 = mt * 256 + (int)x.rank * 128 + x.quad * 32;
+  const uint32_t swz = (uint32_t)((lane >> 2) & 1) << 4;        // SWIZZLE_32B: 16-byte unit ^= row bit 2
+  const uint32_t rowOff = (uint32_t)lane * 32u;
+  const bool two_acc = S.two_acc;
+  for (int c = 0; c < nchunk; ++c) {
+    const int acol = acc0 + 16 * c;                     // accumulator column of this chunk
+    const int dcol = s3_dest_col(kPack == PACK_PAIR ? S3_PAIR : S3_PLAIN, S.BN, x.half, nt, c);
+    const bool valid = dcol < S.n_out;                  // warp-uniform
+    // The staging tile two chunks back must have been read by its TMA store before it is reused
+    // (by the residual load issued next, or by this chunk's own result when there is no residual).
+    if (lane == 0) tma_store_wait_read1();
+    __syncwarp();
+    next_res(c);
+    float v[16];
+    if (valid) {
+      uint32_t a[16], b[16];
+      tc_ld16(taddr + acol, a);
+      if (two_acc) tc_ld16(taddr + 128u + acol, b);
+      const float4* bp = reinterpret_cast<const float4*>(S.bias + n_idx + acol);
+      float bias[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 q = __ldg(bp + i);
+        bias[4 * i] = q.x; bias[4 * i + 1] = q.y; bias[4 * i + 2] = q.z; bias[4 * i + 3] = q.w;
+      }
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float t = __uint_as_float(a[i]);
+        if (two_acc) t = add_rn(t, __uint_as_float(b[i]));
+        t = add_rn(t, bias[i]);
+        if (kAct == ACT_WSILU) t = wsilu_fast(t);
+        v[i] = t;
+      }
+      if (kPack == PACK_PAIR) {
+        tc_ld16(taddr + acol + 32, a);
+        if (two_acc) tc_ld16(taddr + 128u + acol + 32, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 q = __ldg(bp + 8 + i);
+          bias[4 * i] = q.x; bias[4 * i + 1] = q.y; bias[4 * i + 2] = q.z; bias[4 * i + 3] = q.w;
+        }
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float t = __uint_as_float(a[i]);
+          if (two_acc) t = add_rn(t, __uint_as_float(b[i]));
+          t = add_rn(t, bias[i]);
+          if (kAct == ACT_WSILU) t = wsilu_fast(t);
+          v[i] = add_rn(v[i], t);
+        }
+      }
+    }
+    if (c == nchunk - 1) release_tmem();      // accumulator fully read: hand the TMEM buffer back
+    if (!valid) continue;
+    const uint32_t tileBuf = x.ringBuf + x.slot * kS3ChunkBytes;
+    if (kRes && x.epi_mem) {
+      mbar_wait(x.barRes + 8u * x.slot, (x.res_phase >> x.slot) & 1u, err, 5);
+      x.res_phase ^= 1u << x.slot;
+      const uint32_t src = tileBuf + rowOff;
+      float t[16];
+#pragma unroll
+      for (int pl = 2; pl >= 0; --pl) {    // (lo + mid) + hi, exactly join3
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const uint4 q = ld_shared_v4(src + pl * 1024 + (((uint32_t)hf << 4) ^ swz));
+          const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float lo = bf16lo(u[k]), hi = bf16hi(u[k]);
+            const int i = 8 * hf + 2 * k;
+            t[i] = pl == 2 ? lo : add_rn(t[i], lo);
+            t[i + 1] = pl == 2 ? hi : add_rn(t[i + 1], hi);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = add_rn(v[i], t[i]);
+    }
+    if (S.scale) {
+      const float4* sp = reinterpret_cast<const float4*>(S.scale + dcol);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 q = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (dcol + 4 * i < S.n_out) q = __ldg(sp + i);
+        v[4 * i] = mul_rn(v[4 * i], q.x); v[4 * i + 1] = mul_rn(v[4 * i + 1], q.y);
+        v[4 * i + 2] = mul_rn(v[4 * i + 2], q.z); v[4 * i + 3] = mul_rn(v[4 * i + 3], q.w);
+      }
+    }
+    if (kF32) {
+      // fp32 rows: 64 B per lane, 16-byte unit u of row r sits at u ^ ((r >> 1) & 3)  (SWIZZLE_64B)
+      const uint32_t dst = tileBuf + (uint32_t)lane * 64u;
+      const uint32_t sw64 = (uint32_t)((lane >> 1) & 3) << 4;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        st_shared_v4(dst + (((uint32_t)u << 4) ^ sw64), __float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
+                     __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0 && x.epi_mem) tma_store_2d(S.tmOut, tileBuf, dcol, row0);
+    } else {
+      // exact 3-way split, two elements per conversion
+      uint32_t ph_[8], pm_[8], pl_[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x0 = v[2 * i], x1 = v[2 * i + 1];
+        const uint32_t h = cvt_bf16x2(x0, x1);
+        const float r0 = sub_rn(x0, bf16lo(h)), r1 = sub_rn(x1, bf16hi(h));
+        const uint32_t m = cvt_bf16x2(r0, r1);
+        ph_[i] = h;
+        pm_[i] = m;
+        pl_[i] = cvt_bf16x2(sub_rn(r0, bf16lo(m)), sub_rn(r1, bf16hi(m)));
+      }
+      const uint32_t dst = tileBuf + rowOff;
+      st_shared_v4(dst + swz, ph_[0], ph_[1], ph_[2], ph_[3]);
+      st_shared_v4(dst + (16u ^ swz), ph_[4], ph_[5], ph_[6], ph_[7]);
+      st_shared_v4(dst + 1024 + swz, pm_[0], pm_[1], pm_[2], pm_[3]);
+      st_shared_v4(dst + 1024 + (16u ^ swz), pm_[4], pm_[5], pm_[6], pm_[7]);
+      st_shared_v4(dst + 2048 + swz, pl_[0], pl_[1], pl_[2], pl_[3]);
+      st_shared_v4(dst + 2048 + (16u ^ swz), pl_[4], pl_[5], pl_[6], pl_[7]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0 && x.epi_mem) tma_store(S.tmOut, tileBuf, dcol, row0);
+    }
+    if (++x.slot == kS3Ring) x.slot = 0;
+  }
+}
+
 __global__ void __launch_bounds__(kS3Threads, 1)
-k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-          const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-          const S3Params p) {
+k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   using namespace s3;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t rank = blockIdx.x & 1u;             // cluster = (2,1,1): rank in the pair, provably warp-uniform
   const bool leader = rank == 0;
-  const uint32_t wRows = (uint32_t)p.BN >> 1;
-  const uint32_t wPlane = wRows * (kS3BK * 2);
-  const uint32_t stageBytes = 3u * (kS3APlane + wPlane);
+  const uint32_t stageBytes = p.stageBytes;
   const uint32_t epiBase = base + (uint32_t)p.stages * stageBytes;
   const uint32_t barBase = epiBase + kS3EpiWarps * kS3WarpSmem;
-  // barriers: full[8] | empty[8] | tfull[2] | tempty[2] | res[8 warps][3 (+1 pad)] | tmem slot
+  // barriers: full[8] | empty[8] | tfull[2] | tempty[2] | res[8 warps][3 (+1 pad)] | tmem slot | deps_ok
   auto bar_full = [&](int s) { return barBase + 8u * s; };
   auto bar_empty = [&](int s) { return barBase + 64u + 8u * s; };
   auto bar_tfull = [&](int b) { return barBase + 128u + 8u * b; };
   auto bar_tempty = [&](int b) { return barBase + 144u + 8u * b; };
   auto bar_res = [&](int w, int b) { return barBase + 160u + 32u * w + 8u * b; };
   const uint32_t tmemSlot = barBase + 416u;
+  const uint32_t depsOk = barBase + 420u;            // number of this CTA's tiles whose dependencies are met
+  const uint32_t warpsDone = barBase + 424u;         // [4] epilogue warps of this CTA that finished tile (t & 3)
 
   if (warp == 0 && lane == 0) {
     if (base & 1023u) {
-      if (p.err) atomicExch(p.err, 9);
-      __trap();
+      mbar_timeout(p.err, 9);
     }
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
-    if (kRes) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmRes) : "memory");
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(bar_full(s), 1);
+      mbar_init(bar_full(s), (p.dbg & 1) ? 2 : 1);   // probe mode without loads: one plain arrival per CTA
       mbar_init(bar_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull(b), 1);
       mbar_init(bar_tempty(b), kS3EpiWarps * 2);
     }
-    for (int w = 0; w < kS3EpiWarps; ++w) {
+    for (int w = 0; w < kS3EpiWarps; ++w)
       for (int b = 0; b < kS3Ring; ++b) mbar_init(bar_res(w, b), 1);
-    }
+    *reinterpret_cast<volatile uint32_t*>(smem_raw + (depsOk - base)) = 0u;
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<volatile uint32_t*>(smem_raw + (warpsDone - base) + 4 * i) = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -377,33 +602,52 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   cluster_sync_all();                      // peer barriers are initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmemSlot - base));
-
   const int unit = (int)(blockIdx.x >> 1);
   const int units = (int)(gridDim.x >> 1);
-  const int total_tiles = p.m_tiles * p.n_tiles;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
   if (warp == 0) {
     // ------------------------------------------------------------ operand producer (both CTAs)
     // (whole warp walks the loop, one elected lane issues: addresses stay in uniform registers)
     int s = 0;
-    uint32_t ph = 0;
-    for (int tile = unit; tile < total_tiles; tile += units) {
-      const int mt = tile / p.n_tiles;
+    uint32_t ph = 0, tcount = 0;
+    for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
+      const uint32_t e = __ldg(p.table + ei);
+      const int l = (int)(e >> 28), nt = (int)((e >> 20) & 0xffu), mt = (int)(e & 0xfffffu);
+      const S3StageDev& S = p.st[l];
+      if (l > 0 && S.need != 0u) {
+        // all N tiles of the previous layer for these rows must be stored
+        const uint32_t* flag = p.done + (size_t)(l - 1) * p.MT + mt;
+        const uint32_t target = p.epoch * S.need;
+        if ((int)(ld_acquire_gpu(flag) - target) < 0) {
+          const long long t0 = clock64();
+          while ((int)(ld_acquire_gpu(flag) - target) < 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > 6000000000LL) mbar_timeout(p.err, 6);
+          }
+        }
+        fence_proxy_async_global();          // the TMA reads below are ordered after the acquire
+      }
+      if (lane == 0) st_release_cta_shared(depsOk, tcount + 1);
+      const uint32_t wRows = (uint32_t)S.BN >> 1;
+      const uint32_t tx = 2u * 3u * (kS3APlane + wRows * (kS3BK * 2));
       const int m_idx = mt * 256 + (int)rank * 128;
-      const int n_idx = (tile - mt * p.n_tiles) * p.BN + (int)(rank * wRows);
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
+      const int n_idx = nt * S.BN + (int)(rank * wRows);
+      for (int kb = 0; kb < S.k_blocks; ++kb) {
         mbar_wait(bar_empty(s), ph ^ 1, p.err, 1);
         const uint32_t sa = base + s * stageBytes;
         const uint32_t sw = sa + 3 * kS3APlane;
         if (elect_one()) {
           if (p.dbg & 1) {
             if (leader) mbar_arrive(bar_full(s));
+            else mbar_arrive_cluster(mapa(bar_full(s), 0));
           } else {
-            // both CTAs' bytes complete on the LEADER's barrier, which the leader arms for two stages' worth
-            if (leader) mbar_expect_tx(bar_full(s), 2u * stageBytes);
+            // both CTAs' bytes complete on the LEADER's barrier, which the leader arms for both
+            if (leader) mbar_expect_tx(bar_full(s), tx);
             const uint32_t lbar = mapa(bar_full(s), 0);
-            tma_load_pair(sa, &tmA, kb * kS3BK, m_idx, lbar);
-            tma_load_pair(sw, &tmW, kb * kS3BK, n_idx, lbar);
+            tma_load_pair(sa, &S.tmA, kb * kS3BK, m_idx, lbar);
+            tma_load_pair(sw, &S.tmW, kb * kS3BK, n_idx, lbar);
           }
         }
         __syncwarp();
@@ -415,19 +659,24 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // The whole warp walks the loop so that every address below is warp-uniform (uniform registers,
     // no per-MMA register -> uniform-register shuffling); one elected lane issues.
     if (leader) {
-      // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
-      // N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | (16u << 24);
-      const uint32_t aStep = kS3APlane >> 4, wStep = wPlane >> 4;
+      const uint32_t aStep = kS3APlane >> 4;
       int s = 0;
       uint32_t ph = 0, tcount = 0;
-      for (int tile = unit; tile < total_tiles; tile += units, ++tcount) {
+      for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
+        const uint32_t e = __ldg(p.table + ei);
+        const S3StageDev& S = p.st[e >> 28];
+        // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
+        // N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(S.BN >> 3) << 17) | (16u << 24);
+        const uint32_t wStep = ((uint32_t)(S.BN >> 1) * (kS3BK * 2)) >> 4;
+        const int k_blocks = S.k_blocks;
+        const bool six = S.nterms != 1;
         const uint32_t buf = tcount & 1;
         mbar_wait(bar_tempty(buf), ((tcount >> 1) & 1) ^ 1, p.err, 2);
         tc_fence_after();
         const uint32_t d_main = tmem_base + buf * 256u;
         const uint32_t d_small = d_main + 128u;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(bar_full(s), ph, p.err, 3);
           tc_fence_after();
           const uint32_t sa = base + s * stageBytes;
@@ -443,209 +692,149 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const uint64_t a0 = da + 2 * ks, a1 = a0 + aStep, a2 = a0 + 2 * aStep;
                 const uint64_t w0 = dw + 2 * ks, w1 = w0 + wStep, w2 = w0 + 2 * wStep;
                 tc_mma_pair(d_main, a0, w0, idesc, ks == 0 ? first : 1u);
-                tc_mma_pair(d_small, a0, w2, idesc, ks == 0 ? first : 1u);
-                tc_mma_pair(d_small, a2, w0, idesc, 1u);
-                tc_mma_pair(d_small, a1, w1, idesc, 1u);
-                tc_mma_pair(d_small, a0, w1, idesc, 1u);
-                tc_mma_pair(d_small, a1, w0, idesc, 1u);
+                if (six) {
+                  tc_mma_pair(d_small, a0, w2, idesc, ks == 0 ? first : 1u);
+                  tc_mma_pair(d_small, a2, w0, idesc, 1u);
+                  tc_mma_pair(d_small, a1, w1, idesc, 1u);
+                  tc_mma_pair(d_small, a0, w1, idesc, 1u);
+                  tc_mma_pair(d_small, a1, w0, idesc, 1u);
+                }
               }
             }
             tc_commit_pair(bar_empty(s));
-            if (kb == p.k_blocks - 1) tc_commit_pair(bar_tfull(buf));
+            if (kb == k_blocks - 1) tc_commit_pair(bar_tfull(buf));
           }
           __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
+  }
   } else {
     // ------------------------------------------------------------ epilogue warps
-    const int ew = warp - 2;
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                  // two warps per quadrant split the columns
-    // chunks of 16 destination columns this warp produces per tile, and where they sit in the accumulator
-    int nchunk, acc0;
-    if (kPack == PACK_PAIR) {
-      nchunk = (half * 64 < p.BN) ? 2 : 0;     // one 64-column group (32 values + 32 partners) per warp
-      acc0 = half * 64;
-    } else {
-      nchunk = p.BN >> 5;
-      acc0 = half * (p.BN >> 1);
-    }
-    // ring of staging tiles: chunk k of this warp lives in tile k % kS3Ring -- first as the residual
-    // (TMA load, issued one chunk ahead), then overwritten in place by the result (TMA store)
-    const uint32_t ringBuf = epiBase + (uint32_t)ew * kS3WarpSmem;
-    const uint32_t swz = (uint32_t)((lane >> 2) & 1) << 4;        // SWIZZLE_32B: 16-byte unit ^= row bit 2
-    const uint32_t rowOff = (uint32_t)lane * 32u;
-    const bool epi_mem = !(p.dbg & 12);
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+    const int ew = warp - 4;
+    EpiCtx x;
+    x.ringBuf = epiBase + (uint32_t)ew * kS3WarpSmem;
+    x.barRes = bar_res(ew, 0);
+    x.slot = 0; x.res_phase = 0;
+    x.lane = lane;
+    x.quad = warp & 3;                         // TMEM lane quadrant this warp may read
+    x.half = ew >> 2;                          // two warps per quadrant split the columns
+    x.rank = rank;
+    x.epi_mem = !(p.dbg & 12);
 
-    // destination column of chunk c of tile `tile`
-    auto dest_col = [&](int tile, int c) {
-      const int n_idx = (tile % p.n_tiles) * p.BN;
-      if (kPack == PACK_PAIR) return ((n_idx >> 6) + half) * 32 + 16 * c;
-      return n_idx + acc0 + 16 * c;
-    };
-    auto dest_row = [&](int tile) { return (tile / p.n_tiles) * 256 + (int)rank * 128 + quad * 32; };
-
-    uint32_t ld_slot = 0, ld_par = 0;           // ring position / barrier parity of the next residual load
-    uint32_t slot = 0, par = 0;                 // ... of the chunk being processed
-    auto issue_res = [&](int tile, int c) {     // whole warp; lane 0 issues
-      const int dcol = dest_col(tile, c);
-      if (dcol >= p.n_out) return;
-      if (lane == 0) {
-        mbar_expect_tx(bar_res(ew, ld_slot), kS3ChunkBytes);
-        tma_load_local(ringBuf + ld_slot * kS3ChunkBytes, &tmRes, dcol, dest_row(tile), bar_res(ew, ld_slot));
+    // Residual prefetch of chunk c2 of this CTA's tile number t2 (table entry e2); whole warp, lane 0 issues.
+    // The first chunk of a NEW tile is only prefetched if the producer warp has already seen that tile's
+    // dependencies satisfied (its residual may be written by an earlier layer of this chain); this check
+    // never blocks -- blocking here could close a cycle through a tile this warp has not published yet --
+    // and a prefetch that was skipped is issued when the tile starts (res_tile != tile number).
+    uint32_t res_tile = 0xffffffffu;
+    // `slot2` is the ring tile that chunk will be processed in; R2 are the (cached) fields of its layer.
+    auto issue_res = [&](const StageRegs& R2, uint32_t e2, int c2, uint32_t t2, bool force, uint32_t slot2) {
+      if (R2.kind != S3_RES || !x.epi_mem) return;
+      const int nt2 = (int)((e2 >> 20) & 0xffu), mt2 = (int)(e2 & 0xfffffu);
+      if (c2 == 0) {
+        if (!force && (int)(ld_acquire_cta_shared(depsOk) - (t2 + 1)) < 0) return;
+        if (R2.need != 0u) fence_proxy_async_global();
+        res_tile = t2;
       }
-      if (++ld_slot == kS3Ring) { ld_slot = 0; ld_par ^= 1; }
+      const int dcol = s3_dest_col(S3_PLAIN, R2.BN, x.half, nt2, c2);
+      if (dcol >= R2.n_out) return;
+      if (lane == 0) {
+        const uint32_t bar = x.barRes + 8u * slot2;
+        mbar_expect_tx(bar, kS3ChunkBytes);
+        tma_load_local(x.ringBuf + slot2 * kS3ChunkBytes, R2.tmRes, dcol,
+                       mt2 * 256 + (int)rank * 128 + x.quad * 32, bar);
+      }
     };
-    if (kRes && epi_mem && nchunk > 0 && unit < total_tiles) issue_res(unit, 0);
 
     uint32_t tcount = 0;
-    for (int tile = unit; tile < total_tiles; tile += units, ++tcount) {
+    uint32_t pend_l = 0, pend_mt = 0, pend_t = 0;   // tile whose completion is still to be published
+    bool pending = false;
+    // lane 0, after this warp's stores of the pending tile are complete: the LAST of the CTA's eight epilogue
+    // warps (cta-scope counter; tiles t and t+4 cannot be in flight together) does the one gpu-scope release
+    auto publish = [&]() {
+      const uint32_t cnt = warpsDone + 4u * (pend_t & 3u);
+      uint32_t old;
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt) : "memory");
+      if (old == kS3EpiWarps - 1) {
+        asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(cnt), "r"(0u) : "memory");
+        fence_proxy_async_global();
+        red_release_gpu_add(p.done + (size_t)pend_l * p.MT + pend_mt, 1u);
+      }
+    };
+    uint32_t e_next = unit < p.n_entries ? __ldg(p.table + unit) : 0u;
+    int l_cached = -1;
+    StageRegs S;
+    for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
+      const uint32_t e = e_next;
+      const int l = (int)(e >> 28), nt = (int)((e >> 20) & 0xffu), mt = (int)(e & 0xfffffu);
+      if (l != l_cached) { S = s3_load_stage(p.st[l]); l_cached = l; }
       const uint32_t buf = tcount & 1;
-      const int n_idx = (tile % p.n_tiles) * p.BN;
-      const int row0 = dest_row(tile);
+      const int nchunk = s3_nchunk(S.kind, S.BN, x.half);
+      // the first residual of the next tile is prefetched early only within a layer (same cached fields);
+      // across a layer boundary it is issued when that tile starts
+      bool has_next = ei + units < p.n_entries;
+      if (has_next) {
+        e_next = __ldg(p.table + ei + units);
+        has_next = (e_next >> 28) == (uint32_t)l;
+      }
+      // Publishing the previous tile: if this tile's accumulator is not ready yet there is idle time (and this
+      // tile may even depend on the previous one): wait for the stores and publish now.  If it is ready, its
+      // dependencies were met long ago, so the publication can ride along with chunk 1 below at no cost.
+      if (pending && !mbar_try(bar_tfull(buf), (tcount >> 1) & 1)) {
+        if (lane == 0) { tma_store_wait_all(); publish(); }
+        pending = false;
+      }
       mbar_wait(bar_tfull(buf), (tcount >> 1) & 1, p.err, 4);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256u;
-      if (nchunk == 0 || (p.dbg & 8)) {
+      if (res_tile != tcount) issue_res(S, e, 0, tcount, true, x.slot);   // the early prefetch of chunk 0 was not possible
+      const uint32_t taddr = tmem_base + ((uint32_t)(x.quad * 32) << 16) + buf * 256u;
+      auto release_tmem = [&]() {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (leader) mbar_arrive(bar_tempty(buf));
           else mbar_arrive_cluster(mapa(bar_tempty(buf), 0));
         }
-        continue;
-      }
-      for (int c = 0; c < nchunk; ++c) {
-        const int acol = acc0 + 16 * c;                     // accumulator column of this chunk
-        const int dcol = dest_col(tile, c);
-        const bool valid = dcol < p.n_out;                  // warp-uniform
-        // The staging tile two chunks back must have been read by its TMA store before it is reused
-        // (by the residual load issued next, or by this chunk's own result when there is no residual).
-        if (lane == 0) tma_store_wait_read1();
-        __syncwarp();
-        if (kRes && epi_mem) {                  // prefetch the residual tile of the next chunk
-          int nt = tile, nc = c + 1;
-          if (nc == nchunk) { nc = 0; nt += units; }
-          if (nt < total_tiles) issue_res(nt, nc);
-        }
-        float v[16];
-        if (valid) {
-          uint32_t a[16], b[16];
-          tc_ld16(taddr + acol, a);
-          tc_ld16(taddr + 128u + acol, b);
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n_idx + acol);
-          float bias[16];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 q = __ldg(bp + i);
-            bias[4 * i] = q.x; bias[4 * i + 1] = q.y; bias[4 * i + 2] = q.z; bias[4 * i + 3] = q.w;
-          }
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float t = add_rn(add_rn(__uint_as_float(a[i]), __uint_as_float(b[i])), bias[i]);
-            if (kAct == ACT_WSILU) t = wsilu_fast(t);
-            v[i] = t;
-          }
-          if (kPack == PACK_PAIR) {
-            tc_ld16(taddr + acol + 32, a);
-            tc_ld16(taddr + 128u + acol + 32, b);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 q = __ldg(bp + 8 + i);
-              bias[4 * i] = q.x; bias[4 * i + 1] = q.y; bias[4 * i + 2] = q.z; bias[4 * i + 3] = q.w;
-            }
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float t = add_rn(add_rn(__uint_as_float(a[i]), __uint_as_float(b[i])), bias[i]);
-              if (kAct == ACT_WSILU) t = wsilu_fast(t);
-              v[i] = add_rn(v[i], t);
-            }
-          }
-        }
-        if (c == nchunk - 1) {                 // accumulator fully read: hand the TMEM buffer back
-          tc_fence_before();
-          __syncwarp();
+      };
+      const bool stored0 = x.epi_mem && s3_dest_col(S.kind, S.BN, x.half, nt, 0) < S.n_out;
+      auto next_res = [&](int c) {
+        if (c == 1 && pending) {               // only chunk 0's store (if any) is newer than the previous tile's
           if (lane == 0) {
-            if (leader) mbar_arrive(bar_tempty(buf));
-            else mbar_arrive_cluster(mapa(bar_tempty(buf), 0));
+            if (stored0) tma_store_wait_1(); else tma_store_wait_all();
+            publish();
           }
+          pending = false;
         }
-        if (!valid) continue;
-        if (kRes && epi_mem) {
-          mbar_wait(bar_res(ew, slot), par, p.err, 5);
-          const uint32_t src = ringBuf + slot * kS3ChunkBytes + rowOff;
-          float t[16];
-#pragma unroll
-          for (int pl = 2; pl >= 0; --pl) {    // (lo + mid) + hi, exactly join3
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const uint4 q = ld_shared_v4(src + pl * 1024 + (((uint32_t)hf << 4) ^ swz));
-              const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float lo = bf16lo(u[k]), hi = bf16hi(u[k]);
-                const int i = 8 * hf + 2 * k;
-                t[i] = pl == 2 ? lo : add_rn(t[i], lo);
-                t[i + 1] = pl == 2 ? hi : add_rn(t[i + 1], hi);
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = add_rn(v[i], t[i]);
+        // the item after chunk c lands one ring tile further if chunk c itself stores something
+        const bool valid_c = s3_dest_col(S.kind, S.BN, x.half, nt, c) < S.n_out;
+        uint32_t slot2 = x.slot + (valid_c ? 1u : 0u);
+        if (slot2 == kS3Ring) slot2 = 0;
+        if (c + 1 < nchunk) issue_res(S, e, c + 1, tcount, false, slot2);
+        else if (has_next) issue_res(S, e_next, 0, tcount + 1, false, slot2);
+      };
+      if (nchunk == 0 || (p.dbg & 8)) {
+        release_tmem();
+      } else {
+        switch (S.kind) {
+          case S3_PLAIN: s3_epilogue_tile<ACT_NONE, PACK_PLAIN, 0, 0>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
+          case S3_WSILU: s3_epilogue_tile<ACT_WSILU, PACK_PLAIN, 0, 0>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
+          case S3_RES: s3_epilogue_tile<ACT_NONE, PACK_PLAIN, 1, 0>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
+          case S3_PAIR: s3_epilogue_tile<ACT_WSILU, PACK_PAIR, 0, 0>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
+          case S3_F32: s3_epilogue_tile<ACT_NONE, PACK_PLAIN, 0, 1>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
+          default: s3_epilogue_tile<ACT_WSILU, PACK_PLAIN, 0, 1>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
         }
-        if (p.scale) {
-          const float4* sp = reinterpret_cast<const float4*>(p.scale + dcol);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float4 q = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (dcol + 4 * i < p.n_out) q = __ldg(sp + i);
-            v[4 * i] = mul_rn(v[4 * i], q.x); v[4 * i + 1] = mul_rn(v[4 * i + 1], q.y);
-            v[4 * i + 2] = mul_rn(v[4 * i + 2], q.z); v[4 * i + 3] = mul_rn(v[4 * i + 3], q.w);
-          }
-        }
-        if (kF32) {
-          // fp32 rows: 64 B per lane, 16-byte unit u of row r sits at u ^ ((r >> 1) & 3)  (SWIZZLE_64B)
-          const uint32_t dst = ringBuf + slot * kS3ChunkBytes + (uint32_t)lane * 64u;
-          const uint32_t sw64 = (uint32_t)((lane >> 1) & 3) << 4;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            st_shared_v4(dst + (((uint32_t)u << 4) ^ sw64), __float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
-                         __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0 && epi_mem) tma_store_2d(&tmOut, ringBuf + slot * kS3ChunkBytes, dcol, row0);
-          if (++slot == kS3Ring) { slot = 0; par ^= 1; }
-          continue;
-        }
-        // exact 3-way split, two elements per conversion
-        uint32_t ph_[8], pm_[8], pl_[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float x0 = v[2 * i], x1 = v[2 * i + 1];
-          const uint32_t h = cvt_bf16x2(x0, x1);
-          const float r0 = sub_rn(x0, bf16lo(h)), r1 = sub_rn(x1, bf16hi(h));
-          const uint32_t m = cvt_bf16x2(r0, r1);
-          ph_[i] = h;
-          pm_[i] = m;
-          pl_[i] = cvt_bf16x2(sub_rn(r0, bf16lo(m)), sub_rn(r1, bf16hi(m)));
-        }
-        const uint32_t dst = ringBuf + slot * kS3ChunkBytes + rowOff;
-        st_shared_v4(dst + swz, ph_[0], ph_[1], ph_[2], ph_[3]);
-        st_shared_v4(dst + (16u ^ swz), ph_[4], ph_[5], ph_[6], ph_[7]);
-        st_shared_v4(dst + 1024 + swz, pm_[0], pm_[1], pm_[2], pm_[3]);
-        st_shared_v4(dst + 1024 + (16u ^ swz), pm_[4], pm_[5], pm_[6], pm_[7]);
-        st_shared_v4(dst + 2048 + swz, pl_[0], pl_[1], pl_[2], pl_[3]);
-        st_shared_v4(dst + 2048 + (16u ^ swz), pl_[4], pl_[5], pl_[6], pl_[7]);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0 && epi_mem) tma_store(&tmOut, ringBuf + slot * kS3ChunkBytes, dcol, row0);
-        if (++slot == kS3Ring) { slot = 0; par ^= 1; }
       }
+      if (pending) {                           // (tiles in which this warp has fewer than two chunks)
+        if (lane == 0) { tma_store_wait_all(); publish(); }
+        pending = false;
+      }
+      pend_l = (uint32_t)l; pend_mt = (uint32_t)mt; pend_t = tcount;
+      pending = p.st[l].publish != 0;
     }
+    if (pending && lane == 0) { tma_store_wait_all(); publish(); }
     if (lane == 0) tma_store_wait_all();
   }
 
@@ -658,12 +847,12 @@ k_gemm_s3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
 }
 
-// ------------------------------------------------------------------ host launcher
+// ------------------------------------------------------------------ host side
 static int g_s3_dbg = 0;
 void gemm_s3_set_debug(int mask) { g_s3_dbg = mask; }
 
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit) {
-  if (nsplit != 3 || !w.tmap_s3 || e.do_clamp || e.res2.p) return false;
+  if ((nsplit != 3 && nsplit != 1) || !w.tmap_s3 || e.do_clamp || e.res2.p) return false;
   if (w.BN % 32 || w.BN > 128) return false;
   if (e.out_f32) {                       // fp32 rows: plain layout, no residual, and not both outputs at once
     return !e.out.p && e.pack == PACK_PLAIN && !e.res1.p && (e.act == ACT_NONE || e.act == ACT_WSILU) &&
@@ -678,24 +867,151 @@ bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit) {
   return false;
 }
 
-template <int kAct, int kPack, int kRes, int kF32>
-static cudaError_t launch_s3(int grid, int smem, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tw,
-                             const CUtensorMap& to, const CUtensorMap& tr, const S3Params& p) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    int dev = 0, smem_max = 0;
+struct S3Chain {
+  S3ChainParams p;
+  int n_stages = 0;
+  int grid = 0, smem = 0;
+  uint32_t* d_table = nullptr;
+  uint32_t* d_done = nullptr;
+  const float* scale_table[kS3MaxStages] = {};   // per-QP tables: row picked at launch
+  int scale_C[kS3MaxStages] = {};
+};
+
+static int s3_kind(const Epi& e) {
+  if (e.out_f32) return e.act == ACT_WSILU ? S3_F32_WSILU : S3_F32;
+  if (e.pack == PACK_PAIR) return S3_PAIR;
+  if (e.act == ACT_WSILU) return S3_WSILU;
+  return e.res1.p ? S3_RES : S3_PLAIN;
+}
+
+int s3_chain_max_stages() { return kS3MaxStages; }
+
+S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
+  static int smem_max = 0;
+  static int* d_err = nullptr;
+  if (!smem_max) {
+    int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_s3<kAct, kPack, kRes, kF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem_max);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (cudaFuncSetAttribute(k_gemm_s3_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) {
+      snprintf(g_s3_err, sizeof g_s3_err, "cudaFuncSetAttribute(max dynamic smem=%d) failed", smem_max);
+      smem_max = 0;
+      return nullptr;
+    }
+    // the code of a bounded wait that gave up lives in mapped host memory: it survives the trap
+    int* h_trap = nullptr;
+    if (cudaHostAlloc((void**)&h_trap, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+      *h_trap = 0;
+      g_s3_trap = h_trap;
+      cudaHostGetDevicePointer((void**)&d_err, h_trap, 0);
+    }
   }
+  if (n < 1 || n > kS3MaxStages) {
+    snprintf(g_s3_err, sizeof g_s3_err, "s3_chain_create: %d stages (max %d)", n, kS3MaxStages);
+    return nullptr;
+  }
+  S3Chain* c = new S3Chain();
+  memset(&c->p, 0, sizeof c->p);
+  c->n_stages = n;
+  const int MT = (int)((M + 255) / 256);
+  int maxBN = 0, tiles_per_step = 0;
+  for (int l = 0; l < n; ++l) {
+    const S3StageDesc& d = stages[l];
+    if (!gemm_s3_supports(*d.w, d.e, d.nsplit)) {
+      snprintf(g_s3_err, sizeof g_s3_err, "s3_chain_create: stage %d unsupported (BN=%d act=%d pack=%d)", l, d.w->BN,
+               d.e.act, d.e.pack);
+      delete c;
+      return nullptr;
+    }
+    S3StageDev& S = c->p.st[l];
+    memcpy(&S.tmA, d.tmA, sizeof(CUtensorMap));
+    memcpy(&S.tmW, d.w->tmap_s3, sizeof(CUtensorMap));
+    memcpy(&S.tmOut, d.tmOut, sizeof(CUtensorMap));
+    memcpy(&S.tmRes, d.tmRes ? d.tmRes : d.tmOut, sizeof(CUtensorMap));
+    S.bias = d.e.bias;
+    S.scale = d.e.scale;
+    S.k_blocks = (d.K + kS3BK - 1) / kS3BK;
+    S.BN = d.w->BN;
+    S.n_tiles = (d.w->ncols + d.w->BN - 1) / d.w->BN;
+    S.n_out = d.e.n_out;
+    S.kind = s3_kind(d.e);
+    S.nterms = d.nsplit == 3 ? 6 : 1;
+    S.need = l > 0 ? (uint32_t)c->p.st[l - 1].n_tiles * 2u : 0u;     // one count per CTA of the pair and N tile
+    S.publish = l + 1 < n ? 1 : 0;
+    c->scale_table[l] = d.scale_table;
+    c->scale_C[l] = d.scale_C;
+    if (S.n_tiles > 255 || MT >= (1 << 20)) {
+      snprintf(g_s3_err, sizeof g_s3_err, "s3_chain_create: tile index out of range");
+      delete c;
+      return nullptr;
+    }
+    if (S.BN > maxBN) maxBN = S.BN;
+    tiles_per_step += S.n_tiles;
+  }
+  // smem plan
+  const int stage_bytes = 3 * (kS3APlane + (maxBN / 2) * kS3BK * 2);
+  const int fixed = kS3EpiWarps * kS3WarpSmem + kS3BarBytes;
+  int nst = (smem_max - fixed) / stage_bytes;
+  if (nst > 8) nst = 8;
+  if (nst < 2) {
+    snprintf(g_s3_err, sizeof g_s3_err, "s3_chain_create: stage of %d bytes does not fit", stage_bytes);
+    delete c;
+    return nullptr;
+  }
+  c->p.stageBytes = (uint32_t)stage_bytes;
+  c->p.stages = nst;
+  c->smem = nst * stage_bytes + fixed;
+  // Tile table, layer-major: all tiles of layer 0 (row tile major, N tile minor), then layer 1, ...  Cluster u
+  // takes entries u, u + U, ...: within a layer every tile costs the same, so the round-robin stays balanced, and
+  // a tile's producers sit a whole layer earlier in the table -- they finished long before it is reached (a
+  // simulated DepthConvBlock chain at 1920x1280 runs at 95 % of the no-dependency bound; interleaving the
+  // layers with a lag of d row tiles reached 86-90 %, because the ramps starve and tile costs differ per layer).
+  const int cap = num_sms() & ~1;
+  std::vector<uint32_t> table;
+  for (int l = 0; l < n; ++l)
+    for (int mt = 0; mt < MT; ++mt)
+      for (int nt = 0; nt < c->p.st[l].n_tiles; ++nt)
+        table.push_back(((uint32_t)l << 28) | ((uint32_t)nt << 20) | (uint32_t)mt);
+  (void)tiles_per_step;
+  c->p.n_entries = (int)table.size();
+  c->p.MT = MT;
+  c->p.err = d_err;
+  int grid = 2 * c->p.n_entries;
+  if (grid > cap) grid = cap;
+  c->grid = grid;
+  if (cudaMalloc(&c->d_table, table.size() * sizeof(uint32_t)) != cudaSuccess ||
+      cudaMalloc(&c->d_done, (size_t)n * MT * sizeof(uint32_t)) != cudaSuccess) {
+    snprintf(g_s3_err, sizeof g_s3_err, "s3_chain_create: cudaMalloc failed");
+    s3_chain_destroy(c);
+    return nullptr;
+  }
+  cudaMemcpy(c->d_table, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  cudaMemset(c->d_done, 0, (size_t)n * MT * sizeof(uint32_t));
+  c->p.table = c->d_table;
+  c->p.done = c->d_done;
+  c->p.epoch = 0;
+  return c;
+}
+
+void s3_chain_destroy(S3Chain* c) {
+  if (!c) return;
+  if (c->d_table) cudaFree(c->d_table);
+  if (c->d_done) cudaFree(c->d_done);
+  delete c;
+}
+
+int s3_chain_stages(const S3Chain* c) { return c ? c->n_stages : 0; }
+
+int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
+  c->p.epoch += 1;
+  c->p.dbg = g_s3_dbg;
+  for (int l = 0; l < c->n_stages; ++l)
+    if (c->scale_table[l]) c->p.st[l].scale = c->scale_table[l] + (size_t)qp * c->scale_C[l];
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(grid);
+  cfg.gridDim = dim3(c->grid);
   cfg.blockDim = dim3(kS3Threads);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = c->smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -704,64 +1020,10 @@ static cudaError_t launch_s3(int grid, int smem, cudaStream_t st, const CUtensor
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_gemm_s3<kAct, kPack, kRes, kF32>, ta, tw, to, tr, p);
-}
-
-int gemm_s3(const void* tmapA, const GemmW& w, const Epi& e, const void* tmapOut, const void* tmapRes,
-            long long M, int K, cudaStream_t st) {
-  static int smem_max = 0;
-  static int* d_err = nullptr;
-  if (!smem_max) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaMalloc(&d_err, sizeof(int));
-    cudaMemset(d_err, 0, sizeof(int));
-  }
-  if (!gemm_s3_supports(w, e, 3)) {
-    snprintf(g_s3_err, sizeof g_s3_err, "gemm_s3: unsupported configuration (BN=%d act=%d pack=%d)", w.BN, e.act,
-             e.pack);
-    return -1;
-  }
-  S3Params p;
-  p.M = M;
-  p.m_tiles = (int)((M + 255) / 256);
-  p.n_tiles = (w.ncols + w.BN - 1) / w.BN;
-  p.k_blocks = (K + kS3BK - 1) / kS3BK;
-  p.BN = w.BN;
-  p.n_out = e.n_out;
-  p.bias = e.bias;
-  p.scale = e.scale;
-  p.dbg = g_s3_dbg;
-  p.err = d_err;
-  const int stage_bytes = 3 * (kS3APlane + (w.BN / 2) * kS3BK * 2);
-  const int fixed = kS3EpiWarps * kS3WarpSmem + kS3BarBytes;
-  int stages = (smem_max - fixed) / stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages < 2) {
-    snprintf(g_s3_err, sizeof g_s3_err, "gemm_s3: stage of %d bytes does not fit", stage_bytes);
-    return -1;
-  }
-  p.stages = stages;
-  const int smem = stages * stage_bytes + fixed;
-  int grid = 2 * p.m_tiles * p.n_tiles;
-  const int cap = num_sms() & ~1;
-  if (grid > cap) grid = cap;
-  CUtensorMap ta, tw, to, tr;
-  memcpy(&ta, tmapA, sizeof ta);
-  memcpy(&tw, w.tmap_s3, sizeof tw);
-  memcpy(&to, tmapOut, sizeof to);
-  memcpy(&tr, tmapRes ? tmapRes : tmapOut, sizeof tr);
   note_launch();
-  cudaError_t err;
-  if (e.out_f32 && e.act == ACT_WSILU) err = launch_s3<ACT_WSILU, PACK_PLAIN, 0, 1>(grid, smem, st, ta, tw, to, tr, p);
-  else if (e.out_f32) err = launch_s3<ACT_NONE, PACK_PLAIN, 0, 1>(grid, smem, st, ta, tw, to, tr, p);
-  else if (e.pack == PACK_PAIR) err = launch_s3<ACT_WSILU, PACK_PAIR, 0, 0>(grid, smem, st, ta, tw, to, tr, p);
-  else if (e.act == ACT_WSILU) err = launch_s3<ACT_WSILU, PACK_PLAIN, 0, 0>(grid, smem, st, ta, tw, to, tr, p);
-  else if (e.res1.p) err = launch_s3<ACT_NONE, PACK_PLAIN, 1, 0>(grid, smem, st, ta, tw, to, tr, p);
-  else err = launch_s3<ACT_NONE, PACK_PLAIN, 0, 0>(grid, smem, st, ta, tw, to, tr, p);
+  cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_s3_chain, c->p);
   if (err != cudaSuccess) {
-    snprintf(g_s3_err, sizeof g_s3_err, "k_gemm_s3 launch: %s", cudaGetErrorString(err));
+    snprintf(g_s3_err, sizeof g_s3_err, "k_gemm_s3_chain launch: %s", cudaGetErrorString(err));
     return -1;
   }
   return 0;

@@ -69,9 +69,26 @@ int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M);      // bo
 int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M);   // fp32 rows, box 16 x 32
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit);
 void gemm_s3_set_debug(int mask);
-int gemm_s3(const void* tmapA, const GemmW& w, const Epi& e, const void* tmapOut, const void* tmapRes,
-            long long M, int K, cudaStream_t st);
+// A chain = consecutive 1x1 layers over the same rows, run by ONE persistent launch with tile-level
+// dependencies (see gemm_s3.cu).  A single contraction is a chain of one.
+struct S3StageDesc {
+  const void* tmA;            // host CUtensorMap of the A operand (make_tmap_s3_act)
+  const GemmW* w;
+  Epi e;                      // scale is resolved at launch from scale_table / scale_C and qp
+  const void* tmOut;          // make_tmap_s3_rows or make_tmap_f32_rows
+  const void* tmRes;          // residual (make_tmap_s3_rows) or nullptr
+  int K, nsplit;
+  const float* scale_table;   // (72, scale_C) per-QP table or nullptr
+  int scale_C;
+};
+struct S3Chain;
+int s3_chain_max_stages();
+S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M);   // nullptr on error
+void s3_chain_destroy(S3Chain* c);
+int s3_chain_stages(const S3Chain* c);
+int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st);
 const char* gemm_s3_last_error();
+int gemm_s3_trap_code();     // which bounded wait of the chain kernel gave up (0 = none), readable after a trap
 
 // ---------------- entropy model ----------------
 struct PriorArgs {
