@@ -67,7 +67,10 @@ enum {
   DMC_FLAG_SIMT_GEMM = 1,   /* run every contraction on the fp32 CUDA-core kernel
                                (validation backend) instead of tcgen05          */
   DMC_FLAG_KEEP_TAPS = 2,   /* keep intermediate tensors readable via dmc_get_tap */
-  DMC_FLAG_RECON_BF16X1 = 4 /* recon_generation_net contractions with 1 bf16 term */
+  DMC_FLAG_RECON_BF16X1 = 4, /* (default behaviour since r1: kept for source compatibility, ignored) */
+  DMC_FLAG_RECON_SPLIT3 = 8  /* run recon_generation_net with the fp32-grade 6-term product too.  By default
+                                its contractions use plain bf16 operands (1 term, fp32 accumulate): x_hat of
+                                a P frame never feeds a later symbol, and PSNR moves by < 1e-3 dB */
 };
 
 int dmc_create(int variant, int batch, int height, int width, int flags, dmc_engine** out);

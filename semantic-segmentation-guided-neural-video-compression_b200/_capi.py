@@ -16,6 +16,7 @@ VARIANT_IDS = {"old": 0, "performance": 1, "fast": 2, "mask_prop": 3, "intra": 4
 FLAG_SIMT_GEMM = 1
 FLAG_KEEP_TAPS = 2
 FLAG_RECON_BF16X1 = 4
+FLAG_RECON_SPLIT3 = 8
 
 # every symbol include/dmc_b200.h declares: name -> (restype, argtypes)
 _F = POINTER(c_float)

@@ -59,7 +59,7 @@ struct Act {          // an S3 tensor with its geometry (rows = B*H*W)
 struct Conv {         // dense convolution lowered to a contraction
   GemmW g;
   int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
-  CUtensorMap tmap, tmap_half, tmap_s3;
+  CUtensorMap tmap, tmap_half, tmap_s3, tmap_s3_hi;
 };
 struct DW {
   float* w9c = nullptr;
@@ -251,8 +251,10 @@ struct dmc_engine {
     g.tmap = &c->tmap;
     g.tmap_half = &c->tmap_half;
     g.tmap_s3 = &c->tmap_s3;
+    g.tmap_s3_hi = &c->tmap_s3_hi;
     if (!simt()) {
-      if (make_tmap_s3_weight(&c->tmap_s3, g) != 0) fail("%s: %s", key.c_str(), gemm_s3_last_error());
+      if (make_tmap_s3_weight(&c->tmap_s3, g, 3) != 0 || make_tmap_s3_weight(&c->tmap_s3_hi, g, 1) != 0)
+        fail("%s: %s", key.c_str(), gemm_s3_last_error());
       if (make_tmap_weight(&c->tmap, g, g.BN) != 0) fail("%s: %s", key.c_str(), umma_last_error());
       if (make_tmap_weight(&c->tmap_half, g, g.BN / 2) != 0) fail("%s: %s", key.c_str(), umma_last_error());
     }
@@ -371,7 +373,7 @@ struct dmc_engine {
         tmaps.emplace_back(new CUtensorMap());
         t = tmaps.back().get();
       }
-      if (make_tmap_s3_act(tm3[0], a, M) != 0) fail("gemm A map: %s", gemm_s3_last_error());
+      if (make_tmap_s3_act(tm3[0], a, M, nsplit == 3 ? 3 : 1) != 0) fail("gemm A map: %s", gemm_s3_last_error());
       if (spec.out_f32) {
         if (make_tmap_f32_rows(tm3[1], spec.out_f32, e.n_out, spec.ld_f32, M) != 0)
           fail("gemm fp32 out map: %s", gemm_s3_last_error());
@@ -489,7 +491,9 @@ void dmc_engine::build_p() {
             H64 = H / 64, W64 = W / 64;
   const int CD = 256, CY = 128, CZ = 128, CR = 320, QP = 72;
   const int ns = 3;
-  const int ns_recon = (flags & DMC_FLAG_RECON_BF16X1) ? 1 : 3;
+  // recon_generation_net never feeds a later symbol: plain bf16 operands unless the caller asks
+  // for the fp32-grade product there too
+  const int ns_recon = (flags & DMC_FLAG_RECON_SPLIT3) ? 3 : 1;
   dmc_engine* self = this;
 
   // ---- weights, in the reference's registration order (documentation only; lookup is by key)

@@ -57,7 +57,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 s3_get_encode() {
 
 // 3-D map {columns, rows, 3 planes} of an S3 tensor with a box of {box0 columns, box1 rows, 3 planes}
 static int s3_encode(void* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_bytes,
-                     uint64_t plane_bytes, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz) {
+                     uint64_t plane_bytes, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz, uint32_t planes = 3) {
   auto fn = s3_get_encode();
   if (!fn) {
     snprintf(g_s3_err, sizeof g_s3_err, "cuTensorMapEncodeTiled entry point unavailable");
@@ -65,7 +65,7 @@ static int s3_encode(void* out, const void* base, uint64_t cols, uint64_t rows, 
   }
   cuuint64_t dims[3] = {cols, rows, 3};
   cuuint64_t strides[2] = {row_bytes, plane_bytes};
-  cuuint32_t box[3] = {box0, box1, 3};
+  cuuint32_t box[3] = {box0, box1, planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -80,15 +80,16 @@ static int s3_encode(void* out, const void* base, uint64_t cols, uint64_t rows, 
   return 0;
 }
 
-// A operand: box = 32 k x 128 rows x 3 planes, SWIZZLE_64B
-int make_tmap_s3_act(void* tmap_out, View a, long long M) {
+// A operand: box = 32 k x 128 rows x `planes` planes (3, or 1 = hi only for single-term products), SWIZZLE_64B
+int make_tmap_s3_act(void* tmap_out, View a, long long M, int planes) {
   return s3_encode(tmap_out, a.p, (uint64_t)a.C, (uint64_t)M, (uint64_t)a.ld * 2, (uint64_t)a.ps * 2, 32, 128,
-                   CU_TENSOR_MAP_SWIZZLE_64B);
+                   CU_TENSOR_MAP_SWIZZLE_64B, (uint32_t)planes);
 }
-// W operand: box = 32 k x BN/2 rows x 3 planes (each CTA of the pair loads half of the tile)
-int make_tmap_s3_weight(void* tmap_out, const GemmW& w) {
+// W operand: box = 32 k x BN/2 rows x planes (each CTA of the pair loads half of the tile)
+int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes) {
   return s3_encode(tmap_out, w.w, (uint64_t)w.Kld, (uint64_t)w.Npad, (uint64_t)w.Kld * 2,
-                   (uint64_t)w.Npad * w.Kld * 2, 32, (uint32_t)(w.BN / 2), CU_TENSOR_MAP_SWIZZLE_64B);
+                   (uint64_t)w.Npad * w.Kld * 2, 32, (uint32_t)(w.BN / 2), CU_TENSOR_MAP_SWIZZLE_64B,
+                   (uint32_t)planes);
 }
 // epilogue tiles (residual in / result out): box = 16 columns x 32 rows x 3 planes, SWIZZLE_32B;
 // only the first `cols` columns of the view exist for the map, so partial chunks are clipped by TMA
@@ -631,7 +632,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       }
       if (lane == 0) st_release_cta_shared(depsOk, tcount + 1);
       const uint32_t wRows = (uint32_t)S.BN >> 1;
-      const uint32_t tx = 2u * 3u * (kS3APlane + wRows * (kS3BK * 2));
+      const uint32_t tx = 2u * (S.nterms == 1 ? 1u : 3u) * (kS3APlane + wRows * (kS3BK * 2));   // 1 term: hi planes only
       const int m_idx = mt * 256 + (int)rank * 128;
       const int n_idx = nt * S.BN + (int)(rank * wRows);
       for (int kb = 0; kb < S.k_blocks; ++kb) {
@@ -852,7 +853,7 @@ static int g_s3_dbg = 0;
 void gemm_s3_set_debug(int mask) { g_s3_dbg = mask; }
 
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit) {
-  if ((nsplit != 3 && nsplit != 1) || !w.tmap_s3 || e.do_clamp || e.res2.p) return false;
+  if ((nsplit != 3 && nsplit != 1) || !w.tmap_s3 || !w.tmap_s3_hi || e.do_clamp || e.res2.p) return false;
   if (w.BN % 32 || w.BN > 128) return false;
   if (e.out_f32) {                       // fp32 rows: plain layout, no residual, and not both outputs at once
     return !e.out.p && e.pack == PACK_PLAIN && !e.res1.p && (e.act == ACT_NONE || e.act == ACT_WSILU) &&
@@ -925,7 +926,7 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     }
     S3StageDev& S = c->p.st[l];
     memcpy(&S.tmA, d.tmA, sizeof(CUtensorMap));
-    memcpy(&S.tmW, d.w->tmap_s3, sizeof(CUtensorMap));
+    memcpy(&S.tmW, d.nsplit == 3 ? d.w->tmap_s3 : d.w->tmap_s3_hi, sizeof(CUtensorMap));
     memcpy(&S.tmOut, d.tmOut, sizeof(CUtensorMap));
     memcpy(&S.tmRes, d.tmRes ? d.tmRes : d.tmOut, sizeof(CUtensorMap));
     S.bias = d.e.bias;

@@ -22,6 +22,7 @@ struct GemmW {
   void* tmap = nullptr;    // host CUtensorMap (128 B), box = 64 k x BN rows (one-CTA kernel)
   void* tmap_half = nullptr;  // box = 64 k x BN/2 rows (CTA-pair kernel: each CTA loads half of W)
   void* tmap_s3 = nullptr;    // box = 32 k x BN/2 rows x 3 planes, SWIZZLE_64B (gemm_s3.cu)
+  void* tmap_s3_hi = nullptr; // same with the hi plane only (single-term products)
 };
 void pack_gemm_weight(const float* w_oihw, int cout, int cin, int kh, int kw, const GemmW& g,
                       cudaStream_t st);
@@ -63,8 +64,8 @@ const char* umma_last_error();
 
 // Specialised CTA-pair kernel with a TMA epilogue (gemm_s3.cu): S3 out, plain / chunk-add-pair column
 // layouts, <= 1 residual, 6-term product.  gemm_s3_supports() says whether a launch qualifies.
-int make_tmap_s3_act(void* tmap_out, View a, long long M);                 // box 32 x 128 x 3
-int make_tmap_s3_weight(void* tmap_out, const GemmW& w);                   // box 32 x BN/2 x 3
+int make_tmap_s3_act(void* tmap_out, View a, long long M, int planes);     // box 32 x 128 x planes
+int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes);       // box 32 x BN/2 x planes
 int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M);      // box 16 x 32 x 3
 int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M);   // fp32 rows, box 16 x 32
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit);

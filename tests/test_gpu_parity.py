@@ -284,3 +284,30 @@ def test_full_size_properties():
     # same inputs -> same bits (run-to-run deterministic apart from fp64 atomics far below fp32 ulp)
     assert torch.equal(r1["dpb"]["frame"], r1b["dpb"]["frame"])
     assert abs(float(r1["bpp"] - r1b["bpp"])) <= 1e-6 * float(r1["bpp"])
+
+
+def test_recon_single_term_against_split_product():
+    """recon_generation_net runs with plain bf16 operands by default (x_hat of a P frame feeds no later
+    symbol).  Against the fp32-grade product everywhere: identical symbols / bpp / feature, PSNR within
+    the 0.02 dB gate with a wide margin, and a small element-wise x_hat difference."""
+    case = gc.case_by_name("anchor_256")
+    frames, masks = gc.case_inputs(case)
+    outs = {}
+    for name, flags in (("default", capi.FLAG_KEEP_TAPS), ("split3", capi.FLAG_KEEP_TAPS | capi.FLAG_RECON_SPLIT3)):
+        _, mp = seeded_models("performance", case)
+        mp = mp.cuda()
+        mp.engine_flags = flags
+        fr, mk = frames.cuda(), masks.cuda()
+        with torch.no_grad():
+            x_in = torch.cat([fr[:, 1], mk[:, 1]], 1)
+            r = mp(x_in, 40, {"frame": fr[:, 0], "feature": None}, after_i=True)
+            outs[name] = (r, mp.get_tap("y_q", x_in).cpu())
+    (rd, yd), (rs, ys) = outs["default"], outs["split3"]
+    assert torch.equal(yd, ys)
+    assert torch.equal(rd["bpp"], rs["bpp"])
+    assert torch.equal(rd["dpb"]["feature"], rs["dpb"]["feature"])
+    xd, xs = rd["dpb"]["frame"].cpu(), rs["dpb"]["frame"].cpu()
+    assert float((xd - xs).abs().max()) < 2e-2 and float((xd - xs).abs().mean()) < 2e-3
+    pd, rod = gc.metrics(xd, frames[:, 1], masks[:, 1])
+    ps, ros = gc.metrics(xs, frames[:, 1], masks[:, 1])
+    assert abs(pd - ps) <= PSNR_TOL_DB / 4 and abs(rod - ros) <= PSNR_TOL_DB / 4
