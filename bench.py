@@ -49,6 +49,17 @@ def peaks():
     return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic():
+    """dram bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture."""
+    path = os.path.join(ROOT, "profiles", "chain_dcb_r01_ncu_summary.json")
+    try:
+        d = json.load(open(path))
+        return {"bytes": d["dram_bytes_read"] + d["dram_bytes_write"], "launch": d["launch"],
+                "algorithmic_bytes": d["algorithmic_bytes"], "source": "profiles/" + os.path.basename(path)}
+    except Exception:   # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons with NVML while the timed region runs."""
 
@@ -208,15 +219,50 @@ def main():
             dpb = res["dpb"]
             return res, t
 
-        def step_host(out_host):
+        copy_stream = torch.cuda.Stream(dev)
+
+        def prefetch(step_index):
+            """H2D of the frame + mask of step `step_index` from pinned host memory, on the copy stream."""
+            t = 1 + (step_index % (CLIP_FRAMES - 1))
+            with torch.cuda.stream(copy_stream):
+                x = xin_host[:, t].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return x, ev
+
+        def step_host(x, ev, out_host):
+            """One step through the public API on a frame that was copied from the host for this step; its
+            (bpp, bpp_y, bpp_z) go back to pinned host memory and an event marks when they are readable."""
             nonlocal dpb
             step_no[0] += 1
-            t = 1 + (step_no[0] % (CLIP_FRAMES - 1))
-            x = xin_host[:, t].to(dev, non_blocking=True)
+            torch.cuda.current_stream().wait_event(ev)
+            x.record_stream(torch.cuda.current_stream())
             res = mp(x, qp_at(step_no[0]), dpb, after_i=False)
             dpb = res["dpb"]
             out_host.copy_(torch.stack([res["bpp"], res["bpp_y"], res["bpp_z"]], 1), non_blocking=True)
-            return res
+            done = torch.cuda.Event()
+            done.record()
+            return done
+
+        def run_host(n):
+            """n end-to-end steps, software-pipelined two deep: the H2D copy of step i+1 overlaps the kernels of
+            step i, and the host reads the bpp of step i (after its D2H) while step i+1 is already queued."""
+            outs = [torch.empty(B, 3).pin_memory() for _ in range(2)]
+            total = 0.0
+            nxt = prefetch(step_no[0] + 1)
+            prev = None
+            for i in range(n):
+                x, ev = nxt
+                done = step_host(x, ev, outs[i & 1])
+                if i + 1 < n:
+                    nxt = prefetch(step_no[0] + 1)
+                if prev is not None:
+                    prev[0].synchronize()
+                    total += float(prev[1][0, 0])          # the caller consumes bpp of every step
+                prev = (done, outs[i & 1])
+            prev[0].synchronize()
+            total += float(prev[1][0, 0])
+            return total
 
         for _ in range(max(3, args.warmup)):
             step_resident()
@@ -235,15 +281,11 @@ def main():
         launches = lib.dmc_kernel_launches() - l0
         ms = e0.elapsed_time(e1)
         # ---- timed: end to end through the public API with host buffers
-        out_host = torch.empty(B, 3).pin_memory()
-        for _ in range(2):
-            step_host(out_host)
+        run_host(2)
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
-        for _ in range(args.steps):
-            step_host(out_host)
-            torch.cuda.current_stream().synchronize()      # the caller reads bpp every step
+        run_host(args.steps)
         e3.record()
         barrier()
         ms_e2e = e2.elapsed_time(e3)
@@ -272,20 +314,28 @@ def main():
         summ = stats.summary()
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 split operands, fp32 accumulate",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 tensor-core operands, fp32 accumulate (6-term bf16x3 split product on every layer that "
+                         "can reach a symbol; single term in recon_generation_net)",
                 "data": "synthetic", "config": config, "clocks": clk.summary(),
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * 4 * H * W * 4,
                         "d2h_bytes_per_step": B * 3 * 4},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "tensor", "kernel": "k_gemm_umma (tcgen05 split-bf16 contraction)",
+                "roofline": {"bound": "tensor",
+                             "kernel": "k_gemm_s3_chain (persistent tcgen05 chain of 1x1 layers, 6-term bf16 split)",
                              "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                             "frac": achieved / pk["bf16_tflops"] if pk["bf16_tflops"] else None, "traffic": None,
+                             "frac": achieved / pk["bf16_tflops"] if pk["bf16_tflops"] else None,
+                             "traffic": ncu_traffic(),
                              "peak_source": pk["source"],
                              "launches_per_frame": g_n.value / nprof, "avg_launch_ms": per_launch_ms,
                              "gemm_share_of_step": (g_ms.value / nprof) / (ms / args.steps),
                              "issued_mma_tflops": g_is.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value else 0.0,
-                             "note": "achieved = algorithmic conv FLOPs (2*M*N*K) per launch / mean launch time; "
-                                     "fp32-grade layers issue 6 bf16 MMA terms per product, so frac <= 1/6 there"},
+                             "issued_frac": (g_is.value / (g_ms.value * 1e-3) / 1e12 / pk["bf16_tflops"])
+                             if g_ms.value and pk["bf16_tflops"] else None,
+                             "note": "achieved = algorithmic conv FLOPs (2*M*N*K) per contraction launch / mean launch "
+                                     "time (CUDA events around every launch, 3 frames); a launch is a chain of 1-5 "
+                                     "layers.  fp32-grade layers issue 6 bf16 MMA terms per product, so frac <= 1/6 "
+                                     "there: issued_mma_tflops / issued_frac count the MMAs actually issued"},
                 "quality": {"bpp": summ["bpp"], "psnr": summ["psnr"], "roi_psnr": summ["roi_psnr"],
                             "frames": summ["frames"]},
                 "algorithmic_tflops": ALGO_GFLOP_PER_FRAME * value / 1e3}

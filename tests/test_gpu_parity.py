@@ -99,10 +99,14 @@ def test_depthwise_matches_torch_fp32():
                                                       (128, 128, True, False), (256, 320, False, True),
                                                       (368, 368, False, False)])
 def test_depth_conv_block_matches_oracle(cin, cout, shortcut, use_q, backend):
+    _check_dcb(cin, cout, shortcut, use_q, BACKENDS[backend], 2, 16, 24)
+
+
+def _check_dcb(cin, cout, shortcut, use_q, backend, batch, h, w):
     g = torch.Generator().manual_seed(cin + cout)
     m = D.modules._dcb(cin, cout)
     sd = {"b." + k: v.detach() for k, v in m.state_dict().items()}
-    x = torch.randn(2, cin, 16, 24, generator=g)
+    x = torch.randn(batch, cin, h, w, generator=g)
     q = (1 + 0.1 * torch.randn(cout, generator=g)) if use_q else None
     ref = O.depth_conv_block(sd, "b", x, shortcut=shortcut, quant_step=q.view(1, -1, 1, 1) if use_q else None)
     names = ["adaptor", "dc.0", "dc.2", "dc.3", "ffn.0", "ffn.2"]
@@ -116,12 +120,20 @@ def test_depth_conv_block_matches_oracle(cin, cout, shortcut, use_q, backend):
                 ptrs[2 * i + j] = t.data_ptr()
     xb = x.cuda()
     qb = q.cuda() if use_q else None
-    out = torch.empty(2, cout, 16, 24, device="cuda")
+    out = torch.empty(batch, cout, h, w, device="cuda")
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    rc = capi.load().dmc_op_depth_conv_block(_p(xb), ptrs, _p(qb), _p(out), 2, cin, cout, 16, 24, int(shortcut), 3,
-                                             BACKENDS[backend], st)
+    rc = capi.load().dmc_op_depth_conv_block(_p(xb), ptrs, _p(qb), _p(out), batch, cin, cout, h, w, int(shortcut), 3,
+                                             backend, st)
     capi.check(rc, None)
     assert float((out.cpu() - ref).abs().max()) <= 3e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(256, 256, 160, 240), (192, 320, 160, 240), (384, 384, 80, 120)])
+def test_depth_conv_block_chain_at_frame_scale(cin, cout, h, w):
+    """The chained launch (dc.3 -> ffn.0 -> ffn.2 in one persistent kernel with row-tile dependencies) on the
+    feature-map sizes of a 1920x1280 frame: 150 / 38 row tiles over 74 CTA pairs, random data, so a tile that
+    started before its producers were stored would show up as a wrong value."""
+    _check_dcb(cin, cout, False, True, 0, 1, h, w)
 
 
 @pytest.mark.parametrize("formula", [0, 1])
