@@ -368,11 +368,12 @@ struct dmc_engine {
     auto tma_ok = [](const View& v) { return (uintptr_t)v.p % 16 == 0 && v.ld % 8 == 0 && v.ps % 8 == 0; };
     if (use_umma && use_s3 && gemm_s3_supports(*g, e, nsplit) && (!out || tma_ok(out->v)) &&
         (!spec.res1 || tma_ok(spec.res1->v))) {
-      CUtensorMap* tm3[3];
+      CUtensorMap* tm3[4];
       for (auto& t : tm3) {
         tmaps.emplace_back(new CUtensorMap());
         t = tmaps.back().get();
       }
+      if (make_tmap_s3_act64(tm3[3], a, M) != 0) fail("gemm A map (64 rows): %s", gemm_s3_last_error());
       if (make_tmap_s3_act(tm3[0], a, M, nsplit == 3 ? 3 : 1) != 0) fail("gemm A map: %s", gemm_s3_last_error());
       if (spec.out_f32) {
         if (make_tmap_f32_rows(tm3[1], spec.out_f32, e.n_out, spec.ld_f32, M) != 0)
@@ -386,6 +387,7 @@ struct dmc_engine {
       if (!pend.empty() && (pend_M != M || (int)pend.size() >= s3_chain_max_stages() || !chain_layers)) flush_chain();
       S3StageDesc d;
       d.tmA = tm3[0];
+      d.tmA64 = tm3[3];
       d.w = g;
       d.e = e;
       d.tmOut = tm3[1];

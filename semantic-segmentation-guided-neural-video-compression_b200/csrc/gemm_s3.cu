@@ -85,6 +85,11 @@ int make_tmap_s3_act(void* tmap_out, View a, long long M, int planes) {
   return s3_encode(tmap_out, a.p, (uint64_t)a.C, (uint64_t)M, (uint64_t)a.ld * 2, (uint64_t)a.ps * 2, 32, 128,
                    CU_TENSOR_MAP_SWIZZLE_64B, (uint32_t)planes);
 }
+// A operand for 4-CTA clusters: box = 32 k x 64 rows x 1 plane
+int make_tmap_s3_act64(void* tmap_out, View a, long long M) {
+  return s3_encode(tmap_out, a.p, (uint64_t)a.C, (uint64_t)M, (uint64_t)a.ld * 2, (uint64_t)a.ps * 2, 32, 64,
+                   CU_TENSOR_MAP_SWIZZLE_64B, 1);
+}
 // W operand: box = 32 k x BN/2 rows x planes (each CTA of the pair loads half of the tile)
 int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes) {
   return s3_encode(tmap_out, w.w, (uint64_t)w.Kld, (uint64_t)w.Npad, (uint64_t)w.Kld * 2,
@@ -185,6 +190,16 @@ __device__ __forceinline__ void tma_load_pair(uint32_t dst, const CUtensorMap* m
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(0), "r"(leader_bar)
       : "memory");
 }
+// same, delivered to every CTA of `mask` (cluster ranks) at the same smem offset; each copy completes on the
+// barrier at this offset in the destination's pair leader (the address carries the issuer's leader: peer bit clear)
+__device__ __forceinline__ void tma_load_pair_mcast(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                    uint32_t leader_bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar), "h"(mask)
+      : "memory");
+}
 // CTA-local load (residual tiles of the epilogue)
 __device__ __forceinline__ void tma_load_local(uint32_t dst, const CUtensorMap* map, int c0, int c1,
                                                uint32_t bar) {
@@ -224,8 +239,7 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in both CTAs
-  const uint16_t mask = 3;
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {   // arrives on `bar` in the CTAs of `mask`
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(bar), "h"(mask)
@@ -313,6 +327,7 @@ constexpr int kS3MaxStages = 5;
 
 struct alignas(64) S3StageDev {
   CUtensorMap tmA, tmW, tmOut, tmRes;
+  CUtensorMap tmA64;     // A as 32 k x 64 rows x 1 plane boxes (4-CTA clusters: halves multicast between the two pairs)
   const float* bias;
   const float* scale;
   int k_blocks, BN, n_tiles, n_out;
@@ -329,6 +344,7 @@ struct S3ChainParams {
   uint32_t epoch;          // launch number (1-based): layer l-1 is complete at done == epoch * need
   uint32_t stageBytes;     // operand ring stage (sized for the widest W tile of the chain)
   int stages;
+  int cl4;                 // 1: clusters of 4 CTAs = two pairs on the two N tiles of an entry, sharing A by TMA multicast
   int dbg;                 // probe switches: 1 no operand loads, 2 no MMA issue, 4 no epilogue TMA traffic, 8 no epilogue math
   int* err;
 };
@@ -559,7 +575,12 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = smem_u32(smem_raw);
-  const uint32_t rank = blockIdx.x & 1u;             // cluster = (2,1,1): rank in the pair, provably warp-uniform
+  // cluster = (2,1,1) or (4,1,1): rank in the CTA pair / which pair of the cluster (provably warp-uniform)
+  const uint32_t rank = blockIdx.x & 1u;
+  const uint32_t pairIdx = p.cl4 ? ((blockIdx.x >> 1) & 1u) : 0u;
+  const uint32_t leaderRank = pairIdx << 1;          // cluster rank of this pair's leader CTA
+  const uint16_t pairMask = (uint16_t)(3u << leaderRank);
+  const uint16_t clusterMask = p.cl4 ? (uint16_t)0xF : (uint16_t)0x3;
   const bool leader = rank == 0;
   const uint32_t stageBytes = p.stageBytes;
   const uint32_t epiBase = base + (uint32_t)p.stages * stageBytes;
@@ -580,7 +601,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full(s), (p.dbg & 1) ? 2 : 1);   // probe mode without loads: one plain arrival per CTA
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_empty(s), p.cl4 ? 2 : 1);        // every pair that writes into this stage has consumed it
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull(b), 1);
@@ -603,8 +624,8 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   cluster_sync_all();                      // peer barriers are initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmemSlot - base));
-  const int unit = (int)(blockIdx.x >> 1);
-  const int units = (int)(gridDim.x >> 1);
+  const int unit = (int)(p.cl4 ? blockIdx.x >> 2 : blockIdx.x >> 1);
+  const int units = (int)(p.cl4 ? gridDim.x >> 2 : gridDim.x >> 1);
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
@@ -615,7 +636,8 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     uint32_t ph = 0, tcount = 0;
     for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
       const uint32_t e = __ldg(p.table + ei);
-      const int l = (int)(e >> 28), nt = (int)((e >> 20) & 0xffu), mt = (int)(e & 0xfffffu);
+      const int l = (int)(e >> 28), mt = (int)(e & 0xfffffu);
+      const int nt = p.cl4 ? 2 * (int)((e >> 20) & 0xffu) + (int)pairIdx : (int)((e >> 20) & 0xffu);
       const S3StageDev& S = p.st[l];
       if (l > 0 && S.need != 0u) {
         // all N tiles of the previous layer for these rows must be stored
@@ -640,14 +662,24 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         const uint32_t sa = base + s * stageBytes;
         const uint32_t sw = sa + 3 * kS3APlane;
         if (elect_one()) {
+          const uint32_t lbar = mapa(bar_full(s), leaderRank);
           if (p.dbg & 1) {
             if (leader) mbar_arrive(bar_full(s));
-            else mbar_arrive_cluster(mapa(bar_full(s), 0));
+            else mbar_arrive_cluster(lbar);
           } else {
             // both CTAs' bytes complete on the LEADER's barrier, which the leader arms for both
             if (leader) mbar_expect_tx(bar_full(s), tx);
-            const uint32_t lbar = mapa(bar_full(s), 0);
-            tma_load_pair(sa, &S.tmA, kb * kS3BK, m_idx, lbar);
+            if (p.cl4) {
+              // the two pairs work on the same rows: this CTA fetches 64 of its 128 rows and multicasts them to
+              // the CTA of the same rank in the other pair (which sends the other 64)
+              const uint16_t mc = (uint16_t)((1u << rank) | (4u << rank));
+              const int planes = S.nterms == 1 ? 1 : 3;
+              for (int pl = 0; pl < planes; ++pl)
+                tma_load_pair_mcast(sa + pl * kS3APlane + pairIdx * (kS3APlane / 2), &S.tmA64, kb * kS3BK,
+                                    m_idx + (int)pairIdx * 64, pl, lbar, mc);
+            } else {
+              tma_load_pair(sa, &S.tmA, kb * kS3BK, m_idx, lbar);
+            }
             tma_load_pair(sw, &S.tmW, kb * kS3BK, n_idx, lbar);
           }
         }
@@ -702,8 +734,8 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
                 }
               }
             }
-            tc_commit_pair(bar_empty(s));
-            if (kb == k_blocks - 1) tc_commit_pair(bar_tfull(buf));
+            tc_commit_pair(bar_empty(s), clusterMask);
+            if (kb == k_blocks - 1) tc_commit_pair(bar_tfull(buf), pairMask);
           }
           __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -734,7 +766,8 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     // `slot2` is the ring tile that chunk will be processed in; R2 are the (cached) fields of its layer.
     auto issue_res = [&](const StageRegs& R2, uint32_t e2, int c2, uint32_t t2, bool force, uint32_t slot2) {
       if (R2.kind != S3_RES || !x.epi_mem) return;
-      const int nt2 = (int)((e2 >> 20) & 0xffu), mt2 = (int)(e2 & 0xfffffu);
+      const int mt2 = (int)(e2 & 0xfffffu);
+      const int nt2 = p.cl4 ? 2 * (int)((e2 >> 20) & 0xffu) + (int)pairIdx : (int)((e2 >> 20) & 0xffu);
       if (c2 == 0) {
         if (!force && (int)(ld_acquire_cta_shared(depsOk) - (t2 + 1)) < 0) return;
         if (R2.need != 0u) fence_proxy_async_global();
@@ -770,7 +803,8 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     StageRegs S;
     for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
       const uint32_t e = e_next;
-      const int l = (int)(e >> 28), nt = (int)((e >> 20) & 0xffu), mt = (int)(e & 0xfffffu);
+      const int l = (int)(e >> 28), mt = (int)(e & 0xfffffu);
+      const int nt = p.cl4 ? 2 * (int)((e >> 20) & 0xffu) + (int)pairIdx : (int)((e >> 20) & 0xffu);
       if (l != l_cached) { S = s3_load_stage(p.st[l]); l_cached = l; }
       const uint32_t buf = tcount & 1;
       const int nchunk = s3_nchunk(S.kind, S.BN, x.half);
@@ -797,7 +831,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         __syncwarp();
         if (lane == 0) {
           if (leader) mbar_arrive(bar_tempty(buf));
-          else mbar_arrive_cluster(mapa(bar_tempty(buf), 0));
+          else mbar_arrive_cluster(mapa(bar_tempty(buf), leaderRank));
         }
       };
       const bool stored0 = x.epi_mem && s3_dest_col(S.kind, S.BN, x.half, nt, 0) < S.n_out;
@@ -911,9 +945,33 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     snprintf(g_s3_err, sizeof g_s3_err, "s3_chain_create: %d stages (max %d)", n, kS3MaxStages);
     return nullptr;
   }
+  // 4-CTA clusters (A shared between two CTA pairs by TMA multicast) need every stage's 64-row A map and are
+  // limited to the clusters that can be co-resident (33 = 132 SMs on B200); DMC_GEMM_CL4=1 selects them
+  static int cl4_mode = -1, cl4_clusters = 0;
+  if (cl4_mode < 0) {
+    const char* v = getenv("DMC_GEMM_CL4");
+    cl4_mode = (v && v[0] == '1') ? 1 : 0;
+    if (cl4_mode) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3((num_sms() / 4) * 4);
+      cfg.blockDim = dim3(kS3Threads);
+      cfg.dynamicSmemBytes = smem_max;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&cl4_clusters, k_gemm_s3_chain, &cfg) != cudaSuccess || cl4_clusters < 1)
+        cl4_mode = 0;
+    }
+  }
+  bool cl4 = cl4_mode == 1;
+  for (int l = 0; l < n; ++l) cl4 = cl4 && stages[l].tmA64 != nullptr;
   S3Chain* c = new S3Chain();
   memset(&c->p, 0, sizeof c->p);
   c->n_stages = n;
+  c->p.cl4 = cl4 ? 1 : 0;
   const int MT = (int)((M + 255) / 256);
   int maxBN = 0, tiles_per_step = 0;
   for (int l = 0; l < n; ++l) {
@@ -926,6 +984,7 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     }
     S3StageDev& S = c->p.st[l];
     memcpy(&S.tmA, d.tmA, sizeof(CUtensorMap));
+    memcpy(&S.tmA64, d.tmA64 ? d.tmA64 : d.tmA, sizeof(CUtensorMap));
     memcpy(&S.tmW, d.nsplit == 3 ? d.w->tmap_s3 : d.w->tmap_s3_hi, sizeof(CUtensorMap));
     memcpy(&S.tmOut, d.tmOut, sizeof(CUtensorMap));
     memcpy(&S.tmRes, d.tmRes ? d.tmRes : d.tmOut, sizeof(CUtensorMap));
@@ -937,7 +996,8 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     S.n_out = d.e.n_out;
     S.kind = s3_kind(d.e);
     S.nterms = d.nsplit == 3 ? 6 : 1;
-    S.need = l > 0 ? (uint32_t)c->p.st[l - 1].n_tiles * 2u : 0u;     // one count per CTA of the pair and N tile
+    // one count per CTA and table entry of the previous layer for these rows
+    S.need = l == 0 ? 0u : (cl4 ? (uint32_t)((c->p.st[l - 1].n_tiles + 1) / 2) * 4u : (uint32_t)c->p.st[l - 1].n_tiles * 2u);
     S.publish = l + 1 < n ? 1 : 0;
     c->scale_table[l] = d.scale_table;
     c->scale_C[l] = d.scale_C;
@@ -967,17 +1027,20 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
   // a tile's producers sit a whole layer earlier in the table -- they finished long before it is reached (a
   // simulated DepthConvBlock chain at 1920x1280 runs at 95 % of the no-dependency bound; interleaving the
   // layers with a lag of d row tiles reached 86-90 %, because the ramps starve and tile costs differ per layer).
-  const int cap = num_sms() & ~1;
+  const int cap = cl4 ? 4 * cl4_clusters : (num_sms() & ~1);
   std::vector<uint32_t> table;
   for (int l = 0; l < n; ++l)
-    for (int mt = 0; mt < MT; ++mt)
-      for (int nt = 0; nt < c->p.st[l].n_tiles; ++nt)
+    for (int mt = 0; mt < MT; ++mt) {
+      // an entry is one N tile for a CTA pair, or two adjacent N tiles for the two pairs of a 4-CTA cluster
+      const int per_mt = cl4 ? (c->p.st[l].n_tiles + 1) / 2 : c->p.st[l].n_tiles;
+      for (int nt = 0; nt < per_mt; ++nt)
         table.push_back(((uint32_t)l << 28) | ((uint32_t)nt << 20) | (uint32_t)mt);
+    }
   (void)tiles_per_step;
   c->p.n_entries = (int)table.size();
   c->p.MT = MT;
   c->p.err = d_err;
-  int grid = 2 * c->p.n_entries;
+  int grid = (cl4 ? 4 : 2) * c->p.n_entries;
   if (grid > cap) grid = cap;
   c->grid = grid;
   if (cudaMalloc(&c->d_table, table.size() * sizeof(uint32_t)) != cudaSuccess ||
@@ -1016,7 +1079,7 @@ int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = c->p.cl4 ? 4 : 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;

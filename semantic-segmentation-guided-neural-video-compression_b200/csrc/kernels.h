@@ -65,6 +65,7 @@ const char* umma_last_error();
 // Specialised CTA-pair kernel with a TMA epilogue (gemm_s3.cu): S3 out, plain / chunk-add-pair column
 // layouts, <= 1 residual, 6-term product.  gemm_s3_supports() says whether a launch qualifies.
 int make_tmap_s3_act(void* tmap_out, View a, long long M, int planes);     // box 32 x 128 x planes
+int make_tmap_s3_act64(void* tmap_out, View a, long long M);               // box 32 x 64 x 1
 int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes);       // box 32 x BN/2 x planes
 int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M);      // box 16 x 32 x 3
 int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M);   // fp32 rows, box 16 x 32
@@ -74,6 +75,7 @@ void gemm_s3_set_debug(int mask);
 // dependencies (see gemm_s3.cu).  A single contraction is a chain of one.
 struct S3StageDesc {
   const void* tmA;            // host CUtensorMap of the A operand (make_tmap_s3_act)
+  const void* tmA64;          // the same operand as 64-row single-plane boxes (make_tmap_s3_act64) or nullptr
   const GemmW* w;
   Epi e;                      // scale is resolved at launch from scale_table / scale_C and qp
   const void* tmOut;          // make_tmap_s3_rows or make_tmap_f32_rows
