@@ -247,6 +247,7 @@ struct dmc_engine {
     g.Npad = round_up(round_up(g.ncols, g.BN), 64);
     g.Kld = round_up(g.K, 64);
     g.w = (bf16*)dalloc((size_t)3 * g.Npad * g.Kld * sizeof(bf16));
+    if (!simt()) g.wb = (bf16*)dalloc((size_t)3 * g.Npad * g.Kld * sizeof(bf16));
     g.bias = new_f32(g.Npad);
     g.tmap = &c->tmap;
     g.tmap_half = &c->tmap_half;
@@ -1286,6 +1287,7 @@ extern "C" int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int 
     e.use_s3 = pair == 2;
     Conv* c = e.add_conv("w", k, n, 1, 1, 0, mode == 3 ? PACK_PAIR : PACK_PLAIN);
     CUDA_OK(cudaMemset(c->g.w, 0, (size_t)3 * c->g.Npad * c->g.Kld * sizeof(bf16)));
+    CUDA_OK(cudaMemset(c->g.wb, 0, (size_t)3 * c->g.Npad * c->g.Kld * sizeof(bf16)));
     CUDA_OK(cudaMemset(c->g.bias, 0, sizeof(float) * c->g.Npad));
     Act in = e.new_act(1, 1, rows, k);
     Act out = e.new_act(1, 1, rows, mode == 3 ? n / 2 : n);
@@ -1374,6 +1376,7 @@ extern "C" int dmc_bench_dcb(int batch, int height, int width, int cin, int cout
     e.flush_chain();
     for (auto& cv : e.convs) {
       CUDA_OK(cudaMemset(cv->g.w, 0, (size_t)3 * cv->g.Npad * cv->g.Kld * sizeof(bf16)));
+      CUDA_OK(cudaMemset(cv->g.wb, 0, (size_t)3 * cv->g.Npad * cv->g.Kld * sizeof(bf16)));
       CUDA_OK(cudaMemset(cv->g.bias, 0, sizeof(float) * cv->g.Npad));
     }
     for (auto& d : e.dws) {

@@ -90,11 +90,29 @@ int make_tmap_s3_act64(void* tmap_out, View a, long long M) {
   return s3_encode(tmap_out, a.p, (uint64_t)a.C, (uint64_t)M, (uint64_t)a.ld * 2, (uint64_t)a.ps * 2, 32, 64,
                    CU_TENSOR_MAP_SWIZZLE_64B, 1);
 }
-// W operand: box = 32 k x BN/2 rows x planes (each CTA of the pair loads half of the tile)
+// W operand, from the tile-blocked copy [3][Kld/16][Npad][16]: 4-D map {256 elements, Npad/16, Kld/16, 3} with a box
+// of {256, BN/32, 2 k blocks, planes}: the BN/2 x 32 half tile of one CTA arrives as BN/16 segments of 512 bytes per
+// plane (row-major it was BN/2 segments of 64 bytes, and the TMA unit retires well under one segment per clock)
 int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes) {
-  return s3_encode(tmap_out, w.w, (uint64_t)w.Kld, (uint64_t)w.Npad, (uint64_t)w.Kld * 2,
-                   (uint64_t)w.Npad * w.Kld * 2, 32, (uint32_t)(w.BN / 2), CU_TENSOR_MAP_SWIZZLE_64B,
-                   (uint32_t)planes);
+  auto fn = s3_get_encode();
+  if (!fn || !w.wb) {
+    snprintf(g_s3_err, sizeof g_s3_err, "make_tmap_s3_weight: no blocked weight copy / encode entry point");
+    return -1;
+  }
+  const uint64_t plane_bytes = (uint64_t)w.Npad * w.Kld * 2;
+  cuuint64_t dims[4] = {256, (cuuint64_t)w.Npad / 16, (cuuint64_t)w.Kld / 16, 3};
+  cuuint64_t strides[3] = {512, (cuuint64_t)w.Npad * 32, plane_bytes};
+  cuuint32_t box[4] = {256, (cuuint32_t)(w.BN / 32), 2, (cuuint32_t)planes};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn((CUtensorMap*)tmap_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, w.wb, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_s3_err, sizeof g_s3_err, "cuTensorMapEncodeTiled (blocked W) failed (%d): Npad=%d Kld=%d BN=%d", (int)r,
+             w.Npad, w.Kld, w.BN);
+    return -1;
+  }
+  return 0;
 }
 // epilogue tiles (residual in / result out): box = 16 columns x 32 rows x 3 planes, SWIZZLE_32B;
 // only the first `cols` columns of the view exist for the map, so partial chunks are clipped by TMA
@@ -188,6 +206,15 @@ __device__ __forceinline__ void tma_load_pair(uint32_t dst, const CUtensorMap* m
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(0), "r"(leader_bar)
+      : "memory");
+}
+// W half tile from the blocked weight copy (4-D map: element, 16-row group, 16-wide k block, plane)
+__device__ __forceinline__ void tma_load_pair_w(uint32_t dst, const CUtensorMap* map, int row16, int kblk16,
+                                                uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(0), "r"(row16), "r"(kblk16), "r"(0), "r"(leader_bar)
       : "memory");
 }
 // same, delivered to every CTA of `mask` (cluster ranks) at the same smem offset; each copy completes on the
@@ -367,6 +394,13 @@ constexpr int kS3BarBytes = 512;
 __device__ __forceinline__ uint64_t s3_desc(uint32_t saddr) {
   const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
   const uint32_t hi = 32u | (1u << 14) | (4u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+// K-major SWIZZLE_32B tile (rows of 16 bf16 = 32 B, the blocked weight image): SBO = 8 rows x 32 B = 256 -> 16,
+// layout SWIZZLE_32B = 6
+__device__ __forceinline__ uint64_t s3_desc32(uint32_t saddr) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+  const uint32_t hi = 16u | (1u << 14) | (6u << 29);
   return ((uint64_t)hi << 32) | lo;
 }
 
@@ -680,7 +714,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
             } else {
               tma_load_pair(sa, &S.tmA, kb * kS3BK, m_idx, lbar);
             }
-            tma_load_pair(sw, &S.tmW, kb * kS3BK, n_idx, lbar);
+            tma_load_pair_w(sw, &S.tmW, n_idx >> 4, kb * 2, lbar);
           }
         }
         __syncwarp();
@@ -701,7 +735,8 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
         // N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(S.BN >> 3) << 17) | (16u << 24);
-        const uint32_t wStep = ((uint32_t)(S.BN >> 1) * (kS3BK * 2)) >> 4;
+        const uint32_t wStep = ((uint32_t)(S.BN >> 1) * (kS3BK * 2)) >> 4;   // plane stride of the W stage
+        const uint32_t wKs = ((uint32_t)(S.BN >> 1) * 32u) >> 4;             // second 16-wide k block of a plane
         const int k_blocks = S.k_blocks;
         const bool six = S.nterms != 1;
         const uint32_t buf = tcount & 1;
@@ -714,7 +749,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
           tc_fence_after();
           const uint32_t sa = base + s * stageBytes;
           const uint64_t da = s3_desc(sa);
-          const uint64_t dw = s3_desc(sa + 3 * kS3APlane);
+          const uint64_t dw = s3_desc32(sa + 3 * kS3APlane);
           const uint32_t first = kb == 0 ? 0u : 1u;
           if (elect_one()) {
             if (!(p.dbg & 2)) {
@@ -723,7 +758,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
                 // term 0 = hi*hi -> main accumulator; the five small terms (smallest first) -> second one
                 // (plane index: 0 hi, 1 mid, 2 lo):  hl, lh, mm, hm, mh
                 const uint64_t a0 = da + 2 * ks, a1 = a0 + aStep, a2 = a0 + 2 * aStep;
-                const uint64_t w0 = dw + 2 * ks, w1 = w0 + wStep, w2 = w0 + 2 * wStep;
+                const uint64_t w0 = dw + ks * wKs, w1 = w0 + wStep, w2 = w0 + 2 * wStep;
                 tc_mma_pair(d_main, a0, w0, idesc, ks == 0 ? first : 1u);
                 if (six) {
                   tc_mma_pair(d_small, a0, w2, idesc, ks == 0 ? first : 1u);

@@ -26,8 +26,11 @@ int num_sms() {
 }
 
 // ------------------------------------------------------------------ weights
-__global__ void k_pack_gemm_weight(const float* __restrict__ w, bf16* __restrict__ out, int cout,
-                                   int cin, int kh, int kw, int Npad, int Kld, int K, int pack,
+// `out`: row-major S3 [3][Npad][Kld] (general / SIMT kernels).  `outb`: the same values tile-blocked for the chain
+// kernel, [3][Kld/16][Npad][16] with the 16-byte halves of a row swapped where bit 2 of the row is set -- exactly
+// the shared-memory image of a K-major SWIZZLE_32B operand, so a W tile is fetched as a few 512-byte segments.
+__global__ void k_pack_gemm_weight(const float* __restrict__ w, bf16* __restrict__ out, bf16* __restrict__ outb,
+                                   int cout, int cin, int kh, int kw, int Npad, int Kld, int K, int pack,
                                    int Cg, int Cg_pad) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)Npad * Kld) return;
@@ -55,6 +58,13 @@ __global__ void k_pack_gemm_weight(const float* __restrict__ w, bf16* __restrict
   out[idx] = h;
   out[ps + idx] = m;
   out[2 * ps + idx] = l;
+  if (outb) {
+    const int blk = kk >> 4, half = (kk >> 3) & 1, e8 = kk & 7;
+    const long long ib = ((long long)blk * Npad + r) * 16 + ((half ^ ((r >> 2) & 1)) << 3) + e8;
+    outb[ib] = h;
+    outb[ps + ib] = m;
+    outb[2 * ps + ib] = l;
+  }
 }
 
 __global__ void k_pack_bias(const float* __restrict__ b, float* __restrict__ out, int cout, int Npad,
@@ -78,8 +88,8 @@ __global__ void k_pack_bias(const float* __restrict__ b, float* __restrict__ out
 void pack_gemm_weight(const float* w, int cout, int cin, int kh, int kw, const GemmW& g,
                       cudaStream_t st) {
   long long n = (long long)g.Npad * g.Kld;
-  (note_launch(), k_pack_gemm_weight)<<<cdiv(n, 256), 256, 0, st>>>(w, g.w, cout, cin, kh, kw, g.Npad, g.Kld, g.K,
-                                                   g.pack, g.Cg, g.Cg_pad);
+  (note_launch(), k_pack_gemm_weight)<<<cdiv(n, 256), 256, 0, st>>>(w, g.w, g.wb, cout, cin, kh, kw, g.Npad, g.Kld,
+                                                   g.K, g.pack, g.Cg, g.Cg_pad);
 }
 void pack_gemm_bias(const float* bias, int cout, const GemmW& g, cudaStream_t st) {
   (note_launch(), k_pack_bias)<<<cdiv(g.Npad, 256), 256, 0, st>>>(bias, g.bias, cout, g.Npad, g.pack, g.Cg, g.Cg_pad);

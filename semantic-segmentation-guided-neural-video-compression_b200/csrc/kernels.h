@@ -12,6 +12,7 @@ long long launch_count();
 // Packed contraction weight: S3 [3][Npad][Kld] bf16, K index = (kh*KW + kw)*Cin + ci.
 struct GemmW {
   bf16* w = nullptr;
+  bf16* wb = nullptr;      // tile-blocked, pre-swizzled copy [3][Kld/16][Npad][16] for the chain kernel (or nullptr)
   float* bias = nullptr;   // [Npad], packed order, zero on padding
   int N = 0, K = 0;        // logical (N = cout, K = cin*kh*kw)
   int ncols = 0;           // packed columns before tile padding (pair / shuffle layouts included)
