@@ -1298,11 +1298,11 @@ extern "C" int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int 
     s.nsplit = nsplit;
     if (mode == 1 || mode == 3) s.act = ACT_WSILU;
     if (mode == 2) s.res1 = &res;
+    gemm_s3_set_debug(probe);          // (the blob-store probe is decided when the chain is built)
     e.gemm(in, c, &out, s);
     e.flush_chain();
     umma_set_pair(pair != 0);
     umma_set_debug(probe);
-    gemm_s3_set_debug(probe);
     cudaEvent_t a, b;
     CUDA_OK(cudaEventCreate(&a));
     CUDA_OK(cudaEventCreate(&b));
