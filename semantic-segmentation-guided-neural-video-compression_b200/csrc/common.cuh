@@ -1,9 +1,16 @@
 // Shared types of the DMC engine: the split-bf16 ("S3") activation format, the GEMM
 // epilogue description and the exact-arithmetic helpers.
 //
-// S3 format.  Every activation lives in HBM as THREE bf16 planes hi/mid/lo in NHWC order
-// (row = pixel, column = channel) with hi+mid+lo == the fp32 value exactly (8+8+8 mantissa
-// bits).  The planes are what tcgen05 consumes directly (TMA -> swizzled smem -> kind::f16
+// S3 format.  Every activation lives in HBM as THREE bf16 planes hi/mid/lo (row = pixel, column =
+// channel) with hi+mid+lo == the fp32 value exactly (8+8+8 mantissa bits).
+//
+// Layout of a plane ("tile-blocked"): [C/16 column blocks][Mp rows][16 columns], Mp = rows padded to 256,
+// and inside a row of a block the two 16-byte halves are swapped where bit 2 of the row index is set.
+// That is byte for byte the shared-memory image of a K-major SWIZZLE_32B tcgen05 operand, so a
+// 128-row x 32-column operand tile is two contiguous 4 KB pieces and a 32-row x 16-column epilogue
+// chunk is one contiguous 1 KB piece: TMA moves them as 512-byte segments.  (The TMA unit retires
+// only ~0.55 row segments per clock per SM whatever their width; with row-major planes a tile was
+// ~10 700 segments of 32-64 bytes = 17 000 clocks of TMA work against 6 100 clocks of MMAs.)  The planes are what tcgen05 consumes directly (TMA -> swizzled smem -> kind::f16
 // MMA), so a contraction at fp32-grade accuracy is 6 bf16 MMA terms (hh,hm,mh,hl,lh,mm)
 // accumulated in fp32 TMEM, and the same buffer read with only the hi plane is a plain
 // bf16 GEMM operand.  SURVEY.md 7.1: the reference's symbol-parity gate needs >= ~20
@@ -17,14 +24,18 @@ namespace dmc {
 
 typedef __nv_bfloat16 bf16;
 
-// A (possibly column-sliced) view of an S3 tensor: element (row, col, plane) is at
-// p[plane * ps + row * ld + col].
+// A (possibly column-sliced, at multiples of 16 columns) view of an S3 tensor: the 16-byte unit
+// holding columns [c, c+8) of row r in plane pl is at
+//   p + pl * ps + (c >> 4) * bs + r * 16 + ((((c >> 3) & 1) ^ ((r >> 2) & 1)) << 3)        (elements)
 struct View {
   bf16* p;
   long long ps;   // plane stride, elements
-  int ld;         // row pitch, elements (multiple of 8)
+  long long bs;   // column-block stride, elements (= padded rows * 16)
   int C;          // columns in this view
 };
+__host__ __device__ __forceinline__ long long s3_unit_offset(const View& v, long long row, int col) {
+  return (long long)(col >> 4) * v.bs + row * 16 + ((((col >> 3) & 1) ^ (int)((row >> 2) & 1)) << 3);
+}
 
 enum { ACT_NONE = 0, ACT_WSILU = 1, ACT_RELU = 2 };
 enum { PACK_PLAIN = 0, PACK_PAIR = 1, PACK_SHUF2 = 2 };
@@ -82,13 +93,13 @@ __device__ __forceinline__ uint32_t pack_bf16(bf16 a, bf16 b) {
 }
 
 __device__ __forceinline__ float ld3(const View& v, long long row, int col) {
-  const bf16* q = v.p + row * v.ld + col;
+  const bf16* q = v.p + s3_unit_offset(v, row, col) + (col & 7);
   return join3(q[0], q[v.ps], q[2 * v.ps]);
 }
 __device__ __forceinline__ void st3(const View& v, long long row, int col, float x) {
   bf16 h, m, l;
   split3(x, h, m, l);
-  bf16* q = v.p + row * v.ld + col;
+  bf16* q = v.p + s3_unit_offset(v, row, col) + (col & 7);
   q[0] = h;
   q[v.ps] = m;
   q[2 * v.ps] = l;
@@ -96,7 +107,7 @@ __device__ __forceinline__ void st3(const View& v, long long row, int col, float
 
 // 8 consecutive columns (16 B per plane); col must be a multiple of 8 and the view 16B aligned.
 __device__ __forceinline__ void ld3x8(const View& v, long long row, int col, float* o) {
-  const bf16* q = v.p + row * v.ld + col;
+  const bf16* q = v.p + s3_unit_offset(v, row, col);
   uint4 a = *reinterpret_cast<const uint4*>(q);
   uint4 b = *reinterpret_cast<const uint4*>(q + v.ps);
   uint4 c = *reinterpret_cast<const uint4*>(q + 2 * v.ps);
@@ -120,7 +131,7 @@ __device__ __forceinline__ void st3x8(const View& v, long long row, int col, con
     b[i] = pack_bf16(m0, m1);
     c[i] = pack_bf16(l0, l1);
   }
-  bf16* q = v.p + row * v.ld + col;
+  bf16* q = v.p + s3_unit_offset(v, row, col);
   *reinterpret_cast<uint4*>(q) = make_uint4(a[0], a[1], a[2], a[3]);
   *reinterpret_cast<uint4*>(q + v.ps) = make_uint4(b[0], b[1], b[2], b[3]);
   *reinterpret_cast<uint4*>(q + 2 * v.ps) = make_uint4(c[0], c[1], c[2], c[3]);

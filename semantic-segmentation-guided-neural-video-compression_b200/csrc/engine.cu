@@ -168,12 +168,15 @@ struct dmc_engine {
   Act new_act(int b, int h, int w, int C) {
     Act a;
     a.B = b; a.H = h; a.W = w;
+    // tile-blocked planes (common.cuh): [ceil(C/16)][rows padded to 256][16]; padding rows / columns start as
+    // zeros (padding columns are only ever rewritten with zeros, padding rows never reach a valid row)
     long long M = a.M();
-    int ld = round_up(C, 8);
-    long long ps = (M * ld + 7) / 8 * 8;
+    long long Mp = (M + 255) / 256 * 256;
+    long long bs = Mp * 16;
+    long long ps = bs * ((C + 15) / 16);
     a.v.p = (bf16*)dalloc((size_t)ps * 3 * sizeof(bf16));
-    a.v.ps = ps; a.v.ld = ld; a.v.C = C;
-    if (ld != C) CUDA_OK(cudaMemset(a.v.p, 0, (size_t)ps * 3 * sizeof(bf16)));
+    a.v.ps = ps; a.v.bs = bs; a.v.C = C;
+    CUDA_OK(cudaMemset(a.v.p, 0, (size_t)ps * 3 * sizeof(bf16)));
     return a;
   }
   // scratch buffers are shared by every block of the same geometry (one stream, in-order)
@@ -197,8 +200,9 @@ struct dmc_engine {
     return p;
   }
   static Act slice(const Act& a, int c0, int C) {
+    if (c0 % 16) fail("slice: column offset %d is not a multiple of 16", c0);
     Act s = a;
-    s.v.p = a.v.p + c0;
+    s.v.p = a.v.p + (long long)(c0 / 16) * a.v.bs;
     s.v.C = C;
     return s;
   }
@@ -358,15 +362,14 @@ struct dmc_engine {
     if (out && out->v.C < e.n_out) fail("gemm: destination has %d columns, need %d", out->v.C, e.n_out);
     long long M = in.M();
     View a = in.v;
-    bool aligned = ((uintptr_t)a.p % 16 == 0) && (a.ld % 8 == 0) && (a.ps % 8 == 0);
-    bool out_ok = !out || (((uintptr_t)out->v.p % 16 == 0) && (out->v.ld % 8 == 0));
+    bool aligned = true, out_ok = true;      // blocked planes are always 512-byte aligned
     bool use_umma = !simt() && aligned && out_ok && (g->K % 8 == 0) && (e.n_out % 8 == 0) &&
                     (!spec.out_f32 || (spec.ld_f32 % 4 == 0));
     const float* table = spec.scale_table;
     int sc = spec.scale_C;
     int nsplit = spec.nsplit;
     dmc_engine* self = this;
-    auto tma_ok = [](const View& v) { return (uintptr_t)v.p % 16 == 0 && v.ld % 8 == 0 && v.ps % 8 == 0; };
+    auto tma_ok = [](const View& v) { return (uintptr_t)v.p % 512 == 0; };
     if (use_umma && use_s3 && gemm_s3_supports(*g, e, nsplit) && (!out || tma_ok(out->v)) &&
         (!spec.res1 || tma_ok(spec.res1->v))) {
       CUtensorMap* tm3[4];
@@ -1130,8 +1133,7 @@ int dmc_get_tap(dmc_engine* e, const char* name, float* dst, int64_t capacity, i
       if (shape4) { shape4[0] = a.B; shape4[1] = a.v.C; shape4[2] = a.H; shape4[3] = a.W; }
       if (!dst) return;
       if (capacity < a.M() * a.v.C) fail("tap '%s' needs %lld elements", name, a.M() * a.v.C);
-      if (a.v.ld % 8 == 0 && (uintptr_t)a.v.p % 16 == 0) s3_to_nchw(a.v, dst, a.B, a.v.C, a.H, a.W, st);
-      else fail("tap '%s' has an unaligned layout", name);
+      s3_to_nchw(a.v, dst, a.B, a.v.C, a.H, a.W, st);
       return;
     }
     auto jt = e->ftaps.find(name);

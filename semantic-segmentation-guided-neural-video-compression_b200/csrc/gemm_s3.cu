@@ -55,40 +55,40 @@ static PFN_cuTensorMapEncodeTiled_v12000 s3_get_encode() {
   return fn;
 }
 
-// 3-D map {columns, rows, 3 planes} of an S3 tensor with a box of {box0 columns, box1 rows, 3 planes}
-static int s3_encode(void* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_bytes,
-                     uint64_t plane_bytes, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz, uint32_t planes = 3) {
+// 4-D map of a tile-blocked S3 view (common.cuh): {256 elements = 16 rows x 16 columns (512 contiguous bytes),
+// padded rows / 16, column blocks, 3 planes}; a box is {256, rows / 16, blocks, planes}.  No TMA swizzle: the data
+// is stored pre-swizzled, global memory and shared memory images are identical.
+static int s3_encode(void* out, View v, int cols, uint32_t box_rows, uint32_t box_blocks, uint32_t planes) {
   auto fn = s3_get_encode();
   if (!fn) {
     snprintf(g_s3_err, sizeof g_s3_err, "cuTensorMapEncodeTiled entry point unavailable");
     return -1;
   }
-  cuuint64_t dims[3] = {cols, rows, 3};
-  cuuint64_t strides[2] = {row_bytes, plane_bytes};
-  cuuint32_t box[3] = {box0, box1, planes};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
-                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  cuuint64_t dims[4] = {256, (cuuint64_t)(v.bs / 256), (cuuint64_t)((cols + 15) / 16), 3};
+  cuuint64_t strides[3] = {512, (cuuint64_t)v.bs * 2, (cuuint64_t)v.ps * 2};
+  cuuint32_t box[4] = {256, box_rows / 16, box_blocks, planes};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, v.p, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_s3_err, sizeof g_s3_err,
-             "cuTensorMapEncodeTiled failed (%d): base=%p dims=%llu,%llu strides=%llu,%llu box=%u,%u", (int)r,
-             base, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_bytes,
-             (unsigned long long)plane_bytes, box0, box1);
+             "cuTensorMapEncodeTiled failed (%d): base=%p cols=%d bs=%lld ps=%lld box=%u rows x %u blocks x %u planes",
+             (int)r, (void*)v.p, cols, v.bs, v.ps, box_rows, box_blocks, planes);
     return -1;
   }
   return 0;
 }
 
-// A operand: box = 32 k x 128 rows x `planes` planes (3, or 1 = hi only for single-term products), SWIZZLE_64B
+// A operand: box = 128 rows x 2 column blocks (32 k) x `planes` planes (3, or 1 = hi only for single-term products)
 int make_tmap_s3_act(void* tmap_out, View a, long long M, int planes) {
-  return s3_encode(tmap_out, a.p, (uint64_t)a.C, (uint64_t)M, (uint64_t)a.ld * 2, (uint64_t)a.ps * 2, 32, 128,
-                   CU_TENSOR_MAP_SWIZZLE_64B, (uint32_t)planes);
+  (void)M;
+  return s3_encode(tmap_out, a, a.C, 128, 2, (uint32_t)planes);
 }
-// A operand for 4-CTA clusters: box = 32 k x 64 rows x 1 plane
+// A operand for 4-CTA clusters: box = 64 rows x 1 column block x 1 plane (one contiguous 2 KB piece)
 int make_tmap_s3_act64(void* tmap_out, View a, long long M) {
-  return s3_encode(tmap_out, a.p, (uint64_t)a.C, (uint64_t)M, (uint64_t)a.ld * 2, (uint64_t)a.ps * 2, 32, 64,
-                   CU_TENSOR_MAP_SWIZZLE_64B, 1);
+  (void)M;
+  return s3_encode(tmap_out, a, a.C, 64, 1, 1);
 }
 // W operand, from the tile-blocked copy [3][Kld/16][Npad][16]: 4-D map {256 elements, Npad/16, Kld/16, 3} with a box
 // of {256, BN/32, 2 k blocks, planes}: the BN/2 x 32 half tile of one CTA arrives as BN/16 segments of 512 bytes per
@@ -114,13 +114,12 @@ int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes) {
   }
   return 0;
 }
-// epilogue tiles (residual in / result out): box = 16 columns x 32 rows x 3 planes, SWIZZLE_32B;
-// only the first `cols` columns of the view exist for the map, so partial chunks are clipped by TMA
+// epilogue tiles (residual in / result out): box = 32 rows x 1 column block (16 columns) x 3 planes = three
+// contiguous 1 KB pieces; only the first `cols` columns of the view exist for the map
 int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M) {
-  return s3_encode(tmap_out, v.p, (uint64_t)cols, (uint64_t)M, (uint64_t)v.ld * 2, (uint64_t)v.ps * 2, 16, 32,
-                   CU_TENSOR_MAP_SWIZZLE_32B);
+  (void)M;
+  return s3_encode(tmap_out, v, cols, 32, 1, 3);
 }
-
 // fp32 result rows [M, ld]: 2-D map, box = 16 columns x 32 rows, SWIZZLE_64B
 int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M) {
   auto fn = s3_get_encode();
@@ -200,12 +199,13 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // operand load of the pair kernel: bytes complete on the LEADER CTA's barrier
-__device__ __forceinline__ void tma_load_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+// (tile-blocked maps: coordinates are {0, row / 16, column block, plane})
+__device__ __forceinline__ void tma_load_pair(uint32_t dst, const CUtensorMap* map, int row16, int blk,
                                               uint32_t leader_bar) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(0), "r"(leader_bar)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(0), "r"(row16), "r"(blk), "r"(0), "r"(leader_bar)
       : "memory");
 }
 // W half tile from the blocked weight copy (4-D map: element, 16-row group, 16-wide k block, plane)
@@ -219,26 +219,26 @@ __device__ __forceinline__ void tma_load_pair_w(uint32_t dst, const CUtensorMap*
 }
 // same, delivered to every CTA of `mask` (cluster ranks) at the same smem offset; each copy completes on the
 // barrier at this offset in the destination's pair leader (the address carries the issuer's leader: peer bit clear)
-__device__ __forceinline__ void tma_load_pair_mcast(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+__device__ __forceinline__ void tma_load_pair_mcast(uint32_t dst, const CUtensorMap* map, int row16, int blk, int plane,
                                                     uint32_t leader_bar, uint16_t mask) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%2, %3, %4}], [%5], %6;"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar), "h"(mask)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+      ::"r"(dst), "l"(map), "r"(0), "r"(row16), "r"(blk), "r"(plane), "r"(leader_bar), "h"(mask)
       : "memory");
 }
 // CTA-local load (residual tiles of the epilogue)
-__device__ __forceinline__ void tma_load_local(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+__device__ __forceinline__ void tma_load_local(uint32_t dst, const CUtensorMap* map, int col, int row,
                                                uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(0), "r"(bar)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(0), "r"(row >> 4), "r"(col >> 4), "r"(0), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void tma_store(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(0)
+__device__ __forceinline__ void tma_store(const CUtensorMap* map, uint32_t src, int col, int row) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(0), "r"(row >> 4), "r"(col >> 4), "r"(0)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -390,16 +390,9 @@ constexpr int kS3Ring = 3;                        // staging tiles per epilogue 
 constexpr int kS3WarpSmem = kS3Ring * kS3ChunkBytes;
 constexpr int kS3BarBytes = 512;
 
-// Shared-memory descriptor of a K-major SWIZZLE_64B operand tile (cute::UMMA::SmemDescriptor):
-// start>>4 [0,14) | LBO (unused for one swizzle atom along K) = 1 [16,30) | SBO = 8 rows x 64 B = 512
-// -> 32 [32,46) | version 1 [46,48) | layout SWIZZLE_64B = 4 [61,64)
-__device__ __forceinline__ uint64_t s3_desc(uint32_t saddr) {
-  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
-  const uint32_t hi = 32u | (1u << 14) | (4u << 29);
-  return ((uint64_t)hi << 32) | lo;
-}
-// K-major SWIZZLE_32B tile (rows of 16 bf16 = 32 B, the blocked weight image): SBO = 8 rows x 32 B = 256 -> 16,
-// layout SWIZZLE_32B = 6
+// Shared-memory descriptor (cute::UMMA::SmemDescriptor) of a K-major SWIZZLE_32B operand tile = rows of 16 bf16
+// (32 B), which is what the tile-blocked activations and weights are in shared memory: start>>4 [0,14) | LBO (unused)
+// = 1 [16,30) | SBO = 8 rows x 32 B = 256 -> 16 [32,46) | version 1 [46,48) | layout SWIZZLE_32B = 6 [61,64)
 __device__ __forceinline__ uint64_t s3_desc32(uint32_t saddr) {
   const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
   const uint32_t hi = 16u | (1u << 14) | (6u << 29);
@@ -721,10 +714,11 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
               const uint16_t mc = (uint16_t)((1u << rank) | (4u << rank));
               const int planes = S.nterms == 1 ? 1 : 3;
               for (int pl = 0; pl < planes; ++pl)
-                tma_load_pair_mcast(sa + pl * kS3APlane + pairIdx * (kS3APlane / 2), &S.tmA64, kb * kS3BK,
-                                    m_idx + (int)pairIdx * 64, pl, lbar, mc);
+                for (int blk = 0; blk < 2; ++blk)
+                  tma_load_pair_mcast(sa + pl * kS3APlane + blk * 4096u + pairIdx * 2048u, &S.tmA64,
+                                      (m_idx + (int)pairIdx * 64) >> 4, kb * 2 + blk, pl, lbar, mc);
             } else {
-              tma_load_pair(sa, &S.tmA, kb * kS3BK, m_idx, lbar);
+              tma_load_pair(sa, &S.tmA, m_idx >> 4, kb * 2, lbar);
             }
             tma_load_pair_w(sw, &S.tmW, n_idx >> 4, kb * 2, lbar);
           }
@@ -760,7 +754,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
           mbar_wait(bar_full(s), ph, p.err, 3);
           tc_fence_after();
           const uint32_t sa = base + s * stageBytes;
-          const uint64_t da = s3_desc(sa);
+          const uint64_t da = s3_desc32(sa);
           const uint64_t dw = s3_desc32(sa + 3 * kS3APlane);
           const uint32_t first = kb == 0 ? 0u : 1u;
           if (elect_one()) {
@@ -769,7 +763,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
               for (int ks = 0; ks < 2; ++ks) {
                 // term 0 = hi*hi -> main accumulator; the five small terms (smallest first) -> second one
                 // (plane index: 0 hi, 1 mid, 2 lo):  hl, lh, mm, hm, mh
-                const uint64_t a0 = da + 2 * ks, a1 = a0 + aStep, a2 = a0 + 2 * aStep;
+                const uint64_t a0 = da + ks * (4096u >> 4), a1 = a0 + aStep, a2 = a0 + 2 * aStep;
                 const uint64_t w0 = dw + ks * wKs, w1 = w0 + wStep, w2 = w0 + 2 * wStep;
                 tc_mma_pair(d_main, a0, w0, idesc, ks == 0 ? first : 1u);
                 if (six) {
@@ -935,7 +929,7 @@ void gemm_s3_set_debug(int mask) { g_s3_dbg = mask; }
 
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit) {
   if ((nsplit != 3 && nsplit != 1) || !w.tmap_s3 || !w.tmap_s3_hi || e.do_clamp || e.res2.p) return false;
-  if (w.BN % 32 || w.BN > 128) return false;
+  if (w.BN % 32 || w.BN > 128 || e.n_out % 16) return false;
   if (e.out_f32) {                       // fp32 rows: plain layout, no residual, and not both outputs at once
     return !e.out.p && e.pack == PACK_PLAIN && !e.res1.p && (e.act == ACT_NONE || e.act == ACT_WSILU) &&
            e.ld_f32 % 4 == 0 && (uintptr_t)e.out_f32 % 16 == 0;

@@ -45,36 +45,42 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-static int encode3d(void* out, const void* base, uint64_t d0, uint64_t d1, uint64_t s1_bytes,
-                    uint64_t s2_bytes, uint32_t box1) {
+// 4-D maps over tile-blocked planes (common.cuh): {256 elements = 16 rows x 16 columns, rows / 16, column blocks,
+// planes}; a box is one plane of `box_rows` rows x 4 column blocks (64 k), data pre-swizzled -> no TMA swizzle.
+static int encode4d(void* out, const void* base, uint64_t rows16, uint64_t blocks, uint64_t block_bytes,
+                    uint64_t plane_bytes, uint32_t box_rows) {
   auto fn = get_encode();
   if (!fn) {
     snprintf(g_umma_err, sizeof g_umma_err, "cuTensorMapEncodeTiled entry point unavailable");
     return -1;
   }
-  cuuint64_t dims[3] = {d0, d1, 3};
-  cuuint64_t strides[2] = {s1_bytes, s2_bytes};
-  cuuint32_t box[3] = {64, box1, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base),
-                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cuuint64_t dims[4] = {256, rows16, blocks, 3};
+  cuuint64_t strides[3] = {512, block_bytes, plane_bytes};
+  cuuint32_t box[4] = {256, box_rows / 16, 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_umma_err, sizeof g_umma_err,
-             "cuTensorMapEncodeTiled failed (%d): base=%p dims=%llu,%llu strides=%llu,%llu box1=%u",
-             (int)r, base, (unsigned long long)d0, (unsigned long long)d1,
-             (unsigned long long)s1_bytes, (unsigned long long)s2_bytes, box1);
+             "cuTensorMapEncodeTiled failed (%d): base=%p rows16=%llu blocks=%llu box_rows=%u", (int)r, base,
+             (unsigned long long)rows16, (unsigned long long)blocks, box_rows);
     return -1;
   }
   return 0;
 }
 
 int make_tmap_act(void* tmap_out, View a, long long M) {
-  return encode3d(tmap_out, a.p, (uint64_t)a.C, (uint64_t)M, (uint64_t)a.ld * 2, (uint64_t)a.ps * 2, 128);
+  (void)M;
+  return encode4d(tmap_out, a.p, (uint64_t)(a.bs / 256), (uint64_t)((a.C + 15) / 16), (uint64_t)a.bs * 2,
+                  (uint64_t)a.ps * 2, 128);
 }
 int make_tmap_weight(void* tmap_out, const GemmW& w, int box_rows) {
-  return encode3d(tmap_out, w.w, (uint64_t)w.Kld, (uint64_t)w.Npad, (uint64_t)w.Kld * 2,
+  if (!w.wb) {
+    snprintf(g_umma_err, sizeof g_umma_err, "make_tmap_weight: no blocked weight copy");
+    return -1;
+  }
+  return encode4d(tmap_out, w.wb, (uint64_t)w.Npad / 16, (uint64_t)w.Kld / 16, (uint64_t)w.Npad * 32,
                   (uint64_t)w.Npad * w.Kld * 2, (uint32_t)box_rows);
 }
 
@@ -115,12 +121,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
-                                            int c2, uint32_t bar) {
+// (tile-blocked maps: k0 and row are element / row coordinates, converted to {0, row / 16, k block, plane})
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int k0, int row,
+                                            int plane, uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(0), "r"(row >> 4), "r"(k0 >> 4), "r"(plane), "r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
@@ -159,15 +166,16 @@ __device__ __forceinline__ void tc_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 [0,14) | LBO>>4 = 1 [16,30) | SBO>>4 = 64 (8 rows x 128 B) [32,46) | version 1 [46,48)
-// | layout SWIZZLE_128B = 2 [61,64)
+// K-major, SWIZZLE_32B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout) -- a stage plane is
+// four 16-wide k blocks of [rows][32 B], the image of the tile-blocked tensors:
+// start>>4 [0,14) | LBO>>4 = 1 [16,30) | SBO>>4 = 16 (8 rows x 32 B) [32,46) | version 1 [46,48)
+// | layout SWIZZLE_32B = 6 [61,64)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)64 << 32;
+  d |= (uint64_t)16 << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)6 << 61;
   return d;
 }
 
@@ -264,7 +272,7 @@ __device__ __forceinline__ void staged_load_s3(const View& src, const RowMap& rm
   uint4 gh[4], gm[4], gl[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const bf16* q = src.p + (rm.base[i] + goff) * src.ld + dcol + slot * 8;
+    const bf16* q = src.p + s3_unit_offset(src, rm.base[i] + goff, dcol + slot * 8);
     gh[i] = gm[i] = gl[i] = make_uint4(0, 0, 0, 0);
     if (rm.ok[i] && col_ok) {
       gh[i] = *reinterpret_cast<const uint4*>(q);
@@ -380,7 +388,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, const RowMap& rm, l
     const uint32_t rd = stage + (lane >> 2) * kStageRowBytes + slot * 16;
     bf16* dst[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = e.out.p + (rm.base[i] + goff) * e.out.ld + dcol + slot * 8;
+    for (int i = 0; i < 4; ++i) dst[i] = e.out.p + s3_unit_offset(e.out, rm.base[i] + goff, dcol + slot * 8);
     auto store_plane = [&](const uint32_t* q, long long poff) {
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
@@ -422,12 +430,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, int k0, int row, int plane,
                                                  uint32_t leader_bar) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(0), "r"(row >> 4), "r"(k0 >> 4), "r"(plane), "r"(leader_bar)
       : "memory");
 }
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
@@ -576,8 +584,8 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int ks = 0; ks < 4; ++ks) {
             if (p.dbg & 2) break;
             for (int t = 0; t < nterms; ++t) {
-              const uint64_t ad = make_desc(sa + ta[t] * kATileBytes + ks * 32);
-              const uint64_t bd = make_desc(sw + tw[t] * wTileBytes + ks * 32);
+              const uint64_t ad = make_desc(sa + ta[t] * kATileBytes + ks * 4096);
+              const uint64_t bd = make_desc(sw + tw[t] * wTileBytes + ks * (wRows * 32u));
               const uint32_t d = t == 0 ? d_tmem : d_tmem + 128u;
               const uint32_t acc = t == 0 ? ((kb | ks) ? 1u : 0u) : ((kb | ks | (t - 1)) ? 1u : 0u);
               if (kPair) tc_mma_pair(d, ad, bd, idesc, acc);

@@ -230,7 +230,7 @@ __global__ void k_finite_check(View v, long long M, int C8, int* flag) {
   if (idx >= M * C8) return;
   long long m = idx / C8;
   int c = (int)(idx % C8) * 8;
-  uint4 a = *reinterpret_cast<const uint4*>(v.p + m * v.ld + c);
+  uint4 a = *reinterpret_cast<const uint4*>(v.p + s3_unit_offset(v, m, c));
   const uint32_t* u = &a.x;
   bool bad = false;
 #pragma unroll
@@ -355,12 +355,12 @@ __global__ void k_im2col(View in, View out, int B, int H, int W, int k, int stri
   int hi = ho * stride - pad + tap / k, wi = wo * stride - pad + tap % k;
   uint4 z = make_uint4(0, 0, 0, 0), a = z, bb = z, cc = z;
   if ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W) {
-    const bf16* q = in.p + (((long long)b * H + hi) * W + wi) * in.ld + c;
+    const bf16* q = in.p + s3_unit_offset(in, ((long long)b * H + hi) * W + wi, c);
     a = *reinterpret_cast<const uint4*>(q);
     bb = *reinterpret_cast<const uint4*>(q + in.ps);
     cc = *reinterpret_cast<const uint4*>(q + 2 * in.ps);
   }
-  bf16* d = out.p + mo * out.ld + tap * tap_stride + col_off + c;
+  bf16* d = out.p + s3_unit_offset(out, mo, tap * tap_stride + col_off + c);
   *reinterpret_cast<uint4*>(d) = a;
   *reinterpret_cast<uint4*>(d + out.ps) = bb;
   *reinterpret_cast<uint4*>(d + 2 * out.ps) = cc;

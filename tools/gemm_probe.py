@@ -11,7 +11,7 @@ import dmc_b200 as D  # noqa: E402
 
 lib = D._capi.load()
 torch.zeros(1, device="cuda")
-M = 38400
+M = int(os.environ.get("PROBE_M", "38400"))
 SHAPES = [("dc0 256->256 plain", 256, 256, 0), ("dc0 256->256 wsilu", 256, 256, 1), ("dc3 256->256 +res", 256, 256, 2),
           ("ffn0 256->1024 pair", 256, 1024, 3), ("ffn2 512->256 +res", 512, 256, 2), ("head 320->192", 320, 192, 0)]
 PROBES = [(0, "full"), (16, "blob-stores"), (4, "no-epi-mem"), (12, "no-epi"), (2, "no-mma"), (3, "no-tma,no-mma"),
