@@ -329,6 +329,9 @@ void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, in
   note_launch();
   k_dwconv3x3<false><<<cdiv(n, 128), 128, 0, st>>>(in, nullptr, 0, w9c, bias, out, B, H, W, C8, WG);
 }
+// (A mapping with one thread per 16-channel block and consecutive threads along the image row makes the blocked
+// stores contiguous but the fp32 reads strided by a whole pixel: 78 us instead of 33 us at 160x240x256.  The
+// channel-fastest mapping below keeps every 16-byte store inside a fully written 32-byte sector.)
 void dwconv3x3_f32(const float* in, int ld, const float* w9c, const float* bias, View out, int B, int H, int W,
                    cudaStream_t st) {
   const int C8 = out.C / 8;
