@@ -1056,6 +1056,10 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
   const int fixed = kS3EpiWarps * kS3WarpSmem + kS3BarBytes;
   int nst = (smem_max - fixed) / stage_bytes;
   if (nst > 8) nst = 8;
+  if (const char* v = getenv("DMC_S3_STAGES")) {       // experiments: cap the operand ring depth
+    const int cap_st = atoi(v);
+    if (cap_st >= 2 && cap_st < nst) nst = cap_st;
+  }
   if (nst < 2) {
     snprintf(g_s3_err, sizeof g_s3_err, "s3_chain_create: stage of %d bytes does not fit", stage_bytes);
     delete c;
