@@ -315,14 +315,14 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16 tensor-core operands, fp32 accumulate (6-term bf16x3 split product on every layer that "
-                         "can reach a symbol; single term in recon_generation_net)",
+                "dtype": "f16 tensor-core operands (tcgen05 kind::f16), fp32 accumulate: 3-term split product (fp16 hi + "
+                         "2^11-scaled fp16 lo) on every layer that can reach a symbol; single term in recon_generation_net",
                 "data": "synthetic", "config": config, "clocks": clk.summary(),
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * 4 * H * W * 4,
                         "d2h_bytes_per_step": B * 3 * 4},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "tensor",
-                             "kernel": "k_gemm_s3_chain (persistent tcgen05 chain of 1x1 layers, 6-term bf16 split)",
+                             "kernel": "k_gemm_s3_chain (persistent tcgen05 chain of 1x1 layers, 3-term split-fp16 product)",
                              "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                              "frac": achieved / pk["bf16_tflops"] if pk["bf16_tflops"] else None,
                              "traffic": ncu_traffic(),
@@ -334,7 +334,7 @@ def main():
                              if g_ms.value and pk["bf16_tflops"] else None,
                              "note": "achieved = algorithmic conv FLOPs (2*M*N*K) per contraction launch / mean launch "
                                      "time (CUDA events around every launch, 3 frames); a launch is a chain of 1-5 "
-                                     "layers.  fp32-grade layers issue 6 bf16 MMA terms per product, so frac <= 1/6 "
+                                     "layers.  fp32-grade layers issue 3 fp16 MMA terms per product, so frac <= 1/3 "
                                      "there: issued_mma_tflops / issued_frac count the MMAs actually issued"},
                 "quality": {"bpp": summ["bpp"], "psnr": summ["psnr"], "roi_psnr": summ["roi_psnr"],
                             "frames": summ["frames"]},

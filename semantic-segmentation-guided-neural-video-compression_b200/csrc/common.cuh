@@ -1,8 +1,21 @@
-// Shared types of the DMC engine: the split-bf16 ("S3") activation format, the GEMM
-// epilogue description and the exact-arithmetic helpers.
+// Shared types of the DMC engine: the split-fp16 ("S3" in identifiers: split storage) activation
+// format, the GEMM epilogue description and the exact-arithmetic helpers.
 //
-// S3 format.  Every activation lives in HBM as THREE bf16 planes hi/mid/lo (row = pixel, column =
-// channel) with hi+mid+lo == the fp32 value exactly (8+8+8 mantissa bits).
+// Split format.  Every activation lives in HBM as TWO fp16 planes (row = pixel, column = channel):
+//   hi = fp16(x)                      (11 significand bits)
+//   lo = fp16((x - hi) * 2^11)        (the next 11 bits; x - hi is exact in fp32)
+// so  x ~= hi + lo * 2^-11  to 2^-23..2^-22 relative -- one fp32 rounding -- at 4 B/element.  The 2^11
+// pre-scale keeps the low part in fp16's normal range (unscaled it goes subnormal and the symbol-parity
+// gate fails).  A contraction at fp32-grade accuracy is THREE fp16 MMA terms per k step:
+//   acc_main  += a_hi . w_hi
+//   acc_small += a_hi . w_lo + a_lo . w_hi          (2^11-scaled; a_lo . w_lo <= 2^-22 is dropped)
+//   result     = acc_main + acc_small * 2^-11
+// accumulated in fp32 TMEM (0 symbol mismatches over three free-running P frames; plain
+// bf16 / TF32 / unscaled 2-term splits fail the gate, the 6-term bf16x3 split of the first versions of this
+// engine passed at twice the MMAs and 1.5x the operand bytes).  The same buffer read with only the hi
+// plane is a plain fp16 GEMM operand (recon_generation_net).
+// Range: |x| must stay below 65504 (fp16); the conversions saturate instead of producing inf.  Random-init
+// activations peak at 4.6; the reference's own guard trips at 1e6 (trainer:285-287).
 //
 // Layout of a plane ("tile-blocked"): [C/16 column blocks][Mp rows][16 columns], Mp = rows padded to 256,
 // and inside a row of a block the two 16-byte halves are swapped where bit 2 of the row index is set.
@@ -10,25 +23,26 @@
 // 128-row x 32-column operand tile is two contiguous 4 KB pieces and a 32-row x 16-column epilogue
 // chunk is one contiguous 1 KB piece: TMA moves them as 512-byte segments.  (The TMA unit retires
 // only ~0.55 row segments per clock per SM whatever their width; with row-major planes a tile was
-// ~10 700 segments of 32-64 bytes = 17 000 clocks of TMA work against 6 100 clocks of MMAs.)  The planes are what tcgen05 consumes directly (TMA -> swizzled smem -> kind::f16
-// MMA), so a contraction at fp32-grade accuracy is 6 bf16 MMA terms (hh,hm,mh,hl,lh,mm)
-// accumulated in fp32 TMEM, and the same buffer read with only the hi plane is a plain
-// bf16 GEMM operand.  SURVEY.md 7.1: the reference's symbol-parity gate needs >= ~20
-// operand mantissa bits, which plain bf16 / TF32 / 2-term splits do not give.
+// ~10 700 segments of 32-64 bytes = 17 000 clocks of TMA work against 6 100 clocks of MMAs.)  The planes
+// are what tcgen05 consumes directly (TMA -> swizzled smem -> kind::f16 MMA).
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace dmc {
 
-typedef __nv_bfloat16 bf16;
+typedef __half h16;
+
+constexpr int kPlanes = 2;                   // hi, lo
+constexpr float kLoScale = 2048.0f;          // 2^11
+constexpr float kLoInv = 1.0f / 2048.0f;
 
 // A (possibly column-sliced, at multiples of 16 columns) view of an S3 tensor: the 16-byte unit
 // holding columns [c, c+8) of row r in plane pl is at
 //   p + pl * ps + (c >> 4) * bs + r * 16 + ((((c >> 3) & 1) ^ ((r >> 2) & 1)) << 3)        (elements)
 struct View {
-  bf16* p;
+  h16* p;
   long long ps;   // plane stride, elements
   long long bs;   // column-block stride, elements (= padded rows * 16)
   int C;          // columns in this view
@@ -76,65 +90,63 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-__device__ __forceinline__ void split3(float x, bf16& h, bf16& m, bf16& l) {
-  h = __float2bfloat16_rn(x);
-  float r = sub_rn(x, __bfloat162float(h));
-  m = __float2bfloat16_rn(r);
-  r = sub_rn(r, __bfloat162float(m));
-  l = __float2bfloat16_rn(r);
+// two floats -> packed f16x2 (low half = a), round to nearest even, saturating at +-65504
+__device__ __forceinline__ uint32_t cvt_h2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
-__device__ __forceinline__ float join3(bf16 h, bf16 m, bf16 l) {
-  return add_rn(add_rn(__bfloat162float(l), __bfloat162float(m)), __bfloat162float(h));
+__device__ __forceinline__ float h2lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
+__device__ __forceinline__ float h2hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+
+// x -> (hi, lo) of two elements at once: h = f16x2(x), l = f16x2((x - h) * 2^11)
+__device__ __forceinline__ void split2x2(float x0, float x1, uint32_t& h, uint32_t& l) {
+  h = cvt_h2(x0, x1);
+  const float r0 = sub_rn(x0, h2lo(h)), r1 = sub_rn(x1, h2hi(h));
+  l = cvt_h2(mul_rn(r0, kLoScale), mul_rn(r1, kLoScale));
 }
-__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
-__device__ __forceinline__ uint32_t pack_bf16(bf16 a, bf16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+__device__ __forceinline__ void split2(float x, h16& h, h16& l) {
+  uint32_t a, b;
+  split2x2(x, 0.0f, a, b);
+  h = __ushort_as_half((unsigned short)(a & 0xffffu));
+  l = __ushort_as_half((unsigned short)(b & 0xffffu));
 }
+// hi + lo * 2^-11 with one rounding (the product is exact)
+__device__ __forceinline__ float join2(float h, float l) { return fmaf(l, kLoInv, h); }
+__device__ __forceinline__ float join2(h16 h, h16 l) { return join2(__half2float(h), __half2float(l)); }
 
 __device__ __forceinline__ float ld3(const View& v, long long row, int col) {
-  const bf16* q = v.p + s3_unit_offset(v, row, col) + (col & 7);
-  return join3(q[0], q[v.ps], q[2 * v.ps]);
+  const h16* q = v.p + s3_unit_offset(v, row, col) + (col & 7);
+  return join2(q[0], q[v.ps]);
 }
 __device__ __forceinline__ void st3(const View& v, long long row, int col, float x) {
-  bf16 h, m, l;
-  split3(x, h, m, l);
-  bf16* q = v.p + s3_unit_offset(v, row, col) + (col & 7);
+  h16 h, l;
+  split2(x, h, l);
+  h16* q = v.p + s3_unit_offset(v, row, col) + (col & 7);
   q[0] = h;
-  q[v.ps] = m;
-  q[2 * v.ps] = l;
+  q[v.ps] = l;
 }
 
 // 8 consecutive columns (16 B per plane); col must be a multiple of 8 and the view 16B aligned.
 __device__ __forceinline__ void ld3x8(const View& v, long long row, int col, float* o) {
-  const bf16* q = v.p + s3_unit_offset(v, row, col);
+  const h16* q = v.p + s3_unit_offset(v, row, col);
   uint4 a = *reinterpret_cast<const uint4*>(q);
   uint4 b = *reinterpret_cast<const uint4*>(q + v.ps);
-  uint4 c = *reinterpret_cast<const uint4*>(q + 2 * v.ps);
   const uint32_t* ua = &a.x;
   const uint32_t* ub = &b.x;
-  const uint32_t* uc = &c.x;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    o[2 * i] = add_rn(add_rn(bf16lo(uc[i]), bf16lo(ub[i])), bf16lo(ua[i]));
-    o[2 * i + 1] = add_rn(add_rn(bf16hi(uc[i]), bf16hi(ub[i])), bf16hi(ua[i]));
+    o[2 * i] = join2(h2lo(ua[i]), h2lo(ub[i]));
+    o[2 * i + 1] = join2(h2hi(ua[i]), h2hi(ub[i]));
   }
 }
 __device__ __forceinline__ void st3x8(const View& v, long long row, int col, const float* x) {
-  uint32_t a[4], b[4], c[4];
+  uint32_t a[4], b[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    bf16 h0, m0, l0, h1, m1, l1;
-    split3(x[2 * i], h0, m0, l0);
-    split3(x[2 * i + 1], h1, m1, l1);
-    a[i] = pack_bf16(h0, h1);
-    b[i] = pack_bf16(m0, m1);
-    c[i] = pack_bf16(l0, l1);
-  }
-  bf16* q = v.p + s3_unit_offset(v, row, col);
+  for (int i = 0; i < 4; ++i) split2x2(x[2 * i], x[2 * i + 1], a[i], b[i]);
+  h16* q = v.p + s3_unit_offset(v, row, col);
   *reinterpret_cast<uint4*>(q) = make_uint4(a[0], a[1], a[2], a[3]);
   *reinterpret_cast<uint4*>(q + v.ps) = make_uint4(b[0], b[1], b[2], b[3]);
-  *reinterpret_cast<uint4*>(q + 2 * v.ps) = make_uint4(c[0], c[1], c[2], c[3]);
 }
 
 // Packed GEMM column -> destination (row, col).  Returns false for padding columns.

@@ -174,9 +174,9 @@ struct dmc_engine {
     long long Mp = (M + 255) / 256 * 256;
     long long bs = Mp * 16;
     long long ps = bs * ((C + 15) / 16);
-    a.v.p = (bf16*)dalloc((size_t)ps * 3 * sizeof(bf16));
+    a.v.p = (h16*)dalloc((size_t)ps * kPlanes * sizeof(h16));
     a.v.ps = ps; a.v.bs = bs; a.v.C = C;
-    CUDA_OK(cudaMemset(a.v.p, 0, (size_t)ps * 3 * sizeof(bf16)));
+    CUDA_OK(cudaMemset(a.v.p, 0, (size_t)ps * kPlanes * sizeof(h16)));
     return a;
   }
   // scratch buffers are shared by every block of the same geometry (one stream, in-order)
@@ -250,15 +250,15 @@ struct dmc_engine {
     }
     g.Npad = round_up(round_up(g.ncols, g.BN), 64);
     g.Kld = round_up(g.K, 64);
-    g.w = (bf16*)dalloc((size_t)3 * g.Npad * g.Kld * sizeof(bf16));
-    if (!simt()) g.wb = (bf16*)dalloc((size_t)3 * g.Npad * g.Kld * sizeof(bf16));
+    g.w = (h16*)dalloc((size_t)kPlanes * g.Npad * g.Kld * sizeof(h16));
+    if (!simt()) g.wb = (h16*)dalloc((size_t)kPlanes * g.Npad * g.Kld * sizeof(h16));
     g.bias = new_f32(g.Npad);
     g.tmap = &c->tmap;
     g.tmap_half = &c->tmap_half;
     g.tmap_s3 = &c->tmap_s3;
     g.tmap_s3_hi = &c->tmap_s3_hi;
     if (!simt()) {
-      if (make_tmap_s3_weight(&c->tmap_s3, g, 3) != 0 || make_tmap_s3_weight(&c->tmap_s3_hi, g, 1) != 0)
+      if (make_tmap_s3_weight(&c->tmap_s3, g, kPlanes) != 0 || make_tmap_s3_weight(&c->tmap_s3_hi, g, 1) != 0)
         fail("%s: %s", key.c_str(), gemm_s3_last_error());
       if (make_tmap_weight(&c->tmap, g, g.BN) != 0) fail("%s: %s", key.c_str(), umma_last_error());
       if (make_tmap_weight(&c->tmap_half, g, g.BN / 2) != 0) fail("%s: %s", key.c_str(), umma_last_error());
@@ -378,7 +378,7 @@ struct dmc_engine {
         t = tmaps.back().get();
       }
       if (make_tmap_s3_act64(tm3[3], a, M) != 0) fail("gemm A map (64 rows): %s", gemm_s3_last_error());
-      if (make_tmap_s3_act(tm3[0], a, M, nsplit == 3 ? 3 : 1) != 0) fail("gemm A map: %s", gemm_s3_last_error());
+      if (make_tmap_s3_act(tm3[0], a, M, nsplit != 1 ? kPlanes : 1) != 0) fail("gemm A map: %s", gemm_s3_last_error());
       if (spec.out_f32) {
         if (make_tmap_f32_rows(tm3[1], spec.out_f32, e.n_out, spec.ld_f32, M) != 0)
           fail("gemm fp32 out map: %s", gemm_s3_last_error());
@@ -403,7 +403,7 @@ struct dmc_engine {
       pend.push_back(d);
       pend_M = M;
       pend_flops += 2.0 * (double)M * g->N * g->K;
-      pend_issued += 2.0 * (double)M * g->N * g->K * (nsplit == 3 ? 6 : 1);
+      pend_issued += 2.0 * (double)M * g->N * g->K * (nsplit != 1 ? 3 : 1);
     } else if (use_umma) {
       tmaps.emplace_back(new CUtensorMap());
       CUtensorMap* tm = tmaps.back().get();
@@ -413,7 +413,7 @@ struct dmc_engine {
         Epi ee = e;
         if (table) ee.scale = table + (size_t)self->cur.qp * sc;
         double fl = 2.0 * (double)M * g->N * g->K;
-        if (self->profile) self->prof_begin(st, fl, fl * (nsplit == 3 ? 6 : 1));
+        if (self->profile) self->prof_begin(st, fl, fl * (nsplit != 1 ? 3 : 1));
         if (gemm_umma(tm, *g, ee, M, K, nsplit, st) != 0) fail("gemm_umma: %s", umma_last_error());
         if (self->profile) self->prof_end(st);
       });
@@ -671,7 +671,7 @@ void dmc_engine::build_p() {
     Act GB = new_act(B, H16, W16, 2 * CY);
     op([self, MK](cudaStream_t st) {
       if (self->cur.mask) unshuffle8_in(self->cur.mask, MK.v, self->B, 1, self->H, self->W, st);
-      else CUDA_OK(cudaMemsetAsync(MK.v.p, 0, (size_t)MK.v.ps * 3 * sizeof(bf16), st));
+      else CUDA_OK(cudaMemsetAsync(MK.v.p, 0, (size_t)MK.v.ps * kPlanes * sizeof(h16), st));
     });
     EpiSpec s; s.nsplit = ns;
     gemm(MK, sft_conv1, &PB, s);
@@ -1288,14 +1288,14 @@ extern "C" int dmc_bench_gemm(int rows, int k, int n, int mode, int nsplit, int 
     e.prog = &e.prog_common;
     e.use_s3 = pair == 2;
     Conv* c = e.add_conv("w", k, n, 1, 1, 0, mode == 3 ? PACK_PAIR : PACK_PLAIN);
-    CUDA_OK(cudaMemset(c->g.w, 0, (size_t)3 * c->g.Npad * c->g.Kld * sizeof(bf16)));
-    CUDA_OK(cudaMemset(c->g.wb, 0, (size_t)3 * c->g.Npad * c->g.Kld * sizeof(bf16)));
+    CUDA_OK(cudaMemset(c->g.w, 0, (size_t)kPlanes * c->g.Npad * c->g.Kld * sizeof(h16)));
+    CUDA_OK(cudaMemset(c->g.wb, 0, (size_t)kPlanes * c->g.Npad * c->g.Kld * sizeof(h16)));
     CUDA_OK(cudaMemset(c->g.bias, 0, sizeof(float) * c->g.Npad));
     Act in = e.new_act(1, 1, rows, k);
     Act out = e.new_act(1, 1, rows, mode == 3 ? n / 2 : n);
     Act res = e.new_act(1, 1, rows, n);
-    CUDA_OK(cudaMemset(in.v.p, 0, (size_t)in.v.ps * 3 * sizeof(bf16)));
-    CUDA_OK(cudaMemset(res.v.p, 0, (size_t)res.v.ps * 3 * sizeof(bf16)));
+    CUDA_OK(cudaMemset(in.v.p, 0, (size_t)in.v.ps * kPlanes * sizeof(h16)));
+    CUDA_OK(cudaMemset(res.v.p, 0, (size_t)res.v.ps * kPlanes * sizeof(h16)));
     EpiSpec s;
     s.nsplit = nsplit;
     if (mode == 1 || mode == 3) s.act = ACT_WSILU;
@@ -1333,7 +1333,7 @@ extern "C" int dmc_bench_dwconv(int batch, int height, int width, int channels, 
     dmc_engine e;
     e.variant = -1; e.B = batch; e.H = height; e.W = width;
     Act in = e.new_act(batch, height, width, channels), out = e.new_act(batch, height, width, channels);
-    CUDA_OK(cudaMemset(in.v.p, 0, (size_t)in.v.ps * 3 * sizeof(bf16)));
+    CUDA_OK(cudaMemset(in.v.p, 0, (size_t)in.v.ps * kPlanes * sizeof(h16)));
     float* w = e.new_f32((size_t)9 * channels);
     float* b = e.new_f32(channels);
     CUDA_OK(cudaMemset(w, 0, sizeof(float) * 9 * channels));
@@ -1370,15 +1370,15 @@ extern "C" int dmc_bench_dcb(int batch, int height, int width, int cin, int cout
     e.prog = &e.prog_common;
     Act a = e.new_act(batch, height, width, cin), b = e.new_act(batch, height, width, cout),
         c = e.new_act(batch, height, width, cout);
-    CUDA_OK(cudaMemset(a.v.p, 0, (size_t)a.v.ps * 3 * sizeof(bf16)));
+    CUDA_OK(cudaMemset(a.v.p, 0, (size_t)a.v.ps * kPlanes * sizeof(h16)));
     for (int i = 0; i < blocks; ++i) {
       DCB* w = e.add_dcb("b" + std::to_string(i), i == 0 ? cin : cout, cout);
       e.dcb(w, i == 0 ? a : (i % 2 ? b : c), i % 2 ? c : b, false, nullptr, 3);
     }
     e.flush_chain();
     for (auto& cv : e.convs) {
-      CUDA_OK(cudaMemset(cv->g.w, 0, (size_t)3 * cv->g.Npad * cv->g.Kld * sizeof(bf16)));
-      CUDA_OK(cudaMemset(cv->g.wb, 0, (size_t)3 * cv->g.Npad * cv->g.Kld * sizeof(bf16)));
+      CUDA_OK(cudaMemset(cv->g.w, 0, (size_t)kPlanes * cv->g.Npad * cv->g.Kld * sizeof(h16)));
+      CUDA_OK(cudaMemset(cv->g.wb, 0, (size_t)kPlanes * cv->g.Npad * cv->g.Kld * sizeof(h16)));
       CUDA_OK(cudaMemset(cv->g.bias, 0, sizeof(float) * cv->g.Npad));
     }
     for (auto& d : e.dws) {

@@ -16,11 +16,11 @@
 // pixel-shuffle stores, two residuals and odd shapes):
 //   * a cluster of two CTAs works on one 256 x BN tile with cta_group::2 MMAs: each CTA loads its own
 //     128 rows of A and HALF of the W tile (L2 -> SM operand traffic per MMA cycle 64 -> 48 B/clk);
-//   * K is staged in blocks of 32 (SWIZZLE_64B): a stage is 36 KB, four of them are in flight;
+//   * K is staged in blocks of 32 (two 16-wide SWIZZLE_32B k blocks): a stage is 24 KB, up to eight are in flight;
 //   * MMA / TMA issue runs in warp-uniform code with one elected lane, so descriptors live in uniform
 //     registers (the per-thread version spent ~12 instructions and a branch per MMA);
 //   * the epilogue is specialised per layer kind and moves no global memory itself: residual tiles
-//     arrive by TMA (one 3-plane box per warp and 16-column chunk, prefetched one chunk ahead) and
+//     arrive by TMA (one 2-plane box per warp and 16-column chunk, prefetched one chunk ahead) and
 //     results leave by TMA store from a swizzled staging tile (ring of three per warp).
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -56,7 +56,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 s3_get_encode() {
 }
 
 // 4-D map of a tile-blocked S3 view (common.cuh): {256 elements = 16 rows x 16 columns (512 contiguous bytes),
-// padded rows / 16, column blocks, 3 planes}; a box is {256, rows / 16, blocks, planes}.  No TMA swizzle: the data
+// padded rows / 16, column blocks, 2 planes}; a box is {256, rows / 16, blocks, planes}.  No TMA swizzle: the data
 // is stored pre-swizzled, global memory and shared memory images are identical.
 static int s3_encode(void* out, View v, int cols, uint32_t box_rows, uint32_t box_blocks, uint32_t planes) {
   auto fn = s3_get_encode();
@@ -64,11 +64,11 @@ static int s3_encode(void* out, View v, int cols, uint32_t box_rows, uint32_t bo
     snprintf(g_s3_err, sizeof g_s3_err, "cuTensorMapEncodeTiled entry point unavailable");
     return -1;
   }
-  cuuint64_t dims[4] = {256, (cuuint64_t)(v.bs / 256), (cuuint64_t)((cols + 15) / 16), 3};
+  cuuint64_t dims[4] = {256, (cuuint64_t)(v.bs / 256), (cuuint64_t)((cols + 15) / 16), (cuuint64_t)kPlanes};
   cuuint64_t strides[3] = {512, (cuuint64_t)v.bs * 2, (cuuint64_t)v.ps * 2};
   cuuint32_t box[4] = {256, box_rows / 16, box_blocks, planes};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, v.p, dims, strides, box, estr,
+  CUresult r = fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, v.p, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -80,7 +80,7 @@ static int s3_encode(void* out, View v, int cols, uint32_t box_rows, uint32_t bo
   return 0;
 }
 
-// A operand: box = 128 rows x 2 column blocks (32 k) x `planes` planes (3, or 1 = hi only for single-term products)
+// A operand: box = 128 rows x 2 column blocks (32 k) x `planes` planes (2, or 1 = hi only for single-term products)
 int make_tmap_s3_act(void* tmap_out, View a, long long M, int planes) {
   (void)M;
   return s3_encode(tmap_out, a, a.C, 128, 2, (uint32_t)planes);
@@ -90,7 +90,7 @@ int make_tmap_s3_act64(void* tmap_out, View a, long long M) {
   (void)M;
   return s3_encode(tmap_out, a, a.C, 64, 1, 1);
 }
-// W operand, from the tile-blocked copy [3][Kld/16][Npad][16]: 4-D map {256 elements, Npad/16, Kld/16, 3} with a box
+// W operand, from the tile-blocked copy [2][Kld/16][Npad][16]: 4-D map {256 elements, Npad/16, Kld/16, 2} with a box
 // of {256, BN/32, 2 k blocks, planes}: the BN/2 x 32 half tile of one CTA arrives as BN/16 segments of 512 bytes per
 // plane (row-major it was BN/2 segments of 64 bytes, and the TMA unit retires well under one segment per clock)
 int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes) {
@@ -100,11 +100,11 @@ int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes) {
     return -1;
   }
   const uint64_t plane_bytes = (uint64_t)w.Npad * w.Kld * 2;
-  cuuint64_t dims[4] = {256, (cuuint64_t)w.Npad / 16, (cuuint64_t)w.Kld / 16, 3};
+  cuuint64_t dims[4] = {256, (cuuint64_t)w.Npad / 16, (cuuint64_t)w.Kld / 16, (cuuint64_t)kPlanes};
   cuuint64_t strides[3] = {512, (cuuint64_t)w.Npad * 32, plane_bytes};
   cuuint32_t box[4] = {256, (cuuint32_t)(w.BN / 32), 2, (cuuint32_t)planes};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn((CUtensorMap*)tmap_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, w.wb, dims, strides, box, estr,
+  CUresult r = fn((CUtensorMap*)tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, w.wb, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -114,11 +114,11 @@ int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes) {
   }
   return 0;
 }
-// epilogue tiles (residual in / result out): box = 32 rows x 1 column block (16 columns) x 3 planes = three
+// epilogue tiles (residual in / result out): box = 32 rows x 1 column block (16 columns) x 2 planes = two
 // contiguous 1 KB pieces; only the first `cols` columns of the view exist for the map
 int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M) {
   (void)M;
-  return s3_encode(tmap_out, v, cols, 32, 1, 3);
+  return s3_encode(tmap_out, v, cols, 32, 1, kPlanes);
 }
 // fp32 result rows [M, ld]: 2-D map, box = 16 columns x 32 rows, SWIZZLE_64B
 int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M) {
@@ -331,12 +331,6 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
                : "memory");
   return v;
 }
-// two floats -> packed bf16x2 (low half = a), round to nearest even
-__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
 // layers.py:8-10  silu(4x)/4 == x / (1 + exp(-4x)); MUFU.RCP instead of an IEEE division (<= 2 ulp
 // from the reference's result; the GOP parity tests run through this path)
 __device__ __forceinline__ float wsilu_fast(float x) {
@@ -359,10 +353,10 @@ struct alignas(64) S3StageDev {
   const float* scale;
   int k_blocks, BN, n_tiles, n_out;
   int kind;          // S3_*
-  int nterms;        // 6: fp32-grade split product (two accumulators), 1: hi*hi only
+  int nterms;        // 3: fp32-grade split product (two accumulators), 1: hi*hi only
   uint32_t need;     // increments of done[l-1][row tile] per launch that complete layer l-1 for a row tile
   int publish;       // a later layer of the chain waits for this one: completed tiles are counted in done[l]
-  uint8_t* blob;     // probe switch 16 only: S3 result buffer, written as contiguous 3 KB blobs (layout garbage)
+  uint8_t* blob;     // probe switch 16 only: result buffer, written as contiguous 2 KB blobs (layout garbage)
   long long blob_pad_;
 };
 struct S3ChainParams {
@@ -379,18 +373,18 @@ struct S3ChainParams {
 };
 
 constexpr int kS3BK = 32;
-constexpr int kS3APlane = 128 * kS3BK * 2;        // one plane of a 128 x 32 bf16 tile
+constexpr int kS3APlane = 128 * kS3BK * 2;        // one plane of a 128 x 32 fp16 tile
 constexpr int kS3EpiWarps = 8;
 // warp group 0: TMA producer, MMA issuer, two spare warps (56 registers); warp groups 1-2: eight epilogue
 // warps (224 registers, setmaxnreg) -- the six inlined epilogue variants do not fit the 168 registers a
 // 384-thread CTA gets by default
 constexpr int kS3Threads = 128 + 32 * kS3EpiWarps;
-constexpr int kS3ChunkBytes = 3 * 32 * 32;        // [3 planes][32 rows][16 bf16]
+constexpr int kS3ChunkBytes = kPlanes * 32 * 32;  // [2 planes][32 rows][16 fp16]
 constexpr int kS3Ring = 3;                        // staging tiles per epilogue warp (residual in -> result out)
 constexpr int kS3WarpSmem = kS3Ring * kS3ChunkBytes;
 constexpr int kS3BarBytes = 512;
 
-// Shared-memory descriptor (cute::UMMA::SmemDescriptor) of a K-major SWIZZLE_32B operand tile = rows of 16 bf16
+// Shared-memory descriptor (cute::UMMA::SmemDescriptor) of a K-major SWIZZLE_32B operand tile = rows of 16 fp16
 // (32 B), which is what the tile-blocked activations and weights are in shared memory: start>>4 [0,14) | LBO (unused)
 // = 1 [16,30) | SBO = 8 rows x 32 B = 256 -> 16 [32,46) | version 1 [46,48) | layout SWIZZLE_32B = 6 [61,64)
 __device__ __forceinline__ uint64_t s3_desc32(uint32_t saddr) {
@@ -500,7 +494,7 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float t = __uint_as_float(a[i]);
-        if (two_acc) t = add_rn(t, __uint_as_float(b[i]));
+        if (two_acc) t = fmaf(__uint_as_float(b[i]), kLoInv, t);
         t = add_rn(t, bias[i]);
         if (kAct == ACT_WSILU) t = wsilu_fast(t);
         v[i] = t;
@@ -517,7 +511,7 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float t = __uint_as_float(a[i]);
-          if (two_acc) t = add_rn(t, __uint_as_float(b[i]));
+          if (two_acc) t = fmaf(__uint_as_float(b[i]), kLoInv, t);
           t = add_rn(t, bias[i]);
           if (kAct == ACT_WSILU) t = wsilu_fast(t);
           v[i] = add_rn(v[i], t);
@@ -533,18 +527,16 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
       const uint32_t src = tileBuf + rowOff;
       float t[16];
 #pragma unroll
-      for (int pl = 2; pl >= 0; --pl) {    // (lo + mid) + hi, exactly join3
+      for (int hf = 0; hf < 2; ++hf) {     // hi + lo * 2^-11, exactly join2
+        const uint4 qh = ld_shared_v4(src + (((uint32_t)hf << 4) ^ swz));
+        const uint4 ql = ld_shared_v4(src + 1024 + (((uint32_t)hf << 4) ^ swz));
+        const uint32_t uh[4] = {qh.x, qh.y, qh.z, qh.w};
+        const uint32_t ul[4] = {ql.x, ql.y, ql.z, ql.w};
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const uint4 q = ld_shared_v4(src + pl * 1024 + (((uint32_t)hf << 4) ^ swz));
-          const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float lo = bf16lo(u[k]), hi = bf16hi(u[k]);
-            const int i = 8 * hf + 2 * k;
-            t[i] = pl == 2 ? lo : add_rn(t[i], lo);
-            t[i + 1] = pl == 2 ? hi : add_rn(t[i + 1], hi);
-          }
+        for (int k = 0; k < 4; ++k) {
+          const int i = 8 * hf + 2 * k;
+          t[i] = join2(h2lo(uh[k]), h2lo(ul[k]));
+          t[i + 1] = join2(h2hi(uh[k]), h2hi(ul[k]));
         }
       }
 #pragma unroll
@@ -572,29 +564,19 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
       __syncwarp();
       if (lane == 0 && x.epi_mem) tma_store_2d(S.tmOut, tileBuf, dcol, row0);
     } else {
-      // exact 3-way split, two elements per conversion
-      uint32_t ph_[8], pm_[8], pl_[8];
+      // hi / 2^11-scaled lo split, two elements per conversion
+      uint32_t ph_[8], pl_[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float x0 = v[2 * i], x1 = v[2 * i + 1];
-        const uint32_t h = cvt_bf16x2(x0, x1);
-        const float r0 = sub_rn(x0, bf16lo(h)), r1 = sub_rn(x1, bf16hi(h));
-        const uint32_t m = cvt_bf16x2(r0, r1);
-        ph_[i] = h;
-        pm_[i] = m;
-        pl_[i] = cvt_bf16x2(sub_rn(r0, bf16lo(m)), sub_rn(r1, bf16hi(m)));
-      }
+      for (int i = 0; i < 8; ++i) split2x2(v[2 * i], v[2 * i + 1], ph_[i], pl_[i]);
       const uint32_t dst = tileBuf + rowOff;
       st_shared_v4(dst + swz, ph_[0], ph_[1], ph_[2], ph_[3]);
       st_shared_v4(dst + (16u ^ swz), ph_[4], ph_[5], ph_[6], ph_[7]);
-      st_shared_v4(dst + 1024 + swz, pm_[0], pm_[1], pm_[2], pm_[3]);
-      st_shared_v4(dst + 1024 + (16u ^ swz), pm_[4], pm_[5], pm_[6], pm_[7]);
-      st_shared_v4(dst + 2048 + swz, pl_[0], pl_[1], pl_[2], pl_[3]);
-      st_shared_v4(dst + 2048 + (16u ^ swz), pl_[4], pl_[5], pl_[6], pl_[7]);
+      st_shared_v4(dst + 1024 + swz, pl_[0], pl_[1], pl_[2], pl_[3]);
+      st_shared_v4(dst + 1024 + (16u ^ swz), pl_[4], pl_[5], pl_[6], pl_[7]);
       fence_async_smem();
       __syncwarp();
       if (lane == 0 && x.epi_mem) {
-        if (S.blob) {          // probe: same bytes, one contiguous 3 KB bulk copy (6 segments of 512 B instead of 96 of 32 B)
+        if (S.blob) {          // probe: same bytes, one contiguous 2 KB bulk copy
           uint8_t* g = S.blob + ((size_t)(row0 >> 5) * (size_t)(S.n_out >> 4) + (size_t)(dcol >> 4)) * kS3ChunkBytes;
           asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(tileBuf),
                        "r"((uint32_t)kS3ChunkBytes) : "memory");
@@ -693,13 +675,13 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       }
       if (lane == 0) st_release_cta_shared(depsOk, tcount + 1);
       const uint32_t wRows = (uint32_t)S.BN >> 1;
-      const uint32_t tx = 2u * (S.nterms == 1 ? 1u : 3u) * (kS3APlane + wRows * (kS3BK * 2));   // 1 term: hi planes only
+      const uint32_t tx = 2u * (S.nterms == 1 ? 1u : (uint32_t)kPlanes) * (kS3APlane + wRows * (kS3BK * 2));   // 1 term: hi planes only
       const int m_idx = mt * 256 + (int)rank * 128;
       const int n_idx = nt * S.BN + (int)(rank * wRows);
       for (int kb = 0; kb < S.k_blocks; ++kb) {
         mbar_wait(bar_empty(s), ph ^ 1, p.err, 1);
         const uint32_t sa = base + s * stageBytes;
-        const uint32_t sw = sa + 3 * kS3APlane;
+        const uint32_t sw = sa + kPlanes * kS3APlane;
         if (elect_one()) {
           const uint32_t lbar = mapa(bar_full(s), leaderRank);
           if (p.dbg & 1) {
@@ -712,7 +694,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
               // the two pairs work on the same rows: this CTA fetches 64 of its 128 rows and multicasts them to
               // the CTA of the same rank in the other pair (which sends the other 64)
               const uint16_t mc = (uint16_t)((1u << rank) | (4u << rank));
-              const int planes = S.nterms == 1 ? 1 : 3;
+              const int planes = S.nterms == 1 ? 1 : kPlanes;
               for (int pl = 0; pl < planes; ++pl)
                 for (int blk = 0; blk < 2; ++blk)
                   tma_load_pair_mcast(sa + pl * kS3APlane + blk * 4096u + pairIdx * 2048u, &S.tmA64,
@@ -738,13 +720,13 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
         const uint32_t e = __ldg(p.table + ei);
         const S3StageDev& S = p.st[e >> 28];
-        // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
+        // instruction descriptor: D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0, K-major both,
         // N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(S.BN >> 3) << 17) | (16u << 24);
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(S.BN >> 3) << 17) | (16u << 24);
         const uint32_t wStep = ((uint32_t)(S.BN >> 1) * (kS3BK * 2)) >> 4;   // plane stride of the W stage
         const uint32_t wKs = ((uint32_t)(S.BN >> 1) * 32u) >> 4;             // second 16-wide k block of a plane
         const int k_blocks = S.k_blocks;
-        const bool six = S.nterms != 1;
+        const bool split = S.nterms != 1;
         const uint32_t buf = tcount & 1;
         mbar_wait(bar_tempty(buf), ((tcount >> 1) & 1) ^ 1, p.err, 2);
         tc_fence_after();
@@ -755,22 +737,19 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
           tc_fence_after();
           const uint32_t sa = base + s * stageBytes;
           const uint64_t da = s3_desc32(sa);
-          const uint64_t dw = s3_desc32(sa + 3 * kS3APlane);
+          const uint64_t dw = s3_desc32(sa + kPlanes * kS3APlane);
           const uint32_t first = kb == 0 ? 0u : 1u;
           if (elect_one()) {
             if (!(p.dbg & 2)) {
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
-                // term 0 = hi*hi -> main accumulator; the five small terms (smallest first) -> second one
-                // (plane index: 0 hi, 1 mid, 2 lo):  hl, lh, mm, hm, mh
-                const uint64_t a0 = da + ks * (4096u >> 4), a1 = a0 + aStep, a2 = a0 + 2 * aStep;
-                const uint64_t w0 = dw + ks * wKs, w1 = w0 + wStep, w2 = w0 + 2 * wStep;
+                // hi*hi -> main accumulator; the two 2^11-scaled cross terms hi*lo', lo'*hi -> second one
+                // (plane index: 0 hi, 1 lo')
+                const uint64_t a0 = da + ks * (4096u >> 4), a1 = a0 + aStep;
+                const uint64_t w0 = dw + ks * wKs, w1 = w0 + wStep;
                 tc_mma_pair(d_main, a0, w0, idesc, ks == 0 ? first : 1u);
-                if (six) {
-                  tc_mma_pair(d_small, a0, w2, idesc, ks == 0 ? first : 1u);
-                  tc_mma_pair(d_small, a2, w0, idesc, 1u);
-                  tc_mma_pair(d_small, a1, w1, idesc, 1u);
-                  tc_mma_pair(d_small, a0, w1, idesc, 1u);
+                if (split) {
+                  tc_mma_pair(d_small, a0, w1, idesc, ks == 0 ? first : 1u);
                   tc_mma_pair(d_small, a1, w0, idesc, 1u);
                 }
               }
@@ -928,7 +907,7 @@ static int g_s3_dbg = 0;
 void gemm_s3_set_debug(int mask) { g_s3_dbg = mask; }
 
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit) {
-  if ((nsplit != 3 && nsplit != 1) || !w.tmap_s3 || !w.tmap_s3_hi || e.do_clamp || e.res2.p) return false;
+  if (!w.tmap_s3 || !w.tmap_s3_hi || e.do_clamp || e.res2.p) return false;
   if (w.BN % 32 || w.BN > 128 || e.n_out % 16) return false;
   if (e.out_f32) {                       // fp32 rows: plain layout, no residual, and not both outputs at once
     return !e.out.p && e.pack == PACK_PLAIN && !e.res1.p && (e.act == ACT_NONE || e.act == ACT_WSILU) &&
@@ -1026,7 +1005,7 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     S3StageDev& S = c->p.st[l];
     memcpy(&S.tmA, d.tmA, sizeof(CUtensorMap));
     memcpy(&S.tmA64, d.tmA64 ? d.tmA64 : d.tmA, sizeof(CUtensorMap));
-    memcpy(&S.tmW, d.nsplit == 3 ? d.w->tmap_s3 : d.w->tmap_s3_hi, sizeof(CUtensorMap));
+    memcpy(&S.tmW, d.nsplit != 1 ? d.w->tmap_s3 : d.w->tmap_s3_hi, sizeof(CUtensorMap));
     memcpy(&S.tmOut, d.tmOut, sizeof(CUtensorMap));
     memcpy(&S.tmRes, d.tmRes ? d.tmRes : d.tmOut, sizeof(CUtensorMap));
     S.bias = d.e.bias;
@@ -1037,7 +1016,7 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     S.n_tiles = (d.w->ncols + d.w->BN - 1) / d.w->BN;
     S.n_out = d.e.n_out;
     S.kind = s3_kind(d.e);
-    S.nterms = d.nsplit == 3 ? 6 : 1;
+    S.nterms = d.nsplit != 1 ? 3 : 1;
     // one count per CTA and table entry of the previous layer for these rows
     S.need = l == 0 ? 0u : (cl4 ? (uint32_t)((c->p.st[l - 1].n_tiles + 1) / 2) * 4u : (uint32_t)c->p.st[l - 1].n_tiles * 2u);
     S.publish = l + 1 < n ? 1 : 0;
@@ -1052,7 +1031,7 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     tiles_per_step += S.n_tiles;
   }
   // smem plan
-  const int stage_bytes = 3 * (kS3APlane + (maxBN / 2) * kS3BK * 2);
+  const int stage_bytes = kPlanes * (kS3APlane + (maxBN / 2) * kS3BK * 2);
   const int fixed = kS3EpiWarps * kS3WarpSmem + kS3BarBytes;
   int nst = (smem_max - fixed) / stage_bytes;
   if (nst > 8) nst = 8;

@@ -1,17 +1,17 @@
 // tcgen05 / TMA / TMEM contraction kernel for sm_100a:  out = epilogue(A[M,K] . W[N,K]^T).
 //
-// Operands are S3 tensors (three bf16 planes hi/mid/lo, see common.cuh).  One persistent CTA
+// Operands are split-fp16 tensors (two planes hi / 2^11-scaled lo, see common.cuh).  One persistent CTA
 // per SM walks 128 x BN output tiles.  Warp roles:
 //   warp 0      TMA producer: cp.async.bulk.tensor (3-D maps {K, rows, plane}, SWIZZLE_128B)
 //               into a ring of smem stages, completion on mbarriers
-//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 ->
-//               fp32 in TMEM).  nsplit == 3 issues the 6 cross terms hh,hm,mh,hl,lh,mm per
-//               16-wide k step (fp32-grade product), nsplit == 1 issues hh only.
-//               The tensor core adds into its fp32 accumulator with truncation, a bias that grows
-//               with the number of adds (measured: ~0.2 ulp per MMA).  The dominant hh term
-//               therefore has its own accumulator and the five small terms (<= 2^-8 of it) share
-//               a second one; the epilogue adds the two in round-to-nearest fp32.  That cuts the
-//               truncating adds into the large accumulator 6x.
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (fp16 x fp16 ->
+//               fp32 in TMEM).  nsplit != 1 issues the 3 terms hh | hl, lh per 16-wide k step
+//               (fp32-grade product), nsplit == 1 issues hh only.
+//               hh has its own accumulator; the two cross terms carry the 2^11 scale of the lo planes
+//               and share a second one; the epilogue computes main + small * 2^-11 in one fp32 FMA.
+//               (The tensor core adds into its fp32 accumulator with truncation, a bias that grows
+//               with the number of adds -- measured ~0.2 ulp per MMA: keeping the small terms out of
+//               the main accumulator also keeps its truncating adds to one per k step.)
 //   warps 2..9  epilogue (two warps per TMEM lane quadrant, alternating 32-column chunks):
 //               tcgen05.ld the accumulator (lane == output row), bias / WSiLU / chunk-add pairing /
 //               residuals / per-channel scale, split back into S3 planes; residual loads and
@@ -54,11 +54,11 @@ static int encode4d(void* out, const void* base, uint64_t rows16, uint64_t block
     snprintf(g_umma_err, sizeof g_umma_err, "cuTensorMapEncodeTiled entry point unavailable");
     return -1;
   }
-  cuuint64_t dims[4] = {256, rows16, blocks, 3};
+  cuuint64_t dims[4] = {256, rows16, blocks, (cuuint64_t)kPlanes};
   cuuint64_t strides[3] = {512, block_bytes, plane_bytes};
   cuuint32_t box[4] = {256, box_rows / 16, 4, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+  CUresult r = fn((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -187,7 +187,7 @@ struct UmmaParams {
   int* err;
 };
 
-constexpr int kATileBytes = 128 * 64 * 2;   // one plane of a 128 x 64 bf16 tile
+constexpr int kATileBytes = 128 * 64 * 2;   // one plane of a 128 x 64 fp16 tile
 constexpr int kThreads = 64 + 32 * 8;   // TMA warp, MMA warp, 8 epilogue warps
 
 // ---- epilogue of one 32-column chunk, executed by a whole warp (lane == accumulator row) ----
@@ -211,12 +211,6 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
                : "memory");
   return v;
 }
-// two floats -> packed bf16x2 (lo half = a), round to nearest even: one F2FP instruction
-__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
 // layers.py:8-10 silu(4x)/4 == x / (1 + exp(-4x)); the reciprocal is MUFU.RCP (<= 1 ulp) instead of
 // an IEEE division: <= 2 ulp from the reference's result, 10 instructions instead of ~30.
 __device__ __forceinline__ float wsilu_fast(float x) {
@@ -237,7 +231,7 @@ struct RowMap {
   bool ok[4];
 };
 
-// one S3 plane of 32 rows x 32 columns through the staging tile: t = g (first) or t += g
+// one plane of 32 rows x 32 columns through the staging tile: t = g * 2^-11 (lo plane, first) or t += g (hi)
 template <bool kFirst>
 __device__ __forceinline__ void stage_plane_in(const uint4 (&g)[4], uint32_t wr, uint32_t rd, int lane, float* t) {
 #pragma unroll
@@ -252,9 +246,9 @@ __device__ __forceinline__ void stage_plane_in(const uint4 (&g)[4], uint32_t wr,
         const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float lo = bf16lo(u[k]), hi = bf16hi(u[k]);
-          t[8 * j + 2 * k] = kFirst ? lo : add_rn(t[8 * j + 2 * k], lo);
-          t[8 * j + 2 * k + 1] = kFirst ? hi : add_rn(t[8 * j + 2 * k + 1], hi);
+          const float lo = h2lo(u[k]), hi = h2hi(u[k]);
+          t[8 * j + 2 * k] = kFirst ? mul_rn(lo, kLoInv) : add_rn(t[8 * j + 2 * k], lo);
+          t[8 * j + 2 * k + 1] = kFirst ? mul_rn(hi, kLoInv) : add_rn(t[8 * j + 2 * k + 1], hi);
         }
       }
     }
@@ -262,28 +256,26 @@ __device__ __forceinline__ void stage_plane_in(const uint4 (&g)[4], uint32_t wr,
   }
 }
 
-// t[32] = hi+mid+lo of the 32 columns [dcol, dcol+32) of this lane's row of `src` ((lo+mid)+hi, exactly
-// join3).  All 12 global loads (3 planes x 4 row groups) are issued before the first use, so a
+// t[32] = hi + lo * 2^-11 of the 32 columns [dcol, dcol+32) of this lane's row of `src` (exactly
+// join2).  All 8 global loads (2 planes x 4 row groups) are issued before the first use, so a
 // residual costs one memory round trip; the rows then pass through the staging tile 16 at a time.
 __device__ __forceinline__ void staged_load_s3(const View& src, const RowMap& rm, long long goff, int dcol,
                                                int ncols, uint32_t stage, int lane, float* t) {
   const int slot = lane & 3;
   const bool col_ok = slot * 8 < ncols;
-  uint4 gh[4], gm[4], gl[4];
+  uint4 gh[4], gl[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const bf16* q = src.p + s3_unit_offset(src, rm.base[i] + goff, dcol + slot * 8);
-    gh[i] = gm[i] = gl[i] = make_uint4(0, 0, 0, 0);
+    const h16* q = src.p + s3_unit_offset(src, rm.base[i] + goff, dcol + slot * 8);
+    gh[i] = gl[i] = make_uint4(0, 0, 0, 0);
     if (rm.ok[i] && col_ok) {
       gh[i] = *reinterpret_cast<const uint4*>(q);
-      gm[i] = *reinterpret_cast<const uint4*>(q + src.ps);
-      gl[i] = *reinterpret_cast<const uint4*>(q + 2 * src.ps);
+      gl[i] = *reinterpret_cast<const uint4*>(q + src.ps);
     }
   }
   const uint32_t wr = stage + (lane >> 2) * kStageRowBytes + slot * 16;
   const uint32_t rd = stage + (lane & 15) * kStageRowBytes;
   stage_plane_in<true>(gl, wr, rd, lane, t);
-  stage_plane_in<false>(gm, wr, rd, lane, t);
   stage_plane_in<false>(gh, wr, rd, lane, t);
 }
 
@@ -369,24 +361,16 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, const RowMap& rm, l
       if (i < ncols) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
   if (e.out.p) {
-    // exact 3-way split, two elements per conversion: hi = bf16x2(v), mid = bf16x2(v - hi), lo = bf16x2(rest)
+    // 2-way split, two elements per conversion: hi = f16x2(v), lo = f16x2((v - hi) * 2^11)
     uint32_t* ph = r0;                              // the accumulator registers are dead by now
-    uint32_t pm[16], pl[16];
+    uint32_t pl[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float a = v[2 * i], b = v[2 * i + 1];
-      const uint32_t h = cvt_bf16x2(a, b);
-      const float ra = sub_rn(a, bf16lo(h)), rb = sub_rn(b, bf16hi(h));
-      const uint32_t mm = cvt_bf16x2(ra, rb);
-      ph[i] = h;
-      pm[i] = mm;
-      pl[i] = cvt_bf16x2(sub_rn(ra, bf16lo(mm)), sub_rn(rb, bf16hi(mm)));
-    }
+    for (int i = 0; i < 16; ++i) split2x2(v[2 * i], v[2 * i + 1], ph[i], pl[i]);
     const int slot = lane & 3;
     const bool col_ok = slot * 8 < ncols;
     const uint32_t wr = stage + (lane & 15) * kStageRowBytes;
     const uint32_t rd = stage + (lane >> 2) * kStageRowBytes + slot * 16;
-    bf16* dst[4];
+    h16* dst[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) dst[i] = e.out.p + s3_unit_offset(e.out, rm.base[i] + goff, dcol + slot * 8);
     auto store_plane = [&](const uint32_t* q, long long poff) {
@@ -407,8 +391,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, const RowMap& rm, l
       }
     };
     store_plane(ph, 0);
-    store_plane(pm, e.out.ps);
-    store_plane(pl, 2 * e.out.ps);
+    store_plane(pl, e.out.ps);
   }
 }
 
@@ -460,7 +443,7 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uin
 //                 128 rows of A and HALF of the W tile (BN/2 rows); the leader CTA issues one
 //                 M=256 MMA that reads W from both CTAs' shared memory and writes each CTA's 128
 //                 accumulator rows into that CTA's TMEM.  L2->SM operand traffic per MMA drops to
-//                 3/4 and a stage shrinks from 96 KB to 72 KB, so the ring holds 3 stages.
+//                 3/4 and a stage shrinks from 64 KB to 48 KB, so the ring holds 4 stages.
 template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -558,14 +541,14 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
+      // instruction descriptor: D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0, K-major both,
       // N>>3 at [17,23), M>>4 at [24,29)  (M = 256 for the pair)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
-      const int nterms = (p.nsplit == 3) ? 6 : 1;
-      // term 0 = hi*hi -> main accumulator; terms 1..5 (smallest first) -> second accumulator
-      const int ta[6] = {0, 0, 2, 1, 0, 1};
-      const int tw[6] = {0, 2, 0, 1, 1, 0};
+      const int nterms = (p.nsplit != 1) ? 3 : 1;
+      // term 0 = hi*hi -> main accumulator; hi*lo', lo'*hi (2^11-scaled) -> second accumulator
+      const int ta[3] = {0, 0, 1};
+      const int tw[3] = {0, 1, 0};
       uint32_t it = 0, tcount = 0;
       for (int tile = unit; tile < total_tiles; tile += units, ++tcount) {
         const int buf = tcount & 1;
@@ -626,7 +609,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(bar_tfull(buf), tph, p.err, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 256u;
-      const bool two_acc = p.nsplit == 3;
+      const bool two_acc = p.nsplit != 1;
       auto load_chunk = [&](int c, uint32_t* r) {     // accumulator columns [c, c+32) of this row
         tc_ld32(taddr + c, r);
         if (two_acc) {
@@ -635,7 +618,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            r[i] = __float_as_uint(add_rn(__uint_as_float(r[i]), __uint_as_float(s2[i])));
+            r[i] = __float_as_uint(fmaf(__uint_as_float(s2[i]), kLoInv, __uint_as_float(r[i])));
         } else {
           tc_wait_ld();
         }
@@ -705,7 +688,8 @@ int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int 
     cudaMalloc(&d_err, sizeof(int));
     cudaMemset(d_err, 0, sizeof(int));
   }
-  if (!w.tmap || (w.BN % 32) || w.BN > (nsplit == 3 ? 128 : 256) || (e.pack == PACK_PAIR && (w.BN % 64))) {
+  if (nsplit != 1) nsplit = kPlanes;             // planes staged per operand: both, or hi only
+  if (!w.tmap || (w.BN % 32) || w.BN > (nsplit != 1 ? 128 : 256) || (e.pack == PACK_PAIR && (w.BN % 64))) {
     snprintf(g_umma_err, sizeof g_umma_err, "gemm_umma: unsupported weight tiling BN=%d", w.BN);
     return -1;
   }

@@ -26,10 +26,10 @@ int num_sms() {
 }
 
 // ------------------------------------------------------------------ weights
-// `out`: row-major S3 [3][Npad][Kld] (general / SIMT kernels).  `outb`: the same values tile-blocked for the chain
-// kernel, [3][Kld/16][Npad][16] with the 16-byte halves of a row swapped where bit 2 of the row is set -- exactly
+// `out`: row-major split planes [2][Npad][Kld] (SIMT kernel).  `outb`: the same values tile-blocked for the tcgen05
+// kernels, [2][Kld/16][Npad][16] with the 16-byte halves of a row swapped where bit 2 of the row is set -- exactly
 // the shared-memory image of a K-major SWIZZLE_32B operand, so a W tile is fetched as a few 512-byte segments.
-__global__ void k_pack_gemm_weight(const float* __restrict__ w, bf16* __restrict__ out, bf16* __restrict__ outb,
+__global__ void k_pack_gemm_weight(const float* __restrict__ w, h16* __restrict__ out, h16* __restrict__ outb,
                                    int cout, int cin, int kh, int kw, int Npad, int Kld, int K, int pack,
                                    int Cg, int Cg_pad) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,18 +52,16 @@ __global__ void k_pack_gemm_weight(const float* __restrict__ w, bf16* __restrict
     int y = tap / kw, x = tap % kw;
     v = w[(((long long)n * cin + ci) * kh + y) * kw + x];
   }
-  bf16 h, m, l;
-  split3(v, h, m, l);
+  h16 h, l;
+  split2(v, h, l);
   long long ps = (long long)Npad * Kld;
   out[idx] = h;
-  out[ps + idx] = m;
-  out[2 * ps + idx] = l;
+  out[ps + idx] = l;
   if (outb) {
     const int blk = kk >> 4, half = (kk >> 3) & 1, e8 = kk & 7;
     const long long ib = ((long long)blk * Npad + r) * 16 + ((half ^ ((r >> 2) & 1)) << 3) + e8;
     outb[ib] = h;
-    outb[ps + ib] = m;
-    outb[2 * ps + ib] = l;
+    outb[ps + ib] = l;
   }
 }
 
@@ -230,12 +228,13 @@ __global__ void k_finite_check(View v, long long M, int C8, int* flag) {
   if (idx >= M * C8) return;
   long long m = idx / C8;
   int c = (int)(idx % C8) * 8;
+  // hi plane: inf / nan, or saturated at the fp16 range limit (|x| >= 65504 cannot be represented)
   uint4 a = *reinterpret_cast<const uint4*>(v.p + s3_unit_offset(v, m, c));
   const uint32_t* u = &a.x;
   bool bad = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    bad |= ((u[i] & 0x7f80u) == 0x7f80u) | ((u[i] & 0x7f800000u) == 0x7f800000u);
+    bad |= ((u[i] & 0x7fffu) >= 0x7bffu) | ((u[i] & 0x7fff0000u) >= 0x7bff0000u);
   }
   if (bad) atomicOr(flag, 1);
 }
@@ -356,17 +355,15 @@ __global__ void k_im2col(View in, View out, int B, int H, int W, int k, int stri
   int ho = (int)((mo / Wo) % Ho);
   int b = (int)(mo / ((long long)Wo * Ho));
   int hi = ho * stride - pad + tap / k, wi = wo * stride - pad + tap % k;
-  uint4 z = make_uint4(0, 0, 0, 0), a = z, bb = z, cc = z;
+  uint4 z = make_uint4(0, 0, 0, 0), a = z, bb = z;
   if ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W) {
-    const bf16* q = in.p + s3_unit_offset(in, ((long long)b * H + hi) * W + wi, c);
+    const h16* q = in.p + s3_unit_offset(in, ((long long)b * H + hi) * W + wi, c);
     a = *reinterpret_cast<const uint4*>(q);
     bb = *reinterpret_cast<const uint4*>(q + in.ps);
-    cc = *reinterpret_cast<const uint4*>(q + 2 * in.ps);
   }
-  bf16* d = out.p + s3_unit_offset(out, mo, tap * tap_stride + col_off + c);
+  h16* d = out.p + s3_unit_offset(out, mo, tap * tap_stride + col_off + c);
   *reinterpret_cast<uint4*>(d) = a;
   *reinterpret_cast<uint4*>(d + out.ps) = bb;
-  *reinterpret_cast<uint4*>(d + 2 * out.ps) = cc;
 }
 void im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, int Ho, int Wo,
             int tap_stride, int col_off, cudaStream_t st) {
@@ -380,7 +377,7 @@ void im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, 
 // out[m][n] = sum_k A[m][k] * W[n][k]; 64x64 tile, 256 threads, 4x4 outputs per thread with
 // columns tx, tx+16, tx+32, tx+48 so that in PACK_PAIR mode (tile = one 64-column group) a
 // thread holds both members of every chunk-add pair.  Validation backend + odd shapes.
-__global__ void __launch_bounds__(256) k_gemm_simt(View a, const bf16* __restrict__ wp, long long wps,
+__global__ void __launch_bounds__(256) k_gemm_simt(View a, const h16* __restrict__ wp, long long wps,
                                                    int Kld, int K, long long M, Epi e) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
@@ -399,8 +396,8 @@ __global__ void __launch_bounds__(256) k_gemm_simt(View a, const bf16* __restric
     for (int i = 0; i < 4; ++i) {
       int k = k0 + lk + i;
       As[lk + i][lr] = (ar < M && k < K) ? ld3(a, ar, k) : 0.0f;
-      const bf16* q = wp + (long long)(n0 + lr) * Kld + k;
-      Bs[lk + i][lr] = (k < Kld) ? join3(q[0], q[wps], q[2 * wps]) : 0.0f;
+      const h16* q = wp + (long long)(n0 + lr) * Kld + k;
+      Bs[lk + i][lr] = (k < Kld) ? join2(q[0], q[wps]) : 0.0f;
     }
     __syncthreads();
 #pragma unroll

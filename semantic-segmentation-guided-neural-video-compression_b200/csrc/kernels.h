@@ -9,10 +9,10 @@ void note_launch();            // every kernel launch of the library is counted
 long long launch_count();
 
 // ---------------- weights ----------------
-// Packed contraction weight: S3 [3][Npad][Kld] bf16, K index = (kh*KW + kw)*Cin + ci.
+// Packed contraction weight: split planes [2][Npad][Kld] fp16 (hi, 2^11-scaled lo), K index = (kh*KW + kw)*Cin + ci.
 struct GemmW {
-  bf16* w = nullptr;
-  bf16* wb = nullptr;      // tile-blocked, pre-swizzled copy [3][Kld/16][Npad][16] for the chain kernel (or nullptr)
+  h16* w = nullptr;
+  h16* wb = nullptr;       // tile-blocked, pre-swizzled copy [2][Kld/16][Npad][16] for the tcgen05 kernels (or nullptr)
   float* bias = nullptr;   // [Npad], packed order, zero on padding
   int N = 0, K = 0;        // logical (N = cout, K = cin*kh*kw)
   int ncols = 0;           // packed columns before tile padding (pair / shuffle layouts included)
@@ -22,7 +22,7 @@ struct GemmW {
   int Cg = 0, Cg_pad = 0;  // PACK_SHUF2
   void* tmap = nullptr;    // host CUtensorMap (128 B), box = 64 k x BN rows (one-CTA kernel)
   void* tmap_half = nullptr;  // box = 64 k x BN/2 rows (CTA-pair kernel: each CTA loads half of W)
-  void* tmap_s3 = nullptr;    // box = 32 k x BN/2 rows x 3 planes, SWIZZLE_64B (gemm_s3.cu)
+  void* tmap_s3 = nullptr;    // box = 32 k x BN/2 rows x 2 planes (gemm_s3.cu)
   void* tmap_s3_hi = nullptr; // same with the hi plane only (single-term products)
 };
 void pack_gemm_weight(const float* w_oihw, int cout, int cin, int kh, int kw, const GemmW& g,
@@ -64,11 +64,11 @@ int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int 
 const char* umma_last_error();
 
 // Specialised CTA-pair kernel with a TMA epilogue (gemm_s3.cu): S3 out, plain / chunk-add-pair column
-// layouts, <= 1 residual, 6-term product.  gemm_s3_supports() says whether a launch qualifies.
+// layouts, <= 1 residual, 3-term split-fp16 product.  gemm_s3_supports() says whether a launch qualifies.
 int make_tmap_s3_act(void* tmap_out, View a, long long M, int planes);     // box 32 x 128 x planes
 int make_tmap_s3_act64(void* tmap_out, View a, long long M);               // box 32 x 64 x 1
 int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes);       // box 32 x BN/2 x planes
-int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M);      // box 16 x 32 x 3
+int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M);      // box 16 x 32 x 2 planes
 int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M);   // fp32 rows, box 16 x 32
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit);
 void gemm_s3_set_debug(int mask);

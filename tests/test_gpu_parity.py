@@ -69,19 +69,19 @@ def test_conv2d_matches_torch_fp32(cfg, backend):
     b = torch.randn(cout, generator=g)
     ref = _act(F.conv2d(x, w, b, stride=s, padding=p), act)
     out = op_conv2d(x, w, b, s, p, 1, act, 3, BACKENDS[backend])
-    # fp32-grade contraction (6-term bf16 split or fp32 FMA): error ~ sqrt(K) * 2^-24 of the scale
+    # fp32-grade contraction (3-term split-fp16 product or fp32 FMA): error ~ sqrt(K) * 2^-23 of the scale
     tol = 2e-5 * float(ref.abs().max())
     assert float((out - ref).abs().max()) <= tol
 
 
-def test_conv2d_single_bf16_term_is_bf16_accurate():
+def test_conv2d_single_term_is_fp16_accurate():
     g = torch.Generator().manual_seed(1)
     x = torch.randn(1, 256, 16, 24, generator=g)
     w = torch.randn(256, 256, 1, 1, generator=g) / 16
     ref = F.conv2d(x, w, None)
     out = op_conv2d(x, w, None, nsplit=1, backend=0)
     err = float((out - ref).abs().max())
-    assert 1e-5 < err <= 3e-2 * float(ref.abs().max())      # bf16 operands: ~2^-8 relative, and NOT fp32-exact
+    assert 1e-5 < err <= 4e-3 * float(ref.abs().max())      # fp16 hi planes only: ~2^-11 relative, and NOT fp32-exact
 
 
 def test_depthwise_matches_torch_fp32():
@@ -172,7 +172,15 @@ def test_gaussian_bits_match_oracle(formula):
 # ----------------------------------------------------------------------------------------------
 # whole frames
 # ----------------------------------------------------------------------------------------------
-def _run_case(variant, case, flags, record_taps=()):
+def _to_cuda(dpb):
+    return {k: (v.cuda() if v is not None else None) for k, v in dpb.items()}
+
+
+def _run_case(variant, case, flags, record_taps=(), resync=True):
+    """A GOP through the oracle and through the CUDA path.  The CUDA path runs on its OWN dpb (free-running,
+    like the reference's validation loop) as long as its symbols are identical to the oracle's; a frame with
+    a flipped symbol (allowed by the 99.99 % gate) perturbs the decoded feature around it, so after such a
+    frame the next call gets the oracle's dpb again: every call is judged on identical inputs."""
     frames, masks = gc.case_inputs(case)
     mi, mp = seeded_models(variant, case)
     sd_i, sd_p = sd_of(mi), sd_of(mp)
@@ -181,10 +189,14 @@ def _run_case(variant, case, flags, record_taps=()):
     fr, mk = frames.cuda(), masks.cuda()
     report = []
     with torch.no_grad():
-        o_i = O.dmci_forward(sd_i, frames[:, 0], case["qp"])
+        ti = {}
+        o_i = O.dmci_forward(sd_i, frames[:, 0], case["qp"], ti)
         c_i = mi(fr[:, 0], case["qp"])
-        report.append(("intra", o_i, c_i, {}, {}, frames[:, 0], None))
+        taps_ci = {"y_q": mi.get_tap("y_q", fr[:, 0]).cpu()} if "y_q" in record_taps else {}
+        report.append(("intra", o_i, c_i, ti if taps_ci else {}, taps_ci, frames[:, 0], None))
         dpb_o, dpb_c = o_i["dpb"], c_i["dpb"]
+        if resync and taps_ci and not torch.equal(taps_ci["y_q"], ti["y_q"]):
+            dpb_c = _to_cuda(dpb_o)
         for t in range(1, frames.shape[1]):
             qp = mp.shift_qp(case["qp"], O.INDEX_MAP[t % 8])
             if variant == "old":
@@ -197,10 +209,12 @@ def _run_case(variant, case, flags, record_taps=()):
             taps_c = {n: mp.get_tap(n, xc).cpu() for n in record_taps}
             report.append((f"P{t}", o, c, taps_o, taps_c, frames[:, t], masks[:, t]))
             dpb_o, dpb_c = o["dpb"], c["dpb"]
+            if resync and "y_q" in taps_c and not torch.equal(taps_c["y_q"], taps_o["y_q"]):
+                dpb_c = _to_cuda(dpb_o)
     return report
 
 
-def _assert_frame(tag, o, c, target, mask):
+def _assert_frame(tag, o, c, target, mask, exact_symbols=True):
     for k in ("bpp", "bpp_y", "bpp_z"):
         assert rel_err(c[k].cpu(), o[k]) <= BPP_REL_TOL, (tag, k, c[k].cpu(), o[k])
     xo, xc = o["dpb"]["frame"], c["dpb"]["frame"].cpu()
@@ -208,7 +222,8 @@ def _assert_frame(tag, o, c, target, mask):
     po, ro = gc.metrics(xo, target, mask)
     pc, rc = gc.metrics(xc, target, mask)
     assert abs(po - pc) <= PSNR_TOL_DB and abs(ro - rc) <= PSNR_TOL_DB, (tag, po, pc, ro, rc)
-    if o["dpb"].get("feature") is not None:
+    if o["dpb"].get("feature") is not None and exact_symbols:
+        # (a flipped symbol moves the decoded feature around it by ~1e-2: only frames without one are compared)
         fo, fc = o["dpb"]["feature"], c["dpb"]["feature"].cpu()
         assert float((fo - fc).abs().max()) <= 1e-3 * max(1.0, float(fo.abs().max())), tag
 
@@ -220,10 +235,12 @@ def test_gop_parity_with_oracle(variant, case, backend):
     flags = capi.FLAG_KEEP_TAPS | (capi.FLAG_SIMT_GEMM if backend == "simt" else 0)
     rep = _run_case(variant, case, flags, record_taps=("y_q", "z_hat", "scales_hat"))
     for tag, o, c, taps_o, taps_c, target, mask in rep:
-        _assert_frame(f"{variant}/{case['name']}/{backend}/{tag}", o, c, target, mask)
+        exact = not taps_c or torch.equal(taps_c["y_q"], taps_o["y_q"])
+        _assert_frame(f"{variant}/{case['name']}/{backend}/{tag}", o, c, target, mask, exact_symbols=exact)
         if taps_c:
             frac, bad = symbol_match(taps_c["y_q"], taps_o["y_q"])
             assert frac >= SYMBOL_MATCH_MIN, (tag, "y symbols", frac, bad)
+        if "z_hat" in taps_c:
             frac_z, bad_z = symbol_match(taps_c["z_hat"], taps_o["z_hat"])
             assert frac_z >= SYMBOL_MATCH_MIN, (tag, "z symbols", frac_z, bad_z)
         if "mask_pred" in o and o["mask_pred"] is not None:
@@ -298,8 +315,53 @@ def test_full_size_properties():
     assert abs(float(r1["bpp"] - r1b["bpp"])) <= 1e-6 * float(r1["bpp"])
 
 
+def test_full_size_parity_on_identical_inputs():
+    """1920x1280 (BASELINE.json config 2), `performance`: the intra frame and two P frames (after_i True / False)
+    against the oracle, EVERY call on identical inputs (the CUDA path gets the oracle's dpb).  This is the size
+    the gates are quoted on: >= 99.99 % symbols = at most 122 of 1 228 800 per P frame.  (Free-running, the
+    handful of intra-frame flips -- well inside the gate -- are amplified chaotically by the feature recurrence,
+    for the fp32-FMA backend as well: tools/symbol_counts.py)"""
+    H, W = 1280, 1920
+    frames, masks = D.clips.synthetic_clip(3, 1, 3, H, W)
+    torch.manual_seed(gc.SEED_I)
+    mi = D.DMCI().eval()
+    torch.manual_seed(gc.SEED_P)
+    mp = D.build_p_model("performance").eval()
+    sd_i, sd_p = sd_of(mi), sd_of(mp)
+    mi, mp = mi.cuda(), mp.cuda()
+    mi.engine_flags = mp.engine_flags = capi.FLAG_KEEP_TAPS
+    fr, mk = frames.cuda(), masks.cuda()
+    with torch.no_grad():
+        ti = {}
+        o = O.dmci_forward(sd_i, frames[:, 0], 32, ti)
+        c = mi(fr[:, 0], 32)
+        frac, bad = symbol_match(mi.get_tap("y_q", fr[:, 0]).cpu(), ti["y_q"])
+        assert frac >= SYMBOL_MATCH_MIN, ("intra", frac, bad)
+        assert rel_err(c["bpp"].cpu(), o["bpp"]) <= BPP_REL_TOL
+        po, _ = gc.metrics(o["dpb"]["frame"], frames[:, 0], None)
+        pc, _ = gc.metrics(c["dpb"]["frame"].cpu(), frames[:, 0], None)
+        assert abs(po - pc) <= PSNR_TOL_DB
+        dpb_o = o["dpb"]
+        for t in (1, 2):
+            qp = mp.shift_qp(32, O.INDEX_MAP[t % 8])
+            xo = torch.cat([frames[:, t], masks[:, t]], 1)
+            to = {}
+            o = O.dmc_forward(sd_p, "performance", xo, qp, dpb_o, after_i=(t == 1), taps=to)
+            c = mp(xo.cuda(), qp, _to_cuda(dpb_o), after_i=(t == 1))
+            frac, bad = symbol_match(mp.get_tap("y_q", xo.cuda()).cpu(), to["y_q"])
+            assert frac >= SYMBOL_MATCH_MIN, (t, "y symbols", frac, bad)
+            frac_z, bad_z = symbol_match(mp.get_tap("z_hat", xo.cuda()).cpu(), to["z_hat"])
+            assert frac_z >= SYMBOL_MATCH_MIN, (t, "z symbols", frac_z, bad_z)
+            for k in ("bpp", "bpp_y", "bpp_z"):
+                assert rel_err(c[k].cpu(), o[k]) <= BPP_REL_TOL, (t, k)
+            po, ro = gc.metrics(o["dpb"]["frame"], frames[:, t], masks[:, t])
+            pc, rc = gc.metrics(c["dpb"]["frame"].cpu(), frames[:, t], masks[:, t])
+            assert abs(po - pc) <= PSNR_TOL_DB and abs(ro - rc) <= PSNR_TOL_DB, (t, po, pc, ro, rc)
+            dpb_o = o["dpb"]
+
+
 def test_recon_single_term_against_split_product():
-    """recon_generation_net runs with plain bf16 operands by default (x_hat of a P frame feeds no later
+    """recon_generation_net runs with plain fp16 operands (hi planes only) by default (x_hat of a P frame feeds no later
     symbol).  Against the fp32-grade product everywhere: identical symbols / bpp / feature, PSNR within
     the 0.02 dB gate with a wide margin, and a small element-wise x_hat difference."""
     case = gc.case_by_name("anchor_256")
@@ -319,7 +381,7 @@ def test_recon_single_term_against_split_product():
     assert torch.equal(rd["bpp"], rs["bpp"])
     assert torch.equal(rd["dpb"]["feature"], rs["dpb"]["feature"])
     xd, xs = rd["dpb"]["frame"].cpu(), rs["dpb"]["frame"].cpu()
-    assert float((xd - xs).abs().max()) < 2e-2 and float((xd - xs).abs().mean()) < 2e-3
+    assert float((xd - xs).abs().max()) < 4e-3 and float((xd - xs).abs().mean()) < 4e-4
     pd, rod = gc.metrics(xd, frames[:, 1], masks[:, 1])
     ps, ros = gc.metrics(xs, frames[:, 1], masks[:, 1])
     assert abs(pd - ps) <= PSNR_TOL_DB / 4 and abs(rod - ros) <= PSNR_TOL_DB / 4
