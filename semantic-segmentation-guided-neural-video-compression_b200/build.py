@@ -29,6 +29,11 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def _extra_flags() -> list:
+    """DMC_NVCC_EXTRA="-DDMC_EPI_TIMING ..." adds flags (instrumented builds for tools/, never the default)."""
+    return os.environ.get("DMC_NVCC_EXTRA", "").split()
+
+
 def _stamp() -> str:
     h = hashlib.sha256()
     for name in sorted(os.listdir(CSRC)) + ["../../include/dmc_b200.h"]:
@@ -36,7 +41,7 @@ def _stamp() -> str:
         if os.path.isfile(path):
             h.update(name.encode())
             h.update(open(path, "rb").read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -52,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *_extra_flags(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -114,13 +114,14 @@ int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes) {
   }
   return 0;
 }
-// epilogue tiles (residual in / result out): box = 32 rows x 1 column block (16 columns) x 2 planes = two
-// contiguous 1 KB pieces; only the first `cols` columns of the view exist for the map
+// epilogue tiles (residual in / result out): box = 32 rows x 2 column blocks (32 columns) x 2 planes = four
+// contiguous 1 KB pieces; only the first `cols` columns of the view exist for the map (a box that reaches past
+// them is clipped on store and zero-filled on load)
 int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M) {
   (void)M;
-  return s3_encode(tmap_out, v, cols, 32, 1, kPlanes);
+  return s3_encode(tmap_out, v, cols, 32, 2, kPlanes);
 }
-// fp32 result rows [M, ld]: 2-D map, box = 16 columns x 32 rows, SWIZZLE_64B
+// fp32 result rows [M, ld]: 2-D map, box = 32 columns x 32 rows, SWIZZLE_128B
 int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M) {
   auto fn = s3_get_encode();
   if (!fn) {
@@ -129,10 +130,10 @@ int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long 
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)M};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {16, 32};
+  cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn((CUtensorMap*)tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_s3_err, sizeof g_s3_err, "cuTensorMapEncodeTiled (fp32 rows) failed (%d): base=%p cols=%d ld=%d", (int)r,
@@ -320,6 +321,19 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -356,8 +370,6 @@ struct alignas(64) S3StageDev {
   int nterms;        // 3: fp32-grade split product (two accumulators), 1: hi*hi only
   uint32_t need;     // increments of done[l-1][row tile] per launch that complete layer l-1 for a row tile
   int publish;       // a later layer of the chain waits for this one: completed tiles are counted in done[l]
-  uint8_t* blob;     // probe switch 16 only: result buffer, written as contiguous 2 KB blobs (layout garbage)
-  long long blob_pad_;
 };
 struct S3ChainParams {
   S3StageDev st[kS3MaxStages];
@@ -374,15 +386,25 @@ struct S3ChainParams {
 
 constexpr int kS3BK = 32;
 constexpr int kS3APlane = 128 * kS3BK * 2;        // one plane of a 128 x 32 fp16 tile
-constexpr int kS3EpiWarps = 8;
-// warp group 0: TMA producer, MMA issuer, two spare warps (56 registers); warp groups 1-2: eight epilogue
-// warps (224 registers, setmaxnreg) -- the six inlined epilogue variants do not fit the 168 registers a
-// 384-thread CTA gets by default
+#ifndef DMC_S3_EPI_WARPS
+#define DMC_S3_EPI_WARPS 8
+#endif
+constexpr int kS3EpiWarps = DMC_S3_EPI_WARPS;     // 8 or 16
+constexpr int kS3Split = kS3EpiWarps / 4;         // warps per TMEM lane quadrant: they split the tile's columns
+// warp group 0: TMA producer, MMA issuer, two spare warps (56 registers); warp groups 1..: the epilogue warps
+// (setmaxnreg: 224 registers with eight of them; sixteen would get 112, which the inlined epilogue variants do not
+// fit -- ptxas spills ~2 KB per thread -- so the latency hiding comes from 32-column chunks instead).
 constexpr int kS3Threads = 128 + 32 * kS3EpiWarps;
-constexpr int kS3ChunkBytes = kPlanes * 32 * 32;  // [2 planes][32 rows][16 fp16]
+constexpr int kS3EpiRegs = kS3EpiWarps == 16 ? 112 : 224;
+// The epilogue works in chunks of 32 rows x 32 columns per warp (16-column chunks left the warp waiting on one
+// latency after the other: tcgen05.ld, bias loads, the shared-memory fence, the TMA issue -- 1 560 clocks per chunk
+// measured, 6 200 per tile against 3 900 for the MMAs).  Staging tile of a chunk: split planes
+// [2 planes][2 column blocks][32 rows][16 fp16], or fp32 rows [32 rows][32 fp32] in SWIZZLE_128B order.
+constexpr int kS3ChunkCols = 32;
+constexpr int kS3ChunkBytes = kPlanes * 32 * kS3ChunkCols * 2;
 constexpr int kS3Ring = 3;                        // staging tiles per epilogue warp (residual in -> result out)
 constexpr int kS3WarpSmem = kS3Ring * kS3ChunkBytes;
-constexpr int kS3BarBytes = 512;
+constexpr int kS3BarBytes = 1024;
 
 // Shared-memory descriptor (cute::UMMA::SmemDescriptor) of a K-major SWIZZLE_32B operand tile = rows of 16 fp16
 // (32 B), which is what the tile-blocked activations and weights are in shared memory: start>>4 [0,14) | LBO (unused)
@@ -413,26 +435,53 @@ __device__ __forceinline__ void st_release_cta_shared(uint32_t addr, uint32_t v)
 // ones (TMA loads / stores of the tensors the flag guards)
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
+#ifdef DMC_EPI_TIMING
+// phase clocks of epilogue warp 0 of CTA 0, summed over chunks: [0] ring-slot wait + residual prefetch + publish,
+// [1] accumulator loads (tcgen05.ld + bias), [2] combine / bias / activation, [3] residual wait + join,
+// [4] scale + split + st.shared + fence, [5] TMA store issue, [6] chunks, [7] wait for the accumulator (per tile)
+__device__ unsigned long long g_epi_t[8];
+#define EPI_T(i) do { if (x.timed) { const long long t_ = clock64(); x.tacc[i] += t_ - x.tlast; x.tlast = t_; } } while (0)
+#else
+#define EPI_T(i) do { } while (0)
+#endif
+
 // Per-warp epilogue state that lives across tiles and layers.
 struct EpiCtx {
+#ifdef DMC_EPI_TIMING
+  bool timed;
+  long long tlast;
+  long long tacc[8];
+#endif
   uint32_t ringBuf;          // this warp's staging ring
   uint32_t barRes;           // its kS3Ring residual barriers (8 B apart)
   uint32_t slot;             // ring position of the chunk being processed (advances with every stored chunk)
   uint32_t res_phase;        // bit s: parity the next residual wait on ring barrier s has to see
-  int lane, quad, half;
+  int lane, quad, part;      // part: which share of the tile's columns (0 .. kS3Split-1)
   uint32_t rank;
   bool epi_mem;
 };
 
-__device__ __forceinline__ int s3_nchunk(int kind, int BN, int half) {
-  if (kind == S3_PAIR) return (half * 64 < BN) ? 2 : 0;   // one 64-column group (32 values + 32 partners) per warp
-  return BN >> 5;
+// A tile has BN/32 output chunks of 32 columns (PAIR: BN/64 -- a 64-column group of accumulators = 32 values + their
+// 32 chunk-add partners gives one output chunk).  The warps of a quadrant take contiguous shares of `per` chunks.
+__device__ __forceinline__ int s3_per(int kind, int BN) {
+  const int total = kind == S3_PAIR ? BN >> 6 : BN >> 5;
+  return (total + kS3Split - 1) / kS3Split;
+}
+__device__ __forceinline__ int s3_nchunk(int kind, int BN, int part) {
+  const int total = kind == S3_PAIR ? BN >> 6 : BN >> 5;
+  const int per = s3_per(kind, BN);
+  return max(0, min(per, total - part * per));
+}
+// accumulator column (PAIR: of the value half; partners sit 32 columns further) of this warp's chunk c
+__device__ __forceinline__ int s3_acc_col(int kind, int BN, int part, int c) {
+  const int j = part * s3_per(kind, BN) + c;
+  return kind == S3_PAIR ? j * 64 : j * 32;
 }
 // destination column of chunk c of N tile nt for this warp
-__device__ __forceinline__ int s3_dest_col(int kind, int BN, int half, int nt, int c) {
+__device__ __forceinline__ int s3_dest_col(int kind, int BN, int part, int nt, int c) {
   const int n_idx = nt * BN;
-  if (kind == S3_PAIR) return ((n_idx >> 6) + half) * 32 + 16 * c;
-  return n_idx + half * (BN >> 1) + 16 * c;
+  const int j = part * s3_per(kind, BN) + c;
+  return (kind == S3_PAIR ? (n_idx >> 1) : n_idx) + j * 32;
 }
 
 // One tile of one layer, one epilogue warp.  `next_res(c)` is called once per chunk (after the staging
@@ -441,7 +490,6 @@ __device__ __forceinline__ int s3_dest_col(int kind, int BN, int half, int nt, i
 // The fields of a layer the epilogue needs, read ONCE per tile into registers (the layer record sits in the
 // kernel parameters under a run-time index: every access is an indexed constant load).
 struct StageRegs {
-  uint8_t* blob;
   const float* bias;
   const float* scale;
   const CUtensorMap* tmOut;
@@ -452,100 +500,107 @@ struct StageRegs {
 };
 __device__ __forceinline__ StageRegs s3_load_stage(const S3StageDev& S) {
   StageRegs r;
-  r.blob = S.blob; r.bias = S.bias; r.scale = S.scale; r.tmOut = &S.tmOut; r.tmRes = &S.tmRes;
+  r.bias = S.bias; r.scale = S.scale; r.tmOut = &S.tmOut; r.tmRes = &S.tmRes;
   r.BN = S.BN; r.n_out = S.n_out; r.kind = S.kind; r.need = S.need; r.two_acc = S.nterms != 1;
   return r;
 }
 
-template <int kAct, int kPack, int kRes, int kF32, class NextRes, class Release>
+// One body for all layer kinds (warp-uniform run-time branches, taken once per 32-column chunk): six inlined
+// template instances of it made ptxas spill ~5 KB per thread, each instance alone compiles without a spill.
+template <class NextRes, class Release>
 __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, int mt, int nt, uint32_t taddr,
                                                  int* err, NextRes next_res, Release release_tmem) {
   using namespace s3;
   const int lane = x.lane;
-  const int nchunk = s3_nchunk(kPack == PACK_PAIR ? S3_PAIR : S3_PLAIN, S.BN, x.half);
-  const int acc0 = (kPack == PACK_PAIR) ? x.half * 64 : x.half * (S.BN >> 1);
+  const bool kF32 = S.kind == S3_F32 || S.kind == S3_F32_WSILU;
+  const bool kRes = S.kind == S3_RES;
+  const bool kWsilu = S.kind == S3_WSILU || S.kind == S3_PAIR || S.kind == S3_F32_WSILU;
+  const bool kPair = S.kind == S3_PAIR;
+  const int kKind = kPair ? S3_PAIR : S3_PLAIN;
+  const int nchunk = s3_nchunk(kKind, S.BN, x.part);
   const int n_idx = nt * S.BN;
   const int row0 = mt * 256 + (int)x.rank * 128 + x.quad * 32;
   const uint32_t swz = (uint32_t)((lane >> 2) & 1) << 4;        // SWIZZLE_32B: 16-byte unit ^= row bit 2
   const uint32_t rowOff = (uint32_t)lane * 32u;
   const bool two_acc = S.two_acc;
   for (int c = 0; c < nchunk; ++c) {
-    const int acol = acc0 + 16 * c;                     // accumulator column of this chunk
-    const int dcol = s3_dest_col(kPack == PACK_PAIR ? S3_PAIR : S3_PLAIN, S.BN, x.half, nt, c);
-    const bool valid = dcol < S.n_out;                  // warp-uniform
+    const int acol = s3_acc_col(kKind, S.BN, x.part, c);         // accumulator column of this chunk
+    const int dcol = s3_dest_col(kKind, S.BN, x.part, nt, c);
+    const bool valid = dcol < S.n_out;                           // warp-uniform
+    EPI_T(7);
     // The staging tile two chunks back must have been read by its TMA store before it is reused
     // (by the residual load issued next, or by this chunk's own result when there is no residual).
     if (lane == 0) tma_store_wait_read1();
     __syncwarp();
     next_res(c);
-    float v[16];
+    EPI_T(0);
+    float v[32];
     if (valid) {
-      uint32_t a[16], b[16];
-      tc_ld16(taddr + acol, a);
-      if (two_acc) tc_ld16(taddr + 128u + acol, b);
-      const float4* bp = reinterpret_cast<const float4*>(S.bias + n_idx + acol);
-      float bias[16];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 q = __ldg(bp + i);
-        bias[4 * i] = q.x; bias[4 * i + 1] = q.y; bias[4 * i + 2] = q.z; bias[4 * i + 3] = q.w;
-      }
-      tc_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float t = __uint_as_float(a[i]);
-        if (two_acc) t = fmaf(__uint_as_float(b[i]), kLoInv, t);
-        t = add_rn(t, bias[i]);
-        if (kAct == ACT_WSILU) t = wsilu_fast(t);
-        v[i] = t;
-      }
-      if (kPack == PACK_PAIR) {
-        tc_ld16(taddr + acol + 32, a);
-        if (two_acc) tc_ld16(taddr + 128u + acol + 32, b);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 q = __ldg(bp + 8 + i);
-          bias[4 * i] = q.x; bias[4 * i + 1] = q.y; bias[4 * i + 2] = q.z; bias[4 * i + 3] = q.w;
-        }
+      // v (+)= act(main + small * 2^-11 + bias) for accumulator columns [col, col + 32)
+      auto load_act = [&](int col, bool accumulate) {
+        uint32_t a[32], b[32];
+        float w[32];
+        tc_ld32(taddr + col, a);
+        if (two_acc) tc_ld32(taddr + 128u + col, b);
         tc_wait_ld();
+        EPI_T(1);
+        const float4* bp = reinterpret_cast<const float4*>(S.bias + n_idx + col);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float t = __uint_as_float(a[i]);
-          if (two_acc) t = fmaf(__uint_as_float(b[i]), kLoInv, t);
-          t = add_rn(t, bias[i]);
-          if (kAct == ACT_WSILU) t = wsilu_fast(t);
-          v[i] = add_rn(v[i], t);
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = __ldg(bp + i);
+          const float bias4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float t = __uint_as_float(a[4 * i + k]);
+            if (two_acc) t = fmaf(__uint_as_float(b[4 * i + k]), kLoInv, t);     // main + small * 2^-11, one rounding
+            w[4 * i + k] = add_rn(t, bias4[k]);
+          }
         }
-      }
+        if (kWsilu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = wsilu_fast(w[i]);
+        }
+        if (accumulate) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = add_rn(v[i], w[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = w[i];
+        }
+      };
+      load_act(acol, false);
+      if (kPair) load_act(acol + 32, true);
     }
     if (c == nchunk - 1) release_tmem();      // accumulator fully read: hand the TMEM buffer back
+    EPI_T(2);
     if (!valid) continue;
     const uint32_t tileBuf = x.ringBuf + x.slot * kS3ChunkBytes;
     if (kRes && x.epi_mem) {
       mbar_wait(x.barRes + 8u * x.slot, (x.res_phase >> x.slot) & 1u, err, 5);
       x.res_phase ^= 1u << x.slot;
       const uint32_t src = tileBuf + rowOff;
-      float t[16];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {     // hi + lo * 2^-11, exactly join2
-        const uint4 qh = ld_shared_v4(src + (((uint32_t)hf << 4) ^ swz));
-        const uint4 ql = ld_shared_v4(src + 1024 + (((uint32_t)hf << 4) ^ swz));
-        const uint32_t uh[4] = {qh.x, qh.y, qh.z, qh.w};
-        const uint32_t ul[4] = {ql.x, ql.y, ql.z, ql.w};
+      for (int blk = 0; blk < 2; ++blk) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = 8 * hf + 2 * k;
-          t[i] = join2(h2lo(uh[k]), h2lo(ul[k]));
-          t[i + 1] = join2(h2hi(uh[k]), h2hi(ul[k]));
+        for (int hf = 0; hf < 2; ++hf) {     // hi + lo * 2^-11, exactly join2
+          const uint4 qh = ld_shared_v4(src + blk * 1024 + (((uint32_t)hf << 4) ^ swz));
+          const uint4 ql = ld_shared_v4(src + 2048 + blk * 1024 + (((uint32_t)hf << 4) ^ swz));
+          const uint32_t uh[4] = {qh.x, qh.y, qh.z, qh.w};
+          const uint32_t ul[4] = {ql.x, ql.y, ql.z, ql.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 16 * blk + 8 * hf + 2 * k;
+            v[i] = add_rn(v[i], join2(h2lo(uh[k]), h2lo(ul[k])));
+            v[i + 1] = add_rn(v[i + 1], join2(h2hi(uh[k]), h2hi(ul[k])));
+          }
         }
       }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = add_rn(v[i], t[i]);
     }
+    EPI_T(3);
     if (S.scale) {
       const float4* sp = reinterpret_cast<const float4*>(S.scale + dcol);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         float4 q = make_float4(1.f, 1.f, 1.f, 1.f);
         if (dcol + 4 * i < S.n_out) q = __ldg(sp + i);
         v[4 * i] = mul_rn(v[4 * i], q.x); v[4 * i + 1] = mul_rn(v[4 * i + 1], q.y);
@@ -553,40 +608,40 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
       }
     }
     if (kF32) {
-      // fp32 rows: 64 B per lane, 16-byte unit u of row r sits at u ^ ((r >> 1) & 3)  (SWIZZLE_64B)
-      const uint32_t dst = tileBuf + (uint32_t)lane * 64u;
-      const uint32_t sw64 = (uint32_t)((lane >> 1) & 3) << 4;
+      // fp32 rows: 128 B per lane, 16-byte unit u of row r sits at u ^ (r & 7)  (SWIZZLE_128B)
+      const uint32_t dst = tileBuf + (uint32_t)lane * 128u;
+      const uint32_t sw128 = (uint32_t)(lane & 7) << 4;
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        st_shared_v4(dst + (((uint32_t)u << 4) ^ sw64), __float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
+      for (int u = 0; u < 8; ++u)
+        st_shared_v4(dst + (((uint32_t)u << 4) ^ sw128), __float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
                      __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
       fence_async_smem();
       __syncwarp();
+      EPI_T(4);
       if (lane == 0 && x.epi_mem) tma_store_2d(S.tmOut, tileBuf, dcol, row0);
     } else {
       // hi / 2^11-scaled lo split, two elements per conversion
-      uint32_t ph_[8], pl_[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) split2x2(v[2 * i], v[2 * i + 1], ph_[i], pl_[i]);
       const uint32_t dst = tileBuf + rowOff;
-      st_shared_v4(dst + swz, ph_[0], ph_[1], ph_[2], ph_[3]);
-      st_shared_v4(dst + (16u ^ swz), ph_[4], ph_[5], ph_[6], ph_[7]);
-      st_shared_v4(dst + 1024 + swz, pl_[0], pl_[1], pl_[2], pl_[3]);
-      st_shared_v4(dst + 1024 + (16u ^ swz), pl_[4], pl_[5], pl_[6], pl_[7]);
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        uint32_t ph_[8], pl_[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split2x2(v[16 * blk + 2 * i], v[16 * blk + 2 * i + 1], ph_[i], pl_[i]);
+        st_shared_v4(dst + blk * 1024 + swz, ph_[0], ph_[1], ph_[2], ph_[3]);
+        st_shared_v4(dst + blk * 1024 + (16u ^ swz), ph_[4], ph_[5], ph_[6], ph_[7]);
+        st_shared_v4(dst + 2048 + blk * 1024 + swz, pl_[0], pl_[1], pl_[2], pl_[3]);
+        st_shared_v4(dst + 2048 + blk * 1024 + (16u ^ swz), pl_[4], pl_[5], pl_[6], pl_[7]);
+      }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0 && x.epi_mem) {
-        if (S.blob) {          // probe: same bytes, one contiguous 2 KB bulk copy
-          uint8_t* g = S.blob + ((size_t)(row0 >> 5) * (size_t)(S.n_out >> 4) + (size_t)(dcol >> 4)) * kS3ChunkBytes;
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(tileBuf),
-                       "r"((uint32_t)kS3ChunkBytes) : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        } else {
-          tma_store(S.tmOut, tileBuf, dcol, row0);
-        }
-      }
+      EPI_T(4);
+      if (lane == 0 && x.epi_mem) tma_store(S.tmOut, tileBuf, dcol, row0);
     }
     if (++x.slot == kS3Ring) x.slot = 0;
+    EPI_T(5);
+#ifdef DMC_EPI_TIMING
+    x.tacc[6] += 1;
+#endif
   }
 }
 
@@ -612,9 +667,9 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   auto bar_tfull = [&](int b) { return barBase + 128u + 8u * b; };
   auto bar_tempty = [&](int b) { return barBase + 144u + 8u * b; };
   auto bar_res = [&](int w, int b) { return barBase + 160u + 32u * w + 8u * b; };
-  const uint32_t tmemSlot = barBase + 416u;
-  const uint32_t depsOk = barBase + 420u;            // number of this CTA's tiles whose dependencies are met
-  const uint32_t warpsDone = barBase + 424u;         // [4] epilogue warps of this CTA that finished tile (t & 3)
+  const uint32_t tmemSlot = barBase + 160u + 32u * kS3EpiWarps;
+  const uint32_t depsOk = tmemSlot + 4u;             // number of this CTA's tiles whose dependencies are met
+  const uint32_t warpsDone = tmemSlot + 8u;          // [4] epilogue warps of this CTA that finished tile (t & 3)
 
   if (warp == 0 && lane == 0) {
     if (base & 1023u) {
@@ -765,7 +820,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   }
   } else {
     // ------------------------------------------------------------ epilogue warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kS3EpiRegs) : "memory");
     const int ew = warp - 4;
     EpiCtx x;
     x.ringBuf = epiBase + (uint32_t)ew * kS3WarpSmem;
@@ -773,9 +828,14 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     x.slot = 0; x.res_phase = 0;
     x.lane = lane;
     x.quad = warp & 3;                         // TMEM lane quadrant this warp may read
-    x.half = ew >> 2;                          // two warps per quadrant split the columns
+    x.part = ew >> 2;                          // the warps of a quadrant split the columns
     x.rank = rank;
     x.epi_mem = !(p.dbg & 12);
+#ifdef DMC_EPI_TIMING
+    x.timed = blockIdx.x == 0 && ew == 0;
+    x.tlast = clock64();
+    for (int i = 0; i < 8; ++i) x.tacc[i] = 0;
+#endif
 
     // Residual prefetch of chunk c2 of this CTA's tile number t2 (table entry e2); whole warp, lane 0 issues.
     // The first chunk of a NEW tile is only prefetched if the producer warp has already seen that tile's
@@ -793,7 +853,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         if (R2.need != 0u) fence_proxy_async_global();
         res_tile = t2;
       }
-      const int dcol = s3_dest_col(S3_PLAIN, R2.BN, x.half, nt2, c2);
+      const int dcol = s3_dest_col(S3_PLAIN, R2.BN, x.part, nt2, c2);
       if (dcol >= R2.n_out) return;
       if (lane == 0) {
         const uint32_t bar = x.barRes + 8u * slot2;
@@ -827,7 +887,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       const int nt = p.cl4 ? 2 * (int)((e >> 20) & 0xffu) + (int)pairIdx : (int)((e >> 20) & 0xffu);
       if (l != l_cached) { S = s3_load_stage(p.st[l]); l_cached = l; }
       const uint32_t buf = tcount & 1;
-      const int nchunk = s3_nchunk(S.kind, S.BN, x.half);
+      const int nchunk = s3_nchunk(S.kind, S.BN, x.part);
       // the first residual of the next tile is prefetched early only within a layer (same cached fields);
       // across a layer boundary it is issued when that tile starts
       bool has_next = ei + units < p.n_entries;
@@ -854,7 +914,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
           else mbar_arrive_cluster(mapa(bar_tempty(buf), leaderRank));
         }
       };
-      const bool stored0 = x.epi_mem && s3_dest_col(S.kind, S.BN, x.half, nt, 0) < S.n_out;
+      const bool stored0 = x.epi_mem && s3_dest_col(S.kind, S.BN, x.part, nt, 0) < S.n_out;
       auto next_res = [&](int c) {
         if (c == 1 && pending) {               // only chunk 0's store (if any) is newer than the previous tile's
           if (lane == 0) {
@@ -864,7 +924,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
           pending = false;
         }
         // the item after chunk c lands one ring tile further if chunk c itself stores something
-        const bool valid_c = s3_dest_col(S.kind, S.BN, x.half, nt, c) < S.n_out;
+        const bool valid_c = s3_dest_col(S.kind, S.BN, x.part, nt, c) < S.n_out;
         uint32_t slot2 = x.slot + (valid_c ? 1u : 0u);
         if (slot2 == kS3Ring) slot2 = 0;
         if (c + 1 < nchunk) issue_res(S, e, c + 1, tcount, false, slot2);
@@ -873,14 +933,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       if (nchunk == 0 || (p.dbg & 8)) {
         release_tmem();
       } else {
-        switch (S.kind) {
-          case S3_PLAIN: s3_epilogue_tile<ACT_NONE, PACK_PLAIN, 0, 0>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
-          case S3_WSILU: s3_epilogue_tile<ACT_WSILU, PACK_PLAIN, 0, 0>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
-          case S3_RES: s3_epilogue_tile<ACT_NONE, PACK_PLAIN, 1, 0>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
-          case S3_PAIR: s3_epilogue_tile<ACT_WSILU, PACK_PAIR, 0, 0>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
-          case S3_F32: s3_epilogue_tile<ACT_NONE, PACK_PLAIN, 0, 1>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
-          default: s3_epilogue_tile<ACT_WSILU, PACK_PLAIN, 0, 1>(S, x, mt, nt, taddr, p.err, next_res, release_tmem); break;
-        }
+        s3_epilogue_tile(S, x, mt, nt, taddr, p.err, next_res, release_tmem);
       }
       if (pending) {                           // (tiles in which this warp has fewer than two chunks)
         if (lane == 0) { tma_store_wait_all(); publish(); }
@@ -891,6 +944,11 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     }
     if (pending && lane == 0) { tma_store_wait_all(); publish(); }
     if (lane == 0) tma_store_wait_all();
+#ifdef DMC_EPI_TIMING
+    if (x.timed && lane == 0) {
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_epi_t[i], (unsigned long long)x.tacc[i]);
+    }
+#endif
   }
 
   tc_fence_before();
@@ -908,7 +966,7 @@ void gemm_s3_set_debug(int mask) { g_s3_dbg = mask; }
 
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit) {
   if (!w.tmap_s3 || !w.tmap_s3_hi || e.do_clamp || e.res2.p) return false;
-  if (w.BN % 32 || w.BN > 128 || e.n_out % 16) return false;
+  if (w.BN % 32 || w.BN > 128 || e.n_out % 16 || e.n_out < 32) return false;
   if (e.out_f32) {                       // fp32 rows: plain layout, no residual, and not both outputs at once
     return !e.out.p && e.pack == PACK_PLAIN && !e.res1.p && (e.act == ACT_NONE || e.act == ACT_WSILU) &&
            e.ld_f32 % 4 == 0 && (uintptr_t)e.out_f32 % 16 == 0;
@@ -1010,7 +1068,6 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     memcpy(&S.tmRes, d.tmRes ? d.tmRes : d.tmOut, sizeof(CUtensorMap));
     S.bias = d.e.bias;
     S.scale = d.e.scale;
-    S.blob = (g_s3_dbg & 16) && d.e.out.p && !d.e.out_f32 ? (uint8_t*)d.e.out.p : nullptr;
     S.k_blocks = (d.K + kS3BK - 1) / kS3BK;
     S.BN = d.w->BN;
     S.n_tiles = (d.w->ncols + d.w->BN - 1) / d.w->BN;
@@ -1119,3 +1176,14 @@ int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
 }
 
 }  // namespace dmc
+
+#ifdef DMC_EPI_TIMING
+extern "C" __attribute__((visibility("default"))) int dmc_debug_epi_timing(unsigned long long* out8, int reset) {
+  if (out8) cudaMemcpyFromSymbol(out8, dmc::g_epi_t, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(dmc::g_epi_t, z, sizeof z);
+  }
+  return 0;
+}
+#endif
