@@ -5,6 +5,7 @@
 #include "kernels.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace dmc {
 
@@ -251,19 +252,25 @@ void finite_check(View v, long long M, int* flag, cudaStream_t st) {
 // fmaf(0, w, acc) == acc, so the result does not depend on the blocking.
 constexpr int kDwPix = 4;
 // kF32In: the input is fp32 rows [M, ld] (no S3 join: the producing contraction writes fp32 for this consumer)
+// A CTA covers kDwTR image rows x kDwTP pixel groups (x all channels): its (kDwTR + 2) x (4 kDwTP + 2) input pixels
+// are fetched from L2 once and the 3 x 3 reuse is served by L1 (one image row per CTA fetched every input row three
+// times: 3.4x the unique bytes over L2).
+constexpr int kDwTP = 2;
 template <bool kF32In>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 k_dwconv3x3(View in, const float* __restrict__ in32, int ld32, const float* __restrict__ w9c,
-            const float* __restrict__ bias, View out, int B, int H, int W, int C8, int WG) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * H * WG * C8;
-  if (idx >= total) return;
-  const int cg = (int)(idx % C8);
-  long long t = idx / C8;
-  const int wg = (int)(t % WG);
-  t /= WG;
-  const int h = (int)(t % H);
-  const long long b = t / H;
+            const float* __restrict__ bias, View out, int B, int H, int W, int C8, int WG, int TR) {
+  const int cg = (int)threadIdx.x % C8;
+  const int pos = (int)threadIdx.x / C8;
+  const int WT = (WG + kDwTP - 1) / kDwTP, HT = (H + TR - 1) / TR;
+  long long t = blockIdx.x;
+  const int wt = (int)(t % WT);
+  t /= WT;
+  const int ht = (int)(t % HT);
+  const long long b = t / HT;
+  const int wg = wt * kDwTP + pos % kDwTP;
+  const int h = ht * TR + pos / kDwTP;
+  if (h >= H || wg >= WG || pos >= TR * kDwTP) return;
   const int c = cg * 8, C = C8 * 8;
   const int w0 = wg * kDwPix;
   float acc[kDwPix][8];
@@ -320,14 +327,34 @@ k_dwconv3x3(View in, const float* __restrict__ in32, int ld32, const float* __re
     st3x8(out, (b * H + h) * W + w0 + p, c, o);
   }
 }
+// rows per CTA tile: as many as keep the CTA at <= 512 threads (C8 * kDwTP threads per row), at most 8
+static int dw_tile_rows(int C8) {
+  static int cap = 0;
+  if (!cap) {
+    const char* v = getenv("DMC_DW_TR");       // experiments: rows per CTA tile
+    cap = v ? atoi(v) : 2;
+    if (cap < 1) cap = 1;
+  }
+  int tr = 512 / (C8 * kDwTP);
+  if (tr > cap) tr = cap;
+  if (tr < 1) tr = 1;
+  return tr;
+}
+static unsigned dw_grid(int B, int H, int WG, int TR) {
+  return (unsigned)((long long)B * ((H + TR - 1) / TR) * ((WG + kDwTP - 1) / kDwTP));
+}
 void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, int H, int W,
                cudaStream_t st) {
   const int C8 = in.C / 8;
   const int WG = (W + kDwPix - 1) / kDwPix;
-  const long long n = (long long)B * H * WG * C8;
+  const int TR = dw_tile_rows(C8);
   note_launch();
-  k_dwconv3x3<false><<<cdiv(n, 128), 128, 0, st>>>(in, nullptr, 0, w9c, bias, out, B, H, W, C8, WG);
+  k_dwconv3x3<false><<<dw_grid(B, H, WG, TR), C8 * kDwTP * TR, 0, st>>>(in, nullptr, 0, w9c, bias, out, B, H, W, C8, WG, TR);
 }
+// (Tried and dropped: the same taps from a shared-memory tile filled by cp.async.bulk -- (4 + 2) row segments of
+// 10 pixels x C floats on one mbarrier, 2 CTAs of 256 threads per SM: 35 us against 29 us at 160x240x256.  ncu on
+// the register version: issue slots 40 % busy, L1 64 %, DRAM 2.6 TB/s -- it is bound by L1 transactions and
+// instruction count, not by latency.  CTA tiles of 2-8 image rows x 8 pixels instead of one row change nothing.)
 // (A mapping with one thread per 16-channel block and consecutive threads along the image row makes the blocked
 // stores contiguous but the fp32 reads strided by a whole pixel: 78 us instead of 33 us at 160x240x256.  The
 // channel-fastest mapping below keeps every 16-byte store inside a fully written 32-byte sector.)
@@ -335,9 +362,9 @@ void dwconv3x3_f32(const float* in, int ld, const float* w9c, const float* bias,
                    cudaStream_t st) {
   const int C8 = out.C / 8;
   const int WG = (W + kDwPix - 1) / kDwPix;
-  const long long n = (long long)B * H * WG * C8;
+  const int TR = dw_tile_rows(C8);
   note_launch();
-  k_dwconv3x3<true><<<cdiv(n, 128), 128, 0, st>>>(out, in, ld, w9c, bias, out, B, H, W, C8, WG);
+  k_dwconv3x3<true><<<dw_grid(B, H, WG, TR), C8 * kDwTP * TR, 0, st>>>(out, in, ld, w9c, bias, out, B, H, W, C8, WG, TR);
 }
 
 // ------------------------------------------------------------------ im2col (k x k, stride, pad)
