@@ -37,7 +37,8 @@ namespace dmc {
 static char g_s3_err[512] = "";
 const char* gemm_s3_last_error() { return g_s3_err; }
 // 0, or which bounded wait of the chain kernel timed out before it trapped: 1 operand ring slot, 2 TMEM buffer,
-// 3 operand bytes, 4 accumulator, 5 residual tile, 6 previous layer's row tile (global counter), 9 smem alignment
+// 3 operand bytes, 4 accumulator, 5 residual tile, 6 previous layer's row tile (global counter), 7 publisher waiting for the
+// epilogue warps, 9 smem alignment
 static volatile int* g_s3_trap = nullptr;
 int gemm_s3_trap_code() { return g_s3_trap ? *g_s3_trap : 0; }
 
@@ -249,6 +250,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_wait_read0() {   // every bulk store has read its shared memory
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_read1() {   // at most one store still reading shared memory
   asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
@@ -418,7 +422,14 @@ constexpr int kS3EpiRegs = kS3EpiWarps == 16 ? 112 : 224;
 // [2 planes][2 column blocks][32 rows][16 fp16], or fp32 rows [32 rows][32 fp32] in SWIZZLE_128B order.
 constexpr int kS3ChunkCols = 32;
 constexpr int kS3ChunkBytes = kPlanes * 32 * kS3ChunkCols * 2;
-constexpr int kS3Ring = 3;                        // staging tiles per epilogue warp (residual in -> result out)
+#ifndef DMC_S3_RING
+#define DMC_S3_RING 2
+#endif
+// Staging tiles per epilogue warp (residual in -> result out).  Two: the residual of chunk c+1 is prefetched into the
+// tile chunk c-1 was stored from -- that store (issued a whole chunk earlier) has read its data long before, the wait
+// for it is a formality -- and the 32 KB a third tile per warp would take go to the operand ring, whose bytes in
+// flight are what bounds the operand supply (5 stages = 120 KB per CTA at ~4 000 clocks of loaded L2 latency).
+constexpr int kS3Ring = DMC_S3_RING;
 constexpr int kS3WarpSmem = kS3Ring * kS3ChunkBytes;
 constexpr int kS3BarBytes = 1024;
 
@@ -456,15 +467,32 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // [1] accumulator loads (tcgen05.ld + bias), [2] combine / bias / activation, [3] residual wait + join,
 // [4] scale + split + st.shared + fence, [5] TMA store issue, [6] chunks, [7] wait for the accumulator (per tile)
 __device__ unsigned long long g_epi_t[8];
-#define EPI_T(i) do { if (x.timed) { const long long t_ = clock64(); x.tacc[i] += t_ - x.tlast; x.tlast = t_; } } while (0)
+// tile timeline of cluster 0 (CTA 0): per tile [0] MMA warp starts waiting for the TMEM buffer, [1] has it,
+// [2] first operand stage arrived, [3] last MMA issued, [4] epilogue warp 0 starts waiting for the accumulator,
+// [5] has it, [6] done with the tile, [7] table entry
+__device__ unsigned long long g_tile_trace[256][8];
+// [CTA 0/1][epilogue warp 0 / 7][tile][got accumulator, released TMEM, done]
+__device__ unsigned long long g_warp_trace[2][2][256][3];
+#define WARP_T(t, i) do { if (blockIdx.x < 2 && x.lane == 0 && (x.ew == 0 || x.ew == 7) && (t) < 256u) \
+  g_warp_trace[blockIdx.x][x.ew == 7][(t)][(i)] = (unsigned long long)clock64(); } while (0)
+#define TILE_T(t, i, v) do { if (blockIdx.x == 0 && lane == 0 && (t) < 256u) g_tile_trace[(t)][(i)] = (unsigned long long)(v); } while (0)
+// (the phase clocks slow the timed warp by ~20 %: -DDMC_EPI_PHASES=0 keeps only the tile / warp traces)
+#ifndef DMC_EPI_PHASES
+#define DMC_EPI_PHASES 1
+#endif
+#define EPI_T(i) do { if (DMC_EPI_PHASES && x.timed) { const long long t_ = clock64(); x.tacc[i] += t_ - x.tlast; x.tlast = t_; } } while (0)
 #else
 #define EPI_T(i) do { } while (0)
+#define TILE_T(t, i, v) do { } while (0)
+#define WARP_T(t, i) do { } while (0)
 #endif
 
 // Per-warp epilogue state that lives across tiles and layers.
 struct EpiCtx {
 #ifdef DMC_EPI_TIMING
   bool timed;
+  int ew;
+  uint32_t tile;
   long long tlast;
   long long tacc[8];
 #endif
@@ -546,7 +574,9 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
     EPI_T(7);
     // The staging tile two chunks back must have been read by its TMA store before it is reused
     // (by the residual load issued next, or by this chunk's own result when there is no residual).
-    if (lane == 0) tma_store_wait_read1();
+    if (lane == 0) {
+      if (kS3Ring >= 3) tma_store_wait_read1(); else tma_store_wait_read0();
+    }
     __syncwarp();
     next_res(c);
     EPI_T(0);
@@ -587,7 +617,12 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
       load_act(acol, false);
       if (kPair) load_act(acol + 32, true);
     }
-    if (c == nchunk - 1) release_tmem();      // accumulator fully read: hand the TMEM buffer back
+    if (c == nchunk - 1) {
+      release_tmem();      // accumulator fully read: hand the TMEM buffer back
+#ifdef DMC_EPI_TIMING
+      WARP_T(x.tile, 1);
+#endif
+    }
     EPI_T(2);
     if (!valid) continue;
     const uint32_t tileBuf = x.ringBuf + x.slot * kS3ChunkBytes;
@@ -685,7 +720,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   auto bar_res = [&](int w, int b) { return barBase + 160u + 32u * w + 8u * b; };
   const uint32_t tmemSlot = barBase + 160u + 32u * kS3EpiWarps;
   const uint32_t depsOk = tmemSlot + 4u;             // number of this CTA's tiles whose dependencies are met
-  const uint32_t warpsDone = tmemSlot + 8u;          // [4] epilogue warps of this CTA that finished tile (t & 3)
+  const uint32_t warpsDone = tmemSlot + 8u;          // [8] epilogue warps of this CTA that finished tile (t & 7)
 
   if (warp == 0 && lane == 0) {
     if (base & 1023u) {
@@ -702,7 +737,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     for (int w = 0; w < kS3EpiWarps; ++w)
       for (int b = 0; b < kS3Ring; ++b) mbar_init(bar_res(w, b), 1);
     *reinterpret_cast<volatile uint32_t*>(smem_raw + (depsOk - base)) = 0u;
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<volatile uint32_t*>(smem_raw + (warpsDone - base) + 4 * i) = 0u;
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<volatile uint32_t*>(smem_raw + (warpsDone - base) + 4 * i) = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -799,12 +834,16 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         const int k_blocks = S.k_blocks;
         const bool split = S.nterms != 1;
         const uint32_t buf = tcount & 1;
+        TILE_T(tcount, 0, clock64());
+        TILE_T(tcount, 7, e);
         mbar_wait(bar_tempty(buf), ((tcount >> 1) & 1) ^ 1, p.err, 2);
+        TILE_T(tcount, 1, clock64());
         tc_fence_after();
         const uint32_t d_main = tmem_base + buf * 256u;
         const uint32_t d_small = d_main + 128u;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(bar_full(s), ph, p.err, 3);
+          if (kb == 0) TILE_T(tcount, 2, clock64());
           tc_fence_after();
           const uint32_t sa = base + s * stageBytes;
           const uint64_t da = s3_desc32(sa);
@@ -828,10 +867,39 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
             tc_commit_pair(bar_empty(s), clusterMask);
             if (kb == k_blocks - 1) tc_commit_pair(bar_tfull(buf), pairMask);
           }
+          if (kb == k_blocks - 1) TILE_T(tcount, 3, clock64());
           __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ publisher (both CTAs)
+    // Announces a finished tile to the layers that depend on it.  The epilogue warps only count themselves in
+    // (cta scope) once their stores of the tile are complete; the gpu-scope release -- a MEMBAR.ALL.GPU of ~1 000
+    // clocks -- is this otherwise idle warp's job.  (When the last epilogue warp did it, it paid those clocks on the
+    // critical path of the tile, stayed the last one, and set the pace of every chunk-add layer: 6 600 clocks per
+    // tile with the MMAs done after 4 300.)
+    uint32_t tcount = 0;
+    for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
+      const uint32_t e = __ldg(p.table + ei);
+      const int l = (int)(e >> 28), mt = (int)(e & 0xfffffu);
+      if (!p.st[l].publish) continue;
+      const uint32_t cnt = warpsDone + 4u * (tcount & 7u);
+      if (ld_acquire_cta_shared(cnt) < (uint32_t)kS3EpiWarps) {
+        const long long t0 = clock64();
+        while (ld_acquire_cta_shared(cnt) < (uint32_t)kS3EpiWarps) {
+          __nanosleep(100);
+          if (clock64() - t0 > 6000000000LL) mbar_timeout(p.err, 7);
+        }
+      }
+      if (lane == 0) {
+        // (tiles t and t + 8 of a CTA cannot be in flight together: two TMEM buffers)
+        asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(cnt), "r"(0u) : "memory");
+        fence_proxy_async_global();
+        red_release_gpu_add(p.done + (size_t)l * p.MT + mt, 1u);
+      }
+      __syncwarp();
     }
   }
   } else {
@@ -849,6 +917,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     x.epi_mem = !(p.dbg & 12);
 #ifdef DMC_EPI_TIMING
     x.timed = blockIdx.x == 0 && ew == 0;
+    x.ew = ew;
     x.tlast = clock64();
     for (int i = 0; i < 8; ++i) x.tacc[i] = 0;
 #endif
@@ -882,17 +951,12 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     uint32_t tcount = 0;
     uint32_t pend_l = 0, pend_mt = 0, pend_t = 0;   // tile whose completion is still to be published
     bool pending = false;
-    // lane 0, after this warp's stores of the pending tile are complete: the LAST of the CTA's eight epilogue
-    // warps (cta-scope counter; tiles t and t+4 cannot be in flight together) does the one gpu-scope release
+    // lane 0, after this warp's stores of the pending tile are complete: count this warp in (cta scope); the
+    // publisher warp does the gpu-scope release once all epilogue warps of the CTA are in
     auto publish = [&]() {
-      const uint32_t cnt = warpsDone + 4u * (pend_t & 3u);
-      uint32_t old;
-      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt) : "memory");
-      if (old == kS3EpiWarps - 1) {
-        asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(cnt), "r"(0u) : "memory");
-        fence_proxy_async_global();
-        red_release_gpu_add(p.done + (size_t)pend_l * p.MT + pend_mt, 1u);
-      }
+      const uint32_t cnt = warpsDone + 4u * (pend_t & 7u);
+      fence_proxy_async_global();
+      asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(cnt), "r"(1u) : "memory");
     };
     uint32_t e_next = unit < p.n_entries ? __ldg(p.table + unit) : 0u;
     int l_cached = -1;
@@ -918,7 +982,13 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         if (lane == 0) { tma_store_wait_all(); publish(); }
         pending = false;
       }
+      if (ew == 0) TILE_T(tcount, 4, clock64());
       mbar_wait(bar_tfull(buf), (tcount >> 1) & 1, p.err, 4);
+      if (ew == 0) TILE_T(tcount, 5, clock64());
+#ifdef DMC_EPI_TIMING
+      x.tile = tcount;
+      WARP_T(tcount, 0);
+#endif
       tc_fence_after();
       if (res_tile != tcount) issue_res(S, e, 0, tcount, true, x.slot);   // the early prefetch of chunk 0 was not possible
       const uint32_t taddr = tmem_base + ((uint32_t)(x.quad * 32) << 16) + buf * 256u;
@@ -951,10 +1021,20 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       } else {
         s3_epilogue_tile(S, x, mt, nt, taddr, p.err, next_res, release_tmem);
       }
-      if (pending) {                           // (tiles in which this warp has fewer than two chunks)
-        if (lane == 0) { tma_store_wait_all(); publish(); }
+      if (pending) {
+        // (tiles in which this warp has fewer than two chunks -- every tile of a chunk-add layer.)  Only the stores of
+        // the PREVIOUS tile have to be complete: waiting for the store just issued put its whole round trip on the
+        // critical path of the warp that publishes, which is the last one of the CTA and stays the last one.
+        if (lane == 0) {
+          if (nchunk == 1 && stored0) tma_store_wait_1(); else tma_store_wait_all();
+          publish();
+        }
         pending = false;
       }
+      if (ew == 0) TILE_T(tcount, 6, clock64());
+#ifdef DMC_EPI_TIMING
+      WARP_T(tcount, 2);
+#endif
       pend_l = (uint32_t)l; pend_mt = (uint32_t)mt; pend_t = tcount;
       pending = p.st[l].publish != 0;
     }
@@ -1194,6 +1274,12 @@ int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
 }  // namespace dmc
 
 #ifdef DMC_EPI_TIMING
+extern "C" __attribute__((visibility("default"))) int dmc_debug_warp_trace(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, dmc::g_warp_trace, sizeof(unsigned long long) * 2 * 2 * 256 * 3) == cudaSuccess ? 0 : -1;
+}
+extern "C" __attribute__((visibility("default"))) int dmc_debug_tile_trace(unsigned long long* out, int ntiles) {
+  return cudaMemcpyFromSymbol(out, dmc::g_tile_trace, sizeof(unsigned long long) * 8 * (size_t)ntiles) == cudaSuccess ? 0 : -1;
+}
 extern "C" __attribute__((visibility("default"))) int dmc_debug_epi_timing(unsigned long long* out8, int reset) {
   if (out8) cudaMemcpyFromSymbol(out8, dmc::g_epi_t, sizeof(unsigned long long) * 8);
   if (reset) {

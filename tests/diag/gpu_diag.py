@@ -1,13 +1,13 @@
 """GPU bring-up diagnostics (not a test): runs each section in its own process so that a trapped
 kernel only kills that section, and prints per-stage differences against the oracle.
 
-    python tools/gpu_diag.py [section ...]      sections: ops_simt ops_umma gop_simt gop_umma
+    python tests/diag/gpu_diag.py [section ...]      sections: ops_simt ops_umma gop_simt gop_umma
 """
 import os
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,6 +1,6 @@
 """Counts quantised-symbol mismatches of the CUDA path against the oracle, frame by frame (not a test).
 
-    python tools/symbol_counts.py [--full] [variant ...]
+    python tests/diag/symbol_counts.py [--full] [variant ...]
 
 Golden-case GOPs for every variant; --full adds a free-running 1 I + 3 P GOP at 1920x1280 (the
 size the 99.99 % gate of BASELINE.json is quoted on: <= 122 mismatches of 1 228 800 symbols);
@@ -10,7 +10,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -320,7 +320,7 @@ def test_full_size_parity_on_identical_inputs():
     against the oracle, EVERY call on identical inputs (the CUDA path gets the oracle's dpb).  This is the size
     the gates are quoted on: >= 99.99 % symbols = at most 122 of 1 228 800 per P frame.  (Free-running, the
     handful of intra-frame flips -- well inside the gate -- are amplified chaotically by the feature recurrence,
-    for the fp32-FMA backend as well: tools/symbol_counts.py)"""
+    for the fp32-FMA backend as well: tests/diag/symbol_counts.py)"""
     H, W = 1280, 1920
     frames, masks = D.clips.synthetic_clip(3, 1, 3, H, W)
     torch.manual_seed(gc.SEED_I)
