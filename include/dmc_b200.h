@@ -68,8 +68,8 @@ enum {
                                (validation backend) instead of tcgen05          */
   DMC_FLAG_KEEP_TAPS = 2,   /* keep intermediate tensors readable via dmc_get_tap */
   DMC_FLAG_RECON_BF16X1 = 4, /* (default behaviour since r1: kept for source compatibility, ignored) */
-  DMC_FLAG_RECON_SPLIT3 = 8  /* run recon_generation_net with the fp32-grade 6-term product too.  By default
-                                its contractions use plain bf16 operands (1 term, fp32 accumulate): x_hat of
+  DMC_FLAG_RECON_SPLIT3 = 8  /* run recon_generation_net with the fp32-grade 3-term split product too.  By default
+                                its contractions use plain fp16 operands (hi planes, 1 term, fp32 accumulate): x_hat of
                                 a P frame never feeds a later symbol, and PSNR moves by < 1e-3 dB */
 };
 
@@ -87,7 +87,7 @@ int dmc_weight_shape(const dmc_engine* e, int index, int64_t* shape4);
 
 /* Hand one state_dict tensor (fp32, device, contiguous) to the engine.  Unknown keys
  * return DMC_E_INVALID; the data is repacked on `stream` into the engine's own
- * split-bf16 tiles, the caller's buffer is not retained. */
+ * split-fp16 tiles (hi + 2^11-scaled lo), the caller's buffer is not retained. */
 int dmc_set_weight(dmc_engine* e, const char* key, const float* dev_ptr,
                    const int64_t* shape, int ndim, void* stream);
 int dmc_finalize_weights(dmc_engine* e, void* stream);
@@ -121,8 +121,9 @@ int dmc_frame_stats(double* stats7, const float* x_hat, const float* x, const fl
 /* ---- single-operator entry points (the same kernels the engine launches), used by the
  * per-layer parity tests.  All tensors NCHW fp32 on the device. ---- */
 
-/* act: 0 none, 1 WSiLU (layers.py:8-10), 2 ReLU.  backend: 0 tcgen05 split-bf16, 1 SIMT fp32.
- * nsplit: 3 (fp32-grade, 6 MMA terms) or 1 (plain bf16).  groups must be 1 or cin (depthwise 3x3). */
+/* act: 0 none, 1 WSiLU (layers.py:8-10), 2 ReLU.  backend: 0 tcgen05 split-fp16, 1 SIMT fp32.
+ * nsplit: 1 = single term (fp16 hi planes only), any other value (3 by convention) = fp32-grade 3-term split
+ * product.  groups must be 1 or cin (depthwise 3x3). */
 int dmc_op_conv2d(const float* x, const float* weight, const float* bias, float* out, int batch,
                   int cin, int height, int width, int cout, int ksize, int stride, int padding,
                   int groups, int act, int nsplit, int backend, void* stream);
