@@ -162,7 +162,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": f"configs[1]: dmc_variant={VARIANT}, {W}x{H}, batch {B}, one P-frame forward per step "
                           f"(after_i=False, qp {BASE_QP}+shift), synthetic clip + masks, random-init weights",
-              "l2": "per-step working set (~6 GB of activations) >> 126 MB L2, no explicit flush",
+              "l2": "per-step working set (~4 GB of activations) >> 126 MB L2, no explicit flush",
               "parallelism": f"clips sharded over {world} GPU(s), weights replicated"}
 
     if args.impl == "reference":
