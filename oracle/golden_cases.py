@@ -21,7 +21,15 @@ SEED_I, SEED_P = 0, 1
 CASES = (
     {"name": "anchor_256", "kind": "rand", "B": 1, "T": 4, "H": 256, "W": 256, "qp": 32, "perturb": False},
     {"name": "rect_128x192", "kind": "clip", "B": 2, "T": 3, "H": 128, "W": 192, "qp": 20, "perturb": True},
+    # ragged: y is 5 x 7 and gets replicate-padded to 8 x 8 for the hyper path (models/common_model.py:68-72);
+    # `performance` does not pad (seg_video_model.py:331) and cannot run this size in the reference either
+    {"name": "ragged_80x112", "kind": "clip", "B": 1, "T": 3, "H": 80, "W": 112, "qp": 28, "perturb": True,
+     "variants": ("old", "fast", "mask_prop")},
 )
+
+
+def case_variants(case):
+    return case.get("variants", VARIANTS)
 
 
 def case_by_name(name):

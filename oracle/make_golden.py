@@ -13,6 +13,9 @@ Cases (per P variant):
           rectangular mask, qp 32  (BASELINE.json config 1 for `old`)
   rect    128x192, B=2, synthetic drifting clip, per-QP tables perturbed so that qp indexing
           matters, 1 I + 2 P, qp 20
+  ragged  80x112, B=1: y (5 x 7) is replicate-padded to 8 x 8 for the hyper path; old / fast / mask_prop only
+
+`python oracle/make_golden.py NAME ...` regenerates only the named cases.
 """
 from __future__ import annotations
 
@@ -63,7 +66,10 @@ def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])
     for case in gc.CASES:
+        if only and case["name"] not in only:
+            continue
         frames, masks = gc.case_inputs(case)
         torch.manual_seed(gc.SEED_I)
         ref_i = RefDMCI().eval()
@@ -72,7 +78,7 @@ def main():
         box_i = capture(ref_i)
         r_i = ref_i(frames[:, 0], case["qp"])
         gc.record(rec, "intra/0", r_i, box_i, frames[:, 0], None)
-        for variant in gc.VARIANTS:
+        for variant in gc.case_variants(case):
             torch.manual_seed(gc.SEED_P)
             ref_p = REF_P[variant]().eval()
             gc.perturb(ref_p, case)

@@ -493,8 +493,10 @@ struct dmc_engine {
 // ====================================================================== P-frame program
 void dmc_engine::build_p() {
   const bool refactor = variant != DMC_VARIANT_OLD;
-  const int H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16, H32 = H / 32, W32 = W / 32,
-            H64 = H / 64, W64 = W / 64;
+  // the hyper path works on y replicate-padded to multiples of 4 (models/common_model.py:68-72): Hp16 x Wp16
+  const int H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16, Hp16 = (H16 + 3) / 4 * 4, Wp16 = (W16 + 3) / 4 * 4,
+            H32 = Hp16 / 2, W32 = Wp16 / 2, H64 = Hp16 / 4, W64 = Wp16 / 4;
+  const bool padded = Hp16 != H16 || Wp16 != W16;
   const int CD = 256, CY = 128, CZ = 128, CR = 320, QP = 72;
   const int ns = 3;
   // recon_generation_net never feeds a later symbol: plain bf16 operands unless the caller asks
@@ -595,12 +597,16 @@ void dmc_engine::build_p() {
   Act XC = new_act(B, H8, W8, 2 * CD);         // [encoder.conv1 out / decoder.up out | ctx]
   Act XC_lo = slice(XC, 0, CD), CTX = slice(XC, CD, CD);
   Act Y = new_act(B, H16, W16, CY);
-  Act YF = new_act(B, H16, W16, CY);           // FiLM'd y (performance) / hyper input (fast)
-  Act HA = new_act(B, H16, W16, CZ);
+  if (padded && variant == DMC_VARIANT_PERFORMANCE)
+    fail("variant performance needs height and width in multiples of 64 (the reference does not pad y there, "
+         "seg_video_model.py:331)");
+  Act YF = new_act(B, Hp16, Wp16, CY);         // FiLM'd y (performance) / hyper input (fast), on the padded grid
+  Act YP = padded ? new_act(B, Hp16, Wp16, CY) : Y;     // y replicate-padded for the hyper path
+  Act HA = new_act(B, Hp16, Wp16, CZ);
   Act D32 = new_act(B, H32, W32, CZ), H32a = new_act(B, H32, W32, CZ);
   Act D64 = new_act(B, H64, W64, CZ), Z = new_act(B, H64, W64, CZ), ZH = new_act(B, H64, W64, CZ);
   Act U32 = new_act(B, H32, W32, CZ), G32 = new_act(B, H32, W32, CZ);
-  Act U16 = new_act(B, H16, W16, CZ), G16 = new_act(B, H16, W16, CZ);
+  Act U16 = new_act(B, Hp16, Wp16, CZ), G16 = new_act(B, Hp16, Wp16, CZ);
   Act HT = new_act(B, H16, W16, 3 * CY);       // [hier | temporal]
   Act HIER = slice(HT, 0, CY), TEMP = slice(HT, CY, 2 * CY);
   Act TD = new_act(B, H16, W16, 2 * CY);
@@ -727,14 +733,19 @@ void dmc_engine::build_p() {
       });
       ftaps["mask_logits8"] = F32Tap{logit8, B, 1, H8, W8};
     }
-    op([self, mpool, logits_full, Y, YF, mf_w0, mf_b0, mf_w2, mf_b2, H16, W16](cudaStream_t st) {
+    if (padded) op([Y, YP, H16, W16, Hp16, Wp16](cudaStream_t st) { regrid(Y.v, H16, W16, YP.v, Hp16, Wp16, Y.B, st); });
+    op([self, mpool, logits_full, YP, YF, mf_w0, mf_b0, mf_w2, mf_b2, H16, W16, Hp16, Wp16](cudaStream_t st) {
       const float* m = self->cur.mask;
       if (self->variant == DMC_VARIANT_MASK_PROP && !self->cur_after_i && m)
         m = self->cur.mask_pred ? self->cur.mask_pred : logits_full;
       if (m) avgpool16_clamp(m, mpool, self->B, self->H, self->W, st);
-      maskfilm_apply(m ? mpool : nullptr, Y.v, YF.v, mf_w0, mf_b0, mf_w2, mf_b2, self->B, H16, W16, 128, st);
+      maskfilm_apply(m ? mpool : nullptr, YP.v, YF.v, mf_w0, mf_b0, mf_w2, mf_b2, self->B, Hp16, Wp16, 128, H16, W16, st);
     });
     HIN = YF;
+  }
+  if (padded && variant == DMC_VARIANT_OLD) {
+    op([Y, YP, H16, W16, Hp16, Wp16](cudaStream_t st) { regrid(Y.v, H16, W16, YP.v, Hp16, Wp16, Y.B, st); });
+    HIN = YP;
   }
   tap("y", YQ);
   tap("hyper_in", HIN);
@@ -765,7 +776,13 @@ void dmc_engine::build_p() {
     dcb(hd0, U32, G32, true, nullptr, ns);
     gemm(G32, hd1u, &U16, s, H32, W32);
     dcb(hd1, U16, G16, true, nullptr, ns);
-    dcb(hd2, G16, HIER, false, nullptr, ns);
+    if (padded) {                 // hierarchical params cropped back to y's grid (video_model.py:238)
+      Act HIERP = new_act(B, Hp16, Wp16, CY);
+      dcb(hd2, G16, HIERP, false, nullptr, ns);
+      op([HIERP, HIER, H16, W16, Hp16, Wp16](cudaStream_t st) { regrid(HIERP.v, Hp16, Wp16, HIER.v, H16, W16, HIER.B, st); });
+    } else {
+      dcb(hd2, G16, HIER, false, nullptr, ns);
+    }
     conv_kxk(CTXT, tpd, &TD, s);
     dcb(tpc, TD, TEMP, true, nullptr, ns);
     tap("hier", HIER);
@@ -837,8 +854,10 @@ void dmc_engine::build_p() {
 
 // ====================================================================== I-frame program
 void dmc_engine::build_intra() {
-  const int H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16, H32 = H / 32, W32 = W / 32,
-            H64 = H / 64, W64 = W / 64;
+  // the hyper path works on y replicate-padded to multiples of 4 (models/common_model.py:68-72): Hp16 x Wp16
+  const int H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16, Hp16 = (H16 + 3) / 4 * 4, Wp16 = (W16 + 3) / 4 * 4,
+            H32 = Hp16 / 2, W32 = Wp16 / 2, H64 = Hp16 / 4, W64 = Wp16 / 4;
+  const bool padded = Hp16 != H16 || Wp16 != W16;
   const int CE = 368, N = 256, CZ = 128, QP = 64;
   const int ns = 3;
   dmc_engine* self = this;
@@ -888,11 +907,12 @@ void dmc_engine::build_intra() {
   Act X8 = new_act(B, H8, W8, 192);
   Act EA = new_act(B, H8, W8, CE), EB = new_act(B, H8, W8, CE);
   Act Y = new_act(B, H16, W16, N);
-  Act HA = new_act(B, H16, W16, CZ);
+  Act YP = padded ? new_act(B, Hp16, Wp16, N) : Y;      // y replicate-padded for the hyper path
+  Act HA = new_act(B, Hp16, Wp16, CZ);
   Act D32 = new_act(B, H32, W32, CZ), H32a = new_act(B, H32, W32, CZ);
   Act D64 = new_act(B, H64, W64, CZ), Z = new_act(B, H64, W64, CZ), ZH = new_act(B, H64, W64, CZ);
   Act U32 = new_act(B, H32, W32, CZ), G32 = new_act(B, H32, W32, CZ);
-  Act U16 = new_act(B, H16, W16, CZ), G16 = new_act(B, H16, W16, CZ);
+  Act U16 = new_act(B, Hp16, Wp16, CZ), G16 = new_act(B, Hp16, Wp16, CZ);
   Act HP = new_act(B, H16, W16, N);
   Act FA = new_act(B, H16, W16, 2 * N), FB = new_act(B, H16, W16, 2 * N);
   Act PARAMS = new_act(B, H16, W16, 2 * N + 2);
@@ -924,7 +944,8 @@ void dmc_engine::build_intra() {
   // hyper path (image_model.py:216-226)
   {
     EpiSpec s; s.nsplit = ns;
-    dcb(he0, Y, HA, false, nullptr, ns);
+    if (padded) op([Y, YP, H16, W16, Hp16, Wp16](cudaStream_t st) { regrid(Y.v, H16, W16, YP.v, Hp16, Wp16, Y.B, st); });
+    dcb(he0, YP, HA, false, nullptr, ns);
     conv_kxk(HA, he1d, &D32, s);
     dcb(he1, D32, H32a, true, nullptr, ns);
     conv_kxk(H32a, he2d, &D64, s);
@@ -941,11 +962,25 @@ void dmc_engine::build_intra() {
     dcb(hd0, U32, G32, true, nullptr, ns);
     gemm(G32, hd1u, &U16, s, H32, W32);
     dcb(hd1, U16, G16, true, nullptr, ns);
-    dcb(hd2, G16, HP, false, nullptr, ns);
-    dcb(pf0, HP, FA, false, nullptr, ns);
-    dcb(pf1, FA, FB, false, nullptr, ns);
-    dcb(pf2, FB, FA, false, nullptr, ns);
-    gemm(FA, pf3, &PARAMS, s);
+    if (padded) {                 // the prior fusion runs on the padded grid, params are cropped (image_model.py:224-226)
+      Act HPP = new_act(B, Hp16, Wp16, N);
+      Act FAP = new_act(B, Hp16, Wp16, 2 * N), FBP = new_act(B, Hp16, Wp16, 2 * N);
+      Act PARAMSP = new_act(B, Hp16, Wp16, 2 * N + 2);
+      dcb(hd2, G16, HPP, false, nullptr, ns);
+      dcb(pf0, HPP, FAP, false, nullptr, ns);
+      dcb(pf1, FAP, FBP, false, nullptr, ns);
+      dcb(pf2, FBP, FAP, false, nullptr, ns);
+      gemm(FAP, pf3, &PARAMSP, s);
+      op([PARAMSP, PARAMS, H16, W16, Hp16, Wp16](cudaStream_t st) {
+        regrid(PARAMSP.v, Hp16, Wp16, PARAMS.v, H16, W16, PARAMS.B, st);
+      });
+    } else {
+      dcb(hd2, G16, HP, false, nullptr, ns);
+      dcb(pf0, HP, FA, false, nullptr, ns);
+      dcb(pf1, FA, FB, false, nullptr, ns);
+      dcb(pf2, FB, FA, false, nullptr, ns);
+      gemm(FA, pf3, &PARAMS, s);
+    }
     tap("params", PARAMS);
     gemm(PARAMS, red, &COMMON, s);
   }
@@ -1023,8 +1058,8 @@ int dmc_create(int variant, int batch, int height, int width, int flags, dmc_eng
   dmc_engine* e = nullptr;
   int rc = guarded(nullptr, [&] {
     if (variant < DMC_VARIANT_OLD || variant > DMC_VARIANT_INTRA) fail("unknown variant %d", variant);
-    if (batch < 1 || height < 64 || width < 64 || height % 64 || width % 64)
-      fail("batch must be >= 1 and height/width multiples of 64 (got %d, %d, %d)", batch, height, width);
+    if (batch < 1 || height < 16 || width < 16 || height % 16 || width % 16)
+      fail("batch must be >= 1 and height/width multiples of 16 (got %d, %d, %d)", batch, height, width);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
       fail("CUDA device required: this engine has no CPU path");

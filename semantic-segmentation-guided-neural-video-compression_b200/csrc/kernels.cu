@@ -224,6 +224,29 @@ void scale_cols(View in, const float* scale, View out, long long M, cudaStream_t
 }
 void copy_view(View in, View out, long long M, cudaStream_t st) { scale_cols(in, nullptr, out, M, st); }
 
+// out[b, h, w, :] = in[b, min(h, Hin-1), min(w, Win-1), :]: replicate padding on the right / bottom when the output
+// grid is larger (inference.py:40-43), a crop to the top-left corner when it is smaller (`[:, :, :h, :w]`).
+__global__ void k_regrid(View in, int Hin, int Win, View out, int Hout, int Wout, int B, int C8) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * Hout * Wout * C8) return;
+  int c = (int)(idx % C8) * 8;
+  long long t = idx / C8;
+  int w = (int)(t % Wout);
+  t /= Wout;
+  int h = (int)(t % Hout);
+  long long b = t / Hout;
+  const long long src = (b * Hin + min(h, Hin - 1)) * Win + min(w, Win - 1);
+  const h16* q = in.p + s3_unit_offset(in, src, c);
+  h16* d = out.p + s3_unit_offset(out, (b * Hout + h) * Wout + w, c);
+  *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(q);
+  *reinterpret_cast<uint4*>(d + out.ps) = *reinterpret_cast<const uint4*>(q + in.ps);
+}
+void regrid(View in, int Hin, int Win, View out, int Hout, int Wout, int B, cudaStream_t st) {
+  int C8 = (in.C + 7) / 8;   // a ragged tail stays inside the last 16-column block
+  long long n = (long long)B * Hout * Wout * C8;
+  (note_launch(), k_regrid)<<<cdiv(n, 256), 256, 0, st>>>(in, Hin, Win, out, Hout, Wout, B, C8);
+}
+
 __global__ void k_finite_check(View v, long long M, int C8, int* flag) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * C8) return;
@@ -689,20 +712,23 @@ void avgpool16_clamp(const float* mask, float* out, int B, int H, int W, cudaStr
 
 // MaskFiLM: 3x3 (1->16) + ReLU + 1x1 (16->2C), then hyper_in = y*(1+gamma)+beta
 // (seg_video_model_fast.py:159-180,312-314).  One block per pixel, one thread per channel.
+// y / out live on an H x W grid; the mask map m is Hm x Wm <= H x W and counts as zero outside (the reference pads
+// y by replication and the pooled mask with zeros, seg_video_model_fast.py:309-311)
 __global__ void k_maskfilm_apply(const float* __restrict__ m, View y, View out,
                                  const float* __restrict__ w0, const float* __restrict__ b0,
                                  const float* __restrict__ w2, const float* __restrict__ b2, int H,
-                                 int W, int C) {
+                                 int W, int C, int Hm, int Wm) {
   __shared__ float hid[16];
   long long pix = blockIdx.x;
   int w = (int)(pix % W), h = (int)((pix / W) % H);
+  long long b = pix / ((long long)W * H);
   if (threadIdx.x < 16) {
     float acc = 0.0f;
     if (m) {
       for (int dy = -1; dy <= 1; ++dy)
         for (int dx = -1; dx <= 1; ++dx) {
-          if ((unsigned)(h + dy) >= (unsigned)H || (unsigned)(w + dx) >= (unsigned)W) continue;
-          acc = fmaf(m[pix + dy * W + dx], w0[threadIdx.x * 9 + (dy + 1) * 3 + dx + 1], acc);
+          if ((unsigned)(h + dy) >= (unsigned)Hm || (unsigned)(w + dx) >= (unsigned)Wm) continue;
+          acc = fmaf(m[(b * Hm + h + dy) * Wm + w + dx], w0[threadIdx.x * 9 + (dy + 1) * 3 + dx + 1], acc);
         }
     }
     hid[threadIdx.x] = fmaxf(add_rn(acc, b0[threadIdx.x]), 0.0f);
@@ -722,8 +748,9 @@ __global__ void k_maskfilm_apply(const float* __restrict__ m, View y, View out,
   }
 }
 void maskfilm_apply(const float* m, View y, View out, const float* w0, const float* b0,
-                    const float* w2, const float* b2, int B, int H, int W, int C, cudaStream_t st) {
-  (note_launch(), k_maskfilm_apply)<<<(unsigned)((long long)B * H * W), 128, 0, st>>>(m, y, out, w0, b0, w2, b2, H, W, C);
+                    const float* w2, const float* b2, int B, int H, int W, int C, int Hm, int Wm, cudaStream_t st) {
+  (note_launch(), k_maskfilm_apply)<<<(unsigned)((long long)B * H * W), 128, 0, st>>>(m, y, out, w0, b0, w2, b2, H, W, C,
+                                                                                    Hm, Wm);
 }
 
 // F.interpolate(bilinear, align_corners=False) by exactly 1/8 and 8 (mask_predictor.py:35,44)

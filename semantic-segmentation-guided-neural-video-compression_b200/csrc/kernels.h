@@ -41,6 +41,8 @@ void s3_to_nchw(View in, float* x, int B, int C, int H, int W, cudaStream_t st);
 void f32rows_to_nchw(const float* in, int ld, float* x, int B, int C, int H, int W, cudaStream_t st);
 void scale_cols(View in, const float* scale, View out, long long M, cudaStream_t st);
 void copy_view(View in, View out, long long M, cudaStream_t st);
+// (B,Hin,Win,C) -> (B,Hout,Wout,C): replicate pad right/bottom (inference.py:40-43) or crop to the top-left corner
+void regrid(View in, int Hin, int Win, View out, int Hout, int Wout, int B, cudaStream_t st);
 void finite_check(View v, long long M, int* flag, cudaStream_t st);
 
 // ---------------- convolution pieces ----------------
@@ -123,9 +125,10 @@ void gaussian_bits(const float* sym, const float* sigma, float* bits, long long 
 void film(View y, View gb, View out, long long M, int C, cudaStream_t st);   // y*(1+g)+b, gb=[g|b]
 // 16x16 block mean of an fp32 (B,1,H,W) map, clamped to [0,1] -> (B,H/16,W/16) fp32
 void avgpool16_clamp(const float* mask, float* out, int B, int H, int W, cudaStream_t st);
-// MaskFiLM (3x3 1->16, ReLU, 1x1 16->2C) + FiLM on y;  m == nullptr means an all-zero mask
+// MaskFiLM (3x3 1->16, ReLU, 1x1 16->2C) + FiLM on y;  m == nullptr means an all-zero mask; m is an Hm x Wm map
+// (zero outside) on y's H x W grid
 void maskfilm_apply(const float* m, View y, View out, const float* w0, const float* b0,
-                    const float* w2, const float* b2, int B, int H, int W, int C, cudaStream_t st);
+                    const float* w2, const float* b2, int B, int H, int W, int C, int Hm, int Wm, cudaStream_t st);
 void bilinear_down8(const float* in, float* out, int B, int H, int W, cudaStream_t st);  // -> H/8
 void bilinear_up8(const float* in, float* out, int B, int h, int w, cudaStream_t st);    // -> 8h
 // 3x3 conv with a single input channel (mask_embed): fp32 map (B,h,w) -> S3 [M, C]

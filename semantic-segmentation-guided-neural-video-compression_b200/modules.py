@@ -267,8 +267,11 @@ class _DMCBase(_EngineModule):
         else:
             # same failure as the reference's encoder.conv1 on a wrong channel count
             raise RuntimeError(f"expected input with 3{' or 4' if takes_mask else ''} channels, got {C}")
-        if H % 64 or W % 64:
-            raise RuntimeError("dmc_b200: height and width must be multiples of 64")
+        # y is replicate-padded to multiples of 4 for the hyper path (old / fast / mask_prop); `performance` does not
+        # pad (seg_video_model.py:331) and fails in the reference on such sizes too
+        need = 64 if self.variant == "performance" else 16
+        if H % need or W % need:
+            raise RuntimeError(f"dmc_b200: height and width must be multiples of {need} for variant {self.variant}")
         x_img = x_img.contiguous()
         frame = feature = None
         if after_i:
@@ -404,8 +407,8 @@ class DMCI(_EngineModule):
         B, C, H, W = x.shape
         if C != 3:
             raise RuntimeError(f"expected a 3-channel frame, got {C}")
-        if H % 64 or W % 64:
-            raise RuntimeError("dmc_b200: height and width must be multiples of 64")
+        if H % 16 or W % 16:
+            raise RuntimeError("dmc_b200: height and width must be multiples of 16")
         x = x.contiguous()
         h, stream = self._engine(B, H, W, x.device)
         x_hat = torch.empty_like(x)

@@ -12,7 +12,7 @@ def test_default_init_matches_reference_checksums(case):
     g = golden(case["name"])
     mi, _ = seeded_models("old", case)
     np.testing.assert_allclose(gc.sd_checksum(mi.state_dict()), g["sd_checksum_intra"], rtol=0, atol=0)
-    for variant in gc.VARIANTS:
+    for variant in gc.case_variants(case):
         _, mp = seeded_models(variant, case)
         np.testing.assert_allclose(gc.sd_checksum(mp.state_dict()), g[f"sd_checksum_{variant}"], rtol=0, atol=0)
 
@@ -38,6 +38,8 @@ def _check(g, tag, res, taps, target, mask):
 @pytest.mark.parametrize("case", gc.CASES, ids=lambda c: c["name"])
 @pytest.mark.parametrize("variant", gc.VARIANTS)
 def test_oracle_reproduces_reference(case, variant):
+    if variant not in gc.case_variants(case):
+        pytest.skip("the reference does not pad y in this variant: it cannot run this size")
     g = golden(case["name"])
     frames, masks = gc.case_inputs(case)
     mi, mp = seeded_models(variant, case)
