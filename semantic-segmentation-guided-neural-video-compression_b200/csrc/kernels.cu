@@ -496,10 +496,17 @@ __device__ __forceinline__ double block_sum(double v) {
 }
 
 // ------------------------------------------------------------------ likelihoods
-// erf rounded from double: correctly rounded fp32, which is what the CPU reference's 1-ulp
-// vectorised erf returns almost everywhere; CUDA's 2-ulp erff flips the last bit often enough to
-// move p by whole quanta where p sits at the fp32 cancellation floor (p ~ 1e-7).
-__device__ __forceinline__ float erf_cr(float x) { return (float)erf((double)x); }
+// erf as the reference's CPU path computes it.  torch's CPU erf is MKL VML's vsErf (high-accuracy mode): within one
+// ulp, equal to the correctly rounded value on 95 % of the inputs -- and saturated to exactly +-1 from
+// |x| >= 3.832507 (0x407547cb) on, where the correctly rounded value stays at 1 - 2^-24 up to 3.9192 (measured over
+// every fp32 in [3, 4)).  The likelihoods below cancel down to the last bit of erf for tail symbols: in that band a
+// symbol costs 29.9 bits with the saturated erf and 25 with the rounded one, which alone moved bpp by 6.5e-4
+// relative (0.1 % of the symbols with random-init weights); CUDA's 2-ulp erff moves it by as much again.  So:
+// correctly rounded from double, with the reference's saturation point.
+__device__ __forceinline__ float erf_cr(float x) {
+  if (fabsf(x) >= __uint_as_float(0x407547cbu)) return copysignf(1.0f, x);
+  return (float)erf((double)x);
+}
 
 __device__ __forceinline__ float bits_old(float s, float sigma) {
   // models/common_model.py:30-42: Normal(0, clamp(sigma)).cdf difference, log(p + 1e-5)

@@ -23,13 +23,17 @@ from helpers import D, O, gc, sd_of, symbol_match  # noqa: E402
 def golden_cases(variants):
     for variant in variants:
         for case in gc.CASES:
+            if variant not in gc.case_variants(case):
+                continue
             rep = T._run_case(variant, case, T.capi.FLAG_KEEP_TAPS, record_taps=("y_q", "z_hat"))
             for tag, o, c, to, tc, target, mask in rep:
                 line = f"{variant:11s} {case['name']:13s} {tag:5s} bpp rel {T.rel_err(c['bpp'].cpu(), o['bpp']):.2e}"
                 if tc:
                     fy, by = symbol_match(tc["y_q"], to["y_q"])
+                    line += f"  y bad {by}/{to['y_q'].numel()}"
+                if "z_hat" in tc:
                     fz, bz = symbol_match(tc["z_hat"], to["z_hat"])
-                    line += f"  y bad {by}/{to['y_q'].numel()}  z bad {bz}/{to['z_hat'].numel()}"
+                    line += f"  z bad {bz}/{to['z_hat'].numel()}"
                 if o["dpb"].get("feature") is not None:
                     d = (o["dpb"]["feature"] - c["dpb"]["feature"].cpu()).abs()
                     line += f"  feature max diff {float(d.max()):.2e}"

@@ -215,13 +215,7 @@ def _run_case(variant, case, flags, record_taps=(), resync=True):
 
 
 def _bpp_tol(case):
-    """1e-3 (north_star), except on frames of a few thousand symbols.  With random-init weights ~0.1 % of the
-    symbols sit where the refactor bits formula (refactor/common_model.py:37-68) cancels down to the last fp32 bit
-    of erf: such a symbol costs 24 or 29.9 bits depending on that bit, and the reference's 1-ulp CPU erf and a
-    correctly rounded erf disagree on it now and then.  That is a 5-7e-4 relative offset on bpp at every size
-    measured (1920x1280 included); on the 4 480 symbols of the ragged case its scatter reaches 1.03e-3."""
-    symbols = (case["H"] // 16) * (case["W"] // 16) * 128
-    return BPP_REL_TOL if symbols >= 8192 else 1.5 * BPP_REL_TOL
+    return BPP_REL_TOL
 
 
 def _assert_frame(tag, o, c, target, mask, exact_symbols=True, bpp_tol=BPP_REL_TOL):
