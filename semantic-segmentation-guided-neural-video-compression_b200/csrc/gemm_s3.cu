@@ -82,9 +82,19 @@ static int s3_encode(void* out, View v, int cols, uint32_t box_rows, uint32_t bo
 }
 
 // A operand: box = 128 rows x 2 column blocks (32 k) x `planes` planes (2, or 1 = hi only for single-term products)
+// 16-wide k blocks per operand stage of a single-term layer: 4 = 64 k of the hi plane, the same bytes in flight per
+// stage as 32 k of both planes (DMC_S3_SINGLE_KBLK=2 restores half-filled stages for A/B runs)
+static int s3_single_kblk() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("DMC_S3_SINGLE_KBLK");
+    v = (e && e[0] == '2') ? 2 : 4;
+  }
+  return v;
+}
 int make_tmap_s3_act(void* tmap_out, View a, long long M, int planes) {
   (void)M;
-  return s3_encode(tmap_out, a, a.C, 128, 2, (uint32_t)planes);
+  return s3_encode(tmap_out, a, a.C, 128, planes == 1 ? s3_single_kblk() : 2, (uint32_t)planes);
 }
 // A operand for 4-CTA clusters: box = 64 rows x 1 column block x 1 plane (one contiguous 2 KB piece)
 int make_tmap_s3_act64(void* tmap_out, View a, long long M) {
@@ -103,7 +113,7 @@ int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes) {
   const uint64_t plane_bytes = (uint64_t)w.Npad * w.Kld * 2;
   cuuint64_t dims[4] = {256, (cuuint64_t)w.Npad / 16, (cuuint64_t)w.Kld / 16, (cuuint64_t)kPlanes};
   cuuint64_t strides[3] = {512, (cuuint64_t)w.Npad * 32, plane_bytes};
-  cuuint32_t box[4] = {256, (cuuint32_t)(w.BN / 32), 2, (cuuint32_t)planes};
+  cuuint32_t box[4] = {256, (cuuint32_t)(w.BN / 32), planes == 1 ? (cuuint32_t)s3_single_kblk() : 2u, (cuuint32_t)planes};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn((CUtensorMap*)tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, w.wb, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -386,6 +396,7 @@ struct alignas(64) S3StageDev {
   const float* bias;
   const float* scale;
   int k_blocks, BN, n_tiles, n_out;
+  int kblk;          // 16-wide k blocks per operand stage: 2 (both planes) or 4 (single term: hi plane only)
   int kind;          // S3_*
   int nterms;        // 3: fp32-grade split product (two accumulators), 1: hi*hi only
   uint32_t need;     // increments of done[l-1][row tile] per launch that complete layer l-1 for a row tile
@@ -781,7 +792,9 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       }
       if (lane == 0) st_release_cta_shared(depsOk, tcount + 1);
       const uint32_t wRows = (uint32_t)S.BN >> 1;
-      const uint32_t tx = 2u * (S.nterms == 1 ? 1u : (uint32_t)kPlanes) * (kS3APlane + wRows * (kS3BK * 2));   // 1 term: hi planes only
+      // both planes x 32 k, or (single term) the hi plane x 64 k: the same bytes
+      const int kblk = S.kblk;
+      const uint32_t tx = (S.nterms == 1 ? (uint32_t)kblk : 4u) * (kS3APlane + wRows * (kS3BK * 2));
       const int m_idx = mt * 256 + (int)rank * 128;
       const int n_idx = nt * S.BN + (int)(rank * wRows);
       for (int kb = 0; kb < S.k_blocks; ++kb) {
@@ -802,13 +815,13 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
               const uint16_t mc = (uint16_t)((1u << rank) | (4u << rank));
               const int planes = S.nterms == 1 ? 1 : kPlanes;
               for (int pl = 0; pl < planes; ++pl)
-                for (int blk = 0; blk < 2; ++blk)
+                for (int blk = 0; blk < kblk; ++blk)
                   tma_load_pair_mcast(sa + pl * kS3APlane + blk * 4096u + pairIdx * 2048u, &S.tmA64,
-                                      (m_idx + (int)pairIdx * 64) >> 4, kb * 2 + blk, pl, lbar, mc);
+                                      (m_idx + (int)pairIdx * 64) >> 4, kb * kblk + blk, pl, lbar, mc);
             } else {
-              tma_load_pair(sa, &S.tmA, m_idx >> 4, kb * 2, lbar);
+              tma_load_pair(sa, &S.tmA, m_idx >> 4, kb * kblk, lbar);
             }
-            tma_load_pair_w(sw, &S.tmW, n_idx >> 4, kb * 2, lbar);
+            tma_load_pair_w(sw, &S.tmW, n_idx >> 4, kb * kblk, lbar);
           }
         }
         __syncwarp();
@@ -833,6 +846,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         const uint32_t wKs = ((uint32_t)(S.BN >> 1) * 32u) >> 4;             // second 16-wide k block of a plane
         const int k_blocks = S.k_blocks;
         const bool split = S.nterms != 1;
+        const int kblk = S.kblk;
         const uint32_t buf = tcount & 1;
         TILE_T(tcount, 0, clock64());
         TILE_T(tcount, 7, e);
@@ -852,9 +866,10 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
           if (elect_one()) {
             if (!(p.dbg & 2)) {
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks >= kblk) break;
                 // hi*hi -> main accumulator; the two 2^11-scaled cross terms hi*lo', lo'*hi -> second one
-                // (plane index: 0 hi, 1 lo')
+                // (plane index: 0 hi, 1 lo'; a single-term stage is four k blocks of the hi plane)
                 const uint64_t a0 = da + ks * (4096u >> 4), a1 = a0 + aStep;
                 const uint64_t w0 = dw + ks * wKs, w1 = w0 + wStep;
                 tc_mma_pair(d_main, a0, w0, idesc, ks == 0 ? first : 1u);
@@ -1164,7 +1179,8 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     memcpy(&S.tmRes, d.tmRes ? d.tmRes : d.tmOut, sizeof(CUtensorMap));
     S.bias = d.e.bias;
     S.scale = d.e.scale;
-    S.k_blocks = (d.K + kS3BK - 1) / kS3BK;
+    S.kblk = d.nsplit != 1 ? 2 : s3_single_kblk();
+    S.k_blocks = (d.K + 16 * S.kblk - 1) / (16 * S.kblk);
     S.BN = d.w->BN;
     S.n_tiles = (d.w->ncols + d.w->BN - 1) / d.w->BN;
     S.n_out = d.e.n_out;
