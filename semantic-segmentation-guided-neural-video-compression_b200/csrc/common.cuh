@@ -197,4 +197,14 @@ __device__ __forceinline__ void epi_store(const Epi& e, long long m, int n, floa
   if (e.out.p) st3(e.out, drow, dcol, v);
 }
 
+// ---- programmatic dependent launch.  Every kernel of the frame is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_prologue_done(): its CTAs are scheduled
+// as soon as the previous kernel's CTAs leave their SMs (that kernel released its dependents at its own start),
+// run their prologue (barrier initialisation, TMEM allocation, index arithmetic), and block in griddepcontrol.wait
+// until the previous grid has completed and its writes are visible.  No global memory is touched before the wait.
+__device__ __forceinline__ void pdl_prologue_done() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 }  // namespace dmc

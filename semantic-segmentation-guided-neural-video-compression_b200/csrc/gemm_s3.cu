@@ -761,6 +761,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   __syncthreads();
   cluster_sync_all();                      // peer barriers are initialised before any remote use
   tc_fence_after();
+  pdl_prologue_done();                     // everything above overlapped the previous kernel's tail
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmemSlot - base));
   const int unit = (int)(p.cl4 ? blockIdx.x >> 2 : blockIdx.x >> 1);
   const int units = (int)(p.cl4 ? gridDim.x >> 2 : gridDim.x >> 1);
@@ -1271,13 +1272,15 @@ int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
   cfg.blockDim = dim3(kS3Threads);
   cfg.dynamicSmemBytes = c->smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = c->p.cl4 ? 4 : 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   note_launch();
   cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_s3_chain, c->p);
   if (err != cudaSuccess) {

@@ -498,6 +498,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   if (kPair) cluster_sync_all();                      // peer barriers are initialised before any remote use
   tc_fence_after();
+  pdl_prologue_done();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmemSlot) : "memory");
 
@@ -729,19 +730,31 @@ int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int 
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     err = cudaLaunchKernelEx(&cfg, k_gemm_umma<true>, ta, tw, e, p);
   } else {
     int grid = p.m_tiles * p.n_tiles;
     if (grid > num_sms()) grid = num_sms();
-    k_gemm_umma<false><<<grid, kThreads, smem, st>>>(ta, tw, e, p);
-    err = cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    err = cudaLaunchKernelEx(&cfg, k_gemm_umma<false>, ta, tw, e, p);
   }
   if (err != cudaSuccess) {
     snprintf(g_umma_err, sizeof g_umma_err, "k_gemm_umma launch: %s", cudaGetErrorString(err));

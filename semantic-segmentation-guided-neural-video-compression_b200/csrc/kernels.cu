@@ -13,6 +13,14 @@ static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b
 
 static long long g_launches = 0;
 void note_launch() { ++g_launches; }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DMC_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 long long launch_count() { return g_launches; }
 
 int num_sms() {
@@ -33,6 +41,7 @@ int num_sms() {
 __global__ void k_pack_gemm_weight(const float* __restrict__ w, h16* __restrict__ out, h16* __restrict__ outb,
                                    int cout, int cin, int kh, int kw, int Npad, int Kld, int K, int pack,
                                    int Cg, int Cg_pad) {
+  pdl_prologue_done();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)Npad * Kld) return;
   int r = (int)(idx / Kld), kk = (int)(idx % Kld);
@@ -68,6 +77,7 @@ __global__ void k_pack_gemm_weight(const float* __restrict__ w, h16* __restrict_
 
 __global__ void k_pack_bias(const float* __restrict__ b, float* __restrict__ out, int cout, int Npad,
                             int pack, int Cg, int Cg_pad) {
+  pdl_prologue_done();
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= Npad) return;
   int n = -1;
@@ -87,25 +97,27 @@ __global__ void k_pack_bias(const float* __restrict__ b, float* __restrict__ out
 void pack_gemm_weight(const float* w, int cout, int cin, int kh, int kw, const GemmW& g,
                       cudaStream_t st) {
   long long n = (long long)g.Npad * g.Kld;
-  (note_launch(), k_pack_gemm_weight)<<<cdiv(n, 256), 256, 0, st>>>(w, g.w, g.wb, cout, cin, kh, kw, g.Npad, g.Kld,
+  launch(k_pack_gemm_weight, cdiv(n, 256), 256, 0, st, w, g.w, g.wb, cout, cin, kh, kw, g.Npad, g.Kld,
                                                    g.K, g.pack, g.Cg, g.Cg_pad);
 }
 void pack_gemm_bias(const float* bias, int cout, const GemmW& g, cudaStream_t st) {
-  (note_launch(), k_pack_bias)<<<cdiv(g.Npad, 256), 256, 0, st>>>(bias, g.bias, cout, g.Npad, g.pack, g.Cg, g.Cg_pad);
+  launch(k_pack_bias, cdiv(g.Npad, 256), 256, 0, st, bias, g.bias, cout, g.Npad, g.pack, g.Cg, g.Cg_pad);
 }
 
 __global__ void k_pack_dw(const float* __restrict__ w, float* __restrict__ out, int C) {
+  pdl_prologue_done();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 9 * C) return;
   int tap = i / C, c = i % C;
   out[i] = w[c * 9 + tap];
 }
 void pack_dw_weight(const float* w, float* out9c, int C, cudaStream_t st) {
-  (note_launch(), k_pack_dw)<<<cdiv(9 * C, 256), 256, 0, st>>>(w, out9c, C);
+  launch(k_pack_dw, cdiv(9 * C, 256), 256, 0, st, w, out9c, C);
 }
 
 // ------------------------------------------------------------------ layout conversion
 __global__ void k_unshuffle8_in(const float* __restrict__ x, View out, int B, int Cimg, int H, int W) {
+  pdl_prologue_done();
   int W8 = W / 8, H8 = H / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * H8 * Cimg * 8 * W8;
@@ -125,11 +137,12 @@ __global__ void k_unshuffle8_in(const float* __restrict__ x, View out, int B, in
 }
 void unshuffle8_in(const float* x, View out, int B, int Cimg, int H, int W, cudaStream_t st) {
   long long total = (long long)B * (H / 8) * Cimg * 8 * (W / 8);
-  (note_launch(), k_unshuffle8_in)<<<cdiv(total, 256), 256, 0, st>>>(x, out, B, Cimg, H, W);
+  launch(k_unshuffle8_in, cdiv(total, 256), 256, 0, st, x, out, B, Cimg, H, W);
 }
 
 __global__ void k_shuffle8_out(const float* __restrict__ in, int ld, float* __restrict__ x, int B,
                                int Cimg, int H, int W) {
+  pdl_prologue_done();
   int W8 = W / 8, H8 = H / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Cimg * H * W8;
@@ -154,11 +167,12 @@ __global__ void k_shuffle8_out(const float* __restrict__ in, int ld, float* __re
 }
 void shuffle8_out(const float* in, int ld, float* x, int B, int Cimg, int H, int W, cudaStream_t st) {
   long long total = (long long)B * Cimg * H * (W / 8);
-  (note_launch(), k_shuffle8_out)<<<cdiv(total, 256), 256, 0, st>>>(in, ld, x, B, Cimg, H, W);
+  launch(k_shuffle8_out, cdiv(total, 256), 256, 0, st, in, ld, x, B, Cimg, H, W);
 }
 
 // NCHW fp32 <-> S3 rows.  Thread = (pixel, 8 channels), pixel fastest so the NCHW side is coalesced.
 __global__ void k_nchw_to_s3(const float* __restrict__ x, View out, int C, long long HW) {
+  pdl_prologue_done();
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   int c8 = blockIdx.y, b = blockIdx.z;
@@ -173,9 +187,10 @@ __global__ void k_nchw_to_s3(const float* __restrict__ x, View out, int C, long 
 void nchw_to_s3(const float* x, View out, int B, int C, int H, int W, cudaStream_t st) {
   long long HW = (long long)H * W;
   dim3 grid(cdiv(HW, 256), (C + 7) / 8, B);
-  (note_launch(), k_nchw_to_s3)<<<grid, 256, 0, st>>>(x, out, C, HW);
+  launch(k_nchw_to_s3, grid, 256, 0, st, x, out, C, HW);
 }
 __global__ void k_s3_to_nchw(View in, float* __restrict__ x, int C, long long HW) {
+  pdl_prologue_done();
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   int c8 = blockIdx.y, b = blockIdx.z;
@@ -190,10 +205,11 @@ __global__ void k_s3_to_nchw(View in, float* __restrict__ x, int C, long long HW
 void s3_to_nchw(View in, float* x, int B, int C, int H, int W, cudaStream_t st) {
   long long HW = (long long)H * W;
   dim3 grid(cdiv(HW, 256), (C + 7) / 8, B);
-  (note_launch(), k_s3_to_nchw)<<<grid, 256, 0, st>>>(in, x, C, HW);
+  launch(k_s3_to_nchw, grid, 256, 0, st, in, x, C, HW);
 }
 __global__ void k_f32rows_to_nchw(const float* __restrict__ in, int ld, float* __restrict__ x, int C,
                                   long long HW) {
+  pdl_prologue_done();
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   int c = blockIdx.y, b = blockIdx.z;
@@ -202,10 +218,11 @@ __global__ void k_f32rows_to_nchw(const float* __restrict__ in, int ld, float* _
 void f32rows_to_nchw(const float* in, int ld, float* x, int B, int C, int H, int W, cudaStream_t st) {
   long long HW = (long long)H * W;
   dim3 grid(cdiv(HW, 256), C, B);
-  (note_launch(), k_f32rows_to_nchw)<<<grid, 256, 0, st>>>(in, ld, x, C, HW);
+  launch(k_f32rows_to_nchw, grid, 256, 0, st, in, ld, x, C, HW);
 }
 
 __global__ void k_scale_cols(View in, const float* __restrict__ scale, View out, long long M, int C8) {
+  pdl_prologue_done();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * C8) return;
   long long m = idx / C8;
@@ -220,13 +237,14 @@ __global__ void k_scale_cols(View in, const float* __restrict__ scale, View out,
 }
 void scale_cols(View in, const float* scale, View out, long long M, cudaStream_t st) {
   int C8 = (in.C + 7) / 8;   // a ragged tail stays inside the row pitch (ld is a multiple of 8)
-  (note_launch(), k_scale_cols)<<<cdiv(M * C8, 256), 256, 0, st>>>(in, scale, out, M, C8);
+  launch(k_scale_cols, cdiv(M * C8, 256), 256, 0, st, in, scale, out, M, C8);
 }
 void copy_view(View in, View out, long long M, cudaStream_t st) { scale_cols(in, nullptr, out, M, st); }
 
 // out[b, h, w, :] = in[b, min(h, Hin-1), min(w, Win-1), :]: replicate padding on the right / bottom when the output
 // grid is larger (inference.py:40-43), a crop to the top-left corner when it is smaller (`[:, :, :h, :w]`).
 __global__ void k_regrid(View in, int Hin, int Win, View out, int Hout, int Wout, int B, int C8) {
+  pdl_prologue_done();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * Hout * Wout * C8) return;
   int c = (int)(idx % C8) * 8;
@@ -244,10 +262,11 @@ __global__ void k_regrid(View in, int Hin, int Win, View out, int Hout, int Wout
 void regrid(View in, int Hin, int Win, View out, int Hout, int Wout, int B, cudaStream_t st) {
   int C8 = (in.C + 7) / 8;   // a ragged tail stays inside the last 16-column block
   long long n = (long long)B * Hout * Wout * C8;
-  (note_launch(), k_regrid)<<<cdiv(n, 256), 256, 0, st>>>(in, Hin, Win, out, Hout, Wout, B, C8);
+  launch(k_regrid, cdiv(n, 256), 256, 0, st, in, Hin, Win, out, Hout, Wout, B, C8);
 }
 
 __global__ void k_finite_check(View v, long long M, int C8, int* flag) {
+  pdl_prologue_done();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * C8) return;
   long long m = idx / C8;
@@ -264,7 +283,7 @@ __global__ void k_finite_check(View v, long long M, int C8, int* flag) {
 }
 void finite_check(View v, long long M, int* flag, cudaStream_t st) {
   int C8 = v.C / 8;
-  (note_launch(), k_finite_check)<<<cdiv(M * C8, 256), 256, 0, st>>>(v, M, C8, flag);
+  launch(k_finite_check, cdiv(M * C8, 256), 256, 0, st, v, M, C8, flag);
 }
 
 // ------------------------------------------------------------------ depthwise 3x3 (layers.py:56)
@@ -283,6 +302,7 @@ template <bool kF32In>
 __global__ void __launch_bounds__(512)
 k_dwconv3x3(View in, const float* __restrict__ in32, int ld32, const float* __restrict__ w9c,
             const float* __restrict__ bias, View out, int B, int H, int W, int C8, int WG, int TR) {
+  pdl_prologue_done();
   const int cg = (int)threadIdx.x % C8;
   const int pos = (int)threadIdx.x / C8;
   const int WT = (WG + kDwTP - 1) / kDwTP, HT = (H + TR - 1) / TR;
@@ -371,8 +391,7 @@ void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, in
   const int C8 = in.C / 8;
   const int WG = (W + kDwPix - 1) / kDwPix;
   const int TR = dw_tile_rows(C8);
-  note_launch();
-  k_dwconv3x3<false><<<dw_grid(B, H, WG, TR), C8 * kDwTP * TR, 0, st>>>(in, nullptr, 0, w9c, bias, out, B, H, W, C8, WG, TR);
+  launch(k_dwconv3x3<false>, dw_grid(B, H, WG, TR), C8 * kDwTP * TR, 0, st, in, (const float*)nullptr, 0, w9c, bias, out, B, H, W, C8, WG, TR);
 }
 // (Tried and dropped: the same taps from a shared-memory tile filled by cp.async.bulk -- (4 + 2) row segments of
 // 10 pixels x C floats on one mbarrier, 2 CTAs of 256 threads per SM: 35 us against 29 us at 160x240x256.  ncu on
@@ -386,13 +405,13 @@ void dwconv3x3_f32(const float* in, int ld, const float* w9c, const float* bias,
   const int C8 = out.C / 8;
   const int WG = (W + kDwPix - 1) / kDwPix;
   const int TR = dw_tile_rows(C8);
-  note_launch();
-  k_dwconv3x3<true><<<dw_grid(B, H, WG, TR), C8 * kDwTP * TR, 0, st>>>(out, in, ld, w9c, bias, out, B, H, W, C8, WG, TR);
+  launch(k_dwconv3x3<true>, dw_grid(B, H, WG, TR), C8 * kDwTP * TR, 0, st, out, in, ld, w9c, bias, out, B, H, W, C8, WG, TR);
 }
 
 // ------------------------------------------------------------------ im2col (k x k, stride, pad)
 __global__ void k_im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, int Ho,
                          int Wo, int tap_stride, int col_off, int C8) {
+  pdl_prologue_done();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long Mo = (long long)B * Ho * Wo;
   int taps = k * k;
@@ -419,7 +438,7 @@ void im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, 
             int tap_stride, int col_off, cudaStream_t st) {
   int C8 = in.C / 8;
   long long n = (long long)B * Ho * Wo * k * k * C8;
-  (note_launch(), k_im2col)<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, H, W, k, stride, pad, Ho, Wo, tap_stride,
+  launch(k_im2col, cdiv(n, 256), 256, 0, st, in, out, B, H, W, k, stride, pad, Ho, Wo, tap_stride,
                                          col_off, C8);
 }
 
@@ -429,6 +448,7 @@ void im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, 
 // thread holds both members of every chunk-add pair.  Validation backend + odd shapes.
 __global__ void __launch_bounds__(256) k_gemm_simt(View a, const h16* __restrict__ wp, long long wps,
                                                    int Kld, int K, long long M, Epi e) {
+  pdl_prologue_done();
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -477,7 +497,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(View a, const h16* __restrict
 }
 void gemm_simt(View a, const GemmW& w, const Epi& e, long long M, cudaStream_t st) {
   dim3 grid(cdiv(M, 64), w.Npad / 64);
-  (note_launch(), k_gemm_simt)<<<grid, 256, 0, st>>>(a, w.w, (long long)w.Npad * w.Kld, w.Kld, w.K, M, e);
+  launch(k_gemm_simt, grid, 256, 0, st, a, w.w, (long long)w.Npad * w.Kld, w.Kld, w.K, M, e);
 }
 
 // ------------------------------------------------------------------ block reduction helper
@@ -542,13 +562,14 @@ __device__ __forceinline__ float bits_refactor(float s, float sigma) {
 
 __global__ void k_gaussian_bits(const float* __restrict__ sym, const float* __restrict__ sigma,
                                 float* __restrict__ bits, long long n, int formula) {
+  pdl_prologue_done();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   bits[i] = formula ? bits_refactor(sym[i], sigma[i]) : bits_old(sym[i], sigma[i]);
 }
 void gaussian_bits(const float* sym, const float* sigma, float* bits, long long n, int formula,
                    cudaStream_t st) {
-  (note_launch(), k_gaussian_bits)<<<cdiv(n, 256), 256, 0, st>>>(sym, sigma, bits, n, formula);
+  launch(k_gaussian_bits, cdiv(n, 256), 256, 0, st, sym, sigma, bits, n, formula);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -563,6 +584,7 @@ __device__ __forceinline__ int prior_owner(int scheme, int h, int w, int c, int 
 
 // One checkerboard step of compress_prior_2x / _4x (models/common_model.py:81-90,121-149,188-248)
 __global__ void k_prior_step(PriorArgs a) {
+  pdl_prologue_done();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long M = (long long)a.B * a.H * a.W;
   if (idx >= M * a.C) return;
@@ -593,10 +615,11 @@ __global__ void k_prior_step(PriorArgs a) {
 }
 void prior_step(const PriorArgs& a, cudaStream_t st) {
   long long n = (long long)a.B * a.H * a.W * a.C;
-  (note_launch(), k_prior_step)<<<cdiv(n, 256), 256, 0, st>>>(a);
+  launch(k_prior_step, cdiv(n, 256), 256, 0, st, a);
 }
 
 __global__ void k_prior_finish(PriorArgs a, View y_hat, int formula, double* bits_acc) {
+  pdl_prologue_done();
   long long per = (long long)a.H * a.W * a.C;
   int b = blockIdx.y;
   double local = 0.0;
@@ -620,7 +643,7 @@ void prior_finish(const PriorArgs& a, View y_hat, int formula, double* bits_acc,
   unsigned gx = cdiv(per, 256 * 4);
   if (gx < 1) gx = 1;
   dim3 grid(gx, a.B);
-  (note_launch(), k_prior_finish)<<<grid, 256, 0, st>>>(a, y_hat, formula, bits_acc);
+  launch(k_prior_finish, grid, 256, 0, st, a, y_hat, formula, bits_acc);
 }
 
 // Bitparm chain (entropy_models.py:84-106) -> sigmoid (:139-150)
@@ -636,6 +659,7 @@ __device__ __forceinline__ float bitparm_cdf(float v, const BitparmRow& t, int c
 }
 __global__ void k_round_z_bits(View z, View z_hat, long long per, int C, BitparmRow t,
                                double* bits_acc) {
+  pdl_prologue_done();
   int b = blockIdx.y;
   double local = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per;
@@ -658,10 +682,11 @@ void round_z_bits(View z, View z_hat, int B, int HW, int C, BitparmRow t, double
   unsigned gx = cdiv(per, 256 * 4);
   if (gx < 1) gx = 1;
   dim3 grid(gx, B);
-  (note_launch(), k_round_z_bits)<<<grid, 256, 0, st>>>(z, z_hat, per, C, t, bits_acc);
+  launch(k_round_z_bits, grid, 256, 0, st, z, z_hat, per, C, t, bits_acc);
 }
 
 __global__ void k_finalize_bpp(const double* by, const double* bz, float* bpp3, int B, float pixels) {
+  pdl_prologue_done();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float y = (float)by[b] / pixels, z = (float)bz[b] / pixels;
@@ -670,11 +695,12 @@ __global__ void k_finalize_bpp(const double* by, const double* bz, float* bpp3, 
   bpp3[3 * b + 2] = z;
 }
 void finalize_bpp(const double* by, const double* bz, float* bpp3, int B, int pixels, cudaStream_t st) {
-  (note_launch(), k_finalize_bpp)<<<cdiv(B, 64), 64, 0, st>>>(by, bz, bpp3, B, (float)pixels);
+  launch(k_finalize_bpp, cdiv(B, 64), 64, 0, st, by, bz, bpp3, B, (float)pixels);
 }
 
 // ------------------------------------------------------------------ mask conditioning
 __global__ void k_film(View y, View gb, View out, long long M, int C) {
+  pdl_prologue_done();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int C8 = C / 8;
   if (idx >= M * C8) return;
@@ -689,12 +715,13 @@ __global__ void k_film(View y, View gb, View out, long long M, int C) {
   st3x8(out, m, c, v);
 }
 void film(View y, View gb, View out, long long M, int C, cudaStream_t st) {
-  (note_launch(), k_film)<<<cdiv(M * (C / 8), 256), 256, 0, st>>>(y, gb, out, M, C);
+  launch(k_film, cdiv(M * (C / 8), 256), 256, 0, st, y, gb, out, M, C);
 }
 
 // F.adaptive_avg_pool2d to (H/16, W/16) + clamp(0,1)  (seg_video_model_fast.py:306-307)
 __global__ void k_avgpool16_clamp(const float* __restrict__ mask, float* __restrict__ out, int B,
                                   int H, int W) {
+  pdl_prologue_done();
   int Wo = W / 16, Ho = H / 16;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * Ho * Wo) return;
@@ -714,7 +741,7 @@ __global__ void k_avgpool16_clamp(const float* __restrict__ mask, float* __restr
 }
 void avgpool16_clamp(const float* mask, float* out, int B, int H, int W, cudaStream_t st) {
   long long n = (long long)B * (H / 16) * (W / 16);
-  (note_launch(), k_avgpool16_clamp)<<<cdiv(n, 128), 128, 0, st>>>(mask, out, B, H, W);
+  launch(k_avgpool16_clamp, cdiv(n, 128), 128, 0, st, mask, out, B, H, W);
 }
 
 // MaskFiLM: 3x3 (1->16) + ReLU + 1x1 (16->2C), then hyper_in = y*(1+gamma)+beta
@@ -725,6 +752,7 @@ __global__ void k_maskfilm_apply(const float* __restrict__ m, View y, View out,
                                  const float* __restrict__ w0, const float* __restrict__ b0,
                                  const float* __restrict__ w2, const float* __restrict__ b2, int H,
                                  int W, int C, int Hm, int Wm) {
+  pdl_prologue_done();
   __shared__ float hid[16];
   long long pix = blockIdx.x;
   int w = (int)(pix % W), h = (int)((pix / W) % H);
@@ -756,13 +784,14 @@ __global__ void k_maskfilm_apply(const float* __restrict__ m, View y, View out,
 }
 void maskfilm_apply(const float* m, View y, View out, const float* w0, const float* b0,
                     const float* w2, const float* b2, int B, int H, int W, int C, int Hm, int Wm, cudaStream_t st) {
-  (note_launch(), k_maskfilm_apply)<<<(unsigned)((long long)B * H * W), 128, 0, st>>>(m, y, out, w0, b0, w2, b2, H, W, C,
+  launch(k_maskfilm_apply, (unsigned)((long long)B * H * W), 128, 0, st, m, y, out, w0, b0, w2, b2, H, W, C,
                                                                                     Hm, Wm);
 }
 
 // F.interpolate(bilinear, align_corners=False) by exactly 1/8 and 8 (mask_predictor.py:35,44)
 __global__ void k_bilinear_down8(const float* __restrict__ in, float* __restrict__ out, int B, int H,
                                  int W) {
+  pdl_prologue_done();
   int Ho = H / 8, Wo = W / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * Ho * Wo) return;
@@ -774,10 +803,11 @@ __global__ void k_bilinear_down8(const float* __restrict__ in, float* __restrict
 }
 void bilinear_down8(const float* in, float* out, int B, int H, int W, cudaStream_t st) {
   long long n = (long long)B * (H / 8) * (W / 8);
-  (note_launch(), k_bilinear_down8)<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, H, W);
+  launch(k_bilinear_down8, cdiv(n, 256), 256, 0, st, in, out, B, H, W);
 }
 __global__ void k_bilinear_up8(const float* __restrict__ in, float* __restrict__ out, int B, int h,
                                int w) {
+  pdl_prologue_done();
   int Ho = h * 8, Wo = w * 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * Ho * Wo) return;
@@ -795,11 +825,12 @@ __global__ void k_bilinear_up8(const float* __restrict__ in, float* __restrict__
 }
 void bilinear_up8(const float* in, float* out, int B, int h, int w, cudaStream_t st) {
   long long n = (long long)B * h * 8 * w * 8;
-  (note_launch(), k_bilinear_up8)<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, h, w);
+  launch(k_bilinear_up8, cdiv(n, 256), 256, 0, st, in, out, B, h, w);
 }
 
 __global__ void k_conv3x3_c1(const float* __restrict__ in, const float* __restrict__ wt,
                              const float* __restrict__ bias, View out, int B, int H, int W, int C) {
+  pdl_prologue_done();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long M = (long long)B * H * W;
   if (idx >= M * C) return;
@@ -819,11 +850,12 @@ __global__ void k_conv3x3_c1(const float* __restrict__ in, const float* __restri
 void conv3x3_c1(const float* in, const float* w, const float* b, View out, int B, int h, int w_,
                 int C, cudaStream_t st) {
   long long n = (long long)B * h * w_ * C;
-  (note_launch(), k_conv3x3_c1)<<<cdiv(n, 256), 256, 0, st>>>(in, w, b, out, B, h, w_, C);
+  launch(k_conv3x3_c1, cdiv(n, 256), 256, 0, st, in, w, b, out, B, h, w_, C);
 }
 
 __global__ void k_conv1x1_to1(View in, const float* __restrict__ wt, const float* __restrict__ bias,
                               float* __restrict__ out, long long M, int K) {
+  pdl_prologue_done();
   long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -834,13 +866,14 @@ __global__ void k_conv1x1_to1(View in, const float* __restrict__ wt, const float
 }
 void conv1x1_to1(View in, const float* w, const float* b, float* out, long long M, int K,
                  cudaStream_t st) {
-  (note_launch(), k_conv1x1_to1)<<<cdiv(M * 32, 256), 256, 0, st>>>(in, w, b, out, M, K);
+  launch(k_conv1x1_to1, cdiv(M * 32, 256), 256, 0, st, in, w, b, out, M, K);
 }
 
 // ------------------------------------------------------------------ caller-side statistics
 // trainer_seg_video_model.py:655-660 (_roi_mse), :904-934 (mse), bits from bpp.
 __global__ void k_frame_stats(double* stats, const float* __restrict__ xh, const float* __restrict__ x,
                               const float* __restrict__ mask, long long HW, long long n) {
+  pdl_prologue_done();
   double se = 0.0, rse = 0.0, rn = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -861,6 +894,7 @@ __global__ void k_frame_stats(double* stats, const float* __restrict__ xh, const
   }
 }
 __global__ void k_frame_stats_bits(double* stats, const float* bpp3, int B, double pixels, double n) {
+  pdl_prologue_done();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (bpp3) {
       double by = 0, bz = 0;
@@ -875,8 +909,8 @@ void frame_stats(double* stats7, const float* x_hat, const float* x, const float
                  const float* bpp3, int B, int H, int W, cudaStream_t st) {
   long long HW = (long long)H * W, n = (long long)B * 3 * HW;
   unsigned grid = (unsigned)min((long long)num_sms() * 8, (long long)cdiv(n, 256));
-  (note_launch(), k_frame_stats)<<<grid, 256, 0, st>>>(stats7, x_hat, x, mask, HW, n);
-  (note_launch(), k_frame_stats_bits)<<<1, 32, 0, st>>>(stats7, bpp3, B, (double)HW, (double)n);
+  launch(k_frame_stats, grid, 256, 0, st, stats7, x_hat, x, mask, HW, n);
+  launch(k_frame_stats_bits, 1, 32, 0, st, stats7, bpp3, B, (double)HW, (double)n);
 }
 
 }  // namespace dmc

@@ -1,12 +1,33 @@
 // Host-side launchers of every kernel of the engine.  All launch asynchronously on `st`.
 #pragma once
 #include "common.cuh"
+#include <string.h>
 
 namespace dmc {
 
 int num_sms();
 void note_launch();            // every kernel launch of the library is counted
 long long launch_count();
+bool pdl_enabled();            // DMC_PDL=0 turns programmatic dependent launch off (A/B runs)
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_prologue_done in common.cuh).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  note_launch();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---------------- weights ----------------
 // Packed contraction weight: split planes [2][Npad][Kld] fp16 (hi, 2^11-scaled lo), K index = (kh*KW + kw)*Cin + ci.
