@@ -197,11 +197,14 @@ __device__ __forceinline__ void epi_store(const Epi& e, long long m, int n, floa
   if (e.out.p) st3(e.out, drow, dcol, v);
 }
 
-// ---- programmatic dependent launch.  Every kernel of the frame is launched with
+// ---- programmatic dependent launch (opt-in, DMC_PDL=1).  Every kernel of the frame is then launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_prologue_done(): its CTAs are scheduled
 // as soon as the previous kernel's CTAs leave their SMs (that kernel released its dependents at its own start),
 // run their prologue (barrier initialisation, TMEM allocation, index arithmetic), and block in griddepcontrol.wait
 // until the previous grid has completed and its writes are visible.  No global memory is touched before the wait.
+// Without the attribute both instructions are no-ops.  Measured on the 1920x1280 frame (power-capped box, three
+// alternating runs each): 9 225 k clocks per frame with, 9 229 k without -- the persistent kernels hold every SM
+// until their last tile, there is little tail to overlap -- so it stays off by default.
 __device__ __forceinline__ void pdl_prologue_done() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -16,8 +16,8 @@ void note_launch() { ++g_launches; }
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("DMC_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    const char* e = getenv("DMC_PDL");       // opt-in: measured neutral on the 1920x1280 frame (9 225 vs 9 229 k clocks)
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }

@@ -8,7 +8,7 @@ namespace dmc {
 int num_sms();
 void note_launch();            // every kernel launch of the library is counted
 long long launch_count();
-bool pdl_enabled();            // DMC_PDL=0 turns programmatic dependent launch off (A/B runs)
+bool pdl_enabled();            // DMC_PDL=1 turns programmatic dependent launch on (measured neutral: off by default)
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_prologue_done in common.cuh).
 template <typename... KArgs, typename... Args>
