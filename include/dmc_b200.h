@@ -97,8 +97,9 @@ int dmc_finalize_weights(dmc_engine* e, void* stream);
  * after_i == 0.  Outputs: x_hat (B,3,H,W) in [0,1]; feature (B,256,H/8,W/8);
  * bpp3 = B x {bpp, bpp_y, bpp_z}; mask_pred (B,1,H,W) or NULL -- written only by
  * mask_prop with after_i == 0 (the predictor's logits); finite_flag (int32, device)
- * or NULL: set to 1 if any latent/feature was non-finite (the reference's
- * _finite_check, seg_video_model_fast.py:152-156, without its host syncs). */
+ * or NULL: set to 1 if any latent/feature was non-finite or hit the fp16 range limit of the
+ * split storage format (|x| >= 65504 saturates) -- the reference's _finite_check,
+ * seg_video_model_fast.py:152-156, without its host syncs. */
 int dmc_forward(dmc_engine* e, const float* x, const float* mask, const float* dpb_frame,
                 const float* dpb_feature, int qp, int after_i, float* x_hat, float* feature,
                 float* bpp3, float* mask_pred, int32_t* finite_flag, void* stream);
