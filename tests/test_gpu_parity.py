@@ -322,38 +322,64 @@ def test_full_size_properties():
     assert abs(float(r1["bpp"] - r1b["bpp"])) <= 1e-6 * float(r1["bpp"])
 
 
-def test_full_size_parity_on_identical_inputs():
-    """1920x1280 (BASELINE.json config 2), `performance`: the intra frame and two P frames (after_i True / False)
+_FULL = {}
+
+
+def _full_size_intra():
+    """The 1920x1280 clip and its intra frame through the oracle and the CUDA path (computed once per session)."""
+    if not _FULL:
+        H, W = 1280, 1920
+        frames, masks = D.clips.synthetic_clip(3, 1, 3, H, W)
+        torch.manual_seed(gc.SEED_I)
+        mi = D.DMCI().eval()
+        sd_i = sd_of(mi)
+        mi = mi.cuda()
+        mi.engine_flags = capi.FLAG_KEEP_TAPS
+        with torch.no_grad():
+            ti = {}
+            o = O.dmci_forward(sd_i, frames[:, 0], 32, ti)
+            c = mi(frames[:, 0].cuda(), 32)
+            y_c = mi.get_tap("y_q", frames[:, 0].cuda()).cpu()
+        _FULL.update(frames=frames, masks=masks, o=o, c={k: (v.cpu() if torch.is_tensor(v) else v) for k, v in c.items()
+                                                         if k != "dpb"},
+                     x_hat_c=c["dpb"]["frame"].cpu(), y_o=ti["y_q"], y_c=y_c)
+        del mi
+        torch.cuda.empty_cache()
+    return _FULL
+
+
+def test_full_size_intra_parity():
+    """1920x1280 intra frame (DMCI) against the oracle: 2 457 600 symbols, gate >= 99.99 %."""
+    f = _full_size_intra()
+    frac, bad = symbol_match(f["y_c"], f["y_o"])
+    assert frac >= SYMBOL_MATCH_MIN, ("intra", frac, bad)
+    assert rel_err(f["c"]["bpp"], f["o"]["bpp"]) <= BPP_REL_TOL
+    po, _ = gc.metrics(f["o"]["dpb"]["frame"], f["frames"][:, 0], None)
+    pc, _ = gc.metrics(f["x_hat_c"], f["frames"][:, 0], None)
+    assert abs(po - pc) <= PSNR_TOL_DB
+
+
+@pytest.mark.parametrize("variant", gc.VARIANTS)
+def test_full_size_parity_on_identical_inputs(variant):
+    """1920x1280 (the size of BASELINE.json configs 2-5), every variant: two P frames (after_i True / False)
     against the oracle, EVERY call on identical inputs (the CUDA path gets the oracle's dpb).  This is the size
     the gates are quoted on: >= 99.99 % symbols = at most 122 of 1 228 800 per P frame.  (Free-running, the
     handful of intra-frame flips -- well inside the gate -- are amplified chaotically by the feature recurrence,
     for the fp32-FMA backend as well: tests/diag/symbol_counts.py)"""
-    H, W = 1280, 1920
-    frames, masks = D.clips.synthetic_clip(3, 1, 3, H, W)
-    torch.manual_seed(gc.SEED_I)
-    mi = D.DMCI().eval()
+    f = _full_size_intra()
+    frames, masks = f["frames"], f["masks"]
     torch.manual_seed(gc.SEED_P)
-    mp = D.build_p_model("performance").eval()
-    sd_i, sd_p = sd_of(mi), sd_of(mp)
-    mi, mp = mi.cuda(), mp.cuda()
-    mi.engine_flags = mp.engine_flags = capi.FLAG_KEEP_TAPS
-    fr, mk = frames.cuda(), masks.cuda()
+    mp = D.build_p_model(variant).eval()
+    sd_p = sd_of(mp)
+    mp = mp.cuda()
+    mp.engine_flags = capi.FLAG_KEEP_TAPS
     with torch.no_grad():
-        ti = {}
-        o = O.dmci_forward(sd_i, frames[:, 0], 32, ti)
-        c = mi(fr[:, 0], 32)
-        frac, bad = symbol_match(mi.get_tap("y_q", fr[:, 0]).cpu(), ti["y_q"])
-        assert frac >= SYMBOL_MATCH_MIN, ("intra", frac, bad)
-        assert rel_err(c["bpp"].cpu(), o["bpp"]) <= BPP_REL_TOL
-        po, _ = gc.metrics(o["dpb"]["frame"], frames[:, 0], None)
-        pc, _ = gc.metrics(c["dpb"]["frame"].cpu(), frames[:, 0], None)
-        assert abs(po - pc) <= PSNR_TOL_DB
-        dpb_o = o["dpb"]
+        dpb_o = f["o"]["dpb"]
         for t in (1, 2):
             qp = mp.shift_qp(32, O.INDEX_MAP[t % 8])
-            xo = torch.cat([frames[:, t], masks[:, t]], 1)
+            xo = frames[:, t] if variant == "old" else torch.cat([frames[:, t], masks[:, t]], 1)
             to = {}
-            o = O.dmc_forward(sd_p, "performance", xo, qp, dpb_o, after_i=(t == 1), taps=to)
+            o = O.dmc_forward(sd_p, variant, xo, qp, dpb_o, after_i=(t == 1), taps=to)
             c = mp(xo.cuda(), qp, _to_cuda(dpb_o), after_i=(t == 1))
             frac, bad = symbol_match(mp.get_tap("y_q", xo.cuda()).cpu(), to["y_q"])
             assert frac >= SYMBOL_MATCH_MIN, (t, "y symbols", frac, bad)
@@ -364,7 +390,12 @@ def test_full_size_parity_on_identical_inputs():
             po, ro = gc.metrics(o["dpb"]["frame"], frames[:, t], masks[:, t])
             pc, rc = gc.metrics(c["dpb"]["frame"].cpu(), frames[:, t], masks[:, t])
             assert abs(po - pc) <= PSNR_TOL_DB and abs(ro - rc) <= PSNR_TOL_DB, (t, po, pc, ro, rc)
+            if o.get("mask_pred") is not None:
+                mo, mc = o["mask_pred"], c["mask_pred"].cpu()
+                assert float((mo - mc).abs().max()) <= 1e-4 * max(1.0, float(mo.abs().max()))
             dpb_o = o["dpb"]
+    del mp
+    torch.cuda.empty_cache()
 
 
 def test_recon_single_term_against_split_product():
