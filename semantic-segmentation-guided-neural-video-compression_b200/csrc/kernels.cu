@@ -396,7 +396,9 @@ void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, in
 // (Tried and dropped: the same taps from a shared-memory tile filled by cp.async.bulk -- (4 + 2) row segments of
 // 10 pixels x C floats on one mbarrier, 2 CTAs of 256 threads per SM: 35 us against 29 us at 160x240x256.  ncu on
 // the register version: issue slots 40 % busy, L1 64 %, DRAM 2.6 TB/s -- it is bound by L1 transactions and
-// instruction count, not by latency.  CTA tiles of 2-8 image rows x 8 pixels instead of one row change nothing.)
+// instruction count, not by latency.  CTA tiles of 2-8 image rows x 8 pixels instead of one row change nothing.
+// A persistent version of the shared-memory kernel -- one CTA per SM, 16 warps, two 108 KB tile buffers filled one
+// tile ahead, taps in shared memory -- is no better either: 32.9 us, +4 % clocks on the frame.)
 // (A mapping with one thread per 16-channel block and consecutive threads along the image row makes the blocked
 // stores contiguous but the fp32 reads strided by a whole pixel: 78 us instead of 33 us at 160x240x256.  The
 // channel-fastest mapping below keeps every 16-byte store inside a fully written 32-byte sector.)
