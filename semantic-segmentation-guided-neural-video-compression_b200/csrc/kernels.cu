@@ -301,7 +301,7 @@ constexpr int kDwTP = 2;
 template <bool kF32In>
 __global__ void __launch_bounds__(512)
 k_dwconv3x3(View in, const float* __restrict__ in32, int ld32, const float* __restrict__ w9c,
-            const float* __restrict__ bias, View out, int B, int H, int W, int C8, int WG, int TR) {
+            const float* __restrict__ bias, View out, int B, int H, int W, int C8, int WG, int TR, int dbg) {
   pdl_prologue_done();
   const int cg = (int)threadIdx.x % C8;
   const int pos = (int)threadIdx.x / C8;
@@ -330,7 +330,7 @@ k_dwconv3x3(View in, const float* __restrict__ in32, int ld32, const float* __re
 #pragma unroll
     for (int j = 0; j < kDwPix + 2; ++j) {
       const int wi = w0 + j - 1;
-      if ((unsigned)wi < (unsigned)W) {
+      if ((unsigned)wi < (unsigned)W && !(dbg & 2)) {
         if (kF32In) {
           const float4* q = reinterpret_cast<const float4*>(in32 + (row + wi) * ld32 + c);
           const float4 a = q[0], d = q[1];
@@ -367,7 +367,7 @@ k_dwconv3x3(View in, const float* __restrict__ in32, int ld32, const float* __re
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = add_rn(acc[p][i], bv[i]);
-    st3x8(out, (b * H + h) * W + w0 + p, c, o);
+    if (!(dbg & 1) || o[0] == 123.456f) st3x8(out, (b * H + h) * W + w0 + p, c, o);
   }
 }
 // rows per CTA tile: as many as keep the CTA at <= 512 threads (C8 * kDwTP threads per row), at most 8
@@ -383,6 +383,13 @@ static int dw_tile_rows(int C8) {
   if (tr < 1) tr = 1;
   return tr;
 }
+// probe switch of the one-row kernel (DMC_DW_DBG: 1 no stores, 2 no input loads): 28.8 / 22.7 / 18.6 / 14.5 us at
+// 160x240x256 for 0 / 1 / 2 / 3 -- half of its time is instruction issue, which is what the strip kernel removes
+static int dw_dbg() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DMC_DW_DBG"); v = e ? atoi(e) : 0; }
+  return v;
+}
 static unsigned dw_grid(int B, int H, int WG, int TR) {
   return (unsigned)((long long)B * ((H + TR - 1) / TR) * ((WG + kDwTP - 1) / kDwTP));
 }
@@ -391,8 +398,90 @@ void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, in
   const int C8 = in.C / 8;
   const int WG = (W + kDwPix - 1) / kDwPix;
   const int TR = dw_tile_rows(C8);
-  launch(k_dwconv3x3<false>, dw_grid(B, H, WG, TR), C8 * kDwTP * TR, 0, st, in, (const float*)nullptr, 0, w9c, bias, out, B, H, W, C8, WG, TR);
+  launch(k_dwconv3x3<false>, dw_grid(B, H, WG, TR), C8 * kDwTP * TR, 0, st, in, (const float*)nullptr, 0, w9c, bias, out, B, H, W, C8, WG, TR, dw_dbg());
 }
+// Strip version for fp32 input rows: a thread owns 4 channels x 4 adjacent pixels and walks `strip` image rows
+// downwards with the three input rows it needs in registers (a rolling window: every input row is loaded once per
+// strip, not once per output row), the nine taps of its channels loaded once.  The kernel above spends 34
+// instructions per output -- 18 tap loads and 36 input loads per 32 outputs, predicates, zero fills -- and half of
+// its time is there (14.5 of 28.8 us at 160x240x256 with loads and stores switched off); this one spends ~16.
+// Same order of the nine FMAs per output as above, so the results are bit-identical.
+struct DwRow { float v[kDwPix + 2][4]; };
+__device__ __forceinline__ void dw_load_row(DwRow& r, const float* __restrict__ in32, int ld, long long rowbase, int h,
+                                            int H, int w0, int W, int c) {
+  if ((unsigned)h >= (unsigned)H) {
+#pragma unroll
+    for (int j = 0; j < kDwPix + 2; ++j) { r.v[j][0] = r.v[j][1] = r.v[j][2] = r.v[j][3] = 0.0f; }
+    return;
+  }
+  const float* q = in32 + ((rowbase + h) * W + w0 - 1) * ld + c;
+#pragma unroll
+  for (int j = 0; j < kDwPix + 2; ++j) {
+    const int wi = w0 + j - 1;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)wi < (unsigned)W) a = *reinterpret_cast<const float4*>(q + (long long)j * ld);
+    r.v[j][0] = a.x; r.v[j][1] = a.y; r.v[j][2] = a.z; r.v[j][3] = a.w;
+  }
+}
+__global__ void __launch_bounds__(128)
+k_dwconv3x3_strip(const float* __restrict__ in32, int ld, const float* __restrict__ w9c,
+                  const float* __restrict__ bias, View out, int B, int H, int W, int C4, int WG, int HS, int strip) {
+  pdl_prologue_done();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HS * WG * C4) return;
+  const int c4 = (int)(idx % C4);
+  long long t = idx / C4;
+  const int wg = (int)(t % WG);
+  t /= WG;
+  const int hs = (int)(t % HS);
+  const long long b = t / HS;
+  const int c = c4 * 4, C = C4 * 4, w0 = wg * kDwPix;
+  const int h0 = hs * strip, h1 = min(h0 + strip, H);
+  float wt[9][4];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + k * C + c));
+    wt[k][0] = a.x; wt[k][1] = a.y; wt[k][2] = a.z; wt[k][3] = a.w;
+  }
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+  const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+  const long long rowbase = b * H;
+  // output row h from rows (top, mid, bot) = (h-1, h, h+1)
+  auto emit = [&](const DwRow& top, const DwRow& mid, const DwRow& bot, int h) {
+    const DwRow* rows[3] = {&top, &mid, &bot};
+#pragma unroll
+    for (int p = 0; p < kDwPix; ++p) {
+      if (w0 + p >= W) break;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fmaf(rows[dy]->v[p + dx][i], wt[dy * 3 + dx][i], acc[i]);
+      uint32_t hi0, lo0, hi1, lo1;
+      split2x2(add_rn(acc[0], bv[0]), add_rn(acc[1], bv[1]), hi0, lo0);
+      split2x2(add_rn(acc[2], bv[2]), add_rn(acc[3], bv[3]), hi1, lo1);
+      h16* q = out.p + s3_unit_offset(out, (rowbase + h) * W + w0 + p, c) + (c & 4);
+      *reinterpret_cast<uint2*>(q) = make_uint2(hi0, hi1);
+      *reinterpret_cast<uint2*>(q + out.ps) = make_uint2(lo0, lo1);
+    }
+  };
+  DwRow r0, r1, r2;
+  dw_load_row(r0, in32, ld, rowbase, h0 - 1, H, w0, W, c);
+  dw_load_row(r1, in32, ld, rowbase, h0, H, w0, W, c);
+  for (int h = h0; h < h1; h += 3) {
+    dw_load_row(r2, in32, ld, rowbase, h + 1, H, w0, W, c);
+    emit(r0, r1, r2, h);
+    if (h + 1 >= h1) break;
+    dw_load_row(r0, in32, ld, rowbase, h + 2, H, w0, W, c);
+    emit(r1, r2, r0, h + 1);
+    if (h + 2 >= h1) break;
+    dw_load_row(r1, in32, ld, rowbase, h + 3, H, w0, W, c);
+    emit(r2, r0, r1, h + 2);
+  }
+}
+
 // (Tried and dropped: the same taps from a shared-memory tile filled by cp.async.bulk -- (4 + 2) row segments of
 // 10 pixels x C floats on one mbarrier, 2 CTAs of 256 threads per SM: 35 us against 29 us at 160x240x256.  ncu on
 // the register version: issue slots 40 % busy, L1 64 %, DRAM 2.6 TB/s -- it is bound by L1 transactions and
@@ -404,10 +493,30 @@ void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, in
 // channel-fastest mapping below keeps every 16-byte store inside a fully written 32-byte sector.)
 void dwconv3x3_f32(const float* in, int ld, const float* w9c, const float* bias, View out, int B, int H, int W,
                    cudaStream_t st) {
-  const int C8 = out.C / 8;
+  static int mode = -1;
+  if (mode < 0) {
+    const char* v = getenv("DMC_DW_STRIP");       // DMC_DW_STRIP=0: the one-row version (A/B runs)
+    mode = (v && v[0] == '0') ? 0 : 1;
+  }
   const int WG = (W + kDwPix - 1) / kDwPix;
+  if (mode == 1 && ld % 4 == 0) {
+    // strips as long as possible while the launch still fills the machine in one wave (157 registers: three
+    // 128-thread CTAs per SM), at least 4 rows (a strip reads its rows + 2)
+    const int C4 = out.C / 4;
+    const long long warps_per_strip = ((long long)B * WG * C4 + 31) / 32;
+    long long hs_max = (long long)num_sms() * 12 / warps_per_strip;
+    if (hs_max < 1) hs_max = 1;
+    int strip = (int)((H + hs_max - 1) / hs_max);
+    if (strip < 4) strip = 4;
+    if (strip > 32) strip = 32;
+    const int HS = (H + strip - 1) / strip;
+    const long long n = (long long)B * HS * WG * C4;
+    launch(k_dwconv3x3_strip, cdiv(n, 128), 128, 0, st, in, ld, w9c, bias, out, B, H, W, C4, WG, HS, strip);
+    return;
+  }
+  const int C8 = out.C / 8;
   const int TR = dw_tile_rows(C8);
-  launch(k_dwconv3x3<true>, dw_grid(B, H, WG, TR), C8 * kDwTP * TR, 0, st, out, in, ld, w9c, bias, out, B, H, W, C8, WG, TR);
+  launch(k_dwconv3x3<true>, dw_grid(B, H, WG, TR), C8 * kDwTP * TR, 0, st, out, in, ld, w9c, bias, out, B, H, W, C8, WG, TR, dw_dbg());
 }
 
 // ------------------------------------------------------------------ im2col (k x k, stride, pad)
