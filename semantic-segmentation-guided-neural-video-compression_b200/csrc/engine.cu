@@ -371,8 +371,8 @@ struct dmc_engine {
     dmc_engine* self = this;
     auto tma_ok = [](const View& v) { return (uintptr_t)v.p % 512 == 0; };
     if (use_umma && use_s3 && gemm_s3_supports(*g, e, nsplit) && (!out || tma_ok(out->v)) &&
-        (!spec.res1 || tma_ok(spec.res1->v))) {
-      CUtensorMap* tm3[4];
+        (!spec.res1 || tma_ok(spec.res1->v)) && (!spec.res2 || tma_ok(spec.res2->v))) {
+      CUtensorMap* tm3[5];
       for (auto& t : tm3) {
         tmaps.emplace_back(new CUtensorMap());
         t = tmaps.back().get();
@@ -387,6 +387,8 @@ struct dmc_engine {
       }
       if (spec.res1 && make_tmap_s3_rows(tm3[2], spec.res1->v, e.n_out, M) != 0)
         fail("gemm residual map: %s", gemm_s3_last_error());
+      if (spec.res2 && make_tmap_s3_rows(tm3[4], spec.res2->v, e.n_out, M) != 0)
+        fail("gemm second residual map: %s", gemm_s3_last_error());
       // consecutive qualifying contractions over the same rows become stages of one chain launch
       if (!pend.empty() && (pend_M != M || (int)pend.size() >= s3_chain_max_stages() || !chain_layers)) flush_chain();
       S3StageDesc d;
@@ -396,6 +398,7 @@ struct dmc_engine {
       d.e = e;
       d.tmOut = tm3[1];
       d.tmRes = spec.res1 ? tm3[2] : nullptr;
+      d.tmRes2 = spec.res2 ? tm3[4] : nullptr;
       d.K = g->K;
       d.nsplit = nsplit;
       d.scale_table = table;

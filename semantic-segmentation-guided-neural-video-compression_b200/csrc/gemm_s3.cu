@@ -387,11 +387,11 @@ __device__ __forceinline__ void wsilu2_fast(float& x0, float& x1) {
 }  // namespace s3
 
 
-enum { S3_PLAIN = 0, S3_WSILU = 1, S3_RES = 2, S3_PAIR = 3, S3_F32 = 4, S3_F32_WSILU = 5 };
+enum { S3_PLAIN = 0, S3_WSILU = 1, S3_RES = 2, S3_PAIR = 3, S3_F32 = 4, S3_F32_WSILU = 5, S3_RES2 = 6 };
 constexpr int kS3MaxStages = 5;
 
 struct alignas(64) S3StageDev {
-  CUtensorMap tmA, tmW, tmOut, tmRes;
+  CUtensorMap tmA, tmW, tmOut, tmRes, tmRes2;
   CUtensorMap tmA64;     // A as 32 k x 64 rows x 1 plane boxes (4-CTA clusters: halves multicast between the two pairs)
   const float* bias;
   const float* scale;
@@ -513,6 +513,7 @@ struct EpiCtx {
   uint32_t res_phase;        // bit s: parity the next residual wait on ring barrier s has to see
   int lane, quad, part;      // part: which share of the tile's columns (0 .. kS3Split-1)
   uint32_t rank;
+  uint32_t depsOk;           // shared-memory word: tiles of this CTA whose dependencies the producer warp has seen met
   bool epi_mem;
 };
 
@@ -549,13 +550,14 @@ struct StageRegs {
   const float* scale;
   const CUtensorMap* tmOut;
   const CUtensorMap* tmRes;
+  const CUtensorMap* tmRes2;
   int BN, n_out, kind;
   uint32_t need;
   bool two_acc;
 };
 __device__ __forceinline__ StageRegs s3_load_stage(const S3StageDev& S) {
   StageRegs r;
-  r.bias = S.bias; r.scale = S.scale; r.tmOut = &S.tmOut; r.tmRes = &S.tmRes;
+  r.bias = S.bias; r.scale = S.scale; r.tmOut = &S.tmOut; r.tmRes = &S.tmRes; r.tmRes2 = &S.tmRes2;
   r.BN = S.BN; r.n_out = S.n_out; r.kind = S.kind; r.need = S.need; r.two_acc = S.nterms != 1;
   return r;
 }
@@ -569,6 +571,7 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
   const int lane = x.lane;
   const bool kF32 = S.kind == S3_F32 || S.kind == S3_F32_WSILU;
   const bool kRes = S.kind == S3_RES;
+  const bool kRes2 = S.kind == S3_RES2;     // shortcut blocks: (acc + res1) + res2, layers.py:75-76
   const bool kWsilu = S.kind == S3_WSILU || S.kind == S3_PAIR || S.kind == S3_F32_WSILU;
   const bool kPair = S.kind == S3_PAIR;
   const int kKind = kPair ? S3_PAIR : S3_PLAIN;
@@ -590,6 +593,23 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
     }
     __syncwarp();
     next_res(c);
+    if (kRes2 && valid && x.epi_mem) {
+      // both staging tiles are this chunk's: the first residual lands where the result will be written, the second
+      // in the other tile (every earlier store has read its data: wait_group.read 0 above)
+      const uint32_t other = x.slot + 1 == kS3Ring ? 0u : x.slot + 1;
+      if (lane == 0) {
+        if (kS3Ring >= 3) tma_store_wait_read0();
+        // (the first residual may come from an earlier layer of this chain: the producer warp acquired its
+        // completion before this tile's MMAs could start -- pick that up, then order the TMA reads after it)
+        (void)ld_acquire_cta_shared(x.depsOk);
+        fence_proxy_async_global();
+        mbar_expect_tx(x.barRes + 8u * x.slot, kS3ChunkBytes);
+        tma_load_local(x.ringBuf + x.slot * kS3ChunkBytes, S.tmRes, dcol, row0, x.barRes + 8u * x.slot);
+        mbar_expect_tx(x.barRes + 8u * other, kS3ChunkBytes);
+        tma_load_local(x.ringBuf + other * kS3ChunkBytes, S.tmRes2, dcol, row0, x.barRes + 8u * other);
+      }
+      __syncwarp();
+    }
     EPI_T(0);
     float v[32];
     if (valid) {
@@ -637,14 +657,15 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
     EPI_T(2);
     if (!valid) continue;
     const uint32_t tileBuf = x.ringBuf + x.slot * kS3ChunkBytes;
-    if (kRes && x.epi_mem) {
-      mbar_wait(x.barRes + 8u * x.slot, (x.res_phase >> x.slot) & 1u, err, 5);
-      x.res_phase ^= 1u << x.slot;
-      const uint32_t src = tileBuf + rowOff;
+    // v += hi + lo * 2^-11 of the residual tile in staging tile `slot` (exactly join2)
+    auto add_residual = [&](uint32_t slot) {
+      mbar_wait(x.barRes + 8u * slot, (x.res_phase >> slot) & 1u, err, 5);
+      x.res_phase ^= 1u << slot;
+      const uint32_t src = x.ringBuf + slot * kS3ChunkBytes + rowOff;
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {     // hi + lo * 2^-11, exactly join2
+        for (int hf = 0; hf < 2; ++hf) {
           const uint4 qh = ld_shared_v4(src + blk * 1024 + (((uint32_t)hf << 4) ^ swz));
           const uint4 ql = ld_shared_v4(src + 2048 + blk * 1024 + (((uint32_t)hf << 4) ^ swz));
           const uint32_t uh[4] = {qh.x, qh.y, qh.z, qh.w};
@@ -657,7 +678,9 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
           }
         }
       }
-    }
+    };
+    if ((kRes || kRes2) && x.epi_mem) add_residual(x.slot);
+    if (kRes2 && x.epi_mem) add_residual(x.slot + 1 == kS3Ring ? 0u : x.slot + 1);
     EPI_T(3);
     if (S.scale) {
       const float4* sp = reinterpret_cast<const float4*>(S.scale + dcol);
@@ -930,6 +953,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     x.quad = warp & 3;                         // TMEM lane quadrant this warp may read
     x.part = ew >> 2;                          // the warps of a quadrant split the columns
     x.rank = rank;
+    x.depsOk = depsOk;
     x.epi_mem = !(p.dbg & 12);
 #ifdef DMC_EPI_TIMING
     x.timed = blockIdx.x == 0 && ew == 0;
@@ -1077,7 +1101,8 @@ static int g_s3_dbg = 0;
 void gemm_s3_set_debug(int mask) { g_s3_dbg = mask; }
 
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit) {
-  if (!w.tmap_s3 || !w.tmap_s3_hi || e.do_clamp || e.res2.p) return false;
+  if (!w.tmap_s3 || !w.tmap_s3_hi || e.do_clamp) return false;
+  if (e.res2.p && !(e.res1.p && e.out.p && !e.out_f32 && e.pack == PACK_PLAIN && e.act == ACT_NONE)) return false;
   if (w.BN % 32 || w.BN > 128 || e.n_out % 16 || e.n_out < 32) return false;
   if (e.out_f32) {                       // fp32 rows: plain layout, no residual, and not both outputs at once
     return !e.out.p && e.pack == PACK_PLAIN && !e.res1.p && (e.act == ACT_NONE || e.act == ACT_WSILU) &&
@@ -1106,6 +1131,7 @@ static int s3_kind(const Epi& e) {
   if (e.out_f32) return e.act == ACT_WSILU ? S3_F32_WSILU : S3_F32;
   if (e.pack == PACK_PAIR) return S3_PAIR;
   if (e.act == ACT_WSILU) return S3_WSILU;
+  if (e.res2.p) return S3_RES2;
   return e.res1.p ? S3_RES : S3_PLAIN;
 }
 
@@ -1178,6 +1204,7 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     memcpy(&S.tmW, d.nsplit != 1 ? d.w->tmap_s3 : d.w->tmap_s3_hi, sizeof(CUtensorMap));
     memcpy(&S.tmOut, d.tmOut, sizeof(CUtensorMap));
     memcpy(&S.tmRes, d.tmRes ? d.tmRes : d.tmOut, sizeof(CUtensorMap));
+    memcpy(&S.tmRes2, d.tmRes2 ? d.tmRes2 : d.tmOut, sizeof(CUtensorMap));
     S.bias = d.e.bias;
     S.scale = d.e.scale;
     S.kblk = d.nsplit != 1 ? 2 : s3_single_kblk();

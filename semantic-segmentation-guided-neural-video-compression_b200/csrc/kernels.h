@@ -104,6 +104,7 @@ struct S3StageDesc {
   Epi e;                      // scale is resolved at launch from scale_table / scale_C and qp
   const void* tmOut;          // make_tmap_s3_rows or make_tmap_f32_rows
   const void* tmRes;          // residual (make_tmap_s3_rows) or nullptr
+  const void* tmRes2;         // second residual (shortcut blocks) or nullptr
   int K, nsplit;
   const float* scale_table;   // (72, scale_C) per-QP table or nullptr
   int scale_C;
