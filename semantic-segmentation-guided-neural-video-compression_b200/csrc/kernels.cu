@@ -982,18 +982,27 @@ void conv1x1_to1(View in, const float* w, const float* b, float* out, long long 
 
 // ------------------------------------------------------------------ caller-side statistics
 // trainer_seg_video_model.py:655-660 (_roi_mse), :904-934 (mse), bits from bpp.
+// grid = (chunks of a plane, B * 3 planes); 4 pixels per thread and step (HW is a multiple of 4: H, W multiples of 16)
 __global__ void k_frame_stats(double* stats, const float* __restrict__ xh, const float* __restrict__ x,
                               const float* __restrict__ mask, long long HW, long long n) {
   pdl_prologue_done();
+  (void)n;
+  const long long plane = blockIdx.y;                 // b * 3 + c
+  const float4* ph = reinterpret_cast<const float4*>(xh + plane * HW);
+  const float4* px = reinterpret_cast<const float4*>(x + plane * HW);
+  const float4* pm = mask ? reinterpret_cast<const float4*>(mask + (plane / 3) * HW) : nullptr;
   double se = 0.0, rse = 0.0, rn = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4;
        i += (long long)gridDim.x * blockDim.x) {
-    float d = sub_rn(xh[i], x[i]);
-    float d2 = mul_rn(d, d);
-    se += (double)d2;
-    if (mask) {
-      long long b = i / (3 * HW);
-      if (mask[b * HW + (i % HW)] > 0.0f) { rse += (double)d2; rn += 1.0; }
+    const float4 a = ph[i], t = px[i];
+    const float d[4] = {sub_rn(a.x, t.x), sub_rn(a.y, t.y), sub_rn(a.z, t.z), sub_rn(a.w, t.w)};
+    float mv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pm) { const float4 m = pm[i]; mv[0] = m.x; mv[1] = m.y; mv[2] = m.z; mv[3] = m.w; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d2 = mul_rn(d[k], d[k]);
+      se += (double)d2;
+      if (mv[k] > 0.0f) { rse += (double)d2; rn += 1.0; }
     }
   }
   se = block_sum(se);
@@ -1019,7 +1028,10 @@ __global__ void k_frame_stats_bits(double* stats, const float* bpp3, int B, doub
 void frame_stats(double* stats7, const float* x_hat, const float* x, const float* mask,
                  const float* bpp3, int B, int H, int W, cudaStream_t st) {
   long long HW = (long long)H * W, n = (long long)B * 3 * HW;
-  unsigned grid = (unsigned)min((long long)num_sms() * 8, (long long)cdiv(n, 256));
+  // (x_hat, x and mask are fp32 NCHW, 16-byte aligned planes: HW is a multiple of 4)
+  unsigned gx = (unsigned)min((long long)(num_sms() * 8 / (3 * B) + 1), (long long)cdiv(HW / 4, 256));
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, 3 * B);
   launch(k_frame_stats, grid, 256, 0, st, stats7, x_hat, x, mask, HW, n);
   launch(k_frame_stats_bits, 1, 32, 0, st, stats7, bpp3, B, (double)HW, (double)n);
 }
