@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed resident region (ncu --profile-from-start off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -281,6 +283,8 @@ def main():
         l0 = lib.dmc_kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as clk:
+            if args.profiler_range:
+                torch.cuda.profiler.start()
             e0.record()
             for _ in range(args.steps):
                 res, t = step_resident()
@@ -288,6 +292,8 @@ def main():
             stats.all_reduce()
             e1.record()
             barrier()
+            if args.profiler_range:
+                torch.cuda.profiler.stop()
         launches = lib.dmc_kernel_launches() - l0
         ms = e0.elapsed_time(e1)
         # ---- timed: end to end through the public API with host buffers
