@@ -145,7 +145,26 @@ class _EngineModule(nn.Module):
             raise TypeError("dmc_b200: float32 input expected")
 
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """(storage pointer, version counter) of every parameter.  Walking the module tree costs ~1 ms per call
+        (378 tensors); the list of Parameter objects is therefore cached and rebuilt every 256 calls and whenever
+        `_apply` (`.to()`, `.cuda()`) or `load_state_dict` runs -- in-place edits are caught by the version
+        counters, `.data` swaps by the pointers, re-registered Parameters by the periodic rebuild."""
+        cache = self.__dict__.get("_param_cache")
+        age = self.__dict__.get("_param_cache_age", 0)
+        if cache is None or age >= 256:
+            cache = list(self.parameters())
+            self.__dict__["_param_cache"] = cache
+            age = 0
+        self.__dict__["_param_cache_age"] = age + 1
+        return tuple((p.data_ptr(), p._version) for p in cache)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_param_cache"] = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__["_param_cache"] = None
+        return super().load_state_dict(*args, **kwargs)
 
     def _engine(self, B: int, H: int, W: int, device: torch.device):
         if self._lib is None:
