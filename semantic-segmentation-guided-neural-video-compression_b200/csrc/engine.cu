@@ -489,6 +489,7 @@ struct dmc_engine {
   void build_intra();
   void finalize(cudaStream_t st);
   void run(std::vector<Op>& p, cudaStream_t st) {
+    pdl_set_auto((long long)B * H * W <= (1LL << 20));   // (kernels.cu: launch-bound frames only)
     for (auto& f : p) f(st);
   }
 };

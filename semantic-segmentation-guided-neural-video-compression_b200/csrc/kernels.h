@@ -8,7 +8,8 @@ namespace dmc {
 int num_sms();
 void note_launch();            // every kernel launch of the library is counted
 long long launch_count();
-bool pdl_enabled();            // DMC_PDL=1 turns programmatic dependent launch on (measured neutral: off by default)
+bool pdl_enabled();            // programmatic dependent launch: DMC_PDL=0/1 forces it, else per frame size
+void pdl_set_auto(bool on);
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_prologue_done in common.cuh).
 template <typename... KArgs, typename... Args>
