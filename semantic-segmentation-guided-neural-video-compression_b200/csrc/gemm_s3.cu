@@ -796,8 +796,12 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     // (whole warp walks the loop, one elected lane issues: addresses stay in uniform registers)
     int s = 0;
     uint32_t ph = 0, tcount = 0;
+    // (the table entry of the next tile is fetched a tile ahead: its ~700 clocks of global latency sat on the
+    // critical path of every tile in this warp and in the MMA warp)
+    uint32_t e_nxt = unit < p.n_entries ? __ldg(p.table + unit) : 0u;
     for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
-      const uint32_t e = __ldg(p.table + ei);
+      const uint32_t e = e_nxt;
+      if (ei + units < p.n_entries) e_nxt = __ldg(p.table + ei + units);
       const int l = (int)(e >> 28), mt = (int)(e & 0xfffffu);
       const int nt = p.cl4 ? 2 * (int)((e >> 20) & 0xffu) + (int)pairIdx : (int)((e >> 20) & 0xffu);
       const S3StageDev& S = p.st[l];
@@ -818,7 +822,8 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       const uint32_t wRows = (uint32_t)S.BN >> 1;
       // both planes x 32 k, or (single term) the hi plane x 64 k: the same bytes
       const int kblk = S.kblk;
-      const uint32_t tx = (S.nterms == 1 ? (uint32_t)kblk : 4u) * (kS3APlane + wRows * (kS3BK * 2));
+      // (probe switch 32: no W loads -- what a W tile kept resident across row tiles would leave of the load time)
+      const uint32_t tx = (S.nterms == 1 ? (uint32_t)kblk : 4u) * (kS3APlane + ((p.dbg & 32) ? 0u : wRows * (kS3BK * 2)));
       const int m_idx = mt * 256 + (int)rank * 128;
       const int n_idx = nt * S.BN + (int)(rank * wRows);
       for (int kb = 0; kb < S.k_blocks; ++kb) {
@@ -845,7 +850,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
             } else {
               tma_load_pair(sa, &S.tmA, m_idx >> 4, kb * kblk, lbar);
             }
-            tma_load_pair_w(sw, &S.tmW, n_idx >> 4, kb * kblk, lbar);
+            if (!(p.dbg & 32)) tma_load_pair_w(sw, &S.tmW, n_idx >> 4, kb * kblk, lbar);
           }
         }
         __syncwarp();
@@ -860,8 +865,10 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       const uint32_t aStep = kS3APlane >> 4;
       int s = 0;
       uint32_t ph = 0, tcount = 0;
+      uint32_t e_nxt = unit < p.n_entries ? __ldg(p.table + unit) : 0u;
       for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
-        const uint32_t e = __ldg(p.table + ei);
+        const uint32_t e = e_nxt;
+        if (ei + units < p.n_entries) e_nxt = __ldg(p.table + ei + units);
         const S3StageDev& S = p.st[e >> 28];
         // instruction descriptor: D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0, K-major both,
         // N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
@@ -900,6 +907,13 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
                 if (split) {
                   tc_mma_pair(d_small, a0, w1, idesc, ks == 0 ? first : 1u);
                   tc_mma_pair(d_small, a1, w0, idesc, 1u);
+                }
+                if (p.dbg & 64) {      // probe: every MMA twice (is a k block bound by the tensor pipe or by its barriers?)
+                  tc_mma_pair(d_main, a0, w0, idesc, 1u);
+                  if (split) {
+                    tc_mma_pair(d_small, a0, w1, idesc, 1u);
+                    tc_mma_pair(d_small, a1, w0, idesc, 1u);
+                  }
                 }
               }
             }

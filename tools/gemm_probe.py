@@ -15,7 +15,7 @@ M = int(os.environ.get("PROBE_M", "38400"))
 SHAPES = [("dc0 256->256 plain", 256, 256, 0), ("dc0 256->256 wsilu", 256, 256, 1), ("dc3 256->256 +res", 256, 256, 2),
           ("ffn0 256->1024 pair", 256, 1024, 3), ("ffn2 512->256 +res", 512, 256, 2), ("head 320->192", 320, 192, 0)]
 PROBES = [(0, "full"), (4, "no-epi-mem"), (12, "no-epi"), (2, "no-mma"), (3, "epi-only"), (13, "mma-only"),
-          (14, "tma-only")]
+          (14, "tma-only"), (32, "no-W-loads"), (46, "tma-only,no-W"), (13 + 64, "mma-only x2")]
 ARGS = sys.argv[1:]
 KERNELS = [int(a) for a in ARGS if a.isdigit()] or ([] if ARGS else [0, 2])   # 0 general one-CTA, 1 its pair variant, 2 gemm_s3
 for name, k, n, mode in SHAPES:
