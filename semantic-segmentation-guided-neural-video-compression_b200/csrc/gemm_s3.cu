@@ -420,7 +420,10 @@ constexpr int kS3APlane = 128 * kS3BK * 2;        // one plane of a 128 x 32 fp1
 #ifndef DMC_S3_EPI_WARPS
 #define DMC_S3_EPI_WARPS 8
 #endif
-constexpr int kS3EpiWarps = DMC_S3_EPI_WARPS;     // 8 or 16
+#if DMC_S3_EPI_WARPS != 8
+#error "only eight epilogue warps are supported: sixteen at 112 registers spill ~1 KB per thread, leave four operand stages, and the variant has not been kept working (it traps on its bounded waits)"
+#endif
+constexpr int kS3EpiWarps = DMC_S3_EPI_WARPS;
 constexpr int kS3Split = kS3EpiWarps / 4;         // warps per TMEM lane quadrant: they split the tile's columns
 // warp group 0: TMA producer, MMA issuer, two spare warps (56 registers); warp groups 1..: the epilogue warps
 // (setmaxnreg: 224 registers with eight of them; sixteen would get 112, which the inlined epilogue variants do not
