@@ -341,7 +341,8 @@ def main():
                              "kernel": "k_gemm_s3_chain (persistent tcgen05 chain of 1x1 layers, 3-term split-fp16 product)",
                              "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                              "frac": achieved / pk["bf16_tflops"] if pk["bf16_tflops"] else None,
-                             "traffic": ncu_traffic(),
+                             "traffic": (ncu_traffic() or {}).get("bytes"),
+                             "traffic_detail": ncu_traffic(),
                              "peak_source": pk["source"],
                              "launches_per_frame": g_n.value / nprof, "avg_launch_ms": per_launch_ms,
                              "gemm_share_of_step": (g_ms.value / nprof) / (ms / args.steps),

@@ -97,3 +97,30 @@ def test_clip_stats_cpu_formulas_match_trainer_metrics():
 def test_gop_qp_schedule():
     assert [clips.gop_qp(32, t) for t in range(1, 9)] == [40, 32, 36, 32, 36, 32, 36, 32]
     assert [O.shift_qp(32, O.INDEX_MAP[t % 8]) for t in range(1, 9)] == [clips.gop_qp(32, t) for t in range(1, 9)]
+
+
+def test_weight_signature_cache_sees_edits_moves_and_reloads():
+    """The drop-in modules re-pack their weights when a parameter changes: the signature is built from a cached
+    parameter list (walking the module tree costs ~1 ms per forward) and must still see in-place edits, `.to()` /
+    `load_state_dict`, and -- at the periodic rebuild -- a re-registered Parameter."""
+    import torch
+    import dmc_b200 as D
+    m = D.build_p_model("old").eval()
+    s0 = m._signature()
+    assert m._signature() == s0
+    with torch.no_grad():
+        next(m.parameters()).add_(1.0)                      # in-place edit: version counter
+    s1 = m._signature()
+    assert s1 != s0
+    m.load_state_dict(m.state_dict())                       # copies in place and drops the cache
+    s2 = m._signature()
+    assert s2 != s1
+    m = m.double().float()                                  # _apply: new storages
+    assert m._signature() != s2
+    first = next(iter(m._parameters)) if m._parameters else None
+    name, mod = next((n, sub) for n, sub in m.named_modules() if getattr(sub, "weight", None) is not None)
+    s3 = m._signature()
+    mod.weight = torch.nn.Parameter(mod.weight.detach().clone())   # re-registered: caught by the periodic rebuild
+    for _ in range(257):
+        s4 = m._signature()
+    assert s4 != s3
