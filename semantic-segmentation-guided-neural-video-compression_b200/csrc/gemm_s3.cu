@@ -410,6 +410,7 @@ struct S3ChainParams {
   uint32_t epoch;          // launch number (1-based): layer l-1 is complete at done == epoch * need
   uint32_t stageBytes;     // operand ring stage (sized for the widest W tile of the chain)
   int stages;
+  int eager;               // 1: few tiles per layer and cluster -- publish a tile as soon as it is stored (below)
   int cl4;                 // 1: clusters of 4 CTAs = two pairs on the two N tiles of an entry, sharing A by TMA multicast
   int dbg;                 // probe switches: 1 no operand loads, 2 no MMA issue, 4 no epilogue TMA traffic, 8 no epilogue math
   int* err;
@@ -1094,6 +1095,14 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
 #endif
       pend_l = (uint32_t)l; pend_mt = (uint32_t)mt; pend_t = tcount;
       pending = p.st[l].publish != 0;
+      // Chains with fewer than ~3 waves of tiles per layer (the H/16 ... H/64 stages at batch 1) run into their
+      // dependencies: a cluster's next tile needs rows another cluster has only just finished, and the deferred
+      // publication above adds most of a tile time (2 500-5 000 clocks) to that wait.  There the ~1 500 clocks an
+      // epilogue warp spends waiting for its stores right away are cheaper.
+      if (pending && p.eager) {
+        if (lane == 0) { tma_store_wait_all(); publish(); }
+        pending = false;
+      }
     }
     if (pending && lane == 0) { tma_store_wait_all(); publish(); }
     if (lane == 0) tma_store_wait_all();
@@ -1277,6 +1286,11 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     }
   (void)tiles_per_step;
   c->p.n_entries = (int)table.size();
+  {
+    const char* v = getenv("DMC_S3_EAGER");          // 0 / 1 forces the publication mode (A/B runs)
+    const int units = cap / (cl4 ? 4 : 2);
+    c->p.eager = v ? (v[0] == '1') : (n > 1 && (int)table.size() < 3 * n * units);
+  }
   c->p.MT = MT;
   c->p.err = d_err;
   int grid = (cl4 ? 4 : 2) * c->p.n_entries;
