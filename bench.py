@@ -51,7 +51,7 @@ def peaks():
 
 def ncu_traffic():
     """dram bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture."""
-    path = os.path.join(ROOT, "profiles", "chain_dcb_r01_v7_ncu_summary.json")
+    path = os.path.join(ROOT, "profiles", "chain_dcb_r01_v8_ncu_summary.json")
     try:
         d = json.load(open(path))
         return {"bytes": d["dram_bytes_read"] + d["dram_bytes_write"], "launch": d["launch"],
