@@ -1289,7 +1289,12 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
   {
     const char* v = getenv("DMC_S3_EAGER");          // 0 / 1 forces the publication mode (A/B runs)
     const int units = cap / (cl4 ? 4 : 2);
-    c->p.eager = v ? (v[0] == '1') : (n > 1 && (int)table.size() < 3 * n * units);
+    int min_layer = 1 << 30;                          // fewest entries of any layer of the chain
+    for (int l = 0; l < n; ++l) {
+      const int per_mt = cl4 ? (c->p.st[l].n_tiles + 1) / 2 : c->p.st[l].n_tiles;
+      if (per_mt * MT < min_layer) min_layer = per_mt * MT;
+    }
+    c->p.eager = v ? (v[0] == '1') : (n > 1 && min_layer < 3 * units);
   }
   c->p.MT = MT;
   c->p.err = d_err;
