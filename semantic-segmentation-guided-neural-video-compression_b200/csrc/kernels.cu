@@ -550,12 +550,53 @@ __global__ void k_im2col(View in, View out, int B, int H, int W, int k, int stri
   *reinterpret_cast<uint4*>(d) = a;
   *reinterpret_cast<uint4*>(d + out.ps) = bb;
 }
+// Row-fastest variant: a thread moves one 16-column block of one (output row, tap) -- 32 contiguous bytes per
+// plane -- and consecutive threads take consecutive output rows, so a warp writes 1 KB contiguous per plane (the
+// blocked layout keeps the rows of a column block together) and, at stride 1, reads as much.
+__global__ void k_im2col_rows(View in, View out, int B, int H, int W, int k, int stride, int pad, int Ho,
+                              int Wo, int tap_stride, int col_off, int C16, unsigned Mo) {
+  pdl_prologue_done();
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned taps = (unsigned)(k * k);
+  if (idx >= Mo * C16) return;
+  const unsigned mo = idx % Mo, blk = idx / Mo, tap = blockIdx.y;
+  (void)taps;
+  const unsigned wo = mo % (unsigned)Wo, t = mo / (unsigned)Wo;
+  const unsigned ho = t % (unsigned)Ho, b = t / (unsigned)Ho;
+  const int hi = (int)ho * stride - pad + (int)tap / k, wi = (int)wo * stride - pad + (int)tap % k;
+  const int c = (int)blk * 16;
+  uint4 z = make_uint4(0, 0, 0, 0), a0 = z, a1 = z, b0 = z, b1 = z;
+  if ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W) {
+    const long long r = ((long long)b * H + hi) * W + wi;
+    const h16* q0 = in.p + s3_unit_offset(in, r, c);
+    const h16* q1 = in.p + s3_unit_offset(in, r, c + 8);
+    a0 = *reinterpret_cast<const uint4*>(q0);
+    a1 = *reinterpret_cast<const uint4*>(q1);
+    b0 = *reinterpret_cast<const uint4*>(q0 + in.ps);
+    b1 = *reinterpret_cast<const uint4*>(q1 + in.ps);
+  }
+  const int dc = (int)tap * tap_stride + col_off + c;
+  h16* d0 = out.p + s3_unit_offset(out, mo, dc);
+  h16* d1 = out.p + s3_unit_offset(out, mo, dc + 8);
+  *reinterpret_cast<uint4*>(d0) = a0;
+  *reinterpret_cast<uint4*>(d1) = a1;
+  *reinterpret_cast<uint4*>(d0 + out.ps) = b0;
+  *reinterpret_cast<uint4*>(d1 + out.ps) = b1;
+}
 void im2col(View in, View out, int B, int H, int W, int k, int stride, int pad, int Ho, int Wo,
             int tap_stride, int col_off, cudaStream_t st) {
+  const long long Mo = (long long)B * Ho * Wo;
+  if (in.C % 16 == 0 && tap_stride % 16 == 0 && col_off % 16 == 0 && Mo * (in.C / 16) < (1LL << 31)) {
+    const int C16 = in.C / 16;
+    dim3 grid(cdiv(Mo * C16, 256), k * k);
+    launch(k_im2col_rows, grid, 256, 0, st, in, out, B, H, W, k, stride, pad, Ho, Wo, tap_stride, col_off, C16,
+           (unsigned)Mo);
+    return;
+  }
   int C8 = in.C / 8;
   long long n = (long long)B * Ho * Wo * k * k * C8;
   launch(k_im2col, cdiv(n, 256), 256, 0, st, in, out, B, H, W, k, stride, pad, Ho, Wo, tap_stride,
-                                         col_off, C8);
+         col_off, C8);
 }
 
 // ------------------------------------------------------------------ fp32 CUDA-core GEMM
