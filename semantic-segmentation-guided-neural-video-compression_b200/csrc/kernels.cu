@@ -411,6 +411,9 @@ void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, in
 // instructions per output -- 18 tap loads and 36 input loads per 32 outputs, predicates, zero fills -- and half of
 // its time is there (14.5 of 28.8 us at 160x240x256 with loads and stores switched off); this one spends ~16.
 // Same order of the nine FMAs per output as above, so the results are bit-identical.
+#ifndef DMC_DW_MINB
+#define DMC_DW_MINB 3
+#endif
 struct DwRow { float v[kDwPix + 2][4]; };
 __device__ __forceinline__ void dw_load_row(DwRow& r, const float* __restrict__ in32, int ld, long long rowbase, int h,
                                             int H, int w0, int W, int c) {
@@ -428,7 +431,7 @@ __device__ __forceinline__ void dw_load_row(DwRow& r, const float* __restrict__ 
     r.v[j][0] = a.x; r.v[j][1] = a.y; r.v[j][2] = a.z; r.v[j][3] = a.w;
   }
 }
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, DMC_DW_MINB)
 k_dwconv3x3_strip(const float* __restrict__ in32, int ld, const float* __restrict__ w9c,
                   const float* __restrict__ bias, View out, int B, int H, int W, int C4, int WG, int HS, int strip) {
   pdl_prologue_done();
@@ -509,7 +512,7 @@ void dwconv3x3_f32(const float* in, int ld, const float* w9c, const float* bias,
     // 128-thread CTAs per SM), at least 4 rows (a strip reads its rows + 2)
     const int C4 = out.C / 4;
     const long long warps_per_strip = ((long long)B * WG * C4 + 31) / 32;
-    long long hs_max = (long long)num_sms() * 12 / warps_per_strip;
+    long long hs_max = (long long)num_sms() * (4 * DMC_DW_MINB) / warps_per_strip;
     if (hs_max < 1) hs_max = 1;
     int strip = (int)((H + hs_max - 1) / hs_max);
     if (strip < 4) strip = 4;
