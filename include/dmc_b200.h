@@ -27,9 +27,14 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *     Work is enqueued asynchronously; nothing here synchronises the host.
  *   - one engine handle per (variant, batch, height, width); a handle is
- *     thread-compatible (use it from one thread / one stream at a time).
- *   - height and width must be multiples of 64 (the reference's `performance`
- *     variant never pads: seg_video_model.py:331).
+ *     thread-compatible (use it from one thread / one stream at a time).  It
+ *     belongs to the CUDA device that was current in dmc_create; every later
+ *     call switches to that device for its duration.
+ *   - height and width must be multiples of 16 for `old`, `fast`, `mask_prop`
+ *     and the intra model (y is replicate-padded to a multiple of 4 for the
+ *     hyper path, models/common_model.py:68-72) and multiples of 64 for
+ *     `performance`, which never pads (seg_video_model.py:331) -- dmc_create
+ *     refuses other sizes.
  */
 #ifndef DMC_B200_H_
 #define DMC_B200_H_
@@ -67,7 +72,6 @@ enum {
   DMC_FLAG_SIMT_GEMM = 1,   /* run every contraction on the fp32 CUDA-core kernel
                                (validation backend) instead of tcgen05          */
   DMC_FLAG_KEEP_TAPS = 2,   /* keep intermediate tensors readable via dmc_get_tap */
-  DMC_FLAG_RECON_BF16X1 = 4, /* (default behaviour since r1: kept for source compatibility, ignored) */
   DMC_FLAG_RECON_SPLIT3 = 8  /* run recon_generation_net with the fp32-grade 3-term split product too.  By default
                                 its contractions use plain fp16 operands (hi planes, 1 term, fp32 accumulate): x_hat of
                                 a P frame never feeds a later symbol, and PSNR moves by < 1e-3 dB */
@@ -97,9 +101,14 @@ int dmc_finalize_weights(dmc_engine* e, void* stream);
  * after_i == 0.  Outputs: x_hat (B,3,H,W) in [0,1]; feature (B,256,H/8,W/8);
  * bpp3 = B x {bpp, bpp_y, bpp_z}; mask_pred (B,1,H,W) or NULL -- written only by
  * mask_prop with after_i == 0 (the predictor's logits); finite_flag (int32, device)
- * or NULL: set to 1 if any latent/feature was non-finite or hit the fp16 range limit of the
- * split storage format (|x| >= 65504 saturates) -- the reference's _finite_check,
- * seg_video_model_fast.py:152-156, without its host syncs. */
+ * or NULL: the reference's _finite_check sites (seg_video_model_fast.py:152-156,269-276,353-371) without their
+ * host syncs -- one fused check at the end of the frame.  The word is zeroed and bit i is set if tensor i holds a
+ * non-finite value or hit the fp16 range limit of the split storage format (|x| >= 65504 saturates):
+ *   0 temporal feature (feature_adaptor_i / _p)   1 feature_extractor.ctx   2 feature_extractor.ctx_t
+ *   3 y (encoder, after FiLM for `performance`)   4 z (hyper_encoder)       5 params (y_prior_fusion)
+ *   6 y_hat (compress_prior_2x)                   7 decoder feature (dpb["feature"]) */
+#define DMC_FINITE_TAGS "feature_adaptor", "feature_extractor.ctx", "feature_extractor.ctx_t", "encoder", \
+                        "hyper_encoder", "y_prior_fusion", "y_hat", "decoder" 
 int dmc_forward(dmc_engine* e, const float* x, const float* mask, const float* dpb_frame,
                 const float* dpb_feature, int qp, int after_i, float* x_hat, float* feature,
                 float* bpp3, float* mask_pred, int32_t* finite_flag, void* stream);
@@ -169,6 +178,12 @@ int dmc_bench_dcb(int batch, int height, int width, int cin, int cout, int block
 
 int dmc_num_sms(void);
 const char* dmc_version(void);
+
+/* Accumulate-truncation compensation of the tcgen05 contractions (csrc/kernels.cu: acc_comp_scaled): kappa in units of
+ * 2^-24 per MMA accumulate step; 0 switches it off.  Default 0.276 (measured), or the environment variable
+ * DMC_ACC_COMP.  Engines created after the call use the new value (diagnostics / A-B runs). */
+int dmc_set_acc_comp(float kappa);
+float dmc_get_acc_comp(void);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -8,14 +8,13 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 
 from . import build as _build
 
 VARIANT_IDS = {"old": 0, "performance": 1, "fast": 2, "mask_prop": 3, "intra": 4}
 FLAG_SIMT_GEMM = 1
 FLAG_KEEP_TAPS = 2
-FLAG_RECON_BF16X1 = 4
 FLAG_RECON_SPLIT3 = 8
 
 # every symbol include/dmc_b200.h declares: name -> (restype, argtypes)
@@ -48,7 +47,13 @@ SIGNATURES = {
     "dmc_bench_dcb": (c_int, [c_int] * 7 + [POINTER(c_float)]),
     "dmc_num_sms": (c_int, []),
     "dmc_version": (c_char_p, []),
+    "dmc_set_acc_comp": (c_int, [c_float]),
+    "dmc_get_acc_comp": (c_float, []),
 }
+
+# names of the bits of dmc_forward's finite_flag (include/dmc_b200.h)
+FINITE_TAGS = ("feature_adaptor", "feature_extractor.ctx", "feature_extractor.ctx_t", "encoder", "hyper_encoder",
+               "y_prior_fusion", "y_hat", "decoder")
 
 _lib = None
 

@@ -94,8 +94,22 @@ struct EpiSpec {
 
 }  // namespace
 
+// Every C-ABI entry that touches an engine runs on the device the engine was created on, whatever the caller's current
+// device is (torch: model.to("cuda:1") without torch.cuda.set_device(1)).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev && dev >= 0) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 struct dmc_engine {
   int variant = 0, B = 0, H = 0, W = 0, flags = 0;
+  int device = -1;                 // CUDA ordinal the buffers, tensor maps and chains belong to
   std::string error;
   bool finalized = false;
 
@@ -145,6 +159,7 @@ struct dmc_engine {
   void prof_end(cudaStream_t st) { CUDA_OK(cudaEventRecord(prof_events.back().second, st)); }
 
   ~dmc_engine() {
+    DeviceGuard g(device);
     for (S3Chain* c : chains) s3_chain_destroy(c);
     for (void* p : allocs) cudaFree(p);
   }
@@ -845,12 +860,18 @@ void dmc_engine::build_p() {
   // ---- rate (video_model.py:373-378)
   int pixels = H * W;
   op([self, by, bz, pixels](cudaStream_t st) { finalize_bpp(by, bz, self->cur.bpp3, self->B, pixels, st); });
-  if (true) {
-    op([self, YQ, FEAT, M16, M8](cudaStream_t st) {
+  {
+    // the reference's _finite_check sites (seg_video_model_fast.py:353-371,269-276), checked in ONE launch at the end
+    // of the frame instead of twelve host syncs inside it: bit i of the flag names tensor i (include/dmc_b200.h)
+    FiniteList fl;
+    memset(&fl, 0, sizeof fl);
+    const Act* list[8] = {&FEAT0, &CTX, &CTXT, &YQ, &Z, &PARAMS, &YHAT, &FEAT};
+    for (int i = 0; i < 8; ++i) { fl.v[i] = list[i]->v; fl.M[i] = list[i]->M(); }
+    fl.n = 8;
+    op([self, fl](cudaStream_t st) {
       if (!self->cur.finite) return;
       CUDA_OK(cudaMemsetAsync(self->cur.finite, 0, sizeof(int32_t), st));
-      finite_check(YQ.v, M16, self->cur.finite, st);
-      finite_check(FEAT.v, M8, self->cur.finite, st);
+      finite_check(fl, self->cur.finite, st);
     });
   }
   flush_chain();
@@ -1069,6 +1090,7 @@ int dmc_create(int variant, int batch, int height, int width, int flags, dmc_eng
       fail("CUDA device required: this engine has no CPU path");
     e = new dmc_engine();
     e->variant = variant; e->B = batch; e->H = height; e->W = width; e->flags = flags;
+    CUDA_OK(cudaGetDevice(&e->device));
     try {
       if (variant == DMC_VARIANT_INTRA) e->build_intra();
       else e->build_p();
@@ -1102,6 +1124,7 @@ int dmc_set_weight(dmc_engine* e, const char* key, const float* dev_ptr, const i
                    void* stream) {
   if (!e || !key || !dev_ptr) return DMC_E_INVALID;
   return guarded(e, [&] {
+    DeviceGuard dg(e->device);
     auto it = e->slot_index.find(key);
     if (it == e->slot_index.end()) fail("unknown state_dict key '%s'", key);
     WSlot& s = e->slots[it->second];
@@ -1132,6 +1155,7 @@ int dmc_forward(dmc_engine* e, const float* x, const float* mask, const float* d
     return DMC_E_INVALID;
   }
   return guarded(e, [&] {
+    DeviceGuard dg(e->device);
     auto& c = e->cur;
     c.x = x; c.mask = (e->variant == DMC_VARIANT_OLD) ? nullptr : mask;
     c.dpb_frame = dpb_frame; c.dpb_feature = dpb_feature; c.qp = qp;
@@ -1153,6 +1177,7 @@ int dmci_forward(dmc_engine* e, const float* x, int qp, float* x_hat, float* bpp
     return DMC_E_INVALID;
   }
   return guarded(e, [&] {
+    DeviceGuard dg(e->device);
     auto& c = e->cur;
     c = dmc_engine::Cur();
     c.x = x; c.qp = qp; c.x_hat = x_hat; c.bpp3 = bpp3;
@@ -1165,6 +1190,7 @@ int dmc_get_tap(dmc_engine* e, const char* name, float* dst, int64_t capacity, i
                 void* stream) {
   if (!e || !name) return DMC_E_INVALID;
   return guarded(e, [&] {
+    DeviceGuard dg(e->device);
     cudaStream_t st = (cudaStream_t)stream;
     auto it = e->taps.find(name);
     if (it != e->taps.end()) {
@@ -1202,6 +1228,7 @@ int dmc_profile_read(dmc_engine* e, double* gemm_ms, int64_t* gemm_launches, dou
                      double* issued_flops) {
   if (!e) return DMC_E_INVALID;
   return guarded(e, [&] {
+    DeviceGuard dg(e->device);
     CUDA_OK(cudaDeviceSynchronize());
     double ms = 0;
     for (auto& pr : e->prof_events) {
@@ -1220,7 +1247,12 @@ int dmc_profile_read(dmc_engine* e, double* gemm_ms, int64_t* gemm_launches, dou
   });
 }
 int dmc_num_sms(void) { return num_sms(); }
-const char* dmc_version(void) { return "dmc_b200 0.1 (sm_100a)"; }
+const char* dmc_version(void) { return "dmc_b200 0.2 (sm_100a)"; }
+int dmc_set_acc_comp(float kappa) {
+  acc_comp_set_kappa(kappa);
+  return DMC_OK;
+}
+float dmc_get_acc_comp(void) { return acc_comp_kappa(); }
 
 }  // extern "C"
 

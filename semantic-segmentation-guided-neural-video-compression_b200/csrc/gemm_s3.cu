@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "kernels.h"
@@ -399,6 +400,7 @@ struct alignas(64) S3StageDev {
   int kblk;          // 16-wide k blocks per operand stage: 2 (both planes) or 4 (single term: hi plane only)
   int kind;          // S3_*
   int nterms;        // 3: fp32-grade split product (two accumulators), 1: hi*hi only
+  float comp;        // accumulate-truncation compensation, pre-scaled by 2^11 (see acc_comp_scaled in kernels.cu); 0 = off
   uint32_t need;     // increments of done[l-1][row tile] per launch that complete layer l-1 for a row tile
   int publish;       // a later layer of the chain waits for this one: completed tiles are counted in done[l]
 };
@@ -558,11 +560,13 @@ struct StageRegs {
   int BN, n_out, kind;
   uint32_t need;
   bool two_acc;
+  float comp;
 };
 __device__ __forceinline__ StageRegs s3_load_stage(const S3StageDev& S) {
   StageRegs r;
   r.bias = S.bias; r.scale = S.scale; r.tmOut = &S.tmOut; r.tmRes = &S.tmRes; r.tmRes2 = &S.tmRes2;
   r.BN = S.BN; r.n_out = S.n_out; r.kind = S.kind; r.need = S.need; r.two_acc = S.nterms != 1;
+  r.comp = S.comp;
   return r;
 }
 
@@ -585,6 +589,7 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
   const uint32_t swz = (uint32_t)((lane >> 2) & 1) << 4;        // SWIZZLE_32B: 16-byte unit ^= row bit 2
   const uint32_t rowOff = (uint32_t)lane * 32u;
   const bool two_acc = S.two_acc;
+  const float comp = S.comp;
   for (int c = 0; c < nchunk; ++c) {
     const int acol = s3_acc_col(kKind, S.BN, x.part, c);         // accumulator column of this chunk
     const int dcol = s3_dest_col(kKind, S.BN, x.part, nt, c);
@@ -633,7 +638,9 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             float t = __uint_as_float(a[4 * i + k]);
-            if (two_acc) t = fmaf(__uint_as_float(b[4 * i + k]), kLoInv, t);     // main + small * 2^-11, one rounding
+            // main + small' * 2^-11 with one rounding; small' = small + main * comp puts back what the tensor core's
+            // truncating accumulation of the main term lost on average (comp is 2^11-scaled like `small`)
+            if (two_acc) t = fmaf(fmaf(t, comp, __uint_as_float(b[4 * i + k])), kLoInv, t);
             w[4 * i + k] = add_rn(t, bias4[k]);
           }
         }
@@ -1163,51 +1170,76 @@ static int s3_kind(const Epi& e) {
 
 int s3_chain_max_stages() { return kS3MaxStages; }
 
-S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
-  static int smem_max = 0;
-  static int* d_err = nullptr;
-  if (!smem_max) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (cudaFuncSetAttribute(k_gemm_s3_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) {
-      snprintf(g_s3_err, sizeof g_s3_err, "cudaFuncSetAttribute(max dynamic smem=%d) failed", smem_max);
-      smem_max = 0;
-      return nullptr;
-    }
-    // the code of a bounded wait that gave up lives in mapped host memory: it survives the trap
-    int* h_trap = nullptr;
-    if (cudaHostAlloc((void**)&h_trap, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
-      *h_trap = 0;
-      g_s3_trap = h_trap;
-      cudaHostGetDevicePointer((void**)&d_err, h_trap, 0);
-    }
+// Per-device launch state: opt-in shared memory, how many CTA pairs can be co-resident (the tile dependencies of
+// the persistent kernel need every cluster of the grid on an SM at the same time), the trap-code word.
+struct S3Device {
+  int smem_max = 0;
+  int pair_clusters = 0;       // cudaOccupancyMaxActiveClusters for (2,1,1) clusters at smem_max
+  int cl4_clusters = 0;        // same for (4,1,1) clusters (DMC_GEMM_CL4=1), 0 = unavailable
+  int* d_err = nullptr;
+};
+static S3Device* s3_device() {
+  static S3Device devs[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  S3Device& d = devs[dev];
+  if (d.smem_max) return &d;
+  int smem = 0;
+  cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (cudaFuncSetAttribute(k_gemm_s3_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    snprintf(g_s3_err, sizeof g_s3_err, "cudaFuncSetAttribute(max dynamic smem=%d) failed", smem);
+    return nullptr;
   }
+  // the code of a bounded wait that gave up lives in mapped host memory: it survives the trap
+  int* h_trap = nullptr;
+  if (cudaHostAlloc((void**)&h_trap, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+    *h_trap = 0;
+    g_s3_trap = h_trap;
+    cudaHostGetDevicePointer((void**)&d.d_err, h_trap, 0);
+  }
+  for (int csz = 2; csz <= 4; csz += 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((num_sms() / csz) * csz);
+    cfg.blockDim = dim3(kS3Threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, k_gemm_s3_chain, &cfg) != cudaSuccess) nc = 0;
+    (csz == 2 ? d.pair_clusters : d.cl4_clusters) = nc;
+  }
+  cudaGetLastError();
+  if (d.pair_clusters < 1) {
+    snprintf(g_s3_err, sizeof g_s3_err, "k_gemm_s3_chain: no CTA pair can be resident on this device (smem %d)", smem);
+    return nullptr;
+  }
+  d.smem_max = smem;
+  return &d;
+}
+
+S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
+  S3Device* dv = s3_device();
+  if (!dv) return nullptr;
+  const int smem_max = dv->smem_max;
+  int* d_err = dv->d_err;
   if (n < 1 || n > kS3MaxStages) {
     snprintf(g_s3_err, sizeof g_s3_err, "s3_chain_create: %d stages (max %d)", n, kS3MaxStages);
     return nullptr;
   }
   // 4-CTA clusters (A shared between two CTA pairs by TMA multicast) need every stage's 64-row A map and are
   // limited to the clusters that can be co-resident (33 = 132 SMs on B200); DMC_GEMM_CL4=1 selects them
-  static int cl4_mode = -1, cl4_clusters = 0;
+  static int cl4_mode = -1;
   if (cl4_mode < 0) {
     const char* v = getenv("DMC_GEMM_CL4");
     cl4_mode = (v && v[0] == '1') ? 1 : 0;
-    if (cl4_mode) {
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof cfg);
-      cfg.gridDim = dim3((num_sms() / 4) * 4);
-      cfg.blockDim = dim3(kS3Threads);
-      cfg.dynamicSmemBytes = smem_max;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      if (cudaOccupancyMaxActiveClusters(&cl4_clusters, k_gemm_s3_chain, &cfg) != cudaSuccess || cl4_clusters < 1)
-        cl4_mode = 0;
-    }
   }
+  const int cl4_clusters = dv->cl4_clusters;
+  if (cl4_mode == 1 && cl4_clusters < 1) cl4_mode = 0;
   bool cl4 = cl4_mode == 1;
   for (int l = 0; l < n; ++l) cl4 = cl4 && stages[l].tmA64 != nullptr;
   S3Chain* c = new S3Chain();
@@ -1240,6 +1272,7 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
     S.n_out = d.e.n_out;
     S.kind = s3_kind(d.e);
     S.nterms = d.nsplit != 1 ? 3 : 1;
+    S.comp = S.nterms == 3 ? acc_comp_scaled(d.K) : 0.0f;
     // one count per CTA and table entry of the previous layer for these rows
     S.need = l == 0 ? 0u : (cl4 ? (uint32_t)((c->p.st[l - 1].n_tiles + 1) / 2) * 4u : (uint32_t)c->p.st[l - 1].n_tiles * 2u);
     S.publish = l + 1 < n ? 1 : 0;
@@ -1275,7 +1308,9 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
   // a tile's producers sit a whole layer earlier in the table -- they finished long before it is reached (a
   // simulated DepthConvBlock chain at 1920x1280 runs at 95 % of the no-dependency bound; interleaving the
   // layers with a lag of d row tiles reached 86-90 %, because the ramps starve and tile costs differ per layer).
-  const int cap = cl4 ? 4 * cl4_clusters : (num_sms() & ~1);
+  // the grid never exceeds what can be co-resident (fewer SMs under MPS / green contexts): every dependency of the
+  // table points backwards and each cluster walks its entries in order, so a fully resident grid cannot deadlock
+  const int cap = cl4 ? 4 * cl4_clusters : std::min(num_sms() & ~1, 2 * dv->pair_clusters);
   std::vector<uint32_t> table;
   for (int l = 0; l < n; ++l)
     for (int mt = 0; mt < MT; ++mt) {
@@ -1325,7 +1360,7 @@ void s3_chain_destroy(S3Chain* c) {
 int s3_chain_stages(const S3Chain* c) { return c ? c->n_stages : 0; }
 
 int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
-  c->p.epoch += 1;
+  c->p.epoch += 1;               // (rolled back below if the launch is refused: the done counters are monotonic)
   c->p.dbg = g_s3_dbg;
   for (int l = 0; l < c->n_stages; ++l)
     if (c->scale_table[l]) c->p.st[l].scale = c->scale_table[l] + (size_t)qp * c->scale_C[l];
@@ -1347,6 +1382,7 @@ int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
   note_launch();
   cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_s3_chain, c->p);
   if (err != cudaSuccess) {
+    c->p.epoch -= 1;
     snprintf(g_s3_err, sizeof g_s3_err, "k_gemm_s3_chain launch: %s", cudaGetErrorString(err));
     return -1;
   }

@@ -184,6 +184,7 @@ struct UmmaParams {
   int m_tiles, n_tiles, k_blocks;
   int BN, nsplit, stages;
   int dbg;     // probe switches: 1 = no TMA loads, 2 = no MMA issue, 4 = no epilogue global traffic
+  float comp;  // accumulate-truncation compensation of the main accumulator (acc_comp_scaled in kernels.cu)
   int* err;
 };
 
@@ -619,7 +620,8 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            r[i] = __float_as_uint(fmaf(__uint_as_float(s2[i]), kLoInv, __uint_as_float(r[i])));
+            r[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(r[i]), p.comp, __uint_as_float(s2[i])), kLoInv,
+                                        __uint_as_float(r[i])));
         } else {
           tc_wait_ld();
         }
@@ -673,22 +675,26 @@ static void read_env_once() {
 
 int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int K, int nsplit,
               cudaStream_t st) {
-  static int smem_max = 0;
-  static int* d_err = nullptr;
+  static int smem_max_dev[64] = {};
+  static int* d_err_dev[64] = {};
   read_env_once();
-  if (!smem_max) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (cudaFuncSetAttribute(k_gemm_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess ||
-        cudaFuncSetAttribute(k_gemm_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) {
-      snprintf(g_umma_err, sizeof g_umma_err, "cudaFuncSetAttribute(max dynamic smem=%d) failed", smem_max);
-      smem_max = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!smem_max_dev[dev]) {
+    int smem = 0;
+    cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (cudaFuncSetAttribute(k_gemm_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gemm_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      snprintf(g_umma_err, sizeof g_umma_err, "cudaFuncSetAttribute(max dynamic smem=%d) failed", smem);
       return -1;
     }
-    cudaMalloc(&d_err, sizeof(int));
-    cudaMemset(d_err, 0, sizeof(int));
+    cudaMalloc(&d_err_dev[dev], sizeof(int));
+    cudaMemset(d_err_dev[dev], 0, sizeof(int));
+    smem_max_dev[dev] = smem;
   }
+  const int smem_max = smem_max_dev[dev];
+  int* d_err = d_err_dev[dev];
   if (nsplit != 1) nsplit = kPlanes;             // planes staged per operand: both, or hi only
   if (!w.tmap || (w.BN % 32) || w.BN > (nsplit != 1 ? 128 : 256) || (e.pack == PACK_PAIR && (w.BN % 64))) {
     snprintf(g_umma_err, sizeof g_umma_err, "gemm_umma: unsupported weight tiling BN=%d", w.BN);
@@ -713,6 +719,7 @@ int gemm_umma(const void* tmapA, const GemmW& w, const Epi& e, long long M, int 
   }
   p.stages = stages;
   p.dbg = g_umma_dbg;
+  p.comp = nsplit != 1 ? acc_comp_scaled(K) : 0.0f;
   p.err = d_err;
   const int smem = stages * stage_bytes + fixed;
   CUtensorMap ta, tw;

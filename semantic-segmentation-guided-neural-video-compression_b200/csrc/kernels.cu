@@ -29,14 +29,41 @@ void pdl_set_auto(bool on) { g_pdl_auto = on ? 1 : 0; }
 long long launch_count() { return g_launches; }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {};          // per device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
+}
+
+// ------------------------------------------------------------------ accumulate-truncation compensation
+// tcgen05.mma adds the 16 products of a k step and the fp32 accumulator at a common alignment and TRUNCATES the sum
+// toward zero when it writes the accumulator back (fp32 FMA rounds to nearest).  Measured on B200 against fp64
+// (tests/diag/acc_bias.py, profiles/tcgen05_accumulate_bias_r01.txt), zero-mean operands: relative bias of the result
+//   K = 64: -1.45   256: -4.69   512: -9.05   1024: -17.67   units of 2^-24   ==  -0.276 * (K/16 + 1)
+// i.e. half an accumulator ulp per MMA step, weighted by how far the running sum has grown -- linear in the number
+// of accumulate steps, independent of the data (the fp32-FMA kernel: 0.00).  The noise of the two paths is the same
+// (rms 7 units at K = 256); what the truncation adds is a MEAN shrink that is coherent across the ~100 layers of a
+// frame, and that is what flipped quantised symbols (14 of 2 457 600 on the full-size intra frame against 0 for
+// fp32 FMA).  The epilogues therefore scale the main accumulator back by (1 + kappa * (K/16 + 1) * 2^-24), folded
+// into the join of the two accumulators (one extra FMA per element).  DMC_ACC_COMP=<kappa> overrides (0 = off).
+static float g_acc_kappa = -1.0f;
+float acc_comp_kappa() {
+  if (g_acc_kappa < 0.0f) {
+    const char* e = getenv("DMC_ACC_COMP");
+    g_acc_kappa = e ? (float)atof(e) : 0.276f;
+    if (!(g_acc_kappa >= 0.0f)) g_acc_kappa = 0.0f;
+  }
+  return g_acc_kappa;
+}
+void acc_comp_set_kappa(float k) { g_acc_kappa = k >= 0.0f ? k : 0.0f; }
+float acc_comp_scaled(int K) {
+  const float steps = (float)((K + 15) / 16 + 1);
+  return acc_comp_kappa() * steps * (kLoScale / 16777216.0f);      // kappa * steps * 2^-24, pre-scaled by 2^11
 }
 
 // ------------------------------------------------------------------ weights
@@ -270,25 +297,32 @@ void regrid(View in, int Hin, int Win, View out, int Hout, int Wout, int B, cuda
   launch(k_regrid, cdiv(n, 256), 256, 0, st, in, Hin, Win, out, Hout, Wout, B, C8);
 }
 
-__global__ void k_finite_check(View v, long long M, int C8, int* flag) {
+// One launch checks up to 8 tensors (blockIdx.y = tensor): bit i of *flag is set if tensor i holds a non-finite value
+// or one saturated at the fp16 range limit of the split storage format (|x| >= 65504 cannot be represented).
+__global__ void k_finite_check(FiniteList l, int* flag) {
   pdl_prologue_done();
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * C8) return;
-  long long m = idx / C8;
-  int c = (int)(idx % C8) * 8;
-  // hi plane: inf / nan, or saturated at the fp16 range limit (|x| >= 65504 cannot be represented)
-  uint4 a = *reinterpret_cast<const uint4*>(v.p + s3_unit_offset(v, m, c));
-  const uint32_t* u = &a.x;
+  const int t = blockIdx.y;
+  const View v = l.v[t];
+  const int C8 = v.C / 8;
+  const long long n = l.M[t] * C8;
   bool bad = false;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / C8;
+    const int c = (int)(idx % C8) * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(v.p + s3_unit_offset(v, m, c));
+    const uint32_t* u = &a.x;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    bad |= ((u[i] & 0x7fffu) >= 0x7bffu) | ((u[i] & 0x7fff0000u) >= 0x7bff0000u);
+    for (int i = 0; i < 4; ++i) bad |= ((u[i] & 0x7fffu) >= 0x7bffu) | ((u[i] & 0x7fff0000u) >= 0x7bff0000u);
   }
-  if (bad) atomicOr(flag, 1);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1 << t);
 }
-void finite_check(View v, long long M, int* flag, cudaStream_t st) {
-  int C8 = v.C / 8;
-  launch(k_finite_check, cdiv(M * C8, 256), 256, 0, st, v, M, C8, flag);
+void finite_check(const FiniteList& l, int* flag, cudaStream_t st) {
+  if (l.n < 1) return;
+  long long most = 0;
+  for (int i = 0; i < l.n; ++i) most = l.M[i] * (l.v[i].C / 8) > most ? l.M[i] * (l.v[i].C / 8) : most;
+  unsigned gx = cdiv(most, 256 * 8);
+  if (gx < 1) gx = 1;
+  launch(k_finite_check, dim3(gx, l.n), 256, 0, st, l, flag);
 }
 
 // ------------------------------------------------------------------ depthwise 3x3 (layers.py:56)

@@ -8,6 +8,10 @@ namespace dmc {
 int num_sms();
 void note_launch();            // every kernel launch of the library is counted
 long long launch_count();
+// accumulate-truncation compensation of the tcgen05 kernels (kernels.cu): kappa in units of 2^-24 per MMA step
+float acc_comp_kappa();
+void acc_comp_set_kappa(float k);
+float acc_comp_scaled(int K);      // kappa * (K/16 + 1) * 2^-24 * 2^11 (the scale of the second accumulator)
 bool pdl_enabled();            // programmatic dependent launch: DMC_PDL=0/1 forces it, else per frame size
 void pdl_set_auto(bool on);
 
@@ -65,7 +69,9 @@ void scale_cols(View in, const float* scale, View out, long long M, cudaStream_t
 void copy_view(View in, View out, long long M, cudaStream_t st);
 // (B,Hin,Win,C) -> (B,Hout,Wout,C): replicate pad right/bottom (inference.py:40-43) or crop to the top-left corner
 void regrid(View in, int Hin, int Win, View out, int Hout, int Wout, int B, cudaStream_t st);
-void finite_check(View v, long long M, int* flag, cudaStream_t st);
+// bit i of *flag |= tensor i has a non-finite / fp16-saturated element (one launch for up to 8 tensors)
+struct FiniteList { View v[8]; long long M[8]; int n; };
+void finite_check(const FiniteList& l, int* flag, cudaStream_t st);
 
 // ---------------- convolution pieces ----------------
 void dwconv3x3(View in, const float* w9c, const float* bias, View out, int B, int H, int W,

@@ -19,7 +19,9 @@ training mode, or with autograd enabled raises.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -29,7 +31,7 @@ from torch import nn
 from . import _capi
 
 __all__ = ["DMCConfig", "DMC_old", "DMC_performance", "DMC_fast", "DMC_mask_prop", "DMCI",
-           "P_MODELS", "build_p_model"]
+           "P_MODELS", "build_p_model", "NonFiniteError"]
 
 
 @dataclass
@@ -87,35 +89,71 @@ def _up2(cin, cout):        # ResidualBlockUpsample + SubpelConv2x, layers.py:22
     return _Tree(("up", _Tree(("conv", _seq(_c(cin, cout * 4, 1))))), ("conv", _dcb(cout, cout)))
 
 
+class _Bitparm(nn.Module):
+    """Parameters of Bitparm, entropy_models.py:84-97 (normal(0, 0.01) init; the final one has no `a`)."""
+
+    def __init__(self, qp_num, ch, final):
+        super().__init__()
+        def table():
+            return nn.Parameter(torch.nn.init.normal_(torch.empty(qp_num, ch, 1, 1), 0, 0.01))
+        self.h = table()
+        self.b = table()
+        if not final:
+            self.a = table()
+
+
 def _bit_estimator(qp_num, ch):
-    """BitEstimator / Bitparm, entropy_models.py:84-97,129-137 (normal(0, 0.01) init)."""
-    def table():
-        return nn.Parameter(torch.nn.init.normal_(torch.empty(qp_num, ch, 1, 1), 0, 0.01))
-
-    class _Bitparm(nn.Module):
-        def __init__(self, final):
-            super().__init__()
-            self.h = table()
-            self.b = table()
-            if not final:
-                self.a = table()
-
-    return _Tree(("f1", _Bitparm(False)), ("f2", _Bitparm(False)), ("f3", _Bitparm(False)),
-                 ("f4", _Bitparm(True)))
+    """BitEstimator, entropy_models.py:129-137."""
+    return _Tree(("f1", _Bitparm(qp_num, ch, False)), ("f2", _Bitparm(qp_num, ch, False)),
+                 ("f3", _Bitparm(qp_num, ch, False)), ("f4", _Bitparm(qp_num, ch, True)))
 
 
 # --------------------------------------------------------------------------
 # engine plumbing shared by all models
 # --------------------------------------------------------------------------
+# Any nn.Module.register_parameter anywhere (also `module.weight = nn.Parameter(...)`) bumps this counter; the
+# modules below rebuild their cached parameter list when it moved, so a re-registered Parameter is never served from
+# a stale list.
+_param_generation = [0]
+
+
+def _on_register_parameter(module, name, param):
+    _param_generation[0] += 1
+    return None
+
+
+torch.nn.modules.module.register_module_parameter_registration_hook(_on_register_parameter)
+
+
+class NonFiniteError(RuntimeError):
+    """The reference's `[NaNGuard]` RuntimeError (seg_video_model_fast.py:152-156)."""
+
+
 class _EngineModule(nn.Module):
     variant = "old"
     #: engine flags (see include/dmc_b200.h); tests switch these per instance
     engine_flags = 0
+    #: engines kept alive per module, one per (B, H, W, device, flags); the least recently used one is destroyed
+    #: beyond this (each holds 1.6-4 GB of workspace at 1920x1280)
+    max_engines = 4
+    #: every N-th forward the parameters are also checksummed on the device.  Writes through `.data`
+    #: (`p.data.copy_(...)`, trainer_seg_video_model.py:789-791) change neither the storage pointer nor the version
+    #: counter; they are caught here, or at once by calling `invalidate_weights()` after such a write.
+    checksum_every = 32
+    #: True: read the finite flag back after every forward and raise like the reference's _finite_check (one host
+    #: sync per frame).  False (default): the flag is copied to pinned memory asynchronously and examined without
+    #: blocking on later calls / by `check_finite()`, so the error surfaces at most a few frames late.
+    strict_finite = os.environ.get("DMC_B200_STRICT_FINITE", "0") == "1"
 
     def _init_engine_state(self):
-        self._engines: Dict[tuple, int] = {}
-        self._weights_sig: Dict[tuple, tuple] = {}
-        self._lib = None
+        self.__dict__["_engines"] = collections.OrderedDict()     # key -> handle, least recently used first
+        self.__dict__["_weights_sig"] = {}
+        self.__dict__["_weights_sum"] = {}
+        self.__dict__["_lib"] = None
+        self.__dict__["_param_cache"] = None
+        self.__dict__["_param_gen"] = -1
+        self.__dict__["_calls"] = 0
+        self.__dict__["_finite"] = None
 
     # -- lifetime ----------------------------------------------------------
     def __del__(self):
@@ -125,12 +163,29 @@ class _EngineModule(nn.Module):
             pass
 
     def release_engines(self):
-        lib = getattr(self, "_lib", None)
-        for h in getattr(self, "_engines", {}).values():
+        """Destroys every engine of this module (their workspaces are freed); the next forward rebuilds what it needs.
+        Call it when the working resolution changes for good."""
+        lib = self.__dict__.get("_lib")
+        for h in self.__dict__.get("_engines", {}).values():
             if lib is not None:
                 lib.dmc_destroy(h)
-        self._engines = {}
-        self._weights_sig = {}
+        self._init_engine_state()
+
+    def invalidate_weights(self):
+        """Forces a repack of the weights on the next forward (use after writing parameters through `.data`)."""
+        self.__dict__["_weights_sig"] = {}
+        self.__dict__["_param_cache"] = None
+
+    # engine handles, the ctypes library and the caches are process-local: copies / pickles start without them
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in ("_engines", "_weights_sig", "_weights_sum", "_lib", "_param_cache", "_param_gen", "_calls", "_finite"):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._init_engine_state()
 
     # -- helpers -----------------------------------------------------------
     def _check_mode(self, x: torch.Tensor):
@@ -144,47 +199,78 @@ class _EngineModule(nn.Module):
         if x.dtype != torch.float32:
             raise TypeError("dmc_b200: float32 input expected")
 
-    def _signature(self):
-        """(storage pointer, version counter) of every parameter.  Walking the module tree costs ~1 ms per call
-        (378 tensors); the list of Parameter objects is therefore cached and rebuilt every 256 calls and whenever
-        `_apply` (`.to()`, `.cuda()`) or `load_state_dict` runs -- in-place edits are caught by the version
-        counters, `.data` swaps by the pointers, re-registered Parameters by the periodic rebuild."""
+    @staticmethod
+    def _check_tensor(name: str, t: torch.Tensor, shape, device):
+        """Same-device float32 tensor of the exact shape, or the shape error the reference's first conv would raise:
+        the kernels read raw pointers, a wrong tensor would be an out-of-bounds access instead of an exception."""
+        if not torch.is_tensor(t):
+            raise TypeError(f"dmc_b200: {name} must be a tensor, got {type(t).__name__}")
+        if t.device != device:
+            raise RuntimeError(f"dmc_b200: {name} is on {t.device}, the input is on {device}")
+        if t.dtype != torch.float32:
+            raise TypeError(f"dmc_b200: {name} must be float32, got {t.dtype}")
+        if tuple(t.shape) != tuple(shape):
+            raise RuntimeError(f"dmc_b200: {name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+
+    def _params(self):
         cache = self.__dict__.get("_param_cache")
-        age = self.__dict__.get("_param_cache_age", 0)
-        if cache is None or age >= 256:
+        if cache is None or self.__dict__.get("_param_gen") != _param_generation[0]:
             cache = list(self.parameters())
             self.__dict__["_param_cache"] = cache
-            age = 0
-        self.__dict__["_param_cache_age"] = age + 1
-        return tuple((p.data_ptr(), p._version) for p in cache)
+            self.__dict__["_param_gen"] = _param_generation[0]
+        return cache
+
+    def _signature(self):
+        """(storage pointer, version counter) of every parameter: in-place edits bump the version, `.data = ...`
+        swaps change the pointer, re-registration rebuilds the list (global registration hook), `.to()` /
+        `load_state_dict` drop it.  What none of these see -- writes THROUGH `.data` -- is covered by the periodic
+        device checksum in `_engine` and by `invalidate_weights()`."""
+        return tuple((p.data_ptr(), p._version) for p in self._params())
+
+    def _checksum(self):
+        ps = [p.detach() for p in self._params() if p.is_cuda]
+        if not ps:
+            return None
+        norms = torch.stack(torch._foreach_norm(ps)).double()
+        return float((norms * torch.arange(1, len(ps) + 1, device=norms.device, dtype=torch.float64)).sum())
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__["_param_cache"] = None
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
-        self.__dict__["_param_cache"] = None
+        self.invalidate_weights()
         return super().load_state_dict(*args, **kwargs)
 
     def _engine(self, B: int, H: int, W: int, device: torch.device):
-        if self._lib is None:
-            self._lib = _capi.load()
+        if self.__dict__.get("_lib") is None:
+            self.__dict__["_lib"] = _capi.load()
         lib = self._lib
         key = (B, H, W, device.index, int(self.engine_flags))
-        h = self._engines.get(key)
+        engines = self._engines
+        h = engines.get(key)
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         if h is None:
+            while len(engines) >= max(1, int(self.max_engines)):
+                old_key, old_h = engines.popitem(last=False)
+                lib.dmc_destroy(old_h)                     # (cudaFree synchronises: nothing of it is in flight)
+                self._weights_sig.pop(old_key, None)
+                self._weights_sum.pop(old_key, None)
             out = ctypes.c_void_p()
             with torch.cuda.device(device):
                 rc = lib.dmc_create(_capi.VARIANT_IDS[self.variant], B, H, W, int(self.engine_flags),
                                     ctypes.byref(out))
             _capi.check(rc, None)
             h = out.value
-            self._engines[key] = h
+            engines[key] = h
+        else:
+            engines.move_to_end(key)
+        self.__dict__["_calls"] += 1
         sig = self._signature()
-        if self._weights_sig.get(key) != sig:
-            # (re)pack: keyed on parameter storage + version counters so in-place edits such as the
-            # trainer's conv inflation (trainer_seg_video_model.py:789-791) are picked up
+        stale = self._weights_sig.get(key) != sig
+        if not stale and self.checksum_every and self._calls % int(self.checksum_every) == 0:
+            stale = self._checksum() != self._weights_sum.get(key)
+        if stale:
             sd = self.state_dict()
             keep = []                      # converted copies must outlive the async repack kernels
             for i in range(lib.dmc_num_weights(h)):
@@ -201,17 +287,74 @@ class _EngineModule(nn.Module):
                 torch.cuda.current_stream(device).synchronize()
             _capi.check(lib.dmc_finalize_weights(h, stream), h)
             self._weights_sig[key] = sig
+            self._weights_sum[key] = self._checksum() if self.checksum_every else None
         return h, stream
+
+    # -- finite flag (the reference's _finite_check, seg_video_model_fast.py:152-156) ------------------
+    class _FiniteRing:
+        """Device flag words + pinned mirrors + events: the check of forward n is examined, without blocking, during
+        forward n+1, n+2, ... (or by check_finite()), so it costs no host sync."""
+        SLOTS = 4
+
+        def __init__(self, device):
+            self.dev = torch.zeros(self.SLOTS, dtype=torch.int32, device=device)
+            self.host = torch.zeros(self.SLOTS, dtype=torch.int32).pin_memory()
+            self.events = [None] * self.SLOTS
+            self.calls = [0] * self.SLOTS
+            self.next = 0
+
+    def _finite_slot(self, device):
+        ring = self.__dict__.get("_finite")
+        if ring is None or ring.dev.device != device:
+            ring = self._FiniteRing(device)
+            self.__dict__["_finite"] = ring
+        self._poll_finite(block_slot=ring.next)            # the slot about to be reused must have been examined
+        return ring, ring.next
+
+    def _finite_submit(self, ring, slot):
+        ring.host[slot:slot + 1].copy_(ring.dev[slot:slot + 1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(ring.dev.device))
+        ring.events[slot] = ev
+        ring.calls[slot] = self._calls
+        ring.next = (slot + 1) % ring.SLOTS
+        if self.strict_finite:
+            self._poll_finite(block_slot=slot)
+
+    def _poll_finite(self, block_slot=None, block_all=False):
+        ring = self.__dict__.get("_finite")
+        if ring is None:
+            return
+        for i, ev in enumerate(ring.events):
+            if ev is None:
+                continue
+            if block_all or i == block_slot:
+                ev.synchronize()
+            elif not ev.query():
+                continue
+            ring.events[i] = None
+            bits = int(ring.host[i])
+            if bits:
+                tags = ", ".join(t for b, t in enumerate(_capi.FINITE_TAGS) if bits >> b & 1)
+                raise NonFiniteError(f"[NaNGuard] non-finite activations after {tags} (forward call {ring.calls[i]} of this "
+                                     f"module; values at or beyond the fp16 range limit 65504 of the split storage "
+                                     f"format count as non-finite)")
+
+    def check_finite(self):
+        """Blocks until every outstanding finite check of this module has been examined; raises like the reference's
+        `_finite_check` if one of them failed."""
+        self._poll_finite(block_all=True)
 
     def get_tap(self, name: str, x_like: torch.Tensor) -> torch.Tensor:
         """Intermediate tensor of the last forward (engine_flags must include FLAG_KEEP_TAPS)."""
         B, _, H, W = x_like.shape
         h, stream = self._engine(B, H, W, x_like.device)
         shape = (ctypes.c_int64 * 4)()
-        _capi.check(self._lib.dmc_get_tap(h, name.encode(), None, 0, shape, stream), h)
-        out = torch.empty(tuple(shape), dtype=torch.float32, device=x_like.device)
-        _capi.check(self._lib.dmc_get_tap(h, name.encode(), ctypes.c_void_p(out.data_ptr()), out.numel(),
-                                          shape, stream), h)
+        with torch.cuda.device(x_like.device):
+            _capi.check(self._lib.dmc_get_tap(h, name.encode(), None, 0, shape, stream), h)
+            out = torch.empty(tuple(shape), dtype=torch.float32, device=x_like.device)
+            _capi.check(self._lib.dmc_get_tap(h, name.encode(), ctypes.c_void_p(out.data_ptr()), out.numel(),
+                                              shape, stream), h)
         return out
 
 
@@ -292,14 +435,18 @@ class _DMCBase(_EngineModule):
         if H % need or W % need:
             raise RuntimeError(f"dmc_b200: height and width must be multiples of {need} for variant {self.variant}")
         x_img = x_img.contiguous()
+        dev = x.device
         frame = feature = None
         if after_i:
-            frame = dpb["frame"].contiguous()
+            frame = dpb["frame"]
+            self._check_tensor("dpb['frame']", frame, (B, 3, H, W), dev)
+            frame = frame.contiguous()
         else:
             if dpb.get("feature") is None:
                 raise RuntimeError("dpb['feature'] is None on a non-first P frame")
-            feature = dpb["feature"].contiguous()
-        dev = x.device
+            feature = dpb["feature"]
+            self._check_tensor("dpb['feature']", feature, (B, self.cfg.ch_d, H // 8, W // 8), dev)
+            feature = feature.contiguous()
         h, stream = self._engine(B, H, W, dev)
         x_hat = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
         feat = torch.empty((B, self.cfg.ch_d, H // 8, W // 8), dtype=torch.float32, device=dev)
@@ -307,10 +454,13 @@ class _DMCBase(_EngineModule):
         mask_pred = None
         if self.variant == "mask_prop" and not after_i and mask is not None:
             mask_pred = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
-        rc = self._lib.dmc_forward(h, _ptr(x_img), _ptr(mask), _ptr(frame), _ptr(feature), int(qp),
-                                   1 if after_i else 0, _ptr(x_hat), _ptr(feat), _ptr(bpp3),
-                                   _ptr(mask_pred), ctypes.c_void_p(), stream)
-        _capi.check(rc, h)
+        ring, slot = self._finite_slot(dev)
+        with torch.cuda.device(dev):
+            rc = self._lib.dmc_forward(h, _ptr(x_img), _ptr(mask), _ptr(frame), _ptr(feature), int(qp),
+                                       1 if after_i else 0, _ptr(x_hat), _ptr(feat), _ptr(bpp3),
+                                       _ptr(mask_pred), ctypes.c_void_p(ring.dev.data_ptr() + 4 * slot), stream)
+            _capi.check(rc, h)
+            self._finite_submit(ring, slot)
         out = {"dpb": {"frame": x_hat, "feature": feat}, "bpp": bpp3[:, 0], "bpp_y": bpp3[:, 1],
                "bpp_z": bpp3[:, 2]}
         if self.variant == "fast":
@@ -432,7 +582,8 @@ class DMCI(_EngineModule):
         h, stream = self._engine(B, H, W, x.device)
         x_hat = torch.empty_like(x)
         bpp3 = torch.empty((B, 3), dtype=torch.float32, device=x.device)
-        _capi.check(self._lib.dmci_forward(h, _ptr(x), int(qp), _ptr(x_hat), _ptr(bpp3), stream), h)
+        with torch.cuda.device(x.device):
+            _capi.check(self._lib.dmci_forward(h, _ptr(x), int(qp), _ptr(x_hat), _ptr(bpp3), stream), h)
         return {"dpb": {"frame": x_hat, "feature": None}, "bpp": bpp3[:, 0], "bpp_y": bpp3[:, 1],
                 "bpp_z": bpp3[:, 2], "bits_y": torch.Size((B, 256, H // 16, W // 16)),
                 "bits_z": torch.Size((B, 128, H // 64, W // 64))}

@@ -102,9 +102,7 @@ def test_gop_qp_schedule():
 def test_weight_signature_cache_sees_edits_moves_and_reloads():
     """The drop-in modules re-pack their weights when a parameter changes: the signature is built from a cached
     parameter list (walking the module tree costs ~1 ms per forward) and must still see in-place edits, `.to()` /
-    `load_state_dict`, and -- at the periodic rebuild -- a re-registered Parameter."""
-    import torch
-    import dmc_b200 as D
+    `load_state_dict`, and -- immediately, through the global registration hook -- a re-registered Parameter."""
     m = D.build_p_model("old").eval()
     s0 = m._signature()
     assert m._signature() == s0
@@ -117,10 +115,53 @@ def test_weight_signature_cache_sees_edits_moves_and_reloads():
     assert s2 != s1
     m = m.double().float()                                  # _apply: new storages
     assert m._signature() != s2
-    first = next(iter(m._parameters)) if m._parameters else None
     name, mod = next((n, sub) for n, sub in m.named_modules() if getattr(sub, "weight", None) is not None)
     s3 = m._signature()
-    mod.weight = torch.nn.Parameter(mod.weight.detach().clone())   # re-registered: caught by the periodic rebuild
-    for _ in range(257):
-        s4 = m._signature()
-    assert s4 != s3
+    mod.weight = torch.nn.Parameter(mod.weight.detach().clone())   # re-registered: the very next signature differs
+    assert m._signature() != s3
+
+
+def test_writes_through_data_need_the_checksum_or_invalidate():
+    """`p.data.copy_()` (trainer_seg_video_model.py:789-791) bumps no version counter and keeps the pointer: the
+    signature cannot see it.  The periodic device checksum does (GPU test), and `invalidate_weights()` forces the
+    repack at once."""
+    m = D.build_p_model("old").eval()
+    s0 = m._signature()
+    p = next(m.parameters())
+    p.data.copy_(p.data + 1.0)
+    assert m._signature() == s0                             # the blind spot the checksum exists for
+    m._weights_sig[("key",)] = s0
+    m.invalidate_weights()
+    assert m._weights_sig == {}
+
+
+def test_modules_copy_and_pickle_without_engine_state():
+    """Engine handles / the ctypes library are process-local: deepcopy and pickle drop them (a copied raw handle
+    would be destroyed twice)."""
+    import copy
+    import pickle
+    m = D.build_p_model("fast").eval()
+    m._engines[(1, 64, 64, 0, 0)] = 12345                   # a fake handle: must not travel
+    m.__dict__["_lib"] = None
+    c = copy.deepcopy(m)
+    assert c._engines == {} and c is not m
+    assert all(torch.equal(a, b) for a, b in zip(c.state_dict().values(), m.state_dict().values()))
+    r = pickle.loads(pickle.dumps(m))
+    assert r._engines == {} and set(r.state_dict()) == set(m.state_dict())
+    m._engines.clear()
+
+
+def test_reference_copy_matches_shim_initialisation():
+    """oracle/_ref (the unmodified reference modules, copied by oracle/make_ref.py) and the drop-in modules give the
+    same parameters under the same seed: same keys, shapes and values."""
+    from oracle import make_ref
+    if not make_ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    R = make_ref.load_reference()
+    for variant in ("old", "performance", "fast", "mask_prop"):
+        torch.manual_seed(7)
+        ref = R[variant]().state_dict()
+        torch.manual_seed(7)
+        mine = D.build_p_model(variant).state_dict()
+        assert list(ref) == list(mine)
+        assert all(torch.equal(ref[k], mine[k]) for k in ref)
