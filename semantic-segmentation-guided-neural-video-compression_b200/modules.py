@@ -58,6 +58,10 @@ class _Tree(nn.Module):
         for name, mod in children:
             self.add_module(str(name), mod)
 
+    def __getitem__(self, name):
+        """tree[3] / tree["down"]: the child registered under that name (like nn.Sequential indexing)."""
+        return self._modules[str(name)]
+
     def forward(self, *a, **k):  # pragma: no cover
         raise RuntimeError("parameter container: the computation lives in the CUDA engine")
 

@@ -1,0 +1,172 @@
+"""Parity at the full size of BASELINE.json configs 3, 4 and 5 (1920x1280), through the C ABI, against the oracle.
+
+  config 3   dmc_variant=fast, batch 8 GOPs: gates per batch item, identical inputs
+  config 4   dmc_variant=mask_prop, 32-frame GOP with the mask feedback protocol of SURVEY.md 8(d):
+             (a) every call on identical inputs (the oracle's dpb and fed-back mask): all gates;
+             (b) free running (the CUDA path's own dpb and its own fed-back mask): bpp / PSNR / ROI-PSNR gates on all
+                 31 P frames, symbol-match curve recorded (gpurun_out/symbols_config4_free_running.txt)
+  config 5   several independent `performance` clips, sharded like bench.py --gpus N, statistics accumulated by the
+             ClipStats kernel and merged as the all-reduce does: equal to the statistics of the oracle's run_gop
+
+Gates (BASELINE.json north_star): >= 99.99 % of quantised y symbols identical (<= 122 of 1 228 800), estimated bpp
+within 1e-3 relative, PSNR and ROI-PSNR within 0.02 dB.
+"""
+import os
+
+import pytest
+import torch
+
+from helpers import BPP_REL_TOL, D, O, PSNR_TOL_DB, ROOT, SYMBOL_MATCH_MIN, gc, rel_err, sd_of, symbol_match
+
+pytestmark = pytest.mark.gpu
+capi = D._capi
+H, W = 1280, 1920
+
+
+def _cuda(dpb):
+    return {k: (v.cuda() if v is not None else None) for k, v in dpb.items()}
+
+
+def _models(variant):
+    torch.manual_seed(gc.SEED_P)
+    mp = D.build_p_model(variant).eval()
+    sd = sd_of(mp)
+    mp = mp.cuda()
+    mp.engine_flags = capi.FLAG_KEEP_TAPS
+    return mp, sd
+
+
+def _item_metrics(x_hat, target, mask):
+    return [gc.metrics(x_hat[b:b + 1], target[b:b + 1], mask[b:b + 1] if mask is not None else None)
+            for b in range(x_hat.shape[0])]
+
+
+def test_config3_fast_batch8_full_size():
+    """`fast`, B = 8, 1920x1280: two P frames (after_i True / False), every call on identical inputs, every gate per
+    batch item (bpp is per sample in the reference: video_model.py:376-378)."""
+    B = 8
+    frames, masks = D.clips.synthetic_clip(31, B, 3, H, W)
+    mp, sd = _models("fast")
+    with torch.no_grad():
+        dpb_o = {"frame": frames[:, 0], "feature": None}     # any frame in [0,1] is a legal reference frame
+        for t in (1, 2):
+            qp = mp.shift_qp(32, O.INDEX_MAP[t % 8])
+            x = torch.cat([frames[:, t], masks[:, t]], 1)
+            taps = {}
+            o = O.dmc_forward(sd, "fast", x, qp, dpb_o, after_i=(t == 1), taps=taps)
+            c = mp(x.cuda(), qp, _cuda(dpb_o), after_i=(t == 1))
+            y_c = mp.get_tap("y_q", x.cuda()).cpu()
+            z_c = mp.get_tap("z_hat", x.cuda()).cpu()
+            s_c = mp.get_tap("scales_hat", x.cuda()).cpu()
+            xo, xc = o["dpb"]["frame"], c["dpb"]["frame"].cpu()
+            mo, mc = _item_metrics(xo, frames[:, t], masks[:, t]), _item_metrics(xc, frames[:, t], masks[:, t])
+            for b in range(B):
+                frac, bad = symbol_match(y_c[b], taps["y_q"][b])
+                assert frac >= SYMBOL_MATCH_MIN, (t, b, "y symbols", frac, bad)
+                frac_z, bad_z = symbol_match(z_c[b], taps["z_hat"][b])
+                assert frac_z >= SYMBOL_MATCH_MIN, (t, b, "z symbols", frac_z, bad_z)
+                for k in ("bpp", "bpp_y", "bpp_z"):
+                    assert rel_err(c[k][b].cpu(), o[k][b]) <= BPP_REL_TOL, (t, b, k)
+                assert abs(mo[b][0] - mc[b][0]) <= PSNR_TOL_DB and abs(mo[b][1] - mc[b][1]) <= PSNR_TOL_DB, (t, b)
+            # scales_hat: the sigma the likelihood sees; equal wherever the symbol agrees up to the contraction's
+            # accuracy (2e-5 of the scale)
+            same = y_c == taps["y_q"]
+            ds = (s_c - taps["scales_hat"]).abs()[same]
+            assert float(ds.max()) <= 1e-4 * max(1.0, float(taps["scales_hat"].abs().max())), (t, float(ds.max()))
+            assert c["mask_pred"] is None if t == 1 else torch.equal(c["mask_pred"].cpu(), masks[:, t])
+            dpb_o = o["dpb"]
+    mp.check_finite()
+
+
+def test_config4_mask_prop_gop32_full_size():
+    """`mask_prop`, 1 I + 31 P at 1920x1280 with mask feedback (t = 1: GT mask, t = 2: mask 1 again, t >= 3: the
+    previous frame's thresholded prediction)."""
+    T = 32
+    frames, masks = D.clips.synthetic_clip(41, 1, T, H, W)
+    torch.manual_seed(gc.SEED_I)
+    mi = D.DMCI().eval()
+    sd_i = sd_of(mi)
+    mi = mi.cuda()
+    mp, sd = _models("mask_prop")
+    fr, mk = frames.cuda(), masks.cuda()
+    curve = []
+    with torch.no_grad():
+        o = O.dmci_forward(sd_i, frames[:, 0], 32)
+        c = mi(fr[:, 0], 32)
+        assert rel_err(c["bpp"].cpu(), o["bpp"]) <= BPP_REL_TOL
+        del mi
+        torch.cuda.empty_cache()
+        dpb_o, dpb_f = o["dpb"], c["dpb"]                  # oracle chain / free-running CUDA chain
+        pred_o = pred_f = None
+        for t in range(1, T):
+            qp = mp.shift_qp(32, O.INDEX_MAP[t % 8])
+            if t == 1:
+                m_o, m_f = masks[:, 1], mk[:, 1]
+            elif t == 2 or pred_o is None:
+                m_o, m_f = masks[:, 1], mk[:, 1]
+            else:
+                m_o, m_f = (pred_o > 0).float(), (pred_f > 0).float()
+            x_o = torch.cat([frames[:, t], m_o], 1)
+            taps = {}
+            o = O.dmc_forward(sd, "mask_prop", x_o, qp, dpb_o, after_i=(t == 1), taps=taps)
+            po, ro = gc.metrics(o["dpb"]["frame"], frames[:, t], masks[:, t])
+            # (a) identical inputs: the oracle's dpb and the oracle's fed-back mask
+            ca = mp(x_o.cuda(), qp, _cuda(dpb_o), after_i=(t == 1))
+            frac, bad = symbol_match(mp.get_tap("y_q", x_o.cuda()).cpu(), taps["y_q"])
+            assert frac >= SYMBOL_MATCH_MIN, (t, "y symbols on identical inputs", frac, bad)
+            for k in ("bpp", "bpp_y", "bpp_z"):
+                assert rel_err(ca[k].cpu(), o[k]) <= BPP_REL_TOL, (t, k)
+            pa, ra = gc.metrics(ca["dpb"]["frame"].cpu(), frames[:, t], masks[:, t])
+            assert abs(po - pa) <= PSNR_TOL_DB and abs(ro - ra) <= PSNR_TOL_DB, (t, po, pa, ro, ra)
+            if o["mask_pred"] is not None:
+                dm = (o["mask_pred"] - ca["mask_pred"].cpu()).abs()
+                assert float(dm.max()) <= 1e-4 * max(1.0, float(o["mask_pred"].abs().max())), (t, float(dm.max()))
+            # (b) free running: own dpb, own fed-back mask
+            x_f = torch.cat([fr[:, t], m_f], 1)
+            cf = mp(x_f, qp, dpb_f, after_i=(t == 1))
+            frac_f, bad_f = symbol_match(mp.get_tap("y_q", x_f).cpu(), taps["y_q"])
+            pf, rf = gc.metrics(cf["dpb"]["frame"].cpu(), frames[:, t], masks[:, t])
+            bpp_f = rel_err(cf["bpp"].cpu(), o["bpp"])
+            mask_px = int(((m_f.cpu() > 0) != (m_o > 0)).sum())
+            curve.append((t, bad, bad_f, bpp_f, abs(po - pf), abs(ro - rf), mask_px))
+            assert bpp_f <= BPP_REL_TOL, (t, "free-running bpp", bpp_f)
+            assert abs(po - pf) <= PSNR_TOL_DB and abs(ro - rf) <= PSNR_TOL_DB, (t, "free-running PSNR", po, pf, ro, rf)
+            dpb_o, dpb_f = o["dpb"], cf["dpb"]
+            pred_o, pred_f = o["mask_pred"], cf["mask_pred"]
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "symbols_config4_free_running.txt"), "w") as f:
+        f.write("mask_prop 1920x1280 1 I + 31 P, mask feedback; y symbols differing from the oracle (of 1 228 800)\n")
+        f.write("frame  identical-inputs  free-running  bpp-rel(free)  dPSNR(free)  dROI-PSNR(free)  fed-back-mask-pixels-differing\n")
+        for row in curve:
+            f.write("%5d  %16d  %12d  %13.2e  %11.1e  %15.1e  %d\n" % row)
+    mp.check_finite()
+
+
+def test_config5_multi_clip_statistics_match_oracle():
+    """Independent `performance` clips (1 I + 2 P each, free running), sharded over two ranks the way
+    bench.py --gpus 2 shards them; each rank accumulates with the ClipStats kernel, the vectors are summed as the
+    all-reduce does.  The merged statistics equal those of the oracle's run_gop over the same clips."""
+    n_clips, T = 3, 3
+    torch.manual_seed(gc.SEED_I)
+    mi = D.DMCI().eval()
+    sd_i = sd_of(mi)
+    mi = mi.cuda()
+    mp, sd = _models("performance")
+    ranks = [D.clips.ClipStats("cuda") for _ in range(2)]
+    ref = D.clips.ClipStats("cpu")
+    for rank in range(2):
+        for cidx in D.clips.shard_clips(n_clips, rank, 2):
+            frames, masks = D.clips.synthetic_clip(500 + cidx, 1, T, H, W)
+            outs_o = O.run_gop(sd_i, sd, "performance", frames, masks, 32)
+            for t in range(1, T):
+                ref.add_frame(outs_o[t], frames[:, t], masks[:, t])
+            D.clips.run_gop(mi, mp, "performance", frames.cuda(), masks.cuda(), 32, stats=ranks[rank])
+    merged = D.clips.ClipStats("cpu")
+    merged.vec = ranks[0].vec.cpu() + ranks[1].vec.cpu()           # what the NCCL sum all-reduce produces
+    s, r = merged.summary(), ref.summary()
+    assert s["frames"] == r["frames"] == n_clips * (T - 1)
+    for k in ("bpp", "bpp_y", "bpp_z"):
+        assert abs(s[k] - r[k]) <= BPP_REL_TOL * r[k], (k, s[k], r[k])
+    assert abs(s["psnr"] - r["psnr"]) <= PSNR_TOL_DB and abs(s["roi_psnr"] - r["roi_psnr"]) <= PSNR_TOL_DB
+    assert merged.vec[4] == ref.vec[4] and merged.vec[5] == ref.vec[5]      # ROI / element counts are exact

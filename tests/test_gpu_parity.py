@@ -153,20 +153,21 @@ def test_gaussian_bits_match_oracle(formula):
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     capi.check(capi.load().dmc_op_gaussian_bits(_p(sb), _p(gb), _p(out), n, formula, st), None)
     out = out.cpu()
-    # The reference formulas difference two erf values that are both ~ +-1 for |z| > 3.5, so p lives on
-    # the fp32 cancellation grid (multiples of 3e-8) and ONE ulp of erf moves it by a whole quantum:
-    # torch's own CPU erf vs a correctly rounded erf already differ on 3 % of inputs, which moves
-    # 0.2-0.3 % of these synthetic elements by > 1e-3 bit (up to 5 bits under the 1e-9 floor of formula 1)
-    # and the formula-1 sum by 4e-4.  The kernel uses a correctly rounded erf; gates: few elements off,
-    # the sum (= bpp) inside the north-star 1e-3, and tight for the well-conditioned formula 0.
+    # The kernel evaluates erf as the reference's CPU path does (correctly rounded from fp64, saturated to +-1 from
+    # |x| >= 3.832507 like MKL's vsErf).  What remains: vsErf differs from the correctly rounded value by one ulp on
+    # ~5 % of its inputs, and for tail symbols p is a difference of two erf values next to +-1, so one ulp is a whole
+    # quantum of p (3e-8).  A CPU emulation of the kernel's formulas against the oracle on these inputs gives:
+    # 0.09-0.10 % of the elements off by > 1e-3 bit, max 0.0086 bit (formula 0) / 1.0 bit (formula 1: a quantum next
+    # to the 1e-9 floor), sums within 7e-8 / 1.9e-6 relative.  Gates = those figures with a 3x margin.
     d = (out - ref).abs()
-    assert float((d > 1e-3).float().mean()) <= 1e-2
+    assert float((d > 1e-3).float().mean()) <= 3e-3
+    tot, tot_ref = float(out.double().sum()), float(ref.double().sum())
     if formula == 0:
-        assert float(d.max()) <= 5e-2
-        assert abs(float(out.double().sum() - ref.double().sum())) <= 1e-5 * float(ref.double().sum())
+        assert float(d.max()) <= 2.5e-2
+        assert abs(tot - tot_ref) <= 1e-6 * tot_ref
     else:
-        assert float((d > 1.0).float().mean()) <= 5e-3
-        assert abs(float(out.double().sum() - ref.double().sum())) <= 1e-3 * float(ref.double().sum())
+        assert float(d.max()) <= 2.0 and float((d > 0.5).float().mean()) <= 1e-3
+        assert abs(tot - tot_ref) <= 1e-5 * tot_ref
 
 
 # ----------------------------------------------------------------------------------------------
@@ -250,6 +251,10 @@ def test_gop_parity_with_oracle(variant, case, backend):
         if "z_hat" in taps_c:
             frac_z, bad_z = symbol_match(taps_c["z_hat"], taps_o["z_hat"])
             assert frac_z >= SYMBOL_MATCH_MIN, (tag, "z symbols", frac_z, bad_z)
+        if "scales_hat" in taps_c and exact:
+            # the sigma handed to the likelihood (merged over the two checkerboard steps, raw network output)
+            so, sc = taps_o["scales_hat"], taps_c["scales_hat"]
+            assert float((so - sc).abs().max()) <= 1e-4 * max(1.0, float(so.abs().max())), (tag, "scales_hat")
         if "mask_pred" in o and o["mask_pred"] is not None:
             mo, mc = o["mask_pred"], c["mask_pred"].cpu()
             assert float((mo - mc).abs().max()) <= 1e-4 * max(1.0, float(mo.abs().max()))
