@@ -6,9 +6,9 @@ the `nn.Module`s in `modules` keep the reference's constructors, state_dict layo
 C ABI in include/dmc_b200.h.  The directory name is not an identifier; import it with
 `importlib.import_module(...)` or through the `dmc_b200` alias module at the repo root.
 """
-from .modules import (DMCConfig, DMCI, DMC_fast, DMC_mask_prop, DMC_old, DMC_performance, P_MODELS,
-                      build_p_model)
+from .modules import (DMCConfig, DMCI, DMC_fast, DMC_mask_prop, DMC_old, DMC_performance, NonFiniteError,
+                      P_MODELS, build_p_model)
 from . import _capi, build, clips  # noqa: F401
 
 __all__ = ["DMCConfig", "DMCI", "DMC_old", "DMC_performance", "DMC_fast", "DMC_mask_prop", "P_MODELS",
-           "build_p_model"]
+           "build_p_model", "NonFiniteError"]

@@ -68,11 +68,16 @@ def test_config3_fast_batch8_full_size():
                 for k in ("bpp", "bpp_y", "bpp_z"):
                     assert rel_err(c[k][b].cpu(), o[k][b]) <= BPP_REL_TOL, (t, b, k)
                 assert abs(mo[b][0] - mc[b][0]) <= PSNR_TOL_DB and abs(mo[b][1] - mc[b][1]) <= PSNR_TOL_DB, (t, b)
-            # scales_hat: the sigma the likelihood sees; equal wherever the symbol agrees up to the contraction's
-            # accuracy (2e-5 of the scale)
-            same = y_c == taps["y_q"]
-            ds = (s_c - taps["scales_hat"]).abs()[same]
-            assert float(ds.max()) <= 1e-4 * max(1.0, float(taps["scales_hat"].abs().max())), (t, float(ds.max()))
+            # scales_hat, the sigma the likelihood sees (raw network output, merged over the two checkerboard steps):
+            # equal up to the contraction's accuracy.  A flipped step-0 symbol changes the spatial prior's input, hence
+            # the step-1 sigmas in its neighbourhood: items without a flip are compared element by element, the whole
+            # batch by the share of elements that moved.
+            ds = (s_c - taps["scales_hat"]).abs()
+            tol = 1e-4 * max(1.0, float(taps["scales_hat"].abs().max()))
+            for b in range(B):
+                if torch.equal(y_c[b], taps["y_q"][b]):
+                    assert float(ds[b].max()) <= tol, (t, b, "scales_hat", float(ds[b].max()))
+            assert float((ds > tol).float().mean()) <= 1e-4, (t, "scales_hat share", float((ds > tol).float().mean()))
             assert c["mask_pred"] is None if t == 1 else torch.equal(c["mask_pred"].cpu(), masks[:, t])
             dpb_o = o["dpb"]
     mp.check_finite()
