@@ -121,6 +121,7 @@ struct dmc_engine {
     int qp = 0;
   } cur;
   bool cur_after_i = true;
+  float* logits_full = nullptr;      // mask_prop: predictor logits at full resolution when the caller passes no mask_pred
 
   std::vector<void*> allocs;
   std::vector<std::unique_ptr<Conv>> convs;
@@ -143,6 +144,70 @@ struct dmc_engine {
   double* bits_z = nullptr;
   float* bpp_scratch = nullptr;
 
+  // ---- caller-owned tensors reach the kernels through device-resident slots (kernels.h: IoSlots), written by one
+  // tiny launch before every forward: the launch program itself never contains a caller pointer, so it can be
+  // captured once per (after_i, qp, mask present) as a CUDA graph and replayed on any tensors.
+  IoSlots* io_dev = nullptr;
+  int* finite_dev = nullptr;
+  const void* const* slot(size_t off) const {
+    return reinterpret_cast<const void* const*>(reinterpret_cast<const char*>(io_dev) + off);
+  }
+#define IO_SLOT(field) slot(offsetof(IoSlots, field))
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+  std::map<uint64_t, GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
+  bool graphs_on = graphs_default();
+  std::string graph_note;                       // why graphs were switched off for this engine (if they were)
+  static bool graphs_default() {
+    const char* v = getenv("DMC_GRAPH");           // DMC_GRAPH=0: launch every kernel of every forward directly
+    return !(v && v[0] == '0');
+  }
+  // Runs `body` (which only enqueues work on the stream it is given) as a CUDA graph keyed by `key`: captured on the
+  // engine's own stream the first time (torch's default stream is the legacy stream, which cannot be captured),
+  // instantiated, and from then on launched with one call.  Any failure switches graphs off for this engine and
+  // falls back to direct launches.
+  template <class Body>
+  void run_graph(uint64_t key, cudaStream_t st, Body body) {
+    if (graphs_on && !profile) {
+      auto it = graphs.find(key);
+      if (it == graphs.end()) {
+        GraphEntry ge;
+        cudaGraph_t g = nullptr;
+        const long long l0 = launch_count();
+        bool ok = true;
+        if (!cap_stream) ok = cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking) == cudaSuccess;
+        if (ok) ok = cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          try {
+            body(cap_stream);
+          } catch (const std::exception& ex) {
+            graph_note = ex.what();
+            ok = false;
+          }
+          if (cudaStreamEndCapture(cap_stream, &g) != cudaSuccess || !g) ok = false;
+        }
+        if (ok) ok = cudaGraphInstantiate(&ge.exec, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        ge.launches = launch_count() - l0;
+        if (!ok) {
+          if (graph_note.empty()) graph_note = cudaGetErrorString(cudaGetLastError());
+          cudaGetLastError();
+          graphs_on = false;
+          add_launches(-ge.launches);          // counted while capturing, never run
+        } else {
+          it = graphs.emplace(key, ge).first;
+          add_launches(-ge.launches);          // (added back below, like every replay)
+        }
+      }
+      if (graphs_on) {
+        CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+        add_launches(it->second.launches);
+        return;
+      }
+    }
+    body(st);
+  }
+
   // measurement (dmc_profile_*): events around every contraction launch
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -160,6 +225,8 @@ struct dmc_engine {
 
   ~dmc_engine() {
     DeviceGuard g(device);
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second.exec);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     for (S3Chain* c : chains) s3_chain_destroy(c);
     for (void* p : allocs) cudaFree(p);
   }
@@ -644,10 +711,12 @@ void dmc_engine::build_p() {
 
   // ---- head: temporal feature (video_model.py:348-351)
   set_prog(&prog_head_i);
-  op([self, F8](cudaStream_t st) { unshuffle8_in(self->cur.dpb_frame, F8.v, self->B, 3, self->H, self->W, st); });
+  io_dev = (IoSlots*)dalloc(sizeof(IoSlots));
+  finite_dev = (int*)dalloc(sizeof(int));
+  op([self, F8](cudaStream_t st) { unshuffle8_in(nullptr, F8.v, self->B, 3, self->H, self->W, st, self->IO_SLOT(dpb_frame)); });
   dcb(fa_i, F8, FEAT0, false, nullptr, ns);
   set_prog(&prog_head_p);
-  op([self, FP](cudaStream_t st) { nchw_to_s3(self->cur.dpb_feature, FP.v, FP.B, 256, FP.H, FP.W, st); });
+  op([self, FP](cudaStream_t st) { nchw_to_s3(nullptr, FP.v, FP.B, 256, FP.H, FP.W, st, self->IO_SLOT(dpb_feature)); });
   {
     EpiSpec s; s.nsplit = ns;
     gemm(FP, fa_p, &FEAT0, s);
@@ -673,7 +742,7 @@ void dmc_engine::build_p() {
   tap("ctx", CTX);
   tap("ctx_t", CTXT);
   // ---- encoder (video_model.py:52-75 / seg_video_model.py:41-59)
-  op([self, X8](cudaStream_t st) { unshuffle8_in(self->cur.x, X8.v, self->B, 3, self->H, self->W, st); });
+  op([self, X8](cudaStream_t st) { unshuffle8_in(nullptr, X8.v, self->B, 3, self->H, self->W, st, self->IO_SLOT(x)); });
   {
     EpiSpec s; s.nsplit = ns;
     gemm(X8, enc_conv1, &XC_lo, s);
@@ -695,7 +764,7 @@ void dmc_engine::build_p() {
     Act MK = new_act(B, H8, W8, 64);
     Act GB = new_act(B, H16, W16, 2 * CY);
     op([self, MK](cudaStream_t st) {
-      if (self->cur.mask) unshuffle8_in(self->cur.mask, MK.v, self->B, 1, self->H, self->W, st);
+      if (self->cur.mask) unshuffle8_in(nullptr, MK.v, self->B, 1, self->H, self->W, st, self->IO_SLOT(mask));
       else CUDA_OK(cudaMemsetAsync(MK.v.p, 0, (size_t)MK.v.ps * kPlanes * sizeof(h16), st));
     });
     EpiSpec s; s.nsplit = ns;
@@ -722,7 +791,7 @@ void dmc_engine::build_p() {
       std::vector<Op> pred;
       std::vector<Op>* saved = prog;
       set_prog(&pred);
-      op([self, mdown](cudaStream_t st) { bilinear_down8(self->cur.mask, mdown, self->B, self->H, self->W, st); });
+      op([self, mdown](cudaStream_t st) { bilinear_down8(nullptr, mdown, self->B, self->H, self->W, st, self->IO_SLOT(mask)); });
       op([mdown, me_w, me_b, ME](cudaStream_t st) { conv3x3_c1(mdown, me_w, me_b, ME.v, ME.B, ME.H, ME.W, 256, st); });
       Act srcs[3] = {ME, CTX, CTXT};
       for (int i = 0; i < 3; ++i) {
@@ -736,9 +805,10 @@ void dmc_engine::build_p() {
       gemm(COL, mp0, &PM1, sa);
       conv_kxk(PM1, mp2, &PM2, sa);
       op([PM2, mp4_w, mp4_b, logit8, M8](cudaStream_t st) { conv1x1_to1(PM2.v, mp4_w, mp4_b, logit8, M8, 64, st); });
-      op([self, logit8, logits_full, H8, W8](cudaStream_t st) {
-        float* dst = self->cur.mask_pred ? self->cur.mask_pred : logits_full;
-        bilinear_up8(logit8, dst, self->B, H8, W8, st);
+      self->logits_full = logits_full;
+      op([self, logit8, H8, W8](cudaStream_t st) {
+        // (the slot holds the caller's mask_pred tensor, or the engine's own buffer when the caller passed none)
+        bilinear_up8(logit8, nullptr, self->B, H8, W8, st, self->IO_SLOT(mask_pred));
       });
       set_prog(saved);
       auto pred_ops = std::make_shared<std::vector<Op>>(std::move(pred));
@@ -753,11 +823,10 @@ void dmc_engine::build_p() {
       ftaps["mask_logits8"] = F32Tap{logit8, B, 1, H8, W8};
     }
     if (padded) op([Y, YP, H16, W16, Hp16, Wp16](cudaStream_t st) { regrid(Y.v, H16, W16, YP.v, Hp16, Wp16, Y.B, st); });
-    op([self, mpool, logits_full, YP, YF, mf_w0, mf_b0, mf_w2, mf_b2, H16, W16, Hp16, Wp16](cudaStream_t st) {
+    op([self, mpool, YP, YF, mf_w0, mf_b0, mf_w2, mf_b2, H16, W16, Hp16, Wp16](cudaStream_t st) {
+      // the mask the FiLM sees: the caller's, or (mask_prop, not after_i) the predictor's logits -- slot mask_src
       const float* m = self->cur.mask;
-      if (self->variant == DMC_VARIANT_MASK_PROP && !self->cur_after_i && m)
-        m = self->cur.mask_pred ? self->cur.mask_pred : logits_full;
-      if (m) avgpool16_clamp(m, mpool, self->B, self->H, self->W, st);
+      if (m) avgpool16_clamp(nullptr, mpool, self->B, self->H, self->W, st, self->IO_SLOT(mask_src));
       maskfilm_apply(m ? mpool : nullptr, YP.v, YF.v, mf_w0, mf_b0, mf_w2, mf_b2, self->B, Hp16, Wp16, 128, H16, W16, st);
     });
     HIN = YF;
@@ -846,7 +915,7 @@ void dmc_engine::build_p() {
     if (!refactor) { s2.scale_table = q_decoder; s2.scale_C = CD; }
     gemm(PA, dec_proj, &FEAT, s2);
   }
-  op([self, FEAT](cudaStream_t st) { s3_to_nchw(FEAT.v, self->cur.feature, FEAT.B, 256, FEAT.H, FEAT.W, st); });
+  op([self, FEAT](cudaStream_t st) { s3_to_nchw(FEAT.v, nullptr, FEAT.B, 256, FEAT.H, FEAT.W, st, self->IO_SLOT(feature)); });
   // ---- reconstruction (video_model.py:100-120)
   dcb(rec[0], FEAT, R0, false, nullptr, ns_recon);
   dcb(rec[1], R0, R1, false, nullptr, ns_recon);
@@ -856,10 +925,10 @@ void dmc_engine::build_p() {
     EpiSpec s; s.nsplit = ns_recon; s.out_f32 = RF; s.ld_f32 = 192;
     gemm(R1, rec_head, nullptr, s);
   }
-  op([self, RF](cudaStream_t st) { shuffle8_out(RF, 192, self->cur.x_hat, self->B, 3, self->H, self->W, st); });
+  op([self, RF](cudaStream_t st) { shuffle8_out(RF, 192, nullptr, self->B, 3, self->H, self->W, st, self->IO_SLOT(x_hat)); });
   // ---- rate (video_model.py:373-378)
   int pixels = H * W;
-  op([self, by, bz, pixels](cudaStream_t st) { finalize_bpp(by, bz, self->cur.bpp3, self->B, pixels, st); });
+  op([self, by, bz, pixels](cudaStream_t st) { finalize_bpp(by, bz, nullptr, self->B, pixels, st, self->IO_SLOT(bpp3)); });
   {
     // the reference's _finite_check sites (seg_video_model_fast.py:353-371,269-276), checked in ONE launch at the end
     // of the frame instead of twelve host syncs inside it: bit i of the flag names tensor i (include/dmc_b200.h)
@@ -869,9 +938,9 @@ void dmc_engine::build_p() {
     for (int i = 0; i < 8; ++i) { fl.v[i] = list[i]->v; fl.M[i] = list[i]->M(); }
     fl.n = 8;
     op([self, fl](cudaStream_t st) {
-      if (!self->cur.finite) return;
-      CUDA_OK(cudaMemsetAsync(self->cur.finite, 0, sizeof(int32_t), st));
-      finite_check(fl, self->cur.finite, st);
+      CUDA_OK(cudaMemsetAsync(self->finite_dev, 0, sizeof(int32_t), st));
+      finite_check(fl, self->finite_dev, st);
+      copy_flag(self->finite_dev, self->IO_SLOT(finite), st);      // (a null caller flag is skipped on the device)
     });
   }
   flush_chain();
@@ -957,7 +1026,8 @@ void dmc_engine::build_intra() {
     CUDA_OK(cudaMemsetAsync(bz, 0, sizeof(double) * nb, st));
   });
   // encoder (image_model.py:16-43)
-  op([self, X8](cudaStream_t st) { unshuffle8_in(self->cur.x, X8.v, self->B, 3, self->H, self->W, st); });
+  io_dev = (IoSlots*)dalloc(sizeof(IoSlots));
+  op([self, X8](cudaStream_t st) { unshuffle8_in(nullptr, X8.v, self->B, 3, self->H, self->W, st, self->IO_SLOT(x)); });
   dcb(enc1, X8, EA, false, q_enc, ns);
   {
     Act a = EA, b = EB;
@@ -1045,9 +1115,9 @@ void dmc_engine::build_intra() {
     }
     dcb(dec2, a, a, false, nullptr, ns, RF, 192);
   }
-  op([self, RF](cudaStream_t st) { shuffle8_out(RF, 192, self->cur.x_hat, self->B, 3, self->H, self->W, st); });
+  op([self, RF](cudaStream_t st) { shuffle8_out(RF, 192, nullptr, self->B, 3, self->H, self->W, st, self->IO_SLOT(x_hat)); });
   int pixels = H * W;
-  op([self, by, bz, pixels](cudaStream_t st) { finalize_bpp(by, bz, self->cur.bpp3, self->B, pixels, st); });
+  op([self, by, bz, pixels](cudaStream_t st) { finalize_bpp(by, bz, nullptr, self->B, pixels, st, self->IO_SLOT(bpp3)); });
   flush_chain();
 }
 
@@ -1162,8 +1232,20 @@ int dmc_forward(dmc_engine* e, const float* x, const float* mask, const float* d
     c.x_hat = x_hat; c.feature = feature; c.bpp3 = bpp3; c.mask_pred = mask_pred; c.finite = finite_flag;
     e->cur_after_i = after_i != 0;
     cudaStream_t st = (cudaStream_t)stream;
-    e->run(after_i ? e->prog_head_i : e->prog_head_p, st);
-    e->run(e->prog_common, st);
+    IoSlots io;
+    memset(&io, 0, sizeof io);
+    io.x = x; io.mask = c.mask; io.dpb_frame = dpb_frame; io.dpb_feature = dpb_feature;
+    io.x_hat = x_hat; io.feature = feature; io.bpp3 = bpp3; io.finite = finite_flag;
+    io.mask_pred = mask_pred ? mask_pred : e->logits_full;
+    io.mask_src = c.mask;
+    if (e->variant == DMC_VARIANT_MASK_PROP && !after_i && c.mask) io.mask_src = io.mask_pred;
+    set_io(e->io_dev, io, st);
+    // what the program's structure depends on: the head, the per-QP table rows, whether a mask came with the frame
+    const uint64_t key = (uint64_t)(after_i != 0) | ((uint64_t)(c.mask != nullptr) << 1) | ((uint64_t)qp << 8);
+    e->run_graph(key, st, [&](cudaStream_t s) {
+      e->run(after_i ? e->prog_head_i : e->prog_head_p, s);
+      e->run(e->prog_common, s);
+    });
     CUDA_OK(cudaGetLastError());
   });
 }
@@ -1181,7 +1263,12 @@ int dmci_forward(dmc_engine* e, const float* x, int qp, float* x_hat, float* bpp
     auto& c = e->cur;
     c = dmc_engine::Cur();
     c.x = x; c.qp = qp; c.x_hat = x_hat; c.bpp3 = bpp3;
-    e->run(e->prog_common, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    IoSlots io;
+    memset(&io, 0, sizeof io);
+    io.x = x; io.x_hat = x_hat; io.bpp3 = bpp3;
+    set_io(e->io_dev, io, st);
+    e->run_graph((uint64_t)qp << 8, st, [&](cudaStream_t s) { e->run(e->prog_common, s); });
     CUDA_OK(cudaGetLastError());
   });
 }

@@ -409,7 +409,9 @@ struct S3ChainParams {
   const uint32_t* table;   // entries: layer << 28 | n tile << 20 | row tile
   uint32_t* done;          // [layers][row tiles], monotonic across launches
   int n_entries, MT;
-  uint32_t epoch;          // launch number (1-based): layer l-1 is complete at done == epoch * need
+  uint32_t* epoch_ctr;     // device words {launches of this chain completed so far, CTAs of this launch that have left}:
+                           // a launch reads its number (1-based) here -- layer l-1 is complete at done == number * need --
+                           // and its last CTA to leave bumps it, so a launch captured in a CUDA graph can be replayed
   uint32_t stageBytes;     // operand ring stage (sized for the widest W tile of the chain)
   int stages;
   int eager;               // 1: few tiles per layer and cluster -- publish a tile as soon as it is stored (below)
@@ -807,6 +809,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     // (whole warp walks the loop, one elected lane issues: addresses stay in uniform registers)
     int s = 0;
     uint32_t ph = 0, tcount = 0;
+    const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(p.epoch_ctr) + 1u;
     // (the table entry of the next tile is fetched a tile ahead: its ~700 clocks of global latency sat on the
     // critical path of every tile in this warp and in the MMA warp)
     uint32_t e_nxt = unit < p.n_entries ? __ldg(p.table + unit) : 0u;
@@ -819,7 +822,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       if (l > 0 && S.need != 0u) {
         // all N tiles of the previous layer for these rows must be stored
         const uint32_t* flag = p.done + (size_t)(l - 1) * p.MT + mt;
-        const uint32_t target = p.epoch * S.need;
+        const uint32_t target = epoch * S.need;
         if ((int)(ld_acquire_gpu(flag) - target) < 0) {
           const long long t0 = clock64();
           while ((int)(ld_acquire_gpu(flag) - target) < 0) {
@@ -1127,6 +1130,15 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     const uint32_t ncols = 512;
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
+  if (threadIdx.x == 0) {
+    // every CTA read the launch number when it started; the last one to leave closes the launch
+    __threadfence();
+    if (atomicAdd(p.epoch_ctr + 1, 1u) == gridDim.x - 1u) {
+      p.epoch_ctr[1] = 0u;
+      __threadfence();
+      atomicAdd(p.epoch_ctr, 1u);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -1337,16 +1349,16 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
   if (grid > cap) grid = cap;
   c->grid = grid;
   if (cudaMalloc(&c->d_table, table.size() * sizeof(uint32_t)) != cudaSuccess ||
-      cudaMalloc(&c->d_done, (size_t)n * MT * sizeof(uint32_t)) != cudaSuccess) {
+      cudaMalloc(&c->d_done, ((size_t)n * MT + 2) * sizeof(uint32_t)) != cudaSuccess) {
     snprintf(g_s3_err, sizeof g_s3_err, "s3_chain_create: cudaMalloc failed");
     s3_chain_destroy(c);
     return nullptr;
   }
   cudaMemcpy(c->d_table, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
-  cudaMemset(c->d_done, 0, (size_t)n * MT * sizeof(uint32_t));
+  cudaMemset(c->d_done, 0, ((size_t)n * MT + 2) * sizeof(uint32_t));
   c->p.table = c->d_table;
   c->p.done = c->d_done;
-  c->p.epoch = 0;
+  c->p.epoch_ctr = c->d_done + (size_t)n * MT;
   return c;
 }
 
@@ -1360,7 +1372,6 @@ void s3_chain_destroy(S3Chain* c) {
 int s3_chain_stages(const S3Chain* c) { return c ? c->n_stages : 0; }
 
 int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
-  c->p.epoch += 1;               // (rolled back below if the launch is refused: the done counters are monotonic)
   c->p.dbg = g_s3_dbg;
   for (int l = 0; l < c->n_stages; ++l)
     if (c->scale_table[l]) c->p.st[l].scale = c->scale_table[l] + (size_t)qp * c->scale_C[l];
@@ -1382,7 +1393,6 @@ int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
   note_launch();
   cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_s3_chain, c->p);
   if (err != cudaSuccess) {
-    c->p.epoch -= 1;
     snprintf(g_s3_err, sizeof g_s3_err, "k_gemm_s3_chain launch: %s", cudaGetErrorString(err));
     return -1;
   }

@@ -27,6 +27,7 @@ bool pdl_enabled() {
 }
 void pdl_set_auto(bool on) { g_pdl_auto = on ? 1 : 0; }
 long long launch_count() { return g_launches; }
+void add_launches(long long n) { g_launches += n; }
 
 int num_sms() {
   static int n[64] = {};          // per device ordinal
@@ -148,8 +149,16 @@ void pack_dw_weight(const float* w, float* out9c, int C, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ layout conversion
-__global__ void k_unshuffle8_in(const float* __restrict__ x, View out, int B, int Cimg, int H, int W) {
+// The kernels that touch a caller-owned tensor take the pointer directly or, when `slot` is given, read it from a
+// device-resident slot at run time: a frame captured once as a CUDA graph then runs on whatever tensors the caller
+// passes to the next forward (engine.cu writes the slots before every launch).
+template <class T>
+__device__ __forceinline__ T* io_ptr(T* p, const void* const* slot) {
+  return slot ? reinterpret_cast<T*>(const_cast<void*>(*slot)) : p;
+}
+__global__ void k_unshuffle8_in(const float* x, View out, int B, int Cimg, int H, int W, const void* const* slot) {
   pdl_prologue_done();
+  x = io_ptr(x, slot);
   int W8 = W / 8, H8 = H / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * H8 * Cimg * 8 * W8;
@@ -167,14 +176,15 @@ __global__ void k_unshuffle8_in(const float* __restrict__ x, View out, int B, in
   long long m = ((long long)b * H8 + h8) * W8 + w8;
   st3x8(out, m, c * 64 + dy * 8, v);
 }
-void unshuffle8_in(const float* x, View out, int B, int Cimg, int H, int W, cudaStream_t st) {
+void unshuffle8_in(const float* x, View out, int B, int Cimg, int H, int W, cudaStream_t st, const void* const* slot) {
   long long total = (long long)B * (H / 8) * Cimg * 8 * (W / 8);
-  launch(k_unshuffle8_in, cdiv(total, 256), 256, 0, st, x, out, B, Cimg, H, W);
+  launch(k_unshuffle8_in, cdiv(total, 256), 256, 0, st, x, out, B, Cimg, H, W, slot);
 }
 
-__global__ void k_shuffle8_out(const float* __restrict__ in, int ld, float* __restrict__ x, int B,
-                               int Cimg, int H, int W) {
+__global__ void k_shuffle8_out(const float* __restrict__ in, int ld, float* x, int B,
+                               int Cimg, int H, int W, const void* const* slot) {
   pdl_prologue_done();
+  x = io_ptr(x, slot);
   int W8 = W / 8, H8 = H / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Cimg * H * W8;
@@ -197,14 +207,15 @@ __global__ void k_shuffle8_out(const float* __restrict__ in, int ld, float* __re
   *reinterpret_cast<float4*>(dst) = a;
   *reinterpret_cast<float4*>(dst + 4) = d;
 }
-void shuffle8_out(const float* in, int ld, float* x, int B, int Cimg, int H, int W, cudaStream_t st) {
+void shuffle8_out(const float* in, int ld, float* x, int B, int Cimg, int H, int W, cudaStream_t st, const void* const* slot) {
   long long total = (long long)B * Cimg * H * (W / 8);
-  launch(k_shuffle8_out, cdiv(total, 256), 256, 0, st, in, ld, x, B, Cimg, H, W);
+  launch(k_shuffle8_out, cdiv(total, 256), 256, 0, st, in, ld, x, B, Cimg, H, W, slot);
 }
 
 // NCHW fp32 <-> S3 rows.  Thread = (pixel, 8 channels), pixel fastest so the NCHW side is coalesced.
-__global__ void k_nchw_to_s3(const float* __restrict__ x, View out, int C, long long HW) {
+__global__ void k_nchw_to_s3(const float* x, View out, int C, long long HW, const void* const* slot) {
   pdl_prologue_done();
+  x = io_ptr(x, slot);
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   int c8 = blockIdx.y, b = blockIdx.z;
@@ -216,13 +227,14 @@ __global__ void k_nchw_to_s3(const float* __restrict__ x, View out, int C, long 
   }
   st3x8(out, (long long)b * HW + p, c8 * 8, v);
 }
-void nchw_to_s3(const float* x, View out, int B, int C, int H, int W, cudaStream_t st) {
+void nchw_to_s3(const float* x, View out, int B, int C, int H, int W, cudaStream_t st, const void* const* slot) {
   long long HW = (long long)H * W;
   dim3 grid(cdiv(HW, 256), (C + 7) / 8, B);
-  launch(k_nchw_to_s3, grid, 256, 0, st, x, out, C, HW);
+  launch(k_nchw_to_s3, grid, 256, 0, st, x, out, C, HW, slot);
 }
-__global__ void k_s3_to_nchw(View in, float* __restrict__ x, int C, long long HW) {
+__global__ void k_s3_to_nchw(View in, float* x, int C, long long HW, const void* const* slot) {
   pdl_prologue_done();
+  x = io_ptr(x, slot);
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   int c8 = blockIdx.y, b = blockIdx.z;
@@ -234,10 +246,10 @@ __global__ void k_s3_to_nchw(View in, float* __restrict__ x, int C, long long HW
     if (c < C) x[((long long)b * C + c) * HW + p] = v[i];
   }
 }
-void s3_to_nchw(View in, float* x, int B, int C, int H, int W, cudaStream_t st) {
+void s3_to_nchw(View in, float* x, int B, int C, int H, int W, cudaStream_t st, const void* const* slot) {
   long long HW = (long long)H * W;
   dim3 grid(cdiv(HW, 256), (C + 7) / 8, B);
-  launch(k_s3_to_nchw, grid, 256, 0, st, in, x, C, HW);
+  launch(k_s3_to_nchw, grid, 256, 0, st, in, x, C, HW, slot);
 }
 __global__ void k_f32rows_to_nchw(const float* __restrict__ in, int ld, float* __restrict__ x, int C,
                                   long long HW) {
@@ -323,6 +335,20 @@ void finite_check(const FiniteList& l, int* flag, cudaStream_t st) {
   unsigned gx = cdiv(most, 256 * 8);
   if (gx < 1) gx = 1;
   launch(k_finite_check, dim3(gx, l.n), 256, 0, st, l, flag);
+}
+
+// copies the engine's flag word to the caller's (if the caller gave one: *slot may be null)
+__global__ void k_copy_flag(const int* src, const void* const* slot) {
+  pdl_prologue_done();
+  int* dst = reinterpret_cast<int*>(const_cast<void*>(*slot));
+  if (dst) *dst = *src;
+}
+void copy_flag(const int* src, const void* const* slot, cudaStream_t st) { launch(k_copy_flag, 1, 1, 0, st, src, slot); }
+
+__global__ void k_set_io(IoSlots* dst, IoSlots v) { *dst = v; }
+void set_io(IoSlots* dst, const IoSlots& v, cudaStream_t st) {
+  note_launch();
+  k_set_io<<<1, 1, 0, st>>>(dst, v);
 }
 
 // ------------------------------------------------------------------ depthwise 3x3 (layers.py:56)
@@ -916,8 +942,10 @@ void round_z_bits(View z, View z_hat, int B, int HW, int C, BitparmRow t, double
   launch(k_round_z_bits, grid, 256, 0, st, z, z_hat, per, C, t, bits_acc);
 }
 
-__global__ void k_finalize_bpp(const double* by, const double* bz, float* bpp3, int B, float pixels) {
+__global__ void k_finalize_bpp(const double* by, const double* bz, float* bpp3, int B, float pixels,
+                               const void* const* slot) {
   pdl_prologue_done();
+  bpp3 = io_ptr(bpp3, slot);
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float y = (float)by[b] / pixels, z = (float)bz[b] / pixels;
@@ -925,8 +953,9 @@ __global__ void k_finalize_bpp(const double* by, const double* bz, float* bpp3, 
   bpp3[3 * b + 1] = y;
   bpp3[3 * b + 2] = z;
 }
-void finalize_bpp(const double* by, const double* bz, float* bpp3, int B, int pixels, cudaStream_t st) {
-  launch(k_finalize_bpp, cdiv(B, 64), 64, 0, st, by, bz, bpp3, B, (float)pixels);
+void finalize_bpp(const double* by, const double* bz, float* bpp3, int B, int pixels, cudaStream_t st,
+                  const void* const* slot) {
+  launch(k_finalize_bpp, cdiv(B, 64), 64, 0, st, by, bz, bpp3, B, (float)pixels, slot);
 }
 
 // ------------------------------------------------------------------ mask conditioning
@@ -950,9 +979,10 @@ void film(View y, View gb, View out, long long M, int C, cudaStream_t st) {
 }
 
 // F.adaptive_avg_pool2d to (H/16, W/16) + clamp(0,1)  (seg_video_model_fast.py:306-307)
-__global__ void k_avgpool16_clamp(const float* __restrict__ mask, float* __restrict__ out, int B,
-                                  int H, int W) {
+__global__ void k_avgpool16_clamp(const float* mask, float* __restrict__ out, int B,
+                                  int H, int W, const void* const* slot) {
   pdl_prologue_done();
+  mask = io_ptr(mask, slot);
   int Wo = W / 16, Ho = H / 16;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * Ho * Wo) return;
@@ -970,9 +1000,9 @@ __global__ void k_avgpool16_clamp(const float* __restrict__ mask, float* __restr
   s = s / 256.0f;
   out[idx] = fminf(fmaxf(s, 0.0f), 1.0f);
 }
-void avgpool16_clamp(const float* mask, float* out, int B, int H, int W, cudaStream_t st) {
+void avgpool16_clamp(const float* mask, float* out, int B, int H, int W, cudaStream_t st, const void* const* slot) {
   long long n = (long long)B * (H / 16) * (W / 16);
-  launch(k_avgpool16_clamp, cdiv(n, 128), 128, 0, st, mask, out, B, H, W);
+  launch(k_avgpool16_clamp, cdiv(n, 128), 128, 0, st, mask, out, B, H, W, slot);
 }
 
 // MaskFiLM: 3x3 (1->16) + ReLU + 1x1 (16->2C), then hyper_in = y*(1+gamma)+beta
@@ -1020,9 +1050,10 @@ void maskfilm_apply(const float* m, View y, View out, const float* w0, const flo
 }
 
 // F.interpolate(bilinear, align_corners=False) by exactly 1/8 and 8 (mask_predictor.py:35,44)
-__global__ void k_bilinear_down8(const float* __restrict__ in, float* __restrict__ out, int B, int H,
-                                 int W) {
+__global__ void k_bilinear_down8(const float* in, float* __restrict__ out, int B, int H,
+                                 int W, const void* const* slot) {
   pdl_prologue_done();
+  in = io_ptr(in, slot);
   int Ho = H / 8, Wo = W / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * Ho * Wo) return;
@@ -1032,13 +1063,14 @@ __global__ void k_bilinear_down8(const float* __restrict__ in, float* __restrict
   float bot = add_rn(mul_rn(0.5f, p[W]), mul_rn(0.5f, p[W + 1]));
   out[idx] = add_rn(mul_rn(0.5f, top), mul_rn(0.5f, bot));
 }
-void bilinear_down8(const float* in, float* out, int B, int H, int W, cudaStream_t st) {
+void bilinear_down8(const float* in, float* out, int B, int H, int W, cudaStream_t st, const void* const* slot) {
   long long n = (long long)B * (H / 8) * (W / 8);
-  launch(k_bilinear_down8, cdiv(n, 256), 256, 0, st, in, out, B, H, W);
+  launch(k_bilinear_down8, cdiv(n, 256), 256, 0, st, in, out, B, H, W, slot);
 }
-__global__ void k_bilinear_up8(const float* __restrict__ in, float* __restrict__ out, int B, int h,
-                               int w) {
+__global__ void k_bilinear_up8(const float* __restrict__ in, float* out, int B, int h,
+                               int w, const void* const* slot) {
   pdl_prologue_done();
+  out = io_ptr(out, slot);
   int Ho = h * 8, Wo = w * 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * Ho * Wo) return;
@@ -1054,9 +1086,9 @@ __global__ void k_bilinear_up8(const float* __restrict__ in, float* __restrict__
   float bot = add_rn(mul_rn(lx0, p[y1 * w + x0]), mul_rn(lx1, p[y1 * w + x1]));
   out[idx] = add_rn(mul_rn(ly0, top), mul_rn(ly1, bot));
 }
-void bilinear_up8(const float* in, float* out, int B, int h, int w, cudaStream_t st) {
+void bilinear_up8(const float* in, float* out, int B, int h, int w, cudaStream_t st, const void* const* slot) {
   long long n = (long long)B * h * 8 * w * 8;
-  launch(k_bilinear_up8, cdiv(n, 256), 256, 0, st, in, out, B, h, w);
+  launch(k_bilinear_up8, cdiv(n, 256), 256, 0, st, in, out, B, h, w, slot);
 }
 
 __global__ void k_conv3x3_c1(const float* __restrict__ in, const float* __restrict__ wt,

@@ -8,6 +8,7 @@ namespace dmc {
 int num_sms();
 void note_launch();            // every kernel launch of the library is counted
 long long launch_count();
+void add_launches(long long n);   // kernels replayed from a captured graph
 // accumulate-truncation compensation of the tcgen05 kernels (kernels.cu): kappa in units of 2^-24 per MMA step
 float acc_comp_kappa();
 void acc_comp_set_kappa(float k);
@@ -57,13 +58,24 @@ void pack_gemm_bias(const float* bias, int cout, const GemmW& g, cudaStream_t st
 // depthwise 3x3: (C,1,3,3) -> [9][C] fp32
 void pack_dw_weight(const float* w, float* out9c, int C, cudaStream_t st);
 
+// ---------------- caller-owned tensors ----------------
+// Device-resident table of the tensors of the current forward call.  Kernels that read / write them take an optional
+// `slot` (address of one entry): the pointer is then fetched at run time, so a captured CUDA graph is independent of
+// the caller's buffers.
+struct IoSlots {
+  const void* x; const void* mask; const void* dpb_frame; const void* dpb_feature;
+  const void* x_hat; const void* feature; const void* bpp3; const void* mask_pred; const void* mask_src; const void* finite;
+};
+void set_io(IoSlots* dst, const IoSlots& v, cudaStream_t st);
+void copy_flag(const int* src, const void* const* slot, cudaStream_t st);
+
 // ---------------- layout conversion ----------------
 // (B,Cimg,H,W) fp32 NCHW -> S3 [B*H/8*W/8, Cimg*64], channel = c*64 + dy*8 + dx (F.pixel_unshuffle)
-void unshuffle8_in(const float* x, View out, int B, int Cimg, int H, int W, cudaStream_t st);
+void unshuffle8_in(const float* x, View out, int B, int Cimg, int H, int W, cudaStream_t st, const void* const* slot = nullptr);
 // fp32 row-major [M, Cimg*64] (ld) -> (B,Cimg,H,W) NCHW, clamped to [0,1] (F.pixel_shuffle + clamp)
-void shuffle8_out(const float* in, int ld, float* x, int B, int Cimg, int H, int W, cudaStream_t st);
-void nchw_to_s3(const float* x, View out, int B, int C, int H, int W, cudaStream_t st);
-void s3_to_nchw(View in, float* x, int B, int C, int H, int W, cudaStream_t st);
+void shuffle8_out(const float* in, int ld, float* x, int B, int Cimg, int H, int W, cudaStream_t st, const void* const* slot = nullptr);
+void nchw_to_s3(const float* x, View out, int B, int C, int H, int W, cudaStream_t st, const void* const* slot = nullptr);
+void s3_to_nchw(View in, float* x, int B, int C, int H, int W, cudaStream_t st, const void* const* slot = nullptr);
 void f32rows_to_nchw(const float* in, int ld, float* x, int B, int C, int H, int W, cudaStream_t st);
 void scale_cols(View in, const float* scale, View out, long long M, cudaStream_t st);
 void copy_view(View in, View out, long long M, cudaStream_t st);
@@ -146,20 +158,20 @@ struct BitparmRow { const float* p[11]; };
 void round_z_bits(View z, View z_hat, int B, int HW, int C, BitparmRow t, double* bits_acc,
                   cudaStream_t st);
 void finalize_bpp(const double* bits_y, const double* bits_z, float* bpp3, int B, int pixels,
-                  cudaStream_t st);
+                  cudaStream_t st, const void* const* slot = nullptr);
 void gaussian_bits(const float* sym, const float* sigma, float* bits, long long n, int formula,
                    cudaStream_t st);
 
 // ---------------- mask conditioning ----------------
 void film(View y, View gb, View out, long long M, int C, cudaStream_t st);   // y*(1+g)+b, gb=[g|b]
 // 16x16 block mean of an fp32 (B,1,H,W) map, clamped to [0,1] -> (B,H/16,W/16) fp32
-void avgpool16_clamp(const float* mask, float* out, int B, int H, int W, cudaStream_t st);
+void avgpool16_clamp(const float* mask, float* out, int B, int H, int W, cudaStream_t st, const void* const* slot = nullptr);
 // MaskFiLM (3x3 1->16, ReLU, 1x1 16->2C) + FiLM on y;  m == nullptr means an all-zero mask; m is an Hm x Wm map
 // (zero outside) on y's H x W grid
 void maskfilm_apply(const float* m, View y, View out, const float* w0, const float* b0,
                     const float* w2, const float* b2, int B, int H, int W, int C, int Hm, int Wm, cudaStream_t st);
-void bilinear_down8(const float* in, float* out, int B, int H, int W, cudaStream_t st);  // -> H/8
-void bilinear_up8(const float* in, float* out, int B, int h, int w, cudaStream_t st);    // -> 8h
+void bilinear_down8(const float* in, float* out, int B, int H, int W, cudaStream_t st, const void* const* slot = nullptr);  // -> H/8
+void bilinear_up8(const float* in, float* out, int B, int h, int w, cudaStream_t st, const void* const* slot = nullptr);    // -> 8h
 // 3x3 conv with a single input channel (mask_embed): fp32 map (B,h,w) -> S3 [M, C]
 void conv3x3_c1(const float* in, const float* w, const float* b, View out, int B, int h, int w_,
                 int C, cudaStream_t st);

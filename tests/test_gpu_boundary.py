@@ -140,3 +140,36 @@ def test_model_on_a_non_current_device():
         assert torch.cuda.current_device() == 0
         got = m1(fr[:, 1].to("cuda:1"), 32, {"frame": fr[:, 0].to("cuda:1"), "feature": None}, after_i=True)
     assert torch.equal(got["dpb"]["frame"].cpu(), want)
+
+
+def test_graph_replay_matches_direct_launches(monkeypatch):
+    """A forward is captured once per (after_i, qp, mask present) as a CUDA graph and replayed on whatever tensors the
+    next call brings (caller pointers live in device slots).  Replays on fresh tensors give the bits of direct launches."""
+    fr, mk = _inputs(seed=9)
+
+    def gop(m):
+        outs = []
+        with torch.no_grad():
+            dpb = {"frame": fr[:, 0].clone(), "feature": None}
+            for rep in range(2):                    # second pass: every graph is a replay, every tensor a new one
+                d = dpb
+                for t, qp in ((1, 40), (2, 32), (2, 36), (1, 32)):
+                    x = torch.cat([fr[:, t], mk[:, t]], 1).clone() if t == 2 else fr[:, t].clone()   # with / without mask
+                    r = m(x, qp, d, after_i=(t == 1))
+                    outs.append((r["dpb"]["frame"].clone(), r["dpb"]["feature"].clone(), r["bpp"].clone()))
+                    if t == 1:
+                        d = r["dpb"]
+        m.check_finite()
+        return outs
+
+    for variant in ("performance", "mask_prop"):
+        a = gop(_model(variant))
+        monkeypatch.setenv("DMC_GRAPH", "0")
+        b = gop(_model(variant))
+        monkeypatch.delenv("DMC_GRAPH")
+        for (xa, fa, ba), (xb, fb, bb) in zip(a, b):
+            assert torch.equal(xa, xb) and torch.equal(fa, fb)
+            assert float((ba - bb).abs().max()) <= 1e-6 * float(bb.abs().max())
+        n = len(a) // 2
+        for i in range(n):                          # pass 2 == pass 1
+            assert torch.equal(a[i][0], a[n + i][0])
