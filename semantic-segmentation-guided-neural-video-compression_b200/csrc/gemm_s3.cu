@@ -628,14 +628,19 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
       auto load_act = [&](int col, bool accumulate) {
         uint32_t a[32], b[32];
         float w[32];
+        // the bias is requested BEFORE the accumulator loads are waited for: fetched after the wait, its L1 latency sat
+        // in front of the first add of every chunk (6 % of the kernel's stall samples, profiles/chain_dcb_r01_v8_stall_summary.txt)
+        const float4* bp = reinterpret_cast<const float4*>(S.bias + n_idx + col);
+        float4 bq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bq[i] = __ldg(bp + i);
         tc_ld32(taddr + col, a);
         if (two_acc) tc_ld32(taddr + 128u + col, b);
         tc_wait_ld();
         EPI_T(1);
-        const float4* bp = reinterpret_cast<const float4*>(S.bias + n_idx + col);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 q = __ldg(bp + i);
+          const float4 q = bq[i];
           const float bias4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
