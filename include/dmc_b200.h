@@ -185,6 +185,34 @@ const char* dmc_version(void);
 int dmc_set_acc_comp(float kappa);
 float dmc_get_acc_comp(void);
 
+/* ---- range coder (rANS) for the quantised latents: the arithmetic-coding half of the reference's entropy models,
+ *   EntropyCoder / RansEncoder / RansDecoder     src/models/entropy_models.py:11-81
+ *   GaussianEncoder.encode_y / decode_y          src/models/entropy_models.py:227-341
+ *   BitEstimator.encode_z / decode_z             src/models/entropy_models.py:152-224
+ * The reference's native coder (MLCodec_extensions_cpp) is not in its tree; this one restates the published algorithm
+ * (byte-wise rANS, 16-bit cdfs, escape + 4-bit bypass groups) with many independent streams of 256 symbols so that a
+ * frame codes in parallel.  Container: u32 n | u32 streams | u16 bytes[streams] | streams... (csrc/rans.cu).
+ * Tables are built on the host exactly as the reference's Python does (GaussianEncoder.update, BitEstimator.update)
+ * and handed over as int32 cdfs: cdf[n_cdf][stride], cdf_len[n_cdf] (= pmf length + 2), offset[n_cdf]. ---- */
+typedef struct dmc_rans dmc_rans;
+int dmc_rans_create(const int32_t* cdf_host, const int32_t* cdf_len_host, const int32_t* offset_host, int n_cdf,
+                    int stride, dmc_rans** out);
+void dmc_rans_destroy(dmc_rans* r);
+const char* dmc_rans_last_error(const dmc_rans* r);
+/* cdf index per symbol, device arrays: y from the predicted scale (build_index_enc / _dec, src/layers/inference.py:63-84:
+ * clamp to [scale_min, scale_max], nearest entry of the log-spaced table); z from the channel of a flattened NCHW
+ * tensor (BitEstimator.build_indexes: base = qp * channels). */
+int dmc_rans_index_gaussian(const float* sigma, int64_t n, float scale_min, float scale_max, int levels, int32_t* idx,
+                            void* stream);
+int dmc_rans_index_channels(int64_t n, int64_t per_channel, int channels, int base, int32_t* idx, void* stream);
+/* upper bound of the container size for n symbols */
+int64_t dmc_rans_max_bytes(int64_t n);
+/* symbols: device fp32, integer valued (what AdaptiveQuant produces).  Both calls synchronise the stream. */
+int dmc_rans_encode(dmc_rans* r, const float* sym, const int32_t* idx, int64_t n, uint8_t* out, int64_t cap,
+                    int64_t* nbytes, void* stream);
+int dmc_rans_decode(dmc_rans* r, const uint8_t* in, int64_t nbytes, const int32_t* idx, int64_t n, float* sym_out,
+                    void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

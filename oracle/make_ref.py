@@ -3,8 +3,8 @@ checkout into oracle/_ref/ so that they travel to the GPU box (oracle/_ref/ is g
 
     python oracle/make_ref.py            (also run by __graft_entry__.build() when /root/reference exists)
 
-What is copied: src/models, src/refactor, src/layers (the files SURVEY.md section 8(a) cites) plus empty package
-markers.  Nothing is edited; a manifest with the sha256 of every file is written next to them, and
+What is copied: src/models, src/refactor, src/layers (the files SURVEY.md section 8(a) cites), src/utils/stream_helper.py
+(section 8(f) rank 1) plus empty package markers.  Nothing is edited; a manifest with the sha256 of every file is written next to them, and
 `load_reference()` verifies it before importing.  Users: bench.py (`--impl reference` CPU arm and the
 `gpu_eager_baseline` block: the reference's own nn.Modules timed on the host cores / eagerly on the same B200) and
 tests.  The product never imports it.
@@ -21,6 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("DMC_REFERENCE", "/root/reference")
 DST = os.path.join(ROOT, "oracle", "_ref")
 PACKAGES = ("src/models", "src/refactor", "src/layers")
+FILES = ("src/utils/stream_helper.py",)          # the bit-stream container helpers (tests of bitstream.py)
 
 
 def _sha(path):
@@ -40,7 +41,11 @@ def make(verbose=True) -> bool:
                 continue
             shutil.copyfile(os.path.join(REF, pkg, name), os.path.join(out, name))
             manifest[f"{pkg}/{name}"] = _sha(os.path.join(out, name))
-    for d in ("src",) + PACKAGES:           # the reference relies on namespace packages; markers keep imports local
+    for rel in FILES:
+        os.makedirs(os.path.dirname(os.path.join(DST, rel)), exist_ok=True)
+        shutil.copyfile(os.path.join(REF, rel), os.path.join(DST, rel))
+        manifest[rel] = _sha(os.path.join(DST, rel))
+    for d in ("src", "src/utils") + PACKAGES:           # the reference relies on namespace packages; markers keep imports local
         marker = os.path.join(DST, d, "__init__.py")
         if not os.path.exists(marker):
             open(marker, "w").close()

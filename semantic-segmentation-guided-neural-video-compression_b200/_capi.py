@@ -49,6 +49,14 @@ SIGNATURES = {
     "dmc_version": (c_char_p, []),
     "dmc_set_acc_comp": (c_int, [c_float]),
     "dmc_get_acc_comp": (c_float, []),
+    "dmc_rans_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "dmc_rans_destroy": (None, [c_void_p]),
+    "dmc_rans_last_error": (c_char_p, [c_void_p]),
+    "dmc_rans_index_gaussian": (c_int, [c_void_p, c_int64, c_float, c_float, c_int, c_void_p, c_void_p]),
+    "dmc_rans_index_channels": (c_int, [c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "dmc_rans_max_bytes": (c_int64, [c_int64]),
+    "dmc_rans_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
+    "dmc_rans_decode": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
 }
 
 # names of the bits of dmc_forward's finite_flag (include/dmc_b200.h)
