@@ -305,8 +305,8 @@ const char* dmc_rans_last_error(const dmc_rans* r) { return r ? r->error.c_str()
 
 int dmc_rans_index_gaussian(const float* sigma, int64_t n, float scale_min, float scale_max, int levels, int32_t* idx,
                             void* stream) {
-  if (!sigma || !idx || n < 0 || levels < 2 || !(scale_min > 0.f) || !(scale_max > scale_min)) return DMC_E_INVALID;
   if (n == 0) return DMC_OK;
+  if (!sigma || !idx || n < 0 || levels < 2 || !(scale_min > 0.f) || !(scale_max > scale_min)) return DMC_E_INVALID;
   const float log_min = logf(scale_min);
   const float step = (logf(scale_max) - log_min) / (float)(levels - 1);
   launch(k_rans_index_gaussian, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, sigma, (long long)n, scale_min,
@@ -315,8 +315,8 @@ int dmc_rans_index_gaussian(const float* sigma, int64_t n, float scale_min, floa
 }
 
 int dmc_rans_index_channels(int64_t n, int64_t per_channel, int channels, int base, int32_t* idx, void* stream) {
-  if (!idx || n < 0 || per_channel < 1 || channels < 1) return DMC_E_INVALID;
   if (n == 0) return DMC_OK;
+  if (!idx || n < 0 || per_channel < 1 || channels < 1) return DMC_E_INVALID;
   launch(k_rans_index_channels, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, (long long)n,
          (long long)per_channel, channels, base, idx);
   return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
@@ -331,7 +331,7 @@ int64_t dmc_rans_max_bytes(int64_t n) {
 // bytes).  Synchronises the stream; *nbytes receives the size of the container (also when it exceeds cap: DMC_E_INVALID).
 int dmc_rans_encode(dmc_rans* r, const float* sym, const int32_t* idx, int64_t n, uint8_t* out, int64_t cap,
                     int64_t* nbytes, void* stream) {
-  if (!r || !sym || !idx || !out || !nbytes || n < 0) return DMC_E_INVALID;
+  if (!r || !out || !nbytes || n < 0 || (n > 0 && (!sym || !idx))) return DMC_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const long long streams = (n + kStreamSyms - 1) / kStreamSyms;
   if (cap < 8) { r->error = "dmc_rans_encode: output buffer smaller than the header"; return DMC_E_INVALID; }
@@ -362,7 +362,7 @@ int dmc_rans_encode(dmc_rans* r, const float* sym, const int32_t* idx, int64_t n
 // Decodes a container produced by dmc_rans_encode (device bytes) into n fp32 symbols; idx as for the encoder.
 int dmc_rans_decode(dmc_rans* r, const uint8_t* in, int64_t nbytes, const int32_t* idx, int64_t n, float* sym_out,
                     void* stream) {
-  if (!r || !in || !idx || !sym_out || n < 0 || nbytes < 8) return DMC_E_INVALID;
+  if (!r || !in || n < 0 || nbytes < 8 || (n > 0 && (!idx || !sym_out))) return DMC_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   uint32_t hdr[2];
   cudaMemcpyAsync(hdr, in, 8, cudaMemcpyDeviceToHost, st);
