@@ -43,6 +43,24 @@ const char* gemm_s3_last_error() { return g_s3_err; }
 static volatile int* g_s3_trap = nullptr;
 int gemm_s3_trap_code() { return g_s3_trap ? *g_s3_trap : 0; }
 
+#ifndef DMC_S3_EPI_WARPS
+#define DMC_S3_EPI_WARPS 8
+#endif
+#if DMC_S3_EPI_WARPS != 8 && DMC_S3_EPI_WARPS != 16
+#error "eight or sixteen epilogue warps"
+#endif
+constexpr int kS3EpiWarps = DMC_S3_EPI_WARPS;
+constexpr int kS3Split = kS3EpiWarps / 4;         // warps per TMEM lane quadrant: they split the tile's columns
+// warp group 0: TMA producer, MMA issuer, two spare warps (56 registers); warp groups 1..: the epilogue warps
+// (setmaxnreg: 224 registers with eight of them; sixteen would get 112, which the inlined epilogue variants do not
+// fit -- ptxas spills ~2 KB per thread -- so the latency hiding comes from 32-column chunks instead).
+// Sixteen epilogue warps (-DDMC_S3_EPI_WARPS=16) work in 16-column chunks -- one column block of the S3 layout, half the
+// registers per chunk, which is what fits the 112 registers a 640-thread CTA leaves them.
+constexpr int kS3ChunkCols = kS3EpiWarps == 16 ? 16 : 32;
+constexpr int kS3ChunkBlocks = kS3ChunkCols / 16;           // 16-column blocks per chunk
+constexpr int kS3PairUnits = 32 / kS3ChunkCols;             // chunks per 64-column chunk-add group (32 outputs)
+constexpr int kS3ChunkBytes = kPlanes * 32 * kS3ChunkCols * 2;
+
 // ------------------------------------------------------------------ tensor maps (host)
 static PFN_cuTensorMapEncodeTiled_v12000 s3_get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -131,7 +149,7 @@ int make_tmap_s3_weight(void* tmap_out, const GemmW& w, int planes) {
 // them is clipped on store and zero-filled on load)
 int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M) {
   (void)M;
-  return s3_encode(tmap_out, v, cols, 32, 2, kPlanes);
+  return s3_encode(tmap_out, v, cols, 32, kS3ChunkBlocks, kPlanes);
 }
 // fp32 result rows [M, ld]: 2-D map, box = 32 columns x 32 rows, SWIZZLE_128B
 int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M) {
@@ -142,10 +160,11 @@ int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long 
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)M};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {(cuuint32_t)kS3ChunkCols, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn((CUtensorMap*)tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, kS3ChunkCols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_s3_err, sizeof g_s3_err, "cuTensorMapEncodeTiled (fp32 rows) failed (%d): base=%p cols=%d ld=%d", (int)r,
@@ -422,25 +441,16 @@ struct S3ChainParams {
 
 constexpr int kS3BK = 32;
 constexpr int kS3APlane = 128 * kS3BK * 2;        // one plane of a 128 x 32 fp16 tile
-#ifndef DMC_S3_EPI_WARPS
-#define DMC_S3_EPI_WARPS 8
-#endif
-#if DMC_S3_EPI_WARPS != 8
-#error "only eight epilogue warps are supported: sixteen at 112 registers spill ~1 KB per thread, leave four operand stages, and the variant has not been kept working (it traps on its bounded waits)"
-#endif
-constexpr int kS3EpiWarps = DMC_S3_EPI_WARPS;
-constexpr int kS3Split = kS3EpiWarps / 4;         // warps per TMEM lane quadrant: they split the tile's columns
-// warp group 0: TMA producer, MMA issuer, two spare warps (56 registers); warp groups 1..: the epilogue warps
-// (setmaxnreg: 224 registers with eight of them; sixteen would get 112, which the inlined epilogue variants do not
-// fit -- ptxas spills ~2 KB per thread -- so the latency hiding comes from 32-column chunks instead).
 constexpr int kS3Threads = 128 + 32 * kS3EpiWarps;
-constexpr int kS3EpiRegs = kS3EpiWarps == 16 ? 112 : 224;
+// setmaxnreg only moves registers INSIDE the CTA's launch allocation (threads x the count ptxas reports: 384 x 168
+// or 640 x 96): what warp group 0 gives up (down to 56) is all the epilogue warp groups can take -- 2 x 128 x 56 = 14 336
+// -> 224 each with eight warps; 4 x 128 x 8 = 4 096 of the 5 120 freed -> 104 each with sixteen (asking for 112 blocks
+// the last warp group forever).
+constexpr int kS3EpiRegs = kS3EpiWarps == 16 ? 104 : 224;
 // The epilogue works in chunks of 32 rows x 32 columns per warp (16-column chunks left the warp waiting on one
 // latency after the other: tcgen05.ld, bias loads, the shared-memory fence, the TMA issue -- 1 560 clocks per chunk
 // measured, 6 200 per tile against 3 900 for the MMAs).  Staging tile of a chunk: split planes
 // [2 planes][2 column blocks][32 rows][16 fp16], or fp32 rows [32 rows][32 fp32] in SWIZZLE_128B order.
-constexpr int kS3ChunkCols = 32;
-constexpr int kS3ChunkBytes = kPlanes * 32 * kS3ChunkCols * 2;
 #ifndef DMC_S3_RING
 #define DMC_S3_RING 2
 #endif
@@ -525,27 +535,26 @@ struct EpiCtx {
   bool epi_mem;
 };
 
-// A tile has BN/32 output chunks of 32 columns (PAIR: BN/64 -- a 64-column group of accumulators = 32 values + their
-// 32 chunk-add partners gives one output chunk).  The warps of a quadrant take contiguous shares of `per` chunks.
-__device__ __forceinline__ int s3_per(int kind, int BN) {
-  const int total = kind == S3_PAIR ? BN >> 6 : BN >> 5;
-  return (total + kS3Split - 1) / kS3Split;
+// A tile has BN/kS3ChunkCols output chunks (PAIR: a 64-column group of accumulators = 32 values + their 32 chunk-add
+// partners gives 32 outputs = 32/kS3ChunkCols chunks).  The warps of a quadrant take contiguous shares of `per` chunks.
+__device__ __forceinline__ int s3_total(int kind, int BN) {
+  return kind == S3_PAIR ? (BN >> 6) * kS3PairUnits : BN / kS3ChunkCols;
 }
+__device__ __forceinline__ int s3_per(int kind, int BN) { return (s3_total(kind, BN) + kS3Split - 1) / kS3Split; }
 __device__ __forceinline__ int s3_nchunk(int kind, int BN, int part) {
-  const int total = kind == S3_PAIR ? BN >> 6 : BN >> 5;
   const int per = s3_per(kind, BN);
-  return max(0, min(per, total - part * per));
+  return max(0, min(per, s3_total(kind, BN) - part * per));
 }
 // accumulator column (PAIR: of the value half; partners sit 32 columns further) of this warp's chunk c
 __device__ __forceinline__ int s3_acc_col(int kind, int BN, int part, int c) {
   const int j = part * s3_per(kind, BN) + c;
-  return kind == S3_PAIR ? j * 64 : j * 32;
+  return kind == S3_PAIR ? (j / kS3PairUnits) * 64 + (j % kS3PairUnits) * kS3ChunkCols : j * kS3ChunkCols;
 }
 // destination column of chunk c of N tile nt for this warp
 __device__ __forceinline__ int s3_dest_col(int kind, int BN, int part, int nt, int c) {
   const int n_idx = nt * BN;
   const int j = part * s3_per(kind, BN) + c;
-  return (kind == S3_PAIR ? (n_idx >> 1) : n_idx) + j * 32;
+  return (kind == S3_PAIR ? (n_idx >> 1) : n_idx) + j * kS3ChunkCols;
 }
 
 // One tile of one layer, one epilogue warp.  `next_res(c)` is called once per chunk (after the staging
@@ -622,24 +631,29 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
       __syncwarp();
     }
     EPI_T(0);
-    float v[32];
+    float v[kS3ChunkCols];
     if (valid) {
-      // v (+)= act(main + small * 2^-11 + bias) for accumulator columns [col, col + 32)
+      // v (+)= act(main + small * 2^-11 + bias) for accumulator columns [col, col + kS3ChunkCols)
       auto load_act = [&](int col, bool accumulate) {
-        uint32_t a[32], b[32];
-        float w[32];
+        uint32_t a[kS3ChunkCols], b[kS3ChunkCols];
+        float w[kS3ChunkCols];
         // the bias is requested BEFORE the accumulator loads are waited for: fetched after the wait, its L1 latency sat
         // in front of the first add of every chunk (6 % of the kernel's stall samples, profiles/chain_dcb_r01_v8_stall_summary.txt)
         const float4* bp = reinterpret_cast<const float4*>(S.bias + n_idx + col);
-        float4 bq[8];
+        float4 bq[kS3ChunkCols / 4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) bq[i] = __ldg(bp + i);
-        tc_ld32(taddr + col, a);
-        if (two_acc) tc_ld32(taddr + 128u + col, b);
+        for (int i = 0; i < kS3ChunkCols / 4; ++i) bq[i] = __ldg(bp + i);
+        if (kS3ChunkCols == 32) {
+          tc_ld32(taddr + col, a);
+          if (two_acc) tc_ld32(taddr + 128u + col, b);
+        } else {
+          tc_ld16(taddr + col, a);
+          if (two_acc) tc_ld16(taddr + 128u + col, b);
+        }
         tc_wait_ld();
         EPI_T(1);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < kS3ChunkCols / 4; ++i) {
           const float4 q = bq[i];
           const float bias4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -653,14 +667,14 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
         }
         if (kWsilu) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) wsilu2_fast(w[2 * i], w[2 * i + 1]);
+          for (int i = 0; i < kS3ChunkCols / 2; ++i) wsilu2_fast(w[2 * i], w[2 * i + 1]);
         }
         if (accumulate) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = add_rn(v[i], w[i]);
+          for (int i = 0; i < kS3ChunkCols; ++i) v[i] = add_rn(v[i], w[i]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = w[i];
+          for (int i = 0; i < kS3ChunkCols; ++i) v[i] = w[i];
         }
       };
       load_act(acol, false);
@@ -681,11 +695,11 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
       x.res_phase ^= 1u << slot;
       const uint32_t src = x.ringBuf + slot * kS3ChunkBytes + rowOff;
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
+      for (int blk = 0; blk < kS3ChunkBlocks; ++blk) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const uint4 qh = ld_shared_v4(src + blk * 1024 + (((uint32_t)hf << 4) ^ swz));
-          const uint4 ql = ld_shared_v4(src + 2048 + blk * 1024 + (((uint32_t)hf << 4) ^ swz));
+          const uint4 ql = ld_shared_v4(src + kS3ChunkBlocks * 1024 + blk * 1024 + (((uint32_t)hf << 4) ^ swz));
           const uint32_t uh[4] = {qh.x, qh.y, qh.z, qh.w};
           const uint32_t ul[4] = {ql.x, ql.y, ql.z, ql.w};
 #pragma unroll
@@ -703,7 +717,7 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
     if (S.scale) {
       const float4* sp = reinterpret_cast<const float4*>(S.scale + dcol);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kS3ChunkCols / 4; ++i) {
         float4 q = make_float4(1.f, 1.f, 1.f, 1.f);
         if (dcol + 4 * i < S.n_out) q = __ldg(sp + i);
         v[4 * i] = mul_rn(v[4 * i], q.x); v[4 * i + 1] = mul_rn(v[4 * i + 1], q.y);
@@ -711,12 +725,13 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
       }
     }
     if (kF32) {
-      // fp32 rows: 128 B per lane, 16-byte unit u of row r sits at u ^ (r & 7)  (SWIZZLE_128B)
-      const uint32_t dst = tileBuf + (uint32_t)lane * 128u;
-      const uint32_t sw128 = (uint32_t)(lane & 7) << 4;
+      // fp32 rows: 4 * kS3ChunkCols bytes per lane; 16-byte unit u of row r sits at u ^ (r & 7) (128-byte rows,
+      // SWIZZLE_128B) or at u ^ ((r >> 1) & 3) (64-byte rows, SWIZZLE_64B)
+      const uint32_t dst = tileBuf + (uint32_t)lane * (4u * kS3ChunkCols);
+      const uint32_t swf = kS3ChunkCols == 32 ? (uint32_t)(lane & 7) << 4 : (uint32_t)((lane >> 1) & 3) << 4;
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        st_shared_v4(dst + (((uint32_t)u << 4) ^ sw128), __float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
+      for (int u = 0; u < kS3ChunkCols / 4; ++u)
+        st_shared_v4(dst + (((uint32_t)u << 4) ^ swf), __float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
                      __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
       fence_async_smem();
       __syncwarp();
@@ -726,14 +741,14 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
       // hi / 2^11-scaled lo split, two elements per conversion
       const uint32_t dst = tileBuf + rowOff;
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
+      for (int blk = 0; blk < kS3ChunkBlocks; ++blk) {
         uint32_t ph_[8], pl_[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) split2x2(v[16 * blk + 2 * i], v[16 * blk + 2 * i + 1], ph_[i], pl_[i]);
         st_shared_v4(dst + blk * 1024 + swz, ph_[0], ph_[1], ph_[2], ph_[3]);
         st_shared_v4(dst + blk * 1024 + (16u ^ swz), ph_[4], ph_[5], ph_[6], ph_[7]);
-        st_shared_v4(dst + 2048 + blk * 1024 + swz, pl_[0], pl_[1], pl_[2], pl_[3]);
-        st_shared_v4(dst + 2048 + blk * 1024 + (16u ^ swz), pl_[4], pl_[5], pl_[6], pl_[7]);
+        st_shared_v4(dst + kS3ChunkBlocks * 1024 + blk * 1024 + swz, pl_[0], pl_[1], pl_[2], pl_[3]);
+        st_shared_v4(dst + kS3ChunkBlocks * 1024 + blk * 1024 + (16u ^ swz), pl_[4], pl_[5], pl_[6], pl_[7]);
       }
       fence_async_smem();
       __syncwarp();
