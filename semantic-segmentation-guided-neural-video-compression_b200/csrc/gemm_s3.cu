@@ -1401,17 +1401,42 @@ int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
   cfg.blockDim = dim3(kS3Threads);
   cfg.dynamicSmemBytes = c->smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = c->p.cl4 ? 4 : 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[3];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = c->p.cl4 ? 4 : 2;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
+  // Cooperative launch: the grid only starts once ALL its clusters can be resident.  The tile dependencies make
+  // resident clusters spin on tiles owned by clusters that are not scheduled yet; alone on the device the grid
+  // (capped by the occupancy query) is always fully resident, but next to another persistent kernel on a second stream
+  // two partially resident grids could wait for each other until the bounded waits trap.  DMC_S3_COOP=0 switches it
+  // off (A/B runs); a driver that refuses the combination with clusters falls back once and for all.
+  static int coop = -1;
+  if (coop < 0) {
+    const char* v = getenv("DMC_S3_COOP");
+    coop = (v && v[0] == '0') ? 0 : 1;
+  }
+  if (coop) {
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  } else if (pdl_enabled()) {                  // (programmatic launch and cooperative launch exclude each other)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = na;
   note_launch();
   cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_s3_chain, c->p);
+  if (err != cudaSuccess && coop) {            // cooperative + cluster launch refused: plain launch from now on
+    cudaGetLastError();
+    coop = 0;
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, k_gemm_s3_chain, c->p);
+  }
   if (err != cudaSuccess) {
     snprintf(g_s3_err, sizeof g_s3_err, "k_gemm_s3_chain launch: %s", cudaGetErrorString(err));
     return -1;

@@ -173,3 +173,27 @@ def test_graph_replay_matches_direct_launches(monkeypatch):
         n = len(a) // 2
         for i in range(n):                          # pass 2 == pass 1
             assert torch.equal(a[i][0], a[n + i][0])
+
+
+def test_two_streams_do_not_trap_the_chain_kernel():
+    """The persistent chain kernel waits on tiles owned by other clusters of its grid, so it needs the whole grid
+    resident; it is launched cooperatively, which makes the driver start a grid only when all of it fits.  Two modules
+    driven from two streams at the same time (the scenario that could otherwise leave two half-resident grids waiting
+    for each other until the bounded waits trap) finish, with the results of a sequential run."""
+    fr, mk = _inputs(seed=21)
+    x = torch.cat([fr[:, 1], mk[:, 1]], 1)
+    dpb = {"frame": fr[:, 0], "feature": None}
+    ma, mb = _model("performance"), _model("fast")
+    with torch.no_grad():
+        want_a = ma(x, 32, dpb, after_i=True)["dpb"]["frame"].clone()
+        want_b = mb(x, 40, dpb, after_i=True)["dpb"]["frame"].clone()
+        torch.cuda.synchronize()
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+        outs_a, outs_b = [], []
+        for _ in range(12):
+            with torch.cuda.stream(sa):
+                outs_a.append(ma(x, 32, dpb, after_i=True)["dpb"]["frame"])
+            with torch.cuda.stream(sb):
+                outs_b.append(mb(x, 40, dpb, after_i=True)["dpb"]["frame"])
+        torch.cuda.synchronize()
+    assert all(torch.equal(o, want_a) for o in outs_a) and all(torch.equal(o, want_b) for o in outs_b)
