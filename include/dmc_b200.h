@@ -116,6 +116,21 @@ int dmc_forward(dmc_engine* e, const float* x, const float* mask, const float* d
 /* One I-frame through DMCI (engine created with DMC_VARIANT_INTRA). */
 int dmci_forward(dmc_engine* e, const float* x, int qp, float* x_hat, float* bpp3, void* stream);
 
+/* Decoder side (the split of DMC.forward / DMCI.forward that the reference sketches in its dead compress / decompress,
+ * src/models/video_model.py:256-333, image_model.py): a decoder knows the dpb, qp and the decoded symbols, not x.
+ *   dmc_decode_begin    temporal context (P engines) + hyper decoder + prior fusion from z_hat (B,128,H/64,W/64)
+ *   for step in 0 .. steps-1   (2 checkerboard steps for P frames, 4 for the intra model):
+ *     dmc_decode_sigma    runs the spatial prior of the step (step > 0) and writes the predicted scale of every element
+ *                         this step owns into sigma_out (B,C,H/16,W/16; other elements are left stale)
+ *     dmc_decode_symbols  takes the step's decoded symbols (same dense shape, read at the owned elements only)
+ *   dmc_decode_finish   y_hat -> decoder -> feature (P engines) and x_hat
+ * The same kernels and buffers as forward(): x_hat / feature are bit-identical to the encoder's. */
+int dmc_decode_begin(dmc_engine* e, const float* dpb_frame, const float* dpb_feature, int qp, int after_i,
+                     const float* z_hat, void* stream);
+int dmc_decode_sigma(dmc_engine* e, int step, float* sigma_out, void* stream);
+int dmc_decode_symbols(dmc_engine* e, int step, const float* symbols, void* stream);
+int dmc_decode_finish(dmc_engine* e, float* x_hat, float* feature, void* stream);
+
 /* Intermediate tensors of the last forward, converted to NCHW fp32 (needs
  * DMC_FLAG_KEEP_TAPS).  shape4 receives (B,C,H,W); dst may be NULL to query the shape. */
 int dmc_get_tap(dmc_engine* e, const char* name, float* dst, int64_t capacity_elems,

@@ -31,6 +31,10 @@ SIGNATURES = {
     "dmc_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dmci_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "dmc_decode_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dmc_decode_sigma": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "dmc_decode_symbols": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "dmc_decode_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "dmc_get_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
     "dmc_frame_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 c_int, c_void_p]),

@@ -6,8 +6,8 @@ units, each starting with one byte `type << 4 | sps_id`.
     P     type 2: same as I
 
 Adaptive-length integers: 1 byte below 2^7 (top bit 0), 2 bytes below 2^14 (top bits 10), else 4 bytes below 2^30 (top
-bits 11), big endian.  The payload of an I / P unit here is `pack_streams(...)`: the two range-coder containers of a
-frame (z, then y) each preceded by its adaptive-length size.  Byte-compatible with the reference's helpers for the unit
+bits 11), big endian.  The payload of an I / P unit here is `pack_streams(...)`: the range-coder containers of a
+frame in decoding order (z, then y of every checkerboard step), each preceded by its adaptive-length size.  Byte-compatible with the reference's helpers for the unit
 headers (tests/test_entropy_host.py checks it against oracle/_ref when that copy is present).
 """
 from __future__ import annotations
@@ -106,17 +106,17 @@ class SPSHelper:
         return next((s for s in self.spss if s["sps_id"] == sps_id), None)
 
 
-def pack_streams(z_stream: bytes, y_stream: bytes) -> bytes:
-    """Payload of one frame: the z container, then the y container, each behind its size."""
+def pack_streams(*streams: bytes) -> bytes:
+    """Payload of one frame: the range-coder containers in decoding order (z, then y step by step), each behind its
+    adaptive-length size, with the number of containers in front."""
     f = io.BytesIO()
-    for s in (z_stream, y_stream):
+    write_uint_adaptive(f, len(streams))
+    for s in streams:
         write_uint_adaptive(f, len(s))
         f.write(s)
     return f.getvalue()
 
 
-def unpack_streams(payload: bytes) -> Tuple[bytes, bytes]:
+def unpack_streams(payload: bytes) -> List[bytes]:
     f = io.BytesIO(payload)
-    z = f.read(read_uint_adaptive(f))
-    y = f.read(read_uint_adaptive(f))
-    return z, y
+    return [f.read(read_uint_adaptive(f)) for _ in range(read_uint_adaptive(f))]

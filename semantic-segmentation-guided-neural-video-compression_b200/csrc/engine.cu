@@ -136,7 +136,26 @@ struct dmc_engine {
   struct F32Tap { const float* p; int B, C, H, W; };
   std::map<std::string, F32Tap> ftaps;           // fp32 row-major [M, C] taps
 
-  typedef std::function<void(cudaStream_t)> Op;
+  // One launch (or a few) of the frame program, tagged with the PHASE of the codec it belongs to.  forward() runs
+  // every phase; the decoder entry points (dmc_decode_*) run the phases a decoder has, with the entropy decoder of
+  // the caller between them.
+  enum Phase { PH_FEAT = 0, PH_ENC = 1, PH_PRIOR = 2, PH_STEP0 = 3, PH_SP1 = 4, PH_STEP1 = 5, PH_SP2 = 6, PH_STEP2 = 7,
+               PH_SP3 = 8, PH_STEP3 = 9, PH_FIN = 10, PH_DEC = 11, PH_RATE = 12 };
+  struct Op {
+    std::function<void(cudaStream_t)> fn;
+    int phase;
+    template <class F>
+    Op(F f) : fn(std::move(f)), phase(tl_phase()) {}
+    void operator()(cudaStream_t st) const { fn(st); }
+  };
+  static int& tl_phase() {
+    static thread_local int p = PH_FEAT;
+    return p;
+  }
+  void set_phase(int ph) {
+    flush_chain();               // (a staged chain belongs to the phase it was staged in)
+    tl_phase() = ph;
+  }
   std::vector<Op> prog_head_i, prog_head_p, prog_common;
   std::vector<Op>* prog = nullptr;               // where the builder appends
 
@@ -570,10 +589,16 @@ struct dmc_engine {
   void build_p();
   void build_intra();
   void finalize(cudaStream_t st);
-  void run(std::vector<Op>& p, cudaStream_t st) {
+  void run(std::vector<Op>& p, cudaStream_t st, uint32_t phases = 0xffffffffu) {
     pdl_set_auto((long long)B * H * W <= (1LL << 20));   // (kernels.cu: launch-bound frames only)
-    for (auto& f : p) f(st);
+    for (auto& f : p)
+      if (phases >> f.phase & 1u) f(st);
   }
+  // ---- decoder state (dmc_decode_*): which buffers the entropy decoder of the caller reads / fills
+  PriorArgs dec_prior{};          // the prior kernels' arguments (step filled in per call)
+  View dec_zhat{nullptr, 0, 0, 0};
+  int dec_zC = 0, dec_zH = 0, dec_zW = 0;
+  int dec_steps = 0;
 };
 
 // ====================================================================== P-frame program
@@ -710,6 +735,7 @@ void dmc_engine::build_p() {
   float* RF = new_f32((size_t)M8 * 192);
 
   // ---- head: temporal feature (video_model.py:348-351)
+  set_phase(PH_FEAT);
   set_prog(&prog_head_i);
   io_dev = (IoSlots*)dalloc(sizeof(IoSlots));
   finite_dev = (int*)dalloc(sizeof(int));
@@ -724,10 +750,12 @@ void dmc_engine::build_p() {
 
   set_prog(&prog_common);
   double* by = bits_y; double* bz = bits_z; int nb = B;
+  set_phase(PH_RATE);
   op([by, bz, nb](cudaStream_t st) {
     CUDA_OK(cudaMemsetAsync(by, 0, sizeof(double) * nb, st));
     CUDA_OK(cudaMemsetAsync(bz, 0, sizeof(double) * nb, st));
   });
+  set_phase(PH_FEAT);
   tap("feature_in", FEAT0);
   // ---- feature extractor (video_model.py:23-49)
   dcb(fe1[0], FEAT0, PA, false, nullptr, ns);
@@ -742,6 +770,7 @@ void dmc_engine::build_p() {
   tap("ctx", CTX);
   tap("ctx_t", CTXT);
   // ---- encoder (video_model.py:52-75 / seg_video_model.py:41-59)
+  set_phase(PH_ENC);
   op([self, X8](cudaStream_t st) { unshuffle8_in(nullptr, X8.v, self->B, 3, self->H, self->W, st, self->IO_SLOT(x)); });
   {
     EpiSpec s; s.nsplit = ns;
@@ -858,6 +887,8 @@ void dmc_engine::build_p() {
   }
   tap("z_hat", ZH);
   // ---- hyper decoder (video_model.py:136-146) + temporal prior + fusion (:236-243,149-160)
+  set_phase(PH_PRIOR);
+  dec_zhat = ZH.v; dec_zC = CZ; dec_zH = H64; dec_zW = W64;
   {
     EpiSpec s; s.nsplit = ns;
     gemm(ZH, hd0u, &U32, s, H64, W64);
@@ -886,21 +917,28 @@ void dmc_engine::build_p() {
   memset(&pa, 0, sizeof pa);
   pa.scheme = 2; pa.B = B; pa.H = H16; pa.W = W16; pa.C = CY;
   pa.y = YQ.v; pa.params = PARAMS.v; pa.sp = SP.v; pa.yh = YH0.v; pa.sym = sym; pa.sig = sig;
+  dec_prior = pa;
+  dec_steps = 2;
   {
     PriorArgs a0 = pa; a0.step = 0;
+    set_phase(PH_STEP0);
     op([a0](cudaStream_t st) { prior_step(a0, st); });
     tap("y_hat_0", YH0);
+    set_phase(PH_SP1);
     dcb(sp0, PC, S0, false, nullptr, ns);
     dcb(sp1, S0, S1, false, nullptr, ns);
     EpiSpec s; s.nsplit = ns;
     gemm(S1, sp2, &SP, s);
     tap("spatial_prior", SP);
     PriorArgs a1 = pa; a1.step = 1;
+    set_phase(PH_STEP1);
     op([a1](cudaStream_t st) { prior_step(a1, st); });
     int formula = refactor ? 1 : 0;
+    set_phase(PH_FIN);
     op([a1, YHAT, formula, by](cudaStream_t st) { prior_finish(a1, YHAT.v, formula, by, st); });
   }
   tap("y_hat", YHAT);
+  set_phase(PH_DEC);
   ftaps["y_q"] = F32Tap{sym, B, CY, H16, W16};
   ftaps["scales_hat"] = F32Tap{sig, B, CY, H16, W16};
   // ---- decoder (video_model.py:78-97 / seg_video_model.py:62-77)
@@ -928,7 +966,9 @@ void dmc_engine::build_p() {
   op([self, RF](cudaStream_t st) { shuffle8_out(RF, 192, nullptr, self->B, 3, self->H, self->W, st, self->IO_SLOT(x_hat)); });
   // ---- rate (video_model.py:373-378)
   int pixels = H * W;
+  set_phase(PH_RATE);
   op([self, by, bz, pixels](cudaStream_t st) { finalize_bpp(by, bz, nullptr, self->B, pixels, st, self->IO_SLOT(bpp3)); });
+  set_phase(PH_DEC);
   {
     // the reference's _finite_check sites (seg_video_model_fast.py:353-371,269-276), checked in ONE launch at the end
     // of the frame instead of twelve host syncs inside it: bit i of the flag names tensor i (include/dmc_b200.h)
@@ -1021,11 +1061,13 @@ void dmc_engine::build_intra() {
 
   set_prog(&prog_common);
   double* by = bits_y; double* bz = bits_z; int nb = B;
+  set_phase(PH_RATE);
   op([by, bz, nb](cudaStream_t st) {
     CUDA_OK(cudaMemsetAsync(by, 0, sizeof(double) * nb, st));
     CUDA_OK(cudaMemsetAsync(bz, 0, sizeof(double) * nb, st));
   });
   // encoder (image_model.py:16-43)
+  set_phase(PH_ENC);
   io_dev = (IoSlots*)dalloc(sizeof(IoSlots));
   op([self, X8](cudaStream_t st) { unshuffle8_in(nullptr, X8.v, self->B, 3, self->H, self->W, st, self->IO_SLOT(x)); });
   dcb(enc1, X8, EA, false, q_enc, ns);
@@ -1053,6 +1095,8 @@ void dmc_engine::build_intra() {
       round_z_bits(Z.v, ZH.v, self->B, HW64, 128, t, bz, st);
     });
     tap("z_hat", ZH);
+    set_phase(PH_PRIOR);
+    dec_zhat = ZH.v; dec_zC = CZ; dec_zH = H64; dec_zW = W64;
     gemm(ZH, hd0u, &U32, s, H64, W64);
     dcb(hd0, U32, G32, true, nullptr, ns);
     gemm(G32, hd1u, &U16, s, H32, W32);
@@ -1084,8 +1128,11 @@ void dmc_engine::build_intra() {
   memset(&pa, 0, sizeof pa);
   pa.scheme = 4; pa.B = B; pa.H = H16; pa.W = W16; pa.C = N;
   pa.y = Y.v; pa.params = PARAMS.v; pa.sp = SP.v; pa.yh = YHS.v; pa.sym = sym; pa.sig = sig;
+  dec_prior = pa;
+  dec_steps = 4;
   for (int step = 0; step < 4; ++step) {
     if (step > 0) {
+      set_phase(PH_STEP0 + 2 * step - 1);         // PH_SP1 / PH_SP2 / PH_SP3
       dcb(ad[step - 1], Q, FA, false, nullptr, ns);
       dcb(spb[0], FA, FB, false, nullptr, ns);
       dcb(spb[1], FB, FA, false, nullptr, ns);
@@ -1094,13 +1141,16 @@ void dmc_engine::build_intra() {
       gemm(FB, sp3, &SP, s);
     }
     PriorArgs a = pa; a.step = step;
+    set_phase(PH_STEP0 + 2 * step);               // PH_STEP0 ... PH_STEP3
     op([a](cudaStream_t st) { prior_step(a, st); });
   }
+  set_phase(PH_FIN);
   {
     PriorArgs a = pa; a.step = 3;
     op([a, YHAT, by](cudaStream_t st) { prior_finish(a, YHAT.v, 0, by, st); });
   }
   tap("y_hat", YHAT);
+  set_phase(PH_DEC);
   ftaps["y_q"] = F32Tap{sym, B, N, H16, W16};
   ftaps["scales_hat"] = F32Tap{sig, B, N, H16, W16};
   // decoder (image_model.py:46-93)
@@ -1117,6 +1167,7 @@ void dmc_engine::build_intra() {
   }
   op([self, RF](cudaStream_t st) { shuffle8_out(RF, 192, nullptr, self->B, 3, self->H, self->W, st, self->IO_SLOT(x_hat)); });
   int pixels = H * W;
+  set_phase(PH_RATE);
   op([self, by, bz, pixels](cudaStream_t st) { finalize_bpp(by, bz, nullptr, self->B, pixels, st, self->IO_SLOT(bpp3)); });
   flush_chain();
 }
@@ -1269,6 +1320,78 @@ int dmci_forward(dmc_engine* e, const float* x, int qp, float* x_hat, float* bpp
     io.x = x; io.x_hat = x_hat; io.bpp3 = bpp3;
     set_io(e->io_dev, io, st);
     e->run_graph((uint64_t)qp << 8, st, [&](cudaStream_t s) { e->run(e->prog_common, s); });
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+// ---- decoder side: the phases of the frame program a decoder has, with the caller's entropy decoder between them
+int dmc_decode_begin(dmc_engine* e, const float* dpb_frame, const float* dpb_feature, int qp, int after_i,
+                     const float* z_hat, void* stream) {
+  if (!e || !z_hat) return DMC_E_INVALID;
+  if (!e->finalized) { e->error = "weights not finalised"; return DMC_E_STATE; }
+  const bool intra = e->variant == DMC_VARIANT_INTRA;
+  if (qp < 0 || qp >= (intra ? 64 : 72) || (!intra && (after_i ? !dpb_frame : !dpb_feature))) {
+    e->error = "dmc_decode_begin: null dpb tensor or qp out of range";
+    return DMC_E_INVALID;
+  }
+  return guarded(e, [&] {
+    DeviceGuard dg(e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    e->cur = dmc_engine::Cur();
+    e->cur.qp = qp;
+    e->cur_after_i = after_i != 0;
+    IoSlots io;
+    memset(&io, 0, sizeof io);
+    io.dpb_frame = dpb_frame; io.dpb_feature = dpb_feature;
+    set_io(e->io_dev, io, st);
+    if (!intra) {
+      e->run(after_i ? e->prog_head_i : e->prog_head_p, st, 1u << dmc_engine::PH_FEAT);
+      e->run(e->prog_common, st, 1u << dmc_engine::PH_FEAT);
+    }
+    nchw_to_s3(z_hat, e->dec_zhat, e->B, e->dec_zC, e->dec_zH, e->dec_zW, st);
+    e->run(e->prog_common, st, 1u << dmc_engine::PH_PRIOR);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int dmc_decode_sigma(dmc_engine* e, int step, float* sigma_out, void* stream) {
+  if (!e || !sigma_out || step < 0 || step >= e->dec_steps) return DMC_E_INVALID;
+  return guarded(e, [&] {
+    DeviceGuard dg(e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (step > 0) e->run(e->prog_common, st, 1u << (dmc_engine::PH_STEP0 + 2 * step - 1));   // the spatial prior of this step
+    PriorArgs a = e->dec_prior;
+    a.step = step;
+    a.mode = 2;
+    prior_step(a, st);
+    f32rows_to_nchw(a.sig, a.C, sigma_out, a.B, a.C, a.H, a.W, st);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int dmc_decode_symbols(dmc_engine* e, int step, const float* symbols, void* stream) {
+  if (!e || !symbols || step < 0 || step >= e->dec_steps) return DMC_E_INVALID;
+  return guarded(e, [&] {
+    DeviceGuard dg(e->device);
+    PriorArgs a = e->dec_prior;
+    a.step = step;
+    a.mode = 1;
+    a.sym_in = symbols;
+    prior_step(a, (cudaStream_t)stream);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int dmc_decode_finish(dmc_engine* e, float* x_hat, float* feature, void* stream) {
+  if (!e || !x_hat || (e->variant != DMC_VARIANT_INTRA && !feature)) return DMC_E_INVALID;
+  return guarded(e, [&] {
+    DeviceGuard dg(e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    IoSlots io;
+    memset(&io, 0, sizeof io);
+    io.x_hat = x_hat; io.feature = feature;
+    set_io(e->io_dev, io, st);
+    e->run(e->prog_common, st, (1u << dmc_engine::PH_FIN) | (1u << dmc_engine::PH_DEC));
     CUDA_OK(cudaGetLastError());
   });
 }

@@ -818,41 +818,57 @@ __global__ void k_prior_step(PriorArgs a) {
   const int w = (int)(m % a.W), h = (int)((m / a.W) % a.H);
   const int owner = prior_owner(a.scheme, h, w, c, a.C);
   if (owner != a.step) {
-    if (a.step == 0) {
+    if (a.step == 0 && a.mode != 2) {
       const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       st3x8(a.yh, m, c, z);
     }
     return;
   }
-  float y[8], sg[8], mu[8], ys[8];
-  ld3x8(a.y, m, c, y);
-  if (a.scheme == 2) {
-    float q[8];
-    ld3x8(a.params, m, c, q);
+  float sg[8], mu[8], ys[8];
+  if (a.mode == 0) {
+    float y[8];
+    ld3x8(a.y, m, c, y);
+    if (a.scheme == 2) {
+      float q[8];
+      ld3x8(a.params, m, c, q);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ys[i] = mul_rn(y[i], 1.0f / fmaxf(q[i], 0.5f));          // inference.py:29-33
-    if (a.step == 0) { ld3x8(a.params, m, a.C + c, sg); ld3x8(a.params, m, 2 * a.C + c, mu); }
-  } else {
-    const float qe = add_rn(mul_rn(sigmoidf_(ld3(a.params, m, 0)), 1.5f), 0.5f);         // common_model.py:178-180
+      for (int i = 0; i < 8; ++i) ys[i] = mul_rn(y[i], 1.0f / fmaxf(q[i], 0.5f));          // inference.py:29-33
+    } else {
+      const float qe = add_rn(mul_rn(sigmoidf_(ld3(a.params, m, 0)), 1.5f), 0.5f);         // common_model.py:178-180
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ys[i] = mul_rn(y[i], qe);
-    if (a.step == 0) {                      // [qe, qd | sigma0 | mu0]: the two leading columns break the 8-alignment
+      for (int i = 0; i < 8; ++i) ys[i] = mul_rn(y[i], qe);
+    }
+  }
+  if (a.step == 0) {
+    if (a.scheme == 2) {
+      ld3x8(a.params, m, a.C + c, sg);
+      ld3x8(a.params, m, 2 * a.C + c, mu);
+    } else {                                // [qe, qd | sigma0 | mu0]: the two leading columns break the 8-alignment
 #pragma unroll
       for (int i = 0; i < 8; ++i) { sg[i] = ld3(a.params, m, 2 + c + i); mu[i] = ld3(a.params, m, 2 + a.C + c + i); }
     }
+  } else {
+    ld3x8(a.sp, m, c, sg);
+    ld3x8(a.sp, m, a.C + c, mu);
   }
-  if (a.step > 0) { ld3x8(a.sp, m, c, sg); ld3x8(a.sp, m, a.C + c, mu); }
+  float4* pg = reinterpret_cast<float4*>(a.sig + m * a.C + c);
+  pg[0] = make_float4(sg[0], sg[1], sg[2], sg[3]); pg[1] = make_float4(sg[4], sg[5], sg[6], sg[7]);
+  if (a.mode == 2) return;
   float s[8], yh[8];
+  if (a.mode == 1) {
+    const long long HW = (long long)a.H * a.W;
+    const float* src = a.sym_in + ((m / HW) * a.C + c) * HW + m % HW;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    s[i] = rintf(sub_rn(ys[i], mu[i]));                   // torch.round = half-to-even
-    yh[i] = add_rn(s[i], mu[i]);
+    for (int i = 0; i < 8; ++i) s[i] = src[i * HW];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = rintf(sub_rn(ys[i], mu[i]));                   // torch.round = half-to-even
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) yh[i] = add_rn(s[i], mu[i]);
   st3x8(a.yh, m, c, yh);
   float4* ps = reinterpret_cast<float4*>(a.sym + m * a.C + c);
-  float4* pg = reinterpret_cast<float4*>(a.sig + m * a.C + c);
   ps[0] = make_float4(s[0], s[1], s[2], s[3]); ps[1] = make_float4(s[4], s[5], s[6], s[7]);
-  pg[0] = make_float4(sg[0], sg[1], sg[2], sg[3]); pg[1] = make_float4(sg[4], sg[5], sg[6], sg[7]);
 }
 void prior_step(const PriorArgs& a, cudaStream_t st) {
   long long n = (long long)a.B * a.H * a.W * (a.C / 8);

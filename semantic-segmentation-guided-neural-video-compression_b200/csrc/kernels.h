@@ -148,6 +148,10 @@ struct PriorArgs {
   View yh;             // running y_hat (pre q_dec), C columns, written for owned elements
   float* sym;          // [M, C] fp32
   float* sig;          // [M, C] fp32
+  int mode;            // 0 encoder: symbols = round(y / q - mu).  Decoder side (dmc_decode_*): 2 = only publish the
+                       // sigmas of this step's elements (what the entropy decoder needs first), 1 = take this step's
+                       // symbols from sym_in and rebuild y_hat from them
+  const float* sym_in; // mode 1: dense (B, C, H, W) fp32, read at this step's elements only
 };
 void prior_step(const PriorArgs& a, cudaStream_t st);
 // y_hat = yh * q_dec -> out; bits(sym, sig) summed per sample into bits_acc[b] (double)

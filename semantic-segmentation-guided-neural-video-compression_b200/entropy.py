@@ -10,9 +10,10 @@ Same names and argument meaning as the reference classes.  Table construction fo
 line (it runs on whatever device the tensors are on); the coder itself is csrc/rans.cu behind the C ABI
 (dmc_rans_* in include/dmc_b200.h).  There is no CPU coder in the product: without a CUDA device `update()` raises.
 
-What this adds to forward(): actual bits.  `FrameCoder.compress` codes the symbols of the last forward (y_q with
-scales_hat, z_hat with the factorized tables) into a byte string, `decompress_symbols` returns them bit-exactly; the
-network half of a stand-alone decoder (running hyper-decoder / spatial prior between the two y steps) is not built.
+What this adds to forward(): actual bits and a decoder.  `FrameCoder.compress` codes the symbols of the last forward
+(z_hat with the factorized tables, then y step by step with the scales each checkerboard step predicted) into the
+frame payload; `FrameCoder.decompress` rebuilds x_hat / feature from the payload and the dpb alone, running the
+decoder half of the network (dmc_decode_* in include/dmc_b200.h) with the range decoder between its phases.
 """
 from __future__ import annotations
 
@@ -24,7 +25,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["EntropyCoder", "GaussianEncoder", "BitEstimatorCoder", "FrameCoder"]
+__all__ = ["EntropyCoder", "GaussianEncoder", "BitEstimatorCoder", "FrameCoder", "owner_mask"]
 
 
 def _ptr(t):
@@ -283,13 +284,36 @@ class BitEstimatorCoder:
         return z.reshape(size).to(dtype)
 
 
+def owner_mask(step: int, shape, steps: int, device) -> torch.Tensor:
+    """Boolean (B, C, H, W) mask of the latent elements coded in checkerboard step `step`
+    (get_mask_2x / get_mask_4x, models/common_model.py:93-114,152-169; kernels.cu: prior_owner)."""
+    B, C, H, W = shape
+    c = torch.arange(C, device=device).view(1, C, 1, 1)
+    h = torch.arange(H, device=device).view(1, 1, H, 1)
+    w = torch.arange(W, device=device).view(1, 1, 1, W)
+    if steps == 2:
+        owner = (h + w + (c >= C // 2).long()) % 2
+    else:
+        table = torch.tensor([[0, 3, 2, 1], [3, 0, 1, 2], [2, 1, 0, 3], [1, 2, 3, 0]], device=device)
+        owner = table[c // (C // 4), (h % 2) * 2 + (w % 2)]
+    return (owner == step).expand(B, C, H, W)
+
+
 class FrameCoder:
-    """Codes the symbols of a model's last forward (engine_flags must include FLAG_KEEP_TAPS): z_hat with the
-    factorized tables of the model's bit estimator, y_q with the Gaussian tables at the predicted scales."""
+    """compress / decompress of one frame around a model of this package (P models and DMCI).
+
+    compress()    after model(...) ran with FLAG_KEEP_TAPS: z_hat with the factorized tables, then the y symbols of
+                  every checkerboard step with the scales that step predicted -- the order a decoder can follow
+                  (the reference's dead compress(), src/models/video_model.py:256-296, codes y_q_w_0 / y_q_w_1 the
+                  same way).  Returns the frame payload (bitstream.pack_streams) and its parts.
+    decompress()  bytes + dpb + qp -> the decoder half of the network through dmc_decode_* with the range decoder
+                  between the phases; returns {"dpb": {"frame", "feature"}} bit-identical to forward()'s."""
 
     def __init__(self, model):
         self.model = model
         dev = next(model.parameters()).device
+        self.intra = model.variant == "intra"
+        self.steps = 4 if self.intra else 2
         self.coder = EntropyCoder()
         self.gaussian = GaussianEncoder()
         self.gaussian.update(self.coder, dev)
@@ -299,19 +323,59 @@ class FrameCoder:
 
     @torch.no_grad()
     def compress(self, x_like: torch.Tensor, qp: int) -> dict:
-        """x_like: the input of the forward that just ran (for the tap shapes).  Returns the two streams and sizes."""
+        """x_like: the input of the forward that just ran (for the tap shapes)."""
+        from . import bitstream
         m = self.model
         y_q = m.get_tap("y_q", x_like)
         scales = m.get_tap("scales_hat", x_like)
         z_hat = m.get_tap("z_hat", x_like)
-        sy = self.gaussian.encode_y(y_q, scales)
-        sz = self.z.encode_z(z_hat, qp)
-        return {"y": sy, "z": sz, "y_shape": tuple(y_q.shape), "z_shape": tuple(z_hat.shape),
-                "bits": 8 * (len(sy) + len(sz))}
+        parts = [self.z.encode_z(z_hat, qp)]
+        for k in range(self.steps):
+            own = owner_mask(k, y_q.shape, self.steps, y_q.device)
+            parts.append(self.gaussian.encode_y(y_q[own], scales[own]))
+        payload = bitstream.pack_streams(*parts)
+        return {"payload": payload, "z": parts[0], "y": parts[1:], "y_shape": tuple(y_q.shape),
+                "z_shape": tuple(z_hat.shape), "bits": 8 * len(payload)}
 
     @torch.no_grad()
-    def decompress_symbols(self, streams: dict, scales: torch.Tensor, qp: int):
-        dev = scales.device
-        z = self.z.decode_z(streams["z"], streams["z_shape"], qp, dev)
-        y = self.gaussian.decode_and_get_y(streams["y"], scales, torch.float32, dev)
-        return y, z
+    def decompress(self, payload: bytes, shape, qp: int, dpb: Optional[dict] = None, after_i: bool = True) -> dict:
+        """shape: (B, 3, H, W) of the frame.  dpb: {"frame", "feature"} for P frames (None for the intra model)."""
+        from . import bitstream
+        m = self.model
+        B, _, H, W = shape
+        dev = next(m.parameters()).device
+        parts = bitstream.unpack_streams(payload)
+        if len(parts) != 1 + self.steps:
+            raise ValueError(f"frame payload holds {len(parts)} streams, expected {1 + self.steps}")
+        h, stream = m._engine(B, H, W, dev)
+        lib = m._lib
+        Cy = 256 if self.intra else m.cfg.ch_y
+        H16, W16 = H // 16, W // 16
+        Hz, Wz = (H16 + 3) // 4, (W16 + 3) // 4
+        z_shape = (B, self.z.channel, Hz, Wz)
+        z_hat = self.z.decode_z(parts[0], z_shape, qp, dev).contiguous()
+        frame = feature = None
+        if not self.intra:
+            if after_i:
+                frame = dpb["frame"].contiguous()
+                m._check_tensor("dpb['frame']", frame, (B, 3, H, W), dev)
+            else:
+                feature = dpb["feature"].contiguous()
+                m._check_tensor("dpb['feature']", feature, (B, m.cfg.ch_d, H // 8, W // 8), dev)
+        with torch.cuda.device(dev):
+            _capi.check(lib.dmc_decode_begin(h, _ptr(frame) if frame is not None else None,
+                                             _ptr(feature) if feature is not None else None, int(qp),
+                                             1 if after_i else 0, _ptr(z_hat), stream), h)
+            y_shape = (B, Cy, H16, W16)
+            sigma = torch.empty(y_shape, dtype=torch.float32, device=dev)
+            for k in range(self.steps):
+                _capi.check(lib.dmc_decode_sigma(h, k, _ptr(sigma), stream), h)
+                own = owner_mask(k, y_shape, self.steps, dev)
+                sym = self.gaussian.decode_and_get_y(parts[1 + k], sigma[own], torch.float32, dev)
+                dense = torch.zeros(y_shape, dtype=torch.float32, device=dev)
+                dense[own] = sym
+                _capi.check(lib.dmc_decode_symbols(h, k, _ptr(dense), stream), h)
+            x_hat = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+            feat = None if self.intra else torch.empty((B, m.cfg.ch_d, H // 8, W // 8), dtype=torch.float32, device=dev)
+            _capi.check(lib.dmc_decode_finish(h, _ptr(x_hat), _ptr(feat) if feat is not None else None, stream), h)
+        return {"dpb": {"frame": x_hat, "feature": feat}}

@@ -154,7 +154,7 @@ def test_container_helpers():
     assert h["nal_type"] == bitstream.NalType.NAL_SPS and bitstream.read_sps_remaining(f, h["sps_id"]) == sps
     h = bitstream.read_header(f)
     qp, payload = bitstream.read_ip_remaining(f)
-    assert h["nal_type"] == bitstream.NalType.NAL_P and qp == 40 and bitstream.unpack_streams(payload) == (b"zz", b"y" * 300)
+    assert h["nal_type"] == bitstream.NalType.NAL_P and qp == 40 and bitstream.unpack_streams(payload) == [b"zz", b"y" * 300]
     helper = bitstream.SPSHelper()
     assert helper.get_sps_id(sps) == (0, True) and helper.get_sps_id(sps) == (0, False)
     assert helper.get_sps_id(dict(sps, width=960)) == (1, True) and helper.get_sps_by_id(1)["width"] == 960

@@ -65,37 +65,95 @@ def test_corrupt_or_mismatched_containers_raise():
     assert torch.equal(coder.decode(g.cdf_group_index, data, idx), sym)       # the coder is still usable
 
 
+def _frame_inputs(variant, H, W, seed=11):
+    frames, masks = D.clips.synthetic_clip(seed, 1, 3, H, W)
+
+    def x_of(t):
+        return frames[:, t].cuda() if variant == "old" else torch.cat([frames[:, t], masks[:, t]], 1).cuda()
+    return frames, x_of
+
+
 @pytest.mark.parametrize("variant", ["old", "performance"])
 def test_frame_symbols_round_trip_and_actual_bits(variant):
-    """forward() -> the frame's y / z symbols coded by the GPU coder -> decoded bit-exactly; the container equals the
+    """forward() -> the frame's z / y symbols coded step by step by the GPU coder; every container equals the
     oracle's; its size is the ideal code length of the tables (+ stream overhead); and -- reported, not gated -- how
     that compares with the bpp forward() estimates (the estimate clamps sigma at 1e-5, the coder's table starts at
     0.11: with random-init weights half the predicted sigmas are negative)."""
     H, W, qp = 256, 384, 32
-    frames, masks = D.clips.synthetic_clip(11, 1, 2, H, W)
+    frames, x_of = _frame_inputs(variant, H, W)
     torch.manual_seed(gc.SEED_P)
     m = D.build_p_model(variant).eval().cuda()
     m.engine_flags = D._capi.FLAG_KEEP_TAPS
-    x = frames[:, 1].cuda() if variant == "old" else torch.cat([frames[:, 1], masks[:, 1]], 1).cuda()
+    x = x_of(1)
     with torch.no_grad():
         r = m(x, qp, {"frame": frames[:, 0].cuda(), "feature": None}, after_i=True)
     fc = entropy.FrameCoder(m)
     streams = fc.compress(x, qp)
     y_q, scales, z_hat = m.get_tap("y_q", x), m.get_tap("scales_hat", x), m.get_tap("z_hat", x)
-    y, z = fc.decompress_symbols(streams, scales, qp)
-    assert torch.equal(y, y_q) and torch.equal(z, z_hat)
-    # the same bytes from the CPU oracle
+    # the same bytes from the CPU oracle, and the symbols back from them
     ty, tz = _tables_of(fc.gaussian), R.Tables(*[a.numpy() for a in fc.z.tables()])
-    iy = fc.gaussian.build_indexes(scales).cpu().numpy()
     iz = fc.z.build_indexes(z_hat.shape, qp, z_hat.device).cpu().numpy()
-    assert streams["y"] == R.encode(ty, y_q.cpu().numpy().astype(np.int32), iy)
     assert streams["z"] == R.encode(tz, z_hat.cpu().numpy().astype(np.int32), iz)
-    ideal = R.ideal_bits(ty, y_q.cpu().numpy(), iy) + R.ideal_bits(tz, z_hat.cpu().numpy(), iz)
-    n_streams = (y_q.numel() + 255) // 256 + (z_hat.numel() + 255) // 256
-    assert streams["bits"] <= 1.02 * ideal + 48 * n_streams + 128
-    payload = D.bitstream.pack_streams(streams["z"], streams["y"])
-    assert D.bitstream.unpack_streams(payload) == (streams["z"], streams["y"])
-    actual_bpp = 8 * len(payload) / (H * W)
+    assert torch.equal(fc.z.decode_z(streams["z"], tuple(z_hat.shape), qp, z_hat.device), z_hat)
+    ideal = R.ideal_bits(tz, z_hat.cpu().numpy(), iz)
+    n_streams = (z_hat.numel() + 255) // 256
+    assert len(streams["y"]) == 2
+    for k, part in enumerate(streams["y"]):
+        own = entropy.owner_mask(k, y_q.shape, 2, y_q.device)
+        sym, sg = y_q[own], scales[own]
+        iy = fc.gaussian.build_indexes(sg).cpu().numpy()
+        assert part == R.encode(ty, sym.cpu().numpy().astype(np.int32), iy)
+        assert torch.equal(fc.gaussian.decode_and_get_y(part, sg, torch.float32, sg.device), sym)
+        ideal += R.ideal_bits(ty, sym.cpu().numpy(), iy)
+        n_streams += (sym.numel() + 255) // 256
+    assert streams["bits"] <= 1.02 * ideal + 48 * n_streams + 256
+    assert D.bitstream.unpack_streams(streams["payload"]) == [streams["z"], *streams["y"]]
+    actual_bpp = streams["bits"] / (H * W)
     print(f"{variant}: estimated bpp {float(r['bpp']):.4f} (sigma clamped at 1e-5), coded {actual_bpp:.4f} bpp "
-          f"({len(payload)} bytes; ideal code length of the tables {ideal / (H * W):.4f} bpp)")
+          f"({len(streams['payload'])} bytes; ideal code length of the tables {ideal / (H * W):.4f} bpp)")
     assert math.isfinite(actual_bpp) and actual_bpp > 0
+
+
+@pytest.mark.parametrize("variant", ["old", "performance", "fast", "mask_prop"])
+def test_p_frames_decode_from_bytes_alone(variant):
+    """The decoder half (dmc_decode_* + the range decoder between its phases) rebuilds x_hat and the feature of both
+    kinds of P frame from the payload, the dpb and qp -- bit-identical to what the encoder's forward() returned, so a
+    decoder's dpb never drifts from the encoder's (video_model.py:256-333: the split the reference sketches)."""
+    H, W, qp = 128, 192, 30
+    frames, x_of = _frame_inputs(variant, H, W, seed=5)
+    torch.manual_seed(gc.SEED_P)
+    m = D.build_p_model(variant).eval().cuda()
+    m.engine_flags = D._capi.FLAG_KEEP_TAPS
+    fc = entropy.FrameCoder(m)
+    dpb_enc = {"frame": frames[:, 0].cuda(), "feature": None}
+    dpb_dec = {"frame": frames[:, 0].cuda(), "feature": None}
+    for t in (1, 2):
+        x = x_of(t)
+        with torch.no_grad():
+            r = m(x, qp, dpb_enc, after_i=(t == 1))
+        payload = fc.compress(x, qp)["payload"]
+        want_frame, want_feat = r["dpb"]["frame"].clone(), r["dpb"]["feature"].clone()
+        d = fc.decompress(payload, (1, 3, H, W), qp, dpb_dec, after_i=(t == 1))
+        assert torch.equal(d["dpb"]["frame"], want_frame), f"{variant} P{t}: x_hat differs"
+        assert torch.equal(d["dpb"]["feature"], want_feat), f"{variant} P{t}: feature differs"
+        dpb_enc, dpb_dec = r["dpb"], d["dpb"]
+    with pytest.raises(ValueError):
+        fc.decompress(D.bitstream.pack_streams(b"", b""), (1, 3, H, W), qp, dpb_dec, after_i=False)
+
+
+def test_intra_frame_decodes_from_bytes_alone():
+    H, W, qp = 128, 192, 37
+    frames, _ = D.clips.synthetic_clip(3, 1, 1, H, W)
+    torch.manual_seed(gc.SEED_I)
+    m = D.DMCI().eval().cuda()
+    m.engine_flags = D._capi.FLAG_KEEP_TAPS
+    fc = entropy.FrameCoder(m)
+    x = frames[:, 0].cuda()
+    with torch.no_grad():
+        r = m(x, qp)
+    want = r["dpb"]["frame"].clone()
+    s = fc.compress(x, qp)
+    assert len(s["y"]) == 4
+    d = fc.decompress(s["payload"], (1, 3, H, W), qp)
+    assert torch.equal(d["dpb"]["frame"], want)
+    print(f"intra: estimated bpp {float(r['bpp']):.4f}, coded {s['bits'] / (H * W):.4f} bpp")
