@@ -337,6 +337,29 @@ __device__ __forceinline__ void tc_mma_pair_sel(uint32_t sel, uint32_t d_tmem, u
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sel)
       : "memory");
 }
+// Same, with the operand descriptors given as their LOW words (start address >> 4 | LBO): the high word is the same
+// constant for every K-major SWIZZLE_32B tile (s3_desc32), and stepping through a stage is then a 32-bit add per
+// operand instead of a 64-bit one (two dependent uniform-datapath instructions per descriptor on the issue path)
+__device__ __forceinline__ void tc_mma_pair_lo(uint32_t sel, uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(sel), "r"(16u | (1u << 14) | (6u << 29))
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mask_sel(uint32_t sel, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(mask), "r"(sel)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_pair_sel(uint32_t sel, uint32_t bar) {
   const uint16_t mask = 3;
   asm volatile(
@@ -446,7 +469,7 @@ constexpr int kS3Threads = 128 + 32 * kS3EpiWarps;
 // or 640 x 96): what warp group 0 gives up (down to 56) is all the epilogue warp groups can take -- 2 x 128 x 56 = 14 336
 // -> 224 each with eight warps; 4 x 128 x 8 = 4 096 of the 5 120 freed -> 104 each with sixteen (asking for 112 blocks
 // the last warp group forever).
-constexpr int kS3EpiRegs = kS3EpiWarps == 16 ? 104 : 224;
+constexpr int kS3EpiRegs = kS3EpiWarps == 16 ? 104 : 216;   // (2 x 128 x 216 + 128 x 72 = 64 512)
 // The epilogue works in chunks of 32 rows x 32 columns per warp (16-column chunks left the warp waiting on one
 // latency after the other: tcgen05.ld, bias loads, the shared-memory fence, the TMA issue -- 1 560 clocks per chunk
 // measured, 6 200 per tile against 3 900 for the MMAs).  Staging tile of a chunk: split planes
@@ -459,8 +482,22 @@ constexpr int kS3EpiRegs = kS3EpiWarps == 16 ? 104 : 224;
 // for it is a formality -- and the 32 KB a third tile per warp would take go to the operand ring, whose bytes in
 // flight are what bounds the operand supply (5 stages = 120 KB per CTA at ~4 000 clocks of loaded L2 latency).
 constexpr int kS3Ring = DMC_S3_RING;
+// 1: an epilogue warp pulls its whole share of the accumulators into registers and hands the TMEM buffer back before any
+// arithmetic.  Measured (profiles/chain_early_release_experiment_r02.txt): the MMA warp no longer waits for buffers, but
+// the 128 pinned registers cost the activation code its interleaving -- epilogue 4 800 -> 5 800 clocks per chunk-add
+// tile, DepthConvBlock-256 148 -> 155 us.  Off: the buffer is released after the last chunk's loads.
+#ifndef DMC_S3_EARLY_RELEASE
+#define DMC_S3_EARLY_RELEASE 0
+#endif
+constexpr bool kS3EarlyRelease = DMC_S3_EARLY_RELEASE != 0;
 constexpr int kS3WarpSmem = kS3Ring * kS3ChunkBytes;
 constexpr int kS3BarBytes = 1024;
+// The bias of a tile, per epilogue warp: the <= 64 accumulator columns the warp works on, double buffered (the next
+// tile's values are requested a tile ahead).  Read straight from global memory per chunk, an L1 miss under the
+// operand traffic sat in front of the first add of the chunk (long-scoreboard stalls on the bias FADDs: 4 % of the
+// kernel's samples, profiles/chain_dcb_r02_stall_summary.txt).
+constexpr int kS3BiasCols = 64;
+constexpr int kS3BiasBytes = kS3EpiWarps * 2 * kS3BiasCols * 4;
 
 // Shared-memory descriptor (cute::UMMA::SmemDescriptor) of a K-major SWIZZLE_32B operand tile = rows of 16 fp16
 // (32 B), which is what the tile-blocked activations and weights are in shared memory: start>>4 [0,14) | LBO (unused)
@@ -469,6 +506,11 @@ __device__ __forceinline__ uint64_t s3_desc32(uint32_t saddr) {
   const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
   const uint32_t hi = 16u | (1u << 14) | (6u << 29);
   return ((uint64_t)hi << 32) | lo;
+}
+
+// ... and from its low word (start >> 4 | LBO), which is what changes from operand to operand
+__device__ __forceinline__ uint64_t s3_desc_lo(uint32_t lo) {
+  return ((uint64_t)(16u | (1u << 14) | (6u << 29)) << 32) | lo;
 }
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -499,7 +541,7 @@ __device__ unsigned long long g_epi_t[8];
 // tile timeline of cluster 0 (CTA 0): per tile [0] MMA warp starts waiting for the TMEM buffer, [1] has it,
 // [2] first operand stage arrived, [3] last MMA issued, [4] epilogue warp 0 starts waiting for the accumulator,
 // [5] has it, [6] done with the tile, [7] table entry
-__device__ unsigned long long g_tile_trace[256][8];
+__device__ unsigned long long g_tile_trace[256][14];   // [8] clocks the MMA warp waited for operand stages, [9] clocks in MMA issue
 // [CTA 0/1][epilogue warp 0 / 7][tile][got accumulator, released TMEM, done]
 __device__ unsigned long long g_warp_trace[2][2][256][3];
 #define WARP_T(t, i) do { if (blockIdx.x < 2 && x.lane == 0 && (x.ew == 0 || x.ew == 7) && (t) < 256u) \
@@ -532,6 +574,8 @@ struct EpiCtx {
   int lane, quad, part;      // part: which share of the tile's columns (0 .. kS3Split-1)
   uint32_t rank;
   uint32_t depsOk;           // shared-memory word: tiles of this CTA whose dependencies the producer warp has seen met
+  uint32_t biasBuf;          // shared-memory copy of the bias of this warp's accumulator columns of the current tile
+  int biasCol0;              // first accumulator column (within the tile) it holds
   bool epi_mem;
 };
 
@@ -601,17 +645,53 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
   const uint32_t rowOff = (uint32_t)lane * 32u;
   const bool two_acc = S.two_acc;
   const float comp = S.comp;
-  for (int c = 0; c < nchunk; ++c) {
+  // ---- phase 1: this warp's whole share of the accumulators leaves TMEM at once (at most two units of kS3ChunkCols
+  // columns x two accumulators: the two chunks of a plain tile, or the value and partner halves of a chunk-add chunk)
+  // and the buffer goes back to the MMA warp BEFORE any arithmetic.  With the release after the last chunk's loads
+  // (i.e. after the whole first chunk: ~3 400 clocks into the tile) the two TMEM buffers tied the MMA side and the
+  // epilogue side together: period = (time to release + time to refill) / 2 instead of max(MMA, epilogue).
+  uint32_t ua[2][kS3ChunkCols], ub[2][kS3ChunkCols];
+#pragma unroll
+  for (int u = 0; u < (kS3EarlyRelease ? 2 : 0); ++u) {
+    const int cu = kPair ? 0 : u;
+    const bool uvalid = cu < nchunk && s3_dest_col(kKind, S.BN, x.part, nt, cu) < S.n_out;   // warp-uniform
+    const int col = s3_acc_col(kKind, S.BN, x.part, cu) + (kPair ? 32 * u : 0);
+    if (uvalid) {
+      if (kS3ChunkCols == 32) {
+        tc_ld32(taddr + col, ua[u]);
+        if (two_acc) tc_ld32(taddr + 128u + col, ub[u]);
+      } else {
+        tc_ld16(taddr + col, ua[u]);
+        if (two_acc) tc_ld16(taddr + 128u + col, ub[u]);
+      }
+    }
+  }
+  if (kS3EarlyRelease) {
+    tc_wait_ld();
+    release_tmem();
+#ifdef DMC_EPI_TIMING
+    WARP_T(x.tile, 1);
+#endif
+    EPI_T(1);
+  }
+  // ---- phase 2: chunk by chunk (from registers, or loading as it goes)
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    if (c >= nchunk) break;
     const int acol = s3_acc_col(kKind, S.BN, x.part, c);         // accumulator column of this chunk
     const int dcol = s3_dest_col(kKind, S.BN, x.part, nt, c);
     const bool valid = dcol < S.n_out;                           // warp-uniform
     EPI_T(7);
-    // The staging tile two chunks back must have been read by its TMA store before it is reused
-    // (by the residual load issued next, or by this chunk's own result when there is no residual).
-    if (lane == 0) {
-      if (kS3Ring >= 3) tma_store_wait_read1(); else tma_store_wait_read0();
+    // Layers with a residual: the tile of chunk c-1 (its store was issued a moment ago) receives the residual of chunk
+    // c+1 now -- it has to arrive a whole chunk ahead (a loaded L2 answers after ~3 000 clocks), so that store's read of
+    // shared memory is waited for here.  Layers without one only need the tile of chunk c-2 back, and not before their
+    // own results are written: that wait (further down) finds the store long done.
+    if (kRes || kRes2) {
+      if (lane == 0) {
+        if (kS3Ring >= 3) tma_store_wait_read1(); else tma_store_wait_read0();
+      }
+      __syncwarp();
     }
-    __syncwarp();
     next_res(c);
     if (kRes2 && valid && x.epi_mem) {
       // both staging tiles are this chunk's: the first residual lands where the result will be written, the second
@@ -633,25 +713,26 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
     EPI_T(0);
     float v[kS3ChunkCols];
     if (valid) {
-      // v (+)= act(main + small * 2^-11 + bias) for accumulator columns [col, col + kS3ChunkCols)
-      auto load_act = [&](int col, bool accumulate) {
-        uint32_t a[kS3ChunkCols], b[kS3ChunkCols];
+      // v (+)= act(main + small * 2^-11 + bias) for the accumulator columns [col, col + kS3ChunkCols) held in a / b
+      auto act = [&](uint32_t* a, uint32_t* b, int col, bool accumulate) {
         float w[kS3ChunkCols];
-        // the bias is requested BEFORE the accumulator loads are waited for: fetched after the wait, its L1 latency sat
-        // in front of the first add of every chunk (6 % of the kernel's stall samples, profiles/chain_dcb_r01_v8_stall_summary.txt)
-        const float4* bp = reinterpret_cast<const float4*>(S.bias + n_idx + col);
         float4 bq[kS3ChunkCols / 4];
 #pragma unroll
-        for (int i = 0; i < kS3ChunkCols / 4; ++i) bq[i] = __ldg(bp + i);
-        if (kS3ChunkCols == 32) {
-          tc_ld32(taddr + col, a);
-          if (two_acc) tc_ld32(taddr + 128u + col, b);
-        } else {
-          tc_ld16(taddr + col, a);
-          if (two_acc) tc_ld16(taddr + 128u + col, b);
+        for (int i = 0; i < kS3ChunkCols / 4; ++i) {
+          const uint4 q = ld_shared_v4(x.biasBuf + (uint32_t)(col - x.biasCol0) * 4u + 16u * i);
+          bq[i] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
         }
-        tc_wait_ld();
-        EPI_T(1);
+        if (!kS3EarlyRelease) {
+          if (kS3ChunkCols == 32) {
+            tc_ld32(taddr + col, a);
+            if (two_acc) tc_ld32(taddr + 128u + col, b);
+          } else {
+            tc_ld16(taddr + col, a);
+            if (two_acc) tc_ld16(taddr + 128u + col, b);
+          }
+          tc_wait_ld();
+          EPI_T(1);
+        }
 #pragma unroll
         for (int i = 0; i < kS3ChunkCols / 4; ++i) {
           const float4 q = bq[i];
@@ -677,10 +758,14 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
           for (int i = 0; i < kS3ChunkCols; ++i) v[i] = w[i];
         }
       };
-      load_act(acol, false);
-      if (kPair) load_act(acol + 32, true);
+      if (kPair) {
+        act(ua[0], ub[0], acol, false);
+        act(ua[kS3EarlyRelease ? 1 : 0], ub[kS3EarlyRelease ? 1 : 0], acol + 32, true);
+      } else {
+        act(ua[kS3EarlyRelease ? c : 0], ub[kS3EarlyRelease ? c : 0], acol, false);
+      }
     }
-    if (c == nchunk - 1) {
+    if (!kS3EarlyRelease && c == nchunk - 1) {
       release_tmem();      // accumulator fully read: hand the TMEM buffer back
 #ifdef DMC_EPI_TIMING
       WARP_T(x.tile, 1);
@@ -714,6 +799,13 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
     if ((kRes || kRes2) && x.epi_mem) add_residual(x.slot);
     if (kRes2 && x.epi_mem) add_residual(x.slot + 1 == kS3Ring ? 0u : x.slot + 1);
     EPI_T(3);
+    if (!(kRes || kRes2)) {
+      // this chunk's staging tile was last read by the store of chunk c-2: all but the newest store have read their data
+      if (lane == 0) {
+        if (kS3Ring >= 3) tma_store_wait_read1(); else tma_store_wait_read1();
+      }
+      __syncwarp();
+    }
     if (S.scale) {
       const float4* sp = reinterpret_cast<const float4*>(S.scale + dcol);
 #pragma unroll
@@ -788,6 +880,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   const uint32_t tmemSlot = barBase + 160u + 32u * kS3EpiWarps;
   const uint32_t depsOk = tmemSlot + 4u;             // number of this CTA's tiles whose dependencies are met
   const uint32_t warpsDone = tmemSlot + 8u;          // [8] epilogue warps of this CTA that finished tile (t & 7)
+  const uint32_t biasBase = barBase + kS3BarBytes;   // [epilogue warp][2][kS3BiasCols] fp32
 
   if (warp == 0 && lane == 0) {
     if (base & 1023u) {
@@ -818,12 +911,20 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   cluster_sync_all();                      // peer barriers are initialised before any remote use
   tc_fence_after();
   pdl_prologue_done();                     // everything above overlapped the previous kernel's tail
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmemSlot - base));
+  // (read where it is used: kept live across the role branches it ended up in local memory, see my_tiles below)
+  auto tmem_base_ld = [&]() { return *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmemSlot - base)); };
   const int unit = (int)(p.cl4 ? blockIdx.x >> 2 : blockIdx.x >> 1);
   const int units = (int)(p.cl4 ? gridDim.x >> 2 : gridDim.x >> 1);
+  // this cluster's entries are table[unit + t * units], t = 0 .. my_tiles-1.  The role loops below count t only: with
+  // an entry index carried as a loop variable ptxas kept it in LOCAL memory, and every publication's
+  // fence.proxy.async.global (CCTL.IVALL: the whole L1 is invalidated) turned the reload at the top of the next tile into
+  // an L2 round trip -- ~770 clocks between two tiles of an epilogue warp, ~300 in the MMA warp.
+  const uint32_t my_tiles = unit < p.n_entries ? (uint32_t)((p.n_entries - unit + units - 1) / units) : 0u;
+  const uint32_t* const my_tab = p.table + unit;
+  auto tab_at = [&](uint32_t t) { return __ldg(my_tab + (size_t)t * (uint32_t)units); };
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kS3EpiWarps == 16 ? 56 : 72) : "memory");
   if (warp == 0) {
     // ------------------------------------------------------------ operand producer (both CTAs)
     // (whole warp walks the loop, one elected lane issues: addresses stay in uniform registers)
@@ -832,10 +933,10 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(p.epoch_ctr) + 1u;
     // (the table entry of the next tile is fetched a tile ahead: its ~700 clocks of global latency sat on the
     // critical path of every tile in this warp and in the MMA warp)
-    uint32_t e_nxt = unit < p.n_entries ? __ldg(p.table + unit) : 0u;
-    for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
+    uint32_t e_nxt = my_tiles ? tab_at(0) : 0u;
+    for (; tcount < my_tiles; ++tcount) {
       const uint32_t e = e_nxt;
-      if (ei + units < p.n_entries) e_nxt = __ldg(p.table + ei + units);
+      if (tcount + 1 < my_tiles) e_nxt = tab_at(tcount + 1);
       const int l = (int)(e >> 28), mt = (int)(e & 0xfffffu);
       const int nt = p.cl4 ? 2 * (int)((e >> 20) & 0xffu) + (int)pairIdx : (int)((e >> 20) & 0xffu);
       const S3StageDev& S = p.st[l];
@@ -897,67 +998,123 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     // no per-MMA register -> uniform-register shuffling); one elected lane issues.
     if (leader) {
       const uint32_t aStep = kS3APlane >> 4;
+      const bool sel = elect_one();                               // the lane that issues
+      const uint32_t alo0 = ((base >> 4) & 0x3FFFu) | (1u << 16);  // low descriptor word of stage 0 (s3_desc32)
+      const uint32_t stageLo = stageBytes >> 4;
+      const bool do_mma = !(p.dbg & 2), twice = (p.dbg & 64) != 0;
       int s = 0;
       uint32_t ph = 0, tcount = 0;
-      uint32_t e_nxt = unit < p.n_entries ? __ldg(p.table + unit) : 0u;
-      for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
+      uint32_t e_nxt = my_tiles ? tab_at(0) : 0u;
+      // the fields of a layer, refreshed when the layer changes (indexed constant loads: ~300 clocks between the last
+      // MMA of a tile and the first of the next when they were read per tile)
+      uint32_t l_c = 0xffffffffu, idesc = 0, wStep = 0, wKs = 0;
+      int k_blocks = 0, kblk = 0;
+      bool split = false;
+      for (; tcount < my_tiles; ++tcount) {
         const uint32_t e = e_nxt;
-        if (ei + units < p.n_entries) e_nxt = __ldg(p.table + ei + units);
-        const S3StageDev& S = p.st[e >> 28];
-        // instruction descriptor: D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0, K-major both,
-        // N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(S.BN >> 3) << 17) | (16u << 24);
-        const uint32_t wStep = ((uint32_t)(S.BN >> 1) * (kS3BK * 2)) >> 4;   // plane stride of the W stage
-        const uint32_t wKs = ((uint32_t)(S.BN >> 1) * 32u) >> 4;             // second 16-wide k block of a plane
-        const int k_blocks = S.k_blocks;
-        const bool split = S.nterms != 1;
-        const int kblk = S.kblk;
+        if (tcount + 1 < my_tiles) e_nxt = tab_at(tcount + 1);
+        if ((e >> 28) != l_c) {
+          l_c = e >> 28;
+          const S3StageDev& S = p.st[l_c];
+          // instruction descriptor: D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0, K-major both,
+          // N>>3 at [17,23), M>>4 at [24,29) with M = 256 for the pair
+          idesc = (1u << 4) | ((uint32_t)(S.BN >> 3) << 17) | (16u << 24);
+          wStep = ((uint32_t)(S.BN >> 1) * (kS3BK * 2)) >> 4;   // plane stride of the W stage
+          wKs = ((uint32_t)(S.BN >> 1) * 32u) >> 4;             // second 16-wide k block of a plane
+          k_blocks = S.k_blocks;
+          split = S.nterms != 1;
+          kblk = S.kblk;
+        }
         const uint32_t buf = tcount & 1;
         TILE_T(tcount, 0, clock64());
         TILE_T(tcount, 7, e);
         mbar_wait(bar_tempty(buf), ((tcount >> 1) & 1) ^ 1, p.err, 2);
         TILE_T(tcount, 1, clock64());
         tc_fence_after();
-        const uint32_t d_main = tmem_base + buf * 256u;
+        const uint32_t d_main = tmem_base_ld() + buf * 256u;
         const uint32_t d_small = d_main + 128u;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+#ifdef DMC_EPI_TIMING
+        long long tw_full = 0, tw_issue = 0, tw_pre = 0, tw_mma = 0, tw_commit = 0;
+        (void)tw_pre; (void)tw_mma; (void)tw_commit;
+#endif
+        // The tensor pipe takes one MMA per 64 clocks and queues hardly any: whatever this warp does between the last
+        // MMA of a stage and the first of the next is idle time of the pipe (tile trace of the one-stage-per-iteration
+        // loop: ~390 clocks of barrier wait / descriptor arithmetic / commit / reconvergence / loop around 360 clocks of
+        // MMA issue per stage: tensor pipe active 46 %).  So TWO operand stages per trip through the loop (one elected
+        // section, one reconvergence), descriptors as 32-bit words stepped by adds, the second stage's barrier
+        // already tested when the first one's MMAs go out.
+        for (int kb = 0; kb < k_blocks; kb += 2) {
+          const bool two = kb + 1 < k_blocks;                       // (an odd count leaves a single stage at the end)
+          int s1 = s + 1;
+          uint32_t ph1 = ph;
+          if (s1 == p.stages) { s1 = 0; ph1 ^= 1; }
+#ifdef DMC_EPI_TIMING
+          const long long tq0 = clock64();
+#endif
           mbar_wait(bar_full(s), ph, p.err, 3);
+          if (two) mbar_wait(bar_full(s1), ph1, p.err, 3);
+#ifdef DMC_EPI_TIMING
+          const long long tq1 = clock64();
+          tw_full += tq1 - tq0;
+#endif
           if (kb == 0) TILE_T(tcount, 2, clock64());
           tc_fence_after();
-          const uint32_t sa = base + s * stageBytes;
-          const uint64_t da = s3_desc32(sa);
-          const uint64_t dw = s3_desc32(sa + kPlanes * kS3APlane);
-          const uint32_t first = kb == 0 ? 0u : 1u;
-          if (elect_one()) {
-            if (!(p.dbg & 2)) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (ks >= kblk) break;
-                // hi*hi -> main accumulator; the two 2^11-scaled cross terms hi*lo', lo'*hi -> second one
-                // (plane index: 0 hi, 1 lo'; a single-term stage is four k blocks of the hi plane)
-                const uint64_t a0 = da + ks * (4096u >> 4), a1 = a0 + aStep;
-                const uint64_t w0 = dw + ks * wKs, w1 = w0 + wStep;
-                tc_mma_pair(d_main, a0, w0, idesc, ks == 0 ? first : 1u);
-                if (split) {
-                  tc_mma_pair(d_small, a0, w1, idesc, ks == 0 ? first : 1u);
-                  tc_mma_pair(d_small, a1, w0, idesc, 1u);
+          const uint32_t alo = alo0 + (uint32_t)s * stageLo;       // low descriptor word: hi plane, first k block
+          const uint32_t wlo = alo + ((kPlanes * kS3APlane) >> 4);
+          const uint32_t alo1 = alo0 + (uint32_t)s1 * stageLo;
+          const uint32_t wlo1 = alo1 + ((kPlanes * kS3APlane) >> 4);
+          const uint32_t acc0 = kb == 0 ? 0u : 1u;
+          const bool last = kb + 2 >= k_blocks;
+          if (sel) {
+            // hi*hi -> main accumulator; the two 2^11-scaled cross terms hi*lo', lo'*hi -> second one
+            // (a plane of the A stage is 8 KB = 512 descriptor units, a 16-wide k block 4 KB = 256; a single-term
+            // stage holds kblk = 2 or 4 k blocks of the hi plane)
+            auto stage_mmas = [&](uint32_t a, uint32_t w, uint32_t acc) {
+              if (!do_mma) return;
+              if (split) {
+                tc_mma_pair(d_main, s3_desc_lo(a), s3_desc_lo(w), idesc, acc);
+                tc_mma_pair(d_small, s3_desc_lo(a), s3_desc_lo(w + wStep), idesc, acc);
+                tc_mma_pair(d_small, s3_desc_lo(a + aStep), s3_desc_lo(w), idesc, 1u);
+                tc_mma_pair(d_main, s3_desc_lo(a + 256u), s3_desc_lo(w + wKs), idesc, 1u);
+                tc_mma_pair(d_small, s3_desc_lo(a + 256u), s3_desc_lo(w + wKs + wStep), idesc, 1u);
+                tc_mma_pair(d_small, s3_desc_lo(a + 256u + aStep), s3_desc_lo(w + wKs), idesc, 1u);
+                if (twice) {           // probe: every MMA twice (is a stage bound by the tensor pipe or by its barriers?)
+                  tc_mma_pair(d_main, s3_desc_lo(a), s3_desc_lo(w), idesc, 1u);
+                  tc_mma_pair(d_small, s3_desc_lo(a), s3_desc_lo(w + wStep), idesc, 1u);
+                  tc_mma_pair(d_small, s3_desc_lo(a + aStep), s3_desc_lo(w), idesc, 1u);
+                  tc_mma_pair(d_main, s3_desc_lo(a + 256u), s3_desc_lo(w + wKs), idesc, 1u);
+                  tc_mma_pair(d_small, s3_desc_lo(a + 256u), s3_desc_lo(w + wKs + wStep), idesc, 1u);
+                  tc_mma_pair(d_small, s3_desc_lo(a + 256u + aStep), s3_desc_lo(w + wKs), idesc, 1u);
                 }
-                if (p.dbg & 64) {      // probe: every MMA twice (is a k block bound by the tensor pipe or by its barriers?)
-                  tc_mma_pair(d_main, a0, w0, idesc, 1u);
-                  if (split) {
-                    tc_mma_pair(d_small, a0, w1, idesc, 1u);
-                    tc_mma_pair(d_small, a1, w0, idesc, 1u);
-                  }
+              } else {
+                tc_mma_pair(d_main, s3_desc_lo(a), s3_desc_lo(w), idesc, acc);
+                tc_mma_pair(d_main, s3_desc_lo(a + 256u), s3_desc_lo(w + wKs), idesc, 1u);
+                if (kblk == 4) {
+                  tc_mma_pair(d_main, s3_desc_lo(a + 512u), s3_desc_lo(w + 2u * wKs), idesc, 1u);
+                  tc_mma_pair(d_main, s3_desc_lo(a + 768u), s3_desc_lo(w + 3u * wKs), idesc, 1u);
                 }
               }
-            }
+            };
+            stage_mmas(alo, wlo, acc0);
             tc_commit_pair(bar_empty(s), clusterMask);
-            if (kb == k_blocks - 1) tc_commit_pair(bar_tfull(buf), pairMask);
+            if (two) {
+              stage_mmas(alo1, wlo1, 1u);
+              tc_commit_pair(bar_empty(s1), clusterMask);
+            }
+            if (last) tc_commit_pair(bar_tfull(buf), pairMask);
           }
-          if (kb == k_blocks - 1) TILE_T(tcount, 3, clock64());
-          __syncwarp();
+          if (last) TILE_T(tcount, 3, clock64());
+#ifdef DMC_EPI_TIMING
+          tw_issue += clock64() - tq1;
+#endif
+          if (two) { s = s1; ph = ph1; }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        TILE_T(tcount, 8, tw_full);
+        TILE_T(tcount, 9, tw_issue);
+        TILE_T(tcount, 10, tw_pre);
+        TILE_T(tcount, 11, tw_mma);
+        TILE_T(tcount, 12, tw_commit);
       }
     }
   } else if (warp == 2) {
@@ -968,8 +1125,10 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     // critical path of the tile, stayed the last one, and set the pace of every chunk-add layer: 6 600 clocks per
     // tile with the MMAs done after 4 300.)
     uint32_t tcount = 0;
-    for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
-      const uint32_t e = __ldg(p.table + ei);
+    uint32_t e_nxt = my_tiles ? tab_at(0) : 0u;
+    for (; tcount < my_tiles; ++tcount) {
+      const uint32_t e = e_nxt;
+      if (tcount + 1 < my_tiles) e_nxt = tab_at(tcount + 1);
       const int l = (int)(e >> 28), mt = (int)(e & 0xfffffu);
       if (!p.st[l].publish) continue;
       const uint32_t cnt = warpsDone + 4u * (tcount & 7u);
@@ -1046,23 +1205,49 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       fence_proxy_async_global();
       asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(cnt), "r"(1u) : "memory");
     };
-    uint32_t e_next = unit < p.n_entries ? __ldg(p.table + unit) : 0u;
+    // table entries are fetched TWO tiles ahead: the entry of the next tile is needed at the top of this one (is it
+    // in the same layer?), and a load issued there put its ~700-900 clocks of global latency between every two tiles
+    // of this warp (tile trace: done(t) -> wait_acc(t+1) = 900 clocks with the accumulator long ready)
+    uint32_t e_next = my_tiles ? tab_at(0) : 0u;
+    uint32_t e_next2 = my_tiles > 1 ? tab_at(1) : 0u;
     int l_cached = -1;
+    bool publish_l = false;
+    uint32_t bias_tile = 0xffffffffu;            // tile number whose bias is already in its shared-memory buffer
     StageRegs S;
-    for (int ei = unit; ei < p.n_entries; ei += units, ++tcount) {
+    for (; tcount < my_tiles; ++tcount) {
       const uint32_t e = e_next;
       const int l = (int)(e >> 28), mt = (int)(e & 0xfffffu);
       const int nt = p.cl4 ? 2 * (int)((e >> 20) & 0xffu) + (int)pairIdx : (int)((e >> 20) & 0xffu);
-      if (l != l_cached) { S = s3_load_stage(p.st[l]); l_cached = l; }
+      if (l != l_cached) { S = s3_load_stage(p.st[l]); publish_l = p.st[l].publish != 0; l_cached = l; }
       const uint32_t buf = tcount & 1;
       const int nchunk = s3_nchunk(S.kind, S.BN, x.part);
+      // bias of this warp's accumulator columns: lane i holds columns 2i, 2i+1 of the warp's window
+      const int bias_col0 = s3_acc_col(S.kind == S3_PAIR ? S3_PAIR : S3_PLAIN, S.BN, x.part, 0);   // (+ up to 64 columns)
+      auto bias_fetch = [&](int nt_) {
+        float2 v = make_float2(0.f, 0.f);
+        if (bias_col0 + 2 * lane < S.BN) v = __ldg(reinterpret_cast<const float2*>(S.bias + nt_ * S.BN + bias_col0) + lane);
+        return v;
+      };
+      auto bias_put = [&](uint32_t b, float2 v) {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(biasBase + ((uint32_t)ew * 2u + b) * (kS3BiasCols * 4u) + 8u * lane),
+                     "f"(v.x), "f"(v.y) : "memory");
+      };
+      if (bias_tile != tcount) {                 // first tile of a layer: not requested a tile ahead
+        bias_put(buf, bias_fetch(nt));
+        __syncwarp();
+      }
+      x.biasBuf = biasBase + ((uint32_t)ew * 2u + buf) * (kS3BiasCols * 4u);
+      x.biasCol0 = bias_col0;
       // the first residual of the next tile is prefetched early only within a layer (same cached fields);
       // across a layer boundary it is issued when that tile starts
-      bool has_next = ei + units < p.n_entries;
-      if (has_next) {
-        e_next = __ldg(p.table + ei + units);
-        has_next = (e_next >> 28) == (uint32_t)l;
-      }
+      bool has_next = tcount + 1 < my_tiles;
+      e_next = e_next2;
+      if (tcount + 2 < my_tiles) e_next2 = tab_at(tcount + 2);
+      if (has_next) has_next = (e_next >> 28) == (uint32_t)l;
+      // (requested now, stored after this tile's work: its latency is never waited for)
+      float2 bias_nxt = make_float2(0.f, 0.f);
+      if (has_next)
+        bias_nxt = bias_fetch(p.cl4 ? 2 * (int)((e_next >> 20) & 0xffu) + (int)pairIdx : (int)((e_next >> 20) & 0xffu));
       // Publishing the previous tile: if this tile's accumulator is not ready yet there is idle time (and this
       // tile may even depend on the previous one): wait for the stores and publish now.  If it is ready, its
       // dependencies were met long ago, so the publication can ride along with chunk 1 below at no cost.
@@ -1078,14 +1263,23 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       WARP_T(tcount, 0);
 #endif
       tc_fence_after();
-      if (res_tile != tcount) issue_res(S, e, 0, tcount, true, x.slot);   // the early prefetch of chunk 0 was not possible
-      const uint32_t taddr = tmem_base + ((uint32_t)(x.quad * 32) << 16) + buf * 256u;
+      if (res_tile != tcount && S.kind == S3_RES) {    // the early prefetch of chunk 0 was not possible
+        // (a tile of a layer without residuals may have left the store two back still reading this staging tile)
+        if (lane == 0) tma_store_wait_read1();
+        __syncwarp();
+        issue_res(S, e, 0, tcount, true, x.slot);
+      }
+      const uint32_t taddr = tmem_base_ld() + ((uint32_t)(x.quad * 32) << 16) + buf * 256u;
       auto release_tmem = [&]() {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (leader) mbar_arrive(bar_tempty(buf));
           else mbar_arrive_cluster(mapa(bar_tempty(buf), leaderRank));
+#ifdef DMC_EPI_TIMING
+          if (blockIdx.x == 0 && tcount < 256u) atomicMax(&g_tile_trace[tcount][13], (unsigned long long)clock64());
+          if (blockIdx.x == 0 && tcount < 256u && ew == 1) g_tile_trace[tcount][10] = (unsigned long long)clock64();
+#endif
         }
       };
       const bool stored0 = x.epi_mem && s3_dest_col(S.kind, S.BN, x.part, nt, 0) < S.n_out;
@@ -1109,6 +1303,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       } else {
         s3_epilogue_tile(S, x, mt, nt, taddr, p.err, next_res, release_tmem);
       }
+      if (ew == 0) TILE_T(tcount, 11, clock64());
       if (pending) {
         // (tiles in which this warp has fewer than two chunks -- every tile of a chunk-add layer.)  Only the stores of
         // the PREVIOUS tile have to be complete: waiting for the store just issued put its whole round trip on the
@@ -1119,12 +1314,18 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         }
         pending = false;
       }
+      if (ew == 0) TILE_T(tcount, 12, clock64());
+      if (has_next) {
+        bias_put(buf ^ 1u, bias_nxt);            // (that buffer was last read two tiles ago by this same warp)
+        __syncwarp();
+        bias_tile = tcount + 1;
+      }
       if (ew == 0) TILE_T(tcount, 6, clock64());
 #ifdef DMC_EPI_TIMING
       WARP_T(tcount, 2);
 #endif
       pend_l = (uint32_t)l; pend_mt = (uint32_t)mt; pend_t = tcount;
-      pending = p.st[l].publish != 0;
+      pending = publish_l;
       // Chains with fewer than ~3 waves of tiles per layer (the H/16 ... H/64 stages at batch 1) run into their
       // dependencies: a cluster's next tile needs rows another cluster has only just finished, and the deferred
       // publication above adds most of a tile time (2 500-5 000 clocks) to that wait.  There the ~1 500 clocks an
@@ -1148,7 +1349,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   cluster_sync_all();                      // nobody leaves while the peer can still touch its smem
   if (warp == 1) {
     const uint32_t ncols = 512;
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_ld()), "r"(ncols) : "memory");
   }
   if (threadIdx.x == 0) {
     // every CTA read the launch number when it started; the last one to leave closes the launch
@@ -1320,7 +1521,7 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
   }
   // smem plan
   const int stage_bytes = kPlanes * (kS3APlane + (maxBN / 2) * kS3BK * 2);
-  const int fixed = kS3EpiWarps * kS3WarpSmem + kS3BarBytes;
+  const int fixed = kS3EpiWarps * kS3WarpSmem + kS3BarBytes + kS3BiasBytes;
   int nst = (smem_max - fixed) / stage_bytes;
   if (nst > 8) nst = 8;
   if (const char* v = getenv("DMC_S3_STAGES")) {       // experiments: cap the operand ring depth
@@ -1451,7 +1652,7 @@ extern "C" __attribute__((visibility("default"))) int dmc_debug_warp_trace(unsig
   return cudaMemcpyFromSymbol(out, dmc::g_warp_trace, sizeof(unsigned long long) * 2 * 2 * 256 * 3) == cudaSuccess ? 0 : -1;
 }
 extern "C" __attribute__((visibility("default"))) int dmc_debug_tile_trace(unsigned long long* out, int ntiles) {
-  return cudaMemcpyFromSymbol(out, dmc::g_tile_trace, sizeof(unsigned long long) * 8 * (size_t)ntiles) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(out, dmc::g_tile_trace, sizeof(unsigned long long) * 14 * (size_t)ntiles) == cudaSuccess ? 0 : -1;
 }
 extern "C" __attribute__((visibility("default"))) int dmc_debug_epi_timing(unsigned long long* out8, int reset) {
   if (out8) cudaMemcpyFromSymbol(out8, dmc::g_epi_t, sizeof(unsigned long long) * 8);
