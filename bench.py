@@ -81,6 +81,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.power, self.power_limit = [], None
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -89,6 +90,10 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            try:
+                self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1000.0
+            except Exception:   # noqa: BLE001
+                pass
         except Exception:   # noqa: BLE001
             self.nv = None
 
@@ -99,6 +104,10 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:   # noqa: BLE001
+                    pass
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
                     nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for k, bit in names.items():
@@ -122,8 +131,13 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
-        return {"sm_mhz": statistics.median(self.samples), "sm_mhz_min": min(self.samples),
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        out = {"sm_mhz": statistics.median(self.samples), "sm_mhz_min": min(self.samples),
+               "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        if self.power:
+            # (board power against its enforced limit: with sw_power_cap set the frame rate is bound by energy per frame)
+            out["power_w"] = round(statistics.median(self.power), 1)
+            out["power_limit_w"] = self.power_limit
+        return out
 
 
 # ----------------------------------------------------------------------------------------------------------

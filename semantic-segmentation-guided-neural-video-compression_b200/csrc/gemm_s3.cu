@@ -490,6 +490,11 @@ constexpr int kS3Ring = DMC_S3_RING;
 #define DMC_S3_EARLY_RELEASE 0
 #endif
 constexpr bool kS3EarlyRelease = DMC_S3_EARLY_RELEASE != 0;
+// 1: the A and W loads of an operand stage are issued by two warps (see the W producer in the kernel)
+#ifndef DMC_S3_SPLIT_PRODUCER
+#define DMC_S3_SPLIT_PRODUCER 1
+#endif
+constexpr bool kS3SplitProducer = DMC_S3_SPLIT_PRODUCER != 0;
 constexpr int kS3WarpSmem = kS3Ring * kS3ChunkBytes;
 constexpr int kS3BarBytes = 1024;
 // The bias of a tile, per epilogue warp: the <= 64 accumulator columns the warp works on, double buffered (the next
@@ -961,8 +966,18 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       const uint32_t tx = (S.nterms == 1 ? (uint32_t)kblk : 4u) * (kS3APlane + ((p.dbg & 32) ? 0u : wRows * (kS3BK * 2)));
       const int m_idx = mt * 256 + (int)rank * 128;
       const int n_idx = nt * S.BN + (int)(rank * wRows);
+#ifdef DMC_EPI_TIMING
+      long long tp_wait = 0, tp_issue = 0;
+#endif
       for (int kb = 0; kb < S.k_blocks; ++kb) {
+#ifdef DMC_EPI_TIMING
+        const long long tp0 = clock64();
+#endif
         mbar_wait(bar_empty(s), ph ^ 1, p.err, 1);
+#ifdef DMC_EPI_TIMING
+        const long long tp1 = clock64();
+        tp_wait += tp1 - tp0;
+#endif
         const uint32_t sa = base + s * stageBytes;
         const uint32_t sw = sa + kPlanes * kS3APlane;
         if (elect_one()) {
@@ -985,12 +1000,17 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
             } else {
               tma_load_pair(sa, &S.tmA, m_idx >> 4, kb * kblk, lbar);
             }
-            if (!(p.dbg & 32)) tma_load_pair_w(sw, &S.tmW, n_idx >> 4, kb * kblk, lbar);
+            if (!kS3SplitProducer && !(p.dbg & 32)) tma_load_pair_w(sw, &S.tmW, n_idx >> 4, kb * kblk, lbar);
           }
         }
         __syncwarp();
+#ifdef DMC_EPI_TIMING
+        tp_issue += clock64() - tp1;
+#endif
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
+      TILE_T(tcount, 11, tp_wait);
+      TILE_T(tcount, 12, tp_issue);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA)
@@ -1112,9 +1132,35 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         }
         TILE_T(tcount, 8, tw_full);
         TILE_T(tcount, 9, tw_issue);
-        TILE_T(tcount, 10, tw_pre);
-        TILE_T(tcount, 11, tw_mma);
-        TILE_T(tcount, 12, tw_commit);
+      }
+    }
+  } else if (warp == 3 && kS3SplitProducer) {
+    // ------------------------------------------------------------ W producer (both CTAs)
+    // Issuing a TMA load costs the issuing warp ~200 clocks whatever its size (producer trace: 440 clocks in the issue
+    // section per operand stage = two loads, against 80 waiting for a free slot): with A and W issued by ONE warp the
+    // operand supply was bound by that warp's instruction stream, 3 500 of a tile's 5 800 clocks, while the ring was never
+    // full.  The otherwise idle fourth warp takes the W half tiles; the leader's A producer still arms the stage's
+    // barrier for all the bytes (complete_tx of W may land before that expect_tx: the phase cannot complete before the
+    // leader's arrival).
+    if (!(p.dbg & (1 | 32))) {
+      int s = 0;
+      uint32_t ph = 0, tcount = 0;
+      uint32_t e_nxt = my_tiles ? tab_at(0) : 0u;
+      for (; tcount < my_tiles; ++tcount) {
+        const uint32_t e = e_nxt;
+        if (tcount + 1 < my_tiles) e_nxt = tab_at(tcount + 1);
+        const int nt = p.cl4 ? 2 * (int)((e >> 20) & 0xffu) + (int)pairIdx : (int)((e >> 20) & 0xffu);
+        const S3StageDev& S = p.st[e >> 28];
+        const int kblk = S.kblk, k_blocks = S.k_blocks;
+        const int n16 = (nt * S.BN + (int)(rank * ((uint32_t)S.BN >> 1))) >> 4;
+        const CUtensorMap* tmW = &S.tmW;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(bar_empty(s), ph ^ 1, p.err, 1);
+          const uint32_t sw = base + s * stageBytes + kPlanes * kS3APlane;
+          if (elect_one()) tma_load_pair_w(sw, tmW, n16, kb * kblk, mapa(bar_full(s), leaderRank));
+          __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 2) {
@@ -1303,7 +1349,6 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       } else {
         s3_epilogue_tile(S, x, mt, nt, taddr, p.err, next_res, release_tmem);
       }
-      if (ew == 0) TILE_T(tcount, 11, clock64());
       if (pending) {
         // (tiles in which this warp has fewer than two chunks -- every tile of a chunk-add layer.)  Only the stores of
         // the PREVIOUS tile have to be complete: waiting for the store just issued put its whole round trip on the
@@ -1314,7 +1359,6 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         }
         pending = false;
       }
-      if (ew == 0) TILE_T(tcount, 12, clock64());
       if (has_next) {
         bias_put(buf ^ 1u, bias_nxt);            // (that buffer was last read two tiles ago by this same warp)
         __syncwarp();

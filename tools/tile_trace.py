@@ -31,7 +31,7 @@ for t in range(N):
     period = "" if prev_done is None else rel[6] - prev_done
     prev_done = rel[6]
     print(f"{t:4d} {e >> 28:5d} {(e >> 20) & 0xff:2d} {e & 0xfffff:4d} | {rel[0]:9d} {rel[1]:9d} {rel[2]:9d} {rel[3]:9d} | "
-          f"{rel[4]:9d} {rel[5]:9d} {rel[6]:9d} | {rel[3] - rel[1]:6d} {rel[6] - rel[5]:6d} {period}  | opwait {r[8]:6d} issue {r[9]:6d} | epi: last release of CTA0 {int(r[13]) - int(t0):9d} (warp 1: {int(r[10]) - int(t0):9d}) tile_end {int(r[11]) - int(t0):9d} published {int(r[12]) - int(t0):9d}")
+          f"{rel[4]:9d} {rel[5]:9d} {rel[6]:9d} | {rel[3] - rel[1]:6d} {rel[6] - rel[5]:6d} {period}  | opwait {r[8]:6d} issue {r[9]:6d} | producer: wait-empty {r[11]:6d} issue {r[12]:6d} | last TMEM release of CTA0 {int(r[13]) - int(t0):9d}")
 
 wb = (ctypes.c_ulonglong * (2 * 2 * 256 * 3))()
 lib.dmc_debug_warp_trace(wb)
