@@ -143,6 +143,23 @@ int dmc_get_tap(dmc_engine* e, const char* name, float* dst, int64_t capacity_el
 int dmc_frame_stats(double* stats7, const float* x_hat, const float* x, const float* mask,
                     const float* bpp3, int batch, int height, int width, void* stream);
 
+/* Device data path (the dataset side of the caller): decoded camera frames, uint8 interleaved (frames, height, width, 3)
+ * in R,G,B order (bgr = 1: B,G,R as cv2.imdecode returns them), and cached masks uint8 (frames, height, width) or
+ * NULL  ->  (frames, out_channels, crop_h, crop_w) fp32 planes [Y, Cb, Cr(, mask)], cropped at (top, left).
+ *   src/dataset/seg_waymo_dataset.py:26-34  _rgb_from_proto        uint8 / 255.0
+ *   src/dataset/seg_waymo_dataset.py:36-43  _rgb_to_ycbcr_bt709    BT.709, clamp to [0, 1]
+ *   src/dataset/seg_waymo_dataset.py:56-79  _load_cached_mask      mask = value > mask_threshold (0 for the 0/1 npz
+ *                                                                  cache, 127 for the png cache); NULL mask = zeros
+ *   src/dataset/seg_waymo_dataset.py:231-245 __getitem__           one crop for all frames, mask as channel 4
+ * Bit-identical to those lines run on the CPU in fp32.  All pointers are device pointers. */
+int dmc_frames_from_u8(const uint8_t* img, const uint8_t* mask, float* out, int frames, int height, int width, int top,
+                       int left, int crop_h, int crop_w, int out_channels, int bgr, int mask_threshold, void* stream);
+
+/* Mask propagation (BASELINE config 4): mask[i] = logits[i] > 0 ? 1 : 0 -- the MaskPredictor's logits of frame t-1
+ * (dmc_forward's mask_pred, src/refactor/mask_predictor.py:27-46) become the mask frame t is coded with.
+ * Both pointers 16-byte aligned. */
+int dmc_mask_from_logits(const float* logits, float* mask, int64_t n, void* stream);
+
 /* ---- single-operator entry points (the same kernels the engine launches), used by the
  * per-layer parity tests.  All tensors NCHW fp32 on the device. ---- */
 

@@ -38,6 +38,8 @@ SIGNATURES = {
     "dmc_get_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
     "dmc_frame_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 c_int, c_void_p]),
+    "dmc_frames_from_u8": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
+    "dmc_mask_from_logits": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dmc_op_conv2d": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
     "dmc_op_depth_conv_block": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p] +
                                 [c_int] * 8 + [c_void_p]),

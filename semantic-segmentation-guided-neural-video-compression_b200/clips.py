@@ -154,3 +154,35 @@ def run_gop(i_model, p_model, variant: str, frames: torch.Tensor, masks: Optiona
             stats.add_frame(res, frames[:, t], masks[:, t] if masks is not None else None)
         outs.append(res)
     return outs
+
+
+class GopCoder:
+    """A `mask_prop` GOP that needs ONE segmentation mask (the replacement of per-frame mask
+    generation, src/utils/build_cache.py:143-236, by propagation).  Protocol of SURVEY.md 8(d) config 4: P frame 1
+    (after the intra frame) and P frame 2 are coded with the given mask; from frame 3 on the mask is the previous
+    frame's `mask_pred` (src/refactor/mask_predictor.py:27-46) thresholded at logit 0 (`data.mask_from_logits`).
+    Same results as `run_gop(..., mask_feedback=True)`; `masks_used` keeps what each P frame saw."""
+
+    def __init__(self, i_model, p_model, qp: int):
+        if getattr(p_model, "variant", None) != "mask_prop":
+            raise ValueError("GopCoder needs the mask_prop variant (the only one with a MaskPredictor)")
+        self.i_model, self.p_model, self.qp = i_model, p_model, int(qp)
+        self.masks_used: List[torch.Tensor] = []
+
+    @torch.no_grad()
+    def code(self, frames: torch.Tensor, first_mask: torch.Tensor, stats: Optional[ClipStats] = None):
+        """frames (B,T,3,H,W); first_mask (B,1,H,W) in {0,1}: the segmentation of frame 1."""
+        from . import data
+        self.masks_used = []
+        res = self.i_model(frames[:, 0], self.qp)
+        outs, dpb, pred = [res], res["dpb"], None
+        for t in range(1, frames.shape[1]):
+            m = first_mask if t <= 2 or pred is None else data.mask_from_logits(pred)
+            self.masks_used.append(m)
+            res = self.p_model(torch.cat([frames[:, t], m], dim=1), self.p_model.shift_qp(self.qp, INDEX_MAP[t % 8]), dpb,
+                               after_i=(t == 1))
+            pred, dpb = res.get("mask_pred"), res["dpb"]
+            if stats is not None:
+                stats.add_frame(res, frames[:, t], m)
+            outs.append(res)
+        return outs

@@ -1428,6 +1428,23 @@ int dmc_frame_stats(double* stats7, const float* x_hat, const float* x, const fl
   return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
 }
 
+int dmc_frames_from_u8(const uint8_t* img, const uint8_t* mask, float* out, int frames, int height, int width, int top,
+                       int left, int crop_h, int crop_w, int out_channels, int bgr, int mask_threshold, void* stream) {
+  if (!img || !out || frames < 1 || height < 1 || width < 1 || crop_h < 1 || crop_w < 1 || top < 0 || left < 0 ||
+      top + crop_h > height || left + crop_w > width || (out_channels != 3 && out_channels != 4) || frames > 65535 ||
+      crop_h > 65535)
+    return DMC_E_INVALID;
+  frames_from_u8(img, mask, out, frames, height, width, top, left, crop_h, crop_w, out_channels, bgr != 0,
+                 mask_threshold, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
+}
+
+int dmc_mask_from_logits(const float* logits, float* mask, int64_t n, void* stream) {
+  if (!logits || !mask || n < 0 || ((uintptr_t)logits | (uintptr_t)mask) % 16) return DMC_E_INVALID;
+  if (n) mask_from_logits(logits, mask, (long long)n, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
+}
+
 int64_t dmc_kernel_launches(void) { return (int64_t)launch_count(); }
 int dmc_profile_enable(dmc_engine* e, int on) {
   if (!e) return DMC_E_INVALID;

@@ -1204,4 +1204,81 @@ void frame_stats(double* stats7, const float* x_hat, const float* x, const float
   launch(k_frame_stats_bits, 1, 32, 0, st, stats7, bpp3, B, (double)HW, (double)n);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Device data path: decoded camera frames (uint8, interleaved) + cached masks (uint8) -> the
+// (N, 4, h, w) fp32 [Y, Cb, Cr, mask] tensors the trainer feeds the codec, cropped on the way.
+//   src/dataset/seg_waymo_dataset.py:26-34   rgb = uint8 / 255.0
+//   src/dataset/seg_waymo_dataset.py:36-43   BT.709: y = Kr r + Kg g + Kb b; cb = 0.5 (b - y) / (1 - Kb) + 0.5; cr likewise; clamp
+//   src/dataset/seg_waymo_dataset.py:56-79   mask in {0, 1} (npz: stored 0/1, png: > 127)
+//   src/dataset/seg_waymo_dataset.py:231-245 one crop for the whole sequence, mask appended as channel 4
+// Every operation in the reference's order with IEEE roundings (the reference runs these lines on the CPU in fp32: true
+// divisions, no FMA contraction): the output is bit-identical.  4 pixels per thread: 12 + 4 bytes in, 4 x 16 bytes out.
+__global__ void k_frames_from_u8(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, float* __restrict__ out,
+                                 int H0, int W0, int top, int left, int h, int w, int out_ch, int bgr, int mask_thr) {
+  pdl_prologue_done();
+  const int n = blockIdx.z, y = blockIdx.y;
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x0 >= w) return;
+  const size_t plane = (size_t)h * w;
+  const uint8_t* src = img + (((size_t)n * H0 + (top + y)) * W0 + (left + x0)) * 3;
+  const uint8_t* msrc = mask ? mask + ((size_t)n * H0 + (top + y)) * W0 + (left + x0) : nullptr;
+  float* dst = out + (size_t)n * out_ch * plane + (size_t)y * w + x0;
+  const int cnt = min(4, w - x0);
+  const float Kr = 0.2126f, Kg = 0.7152f, Kb = 0.0722f;
+  const float dcb = (float)(1.0 - 0.0722), dcr = (float)(1.0 - 0.2126);      // Python doubles, rounded when they meet the tensor
+  float Y[4], Cb[4], Cr[4], M[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < cnt) {
+      const float c0 = __fdiv_rn((float)__ldg(src + 3 * i), 255.0f);
+      const float c1 = __fdiv_rn((float)__ldg(src + 3 * i + 1), 255.0f);
+      const float c2 = __fdiv_rn((float)__ldg(src + 3 * i + 2), 255.0f);
+      const float r = bgr ? c2 : c0, g = c1, b = bgr ? c0 : c2;
+      const float yy = __fadd_rn(__fadd_rn(__fmul_rn(Kr, r), __fmul_rn(Kg, g)), __fmul_rn(Kb, b));
+      const float cb = __fadd_rn(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(b, yy)), dcb), 0.5f);
+      const float cr = __fadd_rn(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(r, yy)), dcr), 0.5f);
+      Y[i] = fminf(fmaxf(yy, 0.0f), 1.0f);
+      Cb[i] = fminf(fmaxf(cb, 0.0f), 1.0f);
+      Cr[i] = fminf(fmaxf(cr, 0.0f), 1.0f);
+      M[i] = (msrc && (int)__ldg(msrc + i) > mask_thr) ? 1.0f : 0.0f;
+    } else {
+      Y[i] = Cb[i] = Cr[i] = M[i] = 0.0f;
+    }
+  }
+  const bool vec = cnt == 4 && (w & 3) == 0;                 // (then every row start is 16-byte aligned)
+  float* planes[4] = {dst, dst + plane, dst + 2 * plane, dst + 3 * plane};
+  const float* vals[4] = {Y, Cb, Cr, M};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c >= out_ch) break;
+    if (vec) {
+      *reinterpret_cast<float4*>(planes[c]) = make_float4(vals[c][0], vals[c][1], vals[c][2], vals[c][3]);
+    } else {
+      for (int i = 0; i < cnt; ++i) planes[c][i] = vals[c][i];
+    }
+  }
+}
+void frames_from_u8(const uint8_t* img, const uint8_t* mask, float* out, int N, int H0, int W0, int top, int left, int h,
+                    int w, int out_ch, int bgr, int mask_thr, cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(cdiv(w, 4), 128), (unsigned)h, (unsigned)N);
+  launch(k_frames_from_u8, grid, 128, 0, st, img, mask, out, H0, W0, top, left, h, w, out_ch, bgr, mask_thr);
+}
+
+// Mask propagation: the predictor's logits of frame t-1, thresholded at sigma = 0.5
+// (logit > 0), are the mask frame t is coded with.
+__global__ void k_mask_from_logits(const float* __restrict__ logits, float* __restrict__ mask, long long n) {
+  pdl_prologue_done();
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(logits + i);
+    *reinterpret_cast<float4*>(mask + i) = make_float4(v.x > 0.f ? 1.f : 0.f, v.y > 0.f ? 1.f : 0.f, v.z > 0.f ? 1.f : 0.f,
+                                                       v.w > 0.f ? 1.f : 0.f);
+  } else {
+    for (long long j = i; j < n; ++j) mask[j] = logits[j] > 0.f ? 1.f : 0.f;
+  }
+}
+void mask_from_logits(const float* logits, float* mask, long long n, cudaStream_t st) {
+  launch(k_mask_from_logits, (unsigned)cdiv(cdiv(n, 4LL), 256LL), 256, 0, st, logits, mask, n);
+}
+
 }  // namespace dmc

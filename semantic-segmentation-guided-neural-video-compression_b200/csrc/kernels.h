@@ -186,5 +186,11 @@ void conv1x1_to1(View in, const float* w, const float* b, float* out, long long 
 // ---------------- caller-side statistics ----------------
 void frame_stats(double* stats7, const float* x_hat, const float* x, const float* mask,
                  const float* bpp3, int B, int H, int W, cudaStream_t st);
+// uint8 camera frames (N, H0, W0, 3) + uint8 masks (N, H0, W0) or NULL -> (N, out_ch, h, w) fp32 [Y, Cb, Cr(, mask)],
+// cropped at (top, left); seg_waymo_dataset.py:26-43,56-79,231-245
+void frames_from_u8(const uint8_t* img, const uint8_t* mask, float* out, int N, int H0, int W0, int top, int left, int h,
+                    int w, int out_ch, int bgr, int mask_thr, cudaStream_t st);
+// mask = (logits > 0) as fp32 {0, 1}
+void mask_from_logits(const float* logits, float* mask, long long n, cudaStream_t st);
 
 }  // namespace dmc
