@@ -325,50 +325,6 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-// Issued from warp-uniform code by the lane whose `sel` is non-zero: no divergent branch around the
-// instruction, so the (uniform) descriptors can stay in uniform registers.
-__device__ __forceinline__ void tc_mma_pair_sel(uint32_t sel, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                                uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sel)
-      : "memory");
-}
-// Same, with the operand descriptors given as their LOW words (start address >> 4 | LBO): the high word is the same
-// constant for every K-major SWIZZLE_32B tile (s3_desc32), and stepping through a stage is then a 32-bit add per
-// operand instead of a 64-bit one (two dependent uniform-datapath instructions per descriptor on the issue path)
-__device__ __forceinline__ void tc_mma_pair_lo(uint32_t sel, uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "mov.b64 da, {%1, %6};\n\t"
-      "mov.b64 db, {%2, %6};\n\t"
-      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(sel), "r"(16u | (1u << 14) | (6u << 29))
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_mask_sel(uint32_t sel, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
-      ::"r"(bar), "h"(mask), "r"(sel)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair_sel(uint32_t sel, uint32_t bar) {
-  const uint16_t mask = 3;
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
-      ::"r"(bar), "h"(mask), "r"(sel)
-      : "memory");
-}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -644,7 +600,6 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
   const bool kPair = S.kind == S3_PAIR;
   const int kKind = kPair ? S3_PAIR : S3_PLAIN;
   const int nchunk = s3_nchunk(kKind, S.BN, x.part);
-  const int n_idx = nt * S.BN;
   const int row0 = mt * 256 + (int)x.rank * 128 + x.quad * 32;
   const uint32_t swz = (uint32_t)((lane >> 2) & 1) << 4;        // SWIZZLE_32B: 16-byte unit ^= row bit 2
   const uint32_t rowOff = (uint32_t)lane * 32u;
@@ -1242,7 +1197,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     };
 
     uint32_t tcount = 0;
-    uint32_t pend_l = 0, pend_mt = 0, pend_t = 0;   // tile whose completion is still to be published
+    uint32_t pend_t = 0;                           // tile whose completion is still to be published
     bool pending = false;
     // lane 0, after this warp's stores of the pending tile are complete: count this warp in (cta scope); the
     // publisher warp does the gpu-scope release once all epilogue warps of the CTA are in
@@ -1368,7 +1323,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
 #ifdef DMC_EPI_TIMING
       WARP_T(tcount, 2);
 #endif
-      pend_l = (uint32_t)l; pend_mt = (uint32_t)mt; pend_t = tcount;
+      pend_t = tcount;
       pending = publish_l;
       // Chains with fewer than ~3 waves of tiles per layer (the H/16 ... H/64 stages at batch 1) run into their
       // dependencies: a cluster's next tile needs rows another cluster has only just finished, and the deferred
@@ -1661,7 +1616,18 @@ int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
   static int coop = -1;
   if (coop < 0) {
     const char* v = getenv("DMC_S3_COOP");
-    coop = (v && v[0] == '0') ? 0 : 1;
+    if (v) {
+      coop = v[0] == '0' ? 0 : 1;
+    } else {
+      // Nsight Compute (and the other injection-based tools) fail a cooperative launch of a cluster kernel with
+      // "LaunchFailed" -- a sticky error that takes the context with it -- and they serialise kernels anyway, so no second
+      // persistent kernel can be co-resident with this one: under a tool the plain launch is both necessary and safe.
+      static const char* const kTools[] = {"NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_NSIGHT_INJECTION_PORT_BASE",
+                                           "NV_SANITIZER_INJECTION_PORT_BASE", "CUDA_INJECTION64_PATH"};
+      coop = 1;
+      for (const char* k : kTools)
+        if (getenv(k)) coop = 0;
+    }
   }
   if (coop) {
     attr[na].id = cudaLaunchAttributeCooperative;

@@ -157,3 +157,43 @@ def test_intra_frame_decodes_from_bytes_alone():
     d = fc.decompress(s["payload"], (1, 3, H, W), qp)
     assert torch.equal(d["dpb"]["frame"], want)
     print(f"intra: estimated bpp {float(r['bpp']):.4f}, coded {s['bits'] / (H * W):.4f} bpp")
+
+
+def test_full_size_gop_decodes_from_bytes_alone():
+    """BASELINE config 2 size (1920x1280, `performance`): intra frame + two P frames coded to bytes; a decoder that only
+    ever sees the payloads (its dpb is what IT decoded) ends with frames bit-identical to the encoder's."""
+    import time
+    H, W, qp = 1280, 1920, 32
+    frames, masks = D.clips.synthetic_clip(21, 1, 3, H, W)
+    torch.manual_seed(gc.SEED_I)
+    mi = D.DMCI().eval().cuda()
+    torch.manual_seed(gc.SEED_P)
+    mp = D.build_p_model("performance").eval().cuda()
+    mi.engine_flags = mp.engine_flags = D._capi.FLAG_KEEP_TAPS
+    ci, cp = entropy.FrameCoder(mi), entropy.FrameCoder(mp)
+    x0 = frames[:, 0].cuda()
+    with torch.no_grad():
+        r = mi(x0, qp)
+    s = ci.compress(x0, qp)
+    d = ci.decompress(s["payload"], (1, 3, H, W), qp)
+    assert torch.equal(d["dpb"]["frame"], r["dpb"]["frame"])
+    print(f"I: estimated {float(r['bpp']):.4f} bpp, coded {s['bits'] / (H * W):.4f} bpp")
+    dpb_enc, dpb_dec = r["dpb"], d["dpb"]
+    for t in (1, 2):
+        x = torch.cat([frames[:, t], masks[:, t]], 1).cuda()
+        q = mp.shift_qp(qp, D.clips.INDEX_MAP[t % 8])
+        with torch.no_grad():
+            r = mp(x, q, dpb_enc, after_i=(t == 1))
+        want_frame, want_feat = r["dpb"]["frame"].clone(), r["dpb"]["feature"].clone()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s = cp.compress(x, q)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        d = cp.decompress(s["payload"], (1, 3, H, W), q, dpb_dec, after_i=(t == 1))
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        assert torch.equal(d["dpb"]["frame"], want_frame) and torch.equal(d["dpb"]["feature"], want_feat)
+        print(f"P{t}: estimated {float(r['bpp']):.4f} bpp, coded {s['bits'] / (H * W):.4f} bpp ({len(s['payload'])} bytes); "
+              f"compress {1e3 * (t1 - t0):.1f} ms, decompress {1e3 * (t2 - t1):.1f} ms")
+        dpb_enc, dpb_dec = r["dpb"], d["dpb"]

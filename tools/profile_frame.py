@@ -13,6 +13,8 @@ B, H, W = 1, 1280, 1920
 dev = torch.device("cuda:0")
 frames, masks = D.clips.synthetic_clip(1000, B, 4, H, W)
 x = torch.cat([frames, masks], 2).to(dev) if variant != "old" else frames.to(dev)
+u8 = torch.randint(0, 256, (1, H, W, 3), dtype=torch.uint8, device=dev)
+m8 = torch.randint(0, 2, (1, H, W), dtype=torch.uint8, device=dev)
 torch.manual_seed(1)
 mp = D.build_p_model(variant).eval().to(dev)
 with torch.no_grad():
@@ -24,6 +26,7 @@ with torch.no_grad():
     e0.record()
     r = mp(x[:, 3], 36, r["dpb"], after_i=False)
     e1.record()
+    D.data.frames_from_u8(u8, m8)                 # (the dataset-side kernel, for its ncu line)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 print(f"{variant} P-frame {e0.elapsed_time(e1):.3f} ms, bpp {r['bpp'].tolist()}")

@@ -14,7 +14,7 @@ ncu -i gpurun_out/chain_dcb_$tag.ncu-rep --page raw --csv > gpurun_out/chain_dcb
 ncu -i gpurun_out/chain_dcb_$tag.ncu-rep --page source --csv > gpurun_out/chain_dcb_${tag}_src.csv 2>/dev/null
 python tools/ncu_summary.py gpurun_out/chain_dcb_${tag}_raw.csv
 python tools/stall_summary.py gpurun_out/chain_dcb_${tag}_src.csv 20 > gpurun_out/chain_dcb_${tag}_stall.txt 2>&1; head -12 gpurun_out/chain_dcb_${tag}_stall.txt
-ncu --set full --clock-control none --profile-from-start off -k "regex:k_prior_step|k_prior_finish|k_dwconv3x3_strip|k_frame_stats|k_round_z_bits" -c 6 -o gpurun_out/hbm_kernels_$tag -f python tools/profile_frame.py > gpurun_out/ncu_hbm_$tag.log 2>&1
+ncu --set full --clock-control none --profile-from-start off -k "regex:k_prior_step|k_prior_finish|k_dwconv3x3_strip|k_frame_stats|k_round_z_bits|k_frames_from_u8" -c 40 -o gpurun_out/hbm_kernels_$tag -f python tools/profile_frame.py > gpurun_out/ncu_hbm_$tag.log 2>&1
 ncu -i gpurun_out/hbm_kernels_$tag.ncu-rep --page raw --csv > gpurun_out/hbm_kernels_${tag}_raw.csv 2>/dev/null
 python tools/ncu_summary.py gpurun_out/hbm_kernels_${tag}_raw.csv
 python tools/gemm_probe.py 2 dw dcb > gpurun_out/probe_$tag.log 2>&1; cat gpurun_out/probe_$tag.log
