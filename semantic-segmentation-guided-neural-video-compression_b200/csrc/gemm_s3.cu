@@ -884,7 +884,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
   auto tab_at = [&](uint32_t t) { return __ldg(my_tab + (size_t)t * (uint32_t)units); };
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kS3EpiWarps == 16 ? 56 : 72) : "memory");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kS3EpiWarps == 16 ? 64 : 72) : "memory");
   if (warp == 0) {
     // ------------------------------------------------------------ operand producer (both CTAs)
     // (whole warp walks the loop, one elected lane issues: addresses stay in uniform registers)

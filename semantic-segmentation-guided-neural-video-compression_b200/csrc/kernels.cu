@@ -1213,37 +1213,61 @@ void frame_stats(double* stats7, const float* x_hat, const float* x, const float
 //   src/dataset/seg_waymo_dataset.py:231-245 one crop for the whole sequence, mask appended as channel 4
 // Every operation in the reference's order with IEEE roundings (the reference runs these lines on the CPU in fp32: true
 // divisions, no FMA contraction): the output is bit-identical.  4 pixels per thread: 12 + 4 bytes in, 4 x 16 bytes out.
+constexpr int kFrameRows = 8;
 __global__ void k_frames_from_u8(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, float* __restrict__ out,
                                  int H0, int W0, int top, int left, int h, int w, int out_ch, int bgr, int mask_thr) {
   pdl_prologue_done();
-  const int n = blockIdx.z, y = blockIdx.y;
+  // value / 255.0f for the 256 possible bytes, each computed once per block with the IEEE division the reference
+  // performs per element (three divisions per pixel otherwise: the kernel was bound by instruction issue, 2.7 TB/s)
+  __shared__ float lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.0f);
+  __syncthreads();
+  const int n = blockIdx.z;
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (x0 >= w) return;
   const size_t plane = (size_t)h * w;
+  // (a block walks kFrameRows image rows: the table above is built once per 8 rows x 512 pixels)
+  for (int y = blockIdx.y * kFrameRows; y < min(h, (int)(blockIdx.y + 1) * kFrameRows); ++y) {
   const uint8_t* src = img + (((size_t)n * H0 + (top + y)) * W0 + (left + x0)) * 3;
   const uint8_t* msrc = mask ? mask + ((size_t)n * H0 + (top + y)) * W0 + (left + x0) : nullptr;
   float* dst = out + (size_t)n * out_ch * plane + (size_t)y * w + x0;
   const int cnt = min(4, w - x0);
   const float Kr = 0.2126f, Kg = 0.7152f, Kb = 0.0722f;
   const float dcb = (float)(1.0 - 0.0722), dcr = (float)(1.0 - 0.2126);      // Python doubles, rounded when they meet the tensor
+  // 12 image bytes and 4 mask bytes of this thread: three / one 32-bit loads where the addresses allow it
+  uint8_t px[12], mk[4] = {0, 0, 0, 0};
+  if (cnt == 4 && ((uintptr_t)src & 3) == 0) {
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const uint32_t v = __ldg(s32 + j);
+      px[4 * j] = (uint8_t)v; px[4 * j + 1] = (uint8_t)(v >> 8); px[4 * j + 2] = (uint8_t)(v >> 16); px[4 * j + 3] = (uint8_t)(v >> 24);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) px[j] = j < 3 * cnt ? __ldg(src + j) : (uint8_t)0;
+  }
+  if (msrc) {
+    if (cnt == 4 && ((uintptr_t)msrc & 3) == 0) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(msrc));
+      mk[0] = (uint8_t)v; mk[1] = (uint8_t)(v >> 8); mk[2] = (uint8_t)(v >> 16); mk[3] = (uint8_t)(v >> 24);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mk[j] = j < cnt ? __ldg(msrc + j) : (uint8_t)0;
+    }
+  }
   float Y[4], Cb[4], Cr[4], M[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (i < cnt) {
-      const float c0 = __fdiv_rn((float)__ldg(src + 3 * i), 255.0f);
-      const float c1 = __fdiv_rn((float)__ldg(src + 3 * i + 1), 255.0f);
-      const float c2 = __fdiv_rn((float)__ldg(src + 3 * i + 2), 255.0f);
-      const float r = bgr ? c2 : c0, g = c1, b = bgr ? c0 : c2;
-      const float yy = __fadd_rn(__fadd_rn(__fmul_rn(Kr, r), __fmul_rn(Kg, g)), __fmul_rn(Kb, b));
-      const float cb = __fadd_rn(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(b, yy)), dcb), 0.5f);
-      const float cr = __fadd_rn(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(r, yy)), dcr), 0.5f);
-      Y[i] = fminf(fmaxf(yy, 0.0f), 1.0f);
-      Cb[i] = fminf(fmaxf(cb, 0.0f), 1.0f);
-      Cr[i] = fminf(fmaxf(cr, 0.0f), 1.0f);
-      M[i] = (msrc && (int)__ldg(msrc + i) > mask_thr) ? 1.0f : 0.0f;
-    } else {
-      Y[i] = Cb[i] = Cr[i] = M[i] = 0.0f;
-    }
+    const float c0 = lut[px[3 * i]], c1 = lut[px[3 * i + 1]], c2 = lut[px[3 * i + 2]];
+    const float r = bgr ? c2 : c0, g = c1, b = bgr ? c0 : c2;
+    const float yy = __fadd_rn(__fadd_rn(__fmul_rn(Kr, r), __fmul_rn(Kg, g)), __fmul_rn(Kb, b));
+    const float cb = __fadd_rn(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(b, yy)), dcb), 0.5f);
+    const float cr = __fadd_rn(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(r, yy)), dcr), 0.5f);
+    Y[i] = fminf(fmaxf(yy, 0.0f), 1.0f);
+    Cb[i] = fminf(fmaxf(cb, 0.0f), 1.0f);
+    Cr[i] = fminf(fmaxf(cr, 0.0f), 1.0f);
+    M[i] = (int)mk[i] > mask_thr ? 1.0f : 0.0f;
   }
   const bool vec = cnt == 4 && (w & 3) == 0;                 // (then every row start is 16-byte aligned)
   float* planes[4] = {dst, dst + plane, dst + 2 * plane, dst + 3 * plane};
@@ -1257,10 +1281,11 @@ __global__ void k_frames_from_u8(const uint8_t* __restrict__ img, const uint8_t*
       for (int i = 0; i < cnt; ++i) planes[c][i] = vals[c][i];
     }
   }
+  }
 }
 void frames_from_u8(const uint8_t* img, const uint8_t* mask, float* out, int N, int H0, int W0, int top, int left, int h,
                     int w, int out_ch, int bgr, int mask_thr, cudaStream_t st) {
-  dim3 grid((unsigned)cdiv(cdiv(w, 4), 128), (unsigned)h, (unsigned)N);
+  dim3 grid((unsigned)cdiv(cdiv(w, 4), 128), (unsigned)cdiv(h, kFrameRows), (unsigned)N);
   launch(k_frames_from_u8, grid, 128, 0, st, img, mask, out, H0, W0, top, left, h, w, out_ch, bgr, mask_thr);
 }
 
