@@ -891,6 +891,11 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     int s = 0;
     uint32_t ph = 0, tcount = 0;
     const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(p.epoch_ctr) + 1u;
+    // what does not change from stage to stage is worked out once: the issuing lane, the leader's barrier of stage 0 as
+    // a cluster address (the others follow at 8-byte steps), whether this launch runs the plain path at all
+    const bool sel = elect_one();
+    const uint32_t lbar0 = mapa(bar_full(0), leaderRank);
+    const bool plain_path = !p.cl4 && !(p.dbg & 1);
     // (the table entry of the next tile is fetched a tile ahead: its ~700 clocks of global latency sat on the
     // critical path of every tile in this warp and in the MMA warp)
     uint32_t e_nxt = my_tiles ? tab_at(0) : 0u;
@@ -921,6 +926,43 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
       const uint32_t tx = (S.nterms == 1 ? (uint32_t)kblk : 4u) * (kS3APlane + ((p.dbg & 32) ? 0u : wRows * (kS3BK * 2)));
       const int m_idx = mt * 256 + (int)rank * 128;
       const int n_idx = nt * S.BN + (int)(rank * wRows);
+      if (plain_path) {
+        // The lean loop: per stage one barrier test, (leader) one expect_tx, one TMA issue -- nothing read from the
+        // kernel parameters, no branch on the launch's modes.  The general loop below spent ~350 clocks per stage on
+        // exactly that (indexed constant loads of the layer record, mode tests, mapa, elect and reconvergence per
+        // stage): with NO loads and NO MMAs the kernel still needed 3 900 clocks per tile (tools/epi_probe.py,
+        // "hand-over only"), the floor under everything else.
+        const CUtensorMap* tmA = &S.tmA;
+        const int k_blocks = S.k_blocks, m16 = m_idx >> 4;
+        const CUtensorMap* tmWl = (!kS3SplitProducer && !(p.dbg & 32)) ? &S.tmW : nullptr;
+        const int n16 = n_idx >> 4;
+#ifdef DMC_EPI_TIMING
+        long long tp_wait = 0, tp_issue = 0;
+#endif
+        for (int kb = 0; kb < k_blocks; ++kb) {
+#ifdef DMC_EPI_TIMING
+          const long long tp0 = clock64();
+#endif
+          mbar_wait(bar_empty(s), ph ^ 1, p.err, 1);
+#ifdef DMC_EPI_TIMING
+          const long long tp1 = clock64();
+          tp_wait += tp1 - tp0;
+#endif
+          if (sel) {
+            const uint32_t sa = base + s * stageBytes;
+            if (leader) mbar_expect_tx(bar_full(s), tx);
+            tma_load_pair(sa, tmA, m16, kb * kblk, lbar0 + 8u * s);
+            if (tmWl) tma_load_pair_w(sa + kPlanes * kS3APlane, tmWl, n16, kb * kblk, lbar0 + 8u * s);
+          }
+#ifdef DMC_EPI_TIMING
+          tp_issue += clock64() - tp1;
+#endif
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        TILE_T(tcount, 11, tp_wait);
+        TILE_T(tcount, 12, tp_issue);
+        continue;
+      }
 #ifdef DMC_EPI_TIMING
       long long tp_wait = 0, tp_issue = 0;
 #endif
@@ -1100,6 +1142,8 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     if (!(p.dbg & (1 | 32))) {
       int s = 0;
       uint32_t ph = 0, tcount = 0;
+      const bool sel = elect_one();
+      const uint32_t lbar0 = mapa(bar_full(0), leaderRank);
       uint32_t e_nxt = my_tiles ? tab_at(0) : 0u;
       for (; tcount < my_tiles; ++tcount) {
         const uint32_t e = e_nxt;
@@ -1111,9 +1155,7 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
         const CUtensorMap* tmW = &S.tmW;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(bar_empty(s), ph ^ 1, p.err, 1);
-          const uint32_t sw = base + s * stageBytes + kPlanes * kS3APlane;
-          if (elect_one()) tma_load_pair_w(sw, tmW, n16, kb * kblk, mapa(bar_full(s), leaderRank));
-          __syncwarp();
+          if (sel) tma_load_pair_w(base + s * stageBytes + kPlanes * kS3APlane, tmW, n16, kb * kblk, lbar0 + 8u * s);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
