@@ -1449,6 +1449,7 @@ int64_t dmc_kernel_launches(void) { return (int64_t)launch_count(); }
 int dmc_profile_enable(dmc_engine* e, int on) {
   if (!e) return DMC_E_INVALID;
   e->profile = on != 0;
+  gemm_s3_set_plain_launch(on != 0);
   return DMC_OK;
 }
 int dmc_profile_read(dmc_engine* e, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops,

@@ -1406,6 +1406,13 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
 // ------------------------------------------------------------------ host side
 static int g_s3_dbg = 0;
 void gemm_s3_set_debug(int mask) { g_s3_dbg = mask; }
+// Measurement pass of bench.py (dmc_profile_enable): an event pair around EVERY contraction launch.  The events break the
+// back-to-back pipelining of the launches, and a cooperative launch then shows its full launch latency (~4 us per
+// launch in a loop of single launches, none inside a frame: DepthConvBlock-256 141.8 vs 141.6 us, bench 209.2 vs 210.1
+// P-frames/s with DMC_S3_COOP=1 / 0) -- the per-launch times would overstate the kernel's share of the frame (92 %
+// against 81.5 % in the ncu launch list).  The pass therefore launches plainly; nothing else runs next to it.
+static int g_s3_plain_launch = 0;
+void gemm_s3_set_plain_launch(int on) { g_s3_plain_launch = on; }
 
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit) {
   if (!w.tmap_s3 || !w.tmap_s3_hi || e.do_clamp) return false;
@@ -1671,7 +1678,8 @@ int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
         if (getenv(k)) coop = 0;
     }
   }
-  if (coop) {
+  const bool use_coop = coop && !g_s3_plain_launch;
+  if (use_coop) {
     attr[na].id = cudaLaunchAttributeCooperative;
     attr[na].val.cooperative = 1;
     ++na;
@@ -1684,7 +1692,7 @@ int s3_chain_launch(S3Chain* c, int qp, cudaStream_t st) {
   cfg.numAttrs = na;
   note_launch();
   cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_s3_chain, c->p);
-  if (err != cudaSuccess && coop) {            // cooperative + cluster launch refused: plain launch from now on
+  if (err != cudaSuccess && use_coop) {        // cooperative + cluster launch refused: plain launch from now on
     cudaGetLastError();
     coop = 0;
     cfg.numAttrs = 1;

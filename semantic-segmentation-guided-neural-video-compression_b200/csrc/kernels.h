@@ -114,6 +114,7 @@ int make_tmap_s3_rows(void* tmap_out, View v, int cols, long long M);      // bo
 int make_tmap_f32_rows(void* tmap_out, float* base, int cols, int ld, long long M);   // fp32 rows, box 16 x 32
 bool gemm_s3_supports(const GemmW& w, const Epi& e, int nsplit);
 void gemm_s3_set_debug(int mask);
+void gemm_s3_set_plain_launch(int on);   // measurement passes: no cooperative launch attribute (gemm_s3.cu)
 // A chain = consecutive 1x1 layers over the same rows, run by ONE persistent launch with tile-level
 // dependencies (see gemm_s3.cu).  A single contraction is a chain of one.
 struct S3StageDesc {

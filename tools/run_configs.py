@@ -43,7 +43,8 @@ def run(cfg):
         with torch.no_grad():
             i_res = mi(fr[:, 0], QP)
             if clip == 0:        # warm-up: builds the engines
-                D.clips.run_gop(mi, mp, variant, fr[:, :3], mk[:, :3], QP, None, feedback, i_result=i_res)
+                # (four frames: every qp of the schedule -- a new qp means a new CUDA graph, captured on first use)
+                D.clips.run_gop(mi, mp, variant, fr[:, :4], mk[:, :4], QP, None, feedback, i_result=i_res)
             outs, ms = timed(lambda: D.clips.run_gop(mi, mp, variant, fr, mk, QP, stats, feedback, i_result=i_res))
         total_ms += ms
         pframes += (frames_n - 1) * batch
