@@ -286,6 +286,9 @@ __device__ __forceinline__ void tma_store_wait_read0() {   // every bulk store h
 __device__ __forceinline__ void tma_store_wait_read1() {   // at most one store still reading shared memory
   asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_wait_read2() {   // at most two stores still reading shared memory
+  asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_1() {       // all but the newest bulk store are complete
   asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
 }
@@ -762,7 +765,7 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
     if (!(kRes || kRes2)) {
       // this chunk's staging tile was last read by the store of chunk c-2: all but the newest store have read their data
       if (lane == 0) {
-        if (kS3Ring >= 3) tma_store_wait_read1(); else tma_store_wait_read1();
+        if (kS3Ring >= 3) tma_store_wait_read2(); else tma_store_wait_read1();
       }
       __syncwarp();
     }
