@@ -637,8 +637,10 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
 #endif
     EPI_T(1);
   }
-  // ---- phase 2: chunk by chunk (from registers, or loading as it goes)
-#pragma unroll
+  // ---- phase 2: chunk by chunk (from registers, or loading as it goes).  Unrolled only when the accumulators sit in
+  // registers (constant indices): a second copy of this body raised the kernel's instruction-fetch stalls from 4 % to
+  // 10 % of its samples (stall_no_inst, profiles/chain_dcb_r02b_stall_summary.txt).
+#pragma unroll(kS3EarlyRelease ? 2 : 1)
   for (int c = 0; c < 2; ++c) {
     if (c >= nchunk) break;
     const int acol = s3_acc_col(kKind, S.BN, x.part, c);         // accumulator column of this chunk
@@ -721,6 +723,8 @@ __device__ __forceinline__ void s3_epilogue_tile(const StageRegs& S, EpiCtx& x, 
           for (int i = 0; i < kS3ChunkCols; ++i) v[i] = w[i];
         }
       };
+      // (three inlined copies of the activation code.  ONE copy in a two-trip loop for the value / partner halves was
+      // tried for the instruction cache's sake: chunk-add epilogue 53.7 -> 59.2 us, the loop-carried v[] costs more.)
       if (kPair) {
         act(ua[0], ub[0], acol, false);
         act(ua[kS3EarlyRelease ? 1 : 0], ub[kS3EarlyRelease ? 1 : 0], acol + 32, true);
