@@ -114,6 +114,30 @@ def test_frame_symbols_round_trip_and_actual_bits(variant):
     assert math.isfinite(actual_bpp) and actual_bpp > 0
 
 
+@pytest.mark.parametrize("variant,H,W,B", [("old", 80, 112, 1), ("fast", 80, 112, 2), ("mask_prop", 144, 208, 1)])
+def test_ragged_and_batched_frames_decode_from_bytes_alone(variant, H, W, B):
+    """Sizes whose latent (H/16 x W/16) is not a multiple of 4: y is replicate-padded for the hyper path and the
+    hyper-decoder output cropped back (models/common_model.py:68-72) -- on both sides of the split; and a batch of 2."""
+    qp = 27
+    frames, masks = D.clips.synthetic_clip(17, B, 3, H, W)
+    torch.manual_seed(gc.SEED_P)
+    m = D.build_p_model(variant).eval().cuda()
+    m.engine_flags = D._capi.FLAG_KEEP_TAPS
+    fc = entropy.FrameCoder(m)
+    dpb_enc = {"frame": frames[:, 0].cuda(), "feature": None}
+    dpb_dec = {"frame": frames[:, 0].cuda(), "feature": None}
+    for t in (1, 2):
+        x = frames[:, t].cuda() if variant == "old" else torch.cat([frames[:, t], masks[:, t]], 1).cuda()
+        with torch.no_grad():
+            r = m(x, qp, dpb_enc, after_i=(t == 1))
+        want_frame, want_feat = r["dpb"]["frame"].clone(), r["dpb"]["feature"].clone()
+        s = fc.compress(x, qp)
+        assert s["z_shape"][2:] == ((H // 16 + 3) // 4, (W // 16 + 3) // 4)
+        d = fc.decompress(s["payload"], (B, 3, H, W), qp, dpb_dec, after_i=(t == 1))
+        assert torch.equal(d["dpb"]["frame"], want_frame) and torch.equal(d["dpb"]["feature"], want_feat)
+        dpb_enc, dpb_dec = r["dpb"], d["dpb"]
+
+
 @pytest.mark.parametrize("variant", ["old", "performance", "fast", "mask_prop"])
 def test_p_frames_decode_from_bytes_alone(variant):
     """The decoder half (dmc_decode_* + the range decoder between its phases) rebuilds x_hat and the feature of both
