@@ -13,15 +13,23 @@
 // (grid <= #SM), so waits cannot deadlock; they are bounded anyway and trap instead of hanging.
 //
 // Inside a tile (what differs from the general kernel in gemm_umma.cu, which stays as the path for
-// pixel-shuffle stores, two residuals and odd shapes):
-//   * a cluster of two CTAs works on one 256 x BN tile with cta_group::2 MMAs: each CTA loads its own
-//     128 rows of A and HALF of the W tile (L2 -> SM operand traffic per MMA cycle 64 -> 48 B/clk);
-//   * K is staged in blocks of 32 (two 16-wide SWIZZLE_32B k blocks): a stage is 24 KB, up to eight are in flight;
-//   * MMA / TMA issue runs in warp-uniform code with one elected lane, so descriptors live in uniform
-//     registers (the per-thread version spent ~12 instructions and a branch per MMA);
-//   * the epilogue is specialised per layer kind and moves no global memory itself: residual tiles
-//     arrive by TMA (one 2-plane box per warp and 16-column chunk, prefetched one chunk ahead) and
-//     results leave by TMA store from a swizzled staging tile (ring of three per warp).
+// pixel-shuffle stores and odd shapes):
+//   * a cluster of two CTAs works on one 256 x BN tile with cta_group::2 MMAs: each CTA loads its own 128 rows of A and
+//     HALF of the W tile (L2 -> SM operand traffic per MMA cycle 64 -> 48 B/clk);
+//   * K is staged in blocks of 32 (two 16-wide SWIZZLE_32B k blocks): a stage is 24 KB, six are in flight;
+//   * warp roles: 0 issues the A loads, 3 the W loads (a TMA issue costs its warp a few hundred clocks: one warp doing
+//     both bound the operand supply), 1 issues the MMAs -- two stages per trip through its loop, descriptors as 32-bit
+//     words, because the tensor pipe queues hardly anything and idles through whatever else that warp does --, 2
+//     publishes finished tiles (the gpu-scope release), 4..11 are the epilogue;
+//   * every issuing loop runs warp-uniformly with one elected lane, so descriptors and addresses live in uniform
+//     registers, and carries nothing that ptxas would spill: fence.proxy.async.global (every publication) and
+//     ld.acquire.gpu (every dependency check) invalidate the whole L1, a spilled loop counter then costs an L2 round trip
+//     per tile;
+//   * the epilogue is one body with run-time layer kinds (its code streams through the instruction cache of eight
+//     warps: a second unrolled copy cost 3 % of a DepthConvBlock) and moves no global memory itself: residual tiles
+//     arrive by TMA (one 2-plane box per warp and 32-column chunk, prefetched one chunk ahead), results leave by TMA
+//     store from a swizzled staging tile (ring of two per warp), the bias comes through shared memory.
+// DESIGN.md 3.1 has the measurements behind each of these.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
