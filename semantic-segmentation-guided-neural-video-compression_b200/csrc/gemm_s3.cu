@@ -1260,7 +1260,9 @@ k_gemm_s3_chain(const __grid_constant__ S3ChainParams p) {
     // publisher warp does the gpu-scope release once all epilogue warps of the CTA are in
     auto publish = [&]() {
       const uint32_t cnt = warpsDone + 4u * (pend_t & 7u);
+#ifndef DMC_S3_NO_EPI_PUBLISH_FENCE
       fence_proxy_async_global();
+#endif
       asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(cnt), "r"(1u) : "memory");
     };
     // table entries are fetched TWO tiles ahead: the entry of the next tile is needed at the top of this one (is it
