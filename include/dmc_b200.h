@@ -178,6 +178,31 @@ int dmc_op_depth_conv_block(const float* x, const float* const* weights12, const
 int dmc_op_gaussian_bits(const float* sym, const float* sigma, float* bits, int64_t n, int formula,
                          void* stream);
 
+/* ---- training mode (STE / noise quantisation, autograd through the fused DepthConvBlock) ----
+ * What trainer_seg_video_model.py:983-1206 needs from the blocks when p_frame_model.train() is on.  A handle owns the
+ * buffers, packed weights and launch programs of ONE DepthConvBlock geometry (layers.py:43-79); forward is the frame
+ * engine's block, backward recomputes the block's intermediates from x (nothing else is kept between the passes) and
+ * returns the gradients torch.autograd would: of x, of the twelve parameters (same order and shapes as weights12;
+ * NULL entries are skipped) and of quant_step.  terms: 3 = fp32-grade split product, 1 = plain fp16 operands.
+ * The gradient arithmetic runs on fp16 split planes: pre-scale grad_out so that max |g| is around 2^8 and un-scale the
+ * results (training.py does).  All tensors NCHW fp32 on the device, calls are asynchronous on `stream`. */
+typedef struct dmc_dcb_train dmc_dcb_train;
+int dmc_dcb_train_create(int batch, int height, int width, int cin, int cout, int force_adaptor, int shortcut,
+                         int has_quant_step, int terms, dmc_dcb_train** out);
+void dmc_dcb_train_destroy(dmc_dcb_train* t);
+const char* dmc_dcb_train_last_error(const dmc_dcb_train* t);
+int dmc_dcb_train_forward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
+                          float* out, void* stream);
+int dmc_dcb_train_backward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
+                           const float* grad_out, float* grad_x, float* const* grad_weights12, float* grad_quant_step,
+                           void* stream);
+/* AdaptiveQuant in training mode (layers/inference.py:16-27).  mode 0 "ste": out = round(x) (the straight-through
+ * gradient is the identity); mode 1 "noise": out = x + noise with noise ~ U(-half_bin, half_bin) drawn by the caller. */
+int dmc_op_quant_train(const float* x, const float* noise, float* out, int64_t n, int mode, void* stream);
+/* Gradient of dmc_op_gaussian_bits with respect to the symbols and sigma (same formula numbers). */
+int dmc_op_gaussian_bits_backward(const float* sym, const float* sigma, const float* grad_bits, float* grad_sym,
+                                  float* grad_sigma, int64_t n, int formula, void* stream);
+
 /* ---- measurement support (bench.py) ---- */
 /* number of kernels this library has launched in this process so far */
 int64_t dmc_kernel_launches(void);

@@ -8,7 +8,7 @@ C ABI in include/dmc_b200.h.  The directory name is not an identifier; import it
 """
 from .modules import (DMCConfig, DMCI, DMC_fast, DMC_mask_prop, DMC_old, DMC_performance, NonFiniteError,
                       P_MODELS, build_p_model)
-from . import _capi, bitstream, build, clips, data, entropy, modules  # noqa: F401
+from . import _capi, bitstream, build, clips, data, entropy, modules, training  # noqa: F401
 
 __all__ = ["DMCConfig", "DMCI", "DMC_old", "DMC_performance", "DMC_fast", "DMC_mask_prop", "P_MODELS",
            "build_p_model", "NonFiniteError"]

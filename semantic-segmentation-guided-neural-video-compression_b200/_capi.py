@@ -44,6 +44,15 @@ SIGNATURES = {
     "dmc_op_depth_conv_block": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p] +
                                 [c_int] * 8 + [c_void_p]),
     "dmc_op_gaussian_bits": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "dmc_dcb_train_create": (c_int, [c_int] * 9 + [POINTER(c_void_p)]),
+    "dmc_dcb_train_destroy": (None, [c_void_p]),
+    "dmc_dcb_train_last_error": (c_char_p, [c_void_p]),
+    "dmc_dcb_train_forward": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p]),
+    "dmc_dcb_train_backward": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p,
+                                       POINTER(c_void_p), c_void_p, c_void_p]),
+    "dmc_op_quant_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "dmc_op_gaussian_bits_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                              c_void_p]),
     "dmc_kernel_launches": (c_int64, []),
     "dmc_profile_enable": (c_int, [c_void_p, c_int]),
     "dmc_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), POINTER(c_double),

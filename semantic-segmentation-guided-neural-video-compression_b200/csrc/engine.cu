@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <functional>
 #include <map>
 #include <memory>
@@ -1575,6 +1576,292 @@ extern "C" int dmc_op_gaussian_bits(const float* sym, const float* sigma, float*
                                     void* stream) {
   if (!sym || !sigma || !bits || n < 0) return DMC_E_INVALID;
   gaussian_bits(sym, sigma, bits, n, formula, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
+}
+
+// ---------------------------------------------------------------- training mode: DepthConvBlock forward / backward
+// SURVEY 8f rank 2 ("autograd through fused DCB").  The forward program is the block of the frame engine (dcb():
+// chain launches + the depthwise kernel); the backward program recomputes the block's intermediates from x -- only x
+// is kept between the two passes -- and walks the block in reverse:
+//   data gradients  = contractions with the transposed weights on the same tcgen05 chain kernel (3-term product),
+//                     residual gradients folded into their epilogues;
+//   weight gradients = k_wgrad_s3 over the pixel axis (train.cu), bias gradients = column sums;
+//   WSiLU' / chunk-add' / depthwise gradients = the elementwise kernels of train.cu.
+struct dmc_dcb_train {
+  dmc_engine e;
+  std::vector<dmc_engine::Op> prog_bwd;
+  int cin = 0, cout = 0, shortcut = 0, has_qs = 0, terms = 3;
+  DCB* blk = nullptr;
+  Conv *T_ad = nullptr, *T_dc0 = nullptr, *T_dc3 = nullptr, *T_ffn0 = nullptr, *T_ffn2 = nullptr, *P_ffn0 = nullptr;
+  float *tmpT = nullptr, *w9c_flip = nullptr, *zero_bias = nullptr, *qs_table = nullptr, *part = nullptr;
+  size_t part_floats = 0;
+  // caller tensors of the current call (read by the launch closures)
+  const float *x = nullptr, *gout = nullptr;
+  float *out = nullptr, *gx = nullptr, *gqs = nullptr;
+  float* gw[12] = {};
+};
+
+namespace {
+const char* const kDcbNames[6] = {"b.adaptor", "b.dc.0", "b.dc.2", "b.dc.3", "b.ffn.0", "b.ffn.2"};
+
+void dcb_train_load(dmc_dcb_train& t, const float* const* w12, const float* quant_step, bool backward, cudaStream_t st) {
+  dmc_engine& e = t.e;
+  if (!w12) fail("null weight list");
+  if (t.blk->adaptor && (!w12[0] || !w12[1])) fail("adaptor weights required (cin != cout or force_adaptor)");
+  for (int i = 0; i < 6; ++i) {
+    if (i == 0 && !t.blk->adaptor) continue;
+    if (!w12[2 * i] || !w12[2 * i + 1]) fail("missing weight %s", kDcbNames[i]);
+    set_slot(e, std::string(kDcbNames[i]) + ".weight", w12[2 * i], st);
+    set_slot(e, std::string(kDcbNames[i]) + ".bias", w12[2 * i + 1], st);
+  }
+  if (t.has_qs) {
+    if (!quant_step) fail("quant_step required: the block was created with has_quant_step");
+    CUDA_OK(cudaMemcpyAsync(t.qs_table, quant_step, sizeof(float) * t.cout, cudaMemcpyDeviceToDevice, st));
+  } else if (quant_step) {
+    fail("quant_step given but the block was created without has_quant_step");
+  }
+  if (!backward) return;
+  const int C = t.cout;
+  set_slot(e, "P.ffn0.weight", w12[8], st);
+  set_slot(e, "P.ffn0.bias", w12[9], st);
+  struct TW { Conv* c; const float* w; int rows, cols; const char* key; };
+  const TW tw[5] = {{t.T_ad, w12[0], C, t.cin, "T.ad"}, {t.T_dc0, w12[2], C, C, "T.dc0"}, {t.T_dc3, w12[6], C, C, "T.dc3"},
+                    {t.T_ffn0, w12[8], 4 * C, C, "T.ffn0"}, {t.T_ffn2, w12[10], C, 2 * C, "T.ffn2"}};
+  for (const TW& w : tw) {
+    if (!w.c) continue;
+    transpose_f32(w.w, t.tmpT, w.rows, w.cols, st);
+    set_slot(e, std::string(w.key) + ".weight", t.tmpT, st);
+    pack_gemm_bias(nullptr, w.c->cout, w.c->g, st);
+  }
+  flip_dw_weight(t.blk->dw->w9c, t.w9c_flip, C, st);
+}
+}  // namespace
+
+extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, int cout, int force_adaptor, int shortcut,
+                                    int has_quant_step, int terms, dmc_dcb_train** out) {
+  if (!out) return DMC_E_INVALID;
+  *out = nullptr;
+  dmc_dcb_train* t = nullptr;
+  int rc = guarded(nullptr, [&] {
+    if (batch < 1 || height < 1 || width < 1) fail("dmc_dcb_train_create: bad geometry");
+    if (cin < 16 || cout < 32 || cin % 16 || cout % 16) fail("dmc_dcb_train_create: channels must be multiples of 16 (cin >= 16, cout >= 32)");
+    if (terms != 1 && terms != 3) fail("dmc_dcb_train_create: terms must be 1 or 3");
+    t = new dmc_dcb_train();
+    dmc_engine& e = t->e;
+    CUDA_OK(cudaGetDevice(&e.device));
+    e.variant = -1; e.B = batch; e.H = height; e.W = width;
+    e.graphs_on = false;
+    t->cin = cin; t->cout = cout; t->shortcut = shortcut != 0; t->has_qs = has_quant_step != 0; t->terms = terms;
+    const int C = cout, B = batch, H = height, W = width;
+    const long long M = (long long)B * H * W;
+    t->blk = e.add_dcb("b", cin, cout, force_adaptor != 0);
+    const bool ad = t->blk->adaptor != nullptr;
+    t->P_ffn0 = e.add_conv("P.ffn0", C, 4 * C, 1, 1, 0);
+    if (ad) t->T_ad = e.add_conv("T.ad", C, cin, 1, 1, 0);
+    t->T_dc0 = e.add_conv("T.dc0", C, C, 1, 1, 0);
+    t->T_dc3 = e.add_conv("T.dc3", C, C, 1, 1, 0);
+    t->T_ffn0 = e.add_conv("T.ffn0", 4 * C, C, 1, 1, 0);
+    t->T_ffn2 = e.add_conv("T.ffn2", C, 2 * C, 1, 1, 0);
+    t->tmpT = e.new_f32((size_t)4 * C * std::max(C, cin));
+    t->w9c_flip = e.new_f32((size_t)9 * C);
+    t->zero_bias = e.new_f32((size_t)4 * C);
+    CUDA_OK(cudaMemset(t->zero_bias, 0, sizeof(float) * 4 * C));
+    t->qs_table = e.new_f32(C);
+    // partial sums: the largest of the weight-gradient splits, the column sums and the depthwise partial rows
+    const int max_parts = 2 * num_sms();
+    size_t pf = (size_t)max_parts * 4 * C;
+    pf = std::max(pf, (size_t)max_parts * C * 10);
+    const int shapes[5][2] = {{C, cin}, {C, C}, {C, C}, {4 * C, C}, {C, 2 * C}};
+    for (auto& sh : shapes) pf = std::max(pf, (size_t)wgrad_splits(M, sh[0], sh[1]) * sh[0] * sh[1]);
+    t->part = e.new_f32(pf);
+    t->part_floats = pf;
+
+    // ---- forward program
+    dmc_dcb_train* self = t;
+    e.prog = &e.prog_common;
+    {
+      Act fin = e.new_act(B, H, W, cin), fout = e.new_act(B, H, W, C);
+      e.op([self, fin, B, H, W, cin](cudaStream_t st) { nchw_to_s3(self->x, fin.v, B, cin, H, W, st); });
+      e.cur.qp = 0;
+      e.dcb(t->blk, fin, fout, t->shortcut, t->has_qs ? t->qs_table : nullptr, terms);
+      e.op([self, fout, B, H, W, C](cudaStream_t st) { s3_to_nchw(fout.v, self->out, B, C, H, W, st); });
+      e.flush_chain();
+    }
+
+    // ---- backward program
+    e.set_prog(&t->prog_bwd);
+    Act xs = e.new_act(B, H, W, cin);
+    Act a = ad ? e.new_act(B, H, W, C) : xs;
+    float* t0 = e.new_f32((size_t)M * C);
+    float* t1 = e.new_f32((size_t)M * C);
+    float* u0 = e.new_f32((size_t)M * 4 * C);
+    Act t2 = e.new_act(B, H, W, C), o1 = e.new_act(B, H, W, C), v = e.new_act(B, H, W, 2 * C);
+    Act g = e.new_act(B, H, W, C), gv = e.new_act(B, H, W, 2 * C), gu = e.new_act(B, H, W, 4 * C);
+    Act go1 = e.new_act(B, H, W, C), gt2 = e.new_act(B, H, W, C), gt1 = e.new_act(B, H, W, C), gt0 = e.new_act(B, H, W, C);
+    Act ga = e.new_act(B, H, W, C);
+    EpiSpec plain;
+    plain.nsplit = terms;
+    // recompute (the forward pass keeps nothing but x)
+    e.op([self, xs, B, H, W, cin](cudaStream_t st) { nchw_to_s3(self->x, xs.v, B, cin, H, W, st); });
+    if (ad) e.gemm(xs, t->blk->adaptor, &a, plain);
+    {
+      EpiSpec s = plain;
+      s.out_f32 = t0; s.ld_f32 = C;
+      e.gemm(a, t->blk->dc0, nullptr, s);
+    }
+    DW* dw = t->blk->dw;
+    e.op([t0, t1, M, C](cudaStream_t st) { wsilu_rows(t0, t1, M * C, st); });
+    e.op([t1, C, t2, dw](cudaStream_t st) { dwconv3x3_f32(t1, C, dw->w9c, dw->bias, t2.v, t2.B, t2.H, t2.W, st); });
+    {
+      EpiSpec s = plain;
+      s.res1 = &a;
+      e.gemm(t2, t->blk->dc3, &o1, s);
+    }
+    {
+      EpiSpec s = plain;
+      s.out_f32 = u0; s.ld_f32 = 4 * C;
+      e.gemm(o1, t->P_ffn0, nullptr, s);
+    }
+    e.op([u0, v, M, C](cudaStream_t st) { chunkadd_fwd(u0, 4 * C, v.v, M, st); });
+    Act gcur = g;
+    e.op([self, g, B, H, W, C](cudaStream_t st) { nchw_to_s3(self->gout, g.v, B, C, H, W, st); });
+    if (t->has_qs) {
+      Act outpre = e.new_act(B, H, W, C), g2 = e.new_act(B, H, W, C);
+      EpiSpec s = plain;
+      s.res1 = &o1;
+      if (t->shortcut) s.res2 = &a;
+      e.gemm(v, t->blk->ffn2, &outpre, s);
+      e.op([self, g, outpre, g2, M, C, max_parts](cudaStream_t st) {
+        if (self->gqs) {
+          int S = colsum_s3(g.v, &outpre.v, M, self->part, C, max_parts, st);
+          reduce_partials(self->part, C, S, self->gqs, C, nullptr, 1.0f, st);
+        }
+        scale_cols(g.v, self->qs_table, g2.v, M, st);
+      });
+      gcur = g2;
+    }
+    // one weight + bias gradient: G [M, N] against the layer input X [M, K]
+    auto wgrad = [&](const Act& G, const Act& X, int iw) {
+      const int terms_ = terms;
+      e.op([self, G, X, M, iw, terms_, max_parts](cudaStream_t st) {
+        const int N = G.v.C, K = X.v.C;
+        if (self->gw[iw]) {
+          int S = wgrad_s3(G.v, X.v, M, terms_, self->part, st);
+          reduce_partials(self->part, (long long)N * K, S, self->gw[iw], (long long)N * K, nullptr, 1.0f, st);
+        }
+        if (self->gw[iw + 1]) {
+          int S = colsum_s3(G.v, nullptr, M, self->part, N, max_parts, st);
+          reduce_partials(self->part, N, S, self->gw[iw + 1], N, nullptr, 1.0f, st);
+        }
+      });
+    };
+    // ffn.2
+    wgrad(gcur, v, 10);
+    e.gemm(gcur, t->T_ffn2, &gv, plain);
+    e.op([gv, u0, gu, M, C](cudaStream_t st) { chunkadd_bwd(gv.v, u0, 4 * C, gu.v, M, st); });
+    // ffn.0 (+ the residual around the ffn)
+    wgrad(gu, o1, 8);
+    {
+      EpiSpec s = plain;
+      s.res1 = &gcur;
+      e.gemm(gu, t->T_ffn0, &go1, s);
+    }
+    // dc.3
+    wgrad(go1, t2, 6);
+    e.gemm(go1, t->T_dc3, &gt2, plain);
+    // depthwise 3x3
+    e.op([self, gt2, gt1, t1, C, B, H, W, max_parts](cudaStream_t st) {
+      dwconv3x3(gt2.v, self->w9c_flip, self->zero_bias, gt1.v, B, H, W, st);
+      if (self->gw[4] || self->gw[5]) {
+        int S = dw_wgrad(gt2.v, t1, C, B, H, W, self->part, C * 10, max_parts, st);
+        reduce_dw(self->part, C * 10, S, self->gw[4], self->gw[5], C, 1.0f, st);
+      }
+    });
+    e.op([gt1, t0, gt0, M, C](cudaStream_t st) { wsilu_bwd(gt1.v, t0, C, gt0.v, M, st); });
+    // dc.0 (+ the residual around dc, + the shortcut)
+    wgrad(gt0, a, 2);
+    {
+      EpiSpec s = plain;
+      s.res1 = &go1;
+      if (t->shortcut) s.res2 = &gcur;
+      e.gemm(gt0, t->T_dc0, &ga, s);
+    }
+    if (ad) {
+      Act gxs = e.new_act(B, H, W, cin);
+      wgrad(ga, xs, 0);
+      e.gemm(ga, t->T_ad, &gxs, plain);
+      e.op([self, gxs, B, H, W, cin](cudaStream_t st) { if (self->gx) s3_to_nchw(gxs.v, self->gx, B, cin, H, W, st); });
+    } else {
+      e.op([self, ga, B, H, W, C](cudaStream_t st) { if (self->gx) s3_to_nchw(ga.v, self->gx, B, C, H, W, st); });
+    }
+    e.flush_chain();
+    e.prog = &e.prog_common;
+    CUDA_OK(cudaDeviceSynchronize());
+  });
+  if (rc != DMC_OK) {
+    delete t;
+    return rc;
+  }
+  *out = t;
+  return DMC_OK;
+}
+
+extern "C" void dmc_dcb_train_destroy(dmc_dcb_train* t) {
+  if (!t) return;
+  {
+    DeviceGuard dg(t->e.device);
+    cudaDeviceSynchronize();
+  }
+  delete t;
+}
+
+extern "C" const char* dmc_dcb_train_last_error(const dmc_dcb_train* t) {
+  return t ? t->e.error.c_str() : g_create_error.c_str();
+}
+
+extern "C" int dmc_dcb_train_forward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
+                                     float* out, void* stream) {
+  if (!t) return DMC_E_INVALID;
+  return guarded(&t->e, [&] {
+    if (!x || !out) fail("dmc_dcb_train_forward: null tensor");
+    DeviceGuard dg(t->e.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    dcb_train_load(*t, weights12, quant_step, false, st);
+    t->x = x; t->out = out;
+    t->e.cur.qp = 0;
+    t->e.run(t->e.prog_common, st);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+extern "C" int dmc_dcb_train_backward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
+                                      const float* grad_out, float* grad_x, float* const* grad_weights12,
+                                      float* grad_quant_step, void* stream) {
+  if (!t) return DMC_E_INVALID;
+  return guarded(&t->e, [&] {
+    if (!x || !grad_out) fail("dmc_dcb_train_backward: null tensor");
+    DeviceGuard dg(t->e.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    dcb_train_load(*t, weights12, quant_step, true, st);
+    t->x = x; t->gout = grad_out; t->gx = grad_x; t->gqs = t->has_qs ? grad_quant_step : nullptr;
+    for (int i = 0; i < 12; ++i) t->gw[i] = grad_weights12 ? grad_weights12[i] : nullptr;
+    if (!t->blk->adaptor) t->gw[0] = t->gw[1] = nullptr;
+    t->e.cur.qp = 0;
+    t->e.run(t->prog_bwd, st);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+extern "C" int dmc_op_quant_train(const float* x, const float* noise, float* out, int64_t n, int mode, void* stream) {
+  if (!x || !out || n < 0 || (mode != 0 && mode != 1) || (mode == 1 && !noise)) return DMC_E_INVALID;
+  if (n) quant_train(x, noise, out, (long long)n, mode, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
+}
+
+extern "C" int dmc_op_gaussian_bits_backward(const float* sym, const float* sigma, const float* grad_bits, float* grad_sym,
+                                             float* grad_sigma, int64_t n, int formula, void* stream) {
+  if (!sym || !sigma || !grad_bits || !grad_sym || !grad_sigma || n < 0) return DMC_E_INVALID;
+  if (n) gaussian_bits_bwd(sym, sigma, grad_bits, grad_sym, grad_sigma, (long long)n, formula, (cudaStream_t)stream);
   return cudaGetLastError() == cudaSuccess ? DMC_OK : DMC_E_CUDA;
 }
 

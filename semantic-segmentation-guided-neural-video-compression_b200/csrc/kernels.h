@@ -194,4 +194,25 @@ void frames_from_u8(const uint8_t* img, const uint8_t* mask, float* out, int N, 
 // mask = (logits > 0) as fp32 {0, 1}
 void mask_from_logits(const float* logits, float* mask, long long n, cudaStream_t st);
 
+// ---------------- training mode (train.cu) ----------------
+void wsilu_rows(const float* in, float* out, long long n, cudaStream_t st);                       // fp32 rows, n % 4 == 0
+void wsilu_bwd(View g, const float* pre, int ld, View out, long long M, cudaStream_t st);         // g * wsilu'(pre)
+void chunkadd_fwd(const float* u, int ld, View v, long long M, cudaStream_t st);                  // layers.py:12-20
+void chunkadd_bwd(View gv, const float* u, int ld, View gu, long long M, cudaStream_t st);
+void transpose_f32(const float* src, float* dst, int R, int C, cudaStream_t st);
+// column sums of g (times h, element by element, when h != nullptr) as per-block partial rows; returns their number
+int colsum_s3(View g, const View* h, long long M, float* part, int ldp, int max_parts, cudaStream_t st);
+void reduce_partials(const float* part, long long stride, int S, float* out, long long n, const float* scale_dev,
+                     float scale, cudaStream_t st);
+// depthwise 3x3 weight (C,1,3,3) + bias gradient as partial rows of C * 10 floats ([c][tap], tap 9 = bias)
+int dw_wgrad(View g, const float* t, int ld, int B, int H, int W, float* part, int ldp, int max_parts, cudaStream_t st);
+void flip_dw_weight(const float* w9c, float* out, int C, cudaStream_t st);
+void reduce_dw(const float* part, long long stride, int S, float* gw, float* gb, int C, float scale, cudaStream_t st);
+// dW[n][k] = sum_m G[m][n] X[m][k] as wgrad_splits() partial matrices of N * K floats (terms: 3 = fp32-grade split product)
+int wgrad_splits(long long M, int N, int K);
+int wgrad_s3(View G, View X, long long M, int terms, float* part, cudaStream_t st);
+void quant_train(const float* x, const float* noise, float* out, long long n, int mode, cudaStream_t st);
+void gaussian_bits_bwd(const float* sym, const float* sigma, const float* go, float* gsym, float* gsig, long long n,
+                       int formula, cudaStream_t st);
+
 }  // namespace dmc

@@ -1,0 +1,541 @@
+// Training-mode kernels: what the backward pass of a DepthConvBlock (layers.py:43-79) and of the
+// quantisation / likelihood terms (inference.py:16-27, entropy_models.py:303-341) needs beyond the forward kernels.
+//
+//   * data gradients of the 1x1 convolutions are ordinary contractions with the transposed weight: they run on the
+//     forward tcgen05 chain kernel (gemm_s3.cu) at the same 3-term split-fp16 accuracy;
+//   * weight gradients dW[n][k] = sum_m G[m][n] X[m][k] contract over the PIXEL axis, i.e. both operands are read
+//     "MN-major" from the pixel-major split planes.  k_wgrad_s3 does that with mma.sync m16n8k16 + ldmatrix.trans
+//     straight from the tile-blocked planes (their 32-byte swizzle is conflict-free for ldmatrix as it is), split
+//     over the pixel axis into per-CTA partial sums that k_reduce_partials adds up in a fixed order;
+//   * everything elementwise (WSiLU', chunk-add', depthwise weight gradient, column sums for the biases) is
+//     HBM-bound and vectorised 8 channels per thread on the split planes.
+//
+// Gradients are linear in the incoming gradient, so the caller pre-scales it by a power of two into fp16's
+// comfortable range (training.py: max |g| -> 2^8) and un-scales the results: `out_scale` of the reductions.
+#include "kernels.h"
+
+namespace dmc {
+
+static inline unsigned cdiv_u(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// d/dx [ silu(4x) / 4 ] = sigmoid(v) * (1 + v * (1 - sigmoid(v))),  v = 4x          (layers.py:8-10)
+__device__ __forceinline__ float wsilu_grad(float x) {
+  const float v = 4.0f * x;
+  const float s = 1.0f / (1.0f + expf(-v));
+  return s * fmaf(v, 1.0f - s, 1.0f);
+}
+
+// ------------------------------------------------------------------ elementwise, fp32 rows / split planes
+// out = wsilu(in), fp32 rows [M, C]
+__global__ void k_wsilu_rows(const float* __restrict__ in, float* __restrict__ out, long long n4) {
+  pdl_prologue_done();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<const float4*>(in)[i];
+  a.x = wsilu(a.x); a.y = wsilu(a.y); a.z = wsilu(a.z); a.w = wsilu(a.w);
+  reinterpret_cast<float4*>(out)[i] = a;
+}
+void wsilu_rows(const float* in, float* out, long long n, cudaStream_t st) {
+  launch(k_wsilu_rows, cdiv_u(n / 4, 256), 256, 0, st, in, out, n / 4);
+}
+
+// out[m, c] = g[m, c] * wsilu'(pre[m, c]);   g, out: split planes [M, C];  pre: fp32 rows [M, ld]
+__global__ void k_wsilu_bwd(View g, const float* __restrict__ pre, int ld, View out, long long M, int C8) {
+  pdl_prologue_done();
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * C8) return;
+  const long long m = idx / C8;
+  const int c = (int)(idx % C8) * 8;
+  float v[8];
+  ld3x8(g, m, c, v);
+  const float4 p0 = *reinterpret_cast<const float4*>(pre + m * ld + c);
+  const float4 p1 = *reinterpret_cast<const float4*>(pre + m * ld + c + 4);
+  const float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] *= wsilu_grad(p[i]);
+  st3x8(out, m, c, v);
+}
+void wsilu_bwd(View g, const float* pre, int ld, View out, long long M, cudaStream_t st) {
+  const int C8 = g.C / 8;
+  launch(k_wsilu_bwd, cdiv_u(M * C8, 256), 256, 0, st, g, pre, ld, out, M, C8);
+}
+
+// WSiLUChunkAdd (layers.py:12-20) from the fp32 pre-activations [M, 2*C2]:  v[m, j] = wsilu(u[m, j]) + wsilu(u[m, j + C2])
+__global__ void k_chunkadd_fwd(const float* __restrict__ u, int ld, View v, long long M, int C2) {
+  pdl_prologue_done();
+  const int C8 = C2 / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * C8) return;
+  const long long m = idx / C8;
+  const int c = (int)(idx % C8) * 8;
+  const float* q = u + m * ld + c;
+  float o[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 a = *reinterpret_cast<const float4*>(q + 4 * h);
+    const float4 b = *reinterpret_cast<const float4*>(q + C2 + 4 * h);
+    o[4 * h + 0] = add_rn(wsilu(a.x), wsilu(b.x));
+    o[4 * h + 1] = add_rn(wsilu(a.y), wsilu(b.y));
+    o[4 * h + 2] = add_rn(wsilu(a.z), wsilu(b.z));
+    o[4 * h + 3] = add_rn(wsilu(a.w), wsilu(b.w));
+  }
+  st3x8(v, m, c, o);
+}
+void chunkadd_fwd(const float* u, int ld, View v, long long M, cudaStream_t st) {
+  const int C2 = v.C;
+  launch(k_chunkadd_fwd, cdiv_u(M * (C2 / 8), 256), 256, 0, st, u, ld, v, M, C2);
+}
+
+// gu[m, j] = gv[m, j mod C2] * wsilu'(u[m, j]),  j < 2*C2
+__global__ void k_chunkadd_bwd(View gv, const float* __restrict__ u, int ld, View gu, long long M, int C2) {
+  pdl_prologue_done();
+  const int C8 = C2 / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * C8) return;
+  const long long m = idx / C8;
+  const int c = (int)(idx % C8) * 8;
+  float g[8];
+  ld3x8(gv, m, c, g);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const float* q = u + m * ld + half * C2 + c;
+    const float4 p0 = *reinterpret_cast<const float4*>(q);
+    const float4 p1 = *reinterpret_cast<const float4*>(q + 4);
+    const float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = g[i] * wsilu_grad(p[i]);
+    st3x8(gu, m, half * C2 + c, o);
+  }
+}
+void chunkadd_bwd(View gv, const float* u, int ld, View gu, long long M, cudaStream_t st) {
+  const int C2 = gv.C;
+  launch(k_chunkadd_bwd, cdiv_u(M * (C2 / 8), 256), 256, 0, st, gv, u, ld, gu, M, C2);
+}
+
+// dst[c][r] = src[r][c]  (fp32; weights of a 1x1 convolution -> the weight of its data gradient)
+__global__ void k_transpose_f32(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
+  pdl_prologue_done();
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < R && c < C) ? src[(long long)r * C + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) dst[(long long)c * R + r] = t[threadIdx.x][i];
+  }
+}
+void transpose_f32(const float* src, float* dst, int R, int C, cudaStream_t st) {
+  dim3 grid(cdiv_u(C, 32), cdiv_u(R, 32));
+  launch(k_transpose_f32, grid, dim3(32, 8), 0, st, src, dst, R, C);
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients, per-channel scale)
+// part[blockIdx.x][c] = sum over this block's rows of g[m, c] (* h[m, c] when h is given)
+__global__ void __launch_bounds__(256) k_colsum_s3(View g, View h, int has_h, long long M, int C8, float* __restrict__ part,
+                                                   int ldp) {
+  pdl_prologue_done();
+  extern __shared__ float red[];        // [rows_per_block][C8 * 8]
+  const int lanes = blockDim.x / C8;    // row lanes per block
+  const int c8 = threadIdx.x % C8, rl = threadIdx.x / C8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rl < lanes) {
+    for (long long m = (long long)blockIdx.x * lanes + rl; m < M; m += (long long)gridDim.x * lanes) {
+      float v[8];
+      ld3x8(g, m, c8 * 8, v);
+      if (has_h) {
+        float w[8];
+        ld3x8(h, m, c8 * 8, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], w[i], acc[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[(rl * C8 + c8) * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C8 * 8; c += blockDim.x) {
+    float s = 0.0f;
+    for (int r = 0; r < lanes; ++r) s += red[r * C8 * 8 + c];
+    part[(long long)blockIdx.x * ldp + c] = s;
+  }
+}
+// returns the number of partial rows written to `part` (each `ldp` floats apart)
+int colsum_s3(View g, const View* h, long long M, float* part, int ldp, int max_parts, cudaStream_t st) {
+  const int C8 = (g.C + 7) / 8;
+  int threads = 256;
+  if (C8 > threads) threads = (C8 + 31) / 32 * 32;
+  const int lanes = threads / C8;
+  int blocks = (int)((M + lanes - 1) / lanes);
+  const int want = 2 * num_sms();
+  if (blocks > want) blocks = want;
+  if (blocks > max_parts) blocks = max_parts;
+  if (blocks < 1) blocks = 1;
+  View hv = h ? *h : g;
+  launch(k_colsum_s3, blocks, threads, (size_t)lanes * C8 * 8 * sizeof(float), st, g, hv, h ? 1 : 0, M, C8, part, ldp);
+  return blocks;
+}
+
+// out[i] = scale * sum_s part[s * stride + i]   (fixed summation order: the result does not depend on scheduling)
+__global__ void k_reduce_partials(const float* __restrict__ part, long long stride, int S, float* __restrict__ out,
+                                  long long n, const float* __restrict__ scale_dev, float scale) {
+  pdl_prologue_done();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int k = 0; k < S; ++k) s += part[(long long)k * stride + i];
+  if (scale_dev) scale *= *scale_dev;
+  out[i] = s * scale;
+}
+void reduce_partials(const float* part, long long stride, int S, float* out, long long n, const float* scale_dev,
+                     float scale, cudaStream_t st) {
+  launch(k_reduce_partials, cdiv_u(n, 256), 256, 0, st, part, stride, S, out, n, scale_dev, scale);
+}
+
+// ------------------------------------------------------------------ depthwise 3x3: weight / bias gradient
+// dW[c][ky][kx] = sum_{b,h,w} g[b,h,w,c] * t[b,h+ky-1,w+kx-1,c]  (zero outside), db[c] = sum g.
+// g: split planes [M, C]; t: fp32 rows [M, ld] (the WSiLU output the forward conv read).
+// Thread = 8 channels x one pixel lane; part[block][c*10 + tap] (tap 9 = bias).
+__global__ void __launch_bounds__(256) k_dw_wgrad(View g, const float* __restrict__ t, int ld, int B, int H, int W, int C8,
+                                                  float* __restrict__ part, int ldp) {
+  pdl_prologue_done();
+  extern __shared__ float red[];        // [lanes][C8*8*10]
+  const int lanes = blockDim.x / C8;
+  const int c8 = threadIdx.x % C8, rl = threadIdx.x / C8;
+  const long long M = (long long)B * H * W;
+  float acc[10][8];
+#pragma unroll
+  for (int k = 0; k < 10; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[k][i] = 0.0f;
+  if (rl < lanes) {
+    for (long long m = (long long)blockIdx.x * lanes + rl; m < M; m += (long long)gridDim.x * lanes) {
+      const int w = (int)(m % W);
+      const int h = (int)((m / W) % H);
+      float gv[8];
+      ld3x8(g, m, c8 * 8, gv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[9][i] += gv[i];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int hh = h + ky - 1;
+        if ((unsigned)hh >= (unsigned)H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ww = w + kx - 1;
+          if ((unsigned)ww >= (unsigned)W) continue;
+          const float* q = t + (m + (long long)(ky - 1) * W + (kx - 1)) * ld + c8 * 8;
+          const float4 a = *reinterpret_cast<const float4*>(q);
+          const float4 b = *reinterpret_cast<const float4*>(q + 4);
+          const float tv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[ky * 3 + kx][i] = fmaf(gv[i], tv[i], acc[ky * 3 + kx][i]);
+        }
+      }
+    }
+    float* r = red + (long long)rl * C8 * 80;
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[(c8 * 8 + i) * 10 + k] = acc[k][i];
+  }
+  __syncthreads();
+  const int n = C8 * 80;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    float s = 0.0f;
+    for (int r = 0; r < lanes; ++r) s += red[(long long)r * n + j];
+    part[(long long)blockIdx.x * ldp + j] = s;
+  }
+}
+int dw_wgrad(View g, const float* t, int ld, int B, int H, int W, float* part, int ldp, int max_parts, cudaStream_t st) {
+  const int C8 = g.C / 8;
+  int threads = 256;
+  int lanes = threads / C8;
+  if (lanes < 1) { lanes = 1; threads = (C8 + 31) / 32 * 32; }
+  // shared memory: lanes * C * 10 floats (256 channels x 8 lanes = 80 KB): opt in once
+  const size_t smem = (size_t)lanes * C8 * 80 * sizeof(float);
+  cudaFuncSetAttribute(k_dw_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long M = (long long)B * H * W;
+  int blocks = (int)((M + lanes - 1) / lanes);
+  const int want = 2 * num_sms();
+  if (blocks > want) blocks = want;
+  if (blocks > max_parts) blocks = max_parts;
+  if (blocks < 1) blocks = 1;
+  launch(k_dw_wgrad, blocks, threads, smem, st, g, t, ld, B, H, W, C8, part, ldp);
+  return blocks;
+}
+
+
+// w9c [9][C] -> the taps of the data gradient: out[tap][c] = w9c[8 - tap][c] (the kernel rotated by 180 degrees)
+__global__ void k_flip_dw(const float* __restrict__ w9c, float* __restrict__ out, int C) {
+  pdl_prologue_done();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * C) return;
+  out[i] = w9c[(8 - i / C) * C + i % C];
+}
+void flip_dw_weight(const float* w9c, float* out, int C, cudaStream_t st) { launch(k_flip_dw, cdiv_u(9 * C, 256), 256, 0, st, w9c, out, C); }
+
+// partial rows of dw_wgrad -> weight gradient (C,1,3,3) and bias gradient (C); either destination may be null
+__global__ void k_reduce_dw(const float* __restrict__ part, long long stride, int S, float* gw, float* gb, int C, float scale) {
+  pdl_prologue_done();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * 10) return;
+  float s = 0.0f;
+  for (int k = 0; k < S; ++k) s += part[(long long)k * stride + i];
+  const int c = i / 10, tap = i % 10;
+  if (tap < 9) { if (gw) gw[c * 9 + tap] = s * scale; }
+  else if (gb) gb[c] = s * scale;
+}
+void reduce_dw(const float* part, long long stride, int S, float* gw, float* gb, int C, float scale, cudaStream_t st) {
+  launch(k_reduce_dw, cdiv_u(C * 10, 256), 256, 0, st, part, stride, S, gw, gb, C, scale);
+}
+
+// ------------------------------------------------------------------ weight gradient of a 1x1 convolution
+// part[z][n][k] = sum over the pixel slice z of G[m][n] * X[m][k].
+//
+// CTA = 128 (n) x 64 (k) outputs, 8 warps of 32 x 32, pixel chunks of 32 through a 3-deep cp.async ring.  A chunk of a
+// plane is one contiguous 1 KB piece per 16-column block -- [32 pixels][16 columns] with the two 16-byte halves of a
+// row swapped where bit 2 of the pixel index is set -- and is copied verbatim: the eight rows an ldmatrix reads (one
+// 16-byte unit each, consecutive pixels, same column group) then fall into eight different 16-byte bank groups.
+// Both fragments come from ldmatrix.trans (the contraction index is the ROW of the stored tiles).  Split product as
+// in the forward kernels: main += Gh.Xh, small += Gh.Xl + Gl.Xh (2^11-scaled), result = main + small * 2^-11.
+constexpr int kWgTN = 128, kWgTK = 64, kWgChunk = 32, kWgStages = 3;
+constexpr int kWgGBytes = (kWgTN / 16) * 1024;       // one plane of the G tile of a chunk
+constexpr int kWgXBytes = (kWgTK / 16) * 1024;
+constexpr int kWgStageBytes = 2 * (kWgGBytes + kWgXBytes);
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// byte offset of the 16-byte unit (pixel r of the chunk, column group cg of 8 columns) inside a plane tile
+__device__ __forceinline__ uint32_t wg_unit(int r, int cg) {
+  return (uint32_t)((cg >> 1) * 1024 + r * 32 + ((((cg & 1) ^ ((r >> 2) & 1))) << 4));
+}
+
+template <int kTerms>
+__global__ void __launch_bounds__(256, 2)
+k_wgrad_s3(View G, View X, int N, int K, int chunks_total, int chunks_per_split, float* __restrict__ part) {
+  pdl_prologue_done();
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * kWgTN, k0 = blockIdx.y * kWgTK;
+  const int c_begin = blockIdx.z * chunks_per_split;
+  int c_end = c_begin + chunks_per_split;
+  if (c_end > chunks_total) c_end = chunks_total;
+  const int nch = c_end - c_begin;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+
+  // column blocks past the tensor stay zero for the whole kernel (ragged N / K)
+  for (int i = tid; i < kWgStages * kWgStageBytes / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
+  const int gblk = (G.C + 15) / 16, xblk = (X.C + 15) / 16;
+  constexpr int kPl = (kTerms == 1) ? 1 : 2;
+  // a stage = [G hi][G lo][X hi][X lo]; 16-byte pieces: G 512 per plane, X 256 per plane
+  auto issue = [&](int chunk, int stage) {
+    const uint32_t s0 = sbase + stage * kWgStageBytes;
+    const long long row0 = (long long)chunk * kWgChunk;
+#pragma unroll
+    for (int it = 0; it < (kPl * (kWgGBytes + kWgXBytes) / 16 + 255) / 256; ++it) {
+      const int p = it * 256 + tid;
+      if (p >= kPl * (kWgGBytes + kWgXBytes) / 16) break;
+      const int per_pl = (kWgGBytes + kWgXBytes) / 16;      // 768
+      const int pl = p / per_pl, q = p % per_pl;
+      if (q < kWgGBytes / 16) {
+        const int blk = q >> 6, u = q & 63;                  // 64 units per 1 KB block
+        const int gb = (n0 >> 4) + blk;
+        if (gb < gblk)
+          cp_async16(s0 + pl * kWgGBytes + blk * 1024 + u * 16,
+                     G.p + pl * G.ps + (long long)gb * G.bs + row0 * 16 + u * 8);
+      } else {
+        const int qq = q - kWgGBytes / 16;
+        const int blk = qq >> 6, u = qq & 63;
+        const int xb = (k0 >> 4) + blk;
+        if (xb < xblk)
+          cp_async16(s0 + 2 * kWgGBytes + pl * kWgXBytes + blk * 1024 + u * 16,
+                     X.p + pl * X.ps + (long long)xb * X.bs + row0 * 16 + u * 8);
+      }
+    }
+  };
+
+  float acc[2][4][4], acs[(kTerms == 1) ? 1 : 2][(kTerms == 1) ? 1 : 4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[i][j][e] = 0.0f;
+        if constexpr (kTerms != 1) acs[i][j][e] = 0.0f;
+      }
+
+  const int wn = (warp & 3) * 32, wk = (warp >> 2) * 32;     // warp tile origin inside the CTA tile
+  // ldmatrix lane roles.  A (from G, rows = pixels): matrix j = lane >> 3: pixels (j >> 1) * 8 + (lane & 7), columns
+  // (j & 1) * 8.  B (from X): pixels (j & 1) * 8 + (lane & 7), columns (j >> 1) * 8.
+  const int lj = lane >> 3, lr = lane & 7;
+  const int a_r = (lj >> 1) * 8 + lr, a_c = (lj & 1) * 8;
+  const int b_r = (lj & 1) * 8 + lr, b_c = (lj >> 1) * 8;
+
+  for (int s = 0; s < kWgStages - 1; ++s) {
+    if (s < nch) issue(c_begin + s, s);
+    cp_async_commit();
+  }
+  for (int i = 0; i < nch; ++i) {
+    cp_async_wait<kWgStages - 2>();
+    __syncthreads();
+    if (i + kWgStages - 1 < nch) issue(c_begin + i + kWgStages - 1, (i + kWgStages - 1) % kWgStages);
+    cp_async_commit();
+    const uint32_t s0 = sbase + (i % kWgStages) * kWgStageBytes;
+    const uint32_t gh = s0, gl = s0 + kWgGBytes, xh = s0 + 2 * kWgGBytes, xl = xh + kWgXBytes;
+#pragma unroll
+    for (int ms = 0; ms < kWgChunk / 16; ++ms) {
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int i16 = 0; i16 < 2; ++i16) {
+        const uint32_t off = wg_unit(ms * 16 + a_r, (wn + i16 * 16 + a_c) >> 3);
+        ldsm_x4_t(gh + off, ah[i16]);
+        if constexpr (kTerms != 1) ldsm_x4_t(gl + off, al[i16]);
+      }
+#pragma unroll
+      for (int j16 = 0; j16 < 2; ++j16) {
+        uint32_t bh[4], bl[4];
+        const uint32_t off = wg_unit(ms * 16 + b_r, (wk + j16 * 16 + b_c) >> 3);
+        ldsm_x4_t(xh + off, bh);
+        if constexpr (kTerms != 1) ldsm_x4_t(xl + off, bl);
+#pragma unroll
+        for (int i16 = 0; i16 < 2; ++i16)
+#pragma unroll
+          for (int j8 = 0; j8 < 2; ++j8) {
+            mma16816(acc[i16][j16 * 2 + j8], ah[i16], bh[2 * j8], bh[2 * j8 + 1]);
+            if constexpr (kTerms != 1) {
+              mma16816(acs[i16][j16 * 2 + j8], ah[i16], bl[2 * j8], bl[2 * j8 + 1]);
+              mma16816(acs[i16][j16 * 2 + j8], al[i16], bh[2 * j8], bh[2 * j8 + 1]);
+            }
+          }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  float* dst = part + (long long)blockIdx.z * N * K;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i16 = 0; i16 < 2; ++i16)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = n0 + wn + i16 * 16 + g + ((e >> 1) << 3);
+        const int k = k0 + wk + j * 8 + 2 * t + (e & 1);
+        if (n < N && k < K) {
+          float v = acc[i16][j][e];
+          if constexpr (kTerms != 1) v = fmaf(acs[i16][j][e], kLoInv, v);
+          dst[(long long)n * K + k] = v;
+        }
+      }
+}
+
+int wgrad_splits(long long M, int N, int K) {
+  const int chunks = (int)((M + kWgChunk - 1) / kWgChunk);
+  const int tiles = ((N + kWgTN - 1) / kWgTN) * ((K + kWgTK - 1) / kWgTK);
+  int S = (2 * num_sms() + tiles - 1) / tiles;
+  if (S > chunks) S = chunks;
+  if (S < 1) S = 1;
+  return S;
+}
+// `part` needs wgrad_splits(M, N, K) * N * K floats.  Rows [M, M rounded up to 32) of both operands must be zero
+// (the padding rows of every engine buffer are).  Returns the number of partial matrices written.
+int wgrad_s3(View G, View X, long long M, int terms, float* part, cudaStream_t st) {
+  const int N = G.C, K = X.C;
+  const int chunks = (int)((M + kWgChunk - 1) / kWgChunk);
+  int S = wgrad_splits(M, N, K);
+  const int per = (chunks + S - 1) / S;
+  S = (chunks + per - 1) / per;
+  const int smem = kWgStages * kWgStageBytes;
+  cudaFuncSetAttribute(k_wgrad_s3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_wgrad_s3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  dim3 grid((N + kWgTN - 1) / kWgTN, (K + kWgTK - 1) / kWgTK, S);
+  if (terms == 1) launch(k_wgrad_s3<1>, grid, 256, smem, st, G, X, N, K, chunks, per, part);
+  else launch(k_wgrad_s3<3>, grid, 256, smem, st, G, X, N, K, chunks, per, part);
+  return S;
+}
+
+// ------------------------------------------------------------------ quantisation / likelihood, training mode
+// inference.py:16-27.  mode 0 "ste": out = round(x) (the gradient passes through unchanged: nothing to compute);
+// mode 1 "noise": out = x + noise, noise ~ U(-half_bin, half_bin) drawn by the caller (torch's generator, so that a
+// seeded run reproduces the reference's).
+__global__ void k_quant_train(const float* __restrict__ x, const float* __restrict__ noise, float* __restrict__ out, long long n,
+                              int mode) {
+  pdl_prologue_done();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = mode == 0 ? rintf(x[i]) : add_rn(x[i], noise[i]);
+}
+void quant_train(const float* x, const float* noise, float* out, long long n, int mode, cudaStream_t st) {
+  launch(k_quant_train, cdiv_u(n, 256), 256, 0, st, x, noise, out, n, mode);
+}
+
+// Gradient of the Gaussian likelihood bits (forward values: k_gaussian_bits in kernels.cu).
+//   formula 0  models/common_model.py:30-42     sg = clamp(sigma, 1e-5, 1e10); p = Phi((s+.5)/sg) - Phi((s-.5)/sg);
+//                                                bits = max(-log2(p + 1e-5), 0)
+//   formula 1  refactor/common_model.py:37-68   s clamped to +-6 (seg_video_model.py:347), z clamped to +-12,
+//                                                bits = -log2(max(p, 1e-9))
+// gs = go * dbits/ds, gsig = go * dbits/dsigma; every clamp passes the gradient on its closed interval and blocks it
+// outside, as torch's clamp does.  Evaluated in fp64 (the differences of cdf values cancel).
+__global__ void k_gaussian_bits_bwd(const float* __restrict__ sym, const float* __restrict__ sigma, const float* __restrict__ go,
+                                    float* __restrict__ gsym, float* __restrict__ gsig, long long n, int formula) {
+  pdl_prologue_done();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double kInvSqrt2 = 0.70710678118654752440, kInvSqrt2Pi = 0.39894228040143267794, kLn2 = 0.69314718055994530942;
+  double s = sym[i], sg = sigma[i];
+  bool s_live = true, sg_live = (sg >= 1e-5 && sg <= 1e10);
+  if (formula) {
+    if (!(fabs(s) <= 6.0)) s_live = false;
+    s = fmin(fmax(s, -6.0), 6.0);
+  }
+  sg = fmin(fmax(sg, 1e-5), 1e10);
+  double zh = (s + 0.5) / sg, zl = (s - 0.5) / sg;
+  bool zh_live = true, zl_live = true;
+  if (formula) {
+    zh_live = fabs(zh) <= 12.0;
+    zl_live = fabs(zl) <= 12.0;
+    zh = fmin(fmax(zh, -12.0), 12.0);
+    zl = fmin(fmax(zl, -12.0), 12.0);
+  }
+  const double p = 0.5 * (erf(zh * kInvSqrt2) - erf(zl * kInvSqrt2));
+  double dbdp;      // d bits / d p
+  if (formula) dbdp = (p >= 1e-9) ? -1.0 / (p * kLn2) : 0.0;
+  else dbdp = (-log(p + 1e-5) / kLn2 >= 0.0) ? -1.0 / ((p + 1e-5) * kLn2) : 0.0;
+  const double ph = zh_live ? kInvSqrt2Pi * exp(-0.5 * zh * zh) : 0.0;     // dp/dzh
+  const double pl = zl_live ? kInvSqrt2Pi * exp(-0.5 * zl * zl) : 0.0;     // -dp/dzl
+  const double dpds = (ph - pl) / sg;
+  const double dpdsg = (-(zh * ph) + zl * pl) / sg;
+  const double g = go[i];
+  gsym[i] = (float)(s_live ? g * dbdp * dpds : 0.0);
+  gsig[i] = (float)(sg_live ? g * dbdp * dpdsg : 0.0);
+}
+void gaussian_bits_bwd(const float* sym, const float* sigma, const float* go, float* gsym, float* gsig, long long n,
+                       int formula, cudaStream_t st) {
+  launch(k_gaussian_bits_bwd, cdiv_u(n, 256), 256, 0, st, sym, sigma, go, gsym, gsig, n, formula);
+}
+
+}  // namespace dmc

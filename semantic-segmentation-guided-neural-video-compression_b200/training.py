@@ -1,0 +1,290 @@
+"""Training-mode building blocks on the CUDA engine.
+
+`p_frame_model.train()` in the reference (trainer_seg_video_model.py:983-1206) back-propagates the rate-distortion loss
+through DepthConvBlock stacks, the STE / additive-noise quantisers and the Gaussian likelihood.  This module gives those
+three pieces as `torch.autograd.Function`s over the C ABI (include/dmc_b200.h, "training mode"), wrapped in modules with
+the reference's constructors and state_dict keys:
+
+    DepthConvBlock(in_ch, out_ch, shortcut=False, force_adaptor=False)      src/layers/layers.py:43-79
+    AdaptiveQuant(mode="ste" | "noise", half_bin=0.5)                       src/layers/inference.py:8-27
+    gaussian_bits(y, sigma, formula)                                        src/models/common_model.py:36-42 (0),
+                                                                            src/refactor/common_model.py:37-68 (1)
+
+Forward values are the inference engine's (same kernels); backward is hand-written CUDA: data gradients on the
+tcgen05 chain kernel with transposed weights, weight gradients by a pixel-axis contraction, everything else
+elementwise (csrc/train.cu).  Only x is kept between forward and backward -- the block's intermediates are recomputed.
+There is no torch / CPU fallback: without the extension or a CUDA tensor the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _capi
+
+__all__ = ["DepthConvBlock", "AdaptiveQuant", "depth_conv_block", "gaussian_bits", "quant_ste", "quant_noise",
+           "release_handles"]
+
+#: DepthConvBlock geometries kept alive (each owns its workspace: ~1.3 GB at 160x240x256); least recently used first out
+max_handles = 8
+#: incoming gradients are scaled so that max |g| = 2^GRAD_LOG2_PEAK before they enter the fp16 split planes
+GRAD_LOG2_PEAK = 8
+
+_handles: "OrderedDict[tuple, int]" = OrderedDict()
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dmc_b200.training: CUDA tensors required (there is no CPU path)")
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def release_handles():
+    """Frees every cached DepthConvBlock workspace."""
+    lib = _capi.load()
+    while _handles:
+        _, h = _handles.popitem(last=False)
+        lib.dmc_dcb_train_destroy(ctypes.c_void_p(h))
+
+
+def _handle(device, B, H, W, cin, cout, force_adaptor, shortcut, has_qs, terms) -> ctypes.c_void_p:
+    key = (device.index, B, H, W, cin, cout, bool(force_adaptor), bool(shortcut), bool(has_qs), terms)
+    lib = _capi.load()
+    if key in _handles:
+        _handles.move_to_end(key)
+        return ctypes.c_void_p(_handles[key])
+    while len(_handles) >= max_handles:
+        _, old = _handles.popitem(last=False)
+        lib.dmc_dcb_train_destroy(ctypes.c_void_p(old))
+    h = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        rc = lib.dmc_dcb_train_create(B, H, W, cin, cout, int(force_adaptor), int(shortcut), int(has_qs), terms,
+                                      ctypes.byref(h))
+    if rc != 0:
+        msg = lib.dmc_dcb_train_last_error(None)
+        raise _capi.EngineError(f"dmc_dcb_train_create: {msg.decode() if msg else rc}")
+    _handles[key] = h.value
+    return h
+
+
+def _check(rc, h):
+    if rc != 0:
+        msg = _capi.load().dmc_dcb_train_last_error(h)
+        raise _capi.EngineError(f"dmc_b200 training error {rc}: {msg.decode() if msg else '?'}")
+
+
+class _DepthConvBlockFn(torch.autograd.Function):
+    """y = DepthConvBlock(x) [* quant_step];  inputs: x, quant_step or None, then the 12 parameters (adaptor.weight,
+    adaptor.bias, dc.0, dc.2, dc.3, ffn.0, ffn.2; None for an absent adaptor)."""
+
+    @staticmethod
+    def forward(ctx, x, quant_step, shortcut, terms, *w12):
+        _need_cuda(x)
+        lib = _capi.load()
+        x = x.contiguous().float()
+        B, cin, H, W = x.shape
+        cout = w12[2].shape[0]
+        has_ad = w12[0] is not None
+        ws = [None if w is None else w.detach().contiguous().float() for w in w12]
+        qs = None
+        if quant_step is not None:
+            if quant_step.numel() != cout:
+                raise RuntimeError("quant_step must hold one value per output channel")
+            qs = quant_step.detach().reshape(cout).contiguous().float()
+        h = _handle(x.device, B, H, W, cin, cout, has_ad, shortcut, qs is not None, terms)
+        out = torch.empty(B, cout, H, W, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _check(lib.dmc_dcb_train_forward(h, _ptr(x), _ptr_array(ws), _ptr(qs), _ptr(out), _stream(x.device)), h)
+        ctx.save_for_backward(x, quant_step, *[w for w in w12 if w is not None])
+        ctx.meta = (has_ad, bool(shortcut), terms, quant_step is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        has_ad, shortcut, terms, has_qs = ctx.meta
+        saved = ctx.saved_tensors
+        x, quant_step = saved[0], saved[1]
+        w12 = list(saved[2:])
+        if not has_ad:
+            w12 = [None, None] + w12
+        lib = _capi.load()
+        B, cin, H, W = x.shape
+        cout = w12[2].shape[0]
+        ws = [None if w is None else w.detach().contiguous().float() for w in w12]
+        qs = quant_step.detach().reshape(cout).contiguous().float() if has_qs else None
+        # power-of-two scale into fp16's range; everything downstream is linear in the gradient
+        g = grad_out.contiguous().float()
+        amax = g.abs().amax().clamp_min(1e-30)
+        scale = torch.exp2(torch.floor(GRAD_LOG2_PEAK - torch.log2(amax)))
+        g = g * scale
+        need = ctx.needs_input_grad            # (x, quant_step, shortcut, terms, *w12)
+        gx = torch.empty_like(x) if need[0] else None
+        sizes = [0 if (w is None or not need[4 + i]) else w.numel() for i, w in enumerate(w12)]
+        n_qs = cout if (has_qs and need[1]) else 0
+        flat = torch.empty(sum(sizes) + n_qs, device=x.device, dtype=torch.float32)
+        gws, off = [], 0
+        for n in sizes:
+            gws.append(flat[off:off + n] if n else None)
+            off += n
+        gqs = flat[off:off + n_qs] if n_qs else None
+        h = _handle(x.device, B, H, W, cin, cout, has_ad, shortcut, has_qs, terms)
+        with torch.cuda.device(x.device):
+            _check(lib.dmc_dcb_train_backward(h, _ptr(x), _ptr_array(ws), _ptr(qs), _ptr(g), _ptr(gx), _ptr_array(gws),
+                                              _ptr(gqs), _stream(x.device)), h)
+        inv = 1.0 / scale
+        flat.mul_(inv)
+        if gx is not None:
+            gx.mul_(inv)
+        grads_w = [None if gw is None else gw.view_as(w) for gw, w in zip(gws, w12)]
+        g_qs = gqs.view_as(quant_step) if gqs is not None else None
+        return (gx, g_qs, None, None, *grads_w)
+
+
+def depth_conv_block(x, weights12, quant_step=None, shortcut=False, terms=3):
+    """Functional form; `weights12` in the order of include/dmc_b200.h (adaptor entries None when the block has none)."""
+    return _DepthConvBlockFn.apply(x, quant_step, bool(shortcut), int(terms), *weights12)
+
+
+class _Seq(nn.Module):
+    """nn.Sequential-like container that keeps the reference's sparse child indices (dc.0, dc.2, dc.3; ffn.0, ffn.2)."""
+
+    def __init__(self, children):
+        super().__init__()
+        for name, m in children:
+            self.add_module(str(name), m)
+
+    def __getitem__(self, i):
+        return self._modules[str(i)]
+
+
+class DepthConvBlock(nn.Module):
+    """src/layers/layers.py:43-79 with the same constructor, parameters and forward signature; runs on the engine in
+    train and eval mode alike (`terms`: 3 = fp32-grade products, 1 = plain fp16 operands)."""
+
+    def __init__(self, in_ch, out_ch, shortcut=False, force_adaptor=False, terms=3):
+        super().__init__()
+        self.adaptor = None
+        if in_ch != out_ch or force_adaptor:
+            self.adaptor = nn.Conv2d(in_ch, out_ch, 1)
+        self.shortcut = shortcut
+        self.terms = terms
+        self.dc = _Seq([(0, nn.Conv2d(out_ch, out_ch, 1)), (2, nn.Conv2d(out_ch, out_ch, 3, padding=1, groups=out_ch)),
+                        (3, nn.Conv2d(out_ch, out_ch, 1))])
+        self.ffn = _Seq([(0, nn.Conv2d(out_ch, out_ch * 4, 1)), (2, nn.Conv2d(out_ch * 2, out_ch, 1))])
+
+    def weights12(self):
+        ad = self.adaptor
+        convs = [self.dc[0], self.dc[2], self.dc[3], self.ffn[0], self.ffn[2]]
+        out = [ad.weight if ad is not None else None, ad.bias if ad is not None else None]
+        for c in convs:
+            out += [c.weight, c.bias]
+        return out
+
+    def forward(self, x, quant_step=None, to_cat=None, cat_at_front=True):
+        out = depth_conv_block(x, self.weights12(), quant_step, self.shortcut, self.terms)
+        if to_cat is not None:
+            out = torch.cat((to_cat, out), dim=1) if cat_at_front else torch.cat((out, to_cat), dim=1)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ quantisation
+class _QuantFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, noise, mode):
+        _need_cuda(x, noise)
+        lib = _capi.load()
+        x = x.contiguous().float()
+        out = torch.empty_like(x)
+        nz = noise.contiguous().float() if noise is not None else None
+        with torch.cuda.device(x.device):
+            rc = lib.dmc_op_quant_train(_ptr(x), _ptr(nz), _ptr(out), x.numel(), mode, _stream(x.device))
+        if rc != 0:
+            raise _capi.EngineError(f"dmc_op_quant_train failed ({rc})")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        # ste: (round(x) - x).detach() + x  and  noise: x + noise  both have d out / d x = 1  (inference.py:18,25)
+        return g, None, None
+
+
+def quant_ste(x):
+    return _QuantFn.apply(x, None, 0)
+
+
+def quant_noise(x, half_bin=0.5, generator=None):
+    noise = torch.empty_like(x).uniform_(-half_bin, half_bin, generator=generator)
+    return _QuantFn.apply(x, noise, 1)
+
+
+class AdaptiveQuant(nn.Module):
+    """src/layers/inference.py:8-27.  Training: "ste" rounds with a straight-through gradient, "noise" adds
+    U(-half_bin, half_bin) drawn from torch's generator in the reference's call order (a seeded run reproduces the
+    reference's noise).  Eval: hard rounding in both modes."""
+
+    def __init__(self, mode="ste", half_bin=0.5):
+        super().__init__()
+        assert mode in ["ste", "noise"], "Unsupported mode"
+        self.mode = mode
+        self.half_bin = half_bin
+
+    def forward(self, x):
+        if self.mode == "noise" and self.training:
+            return quant_noise(x, self.half_bin)
+        return quant_ste(x)
+
+
+# ------------------------------------------------------------------------------------------------ likelihood
+class _GaussianBitsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, sigma, formula):
+        _need_cuda(y, sigma)
+        lib = _capi.load()
+        y = y.contiguous().float()
+        sigma = sigma.contiguous().float()
+        bits = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            rc = lib.dmc_op_gaussian_bits(_ptr(y), _ptr(sigma), _ptr(bits), y.numel(), formula, _stream(y.device))
+        if rc != 0:
+            raise _capi.EngineError(f"dmc_op_gaussian_bits failed ({rc})")
+        ctx.save_for_backward(y, sigma)
+        ctx.formula = formula
+        return bits
+
+    @staticmethod
+    def backward(ctx, g):
+        y, sigma = ctx.saved_tensors
+        lib = _capi.load()
+        g = g.contiguous().float()
+        gy, gs = torch.empty_like(y), torch.empty_like(sigma)
+        with torch.cuda.device(y.device):
+            rc = lib.dmc_op_gaussian_bits_backward(_ptr(y), _ptr(sigma), _ptr(g), _ptr(gy), _ptr(gs), y.numel(),
+                                                   ctx.formula, _stream(y.device))
+        if rc != 0:
+            raise _capi.EngineError(f"dmc_op_gaussian_bits_backward failed ({rc})")
+        return gy, gs, None
+
+
+def gaussian_bits(y, sigma, formula=1):
+    """Per-element likelihood bits with gradients for y and sigma.  formula 0: models/common_model.py:36-42 (`old`,
+    DMCI); 1: refactor/common_model.py:37-68 including the +-6 clamp of seg_video_model.py:347."""
+    return _GaussianBitsFn.apply(y, sigma, int(formula))
