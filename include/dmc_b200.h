@@ -191,11 +191,13 @@ int dmc_dcb_train_create(int batch, int height, int width, int cin, int cout, in
                          int has_quant_step, int terms, dmc_dcb_train** out);
 void dmc_dcb_train_destroy(dmc_dcb_train* t);
 const char* dmc_dcb_train_last_error(const dmc_dcb_train* t);
+/* weights_unchanged != 0: the caller vouches that the twelve parameters hold the VALUES this handle packed at its
+ * previous call (forward followed by backward of one training step): only packed copies still missing are made. */
 int dmc_dcb_train_forward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
-                          float* out, void* stream);
+                          float* out, int weights_unchanged, void* stream);
 int dmc_dcb_train_backward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
                            const float* grad_out, float* grad_x, float* const* grad_weights12, float* grad_quant_step,
-                           void* stream);
+                           int weights_unchanged, void* stream);
 /* AdaptiveQuant in training mode (layers/inference.py:16-27).  mode 0 "ste": out = round(x) (the straight-through
  * gradient is the identity); mode 1 "noise": out = x + noise with noise ~ U(-half_bin, half_bin) drawn by the caller. */
 int dmc_op_quant_train(const float* x, const float* noise, float* out, int64_t n, int mode, void* stream);

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdmc_b200.so")
-SOURCES = ["kernels.cu", "gemm_umma.cu", "gemm_s3.cu", "engine.cu", "rans.cu", "train.cu"]
+SOURCES = ["kernels.cu", "gemm_umma.cu", "gemm_s3.cu", "engine.cu", "rans.cu", "train.cu", "wgrad_umma.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -1593,7 +1593,8 @@ struct dmc_dcb_train {
   int cin = 0, cout = 0, shortcut = 0, has_qs = 0, terms = 3;
   DCB* blk = nullptr;
   Conv *T_ad = nullptr, *T_dc0 = nullptr, *T_dc3 = nullptr, *T_ffn0 = nullptr, *T_ffn2 = nullptr, *P_ffn0 = nullptr;
-  float *tmpT = nullptr, *w9c_flip = nullptr, *zero_bias = nullptr, *qs_table = nullptr, *part = nullptr;
+  bool fwd_packed = false, bwd_packed = false;
+  float *w9c_flip = nullptr, *zero_bias = nullptr, *qs_table = nullptr, *part = nullptr;
   size_t part_floats = 0;
   // caller tensors of the current call (read by the launch closures)
   const float *x = nullptr, *gout = nullptr;
@@ -1604,15 +1605,17 @@ struct dmc_dcb_train {
 namespace {
 const char* const kDcbNames[6] = {"b.adaptor", "b.dc.0", "b.dc.2", "b.dc.3", "b.ffn.0", "b.ffn.2"};
 
-void dcb_train_load(dmc_dcb_train& t, const float* const* w12, const float* quant_step, bool backward, cudaStream_t st) {
+// Packs the caller's parameters for the forward program (`backward` false) or for both.  With `unchanged` set the
+// caller vouches that the parameter VALUES are the ones this handle packed last: only what is still missing is packed
+// (a training step calls forward, then backward, on the same weights).
+void dcb_train_load(dmc_dcb_train& t, const float* const* w12, const float* quant_step, bool backward, bool unchanged,
+                    cudaStream_t st) {
   dmc_engine& e = t.e;
   if (!w12) fail("null weight list");
   if (t.blk->adaptor && (!w12[0] || !w12[1])) fail("adaptor weights required (cin != cout or force_adaptor)");
   for (int i = 0; i < 6; ++i) {
     if (i == 0 && !t.blk->adaptor) continue;
     if (!w12[2 * i] || !w12[2 * i + 1]) fail("missing weight %s", kDcbNames[i]);
-    set_slot(e, std::string(kDcbNames[i]) + ".weight", w12[2 * i], st);
-    set_slot(e, std::string(kDcbNames[i]) + ".bias", w12[2 * i + 1], st);
   }
   if (t.has_qs) {
     if (!quant_step) fail("quant_step required: the block was created with has_quant_step");
@@ -1620,20 +1623,26 @@ void dcb_train_load(dmc_dcb_train& t, const float* const* w12, const float* quan
   } else if (quant_step) {
     fail("quant_step given but the block was created without has_quant_step");
   }
-  if (!backward) return;
+  if (!unchanged) t.fwd_packed = t.bwd_packed = false;
+  if (!t.fwd_packed) {
+    for (int i = 0; i < 6; ++i) {
+      if (i == 0 && !t.blk->adaptor) continue;
+      set_slot(e, std::string(kDcbNames[i]) + ".weight", w12[2 * i], st);
+      set_slot(e, std::string(kDcbNames[i]) + ".bias", w12[2 * i + 1], st);
+    }
+    t.fwd_packed = true;
+  }
+  if (!backward || t.bwd_packed) return;
   const int C = t.cout;
   set_slot(e, "P.ffn0.weight", w12[8], st);
   set_slot(e, "P.ffn0.bias", w12[9], st);
-  struct TW { Conv* c; const float* w; int rows, cols; const char* key; };
-  const TW tw[5] = {{t.T_ad, w12[0], C, t.cin, "T.ad"}, {t.T_dc0, w12[2], C, C, "T.dc0"}, {t.T_dc3, w12[6], C, C, "T.dc3"},
-                    {t.T_ffn0, w12[8], 4 * C, C, "T.ffn0"}, {t.T_ffn2, w12[10], C, 2 * C, "T.ffn2"}};
-  for (const TW& w : tw) {
-    if (!w.c) continue;
-    transpose_f32(w.w, t.tmpT, w.rows, w.cols, st);
-    set_slot(e, std::string(w.key) + ".weight", t.tmpT, st);
-    pack_gemm_bias(nullptr, w.c->cout, w.c->g, st);
-  }
+  // data-gradient weights: the transposes, packed straight from the forward weights
+  struct TW { Conv* c; const float* w; };
+  const TW tw[5] = {{t.T_ad, w12[0]}, {t.T_dc0, w12[2]}, {t.T_dc3, w12[6]}, {t.T_ffn0, w12[8]}, {t.T_ffn2, w12[10]}};
+  for (const TW& w : tw)
+    if (w.c) pack_gemm_weight(w.w, w.c->cout, w.c->cin, 1, 1, w.c->g, st, true);
   flip_dw_weight(t.blk->dw->w9c, t.w9c_flip, C, st);
+  t.bwd_packed = true;
 }
 }  // namespace
 
@@ -1662,7 +1671,8 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     t->T_dc3 = e.add_conv("T.dc3", C, C, 1, 1, 0);
     t->T_ffn0 = e.add_conv("T.ffn0", 4 * C, C, 1, 1, 0);
     t->T_ffn2 = e.add_conv("T.ffn2", C, 2 * C, 1, 1, 0);
-    t->tmpT = e.new_f32((size_t)4 * C * std::max(C, cin));
+    for (Conv* c : {t->T_ad, t->T_dc0, t->T_dc3, t->T_ffn0, t->T_ffn2})
+      if (c) pack_gemm_bias(nullptr, c->cout, c->g, nullptr);      // data gradients carry no bias
     t->w9c_flip = e.new_f32((size_t)9 * C);
     t->zero_bias = e.new_f32((size_t)4 * C);
     CUDA_OK(cudaMemset(t->zero_bias, 0, sizeof(float) * 4 * C));
@@ -1747,6 +1757,7 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
         const int N = G.v.C, K = X.v.C;
         if (self->gw[iw]) {
           int S = wgrad_s3(G.v, X.v, M, terms_, self->part, st);
+          if (S < 1) fail("weight gradient launch: %s", wgrad_umma_last_error());
           reduce_partials(self->part, (long long)N * K, S, self->gw[iw], (long long)N * K, nullptr, 1.0f, st);
         }
         if (self->gw[iw + 1]) {
@@ -1820,13 +1831,13 @@ extern "C" const char* dmc_dcb_train_last_error(const dmc_dcb_train* t) {
 }
 
 extern "C" int dmc_dcb_train_forward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
-                                     float* out, void* stream) {
+                                     float* out, int weights_unchanged, void* stream) {
   if (!t) return DMC_E_INVALID;
   return guarded(&t->e, [&] {
     if (!x || !out) fail("dmc_dcb_train_forward: null tensor");
     DeviceGuard dg(t->e.device);
     cudaStream_t st = (cudaStream_t)stream;
-    dcb_train_load(*t, weights12, quant_step, false, st);
+    dcb_train_load(*t, weights12, quant_step, false, weights_unchanged != 0, st);
     t->x = x; t->out = out;
     t->e.cur.qp = 0;
     t->e.run(t->e.prog_common, st);
@@ -1836,13 +1847,13 @@ extern "C" int dmc_dcb_train_forward(dmc_dcb_train* t, const float* x, const flo
 
 extern "C" int dmc_dcb_train_backward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
                                       const float* grad_out, float* grad_x, float* const* grad_weights12,
-                                      float* grad_quant_step, void* stream) {
+                                      float* grad_quant_step, int weights_unchanged, void* stream) {
   if (!t) return DMC_E_INVALID;
   return guarded(&t->e, [&] {
     if (!x || !grad_out) fail("dmc_dcb_train_backward: null tensor");
     DeviceGuard dg(t->e.device);
     cudaStream_t st = (cudaStream_t)stream;
-    dcb_train_load(*t, weights12, quant_step, true, st);
+    dcb_train_load(*t, weights12, quant_step, true, weights_unchanged != 0, st);
     t->x = x; t->gout = grad_out; t->gx = grad_x; t->gqs = t->has_qs ? grad_quant_step : nullptr;
     for (int i = 0; i < 12; ++i) t->gw[i] = grad_weights12 ? grad_weights12[i] : nullptr;
     if (!t->blk->adaptor) t->gw[0] = t->gw[1] = nullptr;

@@ -73,7 +73,7 @@ float acc_comp_scaled(int K) {
 // the shared-memory image of a K-major SWIZZLE_32B operand, so a W tile is fetched as a few 512-byte segments.
 __global__ void k_pack_gemm_weight(const float* __restrict__ w, h16* __restrict__ out, h16* __restrict__ outb,
                                    int cout, int cin, int kh, int kw, int Npad, int Kld, int K, int pack,
-                                   int Cg, int Cg_pad) {
+                                   int Cg, int Cg_pad, int transposed) {
   pdl_prologue_done();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)Npad * Kld) return;
@@ -93,7 +93,9 @@ __global__ void k_pack_gemm_weight(const float* __restrict__ w, h16* __restrict_
   if (n >= 0 && kk < K) {
     int ci = kk % cin, tap = kk / cin;
     int y = tap / kw, x = tap % kw;
-    v = w[(((long long)n * cin + ci) * kh + y) * kw + x];
+    // transposed (1x1 only): `w` is the (cin, cout, 1, 1) weight of the forward convolution, read as its transpose --
+    // the weight of the convolution's data gradient (train mode)
+    v = transposed ? w[(long long)ci * cout + n] : w[(((long long)n * cin + ci) * kh + y) * kw + x];
   }
   h16 h, l;
   split2(v, h, l);
@@ -128,10 +130,10 @@ __global__ void k_pack_bias(const float* __restrict__ b, float* __restrict__ out
 }
 
 void pack_gemm_weight(const float* w, int cout, int cin, int kh, int kw, const GemmW& g,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool transposed) {
   long long n = (long long)g.Npad * g.Kld;
   launch(k_pack_gemm_weight, cdiv(n, 256), 256, 0, st, w, g.w, g.wb, cout, cin, kh, kw, g.Npad, g.Kld,
-                                                   g.K, g.pack, g.Cg, g.Cg_pad);
+                                                   g.K, g.pack, g.Cg, g.Cg_pad, transposed ? 1 : 0);
 }
 void pack_gemm_bias(const float* bias, int cout, const GemmW& g, cudaStream_t st) {
   launch(k_pack_bias, cdiv(g.Npad, 256), 256, 0, st, bias, g.bias, cout, g.Npad, g.pack, g.Cg, g.Cg_pad);

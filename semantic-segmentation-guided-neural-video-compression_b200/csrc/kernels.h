@@ -52,8 +52,9 @@ struct GemmW {
   void* tmap_s3 = nullptr;    // box = 32 k x BN/2 rows x 2 planes (gemm_s3.cu)
   void* tmap_s3_hi = nullptr; // same with the hi plane only (single-term products)
 };
+// transposed (1x1): w is the (cin, cout, 1, 1) weight of another convolution, packed as its transpose
 void pack_gemm_weight(const float* w_oihw, int cout, int cin, int kh, int kw, const GemmW& g,
-                      cudaStream_t st);
+                      cudaStream_t st, bool transposed = false);
 void pack_gemm_bias(const float* bias, int cout, const GemmW& g, cudaStream_t st);   // nullptr -> zeros
 // depthwise 3x3: (C,1,3,3) -> [9][C] fp32
 void pack_dw_weight(const float* w, float* out9c, int C, cudaStream_t st);
@@ -210,6 +211,11 @@ void flip_dw_weight(const float* w9c, float* out, int C, cudaStream_t st);
 void reduce_dw(const float* part, long long stride, int S, float* gw, float* gb, int C, float scale, cudaStream_t st);
 // dW[n][k] = sum_m G[m][n] X[m][k] as wgrad_splits() partial matrices of N * K floats (terms: 3 = fp32-grade split product)
 int wgrad_splits(long long M, int N, int K);
+// tcgen05 version (wgrad_umma.cu); wgrad_s3 routes to it unless DMC_WGRAD_UMMA=0
+bool wgrad_umma_supported(View G, View X);
+int wgrad_umma_splits(long long M, int N, int K);
+int wgrad_umma(View G, View X, long long M, int terms, float* part, cudaStream_t st);   // -1 on error
+const char* wgrad_umma_last_error();
 int wgrad_s3(View G, View X, long long M, int terms, float* part, cudaStream_t st);
 void quant_train(const float* x, const float* noise, float* out, long long n, int mode, cudaStream_t st);
 void gaussian_bits_bwd(const float* sym, const float* sigma, const float* go, float* gsym, float* gsig, long long n,

@@ -4,14 +4,18 @@
 //   * data gradients of the 1x1 convolutions are ordinary contractions with the transposed weight: they run on the
 //     forward tcgen05 chain kernel (gemm_s3.cu) at the same 3-term split-fp16 accuracy;
 //   * weight gradients dW[n][k] = sum_m G[m][n] X[m][k] contract over the PIXEL axis, i.e. both operands are read
-//     "MN-major" from the pixel-major split planes.  k_wgrad_s3 does that with mma.sync m16n8k16 + ldmatrix.trans
-//     straight from the tile-blocked planes (their 32-byte swizzle is conflict-free for ldmatrix as it is), split
-//     over the pixel axis into per-CTA partial sums that k_reduce_partials adds up in a fixed order;
+//     "MN-major" from the pixel-major split planes.  The product kernel is k_wgrad_umma (wgrad_umma.cu: tcgen05 with
+//     MN-major descriptors); k_wgrad_s3 here does the same with mma.sync m16n8k16 + ldmatrix.trans straight from the
+//     tile-blocked planes (their 32-byte swizzle is conflict-free for ldmatrix as it is) and stays as the A/B and
+//     validation kernel (DMC_WGRAD_UMMA=0: the legacy tensor path measured 110 T MAC/s, 1/16 of tcgen05's peak).
+//     Both split the pixel axis into per-CTA partial sums that k_reduce_partials adds up in a fixed order;
 //   * everything elementwise (WSiLU', chunk-add', depthwise weight gradient, column sums for the biases) is
 //     HBM-bound and vectorised 8 channels per thread on the split planes.
 //
 // Gradients are linear in the incoming gradient, so the caller pre-scales it by a power of two into fp16's
 // comfortable range (training.py: max |g| -> 2^8) and un-scales the results: `out_scale` of the reductions.
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace dmc {
@@ -193,9 +197,31 @@ __global__ void k_reduce_partials(const float* __restrict__ part, long long stri
   if (scale_dev) scale *= *scale_dev;
   out[i] = s * scale;
 }
+// many partial rows, few outputs (column sums): 32 outputs x 8 row lanes per block, the lanes combined in a fixed order
+__global__ void __launch_bounds__(256) k_reduce_partials_tall(const float* __restrict__ part, long long stride, int S,
+                                                              float* __restrict__ out, long long n,
+                                                              const float* __restrict__ scale_dev, float scale) {
+  pdl_prologue_done();
+  __shared__ float red[8][33];
+  const int col = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + col;
+  float s = 0.0f;
+  if (i < n)
+    for (int k = lane; k < S; k += 8) s += part[(long long)k * stride + i];
+  red[lane][col] = s;
+  __syncthreads();
+  if (lane == 0 && i < n) {
+    float t = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][col];
+    if (scale_dev) scale *= *scale_dev;
+    out[i] = t * scale;
+  }
+}
 void reduce_partials(const float* part, long long stride, int S, float* out, long long n, const float* scale_dev,
                      float scale, cudaStream_t st) {
-  launch(k_reduce_partials, cdiv_u(n, 256), 256, 0, st, part, stride, S, out, n, scale_dev, scale);
+  if (S >= 32 && n <= 65536) launch(k_reduce_partials_tall, cdiv_u(n, 32), 256, 0, st, part, stride, S, out, n, scale_dev, scale);
+  else launch(k_reduce_partials, cdiv_u(n, 256), 256, 0, st, part, stride, S, out, n, scale_dev, scale);
 }
 
 // ------------------------------------------------------------------ depthwise 3x3: weight / bias gradient
@@ -282,18 +308,27 @@ __global__ void k_flip_dw(const float* __restrict__ w9c, float* __restrict__ out
 void flip_dw_weight(const float* w9c, float* out, int C, cudaStream_t st) { launch(k_flip_dw, cdiv_u(9 * C, 256), 256, 0, st, w9c, out, C); }
 
 // partial rows of dw_wgrad -> weight gradient (C,1,3,3) and bias gradient (C); either destination may be null
-__global__ void k_reduce_dw(const float* __restrict__ part, long long stride, int S, float* gw, float* gb, int C, float scale) {
+__global__ void __launch_bounds__(256) k_reduce_dw(const float* __restrict__ part, long long stride, int S, float* gw, float* gb,
+                                                   int C, float scale) {
   pdl_prologue_done();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * 10) return;
+  __shared__ float red[8][33];
+  const int col = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + col;
   float s = 0.0f;
-  for (int k = 0; k < S; ++k) s += part[(long long)k * stride + i];
+  if (i < C * 10)
+    for (int k = lane; k < S; k += 8) s += part[(long long)k * stride + i];
+  red[lane][col] = s;
+  __syncthreads();
+  if (lane != 0 || i >= C * 10) return;
+  float t = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) t += red[r][col];
   const int c = i / 10, tap = i % 10;
-  if (tap < 9) { if (gw) gw[c * 9 + tap] = s * scale; }
-  else if (gb) gb[c] = s * scale;
+  if (tap < 9) { if (gw) gw[c * 9 + tap] = t * scale; }
+  else if (gb) gb[c] = t * scale;
 }
 void reduce_dw(const float* part, long long stride, int S, float* gw, float* gb, int C, float scale, cudaStream_t st) {
-  launch(k_reduce_dw, cdiv_u(C * 10, 256), 256, 0, st, part, stride, S, gw, gb, C, scale);
+  launch(k_reduce_dw, cdiv_u(C * 10, 32), 256, 0, st, part, stride, S, gw, gb, C, scale);
 }
 
 // ------------------------------------------------------------------ weight gradient of a 1x1 convolution
@@ -453,7 +488,7 @@ k_wgrad_s3(View G, View X, int N, int K, int chunks_total, int chunks_per_split,
       }
 }
 
-int wgrad_splits(long long M, int N, int K) {
+static int wgrad_mma_splits(long long M, int N, int K) {
   const int chunks = (int)((M + kWgChunk - 1) / kWgChunk);
   const int tiles = ((N + kWgTN - 1) / kWgTN) * ((K + kWgTK - 1) / kWgTK);
   int S = (2 * num_sms() + tiles - 1) / tiles;
@@ -461,12 +496,14 @@ int wgrad_splits(long long M, int N, int K) {
   if (S < 1) S = 1;
   return S;
 }
+int wgrad_splits(long long M, int N, int K) { return std::max(wgrad_mma_splits(M, N, K), wgrad_umma_splits(M, N, K)); }
 // `part` needs wgrad_splits(M, N, K) * N * K floats.  Rows [M, M rounded up to 32) of both operands must be zero
 // (the padding rows of every engine buffer are).  Returns the number of partial matrices written.
 int wgrad_s3(View G, View X, long long M, int terms, float* part, cudaStream_t st) {
+  if (wgrad_umma_supported(G, X)) return wgrad_umma(G, X, M, terms, part, st);      // tcgen05 (wgrad_umma.cu)
   const int N = G.C, K = X.C;
   const int chunks = (int)((M + kWgChunk - 1) / kWgChunk);
-  int S = wgrad_splits(M, N, K);
+  int S = wgrad_mma_splits(M, N, K);
   const int per = (chunks + S - 1) / S;
   S = (chunks + per - 1) / per;
   const int smem = kWgStages * kWgStageBytes;

@@ -27,14 +27,27 @@ from torch import nn
 from . import _capi
 
 __all__ = ["DepthConvBlock", "AdaptiveQuant", "depth_conv_block", "gaussian_bits", "quant_ste", "quant_noise",
-           "release_handles"]
+           "release_handles", "invalidate"]
 
-#: DepthConvBlock geometries kept alive (each owns its workspace: ~1.3 GB at 160x240x256); least recently used first out
-max_handles = 8
+#: DepthConvBlock handles kept alive -- one per (owner module, geometry), each with its own workspace (~1.2 GB at
+#: 160x240x256, 1/4 of that per halving of the resolution) and packed weights; least recently used first out
+max_handles = 32
 #: incoming gradients are scaled so that max |g| = 2^GRAD_LOG2_PEAK before they enter the fp16 split planes
 GRAD_LOG2_PEAK = 8
 
 _handles: "OrderedDict[tuple, int]" = OrderedDict()
+_packed_sig: dict = {}        # handle key -> signature of the parameter values the handle has packed
+
+
+def _signature(w12):
+    """(storage pointer, version counter) per parameter: moves with every in-place update an optimizer makes.  Writes
+    through `.data` bypass the counter (see modules.py); call `invalidate()` after such a write."""
+    return tuple((w.data_ptr(), w._version) for w in w12 if w is not None)
+
+
+def invalidate():
+    """Forget which parameter values the handles have packed (after writes through `.data`)."""
+    _packed_sig.clear()
 
 
 def _need_cuda(*tensors):
@@ -64,16 +77,19 @@ def release_handles():
     while _handles:
         _, h = _handles.popitem(last=False)
         lib.dmc_dcb_train_destroy(ctypes.c_void_p(h))
+    _packed_sig.clear()
 
 
-def _handle(device, B, H, W, cin, cout, force_adaptor, shortcut, has_qs, terms) -> ctypes.c_void_p:
-    key = (device.index, B, H, W, cin, cout, bool(force_adaptor), bool(shortcut), bool(has_qs), terms)
+def _handle(owner, device, B, H, W, cin, cout, force_adaptor, shortcut, has_qs, terms):
+    """-> (key, handle).  `owner` separates blocks of equal geometry so that each keeps its own packed weights."""
+    key = (owner, device.index, B, H, W, cin, cout, bool(force_adaptor), bool(shortcut), bool(has_qs), terms)
     lib = _capi.load()
     if key in _handles:
         _handles.move_to_end(key)
-        return ctypes.c_void_p(_handles[key])
+        return key, ctypes.c_void_p(_handles[key])
     while len(_handles) >= max_handles:
-        _, old = _handles.popitem(last=False)
+        old_key, old = _handles.popitem(last=False)
+        _packed_sig.pop(old_key, None)
         lib.dmc_dcb_train_destroy(ctypes.c_void_p(old))
     h = ctypes.c_void_p()
     with torch.cuda.device(device):
@@ -83,7 +99,7 @@ def _handle(device, B, H, W, cin, cout, force_adaptor, shortcut, has_qs, terms) 
         msg = lib.dmc_dcb_train_last_error(None)
         raise _capi.EngineError(f"dmc_dcb_train_create: {msg.decode() if msg else rc}")
     _handles[key] = h.value
-    return h
+    return key, h
 
 
 def _check(rc, h):
@@ -97,7 +113,7 @@ class _DepthConvBlockFn(torch.autograd.Function):
     adaptor.bias, dc.0, dc.2, dc.3, ffn.0, ffn.2; None for an absent adaptor)."""
 
     @staticmethod
-    def forward(ctx, x, quant_step, shortcut, terms, *w12):
+    def forward(ctx, x, quant_step, shortcut, terms, owner, *w12):
         _need_cuda(x)
         lib = _capi.load()
         x = x.contiguous().float()
@@ -110,17 +126,21 @@ class _DepthConvBlockFn(torch.autograd.Function):
             if quant_step.numel() != cout:
                 raise RuntimeError("quant_step must hold one value per output channel")
             qs = quant_step.detach().reshape(cout).contiguous().float()
-        h = _handle(x.device, B, H, W, cin, cout, has_ad, shortcut, qs is not None, terms)
+        key, h = _handle(owner, x.device, B, H, W, cin, cout, has_ad, shortcut, qs is not None, terms)
+        sig = _signature(w12)
+        unchanged = int(_packed_sig.get(key) == sig)
         out = torch.empty(B, cout, H, W, device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
-            _check(lib.dmc_dcb_train_forward(h, _ptr(x), _ptr_array(ws), _ptr(qs), _ptr(out), _stream(x.device)), h)
+            _check(lib.dmc_dcb_train_forward(h, _ptr(x), _ptr_array(ws), _ptr(qs), _ptr(out), unchanged,
+                                             _stream(x.device)), h)
+        _packed_sig[key] = sig
         ctx.save_for_backward(x, quant_step, *[w for w in w12 if w is not None])
-        ctx.meta = (has_ad, bool(shortcut), terms, quant_step is not None)
+        ctx.meta = (has_ad, bool(shortcut), terms, quant_step is not None, owner, sig)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        has_ad, shortcut, terms, has_qs = ctx.meta
+        has_ad, shortcut, terms, has_qs, owner, sig = ctx.meta
         saved = ctx.saved_tensors
         x, quant_step = saved[0], saved[1]
         w12 = list(saved[2:])
@@ -136,9 +156,9 @@ class _DepthConvBlockFn(torch.autograd.Function):
         amax = g.abs().amax().clamp_min(1e-30)
         scale = torch.exp2(torch.floor(GRAD_LOG2_PEAK - torch.log2(amax)))
         g = g * scale
-        need = ctx.needs_input_grad            # (x, quant_step, shortcut, terms, *w12)
+        need = ctx.needs_input_grad            # (x, quant_step, shortcut, terms, owner, *w12)
         gx = torch.empty_like(x) if need[0] else None
-        sizes = [0 if (w is None or not need[4 + i]) else w.numel() for i, w in enumerate(w12)]
+        sizes = [0 if (w is None or not need[5 + i]) else w.numel() for i, w in enumerate(w12)]
         n_qs = cout if (has_qs and need[1]) else 0
         flat = torch.empty(sum(sizes) + n_qs, device=x.device, dtype=torch.float32)
         gws, off = [], 0
@@ -146,22 +166,25 @@ class _DepthConvBlockFn(torch.autograd.Function):
             gws.append(flat[off:off + n] if n else None)
             off += n
         gqs = flat[off:off + n_qs] if n_qs else None
-        h = _handle(x.device, B, H, W, cin, cout, has_ad, shortcut, has_qs, terms)
+        key, h = _handle(owner, x.device, B, H, W, cin, cout, has_ad, shortcut, has_qs, terms)
+        unchanged = int(_packed_sig.get(key) == sig)      # (autograd itself refuses saved tensors modified in place)
         with torch.cuda.device(x.device):
             _check(lib.dmc_dcb_train_backward(h, _ptr(x), _ptr_array(ws), _ptr(qs), _ptr(g), _ptr(gx), _ptr_array(gws),
-                                              _ptr(gqs), _stream(x.device)), h)
+                                              _ptr(gqs), unchanged, _stream(x.device)), h)
+        _packed_sig[key] = sig
         inv = 1.0 / scale
         flat.mul_(inv)
         if gx is not None:
             gx.mul_(inv)
         grads_w = [None if gw is None else gw.view_as(w) for gw, w in zip(gws, w12)]
         g_qs = gqs.view_as(quant_step) if gqs is not None else None
-        return (gx, g_qs, None, None, *grads_w)
+        return (gx, g_qs, None, None, None, *grads_w)
 
 
-def depth_conv_block(x, weights12, quant_step=None, shortcut=False, terms=3):
-    """Functional form; `weights12` in the order of include/dmc_b200.h (adaptor entries None when the block has none)."""
-    return _DepthConvBlockFn.apply(x, quant_step, bool(shortcut), int(terms), *weights12)
+def depth_conv_block(x, weights12, quant_step=None, shortcut=False, terms=3, owner=0):
+    """Functional form; `weights12` in the order of include/dmc_b200.h (adaptor entries None when the block has none).
+    `owner`: any hashable that tells blocks of equal geometry apart (each then keeps its own packed weights)."""
+    return _DepthConvBlockFn.apply(x, quant_step, bool(shortcut), int(terms), owner, *weights12)
 
 
 class _Seq(nn.Module):
@@ -200,7 +223,7 @@ class DepthConvBlock(nn.Module):
         return out
 
     def forward(self, x, quant_step=None, to_cat=None, cat_at_front=True):
-        out = depth_conv_block(x, self.weights12(), quant_step, self.shortcut, self.terms)
+        out = depth_conv_block(x, self.weights12(), quant_step, self.shortcut, self.terms, owner=id(self))
         if to_cat is not None:
             out = torch.cat((to_cat, out), dim=1) if cat_at_front else torch.cat((out, to_cat), dim=1)
         return out

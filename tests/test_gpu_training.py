@@ -190,3 +190,39 @@ def test_training_blocks_refuse_cpu_tensors():
     blk = T.DepthConvBlock(32, 32)
     with pytest.raises(RuntimeError, match="no CPU path"):
         blk(torch.randn(1, 32, 8, 8))
+
+
+def test_weight_updates_are_picked_up():
+    """An optimizer step (in-place, bumps the version counter) must reach the packed copies; a write through `.data`
+    does after `training.invalidate()`."""
+    torch.manual_seed(3)
+    blk = T.DepthConvBlock(64, 64).cuda().train()
+    ref = RefDCB(64, 64).double()
+    x = torch.randn(1, 64, 16, 16)
+
+    def check():
+        _copy_back(ref, blk)
+        xr = x.double().requires_grad_(True)
+        ref.zero_grad()
+        ref(xr).sum().backward()
+        xg = x.cuda().requires_grad_(True)
+        blk.zero_grad()
+        y = blk(xg)
+        y.sum().backward()
+        assert _relmax(y, ref(xr)) < 2e-5
+        assert _relmax(blk.ffn[0].weight.grad, ref.ffn0.weight.grad) < 2e-4
+        assert _relmax(xg.grad, xr.grad) < 2e-4
+
+    def _copy_back(r, b):      # reference <- engine module (the engine module is the one being updated)
+        with torch.no_grad():
+            for rc, bc in [(r.dc0, b.dc[0]), (r.dc2, b.dc[2]), (r.dc3, b.dc[3]), (r.ffn0, b.ffn[0]), (r.ffn2, b.ffn[2])]:
+                rc.weight.copy_(bc.weight.double().cpu())
+                rc.bias.copy_(bc.bias.double().cpu())
+
+    check()
+    opt = torch.optim.SGD(blk.parameters(), lr=2e-5)   # (a sum loss: gradients are O(1e3))
+    opt.step()                              # uses the gradients of check(): every parameter moves
+    check()
+    blk.ffn[0].weight.data.mul_(1.5)        # invisible to the version counter
+    T.invalidate()
+    check()

@@ -79,7 +79,10 @@ def fwd_only(block, xin, q):
     return step
 
 
+ONLY = os.environ.get("DMC_TB_ONLY", "")      # "dmc3" / "dmc1": just that engine configuration (profiling runs)
 for terms in (3, 1):
+    if ONLY and ONLY != f"dmc{terms}":
+        continue
     blk = D.training.DepthConvBlock(C, C, terms=terms).to(dev).train()
     xin = x.clone().requires_grad_(True)
     q = qs.clone().requires_grad_(True)
@@ -95,7 +98,7 @@ for terms in (3, 1):
     D.training.release_handles()
 
 ref = TorchDCB(C).to(dev).train()
-for name, tf32, amp in (("torch fp32 (TF32 off)", False, None), ("torch default TF32", True, None),
+for name, tf32, amp in () if ONLY else (("torch fp32 (TF32 off)", False, None), ("torch default TF32", True, None),
                         ("torch autocast bf16", True, torch.bfloat16)):
     torch.backends.cuda.matmul.allow_tf32 = tf32
     torch.backends.cudnn.allow_tf32 = tf32
