@@ -27,11 +27,11 @@ from torch import nn
 from . import _capi
 
 __all__ = ["DepthConvBlock", "AdaptiveQuant", "depth_conv_block", "gaussian_bits", "quant_ste", "quant_noise",
-           "release_handles", "invalidate"]
+           "release_handles", "invalidate", "reference_patched", "adopt"]
 
 #: DepthConvBlock handles kept alive -- one per (owner module, geometry), each with its own workspace (~1.2 GB at
 #: 160x240x256, 1/4 of that per halving of the resolution) and packed weights; least recently used first out
-max_handles = 32
+max_handles = 64
 #: incoming gradients are scaled so that max |g| = 2^GRAD_LOG2_PEAK before they enter the fp16 split planes
 GRAD_LOG2_PEAK = 8
 
@@ -223,10 +223,14 @@ class DepthConvBlock(nn.Module):
         return out
 
     def forward(self, x, quant_step=None, to_cat=None, cat_at_front=True):
+        if quant_step is not None and quant_step.numel() != self.dc[0].out_channels:
+            raise RuntimeError("DepthConvBlock: quant_step must be one (1, C, 1, 1) row (a single qp per call)")
         out = depth_conv_block(x, self.weights12(), quant_step, self.shortcut, self.terms, owner=id(self))
         if to_cat is not None:
             out = torch.cat((to_cat, out), dim=1) if cat_at_front else torch.cat((out, to_cat), dim=1)
         return out
+
+    forward_torch = forward        # the reference's forward() delegates to a method of this name
 
 
 # ------------------------------------------------------------------------------------------------ quantisation
@@ -311,3 +315,47 @@ def gaussian_bits(y, sigma, formula=1):
     """Per-element likelihood bits with gradients for y and sigma.  formula 0: models/common_model.py:36-42 (`old`,
     DMCI); 1: refactor/common_model.py:37-68 including the +-6 clamp of seg_video_model.py:347."""
     return _GaussianBitsFn.apply(y, sigma, int(formula))
+
+
+# ------------------------------------------------------------------------------------------------ reference integration
+class reference_patched:
+    """Context manager: inside it, the given (already imported) reference modules construct the engine's blocks.
+
+        import src.layers.layers as L, src.refactor.common_model as CM, src.refactor.seg_video_model as SV
+        with dmc_b200.training.reference_patched(L, CM, SV):
+            p_frame_model = SV.DMC(DMCConfig())          # DepthConvBlock / AdaptiveQuant are now the engine's
+        dmc_b200.training.adopt(p_frame_model, formula=1)   # + the likelihood with its native backward
+        p_frame_model.load_state_dict(checkpoint)        # parameter names and shapes are the reference's
+
+    Every name bound by `from ..layers.layers import DepthConvBlock` is a separate module attribute, so each module that
+    constructs blocks has to be listed (layers.py itself for ResidualBlockWithStride2 / ResidualBlockUpsample)."""
+
+    def __init__(self, *modules):
+        self.modules = modules
+        self.saved = []
+
+    def __enter__(self):
+        for m in self.modules:
+            for name, repl in (("DepthConvBlock", DepthConvBlock), ("AdaptiveQuant", AdaptiveQuant)):
+                if hasattr(m, name):
+                    self.saved.append((m, name, getattr(m, name)))
+                    setattr(m, name, repl)
+        return self
+
+    def __exit__(self, *exc):
+        for m, name, old in reversed(self.saved):
+            setattr(m, name, old)
+        self.saved = []
+        return False
+
+
+def adopt(model, formula=1):
+    """Routes `model.get_y_gaussian_bits` (models/common_model.py:36-42 -> formula 0, refactor/common_model.py:37-68 ->
+    formula 1) of this instance through the engine's likelihood kernels, forward and backward."""
+    import types
+
+    def get_y_gaussian_bits(self, y, sigma):
+        return gaussian_bits(y, sigma, formula)
+
+    model.get_y_gaussian_bits = types.MethodType(get_y_gaussian_bits, model)
+    return model
