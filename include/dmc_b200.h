@@ -184,8 +184,10 @@ int dmc_op_gaussian_bits(const float* sym, const float* sigma, float* bits, int6
  * engine's block, backward recomputes the block's intermediates from x (nothing else is kept between the passes) and
  * returns the gradients torch.autograd would: of x, of the twelve parameters (same order and shapes as weights12;
  * NULL entries are skipped) and of quant_step.  terms: 3 = fp32-grade split product, 1 = plain fp16 operands.
- * The gradient arithmetic runs on fp16 split planes: pre-scale grad_out so that max |g| is around 2^8 and un-scale the
- * results (training.py does).  All tensors NCHW fp32 on the device, calls are asynchronous on `stream`. */
+ * The gradient arithmetic runs on fp16 split planes; backward scales grad_out by a power of two (max |g| -> 2^8,
+ * found on the device) on the way in and un-scales every result, so gradients of any magnitude are fine.  `out` is the
+ * tensor forward returned (needed for grad_quant_step only, else it may be NULL).  All tensors NCHW fp32 on the
+ * device, 16-byte aligned; calls are asynchronous on `stream`. */
 typedef struct dmc_dcb_train dmc_dcb_train;
 int dmc_dcb_train_create(int batch, int height, int width, int cin, int cout, int force_adaptor, int shortcut,
                          int has_quant_step, int terms, dmc_dcb_train** out);
@@ -196,8 +198,8 @@ const char* dmc_dcb_train_last_error(const dmc_dcb_train* t);
 int dmc_dcb_train_forward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
                           float* out, int weights_unchanged, void* stream);
 int dmc_dcb_train_backward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
-                           const float* grad_out, float* grad_x, float* const* grad_weights12, float* grad_quant_step,
-                           int weights_unchanged, void* stream);
+                           const float* out, const float* grad_out, float* grad_x, float* const* grad_weights12,
+                           float* grad_quant_step, int weights_unchanged, void* stream);
 /* AdaptiveQuant in training mode (layers/inference.py:16-27).  mode 0 "ste": out = round(x) (the straight-through
  * gradient is the identity); mode 1 "noise": out = x + noise with noise ~ U(-half_bin, half_bin) drawn by the caller. */
 int dmc_op_quant_train(const float* x, const float* noise, float* out, int64_t n, int mode, void* stream);

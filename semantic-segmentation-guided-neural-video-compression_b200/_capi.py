@@ -48,7 +48,7 @@ SIGNATURES = {
     "dmc_dcb_train_destroy": (None, [c_void_p]),
     "dmc_dcb_train_last_error": (c_char_p, [c_void_p]),
     "dmc_dcb_train_forward": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_int, c_void_p]),
-    "dmc_dcb_train_backward": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p,
+    "dmc_dcb_train_backward": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p,
                                        POINTER(c_void_p), c_void_p, c_int, c_void_p]),
     "dmc_op_quant_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "dmc_op_gaussian_bits_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,

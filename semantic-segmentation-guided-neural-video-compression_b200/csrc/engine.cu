@@ -1597,7 +1597,8 @@ struct dmc_dcb_train {
   float *w9c_flip = nullptr, *zero_bias = nullptr, *qs_table = nullptr, *part = nullptr;
   size_t part_floats = 0;
   // caller tensors of the current call (read by the launch closures)
-  const float *x = nullptr, *gout = nullptr;
+  const float *x = nullptr, *gout = nullptr, *yout = nullptr;
+  float* scale2 = nullptr;       // {gradient scale, its reciprocal}, written on the device at the start of every backward
   float *out = nullptr, *gx = nullptr, *gqs = nullptr;
   float* gw[12] = {};
 };
@@ -1677,9 +1678,10 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     t->zero_bias = e.new_f32((size_t)4 * C);
     CUDA_OK(cudaMemset(t->zero_bias, 0, sizeof(float) * 4 * C));
     t->qs_table = e.new_f32(C);
+    t->scale2 = e.new_f32(2);
     // partial sums: the largest of the weight-gradient splits, the column sums and the depthwise partial rows
     const int max_parts = 2 * num_sms();
-    size_t pf = (size_t)max_parts * 4 * C;
+    size_t pf = (size_t)2 * max_parts * 4 * C;
     pf = std::max(pf, (size_t)max_parts * C * 10);
     const int shapes[5][2] = {{C, cin}, {C, C}, {C, C}, {4 * C, C}, {C, 2 * C}};
     for (auto& sh : shapes) pf = std::max(pf, (size_t)wgrad_splits(M, sh[0], sh[1]) * sh[0] * sh[1]);
@@ -1705,13 +1707,15 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     float* t0 = e.new_f32((size_t)M * C);
     float* t1 = e.new_f32((size_t)M * C);
     float* u0 = e.new_f32((size_t)M * 4 * C);
+    float* gt2 = e.new_f32((size_t)M * C);
     Act t2 = e.new_act(B, H, W, C), o1 = e.new_act(B, H, W, C), v = e.new_act(B, H, W, 2 * C);
     Act g = e.new_act(B, H, W, C), gv = e.new_act(B, H, W, 2 * C), gu = e.new_act(B, H, W, 4 * C);
-    Act go1 = e.new_act(B, H, W, C), gt2 = e.new_act(B, H, W, C), gt1 = e.new_act(B, H, W, C), gt0 = e.new_act(B, H, W, C);
+    Act go1 = e.new_act(B, H, W, C), gt1 = e.new_act(B, H, W, C), gt0 = e.new_act(B, H, W, C);
     Act ga = e.new_act(B, H, W, C);
+    float* scale2 = t->scale2;
     EpiSpec plain;
     plain.nsplit = terms;
-    // recompute (the forward pass keeps nothing but x)
+    // recompute (the forward pass keeps nothing but x and its own output)
     e.op([self, xs, B, H, W, cin](cudaStream_t st) { nchw_to_s3(self->x, xs.v, B, cin, H, W, st); });
     if (ad) e.gemm(xs, t->blk->adaptor, &a, plain);
     {
@@ -1732,78 +1736,87 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
       s.out_f32 = u0; s.ld_f32 = 4 * C;
       e.gemm(o1, t->P_ffn0, nullptr, s);
     }
-    e.op([u0, v, M, C](cudaStream_t st) { chunkadd_fwd(u0, 4 * C, v.v, M, st); });
-    Act gcur = g;
-    e.op([self, g, B, H, W, C](cudaStream_t st) { nchw_to_s3(self->gout, g.v, B, C, H, W, st); });
-    if (t->has_qs) {
-      Act outpre = e.new_act(B, H, W, C), g2 = e.new_act(B, H, W, C);
-      EpiSpec s = plain;
-      s.res1 = &o1;
-      if (t->shortcut) s.res2 = &a;
-      e.gemm(v, t->blk->ffn2, &outpre, s);
-      e.op([self, g, outpre, g2, M, C, max_parts](cudaStream_t st) {
-        if (self->gqs) {
-          int S = colsum_s3(g.v, &outpre.v, M, self->part, C, max_parts, st);
-          reduce_partials(self->part, C, S, self->gqs, C, nullptr, 1.0f, st);
-        }
-        scale_cols(g.v, self->qs_table, g2.v, M, st);
-      });
-      gcur = g2;
-    }
-    // one weight + bias gradient: G [M, N] against the layer input X [M, K]
-    auto wgrad = [&](const Act& G, const Act& X, int iw) {
+    // the incoming gradient: power-of-two scale into fp16's range (everything below is linear in it), times quant_step
+    e.op([self, g, B, H, W, C, M, scale2, max_parts](cudaStream_t st) {
+      grad_scale(self->gout, M * C, 8.0f, self->part, scale2, st);
+      if (self->has_qs && self->gqs) {
+        // out = out_pre * quant_step  ->  d/d quant_step[c] = sum g * out_pre = (sum g * out) / quant_step[c]
+        if (!self->yout) fail("dmc_dcb_train_backward: the forward output is needed for grad_quant_step");
+        int S = nchw_dot(self->gout, self->yout, B, C, (long long)H * W, self->part, max_parts, st);
+        reduce_div(self->part, S, C, self->qs_table, self->gqs, st);
+      }
+      nchw_to_s3_scaled(self->gout, g.v, B, C, H, W, self->has_qs ? self->qs_table : nullptr, scale2, st);
+    });
+    // one weight + bias gradient: G [M, N] against the layer input X [M, K]; `bias_done`: the column sums of G were
+    // already reduced by the kernel that produced G
+    auto wgrad = [&](const Act& G, const Act& X, int iw, bool bias_done) {
       const int terms_ = terms;
-      e.op([self, G, X, M, iw, terms_, max_parts](cudaStream_t st) {
+      e.op([self, G, X, M, iw, terms_, max_parts, bias_done, scale2](cudaStream_t st) {
         const int N = G.v.C, K = X.v.C;
         if (self->gw[iw]) {
           int S = wgrad_s3(G.v, X.v, M, terms_, self->part, st);
           if (S < 1) fail("weight gradient launch: %s", wgrad_umma_last_error());
-          reduce_partials(self->part, (long long)N * K, S, self->gw[iw], (long long)N * K, nullptr, 1.0f, st);
+          reduce_partials(self->part, (long long)N * K, S, self->gw[iw], (long long)N * K, scale2 + 1, 1.0f, st);
         }
-        if (self->gw[iw + 1]) {
+        if (self->gw[iw + 1] && !bias_done) {
           int S = colsum_s3(G.v, nullptr, M, self->part, N, max_parts, st);
-          reduce_partials(self->part, N, S, self->gw[iw + 1], N, nullptr, 1.0f, st);
+          reduce_partials(self->part, N, S, self->gw[iw + 1], N, scale2 + 1, 1.0f, st);
         }
       });
     };
-    // ffn.2
-    wgrad(gcur, v, 10);
-    e.gemm(gcur, t->T_ffn2, &gv, plain);
-    e.op([gv, u0, gu, M, C](cudaStream_t st) { chunkadd_bwd(gv.v, u0, 4 * C, gu.v, M, st); });
+    // ffn.2: data gradient first, then ONE pass over the pre-activations gives v (operand of ffn.2's weight gradient),
+    // the gradient of the pre-activations and ffn.0's bias gradient
+    e.gemm(g, t->T_ffn2, &gv, plain);
+    e.op([self, u0, gv, v, gu, M, C, max_parts, scale2](cudaStream_t st) {
+      int S = chunkadd_fwd_bwd(u0, 4 * C, gv.v, v.v, gu.v, M, self->part, 4 * C, 2 * max_parts, st);
+      if (self->gw[9]) reduce_partials(self->part, 4 * C, S, self->gw[9], 4 * C, scale2 + 1, 1.0f, st);
+    });
+    wgrad(g, v, 10, false);
     // ffn.0 (+ the residual around the ffn)
-    wgrad(gu, o1, 8);
+    wgrad(gu, o1, 8, true);
     {
       EpiSpec s = plain;
-      s.res1 = &gcur;
+      s.res1 = &g;
       e.gemm(gu, t->T_ffn0, &go1, s);
     }
-    // dc.3
-    wgrad(go1, t2, 6);
-    e.gemm(go1, t->T_dc3, &gt2, plain);
+    // dc.3: its data gradient feeds the depthwise kernels only -> fp32 rows
+    wgrad(go1, t2, 6, false);
+    {
+      EpiSpec s = plain;
+      s.out_f32 = gt2; s.ld_f32 = C;
+      e.gemm(go1, t->T_dc3, nullptr, s);
+    }
     // depthwise 3x3
-    e.op([self, gt2, gt1, t1, C, B, H, W, max_parts](cudaStream_t st) {
-      dwconv3x3(gt2.v, self->w9c_flip, self->zero_bias, gt1.v, B, H, W, st);
+    e.op([self, gt2, gt1, t1, C, B, H, W, max_parts, scale2](cudaStream_t st) {
+      dwconv3x3_f32(gt2, C, self->w9c_flip, self->zero_bias, gt1.v, B, H, W, st);
       if (self->gw[4] || self->gw[5]) {
-        int S = dw_wgrad(gt2.v, t1, C, B, H, W, self->part, C * 10, max_parts, st);
-        reduce_dw(self->part, C * 10, S, self->gw[4], self->gw[5], C, 1.0f, st);
+        int S = dw_wgrad(gt2, C, C, t1, C, B, H, W, self->part, C * 10, max_parts, st);
+        reduce_dw(self->part, C * 10, S, self->gw[4], self->gw[5], C, scale2 + 1, 1.0f, st);
       }
     });
-    e.op([gt1, t0, gt0, M, C](cudaStream_t st) { wsilu_bwd(gt1.v, t0, C, gt0.v, M, st); });
+    e.op([self, gt1, t0, gt0, M, C, max_parts, scale2](cudaStream_t st) {
+      int S = wsilu_bwd(gt1.v, t0, C, gt0.v, M, self->part, C, 2 * max_parts, st);
+      if (self->gw[3]) reduce_partials(self->part, C, S, self->gw[3], C, scale2 + 1, 1.0f, st);
+    });
     // dc.0 (+ the residual around dc, + the shortcut)
-    wgrad(gt0, a, 2);
+    wgrad(gt0, a, 2, true);
     {
       EpiSpec s = plain;
       s.res1 = &go1;
-      if (t->shortcut) s.res2 = &gcur;
+      if (t->shortcut) s.res2 = &g;
       e.gemm(gt0, t->T_dc0, &ga, s);
     }
     if (ad) {
       Act gxs = e.new_act(B, H, W, cin);
-      wgrad(ga, xs, 0);
+      wgrad(ga, xs, 0, false);
       e.gemm(ga, t->T_ad, &gxs, plain);
-      e.op([self, gxs, B, H, W, cin](cudaStream_t st) { if (self->gx) s3_to_nchw(gxs.v, self->gx, B, cin, H, W, st); });
+      e.op([self, gxs, B, H, W, cin, scale2](cudaStream_t st) {
+        if (self->gx) s3_to_nchw_scaled(gxs.v, self->gx, B, cin, H, W, scale2 + 1, st);
+      });
     } else {
-      e.op([self, ga, B, H, W, C](cudaStream_t st) { if (self->gx) s3_to_nchw(ga.v, self->gx, B, C, H, W, st); });
+      e.op([self, ga, B, H, W, C, scale2](cudaStream_t st) {
+        if (self->gx) s3_to_nchw_scaled(ga.v, self->gx, B, C, H, W, scale2 + 1, st);
+      });
     }
     e.flush_chain();
     e.prog = &e.prog_common;
@@ -1846,15 +1859,18 @@ extern "C" int dmc_dcb_train_forward(dmc_dcb_train* t, const float* x, const flo
 }
 
 extern "C" int dmc_dcb_train_backward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
-                                      const float* grad_out, float* grad_x, float* const* grad_weights12,
-                                      float* grad_quant_step, int weights_unchanged, void* stream) {
+                                      const float* out, const float* grad_out, float* grad_x,
+                                      float* const* grad_weights12, float* grad_quant_step, int weights_unchanged,
+                                      void* stream) {
   if (!t) return DMC_E_INVALID;
   return guarded(&t->e, [&] {
     if (!x || !grad_out) fail("dmc_dcb_train_backward: null tensor");
     DeviceGuard dg(t->e.device);
     cudaStream_t st = (cudaStream_t)stream;
     dcb_train_load(*t, weights12, quant_step, true, weights_unchanged != 0, st);
-    t->x = x; t->gout = grad_out; t->gx = grad_x; t->gqs = t->has_qs ? grad_quant_step : nullptr;
+    t->x = x; t->gout = grad_out; t->yout = out; t->gx = grad_x; t->gqs = t->has_qs ? grad_quant_step : nullptr;
+    if (t->gqs && !out) fail("dmc_dcb_train_backward: `out` (the forward output) is required for grad_quant_step");
+    if (((uintptr_t)grad_out | (uintptr_t)x) % 16) fail("dmc_dcb_train_backward: tensors must be 16-byte aligned");
     for (int i = 0; i < 12; ++i) t->gw[i] = grad_weights12 ? grad_weights12[i] : nullptr;
     if (!t->blk->adaptor) t->gw[0] = t->gw[1] = nullptr;
     t->e.cur.qp = 0;

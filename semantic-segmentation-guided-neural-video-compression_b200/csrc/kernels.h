@@ -197,18 +197,31 @@ void mask_from_logits(const float* logits, float* mask, long long n, cudaStream_
 
 // ---------------- training mode (train.cu) ----------------
 void wsilu_rows(const float* in, float* out, long long n, cudaStream_t st);                       // fp32 rows, n % 4 == 0
-void wsilu_bwd(View g, const float* pre, int ld, View out, long long M, cudaStream_t st);         // g * wsilu'(pre)
+// out = g * wsilu'(pre) + per-block column sums of out; returns the number of partial rows
+int wsilu_bwd(View g, const float* pre, int ld, View out, long long M, float* part, int ldp, int max_parts, cudaStream_t st);
 void chunkadd_fwd(const float* u, int ld, View v, long long M, cudaStream_t st);                  // layers.py:12-20
 void chunkadd_bwd(View gv, const float* u, int ld, View gu, long long M, cudaStream_t st);
+// forward value v, pre-activation gradient gu and gu's per-block column sums in one pass; returns the number of partial rows
+int chunkadd_fwd_bwd(const float* u, int ld, View gv, View v, View gu, long long M, float* part, int ldp, int max_parts,
+                     cudaStream_t st);
 void transpose_f32(const float* src, float* dst, int R, int C, cudaStream_t st);
 // column sums of g (times h, element by element, when h != nullptr) as per-block partial rows; returns their number
 int colsum_s3(View g, const View* h, long long M, float* part, int ldp, int max_parts, cudaStream_t st);
 void reduce_partials(const float* part, long long stride, int S, float* out, long long n, const float* scale_dev,
                      float scale, cudaStream_t st);
 // depthwise 3x3 weight (C,1,3,3) + bias gradient as partial rows of C * 10 floats ([c][tap], tap 9 = bias)
-int dw_wgrad(View g, const float* t, int ld, int B, int H, int W, float* part, int ldp, int max_parts, cudaStream_t st);
+int dw_wgrad(const float* g, int ldg, int C, const float* t, int ld, int B, int H, int W, float* part, int ldp, int max_parts,
+             cudaStream_t st);
 void flip_dw_weight(const float* w9c, float* out, int C, cudaStream_t st);
-void reduce_dw(const float* part, long long stride, int S, float* gw, float* gb, int C, float scale, cudaStream_t st);
+void reduce_dw(const float* part, long long stride, int S, float* gw, float* gb, int C, const float* scale_dev, float scale,
+               cudaStream_t st);
+// scale2 = {2^floor(peak_log2 - log2 max|g|), its reciprocal}; part: 2 * num_sms() floats of scratch
+void grad_scale(const float* g, long long n, float peak_log2, float* part, float* scale2, cudaStream_t st);
+void nchw_to_s3_scaled(const float* x, View out, int B, int C, int H, int W, const float* chan, const float* gscale,
+                       cudaStream_t st);
+void s3_to_nchw_scaled(View in, float* x, int B, int C, int H, int W, const float* gscale, cudaStream_t st);
+int nchw_dot(const float* a, const float* b, int B, int C, long long HW, float* part, int max_parts, cudaStream_t st);
+void reduce_div(const float* part, int S, int C, const float* div, float* out, cudaStream_t st);
 // dW[n][k] = sum_m G[m][n] X[m][k] as wgrad_splits() partial matrices of N * K floats (terms: 3 = fp32-grade split product)
 int wgrad_splits(long long M, int N, int K);
 // tcgen05 version (wgrad_umma.cu); wgrad_s3 routes to it unless DMC_WGRAD_UMMA=0

@@ -43,25 +43,53 @@ void wsilu_rows(const float* in, float* out, long long n, cudaStream_t st) {
   launch(k_wsilu_rows, cdiv_u(n / 4, 256), 256, 0, st, in, out, n / 4);
 }
 
-// out[m, c] = g[m, c] * wsilu'(pre[m, c]);   g, out: split planes [M, C];  pre: fp32 rows [M, ld]
-__global__ void k_wsilu_bwd(View g, const float* __restrict__ pre, int ld, View out, long long M, int C8) {
+// out[m, c] = g[m, c] * wsilu'(pre[m, c]);   g, out: split planes [M, C];  pre: fp32 rows [M, ld];
+// part[block][c] = the block's column sums of out (dc.0's bias gradient).  Persistent grid, 8 columns per thread.
+__global__ void __launch_bounds__(256) k_wsilu_bwd(View g, const float* __restrict__ pre, int ld, View out, long long M, int C8,
+                                                   float* __restrict__ part, int ldp) {
   pdl_prologue_done();
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * C8) return;
-  const long long m = idx / C8;
-  const int c = (int)(idx % C8) * 8;
-  float v[8];
-  ld3x8(g, m, c, v);
-  const float4 p0 = *reinterpret_cast<const float4*>(pre + m * ld + c);
-  const float4 p1 = *reinterpret_cast<const float4*>(pre + m * ld + c + 4);
-  const float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+  extern __shared__ float red[];        // [lanes][C8 * 8]
+  const int lanes = blockDim.x / C8;
+  const int c8 = threadIdx.x % C8, rl = threadIdx.x / C8;
+  const int c = c8 * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rl < lanes) {
+    for (long long m = (long long)blockIdx.x * lanes + rl; m < M; m += (long long)gridDim.x * lanes) {
+      float v[8];
+      ld3x8(g, m, c, v);
+      const float4 p0 = *reinterpret_cast<const float4*>(pre + m * ld + c);
+      const float4 p1 = *reinterpret_cast<const float4*>(pre + m * ld + c + 4);
+      const float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] *= wsilu_grad(p[i]);
-  st3x8(out, m, c, v);
+      for (int i = 0; i < 8; ++i) {
+        v[i] *= wsilu_grad(p[i]);
+        acc[i] += v[i];
+      }
+      st3x8(out, m, c, v);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[(rl * C8 + c8) * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < C8 * 8; j += blockDim.x) {
+    float s = 0.0f;
+    for (int r = 0; r < lanes; ++r) s += red[r * C8 * 8 + j];
+    part[(long long)blockIdx.x * ldp + j] = s;
+  }
 }
-void wsilu_bwd(View g, const float* pre, int ld, View out, long long M, cudaStream_t st) {
+int wsilu_bwd(View g, const float* pre, int ld, View out, long long M, float* part, int ldp, int max_parts, cudaStream_t st) {
   const int C8 = g.C / 8;
-  launch(k_wsilu_bwd, cdiv_u(M * C8, 256), 256, 0, st, g, pre, ld, out, M, C8);
+  int threads = 256;
+  if (C8 > threads) threads = (C8 + 31) / 32 * 32;
+  const int lanes = threads / C8;
+  int blocks = (int)((M + lanes - 1) / lanes);
+  const int want = 4 * num_sms();
+  if (blocks > want) blocks = want;
+  if (blocks > max_parts) blocks = max_parts;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = (size_t)lanes * C8 * 8 * sizeof(float);
+  launch(k_wsilu_bwd, blocks, threads, smem, st, g, pre, ld, out, M, C8, part, ldp);
+  return blocks;
 }
 
 // WSiLUChunkAdd (layers.py:12-20) from the fp32 pre-activations [M, 2*C2]:  v[m, j] = wsilu(u[m, j]) + wsilu(u[m, j + C2])
@@ -115,6 +143,80 @@ __global__ void k_chunkadd_bwd(View gv, const float* __restrict__ u, int ld, Vie
 void chunkadd_bwd(View gv, const float* u, int ld, View gu, long long M, cudaStream_t st) {
   const int C2 = gv.C;
   launch(k_chunkadd_bwd, cdiv_u(M * (C2 / 8), 256), 256, 0, st, gv, u, ld, gu, M, C2);
+}
+
+// The two directions of WSiLUChunkAdd in one pass over the pre-activations u [M, 2*C2] (fp32 rows):
+//   v[m, j]  = wsilu(u[m, j]) + wsilu(u[m, j + C2])              (the recomputed forward value, operand of ffn.2's dW)
+//   gu[m, j] = gv[m, j mod C2] * wsilu'(u[m, j])                 (gradient of the pre-activations)
+//   part[block][j] = sum over the block's rows of gu[m, j]       (ffn.0's bias gradient, reduced by k_reduce_partials)
+// Persistent grid: a thread owns 8 columns (of both halves) and walks rows.
+__global__ void __launch_bounds__(256) k_chunkadd_fwd_bwd(const float* __restrict__ u, int ld, View gv, View v, View gu,
+                                                          long long M, int C2, float* __restrict__ part, int ldp) {
+  pdl_prologue_done();
+  extern __shared__ float red[];        // [lanes][2 * C2]
+  const int C8 = C2 / 8;
+  const int lanes = blockDim.x / C8;
+  const int c8 = threadIdx.x % C8, rl = threadIdx.x / C8;
+  const int c = c8 * 8;
+  float acc[2][8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[h][i] = 0.0f;
+  if (rl < lanes) {
+    for (long long m = (long long)blockIdx.x * lanes + rl; m < M; m += (long long)gridDim.x * lanes) {
+      float g[8], o[8];
+      ld3x8(gv, m, c, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = 0.0f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const float* q = u + m * ld + half * C2 + c;
+        const float4 p0 = *reinterpret_cast<const float4*>(q);
+        const float4 p1 = *reinterpret_cast<const float4*>(q + 4);
+        const float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        float d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // one exponential for the value and the derivative: s = sigmoid(4p); wsilu = p * s; wsilu' = s * (1 + 4p(1 - s))
+          const float t = 4.0f * p[i];
+          const float sg = 1.0f / (1.0f + expf(-t));
+          o[i] += p[i] * sg;
+          d[i] = g[i] * (sg * fmaf(t, 1.0f - sg, 1.0f));
+          acc[half][i] += d[i];
+        }
+        st3x8(gu, m, half * C2 + c, d);
+      }
+      st3x8(v, m, c, o);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[(long long)rl * 2 * C2 + h * C2 + c + i] = acc[h][i];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * C2; j += blockDim.x) {
+    float s = 0.0f;
+    for (int r = 0; r < lanes; ++r) s += red[(long long)r * 2 * C2 + j];
+    part[(long long)blockIdx.x * ldp + j] = s;
+  }
+}
+// returns the number of partial rows (2 * C2 floats each, pitch ldp)
+int chunkadd_fwd_bwd(const float* u, int ld, View gv, View v, View gu, long long M, float* part, int ldp, int max_parts,
+                     cudaStream_t st) {
+  const int C2 = gv.C, C8 = C2 / 8;
+  int threads = 256;
+  if (C8 > threads) threads = (C8 + 31) / 32 * 32;
+  const int lanes = threads / C8;
+  int blocks = (int)((M + lanes - 1) / lanes);
+  const int want = 4 * num_sms();
+  if (blocks > want) blocks = want;
+  if (blocks > max_parts) blocks = max_parts;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = (size_t)lanes * 2 * C2 * sizeof(float);
+  cudaFuncSetAttribute(k_chunkadd_fwd_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  launch(k_chunkadd_fwd_bwd, blocks, threads, smem, st, u, ld, gv, v, gu, M, C2, part, ldp);
+  return blocks;
 }
 
 // dst[c][r] = src[r][c]  (fp32; weights of a 1x1 convolution -> the weight of its data gradient)
@@ -226,10 +328,10 @@ void reduce_partials(const float* part, long long stride, int S, float* out, lon
 
 // ------------------------------------------------------------------ depthwise 3x3: weight / bias gradient
 // dW[c][ky][kx] = sum_{b,h,w} g[b,h,w,c] * t[b,h+ky-1,w+kx-1,c]  (zero outside), db[c] = sum g.
-// g: split planes [M, C]; t: fp32 rows [M, ld] (the WSiLU output the forward conv read).
+// g: fp32 rows [M, ldg] (what dc.3's data gradient writes); t: fp32 rows [M, ld] (the WSiLU output the forward conv read).
 // Thread = 8 channels x one pixel lane; part[block][c*10 + tap] (tap 9 = bias).
-__global__ void __launch_bounds__(256) k_dw_wgrad(View g, const float* __restrict__ t, int ld, int B, int H, int W, int C8,
-                                                  float* __restrict__ part, int ldp) {
+__global__ void __launch_bounds__(256) k_dw_wgrad(const float* __restrict__ g, int ldg, const float* __restrict__ t, int ld, int B,
+                                                  int H, int W, int C8, float* __restrict__ part, int ldp) {
   pdl_prologue_done();
   extern __shared__ float red[];        // [lanes][C8*8*10]
   const int lanes = blockDim.x / C8;
@@ -244,8 +346,9 @@ __global__ void __launch_bounds__(256) k_dw_wgrad(View g, const float* __restric
     for (long long m = (long long)blockIdx.x * lanes + rl; m < M; m += (long long)gridDim.x * lanes) {
       const int w = (int)(m % W);
       const int h = (int)((m / W) % H);
-      float gv[8];
-      ld3x8(g, m, c8 * 8, gv);
+      const float4 g0 = *reinterpret_cast<const float4*>(g + m * ldg + c8 * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(g + m * ldg + c8 * 8 + 4);
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[9][i] += gv[i];
 #pragma unroll
@@ -279,8 +382,9 @@ __global__ void __launch_bounds__(256) k_dw_wgrad(View g, const float* __restric
     part[(long long)blockIdx.x * ldp + j] = s;
   }
 }
-int dw_wgrad(View g, const float* t, int ld, int B, int H, int W, float* part, int ldp, int max_parts, cudaStream_t st) {
-  const int C8 = g.C / 8;
+int dw_wgrad(const float* g, int ldg, int C, const float* t, int ld, int B, int H, int W, float* part, int ldp, int max_parts,
+             cudaStream_t st) {
+  const int C8 = C / 8;
   int threads = 256;
   int lanes = threads / C8;
   if (lanes < 1) { lanes = 1; threads = (C8 + 31) / 32 * 32; }
@@ -293,7 +397,7 @@ int dw_wgrad(View g, const float* t, int ld, int B, int H, int W, float* part, i
   if (blocks > want) blocks = want;
   if (blocks > max_parts) blocks = max_parts;
   if (blocks < 1) blocks = 1;
-  launch(k_dw_wgrad, blocks, threads, smem, st, g, t, ld, B, H, W, C8, part, ldp);
+  launch(k_dw_wgrad, blocks, threads, smem, st, g, ldg, t, ld, B, H, W, C8, part, ldp);
   return blocks;
 }
 
@@ -309,8 +413,9 @@ void flip_dw_weight(const float* w9c, float* out, int C, cudaStream_t st) { laun
 
 // partial rows of dw_wgrad -> weight gradient (C,1,3,3) and bias gradient (C); either destination may be null
 __global__ void __launch_bounds__(256) k_reduce_dw(const float* __restrict__ part, long long stride, int S, float* gw, float* gb,
-                                                   int C, float scale) {
+                                                   int C, const float* __restrict__ scale_dev, float scale) {
   pdl_prologue_done();
+  if (scale_dev) scale *= *scale_dev;
   __shared__ float red[8][33];
   const int col = threadIdx.x & 31, lane = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + col;
@@ -327,8 +432,9 @@ __global__ void __launch_bounds__(256) k_reduce_dw(const float* __restrict__ par
   if (tap < 9) { if (gw) gw[c * 9 + tap] = t * scale; }
   else if (gb) gb[c] = t * scale;
 }
-void reduce_dw(const float* part, long long stride, int S, float* gw, float* gb, int C, float scale, cudaStream_t st) {
-  launch(k_reduce_dw, cdiv_u(C * 10, 32), 256, 0, st, part, stride, S, gw, gb, C, scale);
+void reduce_dw(const float* part, long long stride, int S, float* gw, float* gb, int C, const float* scale_dev, float scale,
+               cudaStream_t st) {
+  launch(k_reduce_dw, cdiv_u(C * 10, 32), 256, 0, st, part, stride, S, gw, gb, C, scale_dev, scale);
 }
 
 // ------------------------------------------------------------------ weight gradient of a 1x1 convolution
@@ -513,6 +619,143 @@ int wgrad_s3(View G, View X, long long M, int terms, float* part, cudaStream_t s
   if (terms == 1) launch(k_wgrad_s3<1>, grid, 256, smem, st, G, X, N, K, chunks, per, part);
   else launch(k_wgrad_s3<3>, grid, 256, smem, st, G, X, N, K, chunks, per, part);
   return S;
+}
+
+
+// ------------------------------------------------------------------ gradient scale, boundary conversions
+// scale2[0] = 2^floor(peak_log2 - log2(max |g|)) (1 when g is all zero or not finite), scale2[1] = 1 / scale2[0]:
+// the incoming gradient enters the fp16 split planes multiplied by scale2[0], every result leaves multiplied by scale2[1].
+__global__ void __launch_bounds__(256) k_absmax_part(const float* __restrict__ g, long long n4, float* __restrict__ part) {
+  pdl_prologue_done();
+  float m = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(g)[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void k_grad_scale(const float* __restrict__ part, int n, const float* __restrict__ tail, int ntail, float peak_log2,
+                             float* __restrict__ scale2) {
+  pdl_prologue_done();
+  __shared__ float red[256];
+  float m = 0.0f;
+  for (int i = threadIdx.x; i < n; i += 256) m = fmaxf(m, part[i]);
+  for (int i = threadIdx.x; i < ntail; i += 256) m = fmaxf(m, fabsf(tail[i]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float a = red[0];
+    float s = 1.0f;
+    if (a > 0.0f && a < 3.0e38f) s = exp2f(fminf(fmaxf(floorf(peak_log2 - log2f(a)), -100.0f), 100.0f));
+    scale2[0] = s;
+    scale2[1] = 1.0f / s;
+  }
+}
+void grad_scale(const float* g, long long n, float peak_log2, float* part, float* scale2, cudaStream_t st) {
+  const long long n4 = n / 4;
+  int blocks = (int)std::min<long long>((n4 + 255) / 256, 2LL * num_sms());
+  if (blocks < 1) blocks = 1;
+  launch(k_absmax_part, blocks, 256, 0, st, g, n4, part);
+  launch(k_grad_scale, 1, 256, 0, st, (const float*)part, blocks, g + n4 * 4, (int)(n - n4 * 4), peak_log2, scale2);
+}
+
+// NCHW fp32 -> split planes, times chan[c] (or 1) times *gscale (or 1).  Thread = (pixel, 8 channels), pixel fastest.
+__global__ void k_nchw_to_s3_scaled(const float* __restrict__ x, View out, int C, long long HW, const float* __restrict__ chan,
+                                    const float* __restrict__ gscale) {
+  pdl_prologue_done();
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const int c8 = blockIdx.y, b = blockIdx.z;
+  const float gs = gscale ? *gscale : 1.0f;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c8 * 8 + i;
+    v[i] = (c < C) ? x[((long long)b * C + c) * HW + p] * (chan ? chan[c] * gs : gs) : 0.0f;
+  }
+  st3x8(out, (long long)b * HW + p, c8 * 8, v);
+}
+void nchw_to_s3_scaled(const float* x, View out, int B, int C, int H, int W, const float* chan, const float* gscale,
+                       cudaStream_t st) {
+  const long long HW = (long long)H * W;
+  dim3 grid(cdiv_u(HW, 256), (C + 7) / 8, B);
+  launch(k_nchw_to_s3_scaled, grid, 256, 0, st, x, out, C, HW, chan, gscale);
+}
+__global__ void k_s3_to_nchw_scaled(View in, float* __restrict__ x, int C, long long HW, const float* __restrict__ gscale) {
+  pdl_prologue_done();
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const int c8 = blockIdx.y, b = blockIdx.z;
+  const float gs = gscale ? *gscale : 1.0f;
+  float v[8];
+  ld3x8(in, (long long)b * HW + p, c8 * 8, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c8 * 8 + i;
+    if (c < C) x[((long long)b * C + c) * HW + p] = v[i] * gs;
+  }
+}
+void s3_to_nchw_scaled(View in, float* x, int B, int C, int H, int W, const float* gscale, cudaStream_t st) {
+  const long long HW = (long long)H * W;
+  dim3 grid(cdiv_u(HW, 256), (C + 7) / 8, B);
+  launch(k_s3_to_nchw_scaled, grid, 256, 0, st, in, x, C, HW, gscale);
+}
+
+// part[chunk][c] = sum over the chunk's pixels (all batch items) of a[b,c,p] * b_[b,c,p]   (NCHW fp32 both)
+__global__ void __launch_bounds__(256) k_nchw_dot(const float* __restrict__ a, const float* __restrict__ b_, int B, int C,
+                                                  long long HW, long long per, float* __restrict__ part) {
+  pdl_prologue_done();
+  const int c = blockIdx.x;
+  const long long p0 = (long long)blockIdx.y * per;
+  long long p1 = p0 + per;
+  if (p1 > HW) p1 = HW;
+  float s = 0.0f;
+  for (int b = 0; b < B; ++b) {
+    const float* pa = a + ((long long)b * C + c) * HW;
+    const float* pb = b_ + ((long long)b * C + c) * HW;
+    for (long long p = p0 + threadIdx.x; p < p1; p += 256) s = fmaf(pa[p], pb[p], s);
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[(long long)blockIdx.y * C + c] = red[0];
+}
+// returns the number of partial rows (C floats each)
+int nchw_dot(const float* a, const float* b, int B, int C, long long HW, float* part, int max_parts, cudaStream_t st) {
+  int chunks = (int)std::min<long long>((HW + 2047) / 2048, (2LL * num_sms() + C - 1) / C);
+  if (chunks > max_parts) chunks = max_parts;
+  if (chunks < 1) chunks = 1;
+  const long long per = (HW + chunks - 1) / chunks;
+  chunks = (int)((HW + per - 1) / per);
+  launch(k_nchw_dot, dim3(C, chunks), 256, 0, st, a, b, B, C, HW, per, part);
+  return chunks;
+}
+// out[c] = sum_s part[s][c] / div[c]  (0 where div is 0)
+__global__ void k_reduce_div(const float* __restrict__ part, int S, int C, const float* __restrict__ div, float* __restrict__ out) {
+  pdl_prologue_done();
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.0f;
+  for (int k = 0; k < S; ++k) s += part[(long long)k * C + c];
+  out[c] = div[c] != 0.0f ? s / div[c] : 0.0f;
+}
+void reduce_div(const float* part, int S, int C, const float* div, float* out, cudaStream_t st) {
+  launch(k_reduce_div, cdiv_u(C, 256), 256, 0, st, part, S, C, div, out);
 }
 
 // ------------------------------------------------------------------ quantisation / likelihood, training mode

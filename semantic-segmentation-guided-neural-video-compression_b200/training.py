@@ -32,8 +32,6 @@ __all__ = ["DepthConvBlock", "AdaptiveQuant", "depth_conv_block", "gaussian_bits
 #: DepthConvBlock handles kept alive -- one per (owner module, geometry), each with its own workspace (~1.2 GB at
 #: 160x240x256, 1/4 of that per halving of the resolution) and packed weights; least recently used first out
 max_handles = 64
-#: incoming gradients are scaled so that max |g| = 2^GRAD_LOG2_PEAK before they enter the fp16 split planes
-GRAD_LOG2_PEAK = 8
 
 _handles: "OrderedDict[tuple, int]" = OrderedDict()
 _packed_sig: dict = {}        # handle key -> signature of the parameter values the handle has packed
@@ -134,7 +132,9 @@ class _DepthConvBlockFn(torch.autograd.Function):
             _check(lib.dmc_dcb_train_forward(h, _ptr(x), _ptr_array(ws), _ptr(qs), _ptr(out), unchanged,
                                              _stream(x.device)), h)
         _packed_sig[key] = sig
-        ctx.save_for_backward(x, quant_step, *[w for w in w12 if w is not None])
+        # (the output is kept only when quant_step needs a gradient: d out / d quant_step = out / quant_step)
+        keep_out = quant_step is not None and ctx.needs_input_grad[1]
+        ctx.save_for_backward(x, quant_step, out if keep_out else None, *[w for w in w12 if w is not None])
         ctx.meta = (has_ad, bool(shortcut), terms, quant_step is not None, owner, sig)
         return out
 
@@ -142,8 +142,8 @@ class _DepthConvBlockFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         has_ad, shortcut, terms, has_qs, owner, sig = ctx.meta
         saved = ctx.saved_tensors
-        x, quant_step = saved[0], saved[1]
-        w12 = list(saved[2:])
+        x, quant_step, out = saved[0], saved[1], saved[2]
+        w12 = list(saved[3:])
         if not has_ad:
             w12 = [None, None] + w12
         lib = _capi.load()
@@ -151,11 +151,7 @@ class _DepthConvBlockFn(torch.autograd.Function):
         cout = w12[2].shape[0]
         ws = [None if w is None else w.detach().contiguous().float() for w in w12]
         qs = quant_step.detach().reshape(cout).contiguous().float() if has_qs else None
-        # power-of-two scale into fp16's range; everything downstream is linear in the gradient
-        g = grad_out.contiguous().float()
-        amax = g.abs().amax().clamp_min(1e-30)
-        scale = torch.exp2(torch.floor(GRAD_LOG2_PEAK - torch.log2(amax)))
-        g = g * scale
+        g = grad_out.contiguous().float()       # (scaled into fp16's range inside the engine)
         need = ctx.needs_input_grad            # (x, quant_step, shortcut, terms, owner, *w12)
         gx = torch.empty_like(x) if need[0] else None
         sizes = [0 if (w is None or not need[5 + i]) else w.numel() for i, w in enumerate(w12)]
@@ -169,13 +165,9 @@ class _DepthConvBlockFn(torch.autograd.Function):
         key, h = _handle(owner, x.device, B, H, W, cin, cout, has_ad, shortcut, has_qs, terms)
         unchanged = int(_packed_sig.get(key) == sig)      # (autograd itself refuses saved tensors modified in place)
         with torch.cuda.device(x.device):
-            _check(lib.dmc_dcb_train_backward(h, _ptr(x), _ptr_array(ws), _ptr(qs), _ptr(g), _ptr(gx), _ptr_array(gws),
-                                              _ptr(gqs), unchanged, _stream(x.device)), h)
+            _check(lib.dmc_dcb_train_backward(h, _ptr(x), _ptr_array(ws), _ptr(qs), _ptr(out), _ptr(g), _ptr(gx),
+                                              _ptr_array(gws), _ptr(gqs), unchanged, _stream(x.device)), h)
         _packed_sig[key] = sig
-        inv = 1.0 / scale
-        flat.mul_(inv)
-        if gx is not None:
-            gx.mul_(inv)
         grads_w = [None if gw is None else gw.view_as(w) for gw, w in zip(gws, w12)]
         g_qs = gqs.view_as(quant_step) if gqs is not None else None
         return (gx, g_qs, None, None, None, *grads_w)
