@@ -1604,6 +1604,15 @@ struct dmc_dcb_train {
 };
 
 namespace {
+// the incoming gradient is scaled so that max |g| = 2^this before it enters the fp16 split planes
+float grad_peak_log2() {
+  static float v = -1000.0f;
+  if (v < -999.0f) {
+    const char* e = getenv("DMC_TRAIN_GRAD_PEAK_LOG2");
+    v = e ? (float)atof(e) : 8.0f;
+  }
+  return v;
+}
 const char* const kDcbNames[6] = {"b.adaptor", "b.dc.0", "b.dc.2", "b.dc.3", "b.ffn.0", "b.ffn.2"};
 
 // Packs the caller's parameters for the forward program (`backward` false) or for both.  With `unchanged` set the
@@ -1681,7 +1690,8 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     t->scale2 = e.new_f32(2);
     // partial sums: the largest of the weight-gradient splits, the column sums and the depthwise partial rows
     const int max_parts = 2 * num_sms();
-    size_t pf = (size_t)2 * max_parts * 4 * C;
+    const int ca_parts = chunkadd_parts(M, 2 * C);
+    size_t pf = (size_t)std::max(2 * max_parts, ca_parts) * 4 * C;
     pf = std::max(pf, (size_t)max_parts * C * 10);
     const int shapes[5][2] = {{C, cin}, {C, C}, {C, C}, {4 * C, C}, {C, 2 * C}};
     for (auto& sh : shapes) pf = std::max(pf, (size_t)wgrad_splits(M, sh[0], sh[1]) * sh[0] * sh[1]);
@@ -1738,7 +1748,7 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     }
     // the incoming gradient: power-of-two scale into fp16's range (everything below is linear in it), times quant_step
     e.op([self, g, B, H, W, C, M, scale2, max_parts](cudaStream_t st) {
-      grad_scale(self->gout, M * C, 8.0f, self->part, scale2, st);
+      grad_scale(self->gout, M * C, grad_peak_log2(), self->part, scale2, st);
       if (self->has_qs && self->gqs) {
         // out = out_pre * quant_step  ->  d/d quant_step[c] = sum g * out_pre = (sum g * out) / quant_step[c]
         if (!self->yout) fail("dmc_dcb_train_backward: the forward output is needed for grad_quant_step");
@@ -1767,8 +1777,9 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     // ffn.2: data gradient first, then ONE pass over the pre-activations gives v (operand of ffn.2's weight gradient),
     // the gradient of the pre-activations and ffn.0's bias gradient
     e.gemm(g, t->T_ffn2, &gv, plain);
-    e.op([self, u0, gv, v, gu, M, C, max_parts, scale2](cudaStream_t st) {
-      int S = chunkadd_fwd_bwd(u0, 4 * C, gv.v, v.v, gu.v, M, self->part, 4 * C, 2 * max_parts, st);
+    e.op([self, u0, gv, v, gu, M, C, ca_parts, scale2](cudaStream_t st) {
+      int S = chunkadd_fwd_bwd(u0, 4 * C, gv.v, v.v, gu.v, M, self->part, 4 * C, ca_parts, st);
+      if (S < 1) fail("chunkadd_fwd_bwd: partial buffer too small");
       if (self->gw[9]) reduce_partials(self->part, 4 * C, S, self->gw[9], 4 * C, scale2 + 1, 1.0f, st);
     });
     wgrad(g, v, 10, false);

@@ -202,6 +202,7 @@ int wsilu_bwd(View g, const float* pre, int ld, View out, long long M, float* pa
 void chunkadd_fwd(const float* u, int ld, View v, long long M, cudaStream_t st);                  // layers.py:12-20
 void chunkadd_bwd(View gv, const float* u, int ld, View gu, long long M, cudaStream_t st);
 // forward value v, pre-activation gradient gu and gu's per-block column sums in one pass; returns the number of partial rows
+int chunkadd_parts(long long M, int C2);      // partial rows chunkadd_fwd_bwd writes (size `part` for them)
 int chunkadd_fwd_bwd(const float* u, int ld, View gv, View v, View gu, long long M, float* part, int ldp, int max_parts,
                      cudaStream_t st);
 void transpose_f32(const float* src, float* dst, int R, int C, cudaStream_t st);

@@ -149,7 +149,9 @@ void chunkadd_bwd(View gv, const float* u, int ld, View gu, long long M, cudaStr
 //   v[m, j]  = wsilu(u[m, j]) + wsilu(u[m, j + C2])              (the recomputed forward value, operand of ffn.2's dW)
 //   gu[m, j] = gv[m, j mod C2] * wsilu'(u[m, j])                 (gradient of the pre-activations)
 //   part[block][j] = sum over the block's rows of gu[m, j]       (ffn.0's bias gradient, reduced by k_reduce_partials)
-// Persistent grid: a thread owns 8 columns (of both halves) and walks rows.
+// A thread owns 8 columns (of both halves) and kCaRows rows; a block's partial row covers lanes * kCaRows rows (one
+// pass of ~1 200 blocks at 160 x 240 x 512: a persistent grid of 4 blocks per SM ran this kernel at 3.2 TB/s, latency bound).
+constexpr int kCaRows = 8;
 __global__ void __launch_bounds__(256) k_chunkadd_fwd_bwd(const float* __restrict__ u, int ld, View gv, View v, View gu,
                                                           long long M, int C2, float* __restrict__ part, int ldp) {
   pdl_prologue_done();
@@ -164,7 +166,11 @@ __global__ void __launch_bounds__(256) k_chunkadd_fwd_bwd(const float* __restric
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[h][i] = 0.0f;
   if (rl < lanes) {
-    for (long long m = (long long)blockIdx.x * lanes + rl; m < M; m += (long long)gridDim.x * lanes) {
+    const long long m0 = (long long)blockIdx.x * lanes * kCaRows + rl;
+#pragma unroll 2
+    for (int it = 0; it < kCaRows; ++it) {
+      const long long m = m0 + (long long)it * lanes;
+      if (m >= M) break;
       float g[8], o[8];
       ld3x8(gv, m, c, g);
 #pragma unroll
@@ -202,17 +208,22 @@ __global__ void __launch_bounds__(256) k_chunkadd_fwd_bwd(const float* __restric
   }
 }
 // returns the number of partial rows (2 * C2 floats each, pitch ldp)
+int chunkadd_parts(long long M, int C2) {
+  const int C8 = C2 / 8;
+  int threads = 256;
+  if (C8 > threads) threads = (C8 + 31) / 32 * 32;
+  const long long per_block = (long long)(threads / C8) * kCaRows;
+  return (int)((M + per_block - 1) / per_block);
+}
 int chunkadd_fwd_bwd(const float* u, int ld, View gv, View v, View gu, long long M, float* part, int ldp, int max_parts,
                      cudaStream_t st) {
   const int C2 = gv.C, C8 = C2 / 8;
   int threads = 256;
   if (C8 > threads) threads = (C8 + 31) / 32 * 32;
   const int lanes = threads / C8;
-  int blocks = (int)((M + lanes - 1) / lanes);
-  const int want = 4 * num_sms();
-  if (blocks > want) blocks = want;
-  if (blocks > max_parts) blocks = max_parts;
-  if (blocks < 1) blocks = 1;
+  const long long per_block = (long long)lanes * kCaRows;
+  const int blocks = (int)((M + per_block - 1) / per_block);
+  if (blocks > max_parts) return -1;
   const size_t smem = (size_t)lanes * 2 * C2 * sizeof(float);
   cudaFuncSetAttribute(k_chunkadd_fwd_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   launch(k_chunkadd_fwd_bwd, blocks, threads, smem, st, u, ld, gv, v, gu, M, C2, part, ldp);

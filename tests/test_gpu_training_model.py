@@ -47,6 +47,24 @@ def _step(model, x, qp, dpb, after_i, target, seed):
     return r, {"loss": loss.item(), "bpp_y": bpp_y.item(), "bpp_z": bpp_z.item(), "mse": mse.item()}
 
 
+def _grad_errors(ga, gb):
+    """(relative L2 error of all gradients as one vector, worst per-tensor max error / tensor max, its name, count)"""
+    num = den = 0.0
+    worst, worst_name, n = 0.0, "", 0
+    for name, g_ref in gb.items():
+        m = float(g_ref.abs().max())
+        if m == 0.0 or name not in ga:
+            continue
+        d = ga[name].double() - g_ref.double()
+        num += float(d.pow(2).sum())
+        den += float(g_ref.double().pow(2).sum())
+        e = float(d.abs().max()) / m
+        n += 1
+        if e > worst:
+            worst, worst_name = e, name
+    return (num / max(den, 1e-300)) ** 0.5, worst, worst_name, n
+
+
 @pytest.mark.parametrize("engine_likelihood", [False, True], ids=["blocks+quant", "blocks+quant+likelihood"])
 def test_reference_performance_model_trains_on_engine_blocks(engine_likelihood):
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -77,34 +95,26 @@ def test_reference_performance_model_trains_on_engine_blocks(engine_likelihood):
             rel = abs(lo[k] - ls[k]) / max(abs(ls[k]), 1e-12)
             stats[f"frame{t}.{k}"] = rel
             assert rel < 1e-3, (t, k, lo[k], ls[k])           # the bpp gate of the inference path
-        worst, worst_name, n = 0.0, "", 0
-        num = den_all = 0.0
-        gs = dict(stock.named_parameters())
-        for name, p in ours.named_parameters():
-            g_ref = gs[name].grad
-            if g_ref is None:
-                assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
-                continue
-            assert p.grad is not None, f"{name}: no gradient through the engine path"
-            den = float(g_ref.abs().max())
-            if den == 0.0:
-                continue
-            e = float((p.grad - g_ref).abs().max()) / den
-            num += float((p.grad.double() - g_ref.double()).pow(2).sum())
-            den_all += float(g_ref.double().pow(2).sum())
-            n += 1
-            if e > worst:
-                worst, worst_name = e, name
-        stats[f"frame{t}.worst_grad_rel"] = worst
-        l2 = (num / max(den_all, 1e-300)) ** 0.5
-        print(f"\nframe {t}: loss terms rel {[f'{stats[f'frame{t}.{k}']:.1e}' for k in ls]}, {n} parameter gradients, "
-              f"all gradients as one vector: relative L2 error {l2:.2e}; worst single tensor {worst:.2e} of its max "
-              f"({worst_name})")
+        gs = {k: p.grad.clone() for k, p in stock.named_parameters() if p.grad is not None}
+        go = {k: p.grad for k, p in ours.named_parameters() if p.grad is not None}
+        assert set(go) >= {k for k, g in gs.items() if float(g.abs().max()) > 0}, "a parameter lost its gradient on the engine path"
+        l2, worst, worst_name, n = _grad_errors(go, gs)
+        # control: the stock model against ITSELF with the input frame moved by one part in 1e7 (the size of the engine's
+        # forward deviation).  Where the likelihood of a tail symbol cancels down to the last bits of erf, its fp32
+        # autograd gradient -1 / (p ln 2) * dp moves by O(1) under such a change; a frame that has such symbols shows
+        # it in the control exactly as it does in the engine run.
+        xp = x[:, t] * (1.0 + 1e-7 * torch.randn_like(x[:, t]))
+        _step(stock, xp, qp, dpb_s, after_i, x[:, t, :3], seed=100 + t)
+        gp = {k: p.grad for k, p in stock.named_parameters() if p.grad is not None}
+        c_l2, c_worst, c_name, _ = _grad_errors(gp, gs)
+        print(f"\nframe {t}: loss terms rel {[f'{stats[f'frame{t}.{k}']:.1e}' for k in ls]}; {n} parameter gradients as one "
+              f"vector: relative L2 error {l2:.2e} (stock vs stock with a 1e-7 input change: {c_l2:.2e}); worst single "
+              f"tensor {worst:.2e} of its max ({worst_name}) (control: {c_worst:.2e}, {c_name})")
         if not engine_likelihood:
-            # measured on a B200: 3e-4 / 4e-3 (L2), 2.6e-3 / 6e-2 (worst tensor: a bias whose gradient is a small
-            # difference of large sums -- the stock fp32 run carries the same kind of error against fp64)
-            assert l2 < 2e-2, l2
-            assert worst < 0.2, (worst, worst_name)
+            # gate: fp32-rounding level where the reference itself is well conditioned (frame 1 measured 8e-5 against a
+            # control of the same order), never worse than a few times the reference's own sensitivity where it is not
+            assert l2 < max(1e-3, 3.0 * c_l2), (l2, c_l2)
+            assert worst < max(2e-2, 3.0 * c_worst), (worst, worst_name, c_worst)
         dpb_s = {k: v.detach() for k, v in rs["dpb"].items()}
         dpb_o = {k: v.detach() for k, v in ro["dpb"].items()}
     T.release_handles()
