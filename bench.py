@@ -187,6 +187,76 @@ def cpu_reference_fps(steps, warmup, budget_s=240.0):
     return B / t, threads, sample, t * 1e3, kind
 
 
+def training_block(dev, C=256, H=160, W=240, iters=20):
+    """SURVEY 8(f) rank 2 beside the headline: forward + backward of one DepthConvBlock of the frame (256 channels at
+    H/8 x W/8) through dmc_b200.training, and the layer's arithmetic (layers.py:43-79) in stock torch ops under
+    autograd on the same GPU.  CUDA events around `iters` whole passes after 3 warm-up passes; every pass streams > 1 GB."""
+    import torch.nn.functional as F
+    from torch import nn
+    import dmc_b200 as D
+
+    def wsilu(v):
+        return F.silu(4.0 * v) / 4.0
+
+    class TorchDCB(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.dc0, self.dc2, self.dc3 = nn.Conv2d(c, c, 1), nn.Conv2d(c, c, 3, padding=1, groups=c), nn.Conv2d(c, c, 1)
+            self.ffn0, self.ffn2 = nn.Conv2d(c, 4 * c, 1), nn.Conv2d(2 * c, c, 1)
+
+        def forward(self, x, qs):
+            out = self.dc3(self.dc2(wsilu(self.dc0(x)))) + x
+            u1, u2 = torch.chunk(wsilu(self.ffn0(out)), 2, dim=1)
+            return (self.ffn2(u1 + u2) + out) * qs
+
+    x = torch.randn(1, C, H, W, device=dev)
+    qs = torch.rand(1, C, 1, 1, device=dev) + 0.5
+    gout = torch.randn(1, C, H, W, device=dev) * 1e-6
+
+    def timed(block, amp=None):
+        xin, q = x.clone().requires_grad_(True), qs.clone().requires_grad_(True)
+
+        def step():
+            xin.grad = None
+            for p in block.parameters():
+                p.grad = None
+            if amp is not None:
+                with torch.autocast("cuda", dtype=amp):
+                    y = block(xin, q)
+            else:
+                y = block(xin, q)
+            y.backward(gout)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    out = {"what": "DepthConvBlock(%d) forward + backward at %dx%d, B = 1, ms per pass" % (C, H, W),
+           "algorithmic_gflop_per_pass": 3 * 2.0 * H * W * C * C * 8 / 1e9}
+    lib = D._capi.load()
+    l0 = lib.dmc_kernel_launches()
+    blk = D.training.DepthConvBlock(C, C).to(dev).train()
+    out["dmc_b200_ms"] = timed(blk)
+    out["gpu_launches"] = int(lib.dmc_kernel_launches() - l0)
+    del blk
+    D.training.release_handles()
+    ref = TorchDCB(C).to(dev).train()
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    for key, tf32, amp in (("torch_fp32_tf32_off_ms", False, None), ("torch_default_tf32_ms", True, None),
+                           ("torch_autocast_bf16_ms", True, torch.bfloat16)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        out[key] = timed(ref, amp)
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    return out
+
+
 def gpu_eager_baseline(dev, x_frames, n=5):
     """The unmodified reference modules, torch-eager on this GPU, same clip: P-frame forwards (after_i=False)."""
     from oracle import make_ref
@@ -240,6 +310,7 @@ def main():
     ap.add_argument("--clips", type=int, default=64, help="independent clips of the whole job (BASELINE config 5: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-training-block", action="store_true")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed resident region (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -473,6 +544,8 @@ def main():
             mi.release_engines()
             torch.cuda.empty_cache()
             line["gpu_eager_baseline"] = gpu_eager_baseline(dev, devc[0])
+        if world == 1 and not args.no_training_block:
+            line["training_block"] = training_block(dev)
         if world == 1 and not args.no_cpu_baseline:
             fps, threads, sample, _, kind = cpu_reference_fps(3, 0, budget_s=25.0)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample}
