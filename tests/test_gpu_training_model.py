@@ -1,4 +1,5 @@
-"""Training step of the reference's OWN `performance` model with the engine's blocks swapped in.
+"""Training step of the reference's OWN model classes (all four P variants) with the engine's blocks swapped in (SURVEY
+§8f rank 2).
 
 oracle/_ref holds the unmodified reference modules.  The same class is built twice -- stock, and inside
 `training.reference_patched` (DepthConvBlock, AdaptiveQuant from the engine; likelihood through `training.adopt`) --,
@@ -65,26 +66,37 @@ def _grad_errors(ga, gb):
     return (num / max(den, 1e-300)) ** 0.5, worst, worst_name, n
 
 
-@pytest.mark.parametrize("engine_likelihood", [False, True], ids=["blocks+quant", "blocks+quant+likelihood"])
-def test_reference_performance_model_trains_on_engine_blocks(engine_likelihood):
+VARIANT_MODULES = {
+    "performance": ("src.refactor.common_model", "src.refactor.seg_video_model"),
+    "fast": ("src.refactor.common_model", "src.refactor.mask_predictor", "src.refactor.seg_video_model_fast"),
+    "mask_prop": ("src.refactor.common_model", "src.refactor.mask_predictor", "src.refactor.mask_prop_seg_video_model"),
+    "old": ("src.models.common_model", "src.models.video_model"),
+}
+
+
+@pytest.mark.parametrize("variant,engine_likelihood", [("performance", False), ("performance", True), ("fast", False),
+                                                       ("mask_prop", False), ("old", False), ("old", True)],
+                         ids=["performance:blocks+quant", "performance:blocks+quant+likelihood", "fast:blocks+quant",
+                              "mask_prop:blocks+quant", "old:blocks+quant", "old:blocks+quant+likelihood"])
+def test_reference_model_trains_on_engine_blocks(variant, engine_likelihood):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     R = _reference()
     dev = torch.device("cuda:0")
     torch.manual_seed(11)
-    stock = R["performance"]().to(dev).train()
-    mods = [sys.modules[n] for n in ("src.layers.layers", "src.refactor.common_model", "src.refactor.seg_video_model")]
+    stock = R[variant]().to(dev).train()
+    mods = [sys.modules[n] for n in ("src.layers.layers",) + VARIANT_MODULES[variant]]
     with T.reference_patched(*mods):
-        ours = R["performance"]().to(dev).train()
+        ours = R[variant]().to(dev).train()
     if engine_likelihood:
-        T.adopt(ours, formula=1)
+        T.adopt(ours, formula=0 if variant == "old" else 1)
     assert any(isinstance(m, T.DepthConvBlock) for m in ours.modules())
     assert not any(isinstance(m, T.DepthConvBlock) for m in stock.modules())
     ours.load_state_dict(stock.state_dict())            # same names, same shapes
 
     H, W = 128, 192
     frames, masks = D.clips.synthetic_clip(3, 1, 3, H, W)
-    x = torch.cat([frames, masks], 2).to(dev)
+    x = (frames if variant == "old" else torch.cat([frames, masks], 2)).to(dev)      # `old` takes no mask channel
     qp = 32
     stats = {}
     dpb_s = dpb_o = {"frame": x[:, 0, :3].contiguous(), "feature": None}
