@@ -20,6 +20,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -105,6 +106,21 @@ struct DeviceGuard {
   }
   ~DeviceGuard() {
     if (switched) cudaSetDevice(prev);
+  }
+};
+
+// Process-wide pool of training workspaces (dmc_dcb_train_*): blocks of the same geometry share every activation /
+// scratch buffer -- a backward pass recomputes what it needs from x, so nothing has to survive in them between calls --
+// and keep only their packed weights to themselves.  Entries are keyed by device, geometry and allocation order and
+// counted: the memory goes when the last handle using it does.  Handles that share a workspace must be used from one
+// stream at a time (they are: torch's current stream).
+struct TrainPool {
+  struct Buf { void* p; size_t bytes; int refs; };
+  std::map<std::string, Buf> bufs;
+  std::mutex mu;
+  static TrainPool& get() {
+    static TrainPool pool;
+    return pool;
   }
 };
 
@@ -249,6 +265,17 @@ struct dmc_engine {
     if (cap_stream) cudaStreamDestroy(cap_stream);
     for (S3Chain* c : chains) s3_chain_destroy(c);
     for (void* p : allocs) cudaFree(p);
+    if (!pool_keys.empty()) {
+      TrainPool& pool = TrainPool::get();
+      std::lock_guard<std::mutex> lk(pool.mu);
+      for (const std::string& k : pool_keys) {
+        auto it = pool.bufs.find(k);
+        if (it != pool.bufs.end() && --it->second.refs == 0) {
+          cudaFree(it->second.p);
+          pool.bufs.erase(it);
+        }
+      }
+    }
   }
 
   bool simt() const { return flags & DMC_FLAG_SIMT_GEMM; }
@@ -260,9 +287,30 @@ struct dmc_engine {
   bool keep_taps() const { return flags & DMC_FLAG_KEEP_TAPS; }
 
   // ------------------------------------------------------------ memory
-  void* dalloc(size_t bytes) {
+  // `fresh` (optional) tells whether the memory was allocated by this call (pooled buffers may be handed out again)
+  std::string pool_prefix;             // non-empty: allocations come from the shared training pool (TrainPool)
+  std::vector<std::string> pool_keys;
+  void* dalloc(size_t bytes, bool* fresh = nullptr) {
     void* p = nullptr;
     if (bytes == 0) bytes = 16;
+    if (fresh) *fresh = true;
+    if (!pool_prefix.empty()) {
+      TrainPool& pool = TrainPool::get();
+      std::lock_guard<std::mutex> lk(pool.mu);
+      const std::string key = pool_prefix + "#" + std::to_string(pool_keys.size()) + ":" + std::to_string(bytes);
+      auto it = pool.bufs.find(key);
+      if (it != pool.bufs.end()) {
+        ++it->second.refs;
+        if (fresh) *fresh = false;
+        p = it->second.p;
+      } else {
+        CUDA_OK(cudaMalloc(&p, bytes));
+        CUDA_OK(cudaMemset(p, 0, bytes));
+        pool.bufs[key] = TrainPool::Buf{p, bytes, 1};
+      }
+      pool_keys.push_back(key);
+      return p;
+    }
     CUDA_OK(cudaMalloc(&p, bytes));
     allocs.push_back(p);
     return p;
@@ -276,9 +324,10 @@ struct dmc_engine {
     long long Mp = (M + 255) / 256 * 256;
     long long bs = Mp * 16;
     long long ps = bs * ((C + 15) / 16);
-    a.v.p = (h16*)dalloc((size_t)ps * kPlanes * sizeof(h16));
+    bool fresh = true;
+    a.v.p = (h16*)dalloc((size_t)ps * kPlanes * sizeof(h16), &fresh);
     a.v.ps = ps; a.v.bs = bs; a.v.C = C;
-    CUDA_OK(cudaMemset(a.v.p, 0, (size_t)ps * kPlanes * sizeof(h16)));
+    if (fresh && pool_prefix.empty()) CUDA_OK(cudaMemset(a.v.p, 0, (size_t)ps * kPlanes * sizeof(h16)));   // (pool: zeroed once)
     return a;
   }
   // scratch buffers are shared by every block of the same geometry (one stream, in-order)
@@ -1688,6 +1737,16 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     CUDA_OK(cudaMemset(t->zero_bias, 0, sizeof(float) * 4 * C));
     t->qs_table = e.new_f32(C);
     t->scale2 = e.new_f32(2);
+    // everything allocated from here on is workspace, shared with the other blocks of this geometry (TrainPool)
+    {
+      const char* v = getenv("DMC_TRAIN_SHARED_WORKSPACE");      // =0: every handle keeps its own buffers
+      if (!(v && v[0] == '0')) {
+        char key[160];
+        snprintf(key, sizeof key, "dev%d:%dx%dx%d:%d>%d:a%d:s%d:q%d:t%d", e.device, B, H, W, cin, cout, ad ? 1 : 0,
+                 t->shortcut, t->has_qs, terms);
+        e.pool_prefix = key;
+      }
+    }
     // partial sums: the largest of the weight-gradient splits, the column sums and the depthwise partial rows
     const int max_parts = 2 * num_sms();
     const int ca_parts = chunkadd_parts(M, 2 * C);

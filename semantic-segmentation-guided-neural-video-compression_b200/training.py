@@ -18,6 +18,7 @@ There is no torch / CPU fallback: without the extension or a CUDA tensor the cal
 from __future__ import annotations
 
 import ctypes
+import os
 from collections import OrderedDict
 from typing import Optional, Sequence
 
@@ -32,6 +33,11 @@ __all__ = ["DepthConvBlock", "AdaptiveQuant", "depth_conv_block", "gaussian_bits
 #: DepthConvBlock handles kept alive -- one per (owner module, geometry), each with its own workspace (~1.2 GB at
 #: 160x240x256, 1/4 of that per halving of the resolution) and packed weights; least recently used first out
 max_handles = 64
+
+#: True (or DMC_B200_STRICT_FINITE=1): every block output is checked for non-finite / fp16-saturated values and the
+#: reference's NaNGuard error is raised at the call (one host sync per block).  Activations pass through fp16 split planes:
+#: |x| must stay below 65 504 (the conversions saturate).  Off by default, like the inference modules' lazy check.
+strict_finite = os.environ.get("DMC_B200_STRICT_FINITE", "0") == "1"
 
 _handles: "OrderedDict[tuple, int]" = OrderedDict()
 _packed_sig: dict = {}        # handle key -> signature of the parameter values the handle has packed
@@ -132,6 +138,12 @@ class _DepthConvBlockFn(torch.autograd.Function):
             _check(lib.dmc_dcb_train_forward(h, _ptr(x), _ptr_array(ws), _ptr(qs), _ptr(out), unchanged,
                                              _stream(x.device)), h)
         _packed_sig[key] = sig
+        if strict_finite:
+            peak = float(out.abs().max())
+            if not peak < 65504.0:
+                from .modules import NonFiniteError
+                raise NonFiniteError(f"[NaNGuard] non-finite activations after DepthConvBlock({cin}->{cout}) "
+                                     f"(max |x| = {peak}; the engine's fp16 split planes saturate at 65504)")
         # (the output is kept only when quant_step needs a gradient: d out / d quant_step = out / quant_step)
         keep_out = quant_step is not None and ctx.needs_input_grad[1]
         ctx.save_for_backward(x, quant_step, out if keep_out else None, *[w for w in w12 if w is not None])

@@ -226,3 +226,36 @@ def test_weight_updates_are_picked_up():
     blk.ffn[0].weight.data.mul_(1.5)        # invisible to the version counter
     T.invalidate()
     check()
+
+
+def test_strict_finite_raises_on_saturation(monkeypatch):
+    monkeypatch.setattr(T, "strict_finite", True)
+    blk = T.DepthConvBlock(32, 32).cuda()
+    x = torch.randn(1, 32, 8, 8, device="cuda")
+    blk(x)                                            # fine
+    with torch.no_grad():
+        blk.ffn[2].bias.fill_(1e6)                    # pushes the output beyond fp16's range
+    with pytest.raises(D.NonFiniteError, match="NaNGuard"):
+        blk(x)
+
+
+def test_blocks_of_equal_geometry_share_a_workspace_but_not_weights():
+    """Two blocks of the same geometry interleaved (forward A, forward B, backward B, backward A): the shared workspace
+    must not leak one block's intermediates or packed weights into the other's results."""
+    torch.manual_seed(9)
+    a, b = T.DepthConvBlock(64, 64).cuda().train(), T.DepthConvBlock(64, 64).cuda().train()
+    ra, rb = RefDCB(64, 64).double(), RefDCB(64, 64).double()
+    for ref, blk in ((ra, a), (rb, b)):
+        _copy_params(ref, blk)
+    x = torch.randn(1, 64, 12, 20)
+    xa, xb = x.cuda().requires_grad_(True), x.cuda().requires_grad_(True)
+    ya = a(xa)
+    yb = b(xb)
+    (yb * 2).sum().backward()
+    ya.sum().backward()
+    for ref, blk, xg, k in ((ra, a, xa, 1.0), (rb, b, xb, 2.0)):
+        xr = x.double().requires_grad_(True)
+        (ref(xr) * k).sum().backward()
+        assert _relmax(xg.grad, xr.grad) < 2e-4
+        assert _relmax(blk.ffn[0].weight.grad, ref.ffn0.weight.grad) < 2e-4
+        assert _relmax(blk.dc[2].weight.grad, ref.dc2.weight.grad) < 2e-4

@@ -94,12 +94,21 @@ def test_reference_model_trains_on_engine_blocks(variant, engine_likelihood):
     assert not any(isinstance(m, T.DepthConvBlock) for m in stock.modules())
     ours.load_state_dict(stock.state_dict())            # same names, same shapes
 
+    # yardstick: the stock model in fp64 (same parameters, same fp32 noise draws): how far is the stock fp32 run itself
+    # from the exact gradient?
+    import copy
+    stock64 = copy.deepcopy(stock).double()
+    for m in stock64.modules():
+        if type(m).__name__ == "AdaptiveQuant" and m.mode == "noise":
+            m.forward = lambda v, hb=m.half_bin: v + torch.empty_like(v, dtype=torch.float32).uniform_(-hb, hb).double()
+
     H, W = 128, 192
     frames, masks = D.clips.synthetic_clip(3, 1, 3, H, W)
     x = (frames if variant == "old" else torch.cat([frames, masks], 2)).to(dev)      # `old` takes no mask channel
     qp = 32
     stats = {}
     dpb_s = dpb_o = {"frame": x[:, 0, :3].contiguous(), "feature": None}
+    dpb_64 = {"frame": x[:, 0, :3].double().contiguous(), "feature": None}
     for t, after_i in ((1, True), (2, False)):
         rs, ls = _step(stock, x[:, t], qp, dpb_s, after_i, x[:, t, :3], seed=100 + t)
         ro, lo = _step(ours, x[:, t], qp, dpb_o, after_i, x[:, t, :3], seed=100 + t)
@@ -119,7 +128,17 @@ def test_reference_model_trains_on_engine_blocks(variant, engine_likelihood):
         _step(stock, xp, qp, dpb_s, after_i, x[:, t, :3], seed=100 + t)
         gp = {k: p.grad for k, p in stock.named_parameters() if p.grad is not None}
         c_l2, c_worst, c_name, _ = _grad_errors(gp, gs)
-        print(f"\nframe {t}: loss terms rel {[f'{stats[f'frame{t}.{k}']:.1e}' for k in ls]}; {n} parameter gradients as one "
+        try:
+            r64, _ = _step(stock64, x[:, t].double(), qp, dpb_64, after_i, x[:, t, :3].double(), seed=100 + t)
+            g64 = {k: p.grad for k, p in stock64.named_parameters() if p.grad is not None}
+            o64_l2, o64_worst, o64_name, _ = _grad_errors(go, g64)
+            s64_l2, s64_worst, s64_name, _ = _grad_errors(gs, g64)
+            dpb_64 = {k: v.detach() for k, v in r64["dpb"].items()}
+            print(f"\nframe {t}: against the stock model in fp64 -- engine blocks: L2 {o64_l2:.2e}, worst tensor "
+                  f"{o64_worst:.2e} ({o64_name}); stock fp32: L2 {s64_l2:.2e}, worst tensor {s64_worst:.2e} ({s64_name})")
+        except Exception as ex:          # (information only: the reference was not written with fp64 in mind)
+            print(f"\nframe {t}: fp64 yardstick not available: {type(ex).__name__}: {str(ex)[:160]}")
+        print(f"frame {t}: loss terms rel {[f'{stats[f'frame{t}.{k}']:.1e}' for k in ls]}; {n} parameter gradients as one "
               f"vector: relative L2 error {l2:.2e} (stock vs stock with a 1e-7 input change: {c_l2:.2e}); worst single "
               f"tensor {worst:.2e} of its max ({worst_name}) (control: {c_worst:.2e}, {c_name})")
         if not engine_likelihood:
