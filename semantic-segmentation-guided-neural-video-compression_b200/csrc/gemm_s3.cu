@@ -1610,13 +1610,26 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
   // table points backwards and each cluster walks its entries in order, so a fully resident grid cannot deadlock
   const int cap = cl4 ? 4 * cl4_clusters : std::min(num_sms() & ~1, 2 * dv->pair_clusters);
   std::vector<uint32_t> table;
-  for (int l = 0; l < n; ++l)
-    for (int mt = 0; mt < MT; ++mt) {
-      // an entry is one N tile for a CTA pair, or two adjacent N tiles for the two pairs of a 4-CTA cluster
-      const int per_mt = cl4 ? (c->p.st[l].n_tiles + 1) / 2 : c->p.st[l].n_tiles;
-      for (int nt = 0; nt < per_mt; ++nt)
-        table.push_back(((uint32_t)l << 28) | ((uint32_t)nt << 20) | (uint32_t)mt);
-    }
+  // DMC_S3_GROUPS=g (experiment): the row tiles are cut into g groups and the table is layer-major INSIDE a group, group
+  // after group -- the intermediates of a group (1/g of o1, u, ...) are consumed while they are still in L2 instead of
+  // after a whole layer has been written (358 MB of DRAM traffic per DepthConvBlock-256 chain against 157 MB at its
+  // boundary with g = 1).  Dependencies still point backwards; groups do not depend on each other.
+  static int groups_env = -1;
+  if (groups_env < 0) {
+    const char* v = getenv("DMC_S3_GROUPS");
+    groups_env = v ? std::max(1, atoi(v)) : 1;
+  }
+  const int groups = (n > 1) ? std::min(groups_env, MT) : 1;
+  for (int g = 0; g < groups; ++g) {
+    const int mt0 = (int)((long long)MT * g / groups), mt1 = (int)((long long)MT * (g + 1) / groups);
+    for (int l = 0; l < n; ++l)
+      for (int mt = mt0; mt < mt1; ++mt) {
+        // an entry is one N tile for a CTA pair, or two adjacent N tiles for the two pairs of a 4-CTA cluster
+        const int per_mt = cl4 ? (c->p.st[l].n_tiles + 1) / 2 : c->p.st[l].n_tiles;
+        for (int nt = 0; nt < per_mt; ++nt)
+          table.push_back(((uint32_t)l << 28) | ((uint32_t)nt << 20) | (uint32_t)mt);
+      }
+  }
   (void)tiles_per_step;
   c->p.n_entries = (int)table.size();
   {
@@ -1627,7 +1640,7 @@ S3Chain* s3_chain_create(const S3StageDesc* stages, int n, long long M) {
       const int per_mt = cl4 ? (c->p.st[l].n_tiles + 1) / 2 : c->p.st[l].n_tiles;
       if (per_mt * MT < min_layer) min_layer = per_mt * MT;
     }
-    c->p.eager = v ? (v[0] == '1') : (n > 1 && min_layer < 3 * units);
+    c->p.eager = v ? (v[0] == '1') : (n > 1 && min_layer / groups < 3 * units);
   }
   c->p.MT = MT;
   c->p.err = d_err;
