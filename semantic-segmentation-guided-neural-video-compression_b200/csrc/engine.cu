@@ -1638,7 +1638,13 @@ extern "C" int dmc_op_gaussian_bits(const float* sym, const float* sigma, float*
 //   WSiLU' / chunk-add' / depthwise gradients = the elementwise kernels of train.cu.
 struct dmc_dcb_train {
   dmc_engine e;
-  std::vector<dmc_engine::Op> prog_bwd;
+  // backward = head (reads the caller's tensors) + body (works on the handle's own buffers only: replayed as ONE CUDA
+  // graph per set of requested gradients) + tail (writes the caller's tensors)
+  std::vector<dmc_engine::Op> prog_bwd_head, prog_bwd, prog_bwd_tail;
+  float* gflat = nullptr;        // the twelve parameter gradients, in order, as the body writes them
+  size_t goff[13] = {};
+  int gmask = 0;                 // bit i: gradient i is wanted (this call)
+  long long bwd_calls = 0;
   int cin = 0, cout = 0, shortcut = 0, has_qs = 0, terms = 3;
   DCB* blk = nullptr;
   Conv *T_ad = nullptr, *T_dc0 = nullptr, *T_dc3 = nullptr, *T_ffn0 = nullptr, *T_ffn2 = nullptr, *P_ffn0 = nullptr;
@@ -1649,7 +1655,8 @@ struct dmc_dcb_train {
   const float *x = nullptr, *gout = nullptr, *yout = nullptr;
   float* scale2 = nullptr;       // {gradient scale, its reciprocal}, written on the device at the start of every backward
   float *out = nullptr, *gx = nullptr, *gqs = nullptr;
-  float* gw[12] = {};
+  float* gw[12] = {};            // caller's destinations (this call)
+  float* gint(int i) const { return (gmask >> i & 1) ? gflat + goff[i] : nullptr; }
 };
 
 namespace {
@@ -1718,7 +1725,6 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     dmc_engine& e = t->e;
     CUDA_OK(cudaGetDevice(&e.device));
     e.variant = -1; e.B = batch; e.H = height; e.W = width;
-    e.graphs_on = false;
     t->cin = cin; t->cout = cout; t->shortcut = shortcut != 0; t->has_qs = has_quant_step != 0; t->terms = terms;
     const int C = cout, B = batch, H = height, W = width;
     const long long M = (long long)B * H * W;
@@ -1737,6 +1743,12 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     CUDA_OK(cudaMemset(t->zero_bias, 0, sizeof(float) * 4 * C));
     t->qs_table = e.new_f32(C);
     t->scale2 = e.new_f32(2);
+    {
+      const size_t sz[12] = {(size_t)C * cin, (size_t)C, (size_t)C * C, (size_t)C, (size_t)C * 9, (size_t)C, (size_t)C * C, (size_t)C,
+                             (size_t)4 * C * C, (size_t)4 * C, (size_t)2 * C * C, (size_t)C};
+      for (int i = 0; i < 12; ++i) t->goff[i + 1] = t->goff[i] + sz[i];
+      t->gflat = e.new_f32(t->goff[12]);
+    }
     // everything allocated from here on is workspace, shared with the other blocks of this geometry (TrainPool)
     {
       const char* v = getenv("DMC_TRAIN_SHARED_WORKSPACE");      // =0: every handle keeps its own buffers
@@ -1770,7 +1782,7 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     }
 
     // ---- backward program
-    e.set_prog(&t->prog_bwd);
+    e.set_prog(&t->prog_bwd_head);
     Act xs = e.new_act(B, H, W, cin);
     Act a = ad ? e.new_act(B, H, W, C) : xs;
     float* t0 = e.new_f32((size_t)M * C);
@@ -1784,8 +1796,21 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     float* scale2 = t->scale2;
     EpiSpec plain;
     plain.nsplit = terms;
-    // recompute (the forward pass keeps nothing but x and its own output)
+    // head: everything that reads a caller tensor.  The incoming gradient gets a power-of-two scale into fp16's range
+    // (everything below is linear in it) and quant_step
     e.op([self, xs, B, H, W, cin](cudaStream_t st) { nchw_to_s3(self->x, xs.v, B, cin, H, W, st); });
+    e.op([self, g, B, H, W, C, M, scale2, max_parts](cudaStream_t st) {
+      grad_scale(self->gout, M * C, grad_peak_log2(), self->part, scale2, st);
+      if (self->has_qs && self->gqs) {
+        // out = out_pre * quant_step  ->  d/d quant_step[c] = sum g * out_pre = (sum g * out) / quant_step[c]
+        if (!self->yout) fail("dmc_dcb_train_backward: the forward output is needed for grad_quant_step");
+        int S = nchw_dot(self->gout, self->yout, B, C, (long long)H * W, self->part, max_parts, st);
+        reduce_div(self->part, S, C, self->qs_table, self->gqs, st);
+      }
+      nchw_to_s3_scaled(self->gout, g.v, B, C, H, W, self->has_qs ? self->qs_table : nullptr, scale2, st);
+    });
+    // body: recompute (the forward pass keeps nothing but x and its own output), then the block in reverse
+    e.set_prog(&t->prog_bwd);
     if (ad) e.gemm(xs, t->blk->adaptor, &a, plain);
     {
       EpiSpec s = plain;
@@ -1805,31 +1830,20 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
       s.out_f32 = u0; s.ld_f32 = 4 * C;
       e.gemm(o1, t->P_ffn0, nullptr, s);
     }
-    // the incoming gradient: power-of-two scale into fp16's range (everything below is linear in it), times quant_step
-    e.op([self, g, B, H, W, C, M, scale2, max_parts](cudaStream_t st) {
-      grad_scale(self->gout, M * C, grad_peak_log2(), self->part, scale2, st);
-      if (self->has_qs && self->gqs) {
-        // out = out_pre * quant_step  ->  d/d quant_step[c] = sum g * out_pre = (sum g * out) / quant_step[c]
-        if (!self->yout) fail("dmc_dcb_train_backward: the forward output is needed for grad_quant_step");
-        int S = nchw_dot(self->gout, self->yout, B, C, (long long)H * W, self->part, max_parts, st);
-        reduce_div(self->part, S, C, self->qs_table, self->gqs, st);
-      }
-      nchw_to_s3_scaled(self->gout, g.v, B, C, H, W, self->has_qs ? self->qs_table : nullptr, scale2, st);
-    });
     // one weight + bias gradient: G [M, N] against the layer input X [M, K]; `bias_done`: the column sums of G were
     // already reduced by the kernel that produced G
     auto wgrad = [&](const Act& G, const Act& X, int iw, bool bias_done) {
       const int terms_ = terms;
       e.op([self, G, X, M, iw, terms_, max_parts, bias_done, scale2](cudaStream_t st) {
         const int N = G.v.C, K = X.v.C;
-        if (self->gw[iw]) {
+        if (self->gint(iw)) {
           int S = wgrad_s3(G.v, X.v, M, terms_, self->part, st);
           if (S < 1) fail("weight gradient launch: %s", wgrad_umma_last_error());
-          reduce_partials(self->part, (long long)N * K, S, self->gw[iw], (long long)N * K, scale2 + 1, 1.0f, st);
+          reduce_partials(self->part, (long long)N * K, S, self->gint(iw), (long long)N * K, scale2 + 1, 1.0f, st);
         }
-        if (self->gw[iw + 1] && !bias_done) {
+        if (self->gint(iw + 1) && !bias_done) {
           int S = colsum_s3(G.v, nullptr, M, self->part, N, max_parts, st);
-          reduce_partials(self->part, N, S, self->gw[iw + 1], N, scale2 + 1, 1.0f, st);
+          reduce_partials(self->part, N, S, self->gint(iw + 1), N, scale2 + 1, 1.0f, st);
         }
       });
     };
@@ -1839,7 +1853,7 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     e.op([self, u0, gv, v, gu, M, C, ca_parts, scale2](cudaStream_t st) {
       int S = chunkadd_fwd_bwd(u0, 4 * C, gv.v, v.v, gu.v, M, self->part, 4 * C, ca_parts, st);
       if (S < 1) fail("chunkadd_fwd_bwd: partial buffer too small");
-      if (self->gw[9]) reduce_partials(self->part, 4 * C, S, self->gw[9], 4 * C, scale2 + 1, 1.0f, st);
+      if (self->gint(9)) reduce_partials(self->part, 4 * C, S, self->gint(9), 4 * C, scale2 + 1, 1.0f, st);
     });
     wgrad(g, v, 10, false);
     // ffn.0 (+ the residual around the ffn)
@@ -1859,14 +1873,14 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     // depthwise 3x3
     e.op([self, gt2, gt1, t1, C, B, H, W, max_parts, scale2](cudaStream_t st) {
       dwconv3x3_f32(gt2, C, self->w9c_flip, self->zero_bias, gt1.v, B, H, W, st);
-      if (self->gw[4] || self->gw[5]) {
+      if (self->gint(4) || self->gint(5)) {
         int S = dw_wgrad(gt2, C, C, t1, C, B, H, W, self->part, C * 10, max_parts, st);
-        reduce_dw(self->part, C * 10, S, self->gw[4], self->gw[5], C, scale2 + 1, 1.0f, st);
+        reduce_dw(self->part, C * 10, S, self->gint(4), self->gint(5), C, scale2 + 1, 1.0f, st);
       }
     });
     e.op([self, gt1, t0, gt0, M, C, max_parts, scale2](cudaStream_t st) {
       int S = wsilu_bwd(gt1.v, t0, C, gt0.v, M, self->part, C, 2 * max_parts, st);
-      if (self->gw[3]) reduce_partials(self->part, C, S, self->gw[3], C, scale2 + 1, 1.0f, st);
+      if (self->gint(3)) reduce_partials(self->part, C, S, self->gint(3), C, scale2 + 1, 1.0f, st);
     });
     // dc.0 (+ the residual around dc, + the shortcut)
     wgrad(gt0, a, 2, true);
@@ -1880,10 +1894,12 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
       Act gxs = e.new_act(B, H, W, cin);
       wgrad(ga, xs, 0, false);
       e.gemm(ga, t->T_ad, &gxs, plain);
+      e.set_prog(&t->prog_bwd_tail);
       e.op([self, gxs, B, H, W, cin, scale2](cudaStream_t st) {
         if (self->gx) s3_to_nchw_scaled(gxs.v, self->gx, B, cin, H, W, scale2 + 1, st);
       });
     } else {
+      e.set_prog(&t->prog_bwd_tail);
       e.op([self, ga, B, H, W, C, scale2](cudaStream_t st) {
         if (self->gx) s3_to_nchw_scaled(ga.v, self->gx, B, C, H, W, scale2 + 1, st);
       });
@@ -1943,8 +1959,26 @@ extern "C" int dmc_dcb_train_backward(dmc_dcb_train* t, const float* x, const fl
     if (((uintptr_t)grad_out | (uintptr_t)x) % 16) fail("dmc_dcb_train_backward: tensors must be 16-byte aligned");
     for (int i = 0; i < 12; ++i) t->gw[i] = grad_weights12 ? grad_weights12[i] : nullptr;
     if (!t->blk->adaptor) t->gw[0] = t->gw[1] = nullptr;
-    t->e.cur.qp = 0;
-    t->e.run(t->prog_bwd, st);
+    t->gmask = 0;
+    for (int i = 0; i < 12; ++i)
+      if (t->gw[i]) t->gmask |= 1 << i;
+    dmc_engine& e = t->e;
+    e.cur.qp = 0;
+    e.run(t->prog_bwd_head, st);
+    // the body touches only the handle's buffers: one graph per set of requested gradients, from the second call on
+    // (the first call runs directly: one-time allocations inside the launchers are not capturable)
+    if (t->bwd_calls++ > 0) e.run_graph(0x100000ull | (uint64_t)t->gmask, st, [&](cudaStream_t s2) { e.run(t->prog_bwd, s2); });
+    else e.run(t->prog_bwd, st);
+    e.run(t->prog_bwd_tail, st);
+    // gradients leave in as few copies as the caller's layout allows (training.py: one flat tensor in parameter order)
+    for (int i = 0; i < 12;) {
+      if (!t->gw[i]) { ++i; continue; }
+      int j = i;
+      while (j + 1 < 12 && t->gw[j + 1] && t->gw[j + 1] == t->gw[j] + (t->goff[j + 1] - t->goff[j])) ++j;
+      CUDA_OK(cudaMemcpyAsync(t->gw[i], t->gflat + t->goff[i], (t->goff[j + 1] - t->goff[i]) * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+      i = j + 1;
+    }
     CUDA_OK(cudaGetLastError());
   });
 }

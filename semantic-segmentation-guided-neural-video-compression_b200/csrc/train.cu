@@ -15,12 +15,30 @@
 // Gradients are linear in the incoming gradient, so the caller pre-scales it by a power of two into fp16's
 // comfortable range (training.py: max |g| -> 2^8) and un-scales the results: `out_scale` of the reductions.
 #include <algorithm>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "kernels.h"
 
 namespace dmc {
 
 static inline unsigned cdiv_u(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// Opt a kernel in to the device's largest dynamic shared-memory size, once per (kernel, device): the launchers below are
+// also run while a CUDA graph is being captured, where attribute calls are best not made at all.
+template <class K>
+static void optin_max_smem(K kernel) {
+  static std::set<std::pair<const void*, int>> done;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (!done.insert({(const void*)kernel, dev}).second) return;
+  int smem = 0;
+  cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
 
 // d/dx [ silu(4x) / 4 ] = sigmoid(v) * (1 + v * (1 - sigmoid(v))),  v = 4x          (layers.py:8-10)
 __device__ __forceinline__ float wsilu_grad(float x) {
@@ -225,7 +243,7 @@ int chunkadd_fwd_bwd(const float* u, int ld, View gv, View v, View gu, long long
   const int blocks = (int)((M + per_block - 1) / per_block);
   if (blocks > max_parts) return -1;
   const size_t smem = (size_t)lanes * 2 * C2 * sizeof(float);
-  cudaFuncSetAttribute(k_chunkadd_fwd_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  optin_max_smem(k_chunkadd_fwd_bwd);
   launch(k_chunkadd_fwd_bwd, blocks, threads, smem, st, u, ld, gv, v, gu, M, C2, part, ldp);
   return blocks;
 }
@@ -401,7 +419,7 @@ int dw_wgrad(const float* g, int ldg, int C, const float* t, int ld, int B, int 
   if (lanes < 1) { lanes = 1; threads = (C8 + 31) / 32 * 32; }
   // shared memory: lanes * C * 10 floats (256 channels x 8 lanes = 80 KB): opt in once
   const size_t smem = (size_t)lanes * C8 * 80 * sizeof(float);
-  cudaFuncSetAttribute(k_dw_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  optin_max_smem(k_dw_wgrad);
   const long long M = (long long)B * H * W;
   int blocks = (int)((M + lanes - 1) / lanes);
   const int want = 2 * num_sms();
@@ -624,8 +642,8 @@ int wgrad_s3(View G, View X, long long M, int terms, float* part, cudaStream_t s
   const int per = (chunks + S - 1) / S;
   S = (chunks + per - 1) / per;
   const int smem = kWgStages * kWgStageBytes;
-  cudaFuncSetAttribute(k_wgrad_s3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_wgrad_s3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  optin_max_smem(k_wgrad_s3<3>);
+  optin_max_smem(k_wgrad_s3<1>);
   dim3 grid((N + kWgTN - 1) / kWgTN, (K + kWgTK - 1) / kWgTK, S);
   if (terms == 1) launch(k_wgrad_s3<1>, grid, 256, smem, st, G, X, N, K, chunks, per, part);
   else launch(k_wgrad_s3<3>, grid, 256, smem, st, G, X, N, K, chunks, per, part);
