@@ -2,8 +2,9 @@
 
 The checker is a plain torch restatement of src/layers/layers.py:43-79, src/layers/inference.py:16-27 and the two
 `get_y_gaussian_bits` formulas, evaluated in fp64 on the CPU.  Tolerances (relative to the largest magnitude of the
-tensor compared): forward 2e-5 (as the per-layer parity tests), gradients 2e-4 with the fp32-grade 3-term product,
-1e-2 with plain fp16 operands (`terms=1`).  Each is written next to its check.
+tensor compared): forward 2e-5 (as the per-layer parity tests), gradients 1e-5 with the fp32-grade 3-term product
+(measured on a B200: 1.3e-7 ... 6.5e-7 over all cases and tensors), 3e-3 with plain fp16 operands (`terms=1`; measured up to
+6.2e-4).  Each is written next to its check.
 """
 import math
 
@@ -96,8 +97,8 @@ def test_depth_conv_block_forward_backward(case, terms):
     yg.backward(gout.float().cuda())
     torch.cuda.synchronize()
 
-    ftol = 2e-5 if terms == 3 else 5e-3
-    gtol = 2e-4 if terms == 3 else 1e-2
+    ftol = 2e-5 if terms == 3 else 2e-3
+    gtol = 1e-5 if terms == 3 else 3e-3
     errs = {"out": (_relmax(yg, yr), ftol), "grad_x": (_relmax(xg.grad, xr.grad), gtol)}
     if with_qs:
         errs["grad_quant_step"] = (_relmax(qg.grad, qr.grad), gtol)
