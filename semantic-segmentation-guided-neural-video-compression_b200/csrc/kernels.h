@@ -199,13 +199,10 @@ void mask_from_logits(const float* logits, float* mask, long long n, cudaStream_
 void wsilu_rows(const float* in, float* out, long long n, cudaStream_t st);                       // fp32 rows, n % 4 == 0
 // out = g * wsilu'(pre) + per-block column sums of out; returns the number of partial rows
 int wsilu_bwd(View g, const float* pre, int ld, View out, long long M, float* part, int ldp, int max_parts, cudaStream_t st);
-void chunkadd_fwd(const float* u, int ld, View v, long long M, cudaStream_t st);                  // layers.py:12-20
-void chunkadd_bwd(View gv, const float* u, int ld, View gu, long long M, cudaStream_t st);
 // forward value v, pre-activation gradient gu and gu's per-block column sums in one pass; returns the number of partial rows
 int chunkadd_parts(long long M, int C2);      // partial rows chunkadd_fwd_bwd writes (size `part` for them)
 int chunkadd_fwd_bwd(const float* u, int ld, View gv, View v, View gu, long long M, float* part, int ldp, int max_parts,
                      cudaStream_t st);
-void transpose_f32(const float* src, float* dst, int R, int C, cudaStream_t st);
 // column sums of g (times h, element by element, when h != nullptr) as per-block partial rows; returns their number
 int colsum_s3(View g, const View* h, long long M, float* part, int ldp, int max_parts, cudaStream_t st);
 void reduce_partials(const float* part, long long stride, int S, float* out, long long n, const float* scale_dev,

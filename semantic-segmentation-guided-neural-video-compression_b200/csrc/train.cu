@@ -12,8 +12,10 @@
 //   * everything elementwise (WSiLU', chunk-add', depthwise weight gradient, column sums for the biases) is
 //     HBM-bound and vectorised 8 channels per thread on the split planes.
 //
-// Gradients are linear in the incoming gradient, so the caller pre-scales it by a power of two into fp16's
-// comfortable range (training.py: max |g| -> 2^8) and un-scales the results: `out_scale` of the reductions.
+// Gradients are linear in the incoming gradient: it is multiplied by a power of two found on the device (k_absmax_part,
+// k_grad_scale: max |g| -> 2^8) on its way into the fp16 split planes, and every result leaves multiplied by the
+// reciprocal (`scale_dev` of the reductions, k_s3_to_nchw_scaled).  The launch order lives in engine.cu
+// (dmc_dcb_train_create).
 #include <algorithm>
 #include <mutex>
 #include <set>
@@ -110,60 +112,7 @@ int wsilu_bwd(View g, const float* pre, int ld, View out, long long M, float* pa
   return blocks;
 }
 
-// WSiLUChunkAdd (layers.py:12-20) from the fp32 pre-activations [M, 2*C2]:  v[m, j] = wsilu(u[m, j]) + wsilu(u[m, j + C2])
-__global__ void k_chunkadd_fwd(const float* __restrict__ u, int ld, View v, long long M, int C2) {
-  pdl_prologue_done();
-  const int C8 = C2 / 8;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * C8) return;
-  const long long m = idx / C8;
-  const int c = (int)(idx % C8) * 8;
-  const float* q = u + m * ld + c;
-  float o[8];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float4 a = *reinterpret_cast<const float4*>(q + 4 * h);
-    const float4 b = *reinterpret_cast<const float4*>(q + C2 + 4 * h);
-    o[4 * h + 0] = add_rn(wsilu(a.x), wsilu(b.x));
-    o[4 * h + 1] = add_rn(wsilu(a.y), wsilu(b.y));
-    o[4 * h + 2] = add_rn(wsilu(a.z), wsilu(b.z));
-    o[4 * h + 3] = add_rn(wsilu(a.w), wsilu(b.w));
-  }
-  st3x8(v, m, c, o);
-}
-void chunkadd_fwd(const float* u, int ld, View v, long long M, cudaStream_t st) {
-  const int C2 = v.C;
-  launch(k_chunkadd_fwd, cdiv_u(M * (C2 / 8), 256), 256, 0, st, u, ld, v, M, C2);
-}
-
-// gu[m, j] = gv[m, j mod C2] * wsilu'(u[m, j]),  j < 2*C2
-__global__ void k_chunkadd_bwd(View gv, const float* __restrict__ u, int ld, View gu, long long M, int C2) {
-  pdl_prologue_done();
-  const int C8 = C2 / 8;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * C8) return;
-  const long long m = idx / C8;
-  const int c = (int)(idx % C8) * 8;
-  float g[8];
-  ld3x8(gv, m, c, g);
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const float* q = u + m * ld + half * C2 + c;
-    const float4 p0 = *reinterpret_cast<const float4*>(q);
-    const float4 p1 = *reinterpret_cast<const float4*>(q + 4);
-    const float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = g[i] * wsilu_grad(p[i]);
-    st3x8(gu, m, half * C2 + c, o);
-  }
-}
-void chunkadd_bwd(View gv, const float* u, int ld, View gu, long long M, cudaStream_t st) {
-  const int C2 = gv.C;
-  launch(k_chunkadd_bwd, cdiv_u(M * (C2 / 8), 256), 256, 0, st, gv, u, ld, gu, M, C2);
-}
-
-// The two directions of WSiLUChunkAdd in one pass over the pre-activations u [M, 2*C2] (fp32 rows):
+// The two directions of WSiLUChunkAdd (layers.py:12-20) in one pass over the pre-activations u [M, 2*C2] (fp32 rows):
 //   v[m, j]  = wsilu(u[m, j]) + wsilu(u[m, j + C2])              (the recomputed forward value, operand of ffn.2's dW)
 //   gu[m, j] = gv[m, j mod C2] * wsilu'(u[m, j])                 (gradient of the pre-activations)
 //   part[block][j] = sum over the block's rows of gu[m, j]       (ffn.0's bias gradient, reduced by k_reduce_partials)
@@ -246,26 +195,6 @@ int chunkadd_fwd_bwd(const float* u, int ld, View gv, View v, View gu, long long
   optin_max_smem(k_chunkadd_fwd_bwd);
   launch(k_chunkadd_fwd_bwd, blocks, threads, smem, st, u, ld, gv, v, gu, M, C2, part, ldp);
   return blocks;
-}
-
-// dst[c][r] = src[r][c]  (fp32; weights of a 1x1 convolution -> the weight of its data gradient)
-__global__ void k_transpose_f32(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
-  pdl_prologue_done();
-  __shared__ float t[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    t[i][threadIdx.x] = (r < R && c < C) ? src[(long long)r * C + c] : 0.0f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < R && c < C) dst[(long long)c * R + r] = t[threadIdx.x][i];
-  }
-}
-void transpose_f32(const float* src, float* dst, int R, int C, cudaStream_t st) {
-  dim3 grid(cdiv_u(C, 32), cdiv_u(R, 32));
-  launch(k_transpose_f32, grid, dim3(32, 8), 0, st, src, dst, R, C);
 }
 
 // ------------------------------------------------------------------ column sums (bias gradients, per-channel scale)
