@@ -1650,6 +1650,13 @@ struct dmc_dcb_train {
   Conv *T_ad = nullptr, *T_dc0 = nullptr, *T_dc3 = nullptr, *T_ffn0 = nullptr, *T_ffn2 = nullptr, *P_ffn0 = nullptr;
   bool fwd_packed = false, bwd_packed = false;
   float *w9c_flip = nullptr, *zero_bias = nullptr, *qs_table = nullptr, *part = nullptr;
+  // Weight / bias gradients hang off the chain of data gradients as leaves: they run on a second stream (forked and
+  // joined with events, inside the graph too) with partial-sum buffers of their own: partS for the side stream's own
+  // kernels, partA / partB for the column sums the main-stream kernels k_chunkadd_fwd_bwd / k_wsilu_bwd leave behind
+  float *partS = nullptr, *partA = nullptr, *partB = nullptr;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool use_side = true;
   size_t part_floats = 0;
   // caller tensors of the current call (read by the launch closures)
   const float *x = nullptr, *gout = nullptr, *yout = nullptr;
@@ -1762,12 +1769,24 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
     // partial sums: the largest of the weight-gradient splits, the column sums and the depthwise partial rows
     const int max_parts = 2 * num_sms();
     const int ca_parts = chunkadd_parts(M, 2 * C);
-    size_t pf = (size_t)std::max(2 * max_parts, ca_parts) * 4 * C;
-    pf = std::max(pf, (size_t)max_parts * C * 10);
+    size_t pf = (size_t)max_parts * 4 * C;                      // column sums of the widest tensor
+    pf = std::max(pf, (size_t)max_parts * C * 10);              // depthwise partial rows
     const int shapes[5][2] = {{C, cin}, {C, C}, {C, C}, {4 * C, C}, {C, 2 * C}};
     for (auto& sh : shapes) pf = std::max(pf, (size_t)wgrad_splits(M, sh[0], sh[1]) * sh[0] * sh[1]);
-    t->part = e.new_f32(pf);
+    t->partS = e.new_f32(pf);
+    t->partA = e.new_f32((size_t)ca_parts * 4 * C);
+    t->partB = e.new_f32((size_t)2 * max_parts * C);             // k_wsilu_bwd's rows; the head's scratch (absmax, nchw_dot)
+    t->part = t->partB;
     t->part_floats = pf;
+    {
+      const char* v = getenv("DMC_TRAIN_SIDE_STREAM");           // =0: everything on the caller's stream (A/B runs)
+      t->use_side = !(v && v[0] == '0');
+      if (t->use_side) {
+        CUDA_OK(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+      }
+    }
 
     // ---- forward program
     dmc_dcb_train* self = t;
@@ -1830,30 +1849,43 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
       s.out_f32 = u0; s.ld_f32 = 4 * C;
       e.gemm(o1, t->P_ffn0, nullptr, s);
     }
+    // A leaf of the backward pass (nothing on the chain of data gradients waits for it): on the side stream, after
+    // everything launched so far on the main one.  Every tensor of a pass is written once, so the only hazards are the
+    // partial-sum buffers, and those are per stream.
+    auto leaf = [&](std::function<void(cudaStream_t)> fn) {
+      e.op([self, fn](cudaStream_t st) {
+        if (!self->use_side) return fn(st);
+        CUDA_OK(cudaEventRecord(self->ev_fork, st));
+        CUDA_OK(cudaStreamWaitEvent(self->side, self->ev_fork, 0));
+        fn(self->side);
+      });
+    };
     // one weight + bias gradient: G [M, N] against the layer input X [M, K]; `bias_done`: the column sums of G were
     // already reduced by the kernel that produced G
     auto wgrad = [&](const Act& G, const Act& X, int iw, bool bias_done) {
       const int terms_ = terms;
-      e.op([self, G, X, M, iw, terms_, max_parts, bias_done, scale2](cudaStream_t st) {
+      leaf([self, G, X, M, iw, terms_, max_parts, bias_done, scale2](cudaStream_t st) {
         const int N = G.v.C, K = X.v.C;
         if (self->gint(iw)) {
-          int S = wgrad_s3(G.v, X.v, M, terms_, self->part, st);
+          int S = wgrad_s3(G.v, X.v, M, terms_, self->partS, st);
           if (S < 1) fail("weight gradient launch: %s", wgrad_umma_last_error());
-          reduce_partials(self->part, (long long)N * K, S, self->gint(iw), (long long)N * K, scale2 + 1, 1.0f, st);
+          reduce_partials(self->partS, (long long)N * K, S, self->gint(iw), (long long)N * K, scale2 + 1, 1.0f, st);
         }
         if (self->gint(iw + 1) && !bias_done) {
-          int S = colsum_s3(G.v, nullptr, M, self->part, N, max_parts, st);
-          reduce_partials(self->part, N, S, self->gint(iw + 1), N, scale2 + 1, 1.0f, st);
+          int S = colsum_s3(G.v, nullptr, M, self->partS, N, max_parts, st);
+          reduce_partials(self->partS, N, S, self->gint(iw + 1), N, scale2 + 1, 1.0f, st);
         }
       });
     };
     // ffn.2: data gradient first, then ONE pass over the pre-activations gives v (operand of ffn.2's weight gradient),
     // the gradient of the pre-activations and ffn.0's bias gradient
     e.gemm(g, t->T_ffn2, &gv, plain);
-    e.op([self, u0, gv, v, gu, M, C, ca_parts, scale2](cudaStream_t st) {
-      int S = chunkadd_fwd_bwd(u0, 4 * C, gv.v, v.v, gu.v, M, self->part, 4 * C, ca_parts, st);
-      if (S < 1) fail("chunkadd_fwd_bwd: partial buffer too small");
-      if (self->gint(9)) reduce_partials(self->part, 4 * C, S, self->gint(9), 4 * C, scale2 + 1, 1.0f, st);
+    e.op([self, u0, gv, v, gu, M, C, ca_parts](cudaStream_t st) {
+      int S = chunkadd_fwd_bwd(u0, 4 * C, gv.v, v.v, gu.v, M, self->partA, 4 * C, ca_parts, st);
+      if (S != ca_parts) fail("chunkadd_fwd_bwd: partial buffer too small");
+    });
+    leaf([self, C, ca_parts, scale2](cudaStream_t st) {
+      if (self->gint(9)) reduce_partials(self->partA, 4 * C, ca_parts, self->gint(9), 4 * C, scale2 + 1, 1.0f, st);
     });
     wgrad(g, v, 10, false);
     // ffn.0 (+ the residual around the ffn)
@@ -1871,16 +1903,22 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
       e.gemm(go1, t->T_dc3, nullptr, s);
     }
     // depthwise 3x3
-    e.op([self, gt2, gt1, t1, C, B, H, W, max_parts, scale2](cudaStream_t st) {
+    e.op([self, gt2, gt1, C, B, H, W](cudaStream_t st) {
       dwconv3x3_f32(gt2, C, self->w9c_flip, self->zero_bias, gt1.v, B, H, W, st);
+    });
+    leaf([self, gt2, t1, C, B, H, W, max_parts, scale2](cudaStream_t st) {
       if (self->gint(4) || self->gint(5)) {
-        int S = dw_wgrad(gt2, C, C, t1, C, B, H, W, self->part, C * 10, max_parts, st);
-        reduce_dw(self->part, C * 10, S, self->gint(4), self->gint(5), C, scale2 + 1, 1.0f, st);
+        int S = dw_wgrad(gt2, C, C, t1, C, B, H, W, self->partS, C * 10, max_parts, st);
+        reduce_dw(self->partS, C * 10, S, self->gint(4), self->gint(5), C, scale2 + 1, 1.0f, st);
       }
     });
-    e.op([self, gt1, t0, gt0, M, C, max_parts, scale2](cudaStream_t st) {
-      int S = wsilu_bwd(gt1.v, t0, C, gt0.v, M, self->part, C, 2 * max_parts, st);
-      if (self->gint(3)) reduce_partials(self->part, C, S, self->gint(3), C, scale2 + 1, 1.0f, st);
+    const int wb_parts = wsilu_bwd_parts(M, C, 2 * max_parts);
+    e.op([self, gt1, t0, gt0, M, C, max_parts, wb_parts](cudaStream_t st) {
+      int S = wsilu_bwd(gt1.v, t0, C, gt0.v, M, self->partB, C, 2 * max_parts, st);
+      if (S != wb_parts) fail("wsilu_bwd: unexpected number of partial rows");
+    });
+    leaf([self, C, wb_parts, scale2](cudaStream_t st) {
+      if (self->gint(3)) reduce_partials(self->partB, C, wb_parts, self->gint(3), C, scale2 + 1, 1.0f, st);
     });
     // dc.0 (+ the residual around dc, + the shortcut)
     wgrad(gt0, a, 2, true);
@@ -1890,18 +1928,22 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
       if (t->shortcut) s.res2 = &g;
       e.gemm(gt0, t->T_dc0, &ga, s);
     }
+    Act gxs = ad ? e.new_act(B, H, W, cin) : ga;
     if (ad) {
-      Act gxs = e.new_act(B, H, W, cin);
       wgrad(ga, xs, 0, false);
       e.gemm(ga, t->T_ad, &gxs, plain);
-      e.set_prog(&t->prog_bwd_tail);
-      e.op([self, gxs, B, H, W, cin, scale2](cudaStream_t st) {
-        if (self->gx) s3_to_nchw_scaled(gxs.v, self->gx, B, cin, H, W, scale2 + 1, st);
-      });
-    } else {
-      e.set_prog(&t->prog_bwd_tail);
-      e.op([self, ga, B, H, W, C, scale2](cudaStream_t st) {
-        if (self->gx) s3_to_nchw_scaled(ga.v, self->gx, B, C, H, W, scale2 + 1, st);
+    }
+    // join: the pass is over when both streams are
+    e.op([self](cudaStream_t st) {
+      if (!self->use_side) return;
+      CUDA_OK(cudaEventRecord(self->ev_join, self->side));
+      CUDA_OK(cudaStreamWaitEvent(st, self->ev_join, 0));
+    });
+    e.set_prog(&t->prog_bwd_tail);
+    {
+      const int cx = ad ? cin : C;
+      e.op([self, gxs, B, H, W, cx, scale2](cudaStream_t st) {
+        if (self->gx) s3_to_nchw_scaled(gxs.v, self->gx, B, cx, H, W, scale2 + 1, st);
       });
     }
     e.flush_chain();
@@ -1921,6 +1963,9 @@ extern "C" void dmc_dcb_train_destroy(dmc_dcb_train* t) {
   {
     DeviceGuard dg(t->e.device);
     cudaDeviceSynchronize();
+    if (t->side) cudaStreamDestroy(t->side);
+    if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+    if (t->ev_join) cudaEventDestroy(t->ev_join);
   }
   delete t;
 }

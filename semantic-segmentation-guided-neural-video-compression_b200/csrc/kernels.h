@@ -198,6 +198,7 @@ void mask_from_logits(const float* logits, float* mask, long long n, cudaStream_
 // ---------------- training mode (train.cu) ----------------
 void wsilu_rows(const float* in, float* out, long long n, cudaStream_t st);                       // fp32 rows, n % 4 == 0
 // out = g * wsilu'(pre) + per-block column sums of out; returns the number of partial rows
+int wsilu_bwd_parts(long long M, int C, int max_parts);
 int wsilu_bwd(View g, const float* pre, int ld, View out, long long M, float* part, int ldp, int max_parts, cudaStream_t st);
 // forward value v, pre-activation gradient gu and gu's per-block column sums in one pass; returns the number of partial rows
 int chunkadd_parts(long long M, int C2);      // partial rows chunkadd_fwd_bwd writes (size `part` for them)

@@ -97,8 +97,9 @@ __global__ void __launch_bounds__(256) k_wsilu_bwd(View g, const float* __restri
     part[(long long)blockIdx.x * ldp + j] = s;
   }
 }
-int wsilu_bwd(View g, const float* pre, int ld, View out, long long M, float* part, int ldp, int max_parts, cudaStream_t st) {
-  const int C8 = g.C / 8;
+// the number of partial rows wsilu_bwd writes for these sizes
+int wsilu_bwd_parts(long long M, int C, int max_parts) {
+  const int C8 = C / 8;
   int threads = 256;
   if (C8 > threads) threads = (C8 + 31) / 32 * 32;
   const int lanes = threads / C8;
@@ -107,6 +108,14 @@ int wsilu_bwd(View g, const float* pre, int ld, View out, long long M, float* pa
   if (blocks > want) blocks = want;
   if (blocks > max_parts) blocks = max_parts;
   if (blocks < 1) blocks = 1;
+  return blocks;
+}
+int wsilu_bwd(View g, const float* pre, int ld, View out, long long M, float* part, int ldp, int max_parts, cudaStream_t st) {
+  const int C8 = g.C / 8;
+  int threads = 256;
+  if (C8 > threads) threads = (C8 + 31) / 32 * 32;
+  const int lanes = threads / C8;
+  const int blocks = wsilu_bwd_parts(M, g.C, max_parts);
   const size_t smem = (size_t)lanes * C8 * 8 * sizeof(float);
   launch(k_wsilu_bwd, blocks, threads, smem, st, g, pre, ld, out, M, C8, part, ldp);
   return blocks;
