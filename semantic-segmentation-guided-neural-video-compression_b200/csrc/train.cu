@@ -42,10 +42,13 @@ static void optin_max_smem(K kernel) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
+// sigmoid with the hardware exponential and reciprocal (2 ulp): only used where the result feeds a gradient -- the
+// forward values the reference pins bit by bit never pass through here
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 // d/dx [ silu(4x) / 4 ] = sigmoid(v) * (1 + v * (1 - sigmoid(v))),  v = 4x          (layers.py:8-10)
 __device__ __forceinline__ float wsilu_grad(float x) {
   const float v = 4.0f * x;
-  const float s = 1.0f / (1.0f + expf(-v));
+  const float s = sigmoid_fast(v);
   return s * fmaf(v, 1.0f - s, 1.0f);
 }
 
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(256) k_chunkadd_fwd_bwd(const float* __restric
         for (int i = 0; i < 8; ++i) {
           // one exponential for the value and the derivative: s = sigmoid(4p); wsilu = p * s; wsilu' = s * (1 + 4p(1 - s))
           const float t = 4.0f * p[i];
-          const float sg = 1.0f / (1.0f + expf(-t));
+          const float sg = sigmoid_fast(t);
           o[i] += p[i] * sg;
           d[i] = g[i] * (sg * fmaf(t, 1.0f - sg, 1.0f));
           acc[half][i] += d[i];
@@ -261,10 +264,19 @@ __global__ void k_reduce_partials(const float* __restrict__ part, long long stri
   pdl_prologue_done();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float s = 0.0f;
-  for (int k = 0; k < S; ++k) s += part[(long long)k * stride + i];
+  // four independent partial sums keep four loads in flight (the loop is latency bound otherwise); the order of the
+  // additions is fixed by S alone
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  int k = 0;
+  for (; k + 3 < S; k += 4) {
+    s0 += part[(long long)k * stride + i];
+    s1 += part[(long long)(k + 1) * stride + i];
+    s2 += part[(long long)(k + 2) * stride + i];
+    s3 += part[(long long)(k + 3) * stride + i];
+  }
+  for (; k < S; ++k) s0 += part[(long long)k * stride + i];
   if (scale_dev) scale *= *scale_dev;
-  out[i] = s * scale;
+  out[i] = ((s0 + s1) + (s2 + s3)) * scale;
 }
 // many partial rows, few outputs (column sums): 32 outputs x 8 row lanes per block, the lanes combined in a fixed order
 __global__ void __launch_bounds__(256) k_reduce_partials_tall(const float* __restrict__ part, long long stride, int S,
@@ -275,8 +287,18 @@ __global__ void __launch_bounds__(256) k_reduce_partials_tall(const float* __res
   const int col = threadIdx.x & 31, lane = threadIdx.x >> 5;
   const long long i = (long long)blockIdx.x * 32 + col;
   float s = 0.0f;
-  if (i < n)
-    for (int k = lane; k < S; k += 8) s += part[(long long)k * stride + i];
+  if (i < n) {
+    float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int k = lane;
+    for (; k + 24 < S; k += 32) {
+      s += part[(long long)k * stride + i];
+      s1 += part[(long long)(k + 8) * stride + i];
+      s2 += part[(long long)(k + 16) * stride + i];
+      s3 += part[(long long)(k + 24) * stride + i];
+    }
+    for (; k < S; k += 8) s += part[(long long)k * stride + i];
+    s = (s + s1) + (s2 + s3);
+  }
   red[lane][col] = s;
   __syncthreads();
   if (lane == 0 && i < n) {
