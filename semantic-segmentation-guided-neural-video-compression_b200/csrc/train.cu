@@ -278,25 +278,26 @@ __global__ void k_reduce_partials(const float* __restrict__ part, long long stri
   if (scale_dev) scale *= *scale_dev;
   out[i] = ((s0 + s1) + (s2 + s3)) * scale;
 }
-// many partial rows, few outputs (column sums): 32 outputs x 8 row lanes per block, the lanes combined in a fixed order
-__global__ void __launch_bounds__(256) k_reduce_partials_tall(const float* __restrict__ part, long long stride, int S,
-                                                              float* __restrict__ out, long long n,
-                                                              const float* __restrict__ scale_dev, float scale) {
+// many partial rows, few outputs (column sums): 32 outputs x 32 row lanes per block, four loads in flight per thread, the
+// lanes combined in a fixed order
+__global__ void __launch_bounds__(1024) k_reduce_partials_tall(const float* __restrict__ part, long long stride, int S,
+                                                               float* __restrict__ out, long long n,
+                                                               const float* __restrict__ scale_dev, float scale) {
   pdl_prologue_done();
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   const int col = threadIdx.x & 31, lane = threadIdx.x >> 5;
   const long long i = (long long)blockIdx.x * 32 + col;
   float s = 0.0f;
   if (i < n) {
     float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
     int k = lane;
-    for (; k + 24 < S; k += 32) {
+    for (; k + 96 < S; k += 128) {
       s += part[(long long)k * stride + i];
-      s1 += part[(long long)(k + 8) * stride + i];
-      s2 += part[(long long)(k + 16) * stride + i];
-      s3 += part[(long long)(k + 24) * stride + i];
+      s1 += part[(long long)(k + 32) * stride + i];
+      s2 += part[(long long)(k + 64) * stride + i];
+      s3 += part[(long long)(k + 96) * stride + i];
     }
-    for (; k < S; k += 8) s += part[(long long)k * stride + i];
+    for (; k < S; k += 32) s += part[(long long)k * stride + i];
     s = (s + s1) + (s2 + s3);
   }
   red[lane][col] = s;
@@ -304,14 +305,14 @@ __global__ void __launch_bounds__(256) k_reduce_partials_tall(const float* __res
   if (lane == 0 && i < n) {
     float t = 0.0f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += red[r][col];
+    for (int r = 0; r < 32; ++r) t += red[r][col];
     if (scale_dev) scale *= *scale_dev;
     out[i] = t * scale;
   }
 }
 void reduce_partials(const float* part, long long stride, int S, float* out, long long n, const float* scale_dev,
                      float scale, cudaStream_t st) {
-  if (S >= 32 && n <= 65536) launch(k_reduce_partials_tall, cdiv_u(n, 32), 256, 0, st, part, stride, S, out, n, scale_dev, scale);
+  if (S >= 32 && n <= 65536) launch(k_reduce_partials_tall, cdiv_u(n, 32), 1024, 0, st, part, stride, S, out, n, scale_dev, scale);
   else launch(k_reduce_partials, cdiv_u(n, 256), 256, 0, st, part, stride, S, out, n, scale_dev, scale);
 }
 
