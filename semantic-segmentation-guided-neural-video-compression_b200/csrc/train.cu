@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(1024) k_reduce_partials_tall(const float* __re
 }
 void reduce_partials(const float* part, long long stride, int S, float* out, long long n, const float* scale_dev,
                      float scale, cudaStream_t st) {
-  if (S >= 32 && n <= 65536) launch(k_reduce_partials_tall, cdiv_u(n, 32), 1024, 0, st, part, stride, S, out, n, scale_dev, scale);
+  if (S >= 32 && n <= 8192) launch(k_reduce_partials_tall, cdiv_u(n, 32), 1024, 0, st, part, stride, S, out, n, scale_dev, scale);
   else launch(k_reduce_partials, cdiv_u(n, 256), 256, 0, st, part, stride, S, out, n, scale_dev, scale);
 }
 
