@@ -60,6 +60,12 @@ def _need_cuda(*tensors):
             raise RuntimeError("dmc_b200.training: CUDA tensors required (there is no CPU path)")
 
 
+def _dense(t: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous, 16-byte aligned (a contiguous view at an odd storage offset is copied)."""
+    t = t.contiguous().float()
+    return t.clone() if t.data_ptr() % 16 else t
+
+
 def _stream(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -120,7 +126,7 @@ class _DepthConvBlockFn(torch.autograd.Function):
     def forward(ctx, x, quant_step, shortcut, terms, owner, *w12):
         _need_cuda(x)
         lib = _capi.load()
-        x = x.contiguous().float()
+        x = _dense(x)
         B, cin, H, W = x.shape
         cout = w12[2].shape[0]
         has_ad = w12[0] is not None
@@ -163,7 +169,7 @@ class _DepthConvBlockFn(torch.autograd.Function):
         cout = w12[2].shape[0]
         ws = [None if w is None else w.detach().contiguous().float() for w in w12]
         qs = quant_step.detach().reshape(cout).contiguous().float() if has_qs else None
-        g = grad_out.contiguous().float()       # (scaled into fp16's range inside the engine)
+        g = _dense(grad_out)                    # (scaled into fp16's range inside the engine)
         need = ctx.needs_input_grad            # (x, quant_step, shortcut, terms, owner, *w12)
         gx = torch.empty_like(x) if need[0] else None
         sizes = [0 if (w is None or not need[5 + i]) else w.numel() for i, w in enumerate(w12)]

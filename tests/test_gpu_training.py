@@ -260,3 +260,23 @@ def test_blocks_of_equal_geometry_share_a_workspace_but_not_weights():
         assert _relmax(xg.grad, xr.grad) < 2e-4
         assert _relmax(blk.ffn[0].weight.grad, ref.ffn0.weight.grad) < 2e-4
         assert _relmax(blk.dc[2].weight.grad, ref.dc2.weight.grad) < 2e-4
+
+
+def test_unaligned_and_strided_inputs_are_accepted():
+    """A contiguous view at an odd storage offset (not 16-byte aligned) and a channels-last tensor."""
+    torch.manual_seed(4)
+    blk = T.DepthConvBlock(32, 32).cuda().train()
+    base = torch.randn(1 + 32 * 6 * 7, device="cuda")
+    x_odd = base[1:].view(1, 32, 6, 7)                      # data_ptr % 16 == 4
+    assert x_odd.data_ptr() % 16 != 0 and x_odd.is_contiguous()
+    x_ref = x_odd.clone().requires_grad_(True)
+    x_cl = x_odd.clone().to(memory_format=torch.channels_last).requires_grad_(True)
+    y_ref = blk(x_ref)
+    g = torch.randn_like(y_ref)
+    y_ref.backward(g)
+    for xv in (x_odd.detach().requires_grad_(True), x_cl):
+        blk.zero_grad()
+        y = blk(xv)
+        y.backward(g)
+        assert torch.equal(y, y_ref)
+        assert torch.allclose(xv.grad, x_ref.grad, rtol=0, atol=0)
