@@ -1767,7 +1767,7 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
       }
     }
     // partial sums: the largest of the weight-gradient splits, the column sums and the depthwise partial rows
-    const int max_parts = 2 * num_sms();
+    const int max_parts = 8 * num_sms();
     const int ca_parts = chunkadd_parts(M, 2 * C);
     size_t pf = (size_t)max_parts * 4 * C;                      // column sums of the widest tensor
     pf = std::max(pf, (size_t)max_parts * C * 10);              // depthwise partial rows

@@ -214,7 +214,7 @@ int dw_wgrad(const float* g, int ldg, int C, const float* t, int ld, int B, int 
 void flip_dw_weight(const float* w9c, float* out, int C, cudaStream_t st);
 void reduce_dw(const float* part, long long stride, int S, float* gw, float* gb, int C, const float* scale_dev, float scale,
                cudaStream_t st);
-// scale2 = {2^floor(peak_log2 - log2 max|g|), its reciprocal}; part: 2 * num_sms() floats of scratch
+// scale2 = {2^floor(peak_log2 - log2 max|g|), its reciprocal}; part: 8 * num_sms() floats of scratch
 void grad_scale(const float* g, long long n, float peak_log2, float* part, float* scale2, cudaStream_t st);
 void nchw_to_s3_scaled(const float* x, View out, int B, int C, int H, int W, const float* chan, const float* gscale,
                        cudaStream_t st);

@@ -249,7 +249,7 @@ int colsum_s3(View g, const View* h, long long M, float* part, int ldp, int max_
   if (C8 > threads) threads = (C8 + 31) / 32 * 32;
   const int lanes = threads / C8;
   int blocks = (int)((M + lanes - 1) / lanes);
-  const int want = 2 * num_sms();
+  const int want = 8 * num_sms();      // (2 per SM: 2.9 TB/s at 24 % occupancy; more rows in flight)
   if (blocks > want) blocks = want;
   if (blocks > max_parts) blocks = max_parts;
   if (blocks < 1) blocks = 1;
@@ -372,8 +372,99 @@ __global__ void __launch_bounds__(256) k_dw_wgrad(const float* __restrict__ g, i
     part[(long long)blockIdx.x * ldp + j] = s;
   }
 }
+// Strip version: a thread owns 4 channels of ONE image column and walks down a strip of rows with the 3 x 3 window of t
+// in registers (three new float4 loads + one of g per pixel instead of nine + one: the one-pixel-per-iteration kernel
+// above re-reads every t row three times and ran at 1.3 TB/s of algorithmic bytes, 20 % of the HBM roofline).
+__global__ void __launch_bounds__(256, 2)
+k_dw_wgrad_strip(const float* __restrict__ g, int ldg, const float* __restrict__ t, int ld, int B, int H, int W, int C4, int lanes,
+                 int WG, int hs, int HS, float* __restrict__ part, int ldp) {
+  pdl_prologue_done();
+  extern __shared__ float red[];        // [lanes][C4 * 4 * 10]
+  const int c4 = threadIdx.x % C4, ln = threadIdx.x / C4;
+  int blk = blockIdx.x;
+  const int wg = blk % WG;
+  blk /= WG;
+  const int hsi = blk % HS, b = blk / HS;
+  const int w = wg * lanes + ln;
+  const int h0 = hsi * hs, h1 = min(H, h0 + hs);
+  float acc[9][4], accb[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
+  if (ln < lanes && w < W) {
+    const int c = c4 * 4;
+    const long long img = (long long)b * H * W;
+    float4 win[3][3];
+    auto load_row = [&](int h, float4 (&r)[3]) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ww = w + kx - 1;
+        r[kx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if ((unsigned)h < (unsigned)H && (unsigned)ww < (unsigned)W)
+          r[kx] = *reinterpret_cast<const float4*>(t + (img + (long long)h * W + ww) * ld + c);
+      }
+    };
+    load_row(h0 - 1, win[0]);
+    load_row(h0, win[1]);
+    for (int h = h0; h < h1; ++h) {
+      load_row(h + 1, win[2]);
+      const float4 gv = *reinterpret_cast<const float4*>(g + (img + (long long)h * W + w) * ldg + c);
+      accb[0] += gv.x; accb[1] += gv.y; accb[2] += gv.z; accb[3] += gv.w;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 tv = win[ky][kx];
+          float* a = acc[ky * 3 + kx];
+          a[0] = fmaf(gv.x, tv.x, a[0]); a[1] = fmaf(gv.y, tv.y, a[1]);
+          a[2] = fmaf(gv.z, tv.z, a[2]); a[3] = fmaf(gv.w, tv.w, a[3]);
+        }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) { win[0][kx] = win[1][kx]; win[1][kx] = win[2][kx]; }
+    }
+  }
+  const int n = C4 * 40;
+  if (ln < lanes) {
+    float* r = red + (long long)ln * n + c4 * 40;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) r[i * 10 + k] = acc[k][i];
+      r[i * 10 + 9] = accb[i];
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    float sacc = 0.0f;
+    for (int r = 0; r < lanes; ++r) sacc += red[(long long)r * n + j];
+    part[(long long)blockIdx.x * ldp + j] = sacc;
+  }
+}
 int dw_wgrad(const float* g, int ldg, int C, const float* t, int ld, int B, int H, int W, float* part, int ldp, int max_parts,
              cudaStream_t st) {
+  static int strip = -1;
+  if (strip < 0) {
+    const char* v = getenv("DMC_DW_WGRAD_STRIP");       // =0: the one-pixel-per-iteration kernel (A/B runs)
+    strip = (v && v[0] == '0') ? 0 : 1;
+  }
+  if (strip && C % 4 == 0 && ld % 4 == 0 && ldg % 4 == 0 && C / 4 <= 256) {
+    const int C4 = C / 4;
+    const int lanes = std::max(1, 256 / C4);
+    const int WG = (W + lanes - 1) / lanes;
+    int HS = (4 * num_sms() + B * WG - 1) / (B * WG);        // strips per image column group: ~4 blocks per SM
+    if (HS < 1) HS = 1;
+    if (HS > H) HS = H;
+    if ((long long)B * WG * HS > max_parts) HS = std::max(1, max_parts / (B * WG));
+    const int hs = (H + HS - 1) / HS;
+    HS = (H + hs - 1) / hs;
+    const long long blocks = (long long)B * WG * HS;
+    if (blocks <= max_parts) {
+      const size_t smem = (size_t)lanes * C4 * 40 * sizeof(float);
+      optin_max_smem(k_dw_wgrad_strip);
+      launch(k_dw_wgrad_strip, (unsigned)blocks, C4 * lanes, smem, st, g, ldg, t, ld, B, H, W, C4, lanes, WG, hs, HS, part, ldp);
+      return (int)blocks;
+    }
+  }
+
   const int C8 = C / 8;
   int threads = 256;
   int lanes = threads / C8;
@@ -654,7 +745,7 @@ __global__ void k_grad_scale(const float* __restrict__ part, int n, const float*
 }
 void grad_scale(const float* g, long long n, float peak_log2, float* part, float* scale2, cudaStream_t st) {
   const long long n4 = n / 4;
-  int blocks = (int)std::min<long long>((n4 + 255) / 256, 2LL * num_sms());
+  int blocks = (int)std::min<long long>((n4 + 255) / 256, 8LL * num_sms());
   if (blocks < 1) blocks = 1;
   launch(k_absmax_part, blocks, 256, 0, st, g, n4, part);
   launch(k_grad_scale, 1, 256, 0, st, (const float*)part, blocks, g + n4 * 4, (int)(n - n4 * 4), peak_log2, scale2);
@@ -727,7 +818,7 @@ __global__ void __launch_bounds__(256) k_nchw_dot(const float* __restrict__ a, c
 }
 // returns the number of partial rows (C floats each)
 int nchw_dot(const float* a, const float* b, int B, int C, long long HW, float* part, int max_parts, cudaStream_t st) {
-  int chunks = (int)std::min<long long>((HW + 2047) / 2048, (2LL * num_sms() + C - 1) / C);
+  int chunks = (int)std::min<long long>((HW + 2047) / 2048, (8LL * num_sms() + C - 1) / C);
   if (chunks > max_parts) chunks = max_parts;
   if (chunks < 1) chunks = 1;
   const long long per = (HW + chunks - 1) / chunks;
