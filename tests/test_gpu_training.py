@@ -280,3 +280,23 @@ def test_unaligned_and_strided_inputs_are_accepted():
         y.backward(g)
         assert torch.equal(y, y_ref)
         assert torch.allclose(xv.grad, x_ref.grad, rtol=0, atol=0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_block_on_a_device_that_is_not_current():
+    """model.to('cuda:1') while cuda:0 stays the current device (what DDP ranks with CUDA_VISIBLE_DEVICES unset do)."""
+    torch.manual_seed(6)
+    ref = RefDCB(64, 64).double()
+    x = torch.randn(1, 64, 10, 14, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    ref(xr).sum().backward()
+    assert torch.cuda.current_device() == 0
+    for dev in ("cuda:1", "cuda:0"):
+        blk = T.DepthConvBlock(64, 64).to(dev).train()
+        _copy_params(ref, blk)
+        xg = x.float().to(dev).requires_grad_(True)
+        y = blk(xg)
+        y.sum().backward()
+        assert y.device == torch.device(dev) and torch.cuda.current_device() == 0
+        assert _relmax(xg.grad, xr.grad) < 1e-5
+        assert _relmax(blk.ffn[0].weight.grad, ref.ffn0.weight.grad) < 1e-5
