@@ -1664,6 +1664,13 @@ struct dmc_dcb_train {
   float *out = nullptr, *gx = nullptr, *gqs = nullptr;
   float* gw[12] = {};            // caller's destinations (this call)
   float* gint(int i) const { return (gmask >> i & 1) ? gflat + goff[i] : nullptr; }
+  ~dmc_dcb_train() {
+    DeviceGuard dg(e.device);
+    cudaDeviceSynchronize();
+    if (side) cudaStreamDestroy(side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+  }
 };
 
 namespace {
@@ -1961,17 +1968,7 @@ extern "C" int dmc_dcb_train_create(int batch, int height, int width, int cin, i
   return DMC_OK;
 }
 
-extern "C" void dmc_dcb_train_destroy(dmc_dcb_train* t) {
-  if (!t) return;
-  {
-    DeviceGuard dg(t->e.device);
-    cudaDeviceSynchronize();
-    if (t->side) cudaStreamDestroy(t->side);
-    if (t->ev_fork) cudaEventDestroy(t->ev_fork);
-    if (t->ev_join) cudaEventDestroy(t->ev_join);
-  }
-  delete t;
-}
+extern "C" void dmc_dcb_train_destroy(dmc_dcb_train* t) { delete t; }
 
 extern "C" const char* dmc_dcb_train_last_error(const dmc_dcb_train* t) {
   return t ? t->e.error.c_str() : g_create_error.c_str();
