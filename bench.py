@@ -24,7 +24,10 @@ contains the I frames of the following GOPs (their time counts, their frames do 
 reference modules from oracle/_ref (copied there by oracle/make_ref.py; kind "reference"), or the oracle port when
 that copy is absent (kind "port"), all host threads, each step one full-size P-frame forward.
 N = 1 also reports `gpu_eager_baseline`: the same unmodified reference modules run eagerly by PyTorch on the same
-B200 (fp32 with TF32 off = the parity-grade arithmetic, default TF32, autocast bf16).
+B200 (fp32 with TF32 off = the parity-grade arithmetic, default TF32, autocast bf16), and the two training-mode figures of
+SURVEY 8(f) rank 2 (not part of the headline): `training_block` (one DepthConvBlock forward + backward, engine against
+the layer's arithmetic in torch eager) and `training_step` (forward in train mode + loss + backward of the reference's own
+`performance` model class at full size, built from the engine's training blocks against the stock class).
 """
 from __future__ import annotations
 
@@ -300,6 +303,79 @@ def gpu_eager_baseline(dev, x_frames, n=5):
     return out
 
 
+def training_step(dev, x_frames, n=3):
+    """SURVEY 8(f) rank 2 at model scale: one training step (forward in train mode + the trainer's loss + backward) of the
+    reference's OWN `performance` model class at full size -- built from dmc_b200.training's blocks
+    (training.reference_patched + adopt) against the stock class (oracle/_ref, unmodified) in torch eager.  ms per step,
+    CUDA events around `n` steps after one warm-up step."""
+    import torch.nn.functional as F
+    import dmc_b200 as D
+    from oracle import make_ref
+    if not make_ref.available():
+        return {"unavailable": "oracle/_ref not present"}
+    out = {"what": "performance P-frame model, 1920x1280, B = 1, after_i = False: forward (train mode) + bpp_y + bpp_z + "
+                   "256 * mse + backward; ms per step"}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.get_float32_matmul_precision())
+    T = D.training
+    try:
+        R = make_ref.load_reference()
+        x = x_frames[:, 1]
+        target = x[:, :3].contiguous()
+        torch.manual_seed(3)
+        dpb = {"frame": x_frames[:, 0, :3].contiguous(),
+               "feature": torch.randn(x.shape[0], 256, x.shape[2] // 8, x.shape[3] // 8, device=dev) * 0.5}
+        torch.manual_seed(11)
+        stock = R["performance"]().to(dev).train()
+        mods = [sys.modules[k] for k in ("src.layers.layers", "src.refactor.common_model", "src.refactor.seg_video_model")]
+        with T.reference_patched(*mods):
+            ours = R["performance"]().to(dev).train()
+        T.adopt(ours, formula=1)
+        ours.load_state_dict(stock.state_dict())
+
+        def timed(model, amp):
+            def step():
+                model.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                    r = model(x, BASE_QP, dpb, after_i=False)
+                loss = r["bpp_y"].mean() + r["bpp_z"].mean() + 256.0 * F.mse_loss(r["dpb"]["frame"].float(), target)
+                loss.backward()
+                return loss
+            step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / n, float(loss.detach())
+
+        lib = D._capi.load()
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        torch.set_float32_matmul_precision("highest")
+        l0 = lib.dmc_kernel_launches()
+        out["dmc_b200_blocks_ms"], out["dmc_b200_blocks_loss"] = timed(ours, False)
+        out["gpu_launches_per_step"] = int((lib.dmc_kernel_launches() - l0) // (n + 1))
+        T.release_handles()
+        del ours
+        torch.cuda.empty_cache()
+        for name, tf32, prec, amp in (("stock_fp32_tf32_off", False, "highest", False),
+                                      ("stock_fp32_tf32_default", True, "medium", False),
+                                      ("stock_autocast_bf16", True, "medium", True)):
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.set_float32_matmul_precision(prec)
+            out[name + "_ms"], out[name + "_loss"] = timed(stock, amp)
+        del stock
+    except Exception as ex:   # noqa: BLE001
+        out["error"] = repr(ex)[:300]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old[0], old[1]
+        torch.set_float32_matmul_precision(old[2])
+        T.release_handles()
+        torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -546,6 +622,7 @@ def main():
             line["gpu_eager_baseline"] = gpu_eager_baseline(dev, devc[0])
         if world == 1 and not args.no_training_block:
             line["training_block"] = training_block(dev)
+            line["training_step"] = training_step(dev, devc[0])
         if world == 1 and not args.no_cpu_baseline:
             fps, threads, sample, _, kind = cpu_reference_fps(3, 0, budget_s=25.0)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample}
