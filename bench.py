@@ -307,7 +307,7 @@ def training_step(dev, x_frames, n=3):
     """SURVEY 8(f) rank 2 at model scale: one training step (forward in train mode + the trainer's loss + backward) of the
     reference's OWN `performance` model class at full size -- built from dmc_b200.training's blocks
     (training.reference_patched + adopt) against the stock class (oracle/_ref, unmodified) in torch eager.  ms per step,
-    CUDA events around `n` steps after one warm-up step."""
+    CUDA events around `n` steps after two warm-up steps."""
     import torch.nn.functional as F
     import dmc_b200 as D
     from oracle import make_ref
@@ -340,7 +340,8 @@ def training_step(dev, x_frames, n=3):
                 loss = r["bpp_y"].mean() + r["bpp_z"].mean() + 256.0 * F.mse_loss(r["dpb"]["frame"].float(), target)
                 loss.backward()
                 return loss
-            step()
+            for _ in range(2):         # (the engine captures its backward graphs in the second step)
+                step()
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -355,7 +356,7 @@ def training_step(dev, x_frames, n=3):
         torch.set_float32_matmul_precision("highest")
         l0 = lib.dmc_kernel_launches()
         out["dmc_b200_blocks_ms"], out["dmc_b200_blocks_loss"] = timed(ours, False)
-        out["gpu_launches_per_step"] = int((lib.dmc_kernel_launches() - l0) // (n + 1))
+        out["gpu_launches_per_step"] = int((lib.dmc_kernel_launches() - l0) // (n + 2))
         T.release_handles()
         del ours
         torch.cuda.empty_cache()
