@@ -70,10 +70,15 @@ if only in ("", "engine"):
     l0 = lib.dmc_kernel_launches()
     step(ours)
     launches = lib.dmc_kernel_launches() - l0
-    ms, loss = time_steps(ours)
-    print(json.dumps({"impl": "reference model + dmc_b200 training blocks (3-term split fp16, fp32-grade)", "H": H, "W": W,
-                      "train_step_ms": round(ms, 2), "loss": loss, "engine_kernel_launches_per_step": int(launches),
-                      "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1)}), flush=True)
+    # the blocks are fp32-grade either way; what torch still runs between them is timed at both settings
+    for rest, tf32 in (("torch remainder fp32, TF32 off", False), ("torch remainder at default TF32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        ms, loss = time_steps(ours)
+        print(json.dumps({"impl": "reference model + dmc_b200 training blocks (3-term split fp16, fp32-grade); " + rest,
+                          "H": H, "W": W, "train_step_ms": round(ms, 2), "loss": loss,
+                          "engine_kernel_launches_first_step": int(launches),
+                          "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1)}), flush=True)
 T.release_handles()
 del ours
 torch.cuda.empty_cache()
