@@ -200,6 +200,19 @@ int dmc_dcb_train_forward(dmc_dcb_train* t, const float* x, const float* const* 
 int dmc_dcb_train_backward(dmc_dcb_train* t, const float* x, const float* const* weights12, const float* quant_step,
                            const float* out, const float* grad_out, float* grad_x, float* const* grad_weights12,
                            float* grad_quant_step, int weights_unchanged, void* stream);
+/* A plain 1x1 convolution (stride 1, no padding, no groups) with its backward pass: the nn.Conv2d(cin, cout, 1) layers of
+ * the models outside the DepthConvBlocks (feature_adaptor_p, encoder.conv1, decoder.proj, the recon head, sub-pixel and
+ * prior heads).  Same conventions as the block entries above; weight (cout, cin, 1, 1), bias (cout) or NULL; any of the
+ * gradient destinations may be NULL (x is only needed when grad_weight is wanted). */
+typedef struct dmc_conv1x1_train dmc_conv1x1_train;
+int dmc_conv1x1_train_create(int batch, int height, int width, int cin, int cout, int has_bias, int terms,
+                             dmc_conv1x1_train** out);
+void dmc_conv1x1_train_destroy(dmc_conv1x1_train* t);
+const char* dmc_conv1x1_train_last_error(const dmc_conv1x1_train* t);
+int dmc_conv1x1_train_forward(dmc_conv1x1_train* t, const float* x, const float* weight, const float* bias, float* out,
+                              int weights_unchanged, void* stream);
+int dmc_conv1x1_train_backward(dmc_conv1x1_train* t, const float* x, const float* weight, const float* grad_out,
+                               float* grad_x, float* grad_weight, float* grad_bias, int weights_unchanged, void* stream);
 /* AdaptiveQuant in training mode (layers/inference.py:16-27).  mode 0 "ste": out = round(x) (the straight-through
  * gradient is the identity); mode 1 "noise": out = x + noise with noise ~ U(-half_bin, half_bin) drawn by the caller. */
 int dmc_op_quant_train(const float* x, const float* noise, float* out, int64_t n, int mode, void* stream);

@@ -2028,6 +2028,189 @@ extern "C" int dmc_dcb_train_backward(dmc_dcb_train* t, const float* x, const fl
   });
 }
 
+// ---------------------------------------------------------------- training mode: a plain 1x1 convolution
+// The 1x1 convolutions of the models OUTSIDE the DepthConvBlocks (feature_adaptor_p, encoder.conv1, decoder.proj, the
+// recon head, the sub-pixel convolutions' 1x1 kernels, the prior heads): same pieces as the block -- forward = one
+// contraction of the frame engine, data gradient = the contraction with the transposed weight, weight gradient =
+// k_wgrad_umma, bias gradient = a column sum -- so that a training step is fp32-grade end to end without paying
+// cuDNN's fp32 (TF32 off) rate for them.
+struct dmc_conv1x1_train {
+  dmc_engine e;
+  std::vector<dmc_engine::Op> prog_bwd_head, prog_bwd, prog_bwd_tail;
+  int cin = 0, cout = 0, terms = 3;
+  bool has_bias = true, packed = false, packed_T = false;
+  Conv *fw = nullptr, *T = nullptr;
+  float *gflat = nullptr, *scale2 = nullptr, *partS = nullptr, *partB = nullptr;
+  int gmask = 0;                 // bit 0: weight gradient, bit 1: bias gradient, bit 2: input gradient
+  long long bwd_calls = 0;
+  const float *x = nullptr, *gout = nullptr;
+  float *out = nullptr, *gx = nullptr, *gw = nullptr, *gb = nullptr;
+  ~dmc_conv1x1_train() {
+    DeviceGuard dg(e.device);
+    cudaDeviceSynchronize();
+  }
+};
+
+extern "C" int dmc_conv1x1_train_create(int batch, int height, int width, int cin, int cout, int has_bias, int terms,
+                                        dmc_conv1x1_train** out) {
+  if (!out) return DMC_E_INVALID;
+  *out = nullptr;
+  dmc_conv1x1_train* t = nullptr;
+  int rc = guarded(nullptr, [&] {
+    if (batch < 1 || height < 1 || width < 1) fail("dmc_conv1x1_train_create: bad geometry");
+    if (cin < 32 || cout < 32 || cin % 16 || cout % 16) fail("dmc_conv1x1_train_create: channels must be multiples of 16, at least 32");
+    if (terms != 1 && terms != 3) fail("dmc_conv1x1_train_create: terms must be 1 or 3");
+    t = new dmc_conv1x1_train();
+    dmc_engine& e = t->e;
+    CUDA_OK(cudaGetDevice(&e.device));
+    e.variant = -1; e.B = batch; e.H = height; e.W = width;
+    t->cin = cin; t->cout = cout; t->terms = terms; t->has_bias = has_bias != 0;
+    const int B = batch, H = height, W = width;
+    const long long M = (long long)B * H * W;
+    t->fw = e.add_conv("c", cin, cout, 1, 1, 0);
+    t->T = e.add_conv("T", cout, cin, 1, 1, 0);
+    pack_gemm_bias(nullptr, cin, t->T->g, nullptr);
+    pack_gemm_bias(nullptr, cout, t->fw->g, nullptr);
+    t->gflat = e.new_f32((size_t)cout * cin + cout);
+    t->scale2 = e.new_f32(2);
+    {
+      const char* v = getenv("DMC_TRAIN_SHARED_WORKSPACE");
+      if (!(v && v[0] == '0')) {
+        char key[160];
+        snprintf(key, sizeof key, "conv1x1:dev%d:%dx%dx%d:%d>%d:t%d", e.device, B, H, W, cin, cout, terms);
+        e.pool_prefix = key;
+      }
+    }
+    const int max_parts = 8 * num_sms();
+    t->partS = e.new_f32(std::max((size_t)max_parts * cout, (size_t)wgrad_splits(M, cout, cin) * cout * cin));
+    t->partB = e.new_f32((size_t)max_parts);
+    dmc_conv1x1_train* self = t;
+    EpiSpec plain;
+    plain.nsplit = terms;
+    // ---- forward
+    e.prog = &e.prog_common;
+    {
+      Act fin = e.new_act(B, H, W, cin), fout = e.new_act(B, H, W, cout);
+      e.op([self, fin, B, H, W, cin](cudaStream_t st) { nchw_to_s3(self->x, fin.v, B, cin, H, W, st); });
+      e.gemm(fin, t->fw, &fout, plain);
+      e.op([self, fout, B, H, W, cout](cudaStream_t st) { s3_to_nchw(fout.v, self->out, B, cout, H, W, st); });
+      e.flush_chain();
+    }
+    // ---- backward: head (caller tensors -> planes), body (the handle's buffers only: one graph), tail
+    Act xs = e.new_act(B, H, W, cin), g = e.new_act(B, H, W, cout), gxs = e.new_act(B, H, W, cin);
+    float* scale2 = t->scale2;
+    e.set_prog(&t->prog_bwd_head);
+    e.op([self, xs, g, B, H, W, cin, cout, M, scale2](cudaStream_t st) {
+      if (self->gmask & 1) nchw_to_s3(self->x, xs.v, B, cin, H, W, st);
+      grad_scale(self->gout, M * cout, grad_peak_log2(), self->partB, scale2, st);
+      nchw_to_s3_scaled(self->gout, g.v, B, cout, H, W, nullptr, scale2, st);
+    });
+    e.set_prog(&t->prog_bwd);
+    {
+      const int terms_ = terms;
+      e.op([self, g, xs, M, cin, cout, terms_, max_parts, scale2](cudaStream_t st) {
+        if (self->gmask & 1) {
+          int S = wgrad_s3(g.v, xs.v, M, terms_, self->partS, st);
+          if (S < 1) fail("weight gradient launch: %s", wgrad_umma_last_error());
+          reduce_partials(self->partS, (long long)cout * cin, S, self->gflat, (long long)cout * cin, scale2 + 1, 1.0f, st);
+        }
+        if (self->gmask & 2) {
+          int S = colsum_s3(g.v, nullptr, M, self->partS, cout, max_parts, st);
+          reduce_partials(self->partS, cout, S, self->gflat + (size_t)cout * cin, cout, scale2 + 1, 1.0f, st);
+        }
+      });
+    }
+    // (the data gradient is staged unconditionally; the body graph is keyed by the mask and skips it when unwanted)
+    e.gemm(g, t->T, &gxs, plain);
+    e.set_prog(&t->prog_bwd_tail);
+    e.op([self, gxs, B, H, W, cin, scale2](cudaStream_t st) {
+      if (self->gx) s3_to_nchw_scaled(gxs.v, self->gx, B, cin, H, W, scale2 + 1, st);
+    });
+    e.flush_chain();
+    e.prog = &e.prog_common;
+    CUDA_OK(cudaDeviceSynchronize());
+  });
+  if (rc != DMC_OK) {
+    delete t;
+    return rc;
+  }
+  *out = t;
+  return DMC_OK;
+}
+
+extern "C" void dmc_conv1x1_train_destroy(dmc_conv1x1_train* t) { delete t; }
+extern "C" const char* dmc_conv1x1_train_last_error(const dmc_conv1x1_train* t) {
+  return t ? t->e.error.c_str() : g_create_error.c_str();
+}
+
+namespace {
+void conv1x1_train_load(dmc_conv1x1_train& t, const float* weight, const float* bias, bool backward, bool need_T,
+                        bool unchanged, cudaStream_t st) {
+  if (!unchanged) t.packed = t.packed_T = false;
+  if (backward && !need_T) return;
+  if (!weight) fail("null weight");
+  if (t.has_bias && !backward && !bias) fail("bias required: the handle was created with has_bias");
+  if (!backward && !t.packed) {
+    pack_gemm_weight(weight, t.cout, t.cin, 1, 1, t.fw->g, st);
+    if (t.has_bias) pack_gemm_bias(bias, t.cout, t.fw->g, st);
+    t.packed = true;
+  }
+  if (backward && !t.packed_T) {
+    pack_gemm_weight(weight, t.cin, t.cout, 1, 1, t.T->g, st, true);
+    t.packed_T = true;
+  }
+}
+}  // namespace
+
+extern "C" int dmc_conv1x1_train_forward(dmc_conv1x1_train* t, const float* x, const float* weight, const float* bias,
+                                         float* out, int weights_unchanged, void* stream) {
+  if (!t) return DMC_E_INVALID;
+  return guarded(&t->e, [&] {
+    if (!x || !out) fail("dmc_conv1x1_train_forward: null tensor");
+    DeviceGuard dg(t->e.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    conv1x1_train_load(*t, weight, bias, false, false, weights_unchanged != 0, st);
+    t->x = x; t->out = out;
+    t->e.cur.qp = 0;
+    t->e.run(t->e.prog_common, st);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+extern "C" int dmc_conv1x1_train_backward(dmc_conv1x1_train* t, const float* x, const float* weight, const float* grad_out,
+                                          float* grad_x, float* grad_weight, float* grad_bias, int weights_unchanged,
+                                          void* stream) {
+  if (!t) return DMC_E_INVALID;
+  return guarded(&t->e, [&] {
+    if (!grad_out || (grad_weight && !x)) fail("dmc_conv1x1_train_backward: null tensor");
+    if ((uintptr_t)grad_out % 16) fail("dmc_conv1x1_train_backward: grad_out must be 16-byte aligned");
+    DeviceGuard dg(t->e.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    conv1x1_train_load(*t, weight, nullptr, true, grad_x != nullptr, weights_unchanged != 0, st);
+    t->x = x; t->gout = grad_out; t->gx = grad_x; t->gw = grad_weight; t->gb = grad_bias;
+    t->gmask = (grad_weight ? 1 : 0) | (grad_bias ? 2 : 0) | (grad_x ? 4 : 0);
+    dmc_engine& e = t->e;
+    e.cur.qp = 0;
+    e.run(t->prog_bwd_head, st);
+    // body: [0] = weight / bias gradients, [1] = the data-gradient chain (skipped when the input needs no gradient)
+    auto body = [&](cudaStream_t s2) {
+      for (size_t i = 0; i < t->prog_bwd.size(); ++i)
+        if (i == 0 || (t->gmask & 4)) t->prog_bwd[i](s2);
+    };
+    if (t->bwd_calls++ > 0) e.run_graph(0x200000ull | (uint64_t)t->gmask, st, body);
+    else body(st);
+    e.run(t->prog_bwd_tail, st);
+    const size_t wn = (size_t)t->cout * t->cin;
+    if (grad_weight && grad_bias && grad_bias == grad_weight + wn) {
+      CUDA_OK(cudaMemcpyAsync(grad_weight, t->gflat, (wn + t->cout) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (grad_weight) CUDA_OK(cudaMemcpyAsync(grad_weight, t->gflat, wn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (grad_bias) CUDA_OK(cudaMemcpyAsync(grad_bias, t->gflat + wn, t->cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
 extern "C" int dmc_op_quant_train(const float* x, const float* noise, float* out, int64_t n, int mode, void* stream) {
   if (!x || !out || n < 0 || (mode != 0 && mode != 1) || (mode == 1 && !noise)) return DMC_E_INVALID;
   if (n) quant_train(x, noise, out, (long long)n, mode, (cudaStream_t)stream);

@@ -28,11 +28,11 @@ from torch import nn
 from . import _capi
 
 __all__ = ["DepthConvBlock", "AdaptiveQuant", "depth_conv_block", "gaussian_bits", "quant_ste", "quant_noise",
-           "release_handles", "invalidate", "reference_patched", "adopt"]
+           "release_handles", "invalidate", "reference_patched", "adopt", "Conv2d"]
 
 #: DepthConvBlock handles kept alive -- one per (owner module, geometry), each with its own workspace (~1.2 GB at
 #: 160x240x256, 1/4 of that per halving of the resolution) and packed weights; least recently used first out
-max_handles = 64
+max_handles = 96
 
 #: True (or DMC_B200_STRICT_FINITE=1): every block output is checked for non-finite / fp16-saturated values and the
 #: reference's NaNGuard error is raised at the call (one host sync per block).  Activations pass through fp16 split planes:
@@ -81,12 +81,16 @@ def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
     return arr
 
 
-def release_handles():
-    """Frees every cached DepthConvBlock workspace."""
+def _destroy(key, h):
     lib = _capi.load()
+    (lib.dmc_conv1x1_train_destroy if key[0] == "conv1x1" else lib.dmc_dcb_train_destroy)(ctypes.c_void_p(h))
+
+
+def release_handles():
+    """Frees every cached block / convolution handle and workspace."""
     while _handles:
-        _, h = _handles.popitem(last=False)
-        lib.dmc_dcb_train_destroy(ctypes.c_void_p(h))
+        key, h = _handles.popitem(last=False)
+        _destroy(key, h)
     _packed_sig.clear()
 
 
@@ -100,7 +104,7 @@ def _handle(owner, device, B, H, W, cin, cout, force_adaptor, shortcut, has_qs, 
     while len(_handles) >= max_handles:
         old_key, old = _handles.popitem(last=False)
         _packed_sig.pop(old_key, None)
-        lib.dmc_dcb_train_destroy(ctypes.c_void_p(old))
+        _destroy(old_key, old)
     h = ctypes.c_void_p()
     with torch.cuda.device(device):
         rc = lib.dmc_dcb_train_create(B, H, W, cin, cout, int(force_adaptor), int(shortcut), int(has_qs), terms,
@@ -243,6 +247,107 @@ class DepthConvBlock(nn.Module):
     forward_torch = forward        # the reference's forward() delegates to a method of this name
 
 
+# ------------------------------------------------------------------------------------------------ plain 1x1 convolution
+def _conv_handle(owner, device, B, H, W, cin, cout, has_bias, terms):
+    key = ("conv1x1", owner, device.index, B, H, W, cin, cout, bool(has_bias), terms)
+    lib = _capi.load()
+    if key in _handles:
+        _handles.move_to_end(key)
+        return key, ctypes.c_void_p(_handles[key])
+    while len(_handles) >= max_handles:
+        old_key, old = _handles.popitem(last=False)
+        _packed_sig.pop(old_key, None)
+        _destroy(old_key, old)
+    h = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        rc = lib.dmc_conv1x1_train_create(B, H, W, cin, cout, int(has_bias), terms, ctypes.byref(h))
+    if rc != 0:
+        msg = lib.dmc_conv1x1_train_last_error(None)
+        raise _capi.EngineError(f"dmc_conv1x1_train_create: {msg.decode() if msg else rc}")
+    _handles[key] = h.value
+    return key, h
+
+
+def _check_conv(rc, h):
+    if rc != 0:
+        msg = _capi.load().dmc_conv1x1_train_last_error(h)
+        raise _capi.EngineError(f"dmc_b200 training error {rc}: {msg.decode() if msg else '?'}")
+
+
+class _Conv1x1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, terms, owner):
+        _need_cuda(x)
+        lib = _capi.load()
+        x = _dense(x)
+        B, cin, H, W = x.shape
+        cout = weight.shape[0]
+        w = _dense(weight.detach())
+        b = _dense(bias.detach()) if bias is not None else None
+        key, h = _conv_handle(owner, x.device, B, H, W, cin, cout, b is not None, terms)
+        sig = _signature((weight, bias))
+        unchanged = int(_packed_sig.get(key) == sig)
+        out = torch.empty(B, cout, H, W, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _check_conv(lib.dmc_conv1x1_train_forward(h, _ptr(x), _ptr(w), _ptr(b), _ptr(out), unchanged,
+                                                      _stream(x.device)), h)
+        _packed_sig[key] = sig
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (bias is not None, terms, owner, sig)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        has_bias, terms, owner, sig = ctx.meta
+        x, weight = ctx.saved_tensors
+        lib = _capi.load()
+        B, cin, H, W = x.shape
+        cout = weight.shape[0]
+        g = _dense(grad_out)
+        need = ctx.needs_input_grad            # (x, weight, bias, terms, owner)
+        gx = torch.empty_like(x) if need[0] else None
+        nw = weight.numel() if need[1] else 0
+        nb = cout if (has_bias and need[2]) else 0
+        flat = torch.empty(nw + nb, device=x.device, dtype=torch.float32)
+        gw = flat[:nw] if nw else None
+        gb = flat[nw:] if nb else None
+        key, h = _conv_handle(owner, x.device, B, H, W, cin, cout, has_bias, terms)
+        unchanged = int(_packed_sig.get(key) == sig)
+        with torch.cuda.device(x.device):
+            _check_conv(lib.dmc_conv1x1_train_backward(h, _ptr(x), _ptr(_dense(weight.detach())), _ptr(g), _ptr(gx),
+                                                       _ptr(gw), _ptr(gb), unchanged, _stream(x.device)), h)
+        _packed_sig[key] = sig
+        return gx, (gw.view_as(weight) if gw is not None else None), gb, None, None
+
+
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d whose 1x1 / stride 1 / unpadded / ungrouped instances with channel counts in multiples of 16 (>= 32) run
+    on the engine, forward and backward (fp32-grade split products); every other configuration is torch's own
+    convolution, unchanged.  Same constructor, same parameters."""
+
+    terms = 3
+
+    def _on_engine(self, x):
+        return (x.is_cuda and x.dim() == 4 and self.kernel_size == (1, 1) and self.stride == (1, 1)
+                and self.padding == (0, 0) and self.dilation == (1, 1) and self.groups == 1
+                and self.padding_mode == "zeros" and self.in_channels % 16 == 0 and self.out_channels % 16 == 0
+                and self.in_channels >= 32 and self.out_channels >= 32)
+
+    def forward(self, x):
+        if self._on_engine(x):
+            return _Conv1x1Fn.apply(x, self.weight, self.bias, self.terms, id(self))
+        return super().forward(x)
+
+
+class _NNProxy:
+    """`nn` as the reference modules see it inside `reference_patched`: torch.nn with Conv2d replaced."""
+
+    Conv2d = Conv2d
+
+    def __getattr__(self, name):
+        return getattr(nn, name)
+
+
 # ------------------------------------------------------------------------------------------------ quantisation
 class _QuantFn(torch.autograd.Function):
     @staticmethod
@@ -340,16 +445,21 @@ class reference_patched:
     Every name bound by `from ..layers.layers import DepthConvBlock` is a separate module attribute, so each module that
     constructs blocks has to be listed (layers.py itself for ResidualBlockWithStride2 / ResidualBlockUpsample)."""
 
-    def __init__(self, *modules):
+    def __init__(self, *modules, conv1x1=True):
         self.modules = modules
+        self.conv1x1 = conv1x1          # also route the models' plain 1x1 nn.Conv2d layers through the engine (`Conv2d`)
         self.saved = []
 
     def __enter__(self):
+        swaps = [("DepthConvBlock", DepthConvBlock), ("AdaptiveQuant", AdaptiveQuant)]
         for m in self.modules:
-            for name, repl in (("DepthConvBlock", DepthConvBlock), ("AdaptiveQuant", AdaptiveQuant)):
+            for name, repl in swaps:
                 if hasattr(m, name):
                     self.saved.append((m, name, getattr(m, name)))
                     setattr(m, name, repl)
+            if self.conv1x1 and getattr(m, "nn", None) is nn:
+                self.saved.append((m, "nn", nn))
+                setattr(m, "nn", _NNProxy())
         return self
 
     def __exit__(self, *exc):

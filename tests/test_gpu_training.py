@@ -300,3 +300,37 @@ def test_block_on_a_device_that_is_not_current():
         assert y.device == torch.device(dev) and torch.cuda.current_device() == 0
         assert _relmax(xg.grad, xr.grad) < 1e-5
         assert _relmax(blk.ffn[0].weight.grad, ref.ffn0.weight.grad) < 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,bias,x_grad", [(256, 256, True, True), (192, 256, True, False), (64, 512, False, True),
+                                                  (320, 192, True, True)])
+def test_conv1x1_forward_backward(cin, cout, bias, x_grad):
+    """training.Conv2d (the models' plain 1x1 convolutions) against torch.autograd in fp64; other configurations stay torch's."""
+    torch.manual_seed(cin + cout)
+    ref = nn.Conv2d(cin, cout, 1, bias=bias).double()
+    conv = T.Conv2d(cin, cout, 1, bias=bias).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(ref.weight.float())
+        if bias:
+            conv.bias.copy_(ref.bias.float())
+    x = torch.randn(2, cin, 9, 13, dtype=torch.float64)
+    gout = torch.randn(2, cout, 9, 13, dtype=torch.float64) * 1e-5
+    xr = x.clone().requires_grad_(x_grad)
+    ref(xr).backward(gout)
+    for rep in range(3):                       # direct call, graph capture, graph replay
+        conv.zero_grad()
+        xg = x.float().cuda().requires_grad_(x_grad)
+        y = conv(xg)
+        assert isinstance(y.grad_fn, T._Conv1x1Fn._backward_cls)
+        y.backward(gout.float().cuda())
+        assert _relmax(y, ref(x)) < 2e-5
+        assert _relmax(conv.weight.grad, ref.weight.grad) < 1e-5
+        if bias:
+            assert _relmax(conv.bias.grad, ref.bias.grad) < 1e-5
+        if x_grad:
+            assert _relmax(xg.grad, xr.grad) < 1e-5
+        else:
+            assert xg.grad is None
+    k3 = T.Conv2d(32, 32, 3, padding=1).cuda()              # not a 1x1: torch's own path
+    assert not k3._on_engine(torch.empty(1, 32, 4, 4, device="cuda"))
+    assert k3(torch.randn(1, 32, 4, 4, device="cuda")).shape == (1, 32, 4, 4)
