@@ -213,6 +213,18 @@ int dmc_conv1x1_train_forward(dmc_conv1x1_train* t, const float* x, const float*
                               int weights_unchanged, void* stream);
 int dmc_conv1x1_train_backward(dmc_conv1x1_train* t, const float* x, const float* weight, const float* grad_out,
                                float* grad_x, float* grad_weight, float* grad_bias, int weights_unchanged, void* stream);
+/* k x k convolutions (kernel 2 or 3, stride 1 or 2, padding 0 or 1, no groups: encoder.down, mask_sft.down, the sub-pixel
+ * 3x3 of decoder.up, the 2x2 stride-2 downs) with their backward pass, through the im2col view.  Conventions as above;
+ * weight (cout, cin, k, k). */
+typedef struct dmc_convkxk_train dmc_convkxk_train;
+int dmc_convkxk_train_create(int batch, int height, int width, int cin, int cout, int ksize, int stride, int padding,
+                             int has_bias, int terms, dmc_convkxk_train** out);
+void dmc_convkxk_train_destroy(dmc_convkxk_train* t);
+const char* dmc_convkxk_train_last_error(const dmc_convkxk_train* t);
+int dmc_convkxk_train_forward(dmc_convkxk_train* t, const float* x, const float* weight, const float* bias, float* out,
+                              int weights_unchanged, void* stream);
+int dmc_convkxk_train_backward(dmc_convkxk_train* t, const float* x, const float* weight, const float* grad_out,
+                               float* grad_x, float* grad_weight, float* grad_bias, int weights_unchanged, void* stream);
 /* AdaptiveQuant in training mode (layers/inference.py:16-27).  mode 0 "ste": out = round(x) (the straight-through
  * gradient is the identity); mode 1 "noise": out = x + noise with noise ~ U(-half_bin, half_bin) drawn by the caller. */
 int dmc_op_quant_train(const float* x, const float* noise, float* out, int64_t n, int mode, void* stream);

@@ -56,6 +56,12 @@ SIGNATURES = {
     "dmc_conv1x1_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dmc_conv1x1_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                            c_void_p]),
+    "dmc_convkxk_train_create": (c_int, [c_int] * 10 + [POINTER(c_void_p)]),
+    "dmc_convkxk_train_destroy": (None, [c_void_p]),
+    "dmc_convkxk_train_last_error": (c_char_p, [c_void_p]),
+    "dmc_convkxk_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "dmc_convkxk_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                           c_void_p]),
     "dmc_op_quant_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "dmc_op_gaussian_bits_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                               c_void_p]),

@@ -2211,6 +2211,186 @@ extern "C" int dmc_conv1x1_train_backward(dmc_conv1x1_train* t, const float* x, 
   });
 }
 
+// ---------------------------------------------------------------- training mode: k x k convolutions
+// encoder.down / mask_sft.down (3x3 stride 2), the sub-pixel 3x3 of decoder.up, the 2x2 stride-2 downs of the hyper path
+// and the temporal prior: forward = im2col + one contraction (as in the frame engine); backward through the same im2col
+// view: weight gradient = k_wgrad_umma over (gradient rows, im2col rows), data gradient = the contraction with the
+// transposed weight followed by the gather that undoes im2col (k_col2im_nchw).
+struct dmc_convkxk_train {
+  dmc_engine e;
+  std::vector<dmc_engine::Op> prog_bwd_head, prog_bwd, prog_bwd_tail;
+  int cin = 0, cout = 0, k = 1, stride = 1, pad = 0, terms = 3;
+  bool has_bias = true, packed = false, packed_T = false;
+  Conv *fw = nullptr, *T = nullptr;
+  float *gflat = nullptr, *scale2 = nullptr, *partS = nullptr, *partB = nullptr, *wt = nullptr;
+  int gmask = 0;                 // bit 0: weight gradient, bit 1: bias gradient, bit 2: input gradient
+  long long bwd_calls = 0;
+  const float *x = nullptr, *gout = nullptr;
+  float *out = nullptr, *gx = nullptr;
+  ~dmc_convkxk_train() {
+    DeviceGuard dg(e.device);
+    cudaDeviceSynchronize();
+  }
+};
+
+extern "C" int dmc_convkxk_train_create(int batch, int height, int width, int cin, int cout, int ksize, int stride, int padding,
+                                        int has_bias, int terms, dmc_convkxk_train** out) {
+  if (!out) return DMC_E_INVALID;
+  *out = nullptr;
+  dmc_convkxk_train* t = nullptr;
+  int rc = guarded(nullptr, [&] {
+    if (batch < 1 || height < 1 || width < 1) fail("dmc_convkxk_train_create: bad geometry");
+    if (ksize < 2 || ksize > 3 || stride < 1 || stride > 2 || padding < 0 || padding > 1) fail("dmc_convkxk_train_create: kernel 2 or 3, stride 1 or 2, padding 0 or 1");
+    if (cin < 16 || cout < 32 || cin % 16 || cout % 16) fail("dmc_convkxk_train_create: channels must be multiples of 16 (cout >= 32)");
+    if (terms != 1 && terms != 3) fail("dmc_convkxk_train_create: terms must be 1 or 3");
+    const int B = batch, H = height, W = width, k = ksize;
+    const int Ho = (H + 2 * padding - k) / stride + 1, Wo = (W + 2 * padding - k) / stride + 1;
+    if (Ho < 1 || Wo < 1) fail("dmc_convkxk_train_create: empty output");
+    t = new dmc_convkxk_train();
+    dmc_engine& e = t->e;
+    CUDA_OK(cudaGetDevice(&e.device));
+    e.variant = -1; e.B = B; e.H = H; e.W = W;
+    t->cin = cin; t->cout = cout; t->k = k; t->stride = stride; t->pad = padding; t->terms = terms; t->has_bias = has_bias != 0;
+    const long long Mo = (long long)B * Ho * Wo;
+    const int K = k * k * cin;
+    t->fw = e.add_conv("c", cin, cout, k, stride, padding);
+    t->T = e.add_conv("T", cout, K, 1, 1, 0);
+    pack_gemm_bias(nullptr, K, t->T->g, nullptr);
+    pack_gemm_bias(nullptr, cout, t->fw->g, nullptr);
+    t->gflat = e.new_f32((size_t)cout * K + cout);
+    t->wt = e.new_f32((size_t)cout * K);
+    t->scale2 = e.new_f32(2);
+    {
+      const char* v = getenv("DMC_TRAIN_SHARED_WORKSPACE");
+      if (!(v && v[0] == '0')) {
+        char key[200];
+        snprintf(key, sizeof key, "convkxk:dev%d:%dx%dx%d:%d>%d:k%ds%dp%d:t%d", e.device, B, H, W, cin, cout, k, stride, padding, terms);
+        e.pool_prefix = key;
+      }
+    }
+    const int max_parts = 8 * num_sms();
+    t->partS = e.new_f32(std::max((size_t)max_parts * cout, (size_t)wgrad_splits(Mo, cout, K) * cout * K));
+    t->partB = e.new_f32((size_t)max_parts);
+    dmc_convkxk_train* self = t;
+    EpiSpec plain;
+    plain.nsplit = terms;
+    // ---- forward
+    e.prog = &e.prog_common;
+    {
+      Act fin = e.new_act(B, H, W, cin), fout = e.new_act(B, Ho, Wo, cout);
+      e.op([self, fin, B, H, W, cin](cudaStream_t st) { nchw_to_s3(self->x, fin.v, B, cin, H, W, st); });
+      e.conv_kxk(fin, t->fw, &fout, plain);
+      e.op([self, fout, B, Ho, Wo, cout](cudaStream_t st) { s3_to_nchw(fout.v, self->out, B, cout, Ho, Wo, st); });
+      e.flush_chain();
+    }
+    // ---- backward
+    Act xs = e.new_act(B, H, W, cin), g = e.new_act(B, Ho, Wo, cout), gcol = e.new_act(B, Ho, Wo, K);
+    Act col = e.get_scratch("im2col", B, Ho, Wo, K);          // (the forward's scratch: same geometry)
+    float* scale2 = t->scale2;
+    e.set_prog(&t->prog_bwd_head);
+    e.op([self, xs, g, B, H, W, Ho, Wo, cin, cout, Mo, scale2](cudaStream_t st) {
+      if (self->gmask & 1) nchw_to_s3(self->x, xs.v, B, cin, H, W, st);
+      grad_scale(self->gout, Mo * cout, grad_peak_log2(), self->partB, scale2, st);
+      nchw_to_s3_scaled(self->gout, g.v, B, cout, Ho, Wo, nullptr, scale2, st);
+    });
+    e.set_prog(&t->prog_bwd);
+    {
+      const int terms_ = terms;
+      e.op([self, g, xs, col, B, H, W, Ho, Wo, Mo, cin, cout, k, stride, padding, K, terms_, max_parts, scale2](cudaStream_t st) {
+        if (self->gmask & 1) {
+          im2col(xs.v, col.v, B, H, W, k, stride, padding, Ho, Wo, cin, 0, st);
+          int S = wgrad_s3(g.v, col.v, Mo, terms_, self->partS, st);
+          if (S < 1) fail("weight gradient launch: %s", wgrad_umma_last_error());
+          reduce_wgrad_kxk(self->partS, (long long)cout * K, S, self->gflat, cout, cin, k, scale2 + 1, st);
+        }
+        if (self->gmask & 2) {
+          int S = colsum_s3(g.v, nullptr, Mo, self->partS, cout, max_parts, st);
+          reduce_partials(self->partS, cout, S, self->gflat + (size_t)cout * K, cout, scale2 + 1, 1.0f, st);
+        }
+      });
+    }
+    e.gemm(g, t->T, &gcol, plain);
+    e.set_prog(&t->prog_bwd_tail);
+    e.op([self, gcol, B, H, W, Ho, Wo, cin, k, stride, padding, scale2](cudaStream_t st) {
+      if (self->gx) col2im_nchw(gcol.v, self->gx, B, cin, H, W, k, stride, padding, Ho, Wo, scale2 + 1, st);
+    });
+    e.flush_chain();
+    e.prog = &e.prog_common;
+    CUDA_OK(cudaDeviceSynchronize());
+  });
+  if (rc != DMC_OK) {
+    delete t;
+    return rc;
+  }
+  *out = t;
+  return DMC_OK;
+}
+
+extern "C" void dmc_convkxk_train_destroy(dmc_convkxk_train* t) { delete t; }
+extern "C" const char* dmc_convkxk_train_last_error(const dmc_convkxk_train* t) {
+  return t ? t->e.error.c_str() : g_create_error.c_str();
+}
+
+extern "C" int dmc_convkxk_train_forward(dmc_convkxk_train* t, const float* x, const float* weight, const float* bias,
+                                         float* out, int weights_unchanged, void* stream) {
+  if (!t) return DMC_E_INVALID;
+  return guarded(&t->e, [&] {
+    if (!x || !out || !weight) fail("dmc_convkxk_train_forward: null tensor");
+    if (t->has_bias && !bias) fail("bias required: the handle was created with has_bias");
+    DeviceGuard dg(t->e.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!weights_unchanged) t->packed = t->packed_T = false;
+    if (!t->packed) {
+      pack_gemm_weight(weight, t->cout, t->cin, t->k, t->k, t->fw->g, st);
+      if (t->has_bias) pack_gemm_bias(bias, t->cout, t->fw->g, st);
+      t->packed = true;
+    }
+    t->x = x; t->out = out;
+    t->e.cur.qp = 0;
+    t->e.run(t->e.prog_common, st);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+extern "C" int dmc_convkxk_train_backward(dmc_convkxk_train* t, const float* x, const float* weight, const float* grad_out,
+                                          float* grad_x, float* grad_weight, float* grad_bias, int weights_unchanged,
+                                          void* stream) {
+  if (!t) return DMC_E_INVALID;
+  return guarded(&t->e, [&] {
+    if (!grad_out || (grad_weight && !x) || (grad_x && !weight)) fail("dmc_convkxk_train_backward: null tensor");
+    if ((uintptr_t)grad_out % 16) fail("dmc_convkxk_train_backward: grad_out must be 16-byte aligned");
+    DeviceGuard dg(t->e.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!weights_unchanged) t->packed = t->packed_T = false;
+    const int K = t->k * t->k * t->cin;
+    if (grad_x && !t->packed_T) {
+      wt_kxk(weight, t->wt, t->cout, t->cin, t->k, st);
+      pack_gemm_weight(t->wt, K, t->cout, 1, 1, t->T->g, st);
+      t->packed_T = true;
+    }
+    t->x = x; t->gout = grad_out; t->gx = grad_x;
+    t->gmask = (grad_weight ? 1 : 0) | (grad_bias ? 2 : 0) | (grad_x ? 4 : 0);
+    dmc_engine& e = t->e;
+    e.cur.qp = 0;
+    e.run(t->prog_bwd_head, st);
+    auto body = [&](cudaStream_t s2) {
+      for (size_t i = 0; i < t->prog_bwd.size(); ++i)
+        if (i == 0 || (t->gmask & 4)) t->prog_bwd[i](s2);
+    };
+    if (t->bwd_calls++ > 0) e.run_graph(0x300000ull | (uint64_t)t->gmask, st, body);
+    else body(st);
+    e.run(t->prog_bwd_tail, st);
+    const size_t wn = (size_t)t->cout * K;
+    if (grad_weight && grad_bias && grad_bias == grad_weight + wn) {
+      CUDA_OK(cudaMemcpyAsync(grad_weight, t->gflat, (wn + t->cout) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (grad_weight) CUDA_OK(cudaMemcpyAsync(grad_weight, t->gflat, wn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (grad_bias) CUDA_OK(cudaMemcpyAsync(grad_bias, t->gflat + wn, t->cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
 extern "C" int dmc_op_quant_train(const float* x, const float* noise, float* out, int64_t n, int mode, void* stream) {
   if (!x || !out || n < 0 || (mode != 0 && mode != 1) || (mode == 1 && !noise)) return DMC_E_INVALID;
   if (n) quant_train(x, noise, out, (long long)n, mode, (cudaStream_t)stream);

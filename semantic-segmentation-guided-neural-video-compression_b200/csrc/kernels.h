@@ -229,6 +229,12 @@ int wgrad_umma_splits(long long M, int N, int K);
 int wgrad_umma(View G, View X, long long M, int terms, float* part, cudaStream_t st);   // -1 on error
 const char* wgrad_umma_last_error();
 int wgrad_s3(View G, View X, long long M, int terms, float* part, cudaStream_t st);
+// k x k convolutions through the im2col view (train.cu)
+void wt_kxk(const float* w, float* wt, int cout, int cin, int k, cudaStream_t st);
+void reduce_wgrad_kxk(const float* part, long long stride, int S, float* out, int cout, int cin, int k, const float* scale_dev,
+                      cudaStream_t st);
+void col2im_nchw(View gcol, float* gx, int B, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo, const float* gscale,
+                 cudaStream_t st);
 void quant_train(const float* x, const float* noise, float* out, long long n, int mode, cudaStream_t st);
 void gaussian_bits_bwd(const float* sym, const float* sigma, const float* go, float* gsym, float* gsig, long long n,
                        int formula, cudaStream_t st);

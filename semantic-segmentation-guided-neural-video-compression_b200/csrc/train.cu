@@ -839,6 +839,85 @@ void reduce_div(const float* part, int S, int C, const float* div, float* out, c
   launch(k_reduce_div, cdiv_u(C, 256), 256, 0, st, part, S, C, div, out);
 }
 
+// ------------------------------------------------------------------ k x k convolutions (through the im2col view)
+// wt[(tap * cin + ci)][n] = w[n][ci][kh][kw], tap = kh * k + kw: the weight of the data gradient as a (k*k*cin, cout, 1, 1)
+// convolution over the gradient rows, in the column order of im2col
+__global__ void k_wt_kxk(const float* __restrict__ w, float* __restrict__ wt, int cout, int cin, int k) {
+  pdl_prologue_done();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long K = (long long)k * k * cin;
+  if (i >= K * cout) return;
+  const int n = (int)(i % cout);
+  const long long j = i / cout;
+  const int ci = (int)(j % cin), tap = (int)(j / cin);
+  wt[i] = w[(((long long)n * cin + ci) * k + tap / k) * k + tap % k];
+}
+void wt_kxk(const float* w, float* wt, int cout, int cin, int k, cudaStream_t st) {
+  launch(k_wt_kxk, cdiv_u((long long)k * k * cin * cout, 256), 256, 0, st, w, wt, cout, cin, k);
+}
+// partial sums [S][cout][k*k*cin] (im2col column order) -> weight gradient (cout, cin, k, k)
+__global__ void k_reduce_wgrad_kxk(const float* __restrict__ part, long long stride, int S, float* __restrict__ out, int cout,
+                                   int cin, int k, const float* __restrict__ scale_dev) {
+  pdl_prologue_done();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long K = (long long)k * k * cin;
+  if (i >= K * cout) return;
+  float s0 = 0.0f, s1 = 0.0f;
+  int q = 0;
+  for (; q + 1 < S; q += 2) {
+    s0 += part[(long long)q * stride + i];
+    s1 += part[(long long)(q + 1) * stride + i];
+  }
+  if (q < S) s0 += part[(long long)q * stride + i];
+  const int n = (int)(i / K);
+  const long long j = i % K;
+  const int ci = (int)(j % cin), tap = (int)(j / cin);
+  out[(((long long)n * cin + ci) * k + tap / k) * k + tap % k] = (s0 + s1) * (scale_dev ? *scale_dev : 1.0f);
+}
+void reduce_wgrad_kxk(const float* part, long long stride, int S, float* out, int cout, int cin, int k, const float* scale_dev,
+                      cudaStream_t st) {
+  launch(k_reduce_wgrad_kxk, cdiv_u((long long)k * k * cin * cout, 256), 256, 0, st, part, stride, S, out, cout, cin, k, scale_dev);
+}
+// Gradient of im2col: gx[b, c, hi, wi] = scale * sum over the taps that read this pixel of gcol[(b, ho, wo), tap * C + c].
+// gcol: split planes [B*Ho*Wo, k*k*C]; gx: NCHW fp32.  Thread = (pixel, 8 channels), pixel fastest (coalesced NCHW side).
+__global__ void k_col2im_nchw(View gcol, float* __restrict__ gx, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
+                              const float* __restrict__ gscale) {
+  pdl_prologue_done();
+  const long long HW = (long long)H * W;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const int c8 = blockIdx.y, b = blockIdx.z;
+  const int hi = (int)(p / W), wi = (int)(p % W);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int kh = 0; kh < k; ++kh) {
+    const int th = hi + pad - kh;
+    if (th < 0 || th % stride) continue;
+    const int ho = th / stride;
+    if (ho >= Ho) continue;
+    for (int kw = 0; kw < k; ++kw) {
+      const int tw = wi + pad - kw;
+      if (tw < 0 || tw % stride) continue;
+      const int wo = tw / stride;
+      if (wo >= Wo) continue;
+      float v[8];
+      ld3x8(gcol, ((long long)b * Ho + ho) * Wo + wo, (kh * k + kw) * C + c8 * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+  const float gs = gscale ? *gscale : 1.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c8 * 8 + i;
+    if (c < C) gx[((long long)b * C + c) * HW + p] = acc[i] * gs;
+  }
+}
+void col2im_nchw(View gcol, float* gx, int B, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo, const float* gscale,
+                 cudaStream_t st) {
+  dim3 grid(cdiv_u((long long)H * W, 256), (C + 7) / 8, B);
+  launch(k_col2im_nchw, grid, 256, 0, st, gcol, gx, C, H, W, k, stride, pad, Ho, Wo, gscale);
+}
+
 // ------------------------------------------------------------------ quantisation / likelihood, training mode
 // inference.py:16-27.  mode 0 "ste": out = round(x) (the gradient passes through unchanged: nothing to compute);
 // mode 1 "noise": out = x + noise, noise ~ U(-half_bin, half_bin) drawn by the caller (torch's generator, so that a

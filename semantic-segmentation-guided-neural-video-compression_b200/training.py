@@ -83,7 +83,9 @@ def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
 
 def _destroy(key, h):
     lib = _capi.load()
-    (lib.dmc_conv1x1_train_destroy if key[0] == "conv1x1" else lib.dmc_dcb_train_destroy)(ctypes.c_void_p(h))
+    fn = {"conv1x1": lib.dmc_conv1x1_train_destroy, "convkxk": lib.dmc_convkxk_train_destroy}.get(key[0],
+                                                                                                  lib.dmc_dcb_train_destroy)
+    fn(ctypes.c_void_p(h))
 
 
 def release_handles():
@@ -248,8 +250,10 @@ class DepthConvBlock(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ plain 1x1 convolution
-def _conv_handle(owner, device, B, H, W, cin, cout, has_bias, terms):
-    key = ("conv1x1", owner, device.index, B, H, W, cin, cout, bool(has_bias), terms)
+def _conv_handle(owner, device, B, H, W, cin, cout, has_bias, terms, geom=(1, 1, 0)):
+    """geom = (kernel, stride, padding); (1, 1, 0) is the plain 1x1 handle, anything else the im2col one."""
+    kxk = geom != (1, 1, 0)
+    key = ("convkxk" if kxk else "conv1x1", owner, device.index, B, H, W, cin, cout, bool(has_bias), terms, geom)
     lib = _capi.load()
     if key in _handles:
         _handles.move_to_end(key)
@@ -260,82 +264,111 @@ def _conv_handle(owner, device, B, H, W, cin, cout, has_bias, terms):
         _destroy(old_key, old)
     h = ctypes.c_void_p()
     with torch.cuda.device(device):
-        rc = lib.dmc_conv1x1_train_create(B, H, W, cin, cout, int(has_bias), terms, ctypes.byref(h))
+        if kxk:
+            rc = lib.dmc_convkxk_train_create(B, H, W, cin, cout, geom[0], geom[1], geom[2], int(has_bias), terms,
+                                              ctypes.byref(h))
+        else:
+            rc = lib.dmc_conv1x1_train_create(B, H, W, cin, cout, int(has_bias), terms, ctypes.byref(h))
     if rc != 0:
-        msg = lib.dmc_conv1x1_train_last_error(None)
-        raise _capi.EngineError(f"dmc_conv1x1_train_create: {msg.decode() if msg else rc}")
+        msg = (lib.dmc_convkxk_train_last_error if kxk else lib.dmc_conv1x1_train_last_error)(None)
+        raise _capi.EngineError(f"conv train handle: {msg.decode() if msg else rc}")
     _handles[key] = h.value
     return key, h
 
 
-def _check_conv(rc, h):
+def _check_conv(rc, h, kxk=False):
     if rc != 0:
-        msg = _capi.load().dmc_conv1x1_train_last_error(h)
+        lib = _capi.load()
+        msg = (lib.dmc_convkxk_train_last_error if kxk else lib.dmc_conv1x1_train_last_error)(h)
         raise _capi.EngineError(f"dmc_b200 training error {rc}: {msg.decode() if msg else '?'}")
 
 
 class _Conv1x1Fn(torch.autograd.Function):
+    """A dense convolution on the engine: geom = (kernel, stride, padding); (1, 1, 0) is the plain 1x1 case."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, terms, owner):
+    def forward(ctx, x, weight, bias, terms, owner, geom=(1, 1, 0)):
         _need_cuda(x)
         lib = _capi.load()
         x = _dense(x)
         B, cin, H, W = x.shape
         cout = weight.shape[0]
+        k, stride, pad = geom
+        kxk = geom != (1, 1, 0)
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         w = _dense(weight.detach())
         b = _dense(bias.detach()) if bias is not None else None
-        key, h = _conv_handle(owner, x.device, B, H, W, cin, cout, b is not None, terms)
+        key, h = _conv_handle(owner, x.device, B, H, W, cin, cout, b is not None, terms, geom)
         sig = _signature((weight, bias))
         unchanged = int(_packed_sig.get(key) == sig)
-        out = torch.empty(B, cout, H, W, device=x.device, dtype=torch.float32)
+        out = torch.empty(B, cout, Ho, Wo, device=x.device, dtype=torch.float32)
+        fwd = lib.dmc_convkxk_train_forward if kxk else lib.dmc_conv1x1_train_forward
         with torch.cuda.device(x.device):
-            _check_conv(lib.dmc_conv1x1_train_forward(h, _ptr(x), _ptr(w), _ptr(b), _ptr(out), unchanged,
-                                                      _stream(x.device)), h)
+            _check_conv(fwd(h, _ptr(x), _ptr(w), _ptr(b), _ptr(out), unchanged, _stream(x.device)), h, kxk)
         _packed_sig[key] = sig
         ctx.save_for_backward(x, weight)
-        ctx.meta = (bias is not None, terms, owner, sig)
+        ctx.meta = (bias is not None, terms, owner, sig, geom)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        has_bias, terms, owner, sig = ctx.meta
+        has_bias, terms, owner, sig, geom = ctx.meta
         x, weight = ctx.saved_tensors
         lib = _capi.load()
         B, cin, H, W = x.shape
         cout = weight.shape[0]
+        kxk = geom != (1, 1, 0)
         g = _dense(grad_out)
-        need = ctx.needs_input_grad            # (x, weight, bias, terms, owner)
+        need = ctx.needs_input_grad            # (x, weight, bias, terms, owner, geom)
         gx = torch.empty_like(x) if need[0] else None
         nw = weight.numel() if need[1] else 0
         nb = cout if (has_bias and need[2]) else 0
         flat = torch.empty(nw + nb, device=x.device, dtype=torch.float32)
         gw = flat[:nw] if nw else None
         gb = flat[nw:] if nb else None
-        key, h = _conv_handle(owner, x.device, B, H, W, cin, cout, has_bias, terms)
+        key, h = _conv_handle(owner, x.device, B, H, W, cin, cout, has_bias, terms, geom)
         unchanged = int(_packed_sig.get(key) == sig)
+        bwd = lib.dmc_convkxk_train_backward if kxk else lib.dmc_conv1x1_train_backward
         with torch.cuda.device(x.device):
-            _check_conv(lib.dmc_conv1x1_train_backward(h, _ptr(x), _ptr(_dense(weight.detach())), _ptr(g), _ptr(gx),
-                                                       _ptr(gw), _ptr(gb), unchanged, _stream(x.device)), h)
+            _check_conv(bwd(h, _ptr(x), _ptr(_dense(weight.detach())), _ptr(g), _ptr(gx), _ptr(gw), _ptr(gb), unchanged,
+                            _stream(x.device)), h, kxk)
         _packed_sig[key] = sig
-        return gx, (gw.view_as(weight) if gw is not None else None), gb, None, None
+        return gx, (gw.view_as(weight) if gw is not None else None), gb, None, None, None
 
 
 class Conv2d(nn.Conv2d):
-    """nn.Conv2d whose 1x1 / stride 1 / unpadded / ungrouped instances with channel counts in multiples of 16 (>= 32) run
-    on the engine, forward and backward (fp32-grade split products); every other configuration is torch's own
-    convolution, unchanged.  Same constructor, same parameters."""
+    """nn.Conv2d whose dense instances the engine covers run on it, forward and backward (fp32-grade split products):
+    1x1 / stride 1 / unpadded, and k x k with kernel 2 or 3, stride 1 or 2, padding 0 or 1 (through the im2col view) --
+    ungrouped, undilated, zero padding, channel counts in multiples of 16 (cout >= 32; 1x1: cin >= 32).  Every other
+    configuration is torch's own convolution, unchanged.  Same constructor, same parameters."""
 
     terms = 3
+    #: False keeps the k x k instances on torch (A/B runs)
+    kxk_on_engine = True
+
+    def _geom(self, x):
+        """(kernel, stride, padding) when this call runs on the engine, else None."""
+        if not (x.is_cuda and x.dim() == 4 and self.dilation == (1, 1) and self.groups == 1
+                and self.padding_mode == "zeros" and self.in_channels % 16 == 0 and self.out_channels % 16 == 0
+                and self.out_channels >= 32 and isinstance(self.padding, tuple)):
+            return None
+        k, s, p = self.kernel_size, self.stride, self.padding
+        if k[0] != k[1] or s[0] != s[1] or p[0] != p[1]:
+            return None
+        geom = (k[0], s[0], p[0])
+        if geom == (1, 1, 0):
+            return geom if self.in_channels >= 32 else None
+        if self.kxk_on_engine and k[0] in (2, 3) and s[0] in (1, 2) and p[0] in (0, 1):
+            return geom
+        return None
 
     def _on_engine(self, x):
-        return (x.is_cuda and x.dim() == 4 and self.kernel_size == (1, 1) and self.stride == (1, 1)
-                and self.padding == (0, 0) and self.dilation == (1, 1) and self.groups == 1
-                and self.padding_mode == "zeros" and self.in_channels % 16 == 0 and self.out_channels % 16 == 0
-                and self.in_channels >= 32 and self.out_channels >= 32)
+        return self._geom(x) is not None
 
     def forward(self, x):
-        if self._on_engine(x):
-            return _Conv1x1Fn.apply(x, self.weight, self.bias, self.terms, id(self))
+        geom = self._geom(x)
+        if geom is not None:
+            return _Conv1x1Fn.apply(x, self.weight, self.bias, self.terms, id(self), geom)
         return super().forward(x)
 
 

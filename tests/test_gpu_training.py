@@ -334,3 +334,31 @@ def test_conv1x1_forward_backward(cin, cout, bias, x_grad):
     k3 = T.Conv2d(32, 32, 3, padding=1).cuda()              # not a 1x1: torch's own path
     assert not k3._on_engine(torch.empty(1, 32, 4, 4, device="cuda"))
     assert k3(torch.randn(1, 32, 4, 4, device="cuda")).shape == (1, 32, 4, 4)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,H,W", [(128, 128, 2, 2, 0, 8, 12),      # hyper / temporal-prior downs
+                                                       (256, 128, 3, 2, 1, 10, 14),    # encoder.down, mask_sft.down
+                                                       (128, 256, 3, 1, 1, 7, 9),      # the sub-pixel 3x3 of decoder.up
+                                                       (32, 64, 3, 2, 1, 9, 11)])      # odd sizes, stride 2
+def test_conv_kxk_forward_backward(cin, cout, k, stride, pad, H, W):
+    """training.Conv2d's k x k instances (im2col view) against torch.autograd in fp64."""
+    torch.manual_seed(cin + cout + k)
+    ref = nn.Conv2d(cin, cout, k, stride=stride, padding=pad).double()
+    conv = T.Conv2d(cin, cout, k, stride=stride, padding=pad).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(ref.weight.float())
+        conv.bias.copy_(ref.bias.float())
+    x = torch.randn(2, cin, H, W, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gout = torch.randn_like(yr) * 1e-4
+    yr.backward(gout)
+    for rep in range(3):                       # direct call, graph capture, graph replay
+        conv.zero_grad()
+        xg = x.float().cuda().requires_grad_(True)
+        y = conv(xg)
+        assert isinstance(y.grad_fn, T._Conv1x1Fn._backward_cls) and y.shape == yr.shape
+        y.backward(gout.float().cuda())
+        errs = {"out": _relmax(y, yr), "w": _relmax(conv.weight.grad, ref.weight.grad),
+                "b": _relmax(conv.bias.grad, ref.bias.grad), "x": _relmax(xg.grad, xr.grad)}
+        assert errs["out"] < 2e-5 and max(errs["w"], errs["b"], errs["x"]) < 1e-5, errs
