@@ -331,9 +331,11 @@ def test_conv1x1_forward_backward(cin, cout, bias, x_grad):
             assert _relmax(xg.grad, xr.grad) < 1e-5
         else:
             assert xg.grad is None
-    k3 = T.Conv2d(32, 32, 3, padding=1).cuda()              # not a 1x1: torch's own path
-    assert not k3._on_engine(torch.empty(1, 32, 4, 4, device="cuda"))
-    assert k3(torch.randn(1, 32, 4, 4, device="cuda")).shape == (1, 32, 4, 4)
+    for other in (T.Conv2d(32, 32, 3, padding=1, groups=32), T.Conv2d(1, 64, 3, padding=1), T.Conv2d(32, 32, 5, padding=2)):
+        other = other.cuda()                                # depthwise / one input channel / 5x5: torch's own path
+        xo = torch.randn(1, other.in_channels, 6, 6, device="cuda")
+        assert not other._on_engine(xo)
+        assert other(xo).shape == (1, other.out_channels, 6, 6)
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,pad,H,W", [(128, 128, 2, 2, 0, 8, 12),      # hyper / temporal-prior downs
