@@ -6,6 +6,7 @@ three pieces as `torch.autograd.Function`s over the C ABI (include/dmc_b200.h, "
 the reference's constructors and state_dict keys:
 
     DepthConvBlock(in_ch, out_ch, shortcut=False, force_adaptor=False)      src/layers/layers.py:43-79
+    Conv2d(...)   nn.Conv2d subclass: dense 1x1 and k x k (2 / 3, stride 1 / 2) on the engine, the rest torch's
     AdaptiveQuant(mode="ste" | "noise", half_bin=0.5)                       src/layers/inference.py:8-27
     gaussian_bits(y, sigma, formula)                                        src/models/common_model.py:36-42 (0),
                                                                             src/refactor/common_model.py:37-68 (1)
