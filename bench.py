@@ -305,7 +305,7 @@ def gpu_eager_baseline(dev, x_frames, n=5):
 
 def training_step(dev, x_frames, n=3):
     """SURVEY 8(f) rank 2 at model scale: one training step (forward in train mode + the trainer's loss + backward) of the
-    reference's OWN `performance` model class at full size -- built from dmc_b200.training's blocks
+    reference's OWN `performance` model class at full size -- built from dmc_b200.training's blocks and convolutions
     (training.reference_patched + adopt) against the stock class (oracle/_ref, unmodified) in torch eager.  ms per step,
     CUDA events around `n` steps after two warm-up steps."""
     import torch.nn.functional as F
@@ -352,7 +352,7 @@ def training_step(dev, x_frames, n=3):
             return e0.elapsed_time(e1) / n, float(loss.detach())
 
         lib = D._capi.load()
-        # the engine's blocks are fp32-grade either way; what torch still runs between them (k x k convolutions, ...) is
+        # the engine's blocks and convolutions are fp32-grade either way; the few ops torch still runs between them are
         # timed once at the parity-grade setting (TF32 off) and once at the trainer's default (TF32)
         l0 = lib.dmc_kernel_launches()
         for name, tf32, prec in (("dmc_b200_blocks_rest_fp32_tf32_off", False, "highest"),

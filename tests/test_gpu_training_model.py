@@ -2,7 +2,8 @@
 §8f rank 2).
 
 oracle/_ref holds the unmodified reference modules.  The same class is built twice -- stock, and inside
-`training.reference_patched` (DepthConvBlock, AdaptiveQuant from the engine; likelihood through `training.adopt`) --,
+`training.reference_patched` (DepthConvBlock, AdaptiveQuant and the dense nn.Conv2d layers from the engine; likelihood
+through `training.adopt`) --,
 given the same parameters, the same inputs and the same generator state for the noise quantiser, and stepped through the
 trainer's loss (trainer_seg_video_model.py:904-934: bpp_y + bpp_z + lambda * mse) in train mode, fp32 with TF32 off.
 Compared: loss terms and the gradient of EVERY parameter.  The STE rounding makes the forward discontinuous: an
@@ -91,6 +92,7 @@ def test_reference_model_trains_on_engine_blocks(variant, engine_likelihood):
     if engine_likelihood:
         T.adopt(ours, formula=0 if variant == "old" else 1)
     assert any(isinstance(m, T.DepthConvBlock) for m in ours.modules())
+    assert any(isinstance(m, T.Conv2d) for m in ours.modules())
     assert not any(isinstance(m, T.DepthConvBlock) for m in stock.modules())
     ours.load_state_dict(stock.state_dict())            # same names, same shapes
 
