@@ -472,16 +472,16 @@ class reference_patched:
 
         import src.layers.layers as L, src.refactor.common_model as CM, src.refactor.seg_video_model as SV
         with dmc_b200.training.reference_patched(L, CM, SV):
-            p_frame_model = SV.DMC(DMCConfig())          # DepthConvBlock / AdaptiveQuant are now the engine's
+            p_frame_model = SV.DMC(DMCConfig())          # DepthConvBlock / AdaptiveQuant / nn.Conv2d are now the engine's
         dmc_b200.training.adopt(p_frame_model, formula=1)   # + the likelihood with its native backward
         p_frame_model.load_state_dict(checkpoint)        # parameter names and shapes are the reference's
 
     Every name bound by `from ..layers.layers import DepthConvBlock` is a separate module attribute, so each module that
     constructs blocks has to be listed (layers.py itself for ResidualBlockWithStride2 / ResidualBlockUpsample)."""
 
-    def __init__(self, *modules, conv1x1=True):
+    def __init__(self, *modules, convs=True):
         self.modules = modules
-        self.conv1x1 = conv1x1          # also route the models' plain 1x1 nn.Conv2d layers through the engine (`Conv2d`)
+        self.convs = convs              # also build the models' nn.Conv2d layers as `Conv2d` (dense 1x1 / k x k on the engine)
         self.saved = []
 
     def __enter__(self):
@@ -491,7 +491,7 @@ class reference_patched:
                 if hasattr(m, name):
                     self.saved.append((m, name, getattr(m, name)))
                     setattr(m, name, repl)
-            if self.conv1x1 and getattr(m, "nn", None) is nn:
+            if self.convs and getattr(m, "nn", None) is nn:
                 self.saved.append((m, "nn", nn))
                 setattr(m, "nn", _NNProxy())
         return self
